@@ -1,0 +1,213 @@
+/*
+ * giraffe_b200.h — C ABI of libgiraffe_b200.so, the B200-native replacement for the
+ * short-read `vg giraffe` hot path (minimizer lookup -> seed clustering -> gapless
+ * extension -> X-drop tail alignment -> MAPQ).
+ *
+ * Plain C: pointers and sizes only.  No torch / C++ types cross this boundary.
+ * Every entry point cites the reference seam it replaces (paths relative to the vg tree,
+ * commit fd49b9a9).  Errors are integer status codes (no exceptions cross the ABI) plus a
+ * per-item status byte where a batch can partially fail.
+ *
+ * Ownership: the caller owns every input/output buffer; the library owns device state
+ * behind the opaque handles.  Threading: one gb_device handle per GPU; calls on a handle
+ * are serialised on that handle's CUDA stream.
+ */
+#ifndef GIRAFFE_B200_H
+#define GIRAFFE_B200_H
+
+#include <stdint.h>
+#include <stddef.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* ------------------------------------------------------------------------------------
+ * Status codes
+ * ---------------------------------------------------------------------------------- */
+#define GB_OK                 0
+#define GB_ERR_ARG           -1   /* bad argument (null pointer, inconsistent sizes)        */
+#define GB_ERR_CUDA          -2   /* CUDA runtime error; see gb_last_error()                */
+#define GB_ERR_NO_DEVICE     -3   /* no CUDA device: the product path has NO CPU fallback   */
+#define GB_ERR_CAPACITY      -4   /* an output capacity given by the caller was too small   */
+#define GB_ERR_FORMAT        -5   /* flat index failed validation                           */
+
+/* per-item status byte */
+#define GB_ITEM_OK            0
+#define GB_ITEM_QUEUE_FULL    1   /* best-first frontier exceeded the per-warp workspace    */
+#define GB_ITEM_OUT_FULL      2   /* more extensions / path nodes / mismatches than capacity*/
+#define GB_ITEM_DP_REFUSED    3   /* tail DP refused (cells > max_dozeu_cells), softclipped */
+
+/* ------------------------------------------------------------------------------------
+ * Flat ("GBZ-flat") index: what GBZ + .min + distance payload become in HBM.
+ *
+ * Oriented node handle = GBWT node number  v = 2*id + is_reverse   (gbwt::Node::encode;
+ * used by vg at gbwt_extender.hpp:159-162).  ids are 1..max_id, so v in [2, n_nodes).
+ * Both orientations of every node sequence are stored explicitly, 1 byte per base
+ * (ASCII upper-case ACGTN), so a strand walk never complements on the fly.
+ * ---------------------------------------------------------------------------------- */
+
+/* 16-byte node record, one per oriented node (vg: GBWTGraph::get_sequence_view /
+ * get_length / CachedGBWTGraph record lookup, gbwt_extender.cpp:582,616,654). */
+typedef struct gb_node_rec {
+    uint32_t seq_off;   /* byte offset of this orientation's sequence in gb_flat_index.seq */
+    uint32_t rec_off;   /* word offset of the GBWT record in gb_flat_index.gbwt            */
+    uint32_t len;       /* node length in bp (<= 1024)                                     */
+    uint32_t size;      /* number of haplotype visits (GBWT record size); 0 = no record    */
+} gb_node_rec;
+
+/* GBWT record blob at gbwt[rec_off]:
+ *   word 0: n_edges      word 1: n_runs
+ *   n_edges x { to (oriented node, 0 = endmarker), offset (start of our visits in to's record) }
+ *   n_runs  x { (run_len << 10) | outrank }          outrank < 1024, run_len < 2^22
+ * Edges are sorted by `to`.  LF(i, r) = edge[r].offset + |{ j < i : body[j] == r }|.
+ * (restates jltsiren/gbwt @ c2e0199 CompressedRecord; absent from /root/reference) */
+
+/* Distance payload (16 B) — the zipcode-equivalent for "chain of slots" graphs
+ * (vg: ZipCode::payload_type, zip_code.hpp:74-75; consumed by the clusterer).
+ * A graph is a series composition of slots; every node lies in exactly one slot on one
+ * allele (allele 0xFFFF = the slot is a single backbone node).
+ *   x_in  = min distance from the chain start to the first base of the node
+ *   x_out = (min chain coordinate of the slot end) - (min distance from node end to slot end)
+ * For nodes u before v in different slots:  d(end of u -> start of v) = x_in[v] - x_out[u].
+ * In the same slot, v is reachable from u only on the same allele. */
+typedef struct gb_dist_payload {
+    uint32_t x_in;
+    uint32_t x_out;
+    uint32_t slot;
+    uint16_t allele;
+    uint16_t component;
+} gb_dist_payload;
+
+/* Minimizer hash-table cell (16 B): open addressing, linear probing, capacity power of 2.
+ * key = 2-bit packed k-mer (A0 C1 G2 T3, first base most significant); GB_NO_KEY = empty.
+ * (restates gbwtgraph @ e27bc43 MinimizerIndex; call sites minimizer_mapper.cpp:3930-3933) */
+#define GB_NO_KEY 0xFFFFFFFFFFFFFFFFull
+typedef struct gb_min_cell {
+    uint64_t key;
+    uint32_t hit_off;   /* first hit in gb_flat_index.hits */
+    uint32_t hit_cnt;
+} gb_min_cell;
+
+/* One located minimizer occurrence (24 B): packed position + payload
+ * (vg: MinimizerIndex::get_value, minimizer_mapper.cpp:4458-4473).
+ * pos = (v << 10) | offset, v = oriented node of the k-mer's first base in the k-mer's
+ * own orientation (gbwtgraph Position::encode). */
+typedef struct gb_hit {
+    uint64_t pos;
+    gb_dist_payload payload;
+} gb_hit;
+
+typedef struct gb_flat_index {
+    uint32_t n_nodes;                /* number of oriented-node slots = 2*(max_id+1)        */
+    uint32_t k, w;                   /* minimizer parameters (vg default 29 / 11)           */
+    uint32_t n_paths;                /* haplotype paths (each inserted in both orientations)*/
+    const gb_node_rec* nodes;        /* [n_nodes]                                           */
+    const uint8_t* seq;  uint64_t seq_bytes;     /* padded with >= 16 zero bytes           */
+    const uint32_t* gbwt; uint64_t gbwt_words;
+    const gb_dist_payload* dist;     /* [n_nodes/2], indexed by node id                     */
+    const gb_min_cell* table; uint64_t table_cells;  /* power of two                       */
+    const gb_hit* hits;   uint64_t n_hits;
+} gb_flat_index;
+
+/* ------------------------------------------------------------------------------------
+ * Host-side index construction (replaces, for synthetic inputs, what `vg autoindex`
+ * produces: index_registry.cpp:100-119, gbwtgraph_helper.cpp:511-630, and
+ * get_gbwt() gbwt_helper.cpp:702-719 for the unit-test graphs).
+ * ---------------------------------------------------------------------------------- */
+typedef struct gb_host_index gb_host_index;
+
+/* node i (1-based id) has forward sequence node_seq[node_off[i-1] .. node_off[i]).
+ * path p is path_nodes[path_off[p] .. path_off[p+1]) in GBWT node encoding.
+ * dist may be NULL (payload zero, single slot chain not available -> clustering by
+ * payload is then undefined; the extension / alignment stages do not need it). */
+int gb_index_build(uint32_t n_node_ids, const uint8_t* node_seq, const uint64_t* node_off,
+                   uint32_t n_paths, const uint32_t* path_nodes, const uint64_t* path_off,
+                   const gb_dist_payload* dist, uint32_t k, uint32_t w,
+                   gb_host_index** out);
+void gb_index_free(gb_host_index* ix);
+/* Borrowed view; valid until gb_index_free. */
+int gb_index_view(const gb_host_index* ix, gb_flat_index* out);
+
+/* ------------------------------------------------------------------------------------
+ * Device handle
+ * ---------------------------------------------------------------------------------- */
+typedef struct gb_device gb_device;
+
+/* Copies the flat index into HBM of CUDA device `device_ordinal`.
+ * Fails with GB_ERR_NO_DEVICE when there is no GPU (no CPU fallback exists). */
+int gb_device_create(const gb_flat_index* ix, int device_ordinal, gb_device** out);
+void gb_device_destroy(gb_device* dev);
+const char* gb_last_error(void);
+
+/* Scoring (vg: MinimizerMapper::set_alignment_scores minimizer_mapper.cpp:77 ->
+ * Aligner ctor aligner.cpp:1417; defaults alignment_scorer.hpp:18-28: 1/4/6/1/5). */
+typedef struct gb_scores {
+    int8_t match, mismatch, gap_open, gap_extend, full_length_bonus;
+} gb_scores;
+int gb_set_scores(gb_device* dev, const gb_scores* s);
+
+/* ------------------------------------------------------------------------------------
+ * B2: GaplessExtender::extend, batched
+ *   vector<GaplessExtension> GaplessExtender::extend(cluster_type&, std::string sequence,
+ *       const CachedGBWTGraph*, size_t max_mismatches = 4, double overlap_threshold = 0.8,
+ *       bool trim = true) const                     gbwt_extender.hpp:205, .cpp:533-737
+ * One work item = one (read, cluster) call of the reference.
+ * ---------------------------------------------------------------------------------- */
+typedef struct gb_seed {          /* GaplessExtension::seed_type, gbwt_extender.hpp:32    */
+    uint32_t node;                /* oriented node v                                        */
+    int32_t  diag;                /* read_offset - node_offset                              */
+} gb_seed;
+
+#define GB_EXT_LEFT_FULL   1u
+#define GB_EXT_RIGHT_FULL  2u
+
+typedef struct gb_extension {     /* GaplessExtension, gbwt_extender.hpp:30-109             */
+    uint32_t path_off, path_len;  /* into the path pool (oriented nodes)                    */
+    uint32_t mism_off, mism_len;  /* into the mismatch pool (read offsets, ascending)       */
+    uint32_t offset;              /* offset in path[0]                                      */
+    uint32_t read_lo, read_hi;    /* read_interval                                          */
+    int32_t  score;
+    uint32_t flags;               /* GB_EXT_LEFT_FULL | GB_EXT_RIGHT_FULL                   */
+    uint32_t fwd_node, fwd_lo, fwd_hi;   /* gbwt::BidirectionalState forward  (closed range)*/
+    uint32_t bwd_node, bwd_lo, bwd_hi;   /*                           backward              */
+    uint32_t mismatches;          /* internal_score                                         */
+} gb_extension;                   /* 64 bytes                                               */
+
+typedef struct gb_extend_params {
+    uint32_t max_mismatches;      /* reference default 4  (GaplessExtender::MAX_MISMATCHES) */
+    double   overlap_threshold;   /* reference default 0.8                                  */
+    uint32_t trim;                /* reference default 1                                    */
+    uint32_t max_ext_per_item;    /* output capacity per work item                          */
+    uint32_t path_cap_per_item;   /* path-pool capacity per work item (nodes)               */
+    uint32_t mism_cap_per_item;   /* mismatch-pool capacity per work item                   */
+} gb_extend_params;
+
+/* reads: concatenated read bytes (ASCII); read_off[n_reads+1].
+ * item_read[n_items]: which read each work item extends.
+ * seeds / seed_off[n_items+1]: the cluster of each item (duplicates allowed; they collapse,
+ * as in the reference's hash set).
+ * Outputs (host): ext_count[n_items], status[n_items],
+ *   ext[n_items * max_ext_per_item], path_pool[n_items * path_cap_per_item],
+ *   mism_pool[n_items * mism_cap_per_item]; gb_extension.path_off / mism_off are absolute
+ *   indices into those pools.
+ * Canonical order (the reference iterates an unordered set, gbwt_extender.cpp:550): seeds
+ * are processed in ascending (node, diag) order and ties in the full-length sort
+ * (gbwt_extender.cpp:302) keep that order (stable). */
+int gb_extend_batch(gb_device* dev, const gb_extend_params* p,
+                    uint32_t n_reads, const uint8_t* reads, const uint64_t* read_off,
+                    uint32_t n_items, const uint32_t* item_read,
+                    const gb_seed* seeds, const uint64_t* seed_off,
+                    uint32_t* ext_count, uint8_t* status,
+                    gb_extension* ext, uint32_t* path_pool, uint32_t* mism_pool);
+
+/* Kernel-only timing of the last gb_*_batch call on this handle, milliseconds
+ * (CUDA events on the handle's stream around the kernels, copies excluded). */
+float gb_last_kernel_ms(const gb_device* dev);
+/* Number of kernels this library launched on the handle since creation. */
+uint64_t gb_launch_count(const gb_device* dev);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* GIRAFFE_B200_H */

@@ -1,0 +1,35 @@
+/* ORACLE — TEST INFRASTRUCTURE ONLY.
+ * C entry points of liboracle.so: the CPU restatement of the reference algorithms
+ * (vg @ fd49b9a9) that the CUDA path is checked against.  Only tests/,
+ * __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference leg may load it.
+ * The product (vg_b200/, libgiraffe_b200.so) never includes or links this.
+ */
+#ifndef GB_ORACLE_H
+#define GB_ORACLE_H
+#include "../include/giraffe_b200.h"
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* GaplessExtender::extend (gbwt_extender.cpp:533-737).  Returns the number of extensions,
+ * or -1 when an output capacity is too small.  path_off / mism_off are relative to the
+ * pools passed in. */
+int oracle_extend(const gb_flat_index* ix, const gb_scores* scores,
+                  const uint8_t* read, uint32_t read_len,
+                  const gb_seed* seeds, uint32_t n_seeds,
+                  uint32_t max_mismatches, double overlap_threshold, int trim,
+                  gb_extension* ext_out, uint32_t max_ext,
+                  uint32_t* path_pool, uint32_t path_cap,
+                  uint32_t* mism_pool, uint32_t mism_cap);
+
+/* Haplotype-consistency primitives, exposed so tests can cross-check the flat GBWT
+ * against brute-force path scanning.  state = {fwd_node,fwd_lo,fwd_hi,bwd_node,bwd_lo,bwd_hi}
+ * (closed ranges as int64).  Returns number of successor states written (each 6 int64). */
+int oracle_bd_state(const gb_flat_index* ix, uint32_t node, int64_t* state6);
+int oracle_follow_paths(const gb_flat_index* ix, const int64_t* state6, int backward,
+                        int64_t* out_states, int max_out);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

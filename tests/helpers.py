@@ -1,0 +1,145 @@
+"""Shared test plumbing: the oracle's ctypes bindings and converters.
+
+The oracle (oracle/liboracle.so) is TEST INFRASTRUCTURE: it is loaded here, by
+__graft_entry__.smoke() and by bench.py's CPU legs only.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import json
+from pathlib import Path
+
+import numpy as np
+
+from vg_b200 import capi
+
+ROOT = Path(__file__).resolve().parent.parent
+GOLDEN = ROOT / "tests" / "golden"
+
+_oracle = None
+
+
+def oracle_lib() -> C.CDLL:
+    global _oracle
+    if _oracle is None:
+        path = ROOT / "oracle" / "liboracle.so"
+        if not path.exists():
+            from vg_b200 import build
+            build.build_oracle()
+        lib = C.CDLL(str(path))
+        vp, u32 = C.c_void_p, C.c_uint32
+        lib.oracle_extend.argtypes = [C.POINTER(capi.FlatIndex), C.POINTER(capi.Scores), vp, u32, vp, u32, u32,
+                                      C.c_double, C.c_int, vp, u32, vp, u32, vp, u32]
+        lib.oracle_extend.restype = C.c_int
+        lib.oracle_bd_state.argtypes = [C.POINTER(capi.FlatIndex), u32, vp]
+        lib.oracle_bd_state.restype = C.c_int
+        lib.oracle_follow_paths.argtypes = [C.POINTER(capi.FlatIndex), vp, C.c_int, vp, C.c_int]
+        lib.oracle_follow_paths.restype = C.c_int
+        _oracle = lib
+    return _oracle
+
+
+def enc(node_id: int, rev: bool) -> int:
+    """gbwt::Node::encode."""
+    return 2 * node_id + (1 if rev else 0)
+
+
+def oracle_extend(index: capi.HostIndex, read, seeds, max_mismatches=4, overlap_threshold=0.8, trim=True,
+                  scores=None, max_ext=64, path_cap=2048, mism_cap=1024):
+    """seeds: iterable of (node, diag).  Returns list of dict extensions (paths/mismatches expanded)."""
+    lib = oracle_lib()
+    scores = scores or capi.DEFAULT_SCORES
+    rb = read.encode() if isinstance(read, str) else bytes(read)
+    rbuf = np.frombuffer(rb + b"\0", dtype=np.uint8).copy()
+    sd = np.zeros(max(1, len(seeds)), dtype=capi.seed_dt)
+    for i, (node, diag) in enumerate(seeds):
+        sd[i] = (node, diag)
+    ext = np.zeros(max_ext, dtype=capi.extension_dt)
+    pp = np.zeros(path_cap, dtype=np.uint32)
+    mp = np.zeros(mism_cap, dtype=np.uint32)
+    n = lib.oracle_extend(C.byref(index.view), C.byref(scores), capi.ptr(rbuf), len(rb), capi.ptr(sd), len(seeds),
+                          max_mismatches, overlap_threshold, 1 if trim else 0, capi.ptr(ext), max_ext,
+                          capi.ptr(pp), path_cap, capi.ptr(mp), mism_cap)
+    assert n >= 0, "oracle output capacity too small"
+    return [expand_extension(ext[i], pp, mp) for i in range(n)]
+
+
+def expand_extension(e, path_pool, mism_pool) -> dict:
+    return {
+        "path": [int(x) for x in path_pool[int(e["path_off"]): int(e["path_off"]) + int(e["path_len"])]],
+        "mismatches": [int(x) for x in mism_pool[int(e["mism_off"]): int(e["mism_off"]) + int(e["mism_len"])]],
+        "offset": int(e["offset"]), "read_lo": int(e["read_lo"]), "read_hi": int(e["read_hi"]),
+        "score": int(e["score"]), "left_full": bool(e["flags"] & 1), "right_full": bool(e["flags"] & 2),
+        "state": tuple(int(e[f]) for f in ("fwd_node", "fwd_lo", "fwd_hi", "bwd_node", "bwd_lo", "bwd_hi")),
+    }
+
+
+def gpu_extensions(ext_count, status, ext, path_pool, mism_pool, max_ext):
+    """Expand gb_extend_batch outputs into per-item lists of dict extensions."""
+    out = []
+    for i in range(len(ext_count)):
+        assert status[i] == capi.GB_ITEM_OK, f"item {i} status {status[i]}"
+        out.append([expand_extension(ext[i * max_ext + j], path_pool, mism_pool) for j in range(int(ext_count[i]))])
+    return out
+
+
+def extension_to_mappings(e: dict, node_len, read: str):
+    """GaplessExtension::to_path (gbwt_extender.cpp:119-156) as [(node, offset, [(from,to,seq)...])]."""
+    res = []
+    mm = list(e["mismatches"])
+    mi = 0
+    read_offset, node_offset = e["read_lo"], e["offset"]
+    for h in e["path"]:
+        limit = min(read_offset + node_len(h) - node_offset, e["read_hi"])
+        edits = []
+        while mi < len(mm) and mm[mi] < limit:
+            if read_offset < mm[mi]:
+                edits.append((mm[mi] - read_offset, mm[mi] - read_offset, ""))
+            edits.append((1, 1, read[mm[mi]]))
+            read_offset = mm[mi] + 1
+            mi += 1
+        if read_offset < limit:
+            edits.append((limit - read_offset, limit - read_offset, ""))
+            read_offset = limit
+        res.append((h, node_offset, edits))
+        node_offset = 0
+    return res
+
+
+def parse_edit_string(s: str):
+    """The reference unit tests' edit syntax (src/unittest/gbwt_extender.cpp:454-496)."""
+    edits = []
+    i = 0
+    while i < len(s):
+        c = s[i]
+        if "1" <= c <= "9":
+            edits.append((int(c), int(c), ""))
+        elif c == "-":
+            i += 1
+            edits.append((int(s[i]), 0, ""))
+        elif c == "+":
+            i += 1
+            n = int(s[i])
+            edits.append((0, n, s[i + 1: i + 1 + n]))
+            i += n
+        else:
+            edits.append((1, 1, c))
+        i += 1
+    return edits
+
+
+def golden_graph_index(spec, k=29, w=11) -> capi.HostIndex:
+    ids = sorted(int(i) for i in spec["nodes"])
+    assert ids == list(range(1, len(ids) + 1))
+    seqs = [spec["nodes"][str(i)] for i in ids]
+    paths = [[enc(n, r) for n, r in thread] for thread in spec["threads"]]
+    return capi.HostIndex(seqs, paths, None, k=k, w=w)
+
+
+def to_seed(node_id, rev, offset, read_offset):
+    """GaplessExtender::to_seed (gbwt_extender.hpp:159-162)."""
+    return (enc(node_id, rev), int(read_offset) - int(offset))
+
+
+def load_golden(name):
+    return json.loads((GOLDEN / name).read_text())

@@ -1,0 +1,81 @@
+"""Build libgiraffe_b200.so (sm_100a CUDA kernels + C-ABI + host index builder) in-tree.
+
+The shared object is git-ignored but travels to the GPU box with the gpurun snapshot.
+"""
+from __future__ import annotations
+
+import hashlib
+import os
+import shutil
+import subprocess
+import sys
+from pathlib import Path
+
+ROOT = Path(__file__).resolve().parent.parent
+CSRC = ROOT / "vg_b200" / "csrc"
+LIB = ROOT / "vg_b200" / "libgiraffe_b200.so"
+STAMP = ROOT / "vg_b200" / ".build_stamp"
+
+NVCC_FLAGS = [
+    "-gencode", "arch=compute_100a,code=sm_100a",
+    "-lineinfo", "-O3", "-std=c++17",
+    "-Xcompiler", "-fPIC,-O3,-Wall,-Wno-sign-compare,-Wno-unused-function",
+    "--expt-relaxed-constexpr",
+    "-cudart", "static",
+]
+
+
+def _nvcc() -> str:
+    for cand in (shutil.which("nvcc"), "/usr/local/cuda/bin/nvcc"):
+        if cand and os.path.exists(cand):
+            return cand
+    raise RuntimeError("nvcc not found")
+
+
+def _sources():
+    return sorted(list(CSRC.glob("*.cu")) + list(CSRC.glob("*.cpp")))
+
+
+def _digest() -> str:
+    h = hashlib.sha256()
+    for p in sorted(list(CSRC.glob("*")) + [ROOT / "include" / "giraffe_b200.h", Path(__file__)]):
+        if p.is_file():
+            h.update(p.name.encode())
+            h.update(p.read_bytes())
+    return h.hexdigest()
+
+
+def build(force: bool = False, verbose: bool = False) -> Path:
+    digest = _digest()
+    if not force and LIB.exists() and STAMP.exists() and STAMP.read_text() == digest:
+        return LIB
+    cmd = [_nvcc(), *NVCC_FLAGS, "-shared", "-o", str(LIB), "-I", str(ROOT / "include"), "-I", str(CSRC)]
+    if os.path.exists("/usr/bin/g++"):
+        cmd += ["-ccbin", "/usr/bin/g++"]
+    if verbose:
+        cmd += ["-Xptxas", "-v"]
+    cmd += [str(s) for s in _sources()]
+    res = subprocess.run(cmd, capture_output=True, text=True)
+    if res.returncode != 0:
+        sys.stderr.write(res.stdout + res.stderr)
+        raise RuntimeError("nvcc failed")
+    if verbose:
+        sys.stderr.write(res.stdout + res.stderr)
+    STAMP.write_text(digest)
+    return LIB
+
+
+def build_oracle(arch: str = "") -> Path:
+    """Compile oracle/liboracle.so (test infrastructure; never loaded by the product)."""
+    odir = ROOT / "oracle"
+    env = dict(os.environ)
+    res = subprocess.run(["make", "-C", str(odir), f"ARCH={arch}"], capture_output=True, text=True, env=env)
+    if res.returncode != 0:
+        sys.stderr.write(res.stdout + res.stderr)
+        raise RuntimeError("oracle build failed")
+    return odir / "liboracle.so"
+
+
+if __name__ == "__main__":
+    print(build(force="--force" in sys.argv, verbose="-v" in sys.argv))
+    print(build_oracle())

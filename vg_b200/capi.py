@@ -1,0 +1,240 @@
+"""ctypes bindings for libgiraffe_b200.so (include/giraffe_b200.h).
+
+Python is used here the way torch is used in this repo: plumbing for tests, the benchmark
+and data generation.  The product is the shared library; this module only calls it.
+There is no Python or CPU implementation of any hot-path stage in this package.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from pathlib import Path
+
+import numpy as np
+
+ROOT = Path(__file__).resolve().parent.parent
+LIB_PATH = ROOT / "vg_b200" / "libgiraffe_b200.so"
+
+GB_OK = 0
+GB_ERR_ARG, GB_ERR_CUDA, GB_ERR_NO_DEVICE, GB_ERR_CAPACITY, GB_ERR_FORMAT = -1, -2, -3, -4, -5
+GB_ITEM_OK, GB_ITEM_QUEUE_FULL, GB_ITEM_OUT_FULL, GB_ITEM_DP_REFUSED = 0, 1, 2, 3
+GB_EXT_LEFT_FULL, GB_EXT_RIGHT_FULL = 1, 2
+
+# numpy mirrors of the ABI structs
+node_rec_dt = np.dtype([("seq_off", "<u4"), ("rec_off", "<u4"), ("len", "<u4"), ("size", "<u4")])
+dist_dt = np.dtype([("x_in", "<u4"), ("x_out", "<u4"), ("slot", "<u4"), ("allele", "<u2"), ("component", "<u2")])
+min_cell_dt = np.dtype([("key", "<u8"), ("hit_off", "<u4"), ("hit_cnt", "<u4")])
+hit_dt = np.dtype([("pos", "<u8"), ("payload", dist_dt)])
+seed_dt = np.dtype([("node", "<u4"), ("diag", "<i4")])
+extension_dt = np.dtype([
+    ("path_off", "<u4"), ("path_len", "<u4"), ("mism_off", "<u4"), ("mism_len", "<u4"),
+    ("offset", "<u4"), ("read_lo", "<u4"), ("read_hi", "<u4"), ("score", "<i4"), ("flags", "<u4"),
+    ("fwd_node", "<u4"), ("fwd_lo", "<u4"), ("fwd_hi", "<u4"),
+    ("bwd_node", "<u4"), ("bwd_lo", "<u4"), ("bwd_hi", "<u4"), ("mismatches", "<u4"),
+])
+assert node_rec_dt.itemsize == 16 and dist_dt.itemsize == 16 and min_cell_dt.itemsize == 16
+assert hit_dt.itemsize == 24 and seed_dt.itemsize == 8 and extension_dt.itemsize == 64
+
+
+class FlatIndex(C.Structure):
+    _fields_ = [
+        ("n_nodes", C.c_uint32), ("k", C.c_uint32), ("w", C.c_uint32), ("n_paths", C.c_uint32),
+        ("nodes", C.c_void_p),
+        ("seq", C.c_void_p), ("seq_bytes", C.c_uint64),
+        ("gbwt", C.c_void_p), ("gbwt_words", C.c_uint64),
+        ("dist", C.c_void_p),
+        ("table", C.c_void_p), ("table_cells", C.c_uint64),
+        ("hits", C.c_void_p), ("n_hits", C.c_uint64),
+    ]
+
+
+class Scores(C.Structure):
+    _fields_ = [("match", C.c_int8), ("mismatch", C.c_int8), ("gap_open", C.c_int8),
+                ("gap_extend", C.c_int8), ("full_length_bonus", C.c_int8)]
+
+
+class ExtendParams(C.Structure):
+    _fields_ = [("max_mismatches", C.c_uint32), ("overlap_threshold", C.c_double), ("trim", C.c_uint32),
+                ("max_ext_per_item", C.c_uint32), ("path_cap_per_item", C.c_uint32),
+                ("mism_cap_per_item", C.c_uint32)]
+
+
+DEFAULT_SCORES = Scores(1, 4, 6, 1, 5)
+
+_lib = None
+
+
+def load_library() -> C.CDLL:
+    """Load libgiraffe_b200.so; raises if it has not been built (no fallback)."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not LIB_PATH.exists():
+        raise RuntimeError(f"{LIB_PATH} is missing: run `python -m vg_b200.build` (there is no fallback path)")
+    lib = C.CDLL(str(LIB_PATH))
+    vp, u32, u64 = C.c_void_p, C.c_uint32, C.c_uint64
+    lib.gb_index_build.argtypes = [u32, vp, vp, u32, vp, vp, vp, u32, u32, C.POINTER(vp)]
+    lib.gb_index_build.restype = C.c_int
+    lib.gb_index_free.argtypes = [vp]
+    lib.gb_index_free.restype = None
+    lib.gb_index_view.argtypes = [vp, C.POINTER(FlatIndex)]
+    lib.gb_index_view.restype = C.c_int
+    lib.gb_device_create.argtypes = [C.POINTER(FlatIndex), C.c_int, C.POINTER(vp)]
+    lib.gb_device_create.restype = C.c_int
+    lib.gb_device_destroy.argtypes = [vp]
+    lib.gb_device_destroy.restype = None
+    lib.gb_last_error.argtypes = []
+    lib.gb_last_error.restype = C.c_char_p
+    lib.gb_set_scores.argtypes = [vp, C.POINTER(Scores)]
+    lib.gb_set_scores.restype = C.c_int
+    lib.gb_extend_batch.argtypes = [vp, C.POINTER(ExtendParams), u32, vp, vp, u32, vp, vp, vp, vp, vp, vp, vp, vp]
+    lib.gb_extend_batch.restype = C.c_int
+    lib.gb_last_kernel_ms.argtypes = [vp]
+    lib.gb_last_kernel_ms.restype = C.c_float
+    lib.gb_launch_count.argtypes = [vp]
+    lib.gb_launch_count.restype = C.c_uint64
+    _lib = lib
+    return lib
+
+
+def ptr(a: np.ndarray) -> C.c_void_p:
+    return C.c_void_p(a.ctypes.data)
+
+
+class GbError(RuntimeError):
+    def __init__(self, code: int, what: str):
+        msg = load_library().gb_last_error()
+        super().__init__(f"{what} failed with status {code}: {msg.decode() if msg else ''}")
+        self.code = code
+
+
+class HostIndex:
+    """Owns a gb_host_index built by the library from node sequences and haplotype paths."""
+
+    def __init__(self, node_seqs, paths, dist=None, k=29, w=11):
+        lib = load_library()
+        n = len(node_seqs)
+        node_off = np.zeros(n + 1, dtype=np.uint64)
+        node_off[1:] = np.cumsum([len(s) for s in node_seqs])
+        seq = np.frombuffer("".join(node_seqs).encode(), dtype=np.uint8).copy() if n else np.zeros(1, np.uint8)
+        path_off = np.zeros(len(paths) + 1, dtype=np.uint64)
+        path_off[1:] = np.cumsum([len(p) for p in paths])
+        flat = np.concatenate([np.asarray(p, dtype=np.uint32) for p in paths]) if paths else np.zeros(1, np.uint32)
+        flat = np.ascontiguousarray(flat, dtype=np.uint32)
+        dptr = None
+        if dist is not None:
+            dist = np.ascontiguousarray(dist, dtype=dist_dt)
+            assert len(dist) == n + 1, "dist payload is indexed by node id (entry 0 unused)"
+            dptr = ptr(dist)
+        h = C.c_void_p()
+        rc = lib.gb_index_build(n, ptr(seq), ptr(node_off), len(paths), ptr(flat), ptr(path_off), dptr, k, w, C.byref(h))
+        if rc != GB_OK:
+            raise GbError(rc, "gb_index_build")
+        self._h = h
+        self.view = FlatIndex()
+        rc = lib.gb_index_view(h, C.byref(self.view))
+        if rc != GB_OK:
+            raise GbError(rc, "gb_index_view")
+        self.node_seqs = list(node_seqs)
+        self.paths = [list(p) for p in paths]
+        self.k, self.w = k, w
+
+    def array(self, name: str) -> np.ndarray:
+        v = self.view
+        spec = {
+            "nodes": (v.nodes, v.n_nodes, node_rec_dt), "seq": (v.seq, v.seq_bytes, np.uint8),
+            "gbwt": (v.gbwt, v.gbwt_words, np.uint32), "dist": (v.dist, v.n_nodes // 2, dist_dt),
+            "table": (v.table, v.table_cells, min_cell_dt), "hits": (v.hits, v.n_hits, hit_dt),
+        }[name]
+        addr, n, dt = spec
+        dt = np.dtype(dt)
+        if n == 0:
+            return np.zeros(0, dtype=dt)
+        buf = (C.c_uint8 * (n * dt.itemsize)).from_address(addr)
+        return np.frombuffer(buf, dtype=dt)
+
+    def close(self):
+        if getattr(self, "_h", None):
+            load_library().gb_index_free(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+class Device:
+    """gb_device handle on one GPU.  Raises GbError(GB_ERR_NO_DEVICE) when there is no GPU."""
+
+    def __init__(self, index: HostIndex, ordinal: int = 0, scores: Scores | None = None):
+        lib = load_library()
+        h = C.c_void_p()
+        rc = lib.gb_device_create(C.byref(index.view), ordinal, C.byref(h))
+        if rc != GB_OK:
+            raise GbError(rc, "gb_device_create")
+        self._h = h
+        self.index = index
+        if scores is not None:
+            lib.gb_set_scores(h, C.byref(scores))
+
+    @property
+    def handle(self):
+        return self._h
+
+    def kernel_ms(self) -> float:
+        return float(load_library().gb_last_kernel_ms(self._h))
+
+    def launches(self) -> int:
+        return int(load_library().gb_launch_count(self._h))
+
+    def extend_batch(self, reads, items, max_mismatches=4, overlap_threshold=0.8, trim=True,
+                     max_ext=16, path_cap=256, mism_cap=128):
+        """reads: list of bytes/str; items: list of (read_index, [(node, diag), ...]).
+
+        Returns (ext_count, status, ext, path_pool, mism_pool) as numpy arrays."""
+        lib = load_library()
+        enc = [r.encode() if isinstance(r, str) else bytes(r) for r in reads]
+        read_off = np.zeros(len(enc) + 1, dtype=np.uint64)
+        read_off[1:] = np.cumsum([len(r) for r in enc])
+        rbuf = np.frombuffer(b"".join(enc) + b"\0", dtype=np.uint8).copy()
+        n_items = len(items)
+        item_read = np.array([it[0] for it in items], dtype=np.uint32)
+        seed_off = np.zeros(n_items + 1, dtype=np.uint64)
+        seed_off[1:] = np.cumsum([len(it[1]) for it in items])
+        seeds = np.zeros(max(1, int(seed_off[-1])), dtype=seed_dt)
+        j = 0
+        for it in items:
+            for node, diag in it[1]:
+                seeds[j] = (node, diag)
+                j += 1
+        return self.extend_arrays(rbuf, read_off, item_read, seeds, seed_off, max_mismatches, overlap_threshold,
+                                  trim, max_ext, path_cap, mism_cap)
+
+    def extend_arrays(self, rbuf, read_off, item_read, seeds, seed_off, max_mismatches=4, overlap_threshold=0.8,
+                      trim=True, max_ext=16, path_cap=256, mism_cap=128):
+        lib = load_library()
+        n_items = len(item_read)
+        p = ExtendParams(max_mismatches, overlap_threshold, 1 if trim else 0, max_ext, path_cap, mism_cap)
+        ext_count = np.zeros(n_items, dtype=np.uint32)
+        status = np.zeros(n_items, dtype=np.uint8)
+        ext = np.zeros(n_items * max_ext, dtype=extension_dt)
+        path_pool = np.zeros(n_items * path_cap, dtype=np.uint32)
+        mism_pool = np.zeros(n_items * mism_cap, dtype=np.uint32)
+        rc = lib.gb_extend_batch(self._h, C.byref(p), len(read_off) - 1, ptr(rbuf), ptr(read_off), n_items,
+                                 ptr(item_read), ptr(seeds), ptr(seed_off), ptr(ext_count), ptr(status), ptr(ext),
+                                 ptr(path_pool), ptr(mism_pool))
+        if rc != GB_OK:
+            raise GbError(rc, "gb_extend_batch")
+        return ext_count, status, ext, path_pool, mism_pool
+
+    def close(self):
+        if getattr(self, "_h", None):
+            load_library().gb_device_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass

@@ -1,0 +1,230 @@
+// capi.cu — C-ABI entry points of libgiraffe_b200.so (see include/giraffe_b200.h) and the
+// kernels' launch wrappers.  There is no CPU fallback anywhere in this file: without a
+// CUDA device every compute entry point returns GB_ERR_NO_DEVICE.
+#include "giraffe_b200.h"
+#include "device_state.cuh"
+#include "extend.cuh"
+
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+namespace gb {
+
+thread_local std::string g_last_error;
+
+int fail_cuda(cudaError_t e, const char* what) {
+    g_last_error = std::string(what) + ": " + cudaGetErrorString(e);
+    return (e == cudaErrorNoDevice || e == cudaErrorInsufficientDriver) ? GB_ERR_NO_DEVICE : GB_ERR_CUDA;
+}
+
+// ---------------------------------------------------------------------------------------
+// extend kernel: persistent warps pulling work items from a global counter
+// ---------------------------------------------------------------------------------------
+struct ExtendBatch {
+    const uint8_t* reads; const uint64_t* read_off;
+    const uint32_t* item_read;
+    const gb_seed* seeds; const uint64_t* seed_off;
+    uint32_t n_items;
+    uint32_t* ext_count; uint8_t* status;
+    gb_extension* ext; uint32_t* path_pool; uint32_t* mism_pool;
+    uint32_t read_cap;          // bytes of shared memory per warp for the masked read
+    uint32_t* work_counter;
+};
+
+__global__ void __launch_bounds__(EXTEND_WARPS * 32)
+extend_kernel(DevIndex ix, ExtendParams p, ExtendBatch b, ExtendWorkspace ws) {
+    extern __shared__ __align__(16) uint8_t smem[];
+    const int warp_in_block = threadIdx.x >> 5;
+    const int lane = threadIdx.x & 31;
+    const uint32_t gwarp = blockIdx.x * EXTEND_WARPS + warp_in_block;
+    uint8_t* sread = smem + (size_t)warp_in_block * b.read_cap;
+    QEntry* queue = ws.queue + (size_t)gwarp * ws.q_cap;
+    ArenaNode* arena = ws.arena + (size_t)gwarp * ws.a_cap;
+
+    while (true) {
+        uint32_t item = 0;
+        if (lane == 0) item = atomicAdd(b.work_counter, 1u);
+        item = __shfl_sync(FULL, item, 0);
+        if (item >= b.n_items) break;
+
+        const uint32_t r = b.item_read[item];
+        const uint64_t rb = b.read_off[r];
+        const uint32_t read_len = (uint32_t)(b.read_off[r + 1] - rb);
+        uint32_t status = GB_ITEM_OK, n = 0;
+        if (read_len > b.read_cap) {
+            status = GB_ITEM_OUT_FULL;
+        } else {
+            // stage + mask the read (ReadMasker: anything but ACGT becomes 'X')
+            for (uint32_t i = lane; i < read_len; i += 32) {
+                uint8_t c = b.reads[rb + i];
+                if (c != 'A' && c != 'C' && c != 'G' && c != 'T') c = 'X';
+                sread[i] = c;
+            }
+            __syncwarp();
+            const uint64_t sb = b.seed_off[item];
+            const uint32_t n_seeds = (uint32_t)(b.seed_off[item + 1] - sb);
+            n = extend_item(ix, p, sread, read_len, b.seeds + sb, n_seeds,
+                            queue, ws.q_cap, arena, ws.a_cap,
+                            b.ext + (size_t)item * p.max_ext,
+                            b.path_pool + (size_t)item * p.path_cap,
+                            b.mism_pool + (size_t)item * p.mism_cap, &status);
+        }
+        if (lane == 0) { b.ext_count[item] = n; b.status[item] = (uint8_t)status; }
+        __syncwarp();
+    }
+}
+
+} // namespace gb
+
+using namespace gb;
+
+extern "C" const char* gb_last_error(void) { return g_last_error.c_str(); }
+
+extern "C" int gb_device_create(const gb_flat_index* ix, int device_ordinal, gb_device** out) {
+    if (!ix || !out) return GB_ERR_ARG;
+    int ndev = 0;
+    cudaError_t e = cudaGetDeviceCount(&ndev);
+    if (e != cudaSuccess || ndev == 0) {
+        g_last_error = "no CUDA device available (libgiraffe_b200 has no CPU fallback)";
+        return GB_ERR_NO_DEVICE;
+    }
+    if (device_ordinal < 0 || device_ordinal >= ndev) return GB_ERR_ARG;
+    if ((ix->table_cells & (ix->table_cells - 1)) != 0) return GB_ERR_FORMAT;
+    GB_CUDA(cudaSetDevice(device_ordinal));
+    auto* d = new gb_device();
+    d->device = device_ordinal;
+    cudaDeviceProp prop;
+    GB_CUDA(cudaGetDeviceProperties(&prop, device_ordinal));
+    d->n_sms = prop.multiProcessorCount;
+    GB_CUDA(cudaStreamCreateWithFlags(&d->stream, cudaStreamNonBlocking));
+    GB_CUDA(cudaEventCreate(&d->ev0)); GB_CUDA(cudaEventCreate(&d->ev1));
+    int rc;
+    if ((rc = d->nodes.upload(ix->nodes, ix->n_nodes, d->stream))) return rc;
+    if ((rc = d->seq.upload(ix->seq, ix->seq_bytes, d->stream))) return rc;
+    if ((rc = d->gbwt.upload(ix->gbwt, ix->gbwt_words, d->stream))) return rc;
+    if ((rc = d->dist.upload(ix->dist, ix->n_nodes / 2, d->stream))) return rc;
+    if ((rc = d->table.upload(ix->table, ix->table_cells, d->stream))) return rc;
+    if ((rc = d->hits.upload(ix->hits, ix->n_hits ? ix->n_hits : 1, d->stream, ix->n_hits))) return rc;
+    GB_CUDA(cudaStreamSynchronize(d->stream));
+    d->ix.nodes = d->nodes.ptr; d->ix.seq = d->seq.ptr; d->ix.gbwt = d->gbwt.ptr; d->ix.dist = d->dist.ptr;
+    d->ix.table = d->table.ptr; d->ix.hits = d->hits.ptr;
+    d->ix.table_mask = ix->table_cells - 1; d->ix.n_nodes = ix->n_nodes; d->ix.k = ix->k; d->ix.w = ix->w;
+    d->sc = DevScores{1, 4, 6, 1, 5};
+    GB_CUDA(cudaMalloc(&d->work_counter, 64));
+    *out = d;
+    return GB_OK;
+}
+
+extern "C" void gb_device_destroy(gb_device* d) {
+    if (!d) return;
+    cudaSetDevice(d->device);
+    cudaStreamSynchronize(d->stream);
+    d->release_all();
+    cudaFree(d->work_counter);
+    cudaEventDestroy(d->ev0); cudaEventDestroy(d->ev1);
+    cudaStreamDestroy(d->stream);
+    delete d;
+}
+
+extern "C" int gb_set_scores(gb_device* d, const gb_scores* s) {
+    if (!d || !s) return GB_ERR_ARG;
+    d->sc = DevScores{s->match, s->mismatch, s->gap_open, s->gap_extend, s->full_length_bonus};
+    return GB_OK;
+}
+
+extern "C" float gb_last_kernel_ms(const gb_device* d) { return d ? d->last_kernel_ms : 0.f; }
+extern "C" uint64_t gb_launch_count(const gb_device* d) { return d ? d->launches : 0; }
+
+namespace gb {
+
+// Device-resident launch used by both the host-buffer entry point and the mapping pipeline.
+int launch_extend(gb_device* d, const ExtendParams& p, const ExtendBatch& b_in, uint32_t max_read_len) {
+    ExtendBatch b = b_in;
+    b.read_cap = (max_read_len + 15u) & ~15u;
+    if (b.read_cap == 0) b.read_cap = 16;
+    const size_t smem = (size_t)EXTEND_WARPS * b.read_cap;
+    if (smem > 200 * 1024) { g_last_error = "read too long for the extension kernel"; return GB_ERR_ARG; }
+    if (smem > 48 * 1024) GB_CUDA(cudaFuncSetAttribute(extend_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    int blocks_per_sm = 0;
+    GB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocks_per_sm, extend_kernel, EXTEND_WARPS * 32, smem));
+    if (blocks_per_sm < 1) blocks_per_sm = 1;
+    uint32_t grid = (uint32_t)(d->n_sms * blocks_per_sm);
+    const uint32_t needed = (b.n_items + EXTEND_WARPS - 1) / EXTEND_WARPS;
+    if (grid > needed) grid = needed ? needed : 1;
+    const size_t n_warps = (size_t)grid * EXTEND_WARPS;
+    int rc;
+    if ((rc = d->ws_queue.reserve(n_warps * EXTEND_Q_CAP))) return rc;
+    if ((rc = d->ws_arena.reserve(n_warps * EXTEND_A_CAP))) return rc;
+    ExtendWorkspace ws{d->ws_queue.ptr, d->ws_arena.ptr, EXTEND_Q_CAP, EXTEND_A_CAP};
+    b.work_counter = d->work_counter;
+    GB_CUDA(cudaMemsetAsync(d->work_counter, 0, sizeof(uint32_t), d->stream));
+    extend_kernel<<<grid, EXTEND_WARPS * 32, smem, d->stream>>>(d->ix, p, b, ws);
+    d->launches++;
+    GB_CUDA(cudaGetLastError());
+    return GB_OK;
+}
+
+} // namespace gb
+
+extern "C" int gb_extend_batch(gb_device* d, const gb_extend_params* hp,
+                               uint32_t n_reads, const uint8_t* reads, const uint64_t* read_off,
+                               uint32_t n_items, const uint32_t* item_read,
+                               const gb_seed* seeds, const uint64_t* seed_off,
+                               uint32_t* ext_count, uint8_t* status,
+                               gb_extension* ext, uint32_t* path_pool, uint32_t* mism_pool) {
+    if (!d || !hp || !reads || !read_off || !item_read || !seeds || !seed_off || !ext_count || !status || !ext ||
+        !path_pool || !mism_pool) return GB_ERR_ARG;
+    if (hp->max_ext_per_item == 0 || hp->path_cap_per_item == 0 || hp->mism_cap_per_item == 0) return GB_ERR_ARG;
+    if (n_items == 0) return GB_OK;
+    GB_CUDA(cudaSetDevice(d->device));
+    uint32_t max_len = 0;
+    for (uint32_t r = 0; r < n_reads; r++) max_len = std::max<uint32_t>(max_len, (uint32_t)(read_off[r + 1] - read_off[r]));
+    for (uint32_t i = 0; i < n_items; i++) if (item_read[i] >= n_reads) return GB_ERR_ARG;
+    const uint64_t n_seeds = seed_off[n_items];
+
+    DevBuf<uint8_t> d_reads; DevBuf<uint64_t> d_read_off, d_seed_off; DevBuf<uint32_t> d_item_read; DevBuf<gb_seed> d_seeds;
+    DevBuf<uint32_t> d_cnt, d_path, d_mism; DevBuf<uint8_t> d_status; DevBuf<gb_extension> d_ext;
+    int rc;
+    if ((rc = d_reads.upload(reads, read_off[n_reads] ? read_off[n_reads] : 1, d->stream, read_off[n_reads]))) return rc;
+    if ((rc = d_read_off.upload(read_off, n_reads + 1, d->stream))) return rc;
+    if ((rc = d_item_read.upload(item_read, n_items, d->stream))) return rc;
+    if ((rc = d_seeds.upload(seeds, n_seeds ? n_seeds : 1, d->stream, n_seeds))) return rc;
+    if ((rc = d_seed_off.upload(seed_off, n_items + 1, d->stream))) return rc;
+    if ((rc = d_cnt.reserve(n_items))) return rc;
+    if ((rc = d_status.reserve(n_items))) return rc;
+    if ((rc = d_ext.reserve((size_t)n_items * hp->max_ext_per_item))) return rc;
+    if ((rc = d_path.reserve((size_t)n_items * hp->path_cap_per_item))) return rc;
+    if ((rc = d_mism.reserve((size_t)n_items * hp->mism_cap_per_item))) return rc;
+
+    ExtendParams p;
+    p.sc = d->sc; p.max_mismatches = hp->max_mismatches; p.overlap_threshold = hp->overlap_threshold;
+    p.overlap_threshold_unused = 0.f; p.trim = hp->trim;
+    p.max_ext = hp->max_ext_per_item; p.path_cap = hp->path_cap_per_item; p.mism_cap = hp->mism_cap_per_item;
+    ExtendBatch b{};
+    b.reads = d_reads.ptr; b.read_off = d_read_off.ptr; b.item_read = d_item_read.ptr;
+    b.seeds = d_seeds.ptr; b.seed_off = d_seed_off.ptr; b.n_items = n_items;
+    b.ext_count = d_cnt.ptr; b.status = d_status.ptr; b.ext = d_ext.ptr; b.path_pool = d_path.ptr; b.mism_pool = d_mism.ptr;
+
+    GB_CUDA(cudaEventRecord(d->ev0, d->stream));
+    if ((rc = launch_extend(d, p, b, max_len))) return rc;
+    GB_CUDA(cudaEventRecord(d->ev1, d->stream));
+
+    GB_CUDA(cudaMemcpyAsync(ext_count, d_cnt.ptr, sizeof(uint32_t) * n_items, cudaMemcpyDeviceToHost, d->stream));
+    GB_CUDA(cudaMemcpyAsync(status, d_status.ptr, n_items, cudaMemcpyDeviceToHost, d->stream));
+    GB_CUDA(cudaMemcpyAsync(ext, d_ext.ptr, sizeof(gb_extension) * (size_t)n_items * hp->max_ext_per_item, cudaMemcpyDeviceToHost, d->stream));
+    GB_CUDA(cudaMemcpyAsync(path_pool, d_path.ptr, sizeof(uint32_t) * (size_t)n_items * hp->path_cap_per_item, cudaMemcpyDeviceToHost, d->stream));
+    GB_CUDA(cudaMemcpyAsync(mism_pool, d_mism.ptr, sizeof(uint32_t) * (size_t)n_items * hp->mism_cap_per_item, cudaMemcpyDeviceToHost, d->stream));
+    GB_CUDA(cudaStreamSynchronize(d->stream));
+    GB_CUDA(cudaEventElapsedTime(&d->last_kernel_ms, d->ev0, d->ev1));
+    // make pool offsets absolute
+    for (uint32_t i = 0; i < n_items; i++) {
+        for (uint32_t j = 0; j < ext_count[i]; j++) {
+            gb_extension& e = ext[(size_t)i * hp->max_ext_per_item + j];
+            e.path_off += i * hp->path_cap_per_item;
+            e.mism_off += i * hp->mism_cap_per_item;
+        }
+    }
+    return GB_OK;
+}

@@ -1,0 +1,81 @@
+// device_state.cuh — the opaque gb_device handle: HBM-resident index, stream, workspaces.
+#pragma once
+#include "giraffe_b200.h"
+#include "device_index.cuh"
+#include "extend.cuh"
+
+#include <cuda_runtime.h>
+#include <string>
+
+namespace gb {
+
+constexpr int EXTEND_WARPS = 8;           // warps per CTA of the extension kernel
+constexpr uint32_t EXTEND_Q_CAP = 512;    // frontier entries per warp (64 B each)
+constexpr uint32_t EXTEND_A_CAP = 4096;   // path-arena nodes per warp (8 B each)
+
+extern thread_local std::string g_last_error;
+int fail_cuda(cudaError_t e, const char* what);
+
+#define GB_CUDA(call)                                                        \
+    do {                                                                     \
+        cudaError_t _e = (call);                                             \
+        if (_e != cudaSuccess) return ::gb::fail_cuda(_e, #call);            \
+    } while (0)
+
+// Growable device buffer (cudaMalloc on demand, never shrinks).
+template <typename T>
+struct DevBuf {
+    T* ptr = nullptr;
+    size_t cap = 0;
+    DevBuf() = default;
+    DevBuf(const DevBuf&) = delete;
+    DevBuf& operator=(const DevBuf&) = delete;
+    ~DevBuf() { release(); }
+    void release() { if (ptr) cudaFree(ptr); ptr = nullptr; cap = 0; }
+    int reserve(size_t n) {
+        if (n <= cap && ptr) return GB_OK;
+        if (ptr) { cudaFree(ptr); ptr = nullptr; cap = 0; }
+        if (n == 0) n = 1;
+        cudaError_t e = cudaMalloc(&ptr, n * sizeof(T));
+        if (e != cudaSuccess) { ptr = nullptr; return fail_cuda(e, "cudaMalloc"); }
+        cap = n;
+        return GB_OK;
+    }
+    // allocate `n` elements, copy `n_copy` (default n) from host
+    int upload(const T* host, size_t n, cudaStream_t s, size_t n_copy = (size_t)-1) {
+        int rc = reserve(n);
+        if (rc) return rc;
+        if (n_copy == (size_t)-1) n_copy = n;
+        if (n_copy && host) {
+            cudaError_t e = cudaMemcpyAsync(ptr, host, n_copy * sizeof(T), cudaMemcpyHostToDevice, s);
+            if (e != cudaSuccess) return fail_cuda(e, "cudaMemcpyAsync H2D");
+        }
+        return GB_OK;
+    }
+};
+
+} // namespace gb
+
+struct gb_device {
+    int device = 0;
+    int n_sms = 0;
+    cudaStream_t stream = nullptr;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    gb::DevIndex ix{};
+    gb::DevScores sc{1, 4, 6, 1, 5};
+    gb::DevBuf<gb_node_rec> nodes;
+    gb::DevBuf<uint8_t> seq;
+    gb::DevBuf<uint32_t> gbwt;
+    gb::DevBuf<gb_dist_payload> dist;
+    gb::DevBuf<gb_min_cell> table;
+    gb::DevBuf<gb_hit> hits;
+    gb::DevBuf<gb::QEntry> ws_queue;
+    gb::DevBuf<gb::ArenaNode> ws_arena;
+    uint32_t* work_counter = nullptr;
+    float last_kernel_ms = 0.f;
+    uint64_t launches = 0;
+    void release_all() {
+        nodes.release(); seq.release(); gbwt.release(); dist.release(); table.release(); hits.release();
+        ws_queue.release(); ws_arena.release();
+    }
+};

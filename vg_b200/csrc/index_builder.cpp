@@ -1,0 +1,264 @@
+// index_builder.cpp — host-side construction of the flat ("GBZ-flat") index.
+//
+// Builds, from node sequences + haplotype paths:
+//   * both-orientation node sequences, 1 B/base
+//   * a bidirectional GBWT as flat record blobs (each path inserted forward and reverse,
+//     like gbwt::GBWTBuilder::insert(path, true) — vg call site gbwt_helper.cpp:702-719)
+//   * the (k,w)-minimizer hash table over all haplotypes with 16-B distance payloads
+//     (vg: gbwtgraph::index_haplotypes via gbwtgraph_helper.cpp:511-630)
+//
+// This is offline indexing (out of the measured hot path); it exists so the synthetic
+// BASELINE.json configs and the reference's unit-test graphs can be loaded into HBM.
+
+#include "giraffe_b200.h"
+#include "minimizer_common.h"
+
+#include <algorithm>
+#include <cstring>
+#include <numeric>
+#include <string>
+#include <unordered_map>
+#include <vector>
+
+struct gb_host_index {
+    uint32_t n_nodes = 0, k = 0, w = 0, n_paths = 0;
+    std::vector<gb_node_rec> nodes;
+    std::vector<uint8_t> seq;
+    std::vector<uint32_t> gbwt;
+    std::vector<gb_dist_payload> dist;
+    std::vector<gb_min_cell> table;
+    std::vector<gb_hit> hits;
+};
+
+namespace {
+
+inline uint8_t comp(uint8_t c) {
+    switch (c) {
+        case 'A': return 'T'; case 'C': return 'G'; case 'G': return 'C'; case 'T': return 'A';
+        default: return 'N';
+    }
+}
+
+// Order all path visits by their reversed prefix (v_{i-1}, v_{i-2}, ..., v_0, $seq) using
+// prefix doubling; this is the order of visits inside each GBWT record.
+void gbwt_visit_order(const std::vector<std::vector<uint32_t>>& seqs,
+                      std::vector<uint32_t>& rank_out /* per global visit */,
+                      std::vector<uint64_t>& seq_start) {
+    size_t n = 0;
+    seq_start.resize(seqs.size() + 1);
+    for (size_t s = 0; s < seqs.size(); s++) { seq_start[s] = n; n += seqs[s].size(); }
+    seq_start[seqs.size()] = n;
+    std::vector<uint32_t> pos_in_seq(n), seq_of(n);
+    for (size_t s = 0; s < seqs.size(); s++)
+        for (size_t i = 0; i < seqs[s].size(); i++) { pos_in_seq[seq_start[s] + i] = (uint32_t)i; seq_of[seq_start[s] + i] = (uint32_t)s; }
+
+    // Initial key: (own node, predecessor node); visits with no predecessor are unique by seq id.
+    // rank[p] is the rank of the reversed prefix of length h (starting at the predecessor).
+    std::vector<uint64_t> key(n);
+    std::vector<uint32_t> rank(n), tmp(n), order(n);
+    // First element of the key is the predecessor node (0 = endmarker); ties among
+    // endmarker predecessors are broken by sequence id which makes them final.
+    // We use 64-bit keys: (pred_node << 32) | (pred is endmarker ? seq id : 0).
+    for (size_t p = 0; p < n; p++) {
+        uint32_t s = seq_of[p], i = pos_in_seq[p];
+        if (i == 0) key[p] = (uint64_t)s;                         // (0, s)
+        else key[p] = ((uint64_t)seqs[s][i - 1] << 32);
+    }
+    std::iota(order.begin(), order.end(), 0u);
+    std::sort(order.begin(), order.end(), [&](uint32_t a, uint32_t b) { return key[a] < key[b]; });
+    bool all_unique = true;
+    {
+        uint32_t r = 0;
+        for (size_t j = 0; j < n; j++) {
+            if (j > 0 && key[order[j]] != key[order[j - 1]]) r = (uint32_t)j;
+            if (j > 0 && key[order[j]] == key[order[j - 1]]) all_unique = false;
+            rank[order[j]] = r;
+        }
+    }
+    // Doubling: rank_h covers h predecessors; combine with rank_h of the visit h steps back.
+    for (size_t h = 1; !all_unique; h *= 2) {
+        for (size_t p = 0; p < n; p++) {
+            uint32_t i = pos_in_seq[p];
+            // The visit h steps back; if it does not exist the key is already unique.
+            uint64_t second = (i >= h) ? (uint64_t)rank[p - h] + 1 : 0;
+            key[p] = ((uint64_t)rank[p] << 32) | second;
+        }
+        std::sort(order.begin(), order.end(), [&](uint32_t a, uint32_t b) { return key[a] < key[b]; });
+        all_unique = true;
+        uint32_t r = 0;
+        for (size_t j = 0; j < n; j++) {
+            if (j > 0 && key[order[j]] != key[order[j - 1]]) r = (uint32_t)j;
+            else if (j > 0) all_unique = false;
+            tmp[order[j]] = r;
+        }
+        rank.swap(tmp);
+        if (h > n) break;
+    }
+    rank_out = rank;
+}
+
+} // namespace
+
+extern "C" int gb_index_build(uint32_t n_node_ids, const uint8_t* node_seq, const uint64_t* node_off,
+                              uint32_t n_paths, const uint32_t* path_nodes, const uint64_t* path_off,
+                              const gb_dist_payload* dist, uint32_t k, uint32_t w,
+                              gb_host_index** out) {
+    if (!node_seq || !node_off || !out || (n_paths && (!path_nodes || !path_off))) return GB_ERR_ARG;
+    if (k == 0 || k > 31 || w == 0) return GB_ERR_ARG;
+    auto* ix = new gb_host_index();
+    ix->k = k; ix->w = w; ix->n_paths = n_paths;
+    ix->n_nodes = 2 * (n_node_ids + 1);
+    ix->nodes.assign(ix->n_nodes, gb_node_rec{0, 0, 0, 0});
+
+    // --- sequences, both orientations ---
+    uint64_t total = node_off[n_node_ids];
+    ix->seq.reserve(2 * total + 64);
+    for (uint32_t id = 1; id <= n_node_ids; id++) {
+        uint64_t b = node_off[id - 1], e = node_off[id];
+        uint32_t len = (uint32_t)(e - b);
+        if (len == 0 || len > 1024) { delete ix; return GB_ERR_FORMAT; }
+        uint32_t vf = 2 * id, vr = 2 * id + 1;
+        ix->nodes[vf].seq_off = (uint32_t)ix->seq.size(); ix->nodes[vf].len = len;
+        for (uint64_t i = b; i < e; i++) ix->seq.push_back(node_seq[i]);
+        ix->nodes[vr].seq_off = (uint32_t)ix->seq.size(); ix->nodes[vr].len = len;
+        for (uint64_t i = e; i > b; i--) ix->seq.push_back(comp(node_seq[i - 1]));
+    }
+    ix->seq.resize(ix->seq.size() + 64, 0);
+
+    ix->dist.assign(n_node_ids + 1, gb_dist_payload{0, 0, 0, 0xFFFF, 0});
+    if (dist) for (uint32_t id = 1; id <= n_node_ids; id++) ix->dist[id] = dist[id];
+
+    // --- bidirectional GBWT ---
+    std::vector<std::vector<uint32_t>> seqs(2 * (size_t)n_paths);
+    for (uint32_t p = 0; p < n_paths; p++) {
+        uint64_t b = path_off[p], e = path_off[p + 1];
+        auto& f = seqs[2 * p]; auto& r = seqs[2 * p + 1];
+        f.assign(path_nodes + b, path_nodes + e);
+        r.resize(e - b);
+        for (uint64_t i = 0; i < e - b; i++) r[i] = path_nodes[e - 1 - i] ^ 1u;
+        for (uint32_t v : f) if (v < 2 || v >= ix->n_nodes) { delete ix; return GB_ERR_FORMAT; }
+    }
+    std::vector<uint32_t> vrank; std::vector<uint64_t> seq_start;
+    gbwt_visit_order(seqs, vrank, seq_start);
+    size_t nvis = vrank.size();
+    // group visits per node in record order
+    struct Visit { uint32_t node, rank, pred, succ; };
+    std::vector<Visit> visits(nvis);
+    for (size_t s = 0; s < seqs.size(); s++) {
+        for (size_t i = 0; i < seqs[s].size(); i++) {
+            size_t p = seq_start[s] + i;
+            visits[p] = Visit{seqs[s][i], vrank[p], i ? seqs[s][i - 1] : 0u,
+                              i + 1 < seqs[s].size() ? seqs[s][i + 1] : 0u};
+        }
+    }
+    std::sort(visits.begin(), visits.end(), [](const Visit& a, const Visit& b) {
+        if (a.node != b.node) return a.node < b.node;
+        return a.rank < b.rank;
+    });
+    // record start per node
+    std::vector<size_t> rec_begin(ix->n_nodes + 1, 0);
+    for (auto& vis : visits) rec_begin[vis.node + 1]++;
+    for (uint32_t v = 0; v < ix->n_nodes; v++) rec_begin[v + 1] += rec_begin[v];
+
+    ix->gbwt.clear();
+    ix->gbwt.push_back(0); ix->gbwt.push_back(0);   // offset 0 = "no record" sentinel (0 edges, 0 runs)
+    for (uint32_t v = 2; v < ix->n_nodes; v++) {
+        size_t b = rec_begin[v], e = rec_begin[v + 1];
+        ix->nodes[v].size = (uint32_t)(e - b);
+        if (e == b) { ix->nodes[v].rec_off = 0; continue; }
+        // distinct successors, ascending
+        std::vector<uint32_t> succ;
+        for (size_t i = b; i < e; i++) succ.push_back(visits[i].succ);
+        std::sort(succ.begin(), succ.end());
+        succ.erase(std::unique(succ.begin(), succ.end()), succ.end());
+        if (succ.size() >= 1024) { delete ix; return GB_ERR_FORMAT; }
+        if (ix->gbwt.size() & 1) ix->gbwt.push_back(0);   // 8-byte align the edge pairs
+        ix->nodes[v].rec_off = (uint32_t)ix->gbwt.size();
+        ix->gbwt.push_back((uint32_t)succ.size());
+        size_t nruns_at = ix->gbwt.size();
+        ix->gbwt.push_back(0);
+        for (uint32_t wnode : succ) {
+            uint32_t off = 0;
+            if (wnode != 0) {
+                // number of visits in record(w) whose predecessor is smaller than v
+                size_t wb = rec_begin[wnode], we = rec_begin[wnode + 1];
+                // visits in a record are sorted by predecessor first
+                size_t lo = wb, hi = we;
+                while (lo < hi) { size_t mid = (lo + hi) / 2; if (visits[mid].pred < v) lo = mid + 1; else hi = mid; }
+                off = (uint32_t)(lo - wb);
+            }
+            ix->gbwt.push_back(wnode);
+            ix->gbwt.push_back(off);
+        }
+        uint32_t nruns = 0;
+        size_t i = b;
+        while (i < e) {
+            size_t j = i;
+            while (j < e && visits[j].succ == visits[i].succ && (j - i) < ((1u << 22) - 1)) j++;
+            uint32_t outrank = (uint32_t)(std::lower_bound(succ.begin(), succ.end(), visits[i].succ) - succ.begin());
+            ix->gbwt.push_back(((uint32_t)(j - i) << 10) | outrank);
+            nruns++;
+            i = j;
+        }
+        ix->gbwt[nruns_at] = nruns;
+    }
+    ix->gbwt.resize(ix->gbwt.size() + 64, 0);
+
+    // --- minimizer index over forward haplotypes ---
+    struct KP { uint64_t key; uint64_t pos; };
+    std::vector<KP> kps;
+    std::string hap; std::vector<uint32_t> base_node; std::vector<uint32_t> base_off;
+    std::vector<gbmin::Minimizer> mins;
+    for (uint32_t p = 0; p < n_paths; p++) {
+        hap.clear(); base_node.clear(); base_off.clear();
+        for (uint32_t v : seqs[2 * p]) {
+            const gb_node_rec& nr = ix->nodes[v];
+            for (uint32_t o = 0; o < nr.len; o++) {
+                hap.push_back((char)ix->seq[nr.seq_off + o]);
+                base_node.push_back(v); base_off.push_back(o);
+            }
+        }
+        mins.clear();
+        gbmin::minimizers((const uint8_t*)hap.data(), hap.size(), k, w, mins, nullptr);
+        for (const auto& m : mins) {
+            uint32_t v = base_node[m.offset], o = base_off[m.offset];
+            if (m.is_reverse) { o = ix->nodes[v].len - 1 - o; v ^= 1u; }
+            kps.push_back(KP{m.key, ((uint64_t)v << 10) | o});
+        }
+    }
+    std::sort(kps.begin(), kps.end(), [](const KP& a, const KP& b) { return a.key != b.key ? a.key < b.key : a.pos < b.pos; });
+    kps.erase(std::unique(kps.begin(), kps.end(), [](const KP& a, const KP& b) { return a.key == b.key && a.pos == b.pos; }), kps.end());
+    size_t nkeys = 0;
+    for (size_t i = 0; i < kps.size(); i++) if (i == 0 || kps[i].key != kps[i - 1].key) nkeys++;
+    uint64_t cells = 16; while (cells < 2 * nkeys + 1) cells *= 2;
+    ix->table.assign(cells, gb_min_cell{GB_NO_KEY, 0, 0});
+    ix->hits.resize(kps.size());
+    for (size_t i = 0; i < kps.size(); i++) {
+        uint32_t v = (uint32_t)(kps[i].pos >> 10);
+        ix->hits[i].pos = kps[i].pos;
+        ix->hits[i].payload = ix->dist[v >> 1];
+    }
+    for (size_t i = 0; i < kps.size();) {
+        size_t j = i; while (j < kps.size() && kps[j].key == kps[i].key) j++;
+        uint64_t h = gbmin::hash64(kps[i].key) & (cells - 1);
+        while (ix->table[h].key != GB_NO_KEY) h = (h + 1) & (cells - 1);
+        ix->table[h] = gb_min_cell{kps[i].key, (uint32_t)i, (uint32_t)(j - i)};
+        i = j;
+    }
+    *out = ix;
+    return GB_OK;
+}
+
+extern "C" void gb_index_free(gb_host_index* ix) { delete ix; }
+
+extern "C" int gb_index_view(const gb_host_index* ix, gb_flat_index* out) {
+    if (!ix || !out) return GB_ERR_ARG;
+    out->n_nodes = ix->n_nodes; out->k = ix->k; out->w = ix->w; out->n_paths = ix->n_paths;
+    out->nodes = ix->nodes.data();
+    out->seq = ix->seq.data(); out->seq_bytes = ix->seq.size();
+    out->gbwt = ix->gbwt.data(); out->gbwt_words = ix->gbwt.size();
+    out->dist = ix->dist.data();
+    out->table = ix->table.data(); out->table_cells = ix->table.size();
+    out->hits = ix->hits.data(); out->n_hits = ix->hits.size();
+    return GB_OK;
+}
