@@ -201,6 +201,93 @@ int gb_extend_batch(gb_device* dev, const gb_extend_params* p,
                     uint32_t* ext_count, uint8_t* status,
                     gb_extension* ext, uint32_t* path_pool, uint32_t* mism_pool);
 
+/* ------------------------------------------------------------------------------------
+ * B1: MinimizerMapper::map / map_paired, batched
+ *   vector<Alignment> MinimizerMapper::map(Alignment&)           minimizer_mapper.hpp:44-100,
+ *   map_from_extensions                                          minimizer_mapper.cpp:608-1284
+ * Output is the GAM-equivalent record: the fields of vg.proto Alignment / Path / Mapping /
+ * Edit that the reference fills on this path (gbwt_extender.cpp:119-156,
+ * dozeu_interface.cpp:310-336, minimizer_mapper.cpp:1146-1216).
+ * ---------------------------------------------------------------------------------- */
+typedef struct gb_mapping {       /* one Mapping: position + run of edits (8 B)              */
+    uint32_t node;                /* oriented node v = 2*id + is_reverse                     */
+    uint16_t offset;              /* Position.offset                                         */
+    uint16_t n_edits;             /* edits follow each other in the edit pool                */
+} gb_mapping;
+
+/* One Edit (4 B): (length << 4) | (base << 2) | op.
+ * MATCH: from=to=length.  SUB: from=to=1, sequence = base (A0 C1 G2 T3; N is reported as the
+ * read base itself, look it up by query offset).  INS: from=0,to=length (sequence = the read
+ * bases at the current query offset; softclips are insertions at the ends).  DEL: from=length,to=0. */
+#define GB_EDIT_MATCH 0u
+#define GB_EDIT_SUB   1u
+#define GB_EDIT_INS   2u
+#define GB_EDIT_DEL   3u
+
+#define GB_ALN_MAPPED     1u      /* path is non-empty                                       */
+#define GB_ALN_SECONDARY  2u
+#define GB_ALN_PAIRED     4u      /* produced by map_paired                                  */
+#define GB_ALN_RESCUED    8u
+
+typedef struct gb_alignment {     /* 32 B header per output alignment                        */
+    uint32_t read_id;             /* index of the read in the batch                          */
+    int32_t  score;               /* Alignment.score                                         */
+    uint8_t  mapq;                /* Alignment.mapping_quality                               */
+    uint8_t  flags;
+    uint16_t n_mappings;
+    uint32_t mapping_off;         /* into the mapping pool                                   */
+    uint32_t edit_off;            /* into the edit pool                                      */
+    uint32_t n_edits;
+    float    mapq_uncapped;       /* annotation mapq_uncapped (minimizer_mapper.cpp:1173)    */
+    float    mapq_explored_cap;   /* annotation mapq_explored_cap (:1174)                    */
+} gb_alignment;
+
+/* MinimizerMapper settings on this path; defaults = minimizer_mapper.hpp:108-521. */
+typedef struct gb_map_params {
+    uint32_t hit_cap;                    /* 10   */
+    uint32_t hard_hit_cap;               /* 500  */
+    double   minimizer_score_fraction;   /* 0.9  */
+    uint32_t minimizer_coverage_flank;   /* 250  */
+    uint32_t max_unique_min;             /* 500  */
+    uint32_t num_bp_per_min;             /* 1000 */
+    uint32_t distance_limit;             /* 200  */
+    uint32_t min_extensions;             /* 2    */
+    uint32_t max_extensions;             /* 800  */
+    double   cluster_score_threshold;    /* 50   */
+    double   pad_cluster_score_threshold;/* 20   */
+    double   cluster_coverage_threshold; /* 0.3  */
+    double   extension_set_score_threshold; /* 20 */
+    int32_t  extension_score_threshold;  /* 1    */
+    int32_t  min_extension_sets;         /* 2    */
+    int32_t  extension_set_min_score;    /* 20   */
+    uint32_t max_alignments;             /* 8    */
+    uint32_t max_extension_mismatches;   /* 4    */
+    uint32_t max_multimaps;              /* 1 (only 1 is supported)                          */
+    uint32_t max_dozeu_cells;            /* 1.5 * 1024 * 1024                                */
+    uint32_t do_dp;                      /* 1    */
+    /* paired-end (map_paired, minimizer_mapper.cpp:1462) */
+    double   fragment_mean, fragment_stdev;      /* forced distribution (--fragment-mean/-stdev) */
+    double   paired_distance_stdevs;     /* 2.0  */
+    double   paired_rescue_score_limit;  /* 0.9  */
+    double   rescue_subgraph_stdevs;     /* 4.0  */
+    uint32_t max_rescue_attempts;        /* 15   */
+    uint32_t max_fragment_length;        /* 2000 */
+    /* output capacities per read */
+    uint32_t mapping_cap_per_read;
+    uint32_t edit_cap_per_read;
+} gb_map_params;
+
+void gb_map_params_default(gb_map_params* p);
+
+/* Single-end batch.  reads/quals are concatenated bytes addressed by read_off[n_reads+1]
+ * (quals = raw Phred bytes, may be NULL: then the explored-minimizer cap is +inf as in
+ * minimizer_mapper.cpp:2950).  One primary alignment per read (max_multimaps = 1):
+ * aln[n_reads], mappings[n_reads * mapping_cap_per_read], edits[n_reads * edit_cap_per_read],
+ * status[n_reads]. */
+int gb_map_batch(gb_device* dev, const gb_map_params* p,
+                 uint32_t n_reads, const uint8_t* reads, const uint8_t* quals, const uint64_t* read_off,
+                 gb_alignment* aln, gb_mapping* mappings, uint32_t* edits, uint8_t* status);
+
 /* Kernel-only timing of the last gb_*_batch call on this handle, milliseconds
  * (CUDA events on the handle's stream around the kernels, copies excluded). */
 float gb_last_kernel_ms(const gb_device* dev);

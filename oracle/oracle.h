@@ -29,6 +29,26 @@ int oracle_bd_state(const gb_flat_index* ix, uint32_t node, int64_t* state6);
 int oracle_follow_paths(const gb_flat_index* ix, const int64_t* state6, int backward,
                         int64_t* out_states, int max_out);
 
+
+/* MinimizerMapper::map (single-end), minimizer_mapper.cpp:608-1284.  Output layout as
+ * gb_map_batch.  counters_out (13 x uint64, may be NULL): reads, minimizers, seeds, clusters,
+ * extend calls, direct (full-length) alignments, tail DPs, tail DP cells, tail tree nodes,
+ * tail tree bases, path nodes, edits, rescues.  n_threads = OpenMP threads over reads
+ * (the reference's own parallelisation, giraffe_main.cpp:2471). */
+void oracle_map_params_default(gb_map_params* p);
+int oracle_map_batch(const gb_flat_index* ix, const gb_scores* scores, const gb_map_params* p,
+                     uint32_t n_reads, const uint8_t* reads, const uint8_t* quals, const uint64_t* read_off,
+                     gb_alignment* aln, gb_mapping* mappings, uint32_t* edits, uint8_t* status,
+                     int n_threads, uint64_t* counters_out);
+
+/* Pinned X-drop alignment of a query against one haplotype tree (Aligner::align_pinned with
+ * xdrop=true, aligner.cpp:628-686).  Mappings are in TREE space: node = tree index + 1. */
+int oracle_xdrop_pinned(const gb_flat_index* ix, const gb_scores* scores,
+                        const int32_t* tree_parent, const uint32_t* tree_node, uint32_t n_tree, uint32_t root_trim,
+                        const uint8_t* query, uint32_t qlen, uint32_t max_gap,
+                        int32_t* score_out, gb_mapping* mappings, uint32_t mapping_cap, uint32_t* n_mappings,
+                        uint32_t* edits, uint32_t edit_cap, uint32_t* n_edits);
+
 #ifdef __cplusplus
 }
 #endif

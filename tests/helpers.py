@@ -143,3 +143,98 @@ def to_seed(node_id, rev, offset, read_offset):
 
 def load_golden(name):
     return json.loads((GOLDEN / name).read_text())
+
+
+# ---------------------------------------------------------------------------------------
+# mapper-level plumbing
+# ---------------------------------------------------------------------------------------
+alignment_dt = np.dtype([("read_id", "<u4"), ("score", "<i4"), ("mapq", "u1"), ("flags", "u1"), ("n_mappings", "<u2"),
+                         ("mapping_off", "<u4"), ("edit_off", "<u4"), ("n_edits", "<u4"),
+                         ("mapq_uncapped", "<f4"), ("mapq_explored_cap", "<f4")])
+mapping_dt = np.dtype([("node", "<u4"), ("offset", "<u2"), ("n_edits", "<u2")])
+assert alignment_dt.itemsize == 32 and mapping_dt.itemsize == 8
+
+
+class MapParams(C.Structure):
+    _fields_ = [
+        ("hit_cap", C.c_uint32), ("hard_hit_cap", C.c_uint32), ("minimizer_score_fraction", C.c_double),
+        ("minimizer_coverage_flank", C.c_uint32), ("max_unique_min", C.c_uint32), ("num_bp_per_min", C.c_uint32),
+        ("distance_limit", C.c_uint32), ("min_extensions", C.c_uint32), ("max_extensions", C.c_uint32),
+        ("cluster_score_threshold", C.c_double), ("pad_cluster_score_threshold", C.c_double),
+        ("cluster_coverage_threshold", C.c_double), ("extension_set_score_threshold", C.c_double),
+        ("extension_score_threshold", C.c_int32), ("min_extension_sets", C.c_int32),
+        ("extension_set_min_score", C.c_int32), ("max_alignments", C.c_uint32),
+        ("max_extension_mismatches", C.c_uint32), ("max_multimaps", C.c_uint32), ("max_dozeu_cells", C.c_uint32),
+        ("do_dp", C.c_uint32),
+        ("fragment_mean", C.c_double), ("fragment_stdev", C.c_double), ("paired_distance_stdevs", C.c_double),
+        ("paired_rescue_score_limit", C.c_double), ("rescue_subgraph_stdevs", C.c_double),
+        ("max_rescue_attempts", C.c_uint32), ("max_fragment_length", C.c_uint32),
+        ("mapping_cap_per_read", C.c_uint32), ("edit_cap_per_read", C.c_uint32),
+    ]
+
+
+COUNTER_NAMES = ["reads", "minimizers", "seeds", "clusters", "extend_calls", "direct", "tail_dps", "tail_cells",
+                 "tail_nodes", "tail_bases", "path_nodes", "edits", "rescues"]
+
+
+def default_map_params() -> MapParams:
+    lib = oracle_lib()
+    lib.oracle_map_params_default.argtypes = [C.POINTER(MapParams)]
+    lib.oracle_map_params_default.restype = None
+    p = MapParams()
+    lib.oracle_map_params_default(C.byref(p))
+    return p
+
+
+def pack_reads(reads, quals=None):
+    """reads: uint8 [n, L] array or list of bytes -> (buffer, qual buffer or None, read_off)."""
+    if isinstance(reads, np.ndarray) and reads.ndim == 2:
+        n, L = reads.shape
+        read_off = (np.arange(n + 1, dtype=np.uint64) * np.uint64(L))
+        rbuf = np.ascontiguousarray(reads).reshape(-1)
+        qbuf = None if quals is None else np.ascontiguousarray(quals).reshape(-1)
+        return rbuf, qbuf, read_off
+    enc = [r.encode() if isinstance(r, str) else bytes(r) for r in reads]
+    read_off = np.zeros(len(enc) + 1, dtype=np.uint64)
+    read_off[1:] = np.cumsum([len(r) for r in enc])
+    rbuf = np.frombuffer(b"".join(enc) + b"\0", dtype=np.uint8).copy()
+    qbuf = None
+    if quals is not None:
+        qbuf = np.frombuffer(b"".join(bytes(q) for q in quals) + b"\0", dtype=np.uint8).copy()
+    return rbuf, qbuf, read_off
+
+
+def oracle_map(index, reads, quals=None, params=None, scores=None, threads=1):
+    lib = oracle_lib()
+    lib.oracle_map_batch.argtypes = [C.POINTER(capi.FlatIndex), C.POINTER(capi.Scores), C.POINTER(MapParams), C.c_uint32,
+                                     C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
+                                     C.c_int, C.c_void_p]
+    lib.oracle_map_batch.restype = C.c_int
+    p = params or default_map_params()
+    scores = scores or capi.DEFAULT_SCORES
+    rbuf, qbuf, read_off = pack_reads(reads, quals)
+    n = len(read_off) - 1
+    aln = np.zeros(n, dtype=alignment_dt)
+    maps = np.zeros(n * p.mapping_cap_per_read, dtype=mapping_dt)
+    edits = np.zeros(n * p.edit_cap_per_read, dtype=np.uint32)
+    status = np.zeros(n, dtype=np.uint8)
+    counters = np.zeros(len(COUNTER_NAMES), dtype=np.uint64)
+    rc = lib.oracle_map_batch(C.byref(index.view), C.byref(scores), C.byref(p), n, capi.ptr(rbuf),
+                              capi.ptr(qbuf) if qbuf is not None else None, capi.ptr(read_off), capi.ptr(aln),
+                              capi.ptr(maps), capi.ptr(edits), capi.ptr(status), threads, capi.ptr(counters))
+    assert rc == 0, "oracle_map_batch: output capacity too small"
+    return aln, maps, edits, status, dict(zip(COUNTER_NAMES, (int(c) for c in counters)))
+
+
+def decode_alignment(a, maps, edits):
+    """-> (score, mapq, [(node, offset, [(op, length, base)...])...])"""
+    path = []
+    e = int(a["edit_off"])
+    for i in range(int(a["n_mappings"])):
+        m = maps[int(a["mapping_off"]) + i]
+        ed = []
+        for _ in range(int(m["n_edits"])):
+            w = int(edits[e]); e += 1
+            ed.append(("MSID"[w & 3], w >> 4, "ACGT"[(w >> 2) & 3] if (w & 3) == 1 else ""))
+        path.append((int(m["node"]), int(m["offset"]), ed))
+    return int(a["score"]), int(a["mapq"]), path
