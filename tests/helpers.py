@@ -148,29 +148,9 @@ def load_golden(name):
 # ---------------------------------------------------------------------------------------
 # mapper-level plumbing
 # ---------------------------------------------------------------------------------------
-alignment_dt = np.dtype([("read_id", "<u4"), ("score", "<i4"), ("mapq", "u1"), ("flags", "u1"), ("n_mappings", "<u2"),
-                         ("mapping_off", "<u4"), ("edit_off", "<u4"), ("n_edits", "<u4"),
-                         ("mapq_uncapped", "<f4"), ("mapq_explored_cap", "<f4")])
-mapping_dt = np.dtype([("node", "<u4"), ("offset", "<u2"), ("n_edits", "<u2")])
-assert alignment_dt.itemsize == 32 and mapping_dt.itemsize == 8
-
-
-class MapParams(C.Structure):
-    _fields_ = [
-        ("hit_cap", C.c_uint32), ("hard_hit_cap", C.c_uint32), ("minimizer_score_fraction", C.c_double),
-        ("minimizer_coverage_flank", C.c_uint32), ("max_unique_min", C.c_uint32), ("num_bp_per_min", C.c_uint32),
-        ("distance_limit", C.c_uint32), ("min_extensions", C.c_uint32), ("max_extensions", C.c_uint32),
-        ("cluster_score_threshold", C.c_double), ("pad_cluster_score_threshold", C.c_double),
-        ("cluster_coverage_threshold", C.c_double), ("extension_set_score_threshold", C.c_double),
-        ("extension_score_threshold", C.c_int32), ("min_extension_sets", C.c_int32),
-        ("extension_set_min_score", C.c_int32), ("max_alignments", C.c_uint32),
-        ("max_extension_mismatches", C.c_uint32), ("max_multimaps", C.c_uint32), ("max_dozeu_cells", C.c_uint32),
-        ("do_dp", C.c_uint32),
-        ("fragment_mean", C.c_double), ("fragment_stdev", C.c_double), ("paired_distance_stdevs", C.c_double),
-        ("paired_rescue_score_limit", C.c_double), ("rescue_subgraph_stdevs", C.c_double),
-        ("max_rescue_attempts", C.c_uint32), ("max_fragment_length", C.c_uint32),
-        ("mapping_cap_per_read", C.c_uint32), ("edit_cap_per_read", C.c_uint32),
-    ]
+alignment_dt = capi.alignment_dt
+mapping_dt = capi.mapping_dt
+MapParams = capi.MapParams
 
 
 COUNTER_NAMES = ["reads", "minimizers", "seeds", "clusters", "extend_calls", "direct", "tail_dps", "tail_cells",
@@ -178,12 +158,7 @@ COUNTER_NAMES = ["reads", "minimizers", "seeds", "clusters", "extend_calls", "di
 
 
 def default_map_params() -> MapParams:
-    lib = oracle_lib()
-    lib.oracle_map_params_default.argtypes = [C.POINTER(MapParams)]
-    lib.oracle_map_params_default.restype = None
-    p = MapParams()
-    lib.oracle_map_params_default(C.byref(p))
-    return p
+    return capi.default_map_params()
 
 
 def pack_reads(reads, quals=None):
@@ -238,3 +213,24 @@ def decode_alignment(a, maps, edits):
             ed.append(("MSID"[w & 3], w >> 4, "ACGT"[(w >> 2) & 3] if (w & 3) == 1 else ""))
         path.append((int(m["node"]), int(m["offset"]), ed))
     return int(a["score"]), int(a["mapq"]), path
+
+
+def gpu_map(dev, reads, quals=None, params=None):
+    rbuf, qbuf, read_off = pack_reads(reads, quals)
+    return dev.map_arrays(rbuf, qbuf, read_off, params)
+
+
+def compare_alignments(got, want, n, mapq_tol=1):
+    """got / want = (aln, maps, edits, status[, counters]).  Scores, paths and edits must be
+    identical; MAPQ within +-mapq_tol (FP64 libm differences, BASELINE.json north_star)."""
+    ga, gm, ge, gs = got[:4]
+    wa, wm, we, ws = want[:4]
+    bad = []
+    for i in range(n):
+        assert gs[i] == 0, f"read {i}: GPU status {gs[i]}"
+        assert ws[i] == 0
+        gd = decode_alignment(ga[i], gm, ge)
+        wd = decode_alignment(wa[i], wm, we)
+        if gd[0] != wd[0] or gd[2] != wd[2] or abs(gd[1] - wd[1]) > mapq_tol or (ga[i]["flags"] & 1) != (wa[i]["flags"] & 1):
+            bad.append((i, gd, wd))
+    return bad

@@ -60,6 +60,38 @@ class ExtendParams(C.Structure):
 
 DEFAULT_SCORES = Scores(1, 4, 6, 1, 5)
 
+alignment_dt = np.dtype([("read_id", "<u4"), ("score", "<i4"), ("mapq", "u1"), ("flags", "u1"), ("n_mappings", "<u2"),
+                         ("mapping_off", "<u4"), ("edit_off", "<u4"), ("n_edits", "<u4"),
+                         ("mapq_uncapped", "<f4"), ("mapq_explored_cap", "<f4")])
+mapping_dt = np.dtype([("node", "<u4"), ("offset", "<u2"), ("n_edits", "<u2")])
+assert alignment_dt.itemsize == 32 and mapping_dt.itemsize == 8
+
+
+class MapParams(C.Structure):
+    """gb_map_params (include/giraffe_b200.h)."""
+    _fields_ = [
+        ("hit_cap", C.c_uint32), ("hard_hit_cap", C.c_uint32), ("minimizer_score_fraction", C.c_double),
+        ("minimizer_coverage_flank", C.c_uint32), ("max_unique_min", C.c_uint32), ("num_bp_per_min", C.c_uint32),
+        ("distance_limit", C.c_uint32), ("min_extensions", C.c_uint32), ("max_extensions", C.c_uint32),
+        ("cluster_score_threshold", C.c_double), ("pad_cluster_score_threshold", C.c_double),
+        ("cluster_coverage_threshold", C.c_double), ("extension_set_score_threshold", C.c_double),
+        ("extension_score_threshold", C.c_int32), ("min_extension_sets", C.c_int32),
+        ("extension_set_min_score", C.c_int32), ("max_alignments", C.c_uint32),
+        ("max_extension_mismatches", C.c_uint32), ("max_multimaps", C.c_uint32), ("max_dozeu_cells", C.c_uint32),
+        ("do_dp", C.c_uint32),
+        ("fragment_mean", C.c_double), ("fragment_stdev", C.c_double), ("paired_distance_stdevs", C.c_double),
+        ("paired_rescue_score_limit", C.c_double), ("rescue_subgraph_stdevs", C.c_double),
+        ("max_rescue_attempts", C.c_uint32), ("max_fragment_length", C.c_uint32),
+        ("mapping_cap_per_read", C.c_uint32), ("edit_cap_per_read", C.c_uint32),
+    ]
+
+
+def default_map_params() -> "MapParams":
+    p = MapParams()
+    load_library().gb_map_params_default(C.byref(p))
+    return p
+
+
 _lib = None
 
 
@@ -88,6 +120,10 @@ def load_library() -> C.CDLL:
     lib.gb_set_scores.restype = C.c_int
     lib.gb_extend_batch.argtypes = [vp, C.POINTER(ExtendParams), u32, vp, vp, u32, vp, vp, vp, vp, vp, vp, vp, vp]
     lib.gb_extend_batch.restype = C.c_int
+    lib.gb_map_params_default.argtypes = [C.POINTER(MapParams)]
+    lib.gb_map_params_default.restype = None
+    lib.gb_map_batch.argtypes = [vp, C.POINTER(MapParams), u32, vp, vp, vp, vp, vp, vp, vp]
+    lib.gb_map_batch.restype = C.c_int
     lib.gb_last_kernel_ms.argtypes = [vp]
     lib.gb_last_kernel_ms.restype = C.c_float
     lib.gb_launch_count.argtypes = [vp]
@@ -227,6 +263,21 @@ class Device:
         if rc != GB_OK:
             raise GbError(rc, "gb_extend_batch")
         return ext_count, status, ext, path_pool, mism_pool
+
+    def map_arrays(self, rbuf, qbuf, read_off, params=None):
+        """gb_map_batch on packed host arrays.  Returns (aln, mappings, edits, status)."""
+        lib = load_library()
+        p = params or default_map_params()
+        n = len(read_off) - 1
+        aln = np.zeros(n, dtype=alignment_dt)
+        maps = np.zeros(n * p.mapping_cap_per_read, dtype=mapping_dt)
+        edits = np.zeros(n * p.edit_cap_per_read, dtype=np.uint32)
+        status = np.zeros(n, dtype=np.uint8)
+        rc = lib.gb_map_batch(self._h, C.byref(p), n, ptr(rbuf), ptr(qbuf) if qbuf is not None else None,
+                              ptr(read_off), ptr(aln), ptr(maps), ptr(edits), ptr(status))
+        if rc != GB_OK:
+            raise GbError(rc, "gb_map_batch")
+        return aln, maps, edits, status
 
     def close(self):
         if getattr(self, "_h", None):

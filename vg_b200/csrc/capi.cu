@@ -31,6 +31,9 @@ struct ExtendBatch {
     gb_extension* ext; uint32_t* path_pool; uint32_t* mism_pool;
     uint32_t read_cap;          // bytes of shared memory per warp for the masked read
     uint32_t* work_counter;
+    // device-produced work list (mapping pipeline): when `items` is set, item i is
+    // items[i] and the item count is read from *n_items_dev (capped by n_items).
+    const DevItem* items; const uint32_t* n_items_dev;
 };
 
 __global__ void __launch_bounds__(EXTEND_WARPS * 32)
@@ -43,13 +46,16 @@ extend_kernel(DevIndex ix, ExtendParams p, ExtendBatch b, ExtendWorkspace ws) {
     QEntry* queue = ws.queue + (size_t)gwarp * ws.q_cap;
     ArenaNode* arena = ws.arena + (size_t)gwarp * ws.a_cap;
 
+    const uint32_t n_items = b.items ? min(b.n_items, *b.n_items_dev) : b.n_items;
     while (true) {
         uint32_t item = 0;
         if (lane == 0) item = atomicAdd(b.work_counter, 1u);
         item = __shfl_sync(FULL, item, 0);
-        if (item >= b.n_items) break;
+        if (item >= n_items) break;
 
-        const uint32_t r = b.item_read[item];
+        uint32_t r; uint64_t sb; uint32_t n_seeds;
+        if (b.items) { const DevItem it = b.items[item]; r = it.read; sb = it.seed_off; n_seeds = it.seed_cnt; }
+        else { r = b.item_read[item]; sb = b.seed_off[item]; n_seeds = (uint32_t)(b.seed_off[item + 1] - sb); }
         const uint64_t rb = b.read_off[r];
         const uint32_t read_len = (uint32_t)(b.read_off[r + 1] - rb);
         uint32_t status = GB_ITEM_OK, n = 0;
@@ -63,8 +69,6 @@ extend_kernel(DevIndex ix, ExtendParams p, ExtendBatch b, ExtendWorkspace ws) {
                 sread[i] = c;
             }
             __syncwarp();
-            const uint64_t sb = b.seed_off[item];
-            const uint32_t n_seeds = (uint32_t)(b.seed_off[item + 1] - sb);
             n = extend_item(ix, p, sread, read_len, b.seeds + sb, n_seeds,
                             queue, ws.q_cap, arena, ws.a_cap,
                             b.ext + (size_t)item * p.max_ext,
@@ -164,6 +168,18 @@ int launch_extend(gb_device* d, const ExtendParams& p, const ExtendBatch& b_in, 
     d->launches++;
     GB_CUDA(cudaGetLastError());
     return GB_OK;
+}
+
+int launch_extend_device(gb_device* d, const ExtendParams& p, const uint8_t* reads, const uint64_t* read_off,
+                         const uint32_t* item_read, const gb_seed* seeds, const uint64_t* seed_off,
+                         const DevItem* items, const uint32_t* n_items_dev, uint32_t n_items_max,
+                         uint32_t* ext_count, uint8_t* status, gb_extension* ext, uint32_t* path_pool, uint32_t* mism_pool,
+                         uint32_t max_read_len) {
+    ExtendBatch b{};
+    b.reads = reads; b.read_off = read_off; b.item_read = item_read; b.seeds = seeds; b.seed_off = seed_off;
+    b.n_items = n_items_max; b.items = items; b.n_items_dev = n_items_dev;
+    b.ext_count = ext_count; b.status = status; b.ext = ext; b.path_pool = path_pool; b.mism_pool = mism_pool;
+    return launch_extend(d, p, b, max_read_len);
 }
 
 } // namespace gb

@@ -3,6 +3,7 @@
 #include "giraffe_b200.h"
 #include "device_index.cuh"
 #include "extend.cuh"
+#include "map_state.cuh"
 
 #include <cuda_runtime.h>
 #include <string>
@@ -74,8 +75,29 @@ struct gb_device {
     uint32_t* work_counter = nullptr;
     float last_kernel_ms = 0.f;
     uint64_t launches = 0;
+    // mapping pipeline: parameter tables, intermediate pools, workspaces, I/O staging
+    bool tables_ready = false; uint32_t tables_hard_hit_cap = 0;
+    gb::DevBuf<double> t_hit, t_plo, t_phred;
+    gb::DevBuf<gb::ReadState> p_states;
+    gb::DevBuf<gb::DevMinimizer> p_min;
+    gb::DevBuf<gb::DevSeed> p_seeds;
+    gb::DevBuf<gb::DevItem> p_items;
+    gb::DevBuf<gb_seed> p_ext_seeds;
+    gb::DevBuf<uint32_t> p_cursors, p_ext_count, p_path, p_mism;
+    gb::DevBuf<uint8_t> p_ext_status;
+    gb::DevBuf<gb_extension> p_ext;
+    gb::DevBuf<uint8_t> ws_tail, ws_cand;
+    gb::DevBuf<uint8_t> io_reads, io_quals, io_status;
+    gb::DevBuf<uint64_t> io_read_off;
+    gb::DevBuf<gb_alignment> io_aln;
+    gb::DevBuf<gb_mapping> io_maps;
+    gb::DevBuf<uint32_t> io_edits;
     void release_all() {
         nodes.release(); seq.release(); gbwt.release(); dist.release(); table.release(); hits.release();
         ws_queue.release(); ws_arena.release();
+        t_hit.release(); t_plo.release(); t_phred.release(); p_states.release(); p_min.release(); p_seeds.release();
+        p_items.release(); p_ext_seeds.release(); p_cursors.release(); p_ext_count.release(); p_path.release(); p_mism.release();
+        p_ext_status.release(); p_ext.release(); ws_tail.release(); ws_cand.release();
+        io_reads.release(); io_quals.release(); io_status.release(); io_read_off.release(); io_aln.release(); io_maps.release(); io_edits.release();
     }
 };
