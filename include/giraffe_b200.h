@@ -288,6 +288,25 @@ int gb_map_batch(gb_device* dev, const gb_map_params* p,
                  uint32_t n_reads, const uint8_t* reads, const uint8_t* quals, const uint64_t* read_off,
                  gb_alignment* aln, gb_mapping* mappings, uint32_t* edits, uint8_t* status);
 
+/* ------------------------------------------------------------------------------------
+ * B3: Aligner::align_pinned(alignment, graph, pin_left = true, xdrop = true, max_gap),
+ * batched over explicit haplotype trees      aligner.hpp:183, aligner.cpp:628-686,
+ *                                             DozeuInterface::align_pinned dozeu_interface.cpp:724
+ * Problem i: tree nodes tree_off[i] .. tree_off[i+1] as (parent index within the tree or -1,
+ * oriented node) in DFS visit order (the TreeSubgraph numbering of
+ * MinimizerMapper::get_tail_forest, minimizer_mapper.cpp:5838-5845), the root's first
+ * root_trim[i] bases cut off; query i = query[query_off[i] .. query_off[i+1]).
+ * Outputs per problem: score, mappings (node = tree index, offsets in trimmed coordinates),
+ * edits, counts.  Right-pinned problems are posed, as the reference does
+ * (minimizer_mapper.cpp:5663-5665), on the reverse-complemented query and reverse tree.
+ * ---------------------------------------------------------------------------------- */
+int gb_xdrop_pinned_batch(gb_device* dev, uint32_t n,
+                          const int32_t* tree_parent, const uint32_t* tree_node, const uint64_t* tree_off,
+                          const uint32_t* root_trim, const uint8_t* query, const uint64_t* query_off,
+                          const uint32_t* max_gap, uint32_t map_cap, uint32_t edit_cap,
+                          int32_t* score, gb_mapping* maps, uint32_t* edits, uint32_t* n_maps, uint32_t* n_edits,
+                          uint8_t* status);
+
 /* Kernel-only timing of the last gb_*_batch call on this handle, milliseconds
  * (CUDA events on the handle's stream around the kernels, copies excluded). */
 float gb_last_kernel_ms(const gb_device* dev);

@@ -124,6 +124,8 @@ def load_library() -> C.CDLL:
     lib.gb_map_params_default.restype = None
     lib.gb_map_batch.argtypes = [vp, C.POINTER(MapParams), u32, vp, vp, vp, vp, vp, vp, vp]
     lib.gb_map_batch.restype = C.c_int
+    lib.gb_xdrop_pinned_batch.argtypes = [vp, u32, vp, vp, vp, vp, vp, vp, vp, u32, u32, vp, vp, vp, vp, vp, vp]
+    lib.gb_xdrop_pinned_batch.restype = C.c_int
     lib.gb_last_kernel_ms.argtypes = [vp]
     lib.gb_last_kernel_ms.restype = C.c_float
     lib.gb_launch_count.argtypes = [vp]
@@ -263,6 +265,44 @@ class Device:
         if rc != GB_OK:
             raise GbError(rc, "gb_extend_batch")
         return ext_count, status, ext, path_pool, mism_pool
+
+    def xdrop_pinned_batch(self, problems, map_cap=256, edit_cap=1024):
+        """problems: list of (parents, nodes, root_trim, query bytes, max_gap).
+        Returns list of (score, [[tree_index + 1, offset, [[op, len, base], ...]], ...])."""
+        lib = load_library()
+        n = len(problems)
+        tree_off = np.zeros(n + 1, dtype=np.uint64)
+        tree_off[1:] = np.cumsum([len(p[0]) for p in problems])
+        query_off = np.zeros(n + 1, dtype=np.uint64)
+        query_off[1:] = np.cumsum([len(p[3]) for p in problems])
+        par = np.concatenate([np.asarray(p[0], dtype=np.int32) for p in problems])
+        nodes = np.concatenate([np.asarray(p[1], dtype=np.uint32) for p in problems])
+        trim = np.array([p[2] for p in problems], dtype=np.uint32)
+        q = np.frombuffer(b"".join(bytes(p[3]) for p in problems) + b"\0", dtype=np.uint8).copy()
+        gap = np.array([p[4] for p in problems], dtype=np.uint32)
+        score = np.zeros(n, dtype=np.int32)
+        maps = np.zeros(n * map_cap, dtype=mapping_dt)
+        edits = np.zeros(n * edit_cap, dtype=np.uint32)
+        nm = np.zeros(n, dtype=np.uint32); ne = np.zeros(n, dtype=np.uint32)
+        status = np.zeros(n, dtype=np.uint8)
+        rc = lib.gb_xdrop_pinned_batch(self._h, n, ptr(par), ptr(nodes), ptr(tree_off), ptr(trim), ptr(q), ptr(query_off),
+                                       ptr(gap), map_cap, edit_cap, ptr(score), ptr(maps), ptr(edits), ptr(nm), ptr(ne),
+                                       ptr(status))
+        if rc != GB_OK:
+            raise GbError(rc, "gb_xdrop_pinned_batch")
+        out = []
+        for i in range(n):
+            assert status[i] == GB_ITEM_OK, f"problem {i}: status {status[i]}"
+            path, e = [], i * edit_cap
+            for k in range(int(nm[i])):
+                m = maps[i * map_cap + k]
+                ed = []
+                for _ in range(int(m["n_edits"])):
+                    w = int(edits[e]); e += 1
+                    ed.append(["MSID"[w & 3], w >> 4, "ACGT"[(w >> 2) & 3] if (w & 3) == 1 else ""])
+                path.append([int(m["node"]) + 1, int(m["offset"]), ed])
+            out.append((int(score[i]), path))
+        return out
 
     def map_arrays(self, rbuf, qbuf, read_off, params=None):
         """gb_map_batch on packed host arrays.  Returns (aln, mappings, edits, status)."""
