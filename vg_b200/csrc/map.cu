@@ -223,8 +223,8 @@ __device__ inline uint32_t align_read(const DevIndex& ix, const MapParamsDev& P,
             uint32_t min_tails = 1;
             for (uint32_t j = 0; j < n_ext; j++) if (ext_full(ext[j])) min_tails++;
             if (min_tails < 2) min_tails = 2;
-            Pareto lf[40], rf[40]; uint32_t nl = 0, nr = 0;
-            for (uint32_t j = 0; j < n_ext && nl + 3 < 40; j++) {
+            Pareto lf[136], rf[136]; uint32_t nl = 0, nr = 0;
+            for (uint32_t j = 0; j < n_ext && nl + 3 < 136; j++) {
                 const gb_extension& e = ext[j];
                 if (ext_full(e)) continue;
                 const int32_t left_penalty = gap_penalty1(e.read_lo, sc);
@@ -241,7 +241,7 @@ __device__ inline uint32_t align_read(const DevIndex& ix, const MapParamsDev& P,
             nl = find_pareto_frontier(lf, nl); nr = find_pareto_frontier(rf, nr);
 
             // order extensions by score (process_until_threshold_a, :5443)
-            uint8_t eo[16]; const uint32_t ne_ = min(n_ext, 16u);
+            uint8_t eo[64]; const uint32_t ne_ = min(n_ext, 64u);
             for (uint32_t j = 0; j < ne_; j++) { uint32_t x = j; while (x > 0 && ext[j].score > ext[eo[x - 1]].score) { eo[x] = eo[x - 1]; x--; } eo[x] = (uint8_t)j; }
             {
                 uint32_t ties = 0;
@@ -551,7 +551,7 @@ int map_device(gb_device* d, const gb_map_params* hp, uint32_t n_reads, const ui
         GB_CUDA(cudaGetLastError());
     }
     // ---- K2: extension over the items produced on the device ----
-    const uint32_t max_ext = 16, path_cap = 160, mism_cap = 96;
+    const uint32_t max_ext = 48, path_cap = 384, mism_cap = 192;
     if ((rc = d->p_ext_count.reserve(item_cap))) return rc;
     if ((rc = d->p_ext_status.reserve(item_cap))) return rc;
     if ((rc = d->p_ext.reserve(item_cap * max_ext))) return rc;
