@@ -49,6 +49,14 @@ int oracle_xdrop_pinned(const gb_flat_index* ix, const gb_scores* scores,
                         int32_t* score_out, gb_mapping* mappings, uint32_t mapping_cap, uint32_t* n_mappings,
                         uint32_t* edits, uint32_t edit_cap, uint32_t* n_edits);
 
+/* MinimizerMapper::map_paired with a forced fragment distribution and max_rescue_attempts = 0
+ * (minimizer_mapper.cpp:1462-2942 without the rescue branch).  Reads are interleaved
+ * (2i = mate 1, 2i+1 = mate 2, both in input orientation).  Returns -2 if p->max_rescue_attempts != 0. */
+int oracle_map_paired_batch(const gb_flat_index* ix, const gb_scores* scores, const gb_map_params* p,
+                            uint32_t n_reads, const uint8_t* reads, const uint8_t* quals, const uint64_t* read_off,
+                            gb_alignment* aln, gb_mapping* mappings, uint32_t* edits, uint8_t* status,
+                            int n_threads, uint64_t* counters_out);
+
 #ifdef __cplusplus
 }
 #endif

@@ -234,3 +234,34 @@ def compare_alignments(got, want, n, mapq_tol=1):
         if gd[0] != wd[0] or gd[2] != wd[2] or abs(gd[1] - wd[1]) > mapq_tol or (ga[i]["flags"] & 1) != (wa[i]["flags"] & 1):
             bad.append((i, gd, wd))
     return bad
+
+
+def oracle_map_paired(index, reads, quals=None, params=None, scores=None, threads=1):
+    """reads interleaved (2i = mate 1, 2i+1 = mate 2)."""
+    lib = oracle_lib()
+    lib.oracle_map_paired_batch.argtypes = [C.POINTER(capi.FlatIndex), C.POINTER(capi.Scores), C.POINTER(MapParams), C.c_uint32,
+                                            C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
+                                            C.c_int, C.c_void_p]
+    lib.oracle_map_paired_batch.restype = C.c_int
+    p = params
+    scores = scores or capi.DEFAULT_SCORES
+    rbuf, qbuf, read_off = pack_reads(reads, quals)
+    n = len(read_off) - 1
+    aln = np.zeros(n, dtype=alignment_dt)
+    maps = np.zeros(n * p.mapping_cap_per_read, dtype=mapping_dt)
+    edits = np.zeros(n * p.edit_cap_per_read, dtype=np.uint32)
+    status = np.zeros(n, dtype=np.uint8)
+    counters = np.zeros(len(COUNTER_NAMES), dtype=np.uint64)
+    rc = lib.oracle_map_paired_batch(C.byref(index.view), C.byref(scores), C.byref(p), n, capi.ptr(rbuf),
+                                     capi.ptr(qbuf) if qbuf is not None else None, capi.ptr(read_off), capi.ptr(aln),
+                                     capi.ptr(maps), capi.ptr(edits), capi.ptr(status), threads, capi.ptr(counters))
+    assert rc == 0, f"oracle_map_paired_batch rc {rc}"
+    return aln, maps, edits, status, dict(zip(COUNTER_NAMES, (int(c) for c in counters)))
+
+
+def paired_params(mean=400.0, stdev=50.0):
+    p = default_map_params()
+    p.fragment_mean = mean
+    p.fragment_stdev = stdev
+    p.max_rescue_attempts = 0
+    return p
