@@ -50,7 +50,15 @@ seed_kernel(DevIndex ix, MapParamsDev P, MapBatch b, SeedPools pools) {
         memset(&rs, 0, sizeof(rs));
         uint32_t status = GB_ITEM_OK;
         if (L > b.Lc) status = GB_ITEM_OUT_FULL;
-        else status = seed_read(ix, P, sm, b.reads + rb, L, r, pools, rs);
+        else {
+            for (uint32_t i = lane; i < L; i += 32) sm.read[i] = b.reads[rb + i];
+            __syncwarp();
+            DevRng rng; rng.inited = 0; rng.state = 0;
+            rng.seed = fold_seed(0u, sm.read, L);                     // LazyRNG seed: the read sequence (:620-622)
+            status = seed_phase_a(ix, P, sm, L, pools, rng, rs);
+            if (status == GB_ITEM_OK) status = cluster_phase_se(ix, P, sm, L, r, pools, rng, rs);
+            rs.rng = rng;
+        }
         rs.status = status;
         if (status != GB_ITEM_OK) { rs.item_cnt = 0; }
         if (lane == 0) b.states[r] = rs;

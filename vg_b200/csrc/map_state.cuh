@@ -35,11 +35,14 @@ __device__ __forceinline__ uint32_t rng_next(DevRng& r) {
 // One minimizer of the read in SCORE order (MinimizerMapper::Minimizer, minimizer_mapper.hpp:565).
 struct __align__(16) DevMinimizer {
     uint64_t hash;
+    double   score;
     uint16_t fwd_offset;      // forward_offset()
     uint16_t agg_start;
     uint16_t agg_len;
-    uint16_t pad;
+    uint16_t is_reverse;
+    uint32_t pad[2];
 };
+static_assert(sizeof(DevMinimizer) == 32, "DevMinimizer must be 32 bytes");
 
 // One seed (SnarlDistanceIndexClusterer::Seed) plus its chain coordinates.
 struct __align__(16) DevSeed {
@@ -58,7 +61,7 @@ struct __align__(16) DevItem {
     uint32_t read;
     uint32_t seed_off, seed_cnt;          // gb_seed pool
     uint32_t present[PRESENT_WORDS];      // minimizers with a hit in the cluster
-    uint32_t pad;
+    uint32_t fragment;                    // paired-end: fragment cluster of this read cluster
 };
 
 // Per-read state carried from seed_kernel to align_kernel.
@@ -70,6 +73,15 @@ struct __align__(16) ReadState {
     uint32_t status;
     uint32_t n_clusters;
     uint32_t pad[4];
+};
+
+// Paired-end: per-pair state (fragment clusters), minimizer_mapper.cpp:1568-1690.
+constexpr uint32_t MAX_FRAGMENTS = 64;
+struct __align__(16) PairState {
+    uint32_t n_fragments;                 // max_fragment_num + 1 (0 when there are no clusters)
+    uint32_t found_paired_cluster;
+    uint32_t pad[2];
+    uint8_t  better_cluster_count[MAX_FRAGMENTS];
 };
 
 struct MapParamsDev {

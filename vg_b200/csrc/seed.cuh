@@ -1,20 +1,23 @@
-// seed.cuh — seed_kernel: one warp per read does
+// seed.cuh — seeding stage, one warp per read (single-end) or per read pair (paired-end):
 //   find_minimizers            minimizer_mapper.cpp:3918-3974  (gbwtgraph minimizer_regions + find)
 //   sort_minimizers_by_score   :4074-4107  (LazyRNG tie shuffle, utility.hpp:771-794)
 //   find_seeds                 :4109-4517  (filter cascade with running state)
-//   cluster_seeds              snarl_seed_clusterer.cpp:28-63 (connected components under the
-//                              unoriented minimum distance, via the 16-byte distance payload)
+//   cluster_seeds              snarl_seed_clusterer.cpp:28-63 / :65-145 (connected components under
+//                              the unoriented minimum distance, via the 16-byte distance payload)
 //   score_cluster              :4738-4780
-//   cluster selection          :680-832    (process_until_threshold_e + cluster score cutoff)
+//   cluster selection          single-end :655-832, paired-end :1568-1883
 //   extend_seed_group packing  :4784-4850  ((handle, read_offset - node_offset) seeds)
 // and leaves DevMinimizer / DevSeed / DevItem records in HBM for the next kernels.
+//
+// Phase A (per read) needs the k-mer scratch in shared memory; phase B (clusters) works on the
+// HBM records plus a small shared cluster table, so a pair reuses one shared scratch.
 #pragma once
 #include "map_state.cuh"
 #include "minimizer_common.h"
 
 namespace gb {
 
-constexpr uint32_t MAX_CLUSTERS = 64;     // clusters per read kept in shared memory
+constexpr uint32_t MAX_CLUSTERS = 64;     // read clusters per read kept in shared memory
 
 struct SeedPools {
     DevMinimizer* minimizers; uint32_t min_cap;  uint32_t* min_cursor;
@@ -40,25 +43,28 @@ struct SeedSmem {
     uint8_t*  m_rev;
     uint8_t*  m_order;     // score order -> read order index
     uint8_t*  m_pass;      // per score-order minimizer: passed the filters
-    // clusters
-    double*   c_score;     // [MAX_CLUSTERS]
+    // clusters (two reads' worth)
+    double*   c_score;     // [2 * MAX_CLUSTERS]
     double*   c_cov;
     uint32_t* c_label;
-    uint32_t* c_present;   // [MAX_CLUSTERS * PRESENT_WORDS]
-    uint8_t*  c_order;     // processing order
+    uint32_t* c_present;   // [2 * MAX_CLUSTERS * PRESENT_WORDS]
+    uint8_t*  c_order;     // [2 * MAX_CLUSTERS] processing order
+    uint8_t*  c_frag;      // [2 * MAX_CLUSTERS] fragment id of each read cluster
+    uint8_t*  scratch;     // [2 * MAX_CLUSTERS + MAX_MINIMIZERS]
 };
 
 __host__ __device__ inline size_t seed_smem_bytes(uint32_t Lc) {
     size_t b = 0;
-    b += (size_t)Lc * 8 * 2;                       // khash, kkey
-    b += (size_t)MAX_MINIMIZERS * (8 + 8 + 8);     // m_key, m_hash, m_score
-    b += (size_t)MAX_CLUSTERS * (8 + 8);           // c_score, c_cov
-    b += (size_t)MAX_MINIMIZERS * (4 + 4);         // hit_off, hit_cnt
-    b += (size_t)MAX_CLUSTERS * 4 * (1 + PRESENT_WORDS);
-    b += (size_t)MAX_MINIMIZERS * (2 + 2 + 2);     // fwd, agg_start, agg_len
-    b += (size_t)Lc * 2;                           // read, kflag
-    b += (size_t)MAX_MINIMIZERS * 3;               // rev, order, pass
-    b += MAX_CLUSTERS;                             // c_order
+    b += (size_t)Lc * 8 * 2;                            // khash, kkey
+    b += (size_t)MAX_MINIMIZERS * (8 + 8 + 8);          // m_key, m_hash, m_score
+    b += (size_t)2 * MAX_CLUSTERS * (8 + 8);            // c_score, c_cov
+    b += (size_t)MAX_MINIMIZERS * (4 + 4);              // hit_off, hit_cnt
+    b += (size_t)2 * MAX_CLUSTERS * 4 * (1 + PRESENT_WORDS);
+    b += (size_t)MAX_MINIMIZERS * (2 + 2 + 2);          // fwd, agg_start, agg_len
+    b += (size_t)Lc * 2;                                // read, kflag
+    b += (size_t)MAX_MINIMIZERS * 3;                    // rev, order, pass
+    b += (size_t)2 * MAX_CLUSTERS * 2;                  // c_order, c_frag
+    b += (size_t)2 * MAX_CLUSTERS + MAX_MINIMIZERS;     // scratch
     return (b + 15) & ~(size_t)15;
 }
 
@@ -70,12 +76,12 @@ __device__ inline SeedSmem carve_seed_smem(uint8_t* base, uint32_t Lc) {
     s.m_key = (uint64_t*)p; p += MAX_MINIMIZERS * 8;
     s.m_hash = (uint64_t*)p; p += MAX_MINIMIZERS * 8;
     s.m_score = (double*)p; p += MAX_MINIMIZERS * 8;
-    s.c_score = (double*)p; p += MAX_CLUSTERS * 8;
-    s.c_cov = (double*)p; p += MAX_CLUSTERS * 8;
+    s.c_score = (double*)p; p += 2 * MAX_CLUSTERS * 8;
+    s.c_cov = (double*)p; p += 2 * MAX_CLUSTERS * 8;
     s.m_hit_off = (uint32_t*)p; p += MAX_MINIMIZERS * 4;
     s.m_hit_cnt = (uint32_t*)p; p += MAX_MINIMIZERS * 4;
-    s.c_label = (uint32_t*)p; p += MAX_CLUSTERS * 4;
-    s.c_present = (uint32_t*)p; p += MAX_CLUSTERS * 4 * PRESENT_WORDS;
+    s.c_label = (uint32_t*)p; p += 2 * MAX_CLUSTERS * 4;
+    s.c_present = (uint32_t*)p; p += 2 * MAX_CLUSTERS * 4 * PRESENT_WORDS;
     s.m_fwd = (uint16_t*)p; p += MAX_MINIMIZERS * 2;
     s.m_agg_start = (uint16_t*)p; p += MAX_MINIMIZERS * 2;
     s.m_agg_len = (uint16_t*)p; p += MAX_MINIMIZERS * 2;
@@ -84,7 +90,9 @@ __device__ inline SeedSmem carve_seed_smem(uint8_t* base, uint32_t Lc) {
     s.m_rev = p; p += MAX_MINIMIZERS;
     s.m_order = p; p += MAX_MINIMIZERS;
     s.m_pass = p; p += MAX_MINIMIZERS;
-    s.c_order = p; p += MAX_CLUSTERS;
+    s.c_order = p; p += 2 * MAX_CLUSTERS;
+    s.c_frag = p; p += 2 * MAX_CLUSTERS;
+    s.scratch = p; p += 2 * MAX_CLUSTERS + MAX_MINIMIZERS;
     return s;
 }
 
@@ -94,7 +102,40 @@ __device__ __forceinline__ uint32_t pow13(uint32_t e) {
     return r;
 }
 
-// minimum graph distance a -> b on the forward strand (see gb_dist_payload)
+// seedNumber = fold(seed * 13 + byte) over `bytes` (utility.cpp:911-927), continuing from `seed`.
+__device__ inline uint32_t fold_seed(uint32_t seed, const uint8_t* bytes, uint32_t L) {
+    const int lane = lane_id();
+    const uint32_t chunk = (L + 31) / 32;
+    const uint32_t b = min(L, lane * chunk), e = min(L, b + chunk);
+    uint32_t fold = 0;
+    for (uint32_t i = b; i < e; i++) fold = fold * 13u + bytes[i];
+    uint32_t term = fold * pow13(L - e);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) term += __shfl_xor_sync(FULL, term, o);
+    return seed * pow13(L) + term;
+}
+
+// set bits [lo, hi) of a bitmap made of 32-bit words
+__device__ __forceinline__ void set_bit_range(uint32_t* words, uint32_t lo, uint32_t hi) {
+    if (lo >= hi) return;
+    const uint32_t w0 = lo >> 5, w1 = (hi - 1) >> 5;
+    const uint32_t m0 = 0xffffffffu << (lo & 31), m1 = 0xffffffffu >> (31 - ((hi - 1) & 31));
+    if (w0 == w1) { words[w0] |= (m0 & m1); return; }
+    words[w0] |= m0;
+    for (uint32_t w = w0 + 1; w < w1; w++) words[w] = 0xffffffffu;
+    words[w1] |= m1;
+}
+__device__ __forceinline__ bool any_bit_in_range(const uint32_t* words, uint32_t lo, uint32_t hi) {
+    if (lo >= hi) return false;
+    const uint32_t w0 = lo >> 5, w1 = (hi - 1) >> 5;
+    const uint32_t m0 = 0xffffffffu << (lo & 31), m1 = 0xffffffffu >> (31 - ((hi - 1) & 31));
+    if (w0 == w1) return (words[w0] & m0 & m1) != 0;
+    if (words[w0] & m0) return true;
+    for (uint32_t w = w0 + 1; w < w1; w++) if (words[w]) return true;
+    return (words[w1] & m1) != 0;
+}
+
+// unoriented minimum graph distance <= limit between two seeds (see gb_dist_payload)
 __device__ __forceinline__ bool seeds_within(const DevSeed& a, const DevSeed& b, int32_t limit) {
     const uint32_t ida = a.id_off >> 10, idb = b.id_off >> 10;
     if (ida == idb) {
@@ -106,30 +147,18 @@ __device__ __forceinline__ bool seeds_within(const DevSeed& a, const DevSeed& b,
     return false;
 }
 
-// The whole seeding stage for one read.  Returns status.
-__device__ inline uint32_t seed_read(const DevIndex& ix, const MapParamsDev& P, const SeedSmem& sm,
-                                     const uint8_t* __restrict__ gread, uint32_t L, uint32_t read_idx,
-                                     const SeedPools& pools, ReadState& rs) {
+// -----------------------------------------------------------------------------------------
+// Phase A: minimizers -> score order -> filter cascade -> DevMinimizer + DevSeed records.
+// `sm.read` must already hold the read.  rng is advanced by the tie shuffle.
+// -----------------------------------------------------------------------------------------
+__device__ inline uint32_t seed_phase_a(const DevIndex& ix, const MapParamsDev& P, const SeedSmem& sm, uint32_t L,
+                                        const SeedPools& pools, DevRng& rng, ReadState& rs) {
     const int lane = lane_id();
     const uint32_t k = ix.k, w = ix.w;
     const uint32_t window_bp = k + w - 1;
     rs.min_off = rs.min_cnt = rs.item_off = rs.item_cnt = rs.seed_off = rs.seed_cnt = 0; rs.n_clusters = 0;
-    rs.rng.inited = 0; rs.rng.state = 0;
-
-    // ---- stage the read; fold the RNG seed: seed = seed * 13 + byte over the sequence -------
-    {
-        const uint32_t chunk = (L + 31) / 32;
-        const uint32_t b = min(L, lane * chunk), e = min(L, b + chunk);
-        uint32_t fold = 0;
-        for (uint32_t i = b; i < e; i++) { const uint8_t c = gread[i]; sm.read[i] = c; fold = fold * 13u + c; }
-        uint32_t term = fold * pow13(L - e);       // bytes after my chunk
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) term += __shfl_xor_sync(FULL, term, o);
-        rs.rng.seed = term;
-    }
-    __syncwarp();
     if (L > 512) return GB_ITEM_OUT_FULL;          // short-read path: coverage bitmaps are 512 bits
-    if (L < window_bp) return GB_ITEM_OK;          // no minimizers -> no seeds -> unmapped
+    if (L < window_bp) return GB_ITEM_OK;          // no minimizers -> no seeds
 
     // ---- canonical k-mer hashes ------------------------------------------------------------
     const uint32_t nk = L - k + 1;
@@ -221,11 +250,9 @@ __device__ inline uint32_t seed_read(const DevIndex& ix, const MapParamsDev& P, 
     __syncwarp();
 
     // ---- shuffle the runs tied at the top score (sort_shuffling_ties over runs) ----------------------
-    // khash/kkey are dead now: reuse as scratch.
-    uint8_t* run_begin = reinterpret_cast<uint8_t*>(sm.khash);          // [<= M]
+    uint8_t* run_begin = reinterpret_cast<uint8_t*>(sm.khash);          // khash/kkey are dead: scratch
     uint8_t* run_len = run_begin + MAX_MINIMIZERS;
     uint8_t* tmp_order = run_len + MAX_MINIMIZERS;
-    DevRng rng = rs.rng;
     if (lane == 0) {
         const double top = sm.m_score[sm.m_order[0]];
         uint32_t T = 0, pos = 0;
@@ -264,8 +291,7 @@ __device__ inline uint32_t seed_read(const DevIndex& ix, const MapParamsDev& P, 
         uint32_t limit = 0, run_hits = 0; bool taking_run = false;
         uint32_t num_minimizers = 0, worst_kept_hits = 0;
         const uint32_t num_min_by_read_len = L / P.num_bp_per_min;
-        // read_coverage bit vector (only consulted once num_minimizers reaches the cap)
-        uint32_t* cov = reinterpret_cast<uint32_t*>(sm.kkey);
+        uint32_t* cov = reinterpret_cast<uint32_t*>(sm.kkey);          // read_coverage bit vector
         const uint32_t cov_words = (L + 31) / 32;
         for (uint32_t x = 0; x < cov_words; x++) cov[x] = 0;
         for (uint32_t i = 0; i < M; i++) {
@@ -284,15 +310,13 @@ __device__ inline uint32_t seed_read(const DevIndex& ix, const MapParamsDev& P, 
                 const uint32_t cs = fwd < P.minimizer_coverage_flank ? 0 : fwd - P.minimizer_coverage_flank;
                 const uint32_t ce = min(L, fwd + k + P.minimizer_coverage_flank);
                 if (num_minimizers < max(P.max_unique_min, num_min_by_read_len)) {
-                    for (uint32_t x = cs; x < ce; x++) cov[x >> 5] |= 1u << (x & 31);
+                    set_bit_range(cov, cs, ce);
                     worst_kept_hits = max(hits, worst_kept_hits);
                 } else if (hits > worst_kept_hits) {
                     passing = false;
                 } else {
-                    bool covered = false;
-                    for (uint32_t x = cs; x < ce; x++) if (cov[x >> 5] & (1u << (x & 31))) { covered = true; break; }
-                    if (covered) passing = false;
-                    else for (uint32_t x = cs; x < ce; x++) cov[x >> 5] |= 1u << (x & 31);
+                    if (any_bit_in_range(cov, cs, ce)) passing = false;
+                    else set_bit_range(cov, cs, ce);
                 }
             }
             if (passing && use_fraction) {                                  // hit-cap||score-fraction
@@ -306,18 +330,18 @@ __device__ inline uint32_t seed_read(const DevIndex& ix, const MapParamsDev& P, 
     total_hits = __shfl_sync(FULL, total_hits, 0);
     __syncwarp();
 
-    // ---- minimizer records (score order) for the MAPQ cap ------------------------------------------------
+    // ---- minimizer records (score order) -------------------------------------------------------------------
     uint32_t min_off = 0;
     if (lane == 0) min_off = atomicAdd(pools.min_cursor, M);
     min_off = __shfl_sync(FULL, min_off, 0);
     if (min_off + M > pools.min_cap) return GB_ITEM_OUT_FULL;
     for (uint32_t i = lane; i < M; i += 32) {
         const uint32_t a = sm.m_order[i];
-        DevMinimizer dm; dm.hash = sm.m_hash[a]; dm.fwd_offset = sm.m_fwd[a]; dm.agg_start = sm.m_agg_start[a]; dm.agg_len = sm.m_agg_len[a]; dm.pad = 0;
+        DevMinimizer dm; dm.hash = sm.m_hash[a]; dm.score = sm.m_score[a]; dm.fwd_offset = sm.m_fwd[a];
+        dm.agg_start = sm.m_agg_start[a]; dm.agg_len = sm.m_agg_len[a]; dm.is_reverse = sm.m_rev[a]; dm.pad[0] = dm.pad[1] = 0;
         pools.minimizers[min_off + i] = dm;
     }
     rs.min_off = min_off; rs.min_cnt = M;
-    rs.rng = rng;
     if (total_hits == 0) return GB_ITEM_OK;
 
     // ---- seeds ----------------------------------------------------------------------------------------------
@@ -339,7 +363,6 @@ __device__ inline uint32_t seed_read(const DevIndex& ix, const MapParamsDev& P, 
                 const uint2 pw = __ldg(reinterpret_cast<const uint2*>(hp));
                 const uint2 p1 = __ldg(reinterpret_cast<const uint2*>(hp) + 1);
                 const uint2 p2 = __ldg(reinterpret_cast<const uint2*>(hp) + 2);
-                uint4 pl; pl.x = p1.x; pl.y = p1.y; pl.z = p2.x; pl.w = p2.y;
                 const uint64_t pos = ((uint64_t)pw.y << 32) | pw.x;
                 uint32_t node = (uint32_t)(pos >> 10), off = (uint32_t)(pos & 1023u);
                 const uint32_t nlen = load_node(ix, node).len;
@@ -347,9 +370,9 @@ __device__ inline uint32_t seed_read(const DevIndex& ix, const MapParamsDev& P, 
                 const uint32_t off_f = (node & 1u) ? nlen - 1 - off : off;
                 DevSeed s;
                 s.node = node; s.offset = off; s.source = i; s.label = wpos + j;
-                s.c_in = (int32_t)pl.x + (int32_t)off_f;
-                s.c_out = (int32_t)pl.y - (int32_t)(nlen - off_f);
-                s.slot = pl.z;
+                s.c_in = (int32_t)p1.x + (int32_t)off_f;
+                s.c_out = (int32_t)p1.y - (int32_t)(nlen - off_f);
+                s.slot = p2.x;
                 s.id_off = ((node >> 1) << 10) | off_f;
                 seeds[wpos + j] = s;
             }
@@ -358,40 +381,48 @@ __device__ inline uint32_t seed_read(const DevIndex& ix, const MapParamsDev& P, 
     }
     rs.seed_off = seed_off; rs.seed_cnt = total_hits;
     __syncwarp();
+    return GB_ITEM_OK;
+}
 
-    // ---- clustering: label propagation to the smallest seed index of each component ---------------------------
-    const uint32_t H = total_hits;
-    const int32_t limit = (int32_t)max(P.distance_limit, L + 50);      // get_distance_limit, minimizer_mapper.hpp:554
+// Label propagation: every seed's label becomes the smallest label reachable within `limit`.
+__device__ inline void propagate_labels(DevSeed* seeds_a, uint32_t na, DevSeed* seeds_b, uint32_t nb, int32_t limit) {
+    const int lane = lane_id();
+    const uint32_t n = na + nb;
     while (true) {
         bool changed = false;
-        for (uint32_t i = lane; i < H; i += 32) {
-            const DevSeed si = seeds[i];
+        for (uint32_t i = lane; i < n; i += 32) {
+            DevSeed* pi = i < na ? seeds_a + i : seeds_b + (i - na);
+            const DevSeed si = *pi;
             uint32_t best = si.label;
-            for (uint32_t j = 0; j < H; j++) {
+            for (uint32_t j = 0; j < n; j++) {
                 if (j == i) continue;
-                const DevSeed sj = seeds[j];
+                const DevSeed sj = j < na ? seeds_a[j] : seeds_b[j - na];
                 if (sj.label < best && seeds_within(si, sj, limit)) best = sj.label;
             }
-            if (best != si.label) { seeds[i].label = best; changed = true; }
+            if (best != si.label) { pi->label = best; changed = true; }
         }
         __syncwarp();
         if (!__any_sync(FULL, changed)) break;
     }
+}
 
-    // ---- clusters in order of their first seed; score_cluster ---------------------------------------------------
-    uint32_t C = 0;
+// Clusters of one read in order of their first seed + score_cluster (:4738-4780).
+// Cluster c of this read is stored at table index cbase + c.  Returns C, or 0xffffffff on overflow.
+__device__ inline uint32_t collect_clusters(const SeedSmem& sm, const DevSeed* seeds, uint32_t H, const DevMinimizer* mins, uint32_t M,
+                                            uint32_t k, uint32_t L, uint32_t cbase) {
+    const int lane = lane_id();
+    uint32_t Cn = 0;
     for (uint32_t base = 0; base < H; base += 32) {
         const uint32_t i = base + lane;
         const bool root = i < H && seeds[i].label == i;
         const uint32_t bal = __ballot_sync(FULL, root);
-        if (C + __popc(bal) > MAX_CLUSTERS) return GB_ITEM_OUT_FULL;
-        if (root) sm.c_label[C + __popc(bal & ((1u << lane) - 1u))] = i;
-        C += __popc(bal);
+        if (Cn + __popc(bal) > MAX_CLUSTERS) return 0xffffffffu;
+        if (root) sm.c_label[cbase + Cn + __popc(bal & ((1u << lane) - 1u))] = i;
+        Cn += __popc(bal);
     }
     __syncwarp();
-    rs.n_clusters = C;
-    for (uint32_t c = lane; c < C; c += 32) {
-        const uint32_t label = sm.c_label[c];
+    for (uint32_t c = lane; c < Cn; c += 32) {
+        const uint32_t label = sm.c_label[cbase + c];
         uint32_t present[PRESENT_WORDS];
 #pragma unroll
         for (uint32_t x = 0; x < PRESENT_WORDS; x++) present[x] = 0;
@@ -402,79 +433,35 @@ __device__ inline uint32_t seed_read(const DevIndex& ix, const MapParamsDev& P, 
         for (uint32_t x = 0; x < 16; x++) covered[x] = 0;
         for (uint32_t j = 0; j < M; j++) {
             if (!(present[j >> 5] & (1u << (j & 31)))) continue;
-            const uint32_t a = sm.m_order[j];
-            score += sm.m_score[a];
-            const uint32_t s0 = sm.m_fwd[a];
-            for (uint32_t x = s0; x < s0 + k && x < L; x++) covered[x >> 5] |= 1u << (x & 31);
+            const DevMinimizer dm = mins[j];
+            score += dm.score;
+            set_bit_range(covered, dm.fwd_offset, min(L, (uint32_t)dm.fwd_offset + k));
         }
         uint32_t cnt = 0;
 #pragma unroll
         for (uint32_t x = 0; x < 16; x++) cnt += __popc(covered[x]);
-        sm.c_score[c] = score;
-        sm.c_cov[c] = (double)cnt / (double)L;
+        sm.c_score[cbase + c] = score;
+        sm.c_cov[cbase + c] = (double)cnt / (double)L;
 #pragma unroll
-        for (uint32_t x = 0; x < PRESENT_WORDS; x++) sm.c_present[c * PRESENT_WORDS + x] = present[x];
+        for (uint32_t x = 0; x < PRESENT_WORDS; x++) sm.c_present[(cbase + c) * PRESENT_WORDS + x] = present[x];
     }
     __syncwarp();
+    return Cn;
+}
 
-    // ---- cluster selection (minimizer_mapper.cpp:655-832) --------------------------------------------------------------
-    uint32_t n_kept = 0;
-    uint8_t* kept = tmp_order;                    // scratch: kept cluster ids in processing order
-    if (lane == 0) {
-        double best_cluster_score = 0.0, second_best_cluster_score = 0.0;
-        for (uint32_t c = 0; c < C; c++) {
-            const double sc = sm.c_score[c];
-            if (sc > best_cluster_score) { second_best_cluster_score = best_cluster_score; best_cluster_score = sc; }
-            else if (sc > second_best_cluster_score) second_best_cluster_score = sc;
-        }
-        double cluster_score_cutoff = best_cluster_score - P.cluster_score_threshold;
-        if (cluster_score_cutoff - P.pad_cluster_score_threshold < second_best_cluster_score)
-            cluster_score_cutoff = min(cluster_score_cutoff, second_best_cluster_score);
-        // sort_shuffling_ties with comparator (coverage desc, then score desc); stable insertion sort
-        auto comes_before = [&](uint32_t a, uint32_t b) {
-            return (sm.c_cov[a] > sm.c_cov[b]) || (sm.c_cov[a] == sm.c_cov[b] && sm.c_score[a] > sm.c_score[b]);
-        };
-        for (uint32_t c = 0; c < C; c++) {
-            uint32_t j = c;
-            while (j > 0 && comes_before(c, sm.c_order[j - 1])) { sm.c_order[j] = sm.c_order[j - 1]; j--; }
-            sm.c_order[j] = (uint8_t)c;
-        }
-        uint32_t ties = 0;
-        while (ties < C && !comes_before(sm.c_order[0], sm.c_order[ties])) ties++;
-        for (uint32_t i = 1; i < ties; i++) {
-            const uint32_t j = rng_next(rng) % (i + 1);
-            const uint8_t t = sm.c_order[j]; sm.c_order[j] = sm.c_order[i]; sm.c_order[i] = t;
-        }
-        // process_until_threshold_e, minimizer_mapper.hpp:1617-1657
-        const double cutoff = C == 0 ? 0.0 : sm.c_cov[sm.c_order[0]] - P.cluster_coverage_threshold;
-        uint32_t unskipped = 0, kept_cluster_count = 0;
-        for (uint32_t i = 0; i < C; i++) {
-            const uint32_t c = sm.c_order[i];
-            bool process = false;
-            if (P.cluster_coverage_threshold != 0 && sm.c_cov[c] <= cutoff) process = unskipped < P.min_extensions;
-            else process = unskipped < P.max_extensions;
-            if (!process) continue;
-            // additional score filter (:746-762); escaped_threshold is always false here
-            if (P.cluster_score_threshold != 0 && sm.c_score[c] < cluster_score_cutoff && kept_cluster_count >= P.min_extensions) continue;
-            kept[n_kept++] = (uint8_t)c;
-            kept_cluster_count++; unskipped++;
-        }
-    }
-    n_kept = __shfl_sync(FULL, n_kept, 0);
-    rng.state = __shfl_sync(FULL, rng.state, 0); rng.inited = __shfl_sync(FULL, rng.inited, 0);
-    rs.rng = rng;
-    __syncwarp();
+// Emit the work items of one read for the kept clusters kept[0..n_kept) (table indices cbase + c).
+__device__ inline uint32_t emit_items(const DevIndex& ix, const SeedSmem& sm, const SeedPools& pools, const DevSeed* seeds, uint32_t H,
+                                      const DevMinimizer* mins, uint32_t read_idx, const uint8_t* kept, uint32_t n_kept, uint32_t cbase,
+                                      ReadState& rs) {
+    const int lane = lane_id();
     if (n_kept == 0) return GB_ITEM_OK;
-
-    // ---- work items: (handle, read_offset - node_offset) seeds per kept cluster ------------------------------------------
     uint32_t item_off = 0;
     if (lane == 0) item_off = atomicAdd(pools.item_cursor, n_kept);
     item_off = __shfl_sync(FULL, item_off, 0);
     if (item_off + n_kept > pools.item_cap) return GB_ITEM_OUT_FULL;
     for (uint32_t t = 0; t < n_kept; t++) {
         const uint32_t c = kept[t];
-        const uint32_t label = sm.c_label[c];
-        // count + reserve
+        const uint32_t label = sm.c_label[cbase + c];
         uint32_t cnt = 0;
         for (uint32_t i = lane; i < H; i += 32) cnt += seeds[i].label == label ? 1u : 0u;
         cnt = (uint32_t)warp_sum((int)cnt);
@@ -489,22 +476,256 @@ __device__ inline uint32_t seed_read(const DevIndex& ix, const MapParamsDev& P, 
             const uint32_t bal = __ballot_sync(FULL, mine);
             if (mine) {
                 const DevSeed s = seeds[i];
-                const uint32_t a = sm.m_order[s.source];
-                const int32_t pin = (int32_t)sm.m_fwd[a] + (sm.m_rev[a] ? (int32_t)k - 1 : 0);   // value.offset
-                gb_seed g; g.node = s.node; g.diag = pin - (int32_t)s.offset;                  // to_seed, gbwt_extender.hpp:159
+                const DevMinimizer dm = mins[s.source];
+                const int32_t pin = (int32_t)dm.fwd_offset + (dm.is_reverse ? (int32_t)ix.k - 1 : 0);   // value.offset
+                gb_seed g; g.node = s.node; g.diag = pin - (int32_t)s.offset;                      // to_seed, gbwt_extender.hpp:159
                 pools.ext_seeds[eoff + wpos + __popc(bal & ((1u << lane) - 1u))] = g;
             }
             wpos += __popc(bal);
         }
         if (lane == 0) {
-            DevItem it; it.read = read_idx; it.seed_off = eoff; it.seed_cnt = cnt; it.pad = 0;
+            DevItem it; it.read = read_idx; it.seed_off = eoff; it.seed_cnt = cnt; it.fragment = sm.c_frag[cbase + c];
 #pragma unroll
-            for (uint32_t x = 0; x < PRESENT_WORDS; x++) it.present[x] = sm.c_present[c * PRESENT_WORDS + x];
+            for (uint32_t x = 0; x < PRESENT_WORDS; x++) it.present[x] = sm.c_present[(cbase + c) * PRESENT_WORDS + x];
             pools.items[item_off + t] = it;
         }
     }
     rs.item_off = item_off; rs.item_cnt = n_kept;
     return GB_ITEM_OK;
+}
+
+// -----------------------------------------------------------------------------------------
+// Phase B, single-end: clusters, selection (minimizer_mapper.cpp:640-832), items.
+// -----------------------------------------------------------------------------------------
+__device__ inline uint32_t cluster_phase_se(const DevIndex& ix, const MapParamsDev& P, const SeedSmem& sm, uint32_t L, uint32_t read_idx,
+                                            const SeedPools& pools, DevRng& rng, ReadState& rs) {
+    const int lane = lane_id();
+    const uint32_t H = rs.seed_cnt, M = rs.min_cnt;
+    if (H == 0) return GB_ITEM_OK;
+    DevSeed* seeds = pools.seeds + rs.seed_off;
+    const DevMinimizer* mins = pools.minimizers + rs.min_off;
+    const int32_t limit = (int32_t)max(P.distance_limit, L + 50);      // get_distance_limit, minimizer_mapper.hpp:554
+    propagate_labels(seeds, H, seeds, 0, limit);
+    const uint32_t Cn = collect_clusters(sm, seeds, H, mins, M, ix.k, L, 0);
+    if (Cn == 0xffffffffu) return GB_ITEM_OUT_FULL;
+    rs.n_clusters = Cn;
+    for (uint32_t c = lane; c < Cn; c += 32) sm.c_frag[c] = 0;
+
+    uint32_t n_kept = 0;
+    uint8_t* kept = sm.scratch;
+    if (lane == 0) {
+        double best_cluster_score = 0.0, second_best_cluster_score = 0.0;
+        for (uint32_t c = 0; c < Cn; c++) {
+            const double sc = sm.c_score[c];
+            if (sc > best_cluster_score) { second_best_cluster_score = best_cluster_score; best_cluster_score = sc; }
+            else if (sc > second_best_cluster_score) second_best_cluster_score = sc;
+        }
+        double cluster_score_cutoff = best_cluster_score - P.cluster_score_threshold;
+        if (cluster_score_cutoff - P.pad_cluster_score_threshold < second_best_cluster_score)
+            cluster_score_cutoff = min(cluster_score_cutoff, second_best_cluster_score);
+        auto comes_before = [&](uint32_t a, uint32_t b) {
+            return (sm.c_cov[a] > sm.c_cov[b]) || (sm.c_cov[a] == sm.c_cov[b] && sm.c_score[a] > sm.c_score[b]);
+        };
+        for (uint32_t c = 0; c < Cn; c++) {
+            uint32_t j = c;
+            while (j > 0 && comes_before(c, sm.c_order[j - 1])) { sm.c_order[j] = sm.c_order[j - 1]; j--; }
+            sm.c_order[j] = (uint8_t)c;
+        }
+        uint32_t ties = 0;
+        while (ties < Cn && !comes_before(sm.c_order[0], sm.c_order[ties])) ties++;
+        for (uint32_t i = 1; i < ties; i++) {
+            const uint32_t j = rng_next(rng) % (i + 1);
+            const uint8_t t = sm.c_order[j]; sm.c_order[j] = sm.c_order[i]; sm.c_order[i] = t;
+        }
+        const double cutoff = Cn == 0 ? 0.0 : sm.c_cov[sm.c_order[0]] - P.cluster_coverage_threshold;
+        uint32_t unskipped = 0, kept_cluster_count = 0;
+        for (uint32_t i = 0; i < Cn; i++) {
+            const uint32_t c = sm.c_order[i];
+            bool process;
+            if (P.cluster_coverage_threshold != 0 && sm.c_cov[c] <= cutoff) process = unskipped < P.min_extensions;
+            else process = unskipped < P.max_extensions;
+            if (!process) continue;
+            if (P.cluster_score_threshold != 0 && sm.c_score[c] < cluster_score_cutoff && kept_cluster_count >= P.min_extensions) continue;
+            kept[n_kept++] = (uint8_t)c;
+            kept_cluster_count++; unskipped++;
+        }
+    }
+    n_kept = __shfl_sync(FULL, n_kept, 0);
+    rng.state = __shfl_sync(FULL, rng.state, 0); rng.inited = __shfl_sync(FULL, rng.inited, 0);
+    __syncwarp();
+    return emit_items(ix, sm, pools, seeds, H, mins, read_idx, kept, n_kept, 0, rs);
+}
+
+// -----------------------------------------------------------------------------------------
+// Phase B, paired-end: joint clustering (snarl_seed_clusterer.cpp:65-145), fragment bookkeeping
+// and per-read selection (minimizer_mapper.cpp:1561-1883).
+// -----------------------------------------------------------------------------------------
+__device__ inline uint32_t cluster_phase_pe(const DevIndex& ix, const MapParamsDev& P, const SeedSmem& sm,
+                                            uint32_t L0, uint32_t L1, uint32_t read_idx0, int32_t fragment_limit,
+                                            const SeedPools& pools, DevRng& rng, ReadState& rs0, ReadState& rs1, PairState& ps) {
+    const int lane = lane_id();
+    DevSeed* s0 = pools.seeds + rs0.seed_off; DevSeed* s1 = pools.seeds + rs1.seed_off;
+    const uint32_t H0 = rs0.seed_cnt, H1 = rs1.seed_cnt;
+    const DevMinimizer* m0 = pools.minimizers + rs0.min_off; const DevMinimizer* m1 = pools.minimizers + rs1.min_off;
+    ps.n_fragments = 0; ps.found_paired_cluster = 0;
+    if (H0 + H1 == 0) return GB_ITEM_OK;
+    const int32_t read_limit = (int32_t)max(P.distance_limit, L0 + 50);
+
+    // fragment components first (labels over the concatenation), remembered in scratch arrays
+    // of the seed records' `c_out`-independent field: we keep them in a side pass:
+    // 1) fragment pass: labels = global index over both reads
+    for (uint32_t i = lane; i < H0; i += 32) s0[i].label = i;
+    for (uint32_t i = lane; i < H1; i += 32) s1[i].label = H0 + i;
+    __syncwarp();
+    propagate_labels(s0, H0, s1, H1, fragment_limit);
+    // stash fragment labels in `slot`'s high bits?  No: keep them in the id_off-free field `source`'s
+    // upper half (source < 128).
+    for (uint32_t i = lane; i < H0; i += 32) s0[i].source |= s0[i].label << 8;
+    for (uint32_t i = lane; i < H1; i += 32) s1[i].source |= s1[i].label << 8;
+    __syncwarp();
+    // 2) read passes
+    for (uint32_t i = lane; i < H0; i += 32) s0[i].label = i;
+    for (uint32_t i = lane; i < H1; i += 32) s1[i].label = i;
+    __syncwarp();
+    propagate_labels(s0, H0, s0, 0, read_limit);
+    propagate_labels(s1, H1, s1, 0, read_limit);
+    __syncwarp();
+    // un-stash: the fragment label of each read-cluster root goes to a side table living in the
+    // (dead) k-mer scratch (khash and kkey are contiguous: >= 2 * MAX_CLUSTERS words), then the
+    // `source` fields are restored.
+    uint32_t Cn[2];
+    uint32_t* side = reinterpret_cast<uint32_t*>(sm.khash);
+    uint32_t n_roots0 = 0, n_roots1 = 0;
+    for (uint32_t base = 0; base < H0; base += 32) {
+        const uint32_t i = base + lane;
+        const bool root = i < H0 && s0[i].label == i;
+        const uint32_t bal = __ballot_sync(FULL, root);
+        if (n_roots0 + __popc(bal) > MAX_CLUSTERS) return GB_ITEM_OUT_FULL;
+        if (root) side[n_roots0 + __popc(bal & ((1u << lane) - 1u))] = s0[i].source >> 8;
+        n_roots0 += __popc(bal);
+    }
+    for (uint32_t base = 0; base < H1; base += 32) {
+        const uint32_t i = base + lane;
+        const bool root = i < H1 && s1[i].label == i;
+        const uint32_t bal = __ballot_sync(FULL, root);
+        if (n_roots1 + __popc(bal) > MAX_CLUSTERS) return GB_ITEM_OUT_FULL;
+        if (root) side[MAX_CLUSTERS + n_roots1 + __popc(bal & ((1u << lane) - 1u))] = s1[i].source >> 8;
+        n_roots1 += __popc(bal);
+    }
+    __syncwarp();
+    for (uint32_t i = lane; i < H0; i += 32) s0[i].source &= 0xffu;
+    for (uint32_t i = lane; i < H1; i += 32) s1[i].source &= 0xffu;
+    __syncwarp();
+    Cn[0] = collect_clusters(sm, s0, H0, m0, rs0.min_cnt, ix.k, L0, 0);
+    Cn[1] = collect_clusters(sm, s1, H1, m1, rs1.min_cnt, ix.k, L1, MAX_CLUSTERS);
+    if (Cn[0] == 0xffffffffu || Cn[1] == 0xffffffffu) return GB_ITEM_OUT_FULL;
+    rs0.n_clusters = Cn[0]; rs1.n_clusters = Cn[1];
+
+    // ---- fragment ids in order of first appearance; per-fragment bests; better_cluster_count --------------
+    uint8_t* kept0 = sm.scratch; uint8_t* kept1 = sm.scratch + MAX_CLUSTERS;
+    uint32_t n_kept[2] = {0, 0};
+    uint32_t status = GB_ITEM_OK;
+    if (lane == 0) {
+        // fragment renumbering (:129-141 of the clusterer wrapper)
+        uint32_t heads[2 * MAX_CLUSTERS]; uint32_t n_frag = 0;
+        for (uint32_t r = 0; r < 2; r++) for (uint32_t c = 0; c < Cn[r]; c++) {
+            const uint32_t head = side[r * MAX_CLUSTERS + c];
+            uint32_t f = 0; while (f < n_frag && heads[f] != head) f++;
+            if (f == n_frag) heads[n_frag++] = head;
+            sm.c_frag[r * MAX_CLUSTERS + c] = (uint8_t)f;
+        }
+        if (n_frag > MAX_FRAGMENTS) status = GB_ITEM_OUT_FULL;
+        else {
+            bool has_first[MAX_FRAGMENTS], has_pair[MAX_FRAGMENTS];
+            double fs[2][MAX_FRAGMENTS], fc[2][MAX_FRAGMENTS];
+            for (uint32_t f = 0; f < n_frag; f++) { has_first[f] = has_pair[f] = false; fs[0][f] = fs[1][f] = fc[0][f] = fc[1][f] = 0.0; }
+            bool found_paired_cluster = false;
+            for (uint32_t c = 0; c < Cn[0]; c++) has_first[sm.c_frag[c]] = true;
+            for (uint32_t c = 0; c < Cn[1]; c++) { const uint32_t f = sm.c_frag[MAX_CLUSTERS + c]; has_pair[f] = has_first[f]; if (has_first[f]) found_paired_cluster = true; }
+            for (uint32_t r = 0; r < 2; r++) for (uint32_t c = 0; c < Cn[r]; c++) {
+                const uint32_t t = r * MAX_CLUSTERS + c, f = sm.c_frag[t];
+                fs[r][f] = max(fs[r][f], sm.c_score[t]); fc[r][f] = max(fc[r][f], sm.c_cov[t]);
+            }
+            // better_cluster_count (:1657-1690)
+            uint8_t fo[MAX_FRAGMENTS];
+            auto total = [&](uint32_t f) { return (fc[0][f] + fc[1][f]) + (fs[0][f] + fs[1][f]); };
+            for (uint32_t f = 0; f < n_frag; f++) { uint32_t j = f; while (j > 0 && total(f) > total(fo[j - 1])) { fo[j] = fo[j - 1]; j--; } fo[j] = (uint8_t)f; }
+            {
+                uint32_t ties = 0;
+                while (ties < n_frag && !(total(fo[0]) > total(fo[ties]))) ties++;
+                for (uint32_t i = 1; i < ties; i++) { const uint32_t j = rng_next(rng) % (i + 1); const uint8_t t = fo[j]; fo[j] = fo[i]; fo[i] = t; }
+            }
+            double prev_score_sum = 0.0;
+            for (int rank = (int)n_frag - 1; rank >= 0; rank--) {
+                const uint32_t f = fo[rank];
+                if (rank == (int)n_frag - 1) ps.better_cluster_count[f] = (uint8_t)(rank + 1);
+                else {
+                    const double curr = total(f);
+                    if (curr == prev_score_sum) ps.better_cluster_count[f] = ps.better_cluster_count[fo[rank + 1]];
+                    else { ps.better_cluster_count[f] = (uint8_t)(rank + 1); prev_score_sum = curr; }
+                }
+            }
+            ps.n_fragments = n_frag; ps.found_paired_cluster = found_paired_cluster ? 1u : 0u;
+
+            // ---- per-read selection (:1723-1883) ------------------------------------------------------------------
+            for (uint32_t r = 0; r < 2; r++) {
+                const uint32_t cb = r * MAX_CLUSTERS, Cr = Cn[r];
+                double cluster_score_cutoff = 0.0, cluster_coverage_cutoff = 0.0, second_best = 0.0;
+                double best_cov = 0.0, best_cov_score = 0.0;
+                for (uint32_t c = 0; c < Cr; c++) {
+                    const double cov = sm.c_cov[cb + c], sc = sm.c_score[cb + c];
+                    if (cov > best_cov) { best_cov = cov; best_cov_score = sc; }
+                    else if (cov == best_cov) best_cov_score = max(best_cov_score, sc);
+                    cluster_coverage_cutoff = max(cluster_coverage_cutoff, cov);
+                    if (sc > cluster_score_cutoff) { second_best = cluster_score_cutoff; cluster_score_cutoff = sc; }
+                    else if (sc > second_best) second_best = sc;
+                }
+                cluster_score_cutoff -= P.cluster_score_threshold;
+                cluster_coverage_cutoff -= P.cluster_coverage_threshold;
+                if (cluster_score_cutoff - P.pad_cluster_score_threshold < second_best) cluster_score_cutoff = min(cluster_score_cutoff, second_best);
+                auto comes_before = [&](uint32_t a, uint32_t b) {
+                    const uint32_t fa = sm.c_frag[cb + a], fb = sm.c_frag[cb + b];
+                    const double coverage_a = fc[0][fa] + fc[1][fa], coverage_b = fc[0][fb] + fc[1][fb];
+                    const double score_a = fs[0][fa] + fs[1][fa], score_b = fs[0][fb] + fs[1][fb];
+                    if (has_pair[fa] != has_pair[fb]) return has_pair[fa];
+                    else if (coverage_a != coverage_b) return coverage_a > coverage_b;
+                    else if (score_a != score_b) return score_a > score_b;
+                    else if (sm.c_cov[cb + a] != sm.c_cov[cb + b]) return sm.c_cov[cb + a] > sm.c_cov[cb + b];
+                    else return sm.c_score[cb + a] > sm.c_score[cb + b];
+                };
+                uint8_t* order = sm.c_order + cb;
+                for (uint32_t c = 0; c < Cr; c++) { uint32_t j = c; while (j > 0 && comes_before(c, order[j - 1])) { order[j] = order[j - 1]; j--; } order[j] = (uint8_t)c; }
+                uint32_t ties = 0;
+                while (ties < Cr && !comes_before(order[0], order[ties])) ties++;
+                for (uint32_t i = 1; i < ties; i++) { const uint32_t j = rng_next(rng) % (i + 1); const uint8_t t = order[j]; order[j] = order[i]; order[i] = t; }
+                // process_until_threshold_c with threshold 0: everything is "good enough", max_extensions caps
+                uint32_t unskipped = 0, kept_cluster_count = 0;
+                uint8_t* kept = r == 0 ? kept0 : kept1;
+                for (uint32_t i = 0; i < Cr; i++) {
+                    const uint32_t c = order[i];
+                    if (unskipped >= P.max_extensions) continue;
+                    const uint32_t f = sm.c_frag[cb + c];
+                    const double cov = sm.c_cov[cb + c], sc = sm.c_score[cb + c];
+                    bool keep = false;
+                    if (!found_paired_cluster || has_pair[f] || (cov == best_cov && sc == best_cov_score)) {
+                        keep = true;
+                        if (P.cluster_coverage_threshold != 0 && cov < cluster_coverage_cutoff && kept_cluster_count >= P.min_extensions) keep = false;
+                        else if (P.cluster_score_threshold != 0 && sc < cluster_score_cutoff && kept_cluster_count >= P.min_extensions) keep = false;
+                    }
+                    if (keep) { kept[n_kept[r]++] = (uint8_t)c; kept_cluster_count++; unskipped++; }
+                }
+            }
+        }
+    }
+    status = __shfl_sync(FULL, status, 0);
+    n_kept[0] = __shfl_sync(FULL, n_kept[0], 0); n_kept[1] = __shfl_sync(FULL, n_kept[1], 0);
+    rng.state = __shfl_sync(FULL, rng.state, 0); rng.inited = __shfl_sync(FULL, rng.inited, 0);
+    ps.n_fragments = __shfl_sync(FULL, ps.n_fragments, 0); ps.found_paired_cluster = __shfl_sync(FULL, ps.found_paired_cluster, 0);
+    __syncwarp();
+    if (status != GB_ITEM_OK) return status;
+    uint32_t st = emit_items(ix, sm, pools, s0, H0, m0, read_idx0, kept0, n_kept[0], 0, rs0);
+    if (st != GB_ITEM_OK) return st;
+    return emit_items(ix, sm, pools, s1, H1, m1, read_idx0 + 1, kept1, n_kept[1], MAX_CLUSTERS, rs1);
 }
 
 } // namespace gb
