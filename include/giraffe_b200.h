@@ -288,6 +288,18 @@ int gb_map_batch(gb_device* dev, const gb_map_params* p,
                  uint32_t n_reads, const uint8_t* reads, const uint8_t* quals, const uint64_t* read_off,
                  gb_alignment* aln, gb_mapping* mappings, uint32_t* edits, uint8_t* status);
 
+/* Paired-end batch: MinimizerMapper::map_paired(aln1, aln2) with a finalized (forced)
+ * fragment length distribution, minimizer_mapper.hpp:100, minimizer_mapper.cpp:1462-2942
+ * (`vg giraffe --fragment-mean M --fragment-stdev S`).  Reads are interleaved: read 2i is
+ * mate 1 and read 2i+1 mate 2 of pair i, both in sequencer (inward) orientation; outputs are
+ * per read as in gb_map_batch, mate 2 reported in its input orientation, flags |= GB_ALN_PAIRED.
+ * This round builds the configuration p->max_rescue_attempts == 0 (`--rescue-attempts 0`,
+ * reference branch :2238-2287); any other value is refused with GB_ERR_ARG because
+ * attempt_rescue (:3264-3565) is not implemented yet. */
+int gb_map_paired_batch(gb_device* dev, const gb_map_params* p,
+                        uint32_t n_reads, const uint8_t* reads, const uint8_t* quals, const uint64_t* read_off,
+                        gb_alignment* aln, gb_mapping* mappings, uint32_t* edits, uint8_t* status);
+
 /* ------------------------------------------------------------------------------------
  * B3: Aligner::align_pinned(alignment, graph, pin_left = true, xdrop = true, max_gap),
  * batched over explicit haplotype trees      aligner.hpp:183, aligner.cpp:628-686,

@@ -215,9 +215,9 @@ def decode_alignment(a, maps, edits):
     return int(a["score"]), int(a["mapq"]), path
 
 
-def gpu_map(dev, reads, quals=None, params=None):
+def gpu_map(dev, reads, quals=None, params=None, paired=False):
     rbuf, qbuf, read_off = pack_reads(reads, quals)
-    return dev.map_arrays(rbuf, qbuf, read_off, params)
+    return dev.map_arrays(rbuf, qbuf, read_off, params, paired=paired)
 
 
 def compare_alignments(got, want, n, mapq_tol=1):

@@ -1,0 +1,84 @@
+"""MinimizerMapper::map_paired parity (forced fragment distribution, rescue attempts 0):
+gb_map_paired_batch on the GPU vs the oracle restatement, BASELINE.json configs[1] family."""
+import numpy as np
+import pytest
+
+import helpers as H
+from vg_b200 import capi, synth
+
+
+def _run(g, rs, params):
+    index = g.build_index()
+    dev = capi.Device(index)
+    got = H.gpu_map(dev, rs.reads, rs.quals, params, paired=True)
+    want = H.oracle_map_paired(index, rs.reads, rs.quals, params, threads=8)
+    bad = H.compare_alignments(got, want, rs.n)
+    dev.close()
+    assert not bad, f"{len(bad)} of {rs.n} reads differ; first: read {bad[0][0]}\n got={bad[0][1]}\nwant={bad[0][2]}"
+    return got, want
+
+
+def test_oracle_pairs_map_to_their_origin():
+    g = synth.make_variant_graph(length=50000, n_snp=80, n_ins=10, n_del=10, n_haps=4, seed=3)
+    index = g.build_index()
+    rs = synth.simulate_pairs(g, 200, sub_rate=0.0, seed=7)
+    aln, maps, edits, status, counters = H.oracle_map_paired(index, rs.reads, rs.quals, H.paired_params())
+    assert (aln["flags"] & capi.GB_EXT_LEFT_FULL).all()          # bit 0 = mapped
+    assert (aln["score"] == 160).all()
+    assert (aln["mapq"] == 60).mean() > 0.95
+    # mates land on opposite strands (mate 2 is reported in input orientation)
+    strands = np.array([maps[int(a["mapping_off"])]["node"] & 1 for a in aln])
+    assert (strands[0::2] != strands[1::2]).all()
+
+
+def test_paired_refuses_rescue_configuration():
+    g = synth.make_tiny_graph()
+    index = g.build_index()
+    rs = synth.simulate_pairs(g, 4, frag_mean=300, frag_sd=20, sub_rate=0.0, seed=1)
+    p = H.paired_params(300, 20)
+    p.max_rescue_attempts = 15
+    lib = H.oracle_lib()
+    with pytest.raises(AssertionError):
+        H.oracle_map_paired(index, rs.reads, rs.quals, p)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("sub_rate,seed", [(0.002, 22), (0.02, 23), (0.06, 24)])
+def test_map_paired_parity_variant_graph(sub_rate, seed):
+    g = synth.make_variant_graph(length=200000, n_snp=320, n_ins=40, n_del=40, n_haps=8, seed=2)
+    rs = synth.simulate_pairs(g, 2000, sub_rate=sub_rate, seed=seed)
+    _run(g, rs, H.paired_params())
+
+
+@pytest.mark.gpu
+def test_map_paired_parity_with_indels_and_odd_fragments():
+    g = synth.make_variant_graph(length=100000, n_snp=160, n_ins=20, n_del=20, n_haps=8, seed=21)
+    rs = synth.simulate_pairs(g, 1500, frag_mean=400, frag_sd=150, sub_rate=0.01, seed=9)   # many improper fragments
+    # sprinkle indels and a few garbage mates
+    rng = np.random.default_rng(3)
+    for i in rng.integers(0, rs.n, size=150):
+        p = int(rng.integers(10, 140))
+        rs.reads[i, p:-1] = rs.reads[i, p + 1:]
+    for i in rng.integers(0, rs.n, size=40):
+        rs.reads[i] = synth.BASES[rng.integers(0, 4, size=rs.length)]
+    _run(g, rs, H.paired_params())
+
+
+@pytest.mark.gpu
+def test_map_paired_parity_branchy_graph():
+    g = synth.make_branchy_graph(n_layers=4000, n_haps=16, seed=4)
+    rs = synth.simulate_pairs(g, 1000, sub_rate=0.005, seed=44)
+    _run(g, rs, H.paired_params())
+
+
+@pytest.mark.gpu
+def test_paired_rescue_is_refused_loudly():
+    g = synth.make_tiny_graph()
+    index = g.build_index()
+    dev = capi.Device(index)
+    rs = synth.simulate_pairs(g, 4, frag_mean=300, frag_sd=20, sub_rate=0.0, seed=1)
+    p = H.paired_params(300, 20)
+    p.max_rescue_attempts = 15
+    with pytest.raises(capi.GbError):
+        H.gpu_map(dev, rs.reads, rs.quals, p, paired=True)
+    dev.close()

@@ -124,6 +124,8 @@ def load_library() -> C.CDLL:
     lib.gb_map_params_default.restype = None
     lib.gb_map_batch.argtypes = [vp, C.POINTER(MapParams), u32, vp, vp, vp, vp, vp, vp, vp]
     lib.gb_map_batch.restype = C.c_int
+    lib.gb_map_paired_batch.argtypes = [vp, C.POINTER(MapParams), u32, vp, vp, vp, vp, vp, vp, vp]
+    lib.gb_map_paired_batch.restype = C.c_int
     lib.gb_xdrop_pinned_batch.argtypes = [vp, u32, vp, vp, vp, vp, vp, vp, vp, u32, u32, vp, vp, vp, vp, vp, vp]
     lib.gb_xdrop_pinned_batch.restype = C.c_int
     lib.gb_last_kernel_ms.argtypes = [vp]
@@ -304,8 +306,8 @@ class Device:
             out.append((int(score[i]), path))
         return out
 
-    def map_arrays(self, rbuf, qbuf, read_off, params=None):
-        """gb_map_batch on packed host arrays.  Returns (aln, mappings, edits, status)."""
+    def map_arrays(self, rbuf, qbuf, read_off, params=None, paired=False):
+        """gb_map_batch / gb_map_paired_batch on packed host arrays.  Returns (aln, mappings, edits, status)."""
         lib = load_library()
         p = params or default_map_params()
         n = len(read_off) - 1
@@ -313,10 +315,11 @@ class Device:
         maps = np.zeros(n * p.mapping_cap_per_read, dtype=mapping_dt)
         edits = np.zeros(n * p.edit_cap_per_read, dtype=np.uint32)
         status = np.zeros(n, dtype=np.uint8)
-        rc = lib.gb_map_batch(self._h, C.byref(p), n, ptr(rbuf), ptr(qbuf) if qbuf is not None else None,
-                              ptr(read_off), ptr(aln), ptr(maps), ptr(edits), ptr(status))
+        fn = lib.gb_map_paired_batch if paired else lib.gb_map_batch
+        rc = fn(self._h, C.byref(p), n, ptr(rbuf), ptr(qbuf) if qbuf is not None else None,
+                ptr(read_off), ptr(aln), ptr(maps), ptr(edits), ptr(status))
         if rc != GB_OK:
-            raise GbError(rc, "gb_map_batch")
+            raise GbError(rc, "gb_map_paired_batch" if paired else "gb_map_batch")
         return aln, maps, edits, status
 
     def close(self):

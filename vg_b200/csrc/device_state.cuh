@@ -86,7 +86,8 @@ struct gb_device {
     gb::DevBuf<uint32_t> p_cursors, p_ext_count, p_path, p_mism;
     gb::DevBuf<uint8_t> p_ext_status;
     gb::DevBuf<gb_extension> p_ext;
-    gb::DevBuf<uint8_t> ws_tail, ws_cand;
+    gb::DevBuf<uint8_t> ws_tail, ws_cand, w_reads, w_quals;
+    gb::DevBuf<gb::PairState> p_pairs;
     gb::DevBuf<uint8_t> io_reads, io_quals, io_status;
     gb::DevBuf<uint64_t> io_read_off;
     gb::DevBuf<gb_alignment> io_aln;
@@ -97,7 +98,7 @@ struct gb_device {
         ws_queue.release(); ws_arena.release();
         t_hit.release(); t_plo.release(); t_phred.release(); p_states.release(); p_min.release(); p_seeds.release();
         p_items.release(); p_ext_seeds.release(); p_cursors.release(); p_ext_count.release(); p_path.release(); p_mism.release();
-        p_ext_status.release(); p_ext.release(); ws_tail.release(); ws_cand.release();
+        p_ext_status.release(); p_ext.release(); ws_tail.release(); ws_cand.release(); w_reads.release(); w_quals.release(); p_pairs.release();
         io_reads.release(); io_quals.release(); io_status.release(); io_read_off.release(); io_aln.release(); io_maps.release(); io_edits.release();
     }
 };

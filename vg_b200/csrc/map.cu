@@ -69,350 +69,7 @@ seed_kernel(DevIndex ix, MapParamsDev P, MapBatch b, SeedPools pools) {
 // ---------------------------------------------------------------------------------------
 // K3
 // ---------------------------------------------------------------------------------------
-struct AlignArgs {
-    const DevItem* items;
-    const DevMinimizer* minimizers;
-    ExtView ev;
-    uint8_t* ws_base; size_t ws_stride;        // per-warp tail workspace
-    uint8_t* cand_base; size_t cand_stride;    // per-warp candidate buffers
-    gb_alignment* aln; gb_mapping* maps; uint32_t* edits; uint8_t* status;
-    uint32_t tb_cells;
-};
-
-constexpr uint32_t N_SLOTS = MAX_CANDS + 8;
-
-__device__ __forceinline__ double d_add_log(double x, double y) { return x > y ? x + log1p(exp(y - x)) : y + log1p(exp(x - y)); }
-__device__ __forceinline__ double d_subtract_log(double x, double y) { return x + log1p(-exp(y - x)); }
-
-__device__ inline PathBuf slot_buf(uint8_t* cand_base, uint32_t slot, uint32_t map_cap, uint32_t edit_cap) {
-    PathBuf p;
-    const size_t per = (size_t)map_cap * sizeof(gb_mapping) + (size_t)edit_cap * 4;
-    p.maps = (gb_mapping*)(cand_base + per * slot);
-    p.edits = (uint32_t*)(cand_base + per * slot + (size_t)map_cap * sizeof(gb_mapping));
-    p.n_maps = 0; p.n_edits = 0; p.map_cap = map_cap; p.edit_cap = edit_cap; p.overflow = false;
-    return p;
-}
-
-// faster_cap (minimizer_mapper.cpp:2946-3260); sequential FP64, executed uniformly.
-__device__ inline double faster_cap(const MapParamsDev& P, const DevMinimizer* mins, uint32_t k, const uint32_t* explored_mask, uint32_t M,
-                                    const uint8_t* qual, uint32_t L, uint8_t* ord /*[MAX_MINIMIZERS]*/, double* c /*[MAX_MINIMIZERS+1]*/) {
-    if (qual == nullptr) return INFINITY;
-    uint32_t n = 0;
-    for (uint32_t i = 0; i < M; i++) if (explored_mask[i >> 5] & (1u << (i & 31))) {
-        // stable insertion by (agglomeration end, agglomeration start)
-        const uint32_t ae = (uint32_t)mins[i].agg_start + mins[i].agg_len, as = mins[i].agg_start;
-        uint32_t j = n;
-        while (j > 0) {
-            const DevMinimizer& o = mins[ord[j - 1]];
-            const uint32_t oe = (uint32_t)o.agg_start + o.agg_len;
-            if (ae < oe || (ae == oe && as < o.agg_start)) { ord[j] = ord[j - 1]; j--; } else break;
-        }
-        ord[j] = (uint8_t)i; n++;
-    }
-    for (uint32_t i = 0; i <= n; i++) c[i] = -INFINITY;
-    c[0] = 0.0;
-    if (n == 0) return -c[n] * 10;
-    auto column_prob = [&](uint32_t begin, uint32_t end, uint32_t index) {
-        double p = P.phred_prob[qual[index]];
-        for (uint32_t it = begin; it != end; ++it) {
-            const DevMinimizer& m = mins[ord[it]];
-            if (!(m.fwd_offset <= index && index < (uint32_t)m.fwd_offset + k)) {
-                const uint32_t possible = min(k, min(index - m.agg_start + 1, ((uint32_t)m.agg_start + m.agg_len) - index));
-                p *= P.prob_at_least_one[((size_t)possible << 8) + (size_t)(m.hash >> 56)];
-            }
-        }
-        return p;
-    };
-    auto iteratee = [&](uint32_t left, uint32_t right, uint32_t bottom, uint32_t top) {
-        double p_here = 0.0;
-        if (left != right) {
-            double p = column_prob(bottom, top, left);
-            for (uint32_t i = left + 1; i < right; i++) { const double col_p = column_prob(bottom, top, i); p = (p + col_p - (p * col_p)); }
-            p_here = log10(p);
-        }
-        const double pv = c[bottom] + p_here;
-        for (uint32_t i = bottom + 1; i < top + 1; i++) if (c[i] < pv) c[i] = pv;
-    };
-    // for_each_agglomeration_interval (:3088-3161); the "stack" is the window [front, back) of ord
-    uint32_t front = 0, back = 1;
-    uint32_t left = mins[ord[0]].agg_start, bottom = 0;
-    auto emit_preceding = [&](uint32_t right) {
-        while (left < right) {
-            const uint32_t stack_size = back - front;
-            const DevMinimizer& f = mins[ord[front]];
-            const uint32_t stack_top_end = (uint32_t)f.agg_start + f.agg_len;
-            if (stack_top_end <= right) {
-                iteratee(left, stack_top_end, bottom, bottom + stack_size);
-                left = stack_size == 1 ? right : stack_top_end;
-                bottom += 1; front++;
-            } else {
-                iteratee(left, right, bottom, bottom + stack_size);
-                left = right;
-            }
-        }
-    };
-    for (uint32_t it = 1; it < n; it++) { emit_preceding(mins[ord[it]].agg_start); back++; }
-    emit_preceding(L);
-    return -c[n] * 10;
-}
-
-__device__ inline uint32_t align_read(const DevIndex& ix, const MapParamsDev& P, const DevScores& sc, ReadState rs,
-                                      const AlignArgs& a, const uint8_t* sread, const uint8_t* qual, uint32_t L, uint32_t read_idx,
-                                      const TailWs& ws, DpSmem dps, uint8_t* qbuf, uint8_t* cand_base,
-                                      gb_alignment& out, gb_mapping* out_maps, uint32_t* out_edits) {
-    const int lane = lane_id();
-    uint32_t status = GB_ITEM_OK;
-    DevRng rng = rs.rng;
-    const uint32_t S = rs.item_cnt;
-    if (S > MAX_SETS) return GB_ITEM_OUT_FULL;
-    const uint32_t map_cap = P.mapping_cap, edit_cap = P.edit_cap;
-
-    // candidate bookkeeping (uniform registers / local arrays)
-    int32_t cand_score[MAX_CANDS]; uint8_t cand_slot[MAX_CANDS];
-    uint32_t n_cand = 0;
-    bool slot_used[N_SLOTS];
-    for (uint32_t i = 0; i < N_SLOTS; i++) slot_used[i] = false;
-    auto alloc_slot = [&]() -> uint32_t { for (uint32_t i = 0; i < N_SLOTS; i++) if (!slot_used[i]) { slot_used[i] = true; return i; } return 0xffffffffu; };
-    uint32_t explored[PRESENT_WORDS];
-#pragma unroll
-    for (uint32_t x = 0; x < PRESENT_WORDS; x++) explored[x] = 0;
-
-    // ---- extension-set scores ------------------------------------------------------------------
-    int set_score[MAX_SETS]; uint8_t set_order[MAX_SETS];
-    for (uint32_t s = 0; s < S; s++) {
-        const uint32_t item = rs.item_off + s;
-        if (a.ev.ext_status[item] != GB_ITEM_OK) return a.ev.ext_status[item];
-        set_score[s] = score_extension_group(a.ev.ext + (size_t)item * a.ev.max_ext, a.ev.ext_count[item], L, sc.gap_open, sc.gap_extend);
-    }
-    // sort_shuffling_ties (stable, descending) + threshold walk (process_until_threshold_d, :887)
-    for (uint32_t s = 0; s < S; s++) { uint32_t j = s; while (j > 0 && set_score[s] > set_score[set_order[j - 1]]) { set_order[j] = set_order[j - 1]; j--; } set_order[j] = (uint8_t)s; }
-    {
-        uint32_t ties = 0;
-        while (ties < S && !(set_score[set_order[0]] > set_score[set_order[ties]])) ties++;
-        for (uint32_t i = 1; i < ties; i++) { const uint32_t j = rng_next(rng) % (i + 1); const uint8_t t = set_order[j]; set_order[j] = set_order[i]; set_order[i] = t; }
-    }
-    const double set_cutoff = S == 0 ? 0.0 : (double)set_score[set_order[0]] - P.extension_set_score_threshold;
-    uint32_t unskipped = 0;
-
-    PathBuf res_left = slot_buf(cand_base, N_SLOTS, map_cap, edit_cap);
-    PathBuf res_right = slot_buf(cand_base, N_SLOTS + 1, map_cap, edit_cap);
-    PathBuf scratch = slot_buf(cand_base, N_SLOTS + 2, map_cap, edit_cap);
-    PathBuf middle = slot_buf(cand_base, N_SLOTS + 3, map_cap, edit_cap);
-
-    for (uint32_t oi = 0; oi < S && status == GB_ITEM_OK; oi++) {
-        const uint32_t s = set_order[oi];
-        bool process;
-        if (P.extension_set_score_threshold != 0 && (double)set_score[s] <= set_cutoff) process = unskipped < (uint32_t)P.min_extension_sets;
-        else process = unskipped < P.max_alignments;
-        if (!process) continue;
-        if (set_score[s] < P.extension_set_min_score) continue;           // discarded by score: not counted
-        unskipped++;
-        const uint32_t item = rs.item_off + s;
-        const gb_extension* ext = a.ev.ext + (size_t)item * a.ev.max_ext;
-        const uint32_t n_ext = a.ev.ext_count[item];
-        const uint32_t* path_pool = a.ev.path_pool + (size_t)item * a.ev.path_cap;
-        const uint32_t* mism_pool = a.ev.mism_pool + (size_t)item * a.ev.mism_cap;
-
-        // best_alignments of this set: (score, slot) in order
-        int32_t ba_score[18]; uint32_t ba_slot[18]; uint32_t n_ba = 0;
-        if (n_ext > 0 && ext_full(ext[0]) && ext[0].mismatches <= 4) {
-            for (uint32_t j = 0; j < n_ext && (j == 0 || ext_full(ext[j])) && n_ba < 17; j++) {
-                const uint32_t slot = alloc_slot();
-                if (slot == 0xffffffffu) { status = GB_ITEM_OUT_FULL; break; }
-                PathBuf pb = slot_buf(cand_base, slot, map_cap, edit_cap);
-                if (lane == 0) extension_to_path(ix, ext[j], path_pool, mism_pool, sread, pb);
-                const uint32_t nm = __shfl_sync(FULL, pb.n_maps, 0), ne = __shfl_sync(FULL, pb.n_edits, 0);
-                if (__shfl_sync(FULL, (int)pb.overflow, 0)) { status = GB_ITEM_OUT_FULL; break; }
-                if (lane == 0) { ((uint32_t*)pb.maps)[2 * map_cap - 2] = nm; ((uint32_t*)pb.maps)[2 * map_cap - 1] = ne; }
-                ba_score[n_ba] = ext[j].score; ba_slot[n_ba] = slot; n_ba++;
-            }
-        } else if (P.do_dp) {
-            // ---- find_optimal_tail_alignments (:5369-5622) -----------------------------------------
-            uint32_t min_tails = 1;
-            for (uint32_t j = 0; j < n_ext; j++) if (ext_full(ext[j])) min_tails++;
-            if (min_tails < 2) min_tails = 2;
-            Pareto lf[136], rf[136]; uint32_t nl = 0, nr = 0;
-            for (uint32_t j = 0; j < n_ext && nl + 3 < 136; j++) {
-                const gb_extension& e = ext[j];
-                if (ext_full(e)) continue;
-                const int32_t left_penalty = gap_penalty1(e.read_lo, sc);
-                const int32_t mid_penalty = (int32_t)e.mism_len * (sc.match + sc.mismatch);
-                const int32_t right_penalty = gap_penalty1(L - e.read_hi, sc);
-                lf[nl++] = Pareto{e.read_hi, mid_penalty + left_penalty};
-                rf[nr++] = Pareto{L - e.read_lo, mid_penalty + right_penalty};
-                if (e.mism_len > 0) {
-                    lf[nl++] = Pareto{mism_pool[e.mism_off], left_penalty};
-                    rf[nr++] = Pareto{L - mism_pool[e.mism_off + e.mism_len - 1] - 1, right_penalty};
-                }
-            }
-            lf[nl++] = Pareto{ix.k + ix.w - 2, 0}; rf[nr++] = Pareto{ix.k + ix.w - 2, 0};
-            nl = find_pareto_frontier(lf, nl); nr = find_pareto_frontier(rf, nr);
-
-            // order extensions by score (process_until_threshold_a, :5443)
-            uint8_t eo[64]; const uint32_t ne_ = min(n_ext, 64u);
-            for (uint32_t j = 0; j < ne_; j++) { uint32_t x = j; while (x > 0 && ext[j].score > ext[eo[x - 1]].score) { eo[x] = eo[x - 1]; x--; } eo[x] = (uint8_t)j; }
-            {
-                uint32_t ties = 0;
-                while (ties < ne_ && !(ext[eo[0]].score > ext[eo[ties]].score)) ties++;
-                for (uint32_t i = 1; i < ties; i++) { const uint32_t j = rng_next(rng) % (i + 1); const uint8_t t = eo[j]; eo[j] = eo[i]; eo[i] = t; }
-            }
-            const double ecut = ne_ == 0 ? 0.0 : (double)ext[eo[0]].score - (double)P.extension_score_threshold;
-            uint32_t e_unskipped = 0;
-            uint32_t win_slot = 0xffffffffu, sec_slot = 0xffffffffu;
-            int32_t winning_score = 0, second_score = 0;
-            int64_t winning_start = 0, winning_end = 0;
-            bool partial_extension_aligned = false; int32_t threshold = -1;
-            for (uint32_t xi = 0; xi < ne_ && status == GB_ITEM_OK; xi++) {
-                const gb_extension& e = ext[eo[xi]];
-                bool eproc;
-                if (P.extension_score_threshold != 0 && (double)e.score <= ecut) eproc = e_unskipped < min_tails;
-                else eproc = true;                                   // max_local_extensions = SIZE_MAX
-                if (!eproc) continue;
-                e_unskipped++;
-                if (threshold < 0) threshold = e.score - P.extension_score_threshold;
-                if (!ext_full(e)) {
-                    if (partial_extension_aligned && e.score <= threshold) {
-                        int32_t estimate = (int32_t)L * sc.match + 2 * sc.full_length_bonus - (int32_t)e.mism_len * (sc.match + sc.mismatch);
-                        if (!(e.flags & GB_EXT_LEFT_FULL)) estimate -= flank_penalty(e.read_lo, lf, nl, sc);
-                        if (!(e.flags & GB_EXT_RIGHT_FULL)) estimate -= flank_penalty(L - e.read_hi, rf, nr, sc);
-                        if (estimate <= winning_score) continue;
-                    }
-                    partial_extension_aligned = true;
-                }
-                int32_t left_score = 0, right_score = 0;
-                pb_reset(res_left); pb_reset(res_right);
-                if (!(e.flags & GB_EXT_LEFT_FULL)) left_score = align_tail(ix, P, sc, ws, dps, e, path_pool, sread, L, true, qbuf, rng, res_left, scratch, status);
-                if (status != GB_ITEM_OK) break;
-                if (!(e.flags & GB_EXT_RIGHT_FULL)) right_score = align_tail(ix, P, sc, ws, dps, e, path_pool, sread, L, false, qbuf, rng, res_right, scratch, status);
-                if (status != GB_ITEM_OK) break;
-                const int32_t total_score = e.score + left_score + right_score;
-                const uint32_t first_node = path_pool[e.path_off], last_node = path_pool[e.path_off + e.path_len - 1];
-                uint32_t ls = 0, re = 0;
-                if (lane == 0) { ls = res_left.n_maps ? res_left.maps[0].node : first_node; re = res_right.n_maps ? res_right.maps[res_right.n_maps - 1].node : last_node; }
-                ls = __shfl_sync(FULL, ls, 0); re = __shfl_sync(FULL, re, 0);
-                const int64_t current_start = ls >> 1, current_end = re >> 1;
-                const int64_t w_start = winning_score == 0 ? 0 : winning_start, w_end = winning_score == 0 ? 0 : winning_end;
-                const bool different_left = w_start != current_start, different_right = w_end != current_end;
-                int target = 0;      // 1: becomes winner, 2: becomes second
-                if (total_score > winning_score || winning_score == 0) {
-                    if (winning_score != 0 && different_left && different_right) {
-                        if (sec_slot != 0xffffffffu) slot_used[sec_slot] = false;
-                        second_score = winning_score; sec_slot = win_slot; win_slot = 0xffffffffu;
-                    }
-                    target = 1;
-                } else if ((total_score > second_score || second_score == 0) && different_left && different_right) {
-                    target = 2;
-                }
-                if (target) {
-                    uint32_t& dst = target == 1 ? win_slot : sec_slot;
-                    if (dst != 0xffffffffu) slot_used[dst] = false;
-                    dst = alloc_slot();
-                    if (dst == 0xffffffffu) { status = GB_ITEM_OUT_FULL; break; }
-                    PathBuf pb = slot_buf(cand_base, dst, map_cap, edit_cap);
-                    if (lane == 0) {
-                        pb_reset(middle);
-                        extension_to_path(ix, e, path_pool, mism_pool, sread, middle);
-                        add_to_path(pb, res_left.maps, res_left.edits, res_left.n_maps);
-                        add_to_path(pb, middle.maps, middle.edits, middle.n_maps);
-                        add_to_path(pb, res_right.maps, res_right.edits, res_right.n_maps);
-                        if (middle.overflow) pb.overflow = true;
-                        ((uint32_t*)pb.maps)[2 * map_cap - 2] = pb.n_maps; ((uint32_t*)pb.maps)[2 * map_cap - 1] = pb.n_edits;
-                    }
-                    if (__shfl_sync(FULL, (int)pb.overflow, 0)) { status = GB_ITEM_OUT_FULL; break; }
-                    __syncwarp();
-                    if (target == 1) { winning_score = total_score; winning_start = current_start; winning_end = current_end; }
-                    else second_score = total_score;
-                }
-            }
-            if (status != GB_ITEM_OK) break;
-            // best_alignments[0] = best, [1] = second (possibly empty with score 0)
-            ba_score[0] = winning_score; ba_slot[0] = win_slot; ba_score[1] = second_score; ba_slot[1] = sec_slot; n_ba = 2;
-        }
-        if (status != GB_ITEM_OK) break;
-        // keep alignments with score != 0 and >= 0.8 * best (:1025-1028)
-        bool keep = true;
-        for (uint32_t j = 0; j < n_ba; j++) {
-            if (keep && ba_score[j] != 0 && (double)ba_score[j] >= (double)ba_score[0] * 0.8) {
-                if (n_cand >= MAX_CANDS) { status = GB_ITEM_OUT_FULL; break; }
-                cand_score[n_cand] = ba_score[j]; cand_slot[n_cand] = (uint8_t)ba_slot[j]; n_cand++;
-            } else {
-                keep = false;
-                if (ba_slot[j] != 0xffffffffu) slot_used[ba_slot[j]] = false;
-            }
-        }
-        const DevItem it = a.items[item];
-#pragma unroll
-        for (uint32_t x = 0; x < PRESENT_WORDS; x++) explored[x] |= it.present[x];
-    }
-    if (status != GB_ITEM_OK) return status;
-
-    // ---- winner (process_until_threshold_a, :1095) -----------------------------------------------------
-    double scores_sorted[MAX_CANDS + 1];
-    uint32_t n_scores = 0; uint32_t win = 0xffffffffu;
-    if (n_cand == 0) { scores_sorted[0] = 0.0; n_scores = 1; }
-    else {
-        uint8_t co[MAX_CANDS];
-        for (uint32_t c = 0; c < n_cand; c++) { uint32_t j = c; while (j > 0 && cand_score[c] > cand_score[co[j - 1]]) { co[j] = co[j - 1]; j--; } co[j] = (uint8_t)c; }
-        uint32_t ties = 0;
-        while (ties < n_cand && !(cand_score[co[0]] > cand_score[co[ties]])) ties++;
-        for (uint32_t i = 1; i < ties; i++) { const uint32_t j = rng_next(rng) % (i + 1); const uint8_t t = co[j]; co[j] = co[i]; co[i] = t; }
-        for (uint32_t c = 0; c < n_cand; c++) scores_sorted[c] = (double)cand_score[co[c]];
-        n_scores = n_cand; win = co[0];
-    }
-
-    // ---- MAPQ (:1146-1188) ----------------------------------------------------------------------------------
-    double mapq = 0.0;
-    if (win != 0xffffffffu) {
-        const double quality_scale_factor = 10.0 / log(10.0);
-        double log_sum_exp = -DBL_MAX, to_score = -DBL_MAX;
-        for (int64_t i = (int64_t)n_scores - 1; i >= 0; --i) {
-            const double score = P.log_base * scores_sorted[i];
-            if (score >= to_score) to_score = score;
-            log_sum_exp = d_add_log(log_sum_exp, score);
-        }
-        if (n_scores == 1) log_sum_exp = d_add_log(log_sum_exp, 0.0);
-        const double direct = -quality_scale_factor * d_subtract_log(0.0, to_score - log_sum_exp);
-        const double mq = isinf(direct) ? 2147483647.0 : direct;
-        mapq = (double)(int32_t)mq;
-    }
-    const double escape_bonus = mapq < 2147483647.0 ? 1.0 : 2.0;
-    // scratch for the cap lives in the DP columns (free at this point)
-    double* cbuf = reinterpret_cast<double*>(dps.Hp);
-    uint8_t* ordbuf = reinterpret_cast<uint8_t*>(dps.Ep);
-    double cap = 0.0;
-    if (lane == 0) {
-        cap = escape_bonus * faster_cap(P, a.minimizers + rs.min_off, ix.k, explored, rs.min_cnt, qual, L, ordbuf, cbuf);
-    }
-    cap = __shfl_sync(FULL, cap, 0);
-    const double mapq_uncapped = mapq;
-    mapq = round(fmin(cap, fmin(mapq, 60.0)));
-    mapq = fmax(fmin(mapq, 60.0), 0.0);
-
-    // ---- output record -----------------------------------------------------------------------------------------
-    out.read_id = read_idx; out.score = 0; out.mapq = (uint8_t)mapq; out.flags = 0; out.n_mappings = 0; out.n_edits = 0;
-    out.mapq_uncapped = (float)mapq_uncapped; out.mapq_explored_cap = (float)cap;
-    if (win != 0xffffffffu) {
-        PathBuf pb = slot_buf(cand_base, cand_slot[win], map_cap, edit_cap);
-        const uint32_t nm = ((uint32_t*)pb.maps)[2 * map_cap - 2], ne = ((uint32_t*)pb.maps)[2 * map_cap - 1];
-        if (nm + 1 > map_cap || ne > edit_cap) return GB_ITEM_OUT_FULL;
-        out.score = cand_score[win]; out.flags = nm ? GB_ALN_MAPPED : 0; out.n_mappings = (uint16_t)nm; out.n_edits = ne;
-        if (lane == 0) {
-            // copy; substitution bases are (re)read from the read so both strands agree with the Edit.sequence rule
-            uint32_t qoff = 0, e = 0;
-            for (uint32_t i = 0; i < nm; i++) {
-                out_maps[i] = pb.maps[i];
-                for (uint32_t x = 0; x < pb.maps[i].n_edits; x++, e++) {
-                    uint32_t wd = pb.edits[e]; const uint32_t op = wd & 3u, len = wd >> 4;
-                    if (op == GB_EDIT_SUB) { wd = (1u << 4) | (base2(sread[qoff]) << 2) | GB_EDIT_SUB; qoff += 1; }
-                    else if (op == GB_EDIT_MATCH || op == GB_EDIT_INS) qoff += len;
-                    out_edits[e] = wd;
-                }
-            }
-        }
-    }
-    __syncwarp();
-    return GB_ITEM_OK;
-}
+#include "align_read.cuh"
 
 __global__ void __launch_bounds__(ALIGN_WARPS * 32)
 align_kernel(DevIndex ix, MapParamsDev P, DevScores sc, MapBatch b, AlignArgs a) {
@@ -455,6 +112,8 @@ align_kernel(DevIndex ix, MapParamsDev P, DevScores sc, MapBatch b, AlignArgs a)
     }
 }
 
+#include "map_paired.cuh"
+
 // AlignmentScorer::recover_log_base (alignment_scorer.cpp:30-99), gc 0.5, tol 1e-12.
 static double recover_log_base(const DevScores& s) {
     auto partition = [&](double lambda) {
@@ -491,8 +150,12 @@ namespace gb {
 // Device-resident mapping of a batch whose reads are already in HBM.
 int map_device(gb_device* d, const gb_map_params* hp, uint32_t n_reads, const uint8_t* d_reads, const uint8_t* d_quals,
                const uint64_t* d_read_off, uint32_t max_len, uint64_t total_bases,
-               gb_alignment* d_aln, gb_mapping* d_maps, uint32_t* d_edits, uint8_t* d_status) {
-    (void)total_bases;
+               gb_alignment* d_aln, gb_mapping* d_maps, uint32_t* d_edits, uint8_t* d_status, bool paired) {
+    if (paired) {
+        if (n_reads % 2 != 0) { g_last_error = "paired mapping needs an even number of reads"; return GB_ERR_ARG; }
+        if (hp->max_rescue_attempts != 0) { g_last_error = "paired mapping is built for max_rescue_attempts = 0 (vg giraffe --rescue-attempts 0); rescue is not implemented"; return GB_ERR_ARG; }
+        if (!(hp->fragment_stdev > 0)) { g_last_error = "paired mapping needs a forced fragment length distribution"; return GB_ERR_ARG; }
+    }
     if (hp->max_multimaps != 1) { g_last_error = "only max_multimaps = 1 is supported"; return GB_ERR_ARG; }
     const uint32_t Lc = std::max<uint32_t>(32u, (max_len + 15u) & ~15u);
     if (Lc > 512) { g_last_error = "reads longer than 512 bp are not supported by the short-read path"; return GB_ERR_ARG; }
@@ -537,6 +200,21 @@ int map_device(gb_device* d, const gb_map_params* hp, uint32_t n_reads, const ui
     GB_CUDA(cudaMemsetAsync(d->p_cursors.ptr, 0, 16 * sizeof(uint32_t), d->stream));
     uint32_t* cur = d->p_cursors.ptr;   // 0 seed work, 1 min, 2 seed, 3 item, 4 ext, 5 extend work, 6 align work
 
+    int32_t fragment_limit = 0;
+    if (paired) {
+        // rightward working copy of the reads (mate 2 reverse-complemented), :1503-1506
+        int rcw;
+        if ((rcw = d->w_reads.reserve(total_bases ? total_bases : 1))) return rcw;
+        if (d_quals) { if ((rcw = d->w_quals.reserve(total_bases ? total_bases : 1))) return rcw; }
+        prep_pairs_kernel<<<d->n_sms * 8, 256, 0, d->stream>>>(d_reads, d_quals, d_read_off, n_reads, d->w_reads.ptr, d_quals ? d->w_quals.ptr : nullptr);
+        d->launches++;
+        GB_CUDA(cudaGetLastError());
+        d_reads = d->w_reads.ptr; if (d_quals) d_quals = d->w_quals.ptr;
+        fragment_limit = (int32_t)(int64_t)(hp->fragment_mean + hp->paired_distance_stdevs * hp->fragment_stdev);   // :1470
+        const uint32_t read_limit = std::max<uint32_t>(hp->distance_limit, max_len + 50);
+        if (fragment_limit < (int32_t)read_limit) { g_last_error = "fragment distance limit smaller than the read distance limit (the reference falls back to single-end, :1471)"; return GB_ERR_ARG; }
+        if ((rcw = d->p_pairs.reserve(n_reads / 2))) return rcw;
+    }
     MapBatch b; b.reads = d_reads; b.quals = d_quals; b.read_off = d_read_off; b.n_reads = n_reads;
     b.states = d->p_states.ptr; b.work_counter = cur + 0; b.Lc = Lc;
     SeedPools pools;
@@ -548,13 +226,19 @@ int map_device(gb_device* d, const gb_map_params* hp, uint32_t n_reads, const ui
     // ---- K1 ----
     {
         const size_t smem = seed_smem_bytes(Lc) * SEED_WARPS;
-        if (smem > 48 * 1024) GB_CUDA(cudaFuncSetAttribute(seed_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        if (smem > 48 * 1024) {
+            GB_CUDA(cudaFuncSetAttribute(seed_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            GB_CUDA(cudaFuncSetAttribute(seed_kernel_pe, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        }
         int bps = 0;
-        GB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bps, seed_kernel, SEED_WARPS * 32, smem));
+        if (paired) GB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bps, seed_kernel_pe, SEED_WARPS * 32, smem));
+        else GB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bps, seed_kernel, SEED_WARPS * 32, smem));
         if (bps < 1) bps = 1;
         uint32_t grid = std::min<uint32_t>((uint32_t)(d->n_sms * bps), (n_reads + SEED_WARPS - 1) / SEED_WARPS);
         if (grid == 0) grid = 1;
-        seed_kernel<<<grid, SEED_WARPS * 32, smem, d->stream>>>(d->ix, P, b, pools);
+        if (paired) { PairBatch pbatch; pbatch.pairs = d->p_pairs.ptr; pbatch.fragment_limit = fragment_limit;
+                      seed_kernel_pe<<<grid, SEED_WARPS * 32, smem, d->stream>>>(d->ix, P, b, pools, pbatch); }
+        else seed_kernel<<<grid, SEED_WARPS * 32, smem, d->stream>>>(d->ix, P, b, pools);
         d->launches++;
         GB_CUDA(cudaGetLastError());
     }
@@ -576,11 +260,15 @@ int map_device(gb_device* d, const gb_map_params* hp, uint32_t n_reads, const ui
     // ---- K3 ----
     {
         const uint32_t W = Lc + 1;
-        const size_t per_warp = (((size_t)Lc * 3 + 15) & ~(size_t)15) + (size_t)W * 4 * 4 + 64;
+        const size_t per_warp = (((size_t)Lc * (paired ? 5 : 3) + 15) & ~(size_t)15) + (size_t)W * 4 * 4 + 64;
         const size_t smem = per_warp * ALIGN_WARPS;
-        if (smem > 48 * 1024) GB_CUDA(cudaFuncSetAttribute(align_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        if (smem > 48 * 1024) {
+            GB_CUDA(cudaFuncSetAttribute(align_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            GB_CUDA(cudaFuncSetAttribute(align_kernel_pe, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        }
         int bps = 0;
-        GB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bps, align_kernel, ALIGN_WARPS * 32, smem));
+        if (paired) GB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bps, align_kernel_pe, ALIGN_WARPS * 32, smem));
+        else GB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bps, align_kernel, ALIGN_WARPS * 32, smem));
         if (bps < 1) bps = 1;
         if (bps > 2) bps = 2;
         uint32_t grid = std::min<uint32_t>((uint32_t)(d->n_sms * bps), (n_reads + ALIGN_WARPS - 1) / ALIGN_WARPS);
@@ -588,7 +276,7 @@ int map_device(gb_device* d, const gb_map_params* hp, uint32_t n_reads, const ui
         const size_t n_warps = (size_t)grid * ALIGN_WARPS;
         const uint32_t tb_cells = hp->max_dozeu_cells + hp->max_dozeu_cells / 4 + 4096;
         const size_t ws_stride = tail_ws_bytes(Lc, tb_cells);
-        const size_t cand_stride = (((size_t)hp->mapping_cap_per_read * sizeof(gb_mapping) + (size_t)hp->edit_cap_per_read * 4) * (N_SLOTS + 4) + 255) & ~(size_t)255;
+        const size_t cand_stride = (((size_t)hp->mapping_cap_per_read * sizeof(gb_mapping) + (size_t)hp->edit_cap_per_read * 4) * (N_SLOTS + N_TEMP_SLOTS) + 255) & ~(size_t)255;
         if ((rc = d->ws_tail.reserve(ws_stride * n_warps))) return rc;
         if ((rc = d->ws_cand.reserve(cand_stride * n_warps))) return rc;
         AlignArgs a;
@@ -597,8 +285,10 @@ int map_device(gb_device* d, const gb_map_params* hp, uint32_t n_reads, const ui
         a.ev.path_pool = d->p_path.ptr; a.ev.mism_pool = d->p_mism.ptr; a.ev.max_ext = max_ext; a.ev.path_cap = path_cap; a.ev.mism_cap = mism_cap;
         a.ws_base = d->ws_tail.ptr; a.ws_stride = ws_stride; a.cand_base = d->ws_cand.ptr; a.cand_stride = cand_stride;
         a.aln = d_aln; a.maps = d_maps; a.edits = d_edits; a.status = d_status; a.tb_cells = tb_cells;
+        a.pairs = paired ? d->p_pairs.ptr : nullptr; a.frag_mean = hp->fragment_mean; a.frag_sd = hp->fragment_stdev;
         MapBatch b3 = b; b3.work_counter = cur + 6;
-        align_kernel<<<grid, ALIGN_WARPS * 32, smem, d->stream>>>(d->ix, P, d->sc, b3, a);
+        if (paired) align_kernel_pe<<<grid, ALIGN_WARPS * 32, smem, d->stream>>>(d->ix, P, d->sc, b3, a);
+        else align_kernel<<<grid, ALIGN_WARPS * 32, smem, d->stream>>>(d->ix, P, d->sc, b3, a);
         d->launches++;
         GB_CUDA(cudaGetLastError());
     }
@@ -607,7 +297,7 @@ int map_device(gb_device* d, const gb_map_params* hp, uint32_t n_reads, const ui
 
 } // namespace gb
 
-extern "C" int gb_map_batch(gb_device* d, const gb_map_params* hp,
+static int map_batch_host(gb_device* d, const gb_map_params* hp, bool paired,
                             uint32_t n_reads, const uint8_t* reads, const uint8_t* quals, const uint64_t* read_off,
                             gb_alignment* aln, gb_mapping* mappings, uint32_t* edits, uint8_t* status) {
     if (!d || !hp || !reads || !read_off || !aln || !mappings || !edits || !status) return GB_ERR_ARG;
@@ -626,7 +316,7 @@ extern "C" int gb_map_batch(gb_device* d, const gb_map_params* hp,
     if ((rc = d->io_status.reserve(n_reads))) return rc;
     GB_CUDA(cudaEventRecord(d->ev0, d->stream));
     if ((rc = map_device(d, hp, n_reads, d->io_reads.ptr, quals ? d->io_quals.ptr : nullptr, d->io_read_off.ptr, max_len, total,
-                         d->io_aln.ptr, d->io_maps.ptr, d->io_edits.ptr, d->io_status.ptr))) return rc;
+                         d->io_aln.ptr, d->io_maps.ptr, d->io_edits.ptr, d->io_status.ptr, paired))) return rc;
     GB_CUDA(cudaEventRecord(d->ev1, d->stream));
     GB_CUDA(cudaMemcpyAsync(aln, d->io_aln.ptr, sizeof(gb_alignment) * n_reads, cudaMemcpyDeviceToHost, d->stream));
     GB_CUDA(cudaMemcpyAsync(mappings, d->io_maps.ptr, sizeof(gb_mapping) * (size_t)n_reads * hp->mapping_cap_per_read, cudaMemcpyDeviceToHost, d->stream));
@@ -635,6 +325,18 @@ extern "C" int gb_map_batch(gb_device* d, const gb_map_params* hp,
     GB_CUDA(cudaStreamSynchronize(d->stream));
     GB_CUDA(cudaEventElapsedTime(&d->last_kernel_ms, d->ev0, d->ev1));
     return GB_OK;
+}
+
+extern "C" int gb_map_batch(gb_device* d, const gb_map_params* hp,
+                            uint32_t n_reads, const uint8_t* reads, const uint8_t* quals, const uint64_t* read_off,
+                            gb_alignment* aln, gb_mapping* mappings, uint32_t* edits, uint8_t* status) {
+    return map_batch_host(d, hp, false, n_reads, reads, quals, read_off, aln, mappings, edits, status);
+}
+
+extern "C" int gb_map_paired_batch(gb_device* d, const gb_map_params* hp,
+                                   uint32_t n_reads, const uint8_t* reads, const uint8_t* quals, const uint64_t* read_off,
+                                   gb_alignment* aln, gb_mapping* mappings, uint32_t* edits, uint8_t* status) {
+    return map_batch_host(d, hp, true, n_reads, reads, quals, read_off, aln, mappings, edits, status);
 }
 
 // ---------------------------------------------------------------------------------------
