@@ -282,11 +282,14 @@ void gb_map_params_default(gb_map_params* p);
 /* Single-end batch.  reads/quals are concatenated bytes addressed by read_off[n_reads+1]
  * (quals = raw Phred bytes, may be NULL: then the explored-minimizer cap is +inf as in
  * minimizer_mapper.cpp:2950).  One primary alignment per read (max_multimaps = 1):
- * aln[n_reads], mappings[n_reads * mapping_cap_per_read], edits[n_reads * edit_cap_per_read],
- * status[n_reads]. */
+ * aln[n_reads] and status[n_reads]; mappings / edits are DENSE pools of the given capacities
+ * (gb_alignment.mapping_off / edit_off index into them); the elements used are returned
+ * through n_mappings_used / n_edits_used (may be NULL).  GB_ERR_CAPACITY if a pool is too
+ * small.  Internally the batch is processed in chunks of 2^20 reads. */
 int gb_map_batch(gb_device* dev, const gb_map_params* p,
                  uint32_t n_reads, const uint8_t* reads, const uint8_t* quals, const uint64_t* read_off,
-                 gb_alignment* aln, gb_mapping* mappings, uint32_t* edits, uint8_t* status);
+                 gb_alignment* aln, gb_mapping* mappings, uint64_t mapping_pool_cap, uint32_t* edits, uint64_t edit_pool_cap,
+                 uint8_t* status, uint64_t* n_mappings_used, uint64_t* n_edits_used);
 
 /* Paired-end batch: MinimizerMapper::map_paired(aln1, aln2) with a finalized (forced)
  * fragment length distribution, minimizer_mapper.hpp:100, minimizer_mapper.cpp:1462-2942
@@ -298,7 +301,24 @@ int gb_map_batch(gb_device* dev, const gb_map_params* p,
  * attempt_rescue (:3264-3565) is not implemented yet. */
 int gb_map_paired_batch(gb_device* dev, const gb_map_params* p,
                         uint32_t n_reads, const uint8_t* reads, const uint8_t* quals, const uint64_t* read_off,
-                        gb_alignment* aln, gb_mapping* mappings, uint32_t* edits, uint8_t* status);
+                        gb_alignment* aln, gb_mapping* mappings, uint64_t mapping_pool_cap, uint32_t* edits, uint64_t edit_pool_cap,
+                        uint8_t* status, uint64_t* n_mappings_used, uint64_t* n_edits_used);
+
+/* Device-pointer variant of both (paired != 0 selects map_paired): every pointer is a DEVICE
+ * address (inputs already resident in HBM, outputs stay in HBM); all reads are at most
+ * max_read_len long; d_totals[2] (device) receives {mappings used, edits used}.  The call only
+ * enqueues work on the handle's stream (gb_device_set_stream) and returns; use
+ * gb_device_synchronize or stream ordering before reading the outputs. */
+int gb_map_batch_device(gb_device* dev, const gb_map_params* p, int paired, uint32_t n_reads,
+                        const uint8_t* d_reads, const uint8_t* d_quals, const uint64_t* d_read_off, uint32_t max_read_len,
+                        gb_alignment* d_aln, gb_mapping* d_mappings, uint64_t mapping_pool_cap, uint32_t* d_edits, uint64_t edit_pool_cap,
+                        uint8_t* d_status, uint64_t* d_totals);
+
+/* Run this handle's work on the caller's CUDA stream (cudaStream_t; NULL = the handle's own). */
+int gb_device_set_stream(gb_device* dev, void* cuda_stream);
+int gb_device_synchronize(gb_device* dev);
+/* Device time of the four stages of the last mapping call (seed+cluster, extend, align, compact), ms. */
+int gb_stage_times(gb_device* dev, float* ms4);
 
 /* ------------------------------------------------------------------------------------
  * B3: Aligner::align_pinned(alignment, graph, pin_left = true, xdrop = true, max_gap),

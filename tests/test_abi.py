@@ -1,0 +1,113 @@
+"""The C-ABI shared library loads without a GPU, exports every entry point declared in
+include/giraffe_b200.h, and refuses compute loudly when there is no CUDA device."""
+import ctypes as C
+import re
+from pathlib import Path
+
+import numpy as np
+import pytest
+
+import helpers as H
+from vg_b200 import capi, synth
+
+ROOT = Path(__file__).resolve().parent.parent
+
+
+def declared_symbols():
+    text = (ROOT / "include" / "giraffe_b200.h").read_text()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    return sorted(set(re.findall(r"\b(gb_[a-z0-9_]+)\s*\(", text)))
+
+
+def test_every_declared_symbol_is_exported():
+    lib = capi.load_library()
+    names = declared_symbols()
+    assert len(names) >= 15
+    for name in names:
+        assert hasattr(lib, name), f"{name} is declared in include/giraffe_b200.h but not exported"
+
+
+def test_struct_sizes_match_the_header():
+    assert capi.node_rec_dt.itemsize == 16 and capi.hit_dt.itemsize == 24 and capi.extension_dt.itemsize == 64
+    assert capi.alignment_dt.itemsize == 32 and capi.mapping_dt.itemsize == 8
+    assert C.sizeof(capi.MapParams) == C.sizeof(H.MapParams)
+    p = capi.default_map_params()
+    q = H.MapParams()
+    H.oracle_lib().oracle_map_params_default.argtypes = [C.POINTER(H.MapParams)]
+    H.oracle_lib().oracle_map_params_default(C.byref(q))
+    assert bytes(p) == bytes(q), "library and oracle disagree on the MinimizerMapper defaults"
+    assert (p.hit_cap, p.hard_hit_cap, p.max_extension_mismatches, p.max_alignments, p.distance_limit) == (10, 500, 4, 8, 200)
+
+
+def test_no_cpu_fallback_without_a_device():
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("a GPU is present")
+    g = synth.make_tiny_graph()
+    index = g.build_index()
+    with pytest.raises(capi.GbError) as e:
+        capi.Device(index)
+    assert e.value.code == capi.GB_ERR_NO_DEVICE
+
+
+def test_index_builder_arrays_are_consistent():
+    g = synth.make_variant_graph(length=5000, n_snp=20, n_ins=4, n_del=4, n_haps=4, seed=5)
+    index = g.build_index()
+    nodes = index.array("nodes")
+    assert nodes["len"][2::2].tolist() == [len(s) for s in g.node_seqs]
+    seq = index.array("seq")
+    for nid in (1, 2, len(g.node_seqs)):
+        v = 2 * nid
+        fwd = bytes(seq[nodes["seq_off"][v]: nodes["seq_off"][v] + nodes["len"][v]])
+        rev = bytes(seq[nodes["seq_off"][v + 1]: nodes["seq_off"][v + 1] + nodes["len"][v + 1]])
+        assert fwd.decode() == g.node_seqs[nid - 1]
+        assert rev == bytes(synth.revcomp_bytes(np.frombuffer(fwd, dtype=np.uint8)))
+    # every haplotype visit is in exactly one record, both orientations
+    assert int(nodes["size"].sum()) == 2 * sum(len(p) for p in g.paths)
+    table = index.array("table")
+    hits = index.array("hits")
+    used = table[table["key"] != np.uint64(0xFFFFFFFFFFFFFFFF)]
+    assert int(used["hit_cnt"].sum()) == len(hits)
+
+
+def test_distance_payload_matches_bruteforce_shortest_paths():
+    """The 16-byte payload reproduces minimum graph distances (Dijkstra over the graph edges)."""
+    import heapq
+    g = synth.make_variant_graph(length=2500, n_snp=10, n_ins=4, n_del=4, n_haps=6, seed=17)
+    lens = [0] + [len(s) for s in g.node_seqs]
+    # edges of the variation graph itself (every allele, as the distance index sees it; the
+    # haplotypes may not use all of them)
+    succ = {}
+    frontier = set()
+    for alleles in g.slots:
+        nxt = set(a for a in alleles if a)
+        for v in nxt:
+            for u in frontier:
+                succ.setdefault(u, set()).add(v)
+        if 0 in alleles:
+            nxt |= frontier
+        frontier = nxt
+    dist = g.dist
+
+    def brute(u):
+        # distance from the END of u to the START of every reachable node
+        best = {}
+        pq = [(0, v) for v in succ.get(u, ())]
+        heapq.heapify(pq)
+        while pq:
+            d, v = heapq.heappop(pq)
+            if v in best:
+                continue
+            best[v] = d
+            for w in succ.get(v, ()):
+                if w not in best:
+                    heapq.heappush(pq, (d + lens[v], w))
+        return best
+
+    rng = np.random.default_rng(2)
+    for u in rng.integers(1, len(g.node_seqs) + 1, size=60):
+        u = int(u)
+        best = brute(u)
+        for v, d in best.items():
+            if dist[v]["slot"] > dist[u]["slot"]:
+                assert int(dist[v]["x_in"]) - int(dist[u]["x_out"]) == d, (u, v)

@@ -122,9 +122,17 @@ def load_library() -> C.CDLL:
     lib.gb_extend_batch.restype = C.c_int
     lib.gb_map_params_default.argtypes = [C.POINTER(MapParams)]
     lib.gb_map_params_default.restype = None
-    lib.gb_map_batch.argtypes = [vp, C.POINTER(MapParams), u32, vp, vp, vp, vp, vp, vp, vp]
+    lib.gb_map_batch.argtypes = [vp, C.POINTER(MapParams), u32, vp, vp, vp, vp, vp, u64, vp, u64, vp, vp, vp]
     lib.gb_map_batch.restype = C.c_int
-    lib.gb_map_paired_batch.argtypes = [vp, C.POINTER(MapParams), u32, vp, vp, vp, vp, vp, vp, vp]
+    lib.gb_map_paired_batch.argtypes = [vp, C.POINTER(MapParams), u32, vp, vp, vp, vp, vp, u64, vp, u64, vp, vp, vp]
+    lib.gb_map_batch_device.argtypes = [vp, C.POINTER(MapParams), C.c_int, u32, vp, vp, vp, u32, vp, vp, u64, vp, u64, vp, vp]
+    lib.gb_map_batch_device.restype = C.c_int
+    lib.gb_device_set_stream.argtypes = [vp, vp]
+    lib.gb_device_set_stream.restype = C.c_int
+    lib.gb_device_synchronize.argtypes = [vp]
+    lib.gb_device_synchronize.restype = C.c_int
+    lib.gb_stage_times.argtypes = [vp, vp]
+    lib.gb_stage_times.restype = C.c_int
     lib.gb_map_paired_batch.restype = C.c_int
     lib.gb_xdrop_pinned_batch.argtypes = [vp, u32, vp, vp, vp, vp, vp, vp, vp, u32, u32, vp, vp, vp, vp, vp, vp]
     lib.gb_xdrop_pinned_batch.restype = C.c_int
@@ -306,21 +314,39 @@ class Device:
             out.append((int(score[i]), path))
         return out
 
-    def map_arrays(self, rbuf, qbuf, read_off, params=None, paired=False):
-        """gb_map_batch / gb_map_paired_batch on packed host arrays.  Returns (aln, mappings, edits, status)."""
+    def map_arrays(self, rbuf, qbuf, read_off, params=None, paired=False, out=None):
+        """gb_map_batch / gb_map_paired_batch on packed host arrays.
+        Returns (aln, mappings, edits, status); mappings / edits are dense pools."""
         lib = load_library()
         p = params or default_map_params()
         n = len(read_off) - 1
-        aln = np.zeros(n, dtype=alignment_dt)
-        maps = np.zeros(n * p.mapping_cap_per_read, dtype=mapping_dt)
-        edits = np.zeros(n * p.edit_cap_per_read, dtype=np.uint32)
-        status = np.zeros(n, dtype=np.uint8)
+        if out is None:
+            aln = np.zeros(n, dtype=alignment_dt)
+            maps = np.zeros(n * 24 + 1024, dtype=mapping_dt)
+            edits = np.zeros(n * 32 + 1024, dtype=np.uint32)
+            status = np.zeros(n, dtype=np.uint8)
+        else:
+            aln, maps, edits, status = out
+        used = (C.c_uint64(), C.c_uint64())
         fn = lib.gb_map_paired_batch if paired else lib.gb_map_batch
-        rc = fn(self._h, C.byref(p), n, ptr(rbuf), ptr(qbuf) if qbuf is not None else None,
-                ptr(read_off), ptr(aln), ptr(maps), ptr(edits), ptr(status))
+        rc = fn(self._h, C.byref(p), n, ptr(rbuf), ptr(qbuf) if qbuf is not None else None, ptr(read_off), ptr(aln),
+                ptr(maps), len(maps), ptr(edits), len(edits), ptr(status), C.byref(used[0]), C.byref(used[1]))
+        if rc == GB_ERR_CAPACITY and out is None:
+            maps = np.zeros(n * p.mapping_cap_per_read, dtype=mapping_dt)
+            edits = np.zeros(n * p.edit_cap_per_read, dtype=np.uint32)
+            rc = fn(self._h, C.byref(p), n, ptr(rbuf), ptr(qbuf) if qbuf is not None else None, ptr(read_off), ptr(aln),
+                    ptr(maps), len(maps), ptr(edits), len(edits), ptr(status), C.byref(used[0]), C.byref(used[1]))
         if rc != GB_OK:
             raise GbError(rc, "gb_map_paired_batch" if paired else "gb_map_batch")
+        self.last_used = (used[0].value, used[1].value)
         return aln, maps, edits, status
+
+    def stage_times(self):
+        ms = (C.c_float * 4)()
+        rc = load_library().gb_stage_times(self._h, ms)
+        if rc != GB_OK:
+            raise GbError(rc, "gb_stage_times")
+        return [float(x) for x in ms]
 
     def close(self):
         if getattr(self, "_h", None):

@@ -102,7 +102,9 @@ extern "C" int gb_device_create(const gb_flat_index* ix, int device_ordinal, gb_
     cudaDeviceProp prop;
     GB_CUDA(cudaGetDeviceProperties(&prop, device_ordinal));
     d->n_sms = prop.multiProcessorCount;
-    GB_CUDA(cudaStreamCreateWithFlags(&d->stream, cudaStreamNonBlocking));
+    GB_CUDA(cudaStreamCreateWithFlags(&d->own_stream, cudaStreamNonBlocking));
+    d->stream = d->own_stream;
+    for (int i = 0; i < 5; i++) GB_CUDA(cudaEventCreate(&d->ev_stage[i]));
     GB_CUDA(cudaEventCreate(&d->ev0)); GB_CUDA(cudaEventCreate(&d->ev1));
     int rc;
     if ((rc = d->nodes.upload(ix->nodes, ix->n_nodes, d->stream))) return rc;
@@ -126,9 +128,10 @@ extern "C" void gb_device_destroy(gb_device* d) {
     cudaSetDevice(d->device);
     cudaStreamSynchronize(d->stream);
     d->release_all();
+    for (int i = 0; i < 5; i++) cudaEventDestroy(d->ev_stage[i]);
     cudaFree(d->work_counter);
     cudaEventDestroy(d->ev0); cudaEventDestroy(d->ev1);
-    cudaStreamDestroy(d->stream);
+    cudaStreamDestroy(d->own_stream);
     delete d;
 }
 

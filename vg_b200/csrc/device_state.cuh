@@ -60,7 +60,8 @@ struct DevBuf {
 struct gb_device {
     int device = 0;
     int n_sms = 0;
-    cudaStream_t stream = nullptr;
+    cudaStream_t stream = nullptr, own_stream = nullptr;
+    cudaEvent_t ev_stage[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
     gb::DevIndex ix{};
     gb::DevScores sc{1, 4, 6, 1, 5};
@@ -88,6 +89,10 @@ struct gb_device {
     gb::DevBuf<gb_extension> p_ext;
     gb::DevBuf<uint8_t> ws_tail, ws_cand, w_reads, w_quals;
     gb::DevBuf<gb::PairState> p_pairs;
+    gb::DevBuf<gb_mapping> pad_maps;
+    gb::DevBuf<uint32_t> pad_edits;
+    gb::DevBuf<uint64_t> c_map_off, c_edit_off, c_totals;
+    gb::DevBuf<uint8_t> c_tmp;
     gb::DevBuf<uint8_t> io_reads, io_quals, io_status;
     gb::DevBuf<uint64_t> io_read_off;
     gb::DevBuf<gb_alignment> io_aln;
@@ -99,6 +104,7 @@ struct gb_device {
         t_hit.release(); t_plo.release(); t_phred.release(); p_states.release(); p_min.release(); p_seeds.release();
         p_items.release(); p_ext_seeds.release(); p_cursors.release(); p_ext_count.release(); p_path.release(); p_mism.release();
         p_ext_status.release(); p_ext.release(); ws_tail.release(); ws_cand.release(); w_reads.release(); w_quals.release(); p_pairs.release();
+        pad_maps.release(); pad_edits.release(); c_map_off.release(); c_edit_off.release(); c_totals.release(); c_tmp.release();
         io_reads.release(); io_quals.release(); io_status.release(); io_read_off.release(); io_aln.release(); io_maps.release(); io_edits.release();
     }
 };

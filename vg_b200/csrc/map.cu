@@ -2,6 +2,7 @@
 //   seed_kernel -> extend_kernel -> align_kernel, all persistent warp-per-unit kernels pulling
 //   work from atomic counters; intermediate records stay in HBM (map_state.cuh).
 // No CPU fallback: every stage is a CUDA kernel; the host only moves buffers and launches.
+#include <cub/cub.cuh>
 #include "giraffe_b200.h"
 #include "device_state.cuh"
 #include "seed.cuh"
@@ -113,6 +114,7 @@ align_kernel(DevIndex ix, MapParamsDev P, DevScores sc, MapBatch b, AlignArgs a)
 }
 
 #include "map_paired.cuh"
+#include "compact.cuh"
 
 // AlignmentScorer::recover_log_base (alignment_scorer.cpp:30-99), gc 0.5, tol 1e-12.
 static double recover_log_base(const DevScores& s) {
@@ -150,7 +152,13 @@ namespace gb {
 // Device-resident mapping of a batch whose reads are already in HBM.
 int map_device(gb_device* d, const gb_map_params* hp, uint32_t n_reads, const uint8_t* d_reads, const uint8_t* d_quals,
                const uint64_t* d_read_off, uint32_t max_len, uint64_t total_bases,
-               gb_alignment* d_aln, gb_mapping* d_maps, uint32_t* d_edits, uint8_t* d_status, bool paired) {
+               gb_alignment* d_aln, uint8_t* d_status, bool paired,
+               gb_mapping* out_maps, uint64_t out_map_cap, uint32_t* out_edits, uint64_t out_edit_cap,
+               uint64_t map_base, uint64_t edit_base, uint32_t read_base, uint64_t* d_totals) {
+    int rc0;
+    if ((rc0 = d->pad_maps.reserve((size_t)n_reads * hp->mapping_cap_per_read))) return rc0;
+    if ((rc0 = d->pad_edits.reserve((size_t)n_reads * hp->edit_cap_per_read))) return rc0;
+    gb_mapping* d_maps = d->pad_maps.ptr; uint32_t* d_edits = d->pad_edits.ptr;
     if (paired) {
         if (n_reads % 2 != 0) { g_last_error = "paired mapping needs an even number of reads"; return GB_ERR_ARG; }
         if (hp->max_rescue_attempts != 0) { g_last_error = "paired mapping is built for max_rescue_attempts = 0 (vg giraffe --rescue-attempts 0); rescue is not implemented"; return GB_ERR_ARG; }
@@ -223,6 +231,7 @@ int map_device(gb_device* d, const gb_map_params* hp, uint32_t n_reads, const ui
     pools.items = d->p_items.ptr; pools.item_cap = (uint32_t)item_cap; pools.item_cursor = cur + 3;
     pools.ext_seeds = d->p_ext_seeds.ptr; pools.ext_cap = (uint32_t)ext_cap; pools.ext_cursor = cur + 4;
 
+    GB_CUDA(cudaEventRecord(d->ev_stage[0], d->stream));
     // ---- K1 ----
     {
         const size_t smem = seed_smem_bytes(Lc) * SEED_WARPS;
@@ -242,6 +251,7 @@ int map_device(gb_device* d, const gb_map_params* hp, uint32_t n_reads, const ui
         d->launches++;
         GB_CUDA(cudaGetLastError());
     }
+    GB_CUDA(cudaEventRecord(d->ev_stage[1], d->stream));
     // ---- K2: extension over the items produced on the device ----
     const uint32_t max_ext = 48, path_cap = 384, mism_cap = 192;
     if ((rc = d->p_ext_count.reserve(item_cap))) return rc;
@@ -257,6 +267,7 @@ int map_device(gb_device* d, const gb_map_params* hp, uint32_t n_reads, const ui
                                        (uint32_t)item_cap, d->p_ext_count.ptr, d->p_ext_status.ptr, d->p_ext.ptr, d->p_path.ptr,
                                        d->p_mism.ptr, Lc))) return rc;
     }
+    GB_CUDA(cudaEventRecord(d->ev_stage[2], d->stream));
     // ---- K3 ----
     {
         const uint32_t W = Lc + 1;
@@ -292,51 +303,120 @@ int map_device(gb_device* d, const gb_map_params* hp, uint32_t n_reads, const ui
         d->launches++;
         GB_CUDA(cudaGetLastError());
     }
+    GB_CUDA(cudaEventRecord(d->ev_stage[3], d->stream));
+    if ((rc = compact_outputs(d, n_reads, d_aln, d_maps, d_edits, hp->mapping_cap_per_read, hp->edit_cap_per_read,
+                              out_maps, out_map_cap, out_edits, out_edit_cap, map_base, edit_base, read_base, d_totals, d_status))) return rc;
+    GB_CUDA(cudaEventRecord(d->ev_stage[4], d->stream));
     return GB_OK;
 }
 
 } // namespace gb
 
+// Host-buffer entry: chunks of <= MAP_CHUNK reads are copied in, mapped, compacted and copied out.
 static int map_batch_host(gb_device* d, const gb_map_params* hp, bool paired,
-                            uint32_t n_reads, const uint8_t* reads, const uint8_t* quals, const uint64_t* read_off,
-                            gb_alignment* aln, gb_mapping* mappings, uint32_t* edits, uint8_t* status) {
+                          uint32_t n_reads, const uint8_t* reads, const uint8_t* quals, const uint64_t* read_off,
+                          gb_alignment* aln, gb_mapping* mappings, uint64_t mapping_pool_cap, uint32_t* edits, uint64_t edit_pool_cap,
+                          uint8_t* status, uint64_t* n_mappings_used, uint64_t* n_edits_used) {
     if (!d || !hp || !reads || !read_off || !aln || !mappings || !edits || !status) return GB_ERR_ARG;
+    if (n_mappings_used) *n_mappings_used = 0;
+    if (n_edits_used) *n_edits_used = 0;
     if (n_reads == 0) return GB_OK;
     GB_CUDA(cudaSetDevice(d->device));
-    uint32_t max_len = 0;
-    for (uint32_t r = 0; r < n_reads; r++) max_len = std::max<uint32_t>(max_len, (uint32_t)(read_off[r + 1] - read_off[r]));
-    const uint64_t total = read_off[n_reads];
+    const uint32_t MAP_CHUNK = 1u << 20;
+    uint64_t map_used = 0, edit_used = 0;
+    float kernel_ms = 0.f;
     int rc;
-    if ((rc = d->io_reads.upload(reads, total ? total : 1, d->stream, total))) return rc;
-    if (quals) { if ((rc = d->io_quals.upload(quals, total ? total : 1, d->stream, total))) return rc; }
-    if ((rc = d->io_read_off.upload(read_off, n_reads + 1, d->stream))) return rc;
-    if ((rc = d->io_aln.reserve(n_reads))) return rc;
-    if ((rc = d->io_maps.reserve((size_t)n_reads * hp->mapping_cap_per_read))) return rc;
-    if ((rc = d->io_edits.reserve((size_t)n_reads * hp->edit_cap_per_read))) return rc;
-    if ((rc = d->io_status.reserve(n_reads))) return rc;
-    GB_CUDA(cudaEventRecord(d->ev0, d->stream));
-    if ((rc = map_device(d, hp, n_reads, d->io_reads.ptr, quals ? d->io_quals.ptr : nullptr, d->io_read_off.ptr, max_len, total,
-                         d->io_aln.ptr, d->io_maps.ptr, d->io_edits.ptr, d->io_status.ptr, paired))) return rc;
-    GB_CUDA(cudaEventRecord(d->ev1, d->stream));
-    GB_CUDA(cudaMemcpyAsync(aln, d->io_aln.ptr, sizeof(gb_alignment) * n_reads, cudaMemcpyDeviceToHost, d->stream));
-    GB_CUDA(cudaMemcpyAsync(mappings, d->io_maps.ptr, sizeof(gb_mapping) * (size_t)n_reads * hp->mapping_cap_per_read, cudaMemcpyDeviceToHost, d->stream));
-    GB_CUDA(cudaMemcpyAsync(edits, d->io_edits.ptr, 4 * (size_t)n_reads * hp->edit_cap_per_read, cudaMemcpyDeviceToHost, d->stream));
-    GB_CUDA(cudaMemcpyAsync(status, d->io_status.ptr, n_reads, cudaMemcpyDeviceToHost, d->stream));
-    GB_CUDA(cudaStreamSynchronize(d->stream));
-    GB_CUDA(cudaEventElapsedTime(&d->last_kernel_ms, d->ev0, d->ev1));
+    std::vector<uint64_t> local_off;
+    if ((rc = d->c_totals.reserve(2))) return rc;
+    for (uint32_t c0 = 0; c0 < n_reads; c0 += MAP_CHUNK) {
+        const uint32_t cn = std::min<uint32_t>(MAP_CHUNK, n_reads - c0);
+        const uint64_t b0 = read_off[c0], b1 = read_off[c0 + cn], total = b1 - b0;
+        uint32_t max_len = 0;
+        local_off.resize(cn + 1);
+        for (uint32_t r = 0; r <= cn; r++) local_off[r] = read_off[c0 + r] - b0;
+        for (uint32_t r = 0; r < cn; r++) max_len = std::max<uint32_t>(max_len, (uint32_t)(local_off[r + 1] - local_off[r]));
+        if ((rc = d->io_reads.upload(reads + b0, total ? total : 1, d->stream, total))) return rc;
+        if (quals) { if ((rc = d->io_quals.upload(quals + b0, total ? total : 1, d->stream, total))) return rc; }
+        if ((rc = d->io_read_off.upload(local_off.data(), cn + 1, d->stream))) return rc;
+        if ((rc = d->io_aln.reserve(cn))) return rc;
+        if ((rc = d->io_status.reserve(cn))) return rc;
+        const uint64_t chunk_map_cap = (uint64_t)cn * hp->mapping_cap_per_read, chunk_edit_cap = (uint64_t)cn * hp->edit_cap_per_read;
+        if ((rc = d->io_maps.reserve(chunk_map_cap))) return rc;
+        if ((rc = d->io_edits.reserve(chunk_edit_cap))) return rc;
+        GB_CUDA(cudaEventRecord(d->ev0, d->stream));
+        if ((rc = map_device(d, hp, cn, d->io_reads.ptr, quals ? d->io_quals.ptr : nullptr, d->io_read_off.ptr, max_len, total,
+                             d->io_aln.ptr, d->io_status.ptr, paired, d->io_maps.ptr, chunk_map_cap, d->io_edits.ptr, chunk_edit_cap,
+                             map_used, edit_used, c0, d->c_totals.ptr))) return rc;
+        GB_CUDA(cudaEventRecord(d->ev1, d->stream));
+        uint64_t totals[2] = {0, 0};
+        GB_CUDA(cudaMemcpyAsync(totals, d->c_totals.ptr, sizeof(totals), cudaMemcpyDeviceToHost, d->stream));
+        GB_CUDA(cudaMemcpyAsync(aln + c0, d->io_aln.ptr, sizeof(gb_alignment) * cn, cudaMemcpyDeviceToHost, d->stream));
+        GB_CUDA(cudaMemcpyAsync(status + c0, d->io_status.ptr, cn, cudaMemcpyDeviceToHost, d->stream));
+        GB_CUDA(cudaStreamSynchronize(d->stream));
+        if (map_used + totals[0] > mapping_pool_cap || edit_used + totals[1] > edit_pool_cap) {
+            g_last_error = "output pool capacity too small";
+            return GB_ERR_CAPACITY;
+        }
+        if (totals[0]) GB_CUDA(cudaMemcpyAsync(mappings + map_used, d->io_maps.ptr, sizeof(gb_mapping) * totals[0], cudaMemcpyDeviceToHost, d->stream));
+        if (totals[1]) GB_CUDA(cudaMemcpyAsync(edits + edit_used, d->io_edits.ptr, 4 * totals[1], cudaMemcpyDeviceToHost, d->stream));
+        GB_CUDA(cudaStreamSynchronize(d->stream));
+        float ms = 0.f;
+        GB_CUDA(cudaEventElapsedTime(&ms, d->ev0, d->ev1));
+        kernel_ms += ms;
+        map_used += totals[0]; edit_used += totals[1];
+    }
+    d->last_kernel_ms = kernel_ms;
+    if (n_mappings_used) *n_mappings_used = map_used;
+    if (n_edits_used) *n_edits_used = edit_used;
     return GB_OK;
 }
 
 extern "C" int gb_map_batch(gb_device* d, const gb_map_params* hp,
                             uint32_t n_reads, const uint8_t* reads, const uint8_t* quals, const uint64_t* read_off,
-                            gb_alignment* aln, gb_mapping* mappings, uint32_t* edits, uint8_t* status) {
-    return map_batch_host(d, hp, false, n_reads, reads, quals, read_off, aln, mappings, edits, status);
+                            gb_alignment* aln, gb_mapping* mappings, uint64_t mapping_pool_cap, uint32_t* edits, uint64_t edit_pool_cap,
+                            uint8_t* status, uint64_t* n_mappings_used, uint64_t* n_edits_used) {
+    return map_batch_host(d, hp, false, n_reads, reads, quals, read_off, aln, mappings, mapping_pool_cap, edits, edit_pool_cap, status, n_mappings_used, n_edits_used);
 }
 
 extern "C" int gb_map_paired_batch(gb_device* d, const gb_map_params* hp,
                                    uint32_t n_reads, const uint8_t* reads, const uint8_t* quals, const uint64_t* read_off,
-                                   gb_alignment* aln, gb_mapping* mappings, uint32_t* edits, uint8_t* status) {
-    return map_batch_host(d, hp, true, n_reads, reads, quals, read_off, aln, mappings, edits, status);
+                                   gb_alignment* aln, gb_mapping* mappings, uint64_t mapping_pool_cap, uint32_t* edits, uint64_t edit_pool_cap,
+                                   uint8_t* status, uint64_t* n_mappings_used, uint64_t* n_edits_used) {
+    return map_batch_host(d, hp, true, n_reads, reads, quals, read_off, aln, mappings, mapping_pool_cap, edits, edit_pool_cap, status, n_mappings_used, n_edits_used);
+}
+
+// Device-pointer entry: inputs already in HBM, outputs stay in HBM; asynchronous on the handle's stream.
+extern "C" int gb_map_batch_device(gb_device* d, const gb_map_params* hp, int paired, uint32_t n_reads,
+                                   const uint8_t* d_reads, const uint8_t* d_quals, const uint64_t* d_read_off, uint32_t max_read_len,
+                                   gb_alignment* d_aln, gb_mapping* d_mappings, uint64_t mapping_pool_cap, uint32_t* d_edits, uint64_t edit_pool_cap,
+                                   uint8_t* d_status, uint64_t* d_totals) {
+    if (!d || !hp || !d_reads || !d_read_off || !d_aln || !d_mappings || !d_edits || !d_status || !d_totals) return GB_ERR_ARG;
+    if (n_reads == 0) return GB_OK;
+    GB_CUDA(cudaSetDevice(d->device));
+    return map_device(d, hp, n_reads, d_reads, d_quals, d_read_off, max_read_len, (uint64_t)n_reads * max_read_len, d_aln, d_status, paired != 0,
+                      d_mappings, mapping_pool_cap, d_edits, edit_pool_cap, 0, 0, 0, d_totals);
+}
+
+extern "C" int gb_device_set_stream(gb_device* d, void* cuda_stream) {
+    if (!d) return GB_ERR_ARG;
+    d->stream = cuda_stream ? (cudaStream_t)cuda_stream : d->own_stream;
+    return GB_OK;
+}
+
+extern "C" int gb_device_synchronize(gb_device* d) {
+    if (!d) return GB_ERR_ARG;
+    GB_CUDA(cudaSetDevice(d->device));
+    GB_CUDA(cudaStreamSynchronize(d->stream));
+    return GB_OK;
+}
+
+// Stage times of the last map_device call on this handle: seed, extend, align, compact (ms).
+extern "C" int gb_stage_times(gb_device* d, float* ms4) {
+    if (!d || !ms4) return GB_ERR_ARG;
+    GB_CUDA(cudaSetDevice(d->device));
+    GB_CUDA(cudaEventSynchronize(d->ev_stage[4]));
+    for (int i = 0; i < 4; i++) GB_CUDA(cudaEventElapsedTime(&ms4[i], d->ev_stage[i], d->ev_stage[i + 1]));
+    return GB_OK;
 }
 
 // ---------------------------------------------------------------------------------------
