@@ -1,0 +1,472 @@
+#!/usr/bin/env python
+"""bench.py — giraffe reads/sec on BASELINE.json configs[1] (1 Mbp / 1k-variant graph,
+150 bp paired-end reads), one process per GPU.
+
+  python bench.py --gpus N --steps K --warmup W            # this repo's CUDA path
+  python bench.py --impl reference --gpus N --steps K ...  # the CPU restatement of vg giraffe
+                                                           # (oracle/) on the box's host cores
+
+A "step" is one pass of the mapping hot path over one batch of synthetic read pairs.
+value  = whole-job reads/s with the reads already resident in HBM (device-pointer C-ABI entry,
+         CUDA events on the launching stream);
+e2e    = the same batch through the host-buffer C-ABI entry gb_map_paired_batch (pinned host
+         memory, H2D of reads+qualities and D2H of the alignment records inside the timed region).
+Rank 0 prints one JSON line.
+"""
+from __future__ import annotations
+
+import argparse
+import ctypes as C
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+from pathlib import Path
+
+import numpy as np
+
+ROOT = Path(__file__).resolve().parent
+sys.path.insert(0, str(ROOT))
+sys.path.insert(0, str(ROOT / "tests"))
+
+READ_LEN = 150
+FRAG_MEAN, FRAG_SD = 400.0, 50.0
+SUB_RATE = 0.002
+GRAPH_SEED = 2
+
+
+def log(*a):
+    if int(os.environ.get("RANK", "0")) == 0:
+        print(*a, file=sys.stderr, flush=True)
+
+
+# ---------------------------------------------------------------------------------------
+# synthetic workload
+# ---------------------------------------------------------------------------------------
+def make_graph_and_index():
+    from vg_b200 import synth
+    t = time.time()
+    g = synth.make_variant_graph(length=1_000_000, n_snp=800, n_ins=100, n_del=100, n_haps=8, seed=GRAPH_SEED)
+    index = g.build_index(k=29, w=11)
+    log(f"[bench] graph+index: {len(g.node_seqs)} nodes, {index.view.n_hits} minimizer hits, {time.time() - t:.1f}s")
+    return g, index
+
+
+def simulate_pairs_torch(g, n_pairs, seed, device):
+    """GPU version of synth.simulate_pairs (inward 150 bp pairs, fragment N(400, 50), 0.2 % substitutions)."""
+    import torch
+    gen = torch.Generator(device=device)
+    gen.manual_seed(seed)
+    haps = [torch.from_numpy(h.copy()).to(device) for h in g.hap_seq]
+    min_len = min(len(h) for h in haps)
+    comp = torch.full((256,), ord("N"), dtype=torch.uint8, device=device)
+    for a, b in zip(b"ACGT", b"TGCA"):
+        comp[a] = b
+    bases = torch.tensor(list(b"ACGT"), dtype=torch.uint8, device=device)
+    reads = torch.empty((2 * n_pairs, READ_LEN), dtype=torch.uint8, device=device)
+    ar = torch.arange(READ_LEN, device=device)
+    CH = 250_000
+    for c0 in range(0, n_pairs, CH):
+        cn = min(CH, n_pairs - c0)
+        hap = torch.randint(0, len(haps), (cn,), generator=gen, device=device)
+        frag = torch.clamp(torch.round(torch.randn(cn, generator=gen, device=device) * FRAG_SD + FRAG_MEAN), min=READ_LEN).long()
+        start = (torch.rand(cn, generator=gen, device=device) * (min_len - 1000)).long()
+        flip = torch.rand(cn, generator=gen, device=device) < 0.5
+        left = torch.empty((cn, READ_LEN), dtype=torch.uint8, device=device)
+        right = torch.empty((cn, READ_LEN), dtype=torch.uint8, device=device)
+        for h in range(len(haps)):
+            sel = (hap == h).nonzero(as_tuple=True)[0]
+            if sel.numel() == 0:
+                continue
+            left[sel] = haps[h][start[sel, None] + ar[None, :]]
+            rs = start[sel] + frag[sel] - READ_LEN
+            right[sel] = comp[haps[h][rs[:, None] + ar[None, :]].long()].flip(1)
+        m1 = torch.where(flip[:, None], right, left)
+        m2 = torch.where(flip[:, None], left, right)
+        reads[2 * c0: 2 * (c0 + cn): 2] = m1
+        reads[2 * c0 + 1: 2 * (c0 + cn): 2] = m2
+    # substitutions
+    for c0 in range(0, 2 * n_pairs, 1_000_000):
+        blk = reads[c0: c0 + 1_000_000]
+        mask = torch.rand(blk.shape, generator=gen, device=device) < SUB_RATE
+        idx = mask.nonzero(as_tuple=True)
+        if idx[0].numel():
+            old = blk[idx]
+            code = (old == ord("C")).long() + 2 * (old == ord("G")).long() + 3 * (old == ord("T")).long()
+            new = bases[(code + torch.randint(1, 4, code.shape, generator=gen, device=device)) % 4]
+            blk[idx] = new
+    quals = torch.full_like(reads, 30)
+    return reads, quals
+
+
+def simulate_pairs_numpy(g, n_pairs, seed):
+    from vg_b200 import synth
+    rs = synth.simulate_pairs(g, n_pairs, length=READ_LEN, frag_mean=FRAG_MEAN, frag_sd=FRAG_SD, sub_rate=SUB_RATE, seed=seed)
+    return rs.reads, rs.quals
+
+
+# ---------------------------------------------------------------------------------------
+# helpers
+# ---------------------------------------------------------------------------------------
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md recipe)."""
+
+    def __init__(self, gpu_index):
+        self.gpu_index = gpu_index
+        self.rows = []
+        self.proc = None
+
+    def start(self):
+        q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+             "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={q}", "--format=csv,noheader,nounits", "-lms", "200",
+                                          "-i", str(self.gpu_index)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([x.strip() for x in line.split(",")])
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm = [float(r[1]) for r in self.rows if len(r) >= 9 and r[1].replace(".", "").isdigit()]
+        mx = [float(r[2]) for r in self.rows if len(r) >= 9 and r[2].replace(".", "").isdigit()]
+        reasons = set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            if len(r) >= 9:
+                for name, v in zip(names, r[5:9]):
+                    if v.lower().startswith("active"):
+                        reasons.add(name)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def oracle_library(native=True):
+    """liboracle.so, rebuilt with -march=native on this box when gcc is available (test infrastructure;
+    only the cpu_baseline leg and --impl reference use it)."""
+    import helpers as H
+    if native:
+        try:
+            tmp = ROOT / "gpurun_out" / "oracle_native"
+            tmp.mkdir(parents=True, exist_ok=True)
+            so = tmp / "liboracle.so"
+            srcs = sorted(str(p) for p in (ROOT / "oracle").glob("*.cpp"))
+            cxx = "/usr/bin/g++" if os.path.exists("/usr/bin/g++") else "g++"
+            subprocess.run([cxx, "-O3", "-march=native", "-std=c++17", "-fPIC", "-fopenmp", "-shared", "-o", str(so)] + srcs,
+                           check=True, capture_output=True, cwd=str(ROOT / "oracle"))
+            H._oracle = None
+            lib = C.CDLL(str(so))
+            H._oracle = lib
+            H.oracle_lib_configure(lib)
+            return lib, "-O3 -march=native"
+        except Exception as e:  # fall back to the prebuilt generic build
+            log(f"[bench] native oracle build failed ({e}); using the prebuilt library")
+            H._oracle = None
+    return H.oracle_lib(), "-O3 (generic)"
+
+
+def cpu_map_rate(index, reads_np, quals_np, params, threads, target_seconds=15.0):
+    """reads/s of the CPU restatement on `threads` host threads over a bounded sample."""
+    import helpers as H
+    n_total = reads_np.shape[0]
+    probe = min(n_total, 200_000)
+    probe -= probe % 2
+    out = None
+    t = time.time()
+    H.oracle_map_paired(index, reads_np[:probe], quals_np[:probe], params, threads=threads)
+    rate = probe / max(time.time() - t, 1e-6)
+    sample = int(min(n_total, max(probe, rate * target_seconds)))
+    sample -= sample % 2
+    t = time.time()
+    res = H.oracle_map_paired(index, reads_np[:sample], quals_np[:sample], params, threads=threads)
+    dt = time.time() - t
+    return sample / dt, sample, dt, res
+
+
+def algorithmic_bytes_per_read(L, counters, n_reads_sample, mappings_per_read, edits_per_read):
+    """B(read) = 2L + 16M + 24H + X(L + 16 ceil(L/32) + 16) + T(S_t + 16 N_t) + 32 + 8P + 4E."""
+    M = counters["minimizers"] / n_reads_sample
+    Hh = counters["seeds"] / n_reads_sample
+    X = counters["extend_calls"] / n_reads_sample
+    T = counters["tail_dps"] / n_reads_sample
+    St = counters["tail_bases"] / max(counters["tail_dps"], 1)
+    Nt = counters["tail_nodes"] / max(counters["tail_dps"], 1)
+    B = 2 * L + 16 * M + 24 * Hh + X * (L + 16 * -(-L // 32) + 16) + T * (St + 16 * Nt) + 32 + 8 * mappings_per_read + 4 * edits_per_read
+    return B, {"M": round(M, 2), "H": round(Hh, 2), "X": round(X, 3), "T": round(T, 4), "S_t": round(St, 1), "N_t": round(Nt, 1),
+               "P": round(mappings_per_read, 2), "E": round(edits_per_read, 2)}
+
+
+# ---------------------------------------------------------------------------------------
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=3)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--reads", type=int, default=10_000_000, help="reads (not pairs) per GPU per step")
+    ap.add_argument("--cpu-seconds", type=float, default=15.0)
+    args = ap.parse_args()
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    n_reads = args.reads - args.reads % 2
+
+    import helpers as H
+
+    if args.impl == "reference":
+        # The reference arm: vg cannot be built here (all deps/ submodules are empty), so this times the
+        # CPU restatement of the same path (oracle/) with every host thread, on rank 0 only.
+        if rank != 0:
+            return 0
+        g, index = make_graph_and_index()
+        params = H.paired_params(FRAG_MEAN, FRAG_SD)
+        lib, flags = oracle_library()
+        threads = os.cpu_count() or 1
+        sample = min(n_reads, 4_000_000)
+        reads_np, quals_np = simulate_pairs_numpy(g, sample // 2, 22)
+        rate, used, dt, _ = cpu_map_rate(index, reads_np, quals_np, params, threads, target_seconds=min(args.cpu_seconds, 10.0))
+        times = []
+        for s in range(args.warmup + args.steps):
+            t = time.time()
+            H.oracle_map_paired(index, reads_np[:used], quals_np[:used], params, threads=threads)
+            if s >= args.warmup:
+                times.append(time.time() - t)
+        ms = 1e3 * float(np.mean(times))
+        value = used / (ms / 1e3)
+        line = {
+            "impl": "reference", "metric": "giraffe reads/sec (150 bp PE, synthetic)", "value": value, "unit": "reads/s",
+            "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "int32", "data": "synthetic",
+            "config": {"workload": "configs[1]: 1 Mbp / 1k-variant graph, 150 bp PE reads, fragment N(400,50) forced, rescue attempts 0",
+                       "reads_per_step": used, "note": "CPU restatement of vg giraffe (oracle/, OpenMP over read pairs); vg itself cannot be built in this image"},
+            "cpu_baseline": {"value": value, "unit": "reads/s", "cores": threads, "kind": "port", "sample": f"{used} reads per step, {flags}"},
+            "e2e": {"value": value, "unit": "reads/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        }
+        print(json.dumps(line), flush=True)
+        return 0
+
+    import torch
+    import torch.distributed as dist
+    from vg_b200 import capi
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device (the product path has no CPU fallback)")
+    torch.cuda.set_device(local_rank)
+    device = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=device)
+
+    g, index = make_graph_and_index()
+    dev = capi.Device(index, local_rank)
+    lib = capi.load_library()
+    params = H.paired_params(FRAG_MEAN, FRAG_SD)
+    stream = torch.cuda.current_stream(device)
+    lib.gb_device_set_stream(dev.handle, C.c_void_p(stream.cuda_stream))
+
+    t = time.time()
+    d_reads, d_quals = simulate_pairs_torch(g, n_reads // 2, 22 + rank, device)
+    torch.cuda.synchronize()
+    log(f"[bench] rank {rank}: {n_reads} reads generated on the GPU in {time.time() - t:.1f}s")
+    d_read_off = (torch.arange(n_reads + 1, dtype=torch.int64, device=device) * READ_LEN)
+
+    # ---- output buffers (device) ----
+    MAP_PER, EDIT_PER = 14, 20
+    d_aln = torch.zeros((n_reads, 32), dtype=torch.uint8, device=device)
+    d_maps = torch.zeros((n_reads * MAP_PER, 8), dtype=torch.uint8, device=device)
+    d_edits = torch.zeros((n_reads * EDIT_PER,), dtype=torch.int32, device=device)
+    d_status = torch.zeros((n_reads,), dtype=torch.uint8, device=device)
+    CHUNK = 1 << 20
+    n_chunks = (n_reads + CHUNK - 1) // CHUNK
+    d_totals = torch.zeros((n_chunks, 2), dtype=torch.int64, device=device)
+
+    def device_step():
+        """whole batch, device-resident, chunked to bound the intermediate pools"""
+        for ci in range(n_chunks):
+            c0 = ci * CHUNK
+            cn = min(CHUNK, n_reads - c0)
+            off = d_read_off[c0: c0 + cn + 1] - d_read_off[c0]
+            rc = lib.gb_map_batch_device(dev.handle, C.byref(params), 1, cn,
+                                         C.c_void_p(d_reads[c0].data_ptr()), C.c_void_p(d_quals[c0].data_ptr()),
+                                         C.c_void_p(off.data_ptr()), READ_LEN,
+                                         C.c_void_p(d_aln[c0].data_ptr()), C.c_void_p(d_maps[c0 * MAP_PER].data_ptr()), cn * MAP_PER,
+                                         C.c_void_p(d_edits[c0 * EDIT_PER:].data_ptr()), cn * EDIT_PER,
+                                         C.c_void_p(d_status[c0:].data_ptr()), C.c_void_p(d_totals[ci].data_ptr()))
+            if rc != 0:
+                raise capi.GbError(rc, "gb_map_batch_device")
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---- timed region 1: device-resident ----
+    for _ in range(args.warmup):
+        device_step()
+    barrier()
+    stage_ms = np.zeros(4)
+    launches0 = dev.launches()
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    ev = [torch.cuda.Event(enable_timing=True) for _ in range(2)]
+    ev[0].record(stream)
+    for _ in range(args.steps):
+        device_step()
+        # stage timers belong to the last chunk; scale by the chunk count for the share
+    ev[1].record(stream)
+    barrier()
+    dev_ms = ev[0].elapsed_time(ev[1]) / args.steps
+    clocks = sampler.stop()
+    launches = (dev.launches() - launches0) // max(args.steps, 1)
+    last_stage = np.array(dev.stage_times())
+    if world > 1:
+        tms = torch.tensor([dev_ms], device=device)
+        dist.all_reduce(tms, op=dist.ReduceOp.MAX)
+        dev_ms = float(tms.item())
+    value = world * n_reads / (dev_ms / 1e3)
+
+    totals = d_totals.cpu().numpy()
+    status_bad = int((d_status != 0).sum().item())
+    aln_np = d_aln[: min(n_reads, 2_000_000)].cpu().numpy().view(capi.alignment_dt).reshape(-1)
+    mapped_frac = float((aln_np["flags"] & 1).mean())
+    mapq60 = float((aln_np["mapq"] == 60).mean())
+    maps_per_read = float(totals[:, 0].sum()) / n_reads
+    edits_per_read = float(totals[:, 1].sum()) / n_reads
+
+    # ---- timed region 2: end to end through the host-buffer C-ABI (pinned host memory) ----
+    h_reads = torch.empty((n_reads, READ_LEN), dtype=torch.uint8, pin_memory=True)
+    h_quals = torch.empty((n_reads, READ_LEN), dtype=torch.uint8, pin_memory=True)
+    h_reads.copy_(d_reads)
+    h_quals.copy_(d_quals)
+    torch.cuda.synchronize()
+    h_off = torch.arange(n_reads + 1, dtype=torch.int64) * READ_LEN
+    h_aln = torch.zeros((n_reads, 32), dtype=torch.uint8, pin_memory=True)
+    h_maps = torch.zeros((n_reads * MAP_PER, 8), dtype=torch.uint8, pin_memory=True)
+    h_edits = torch.zeros((n_reads * EDIT_PER,), dtype=torch.int32, pin_memory=True)
+    h_status = torch.zeros((n_reads,), dtype=torch.uint8, pin_memory=True)
+    used = (C.c_uint64(), C.c_uint64())
+
+    def e2e_step():
+        rc = lib.gb_map_paired_batch(dev.handle, C.byref(params), n_reads, C.c_void_p(h_reads.data_ptr()), C.c_void_p(h_quals.data_ptr()),
+                                     C.c_void_p(h_off.data_ptr()), C.c_void_p(h_aln.data_ptr()), C.c_void_p(h_maps.data_ptr()),
+                                     n_reads * MAP_PER, C.c_void_p(h_edits.data_ptr()), n_reads * EDIT_PER, C.c_void_p(h_status.data_ptr()),
+                                     C.byref(used[0]), C.byref(used[1]))
+        if rc != 0:
+            raise capi.GbError(rc, "gb_map_paired_batch")
+
+    e2e_warm = min(args.warmup, 3)
+    for _ in range(e2e_warm):
+        e2e_step()
+    barrier()
+    ev2 = [torch.cuda.Event(enable_timing=True) for _ in range(2)]
+    t0 = time.time()
+    ev2[0].record(stream)
+    for _ in range(args.steps):
+        e2e_step()
+        if world > 1:
+            # final alignment emission: fixed-width records gathered on rank 0 over NVLink
+            hdr = d_aln if True else None
+            gather_list = [torch.empty_like(d_aln) for _ in range(world)] if rank == 0 else None
+            dist.gather(d_aln, gather_list, dst=0)
+    ev2[1].record(stream)
+    barrier()
+    e2e_ms_dev = ev2[0].elapsed_time(ev2[1]) / args.steps
+    e2e_ms_wall = 1e3 * (time.time() - t0) / args.steps
+    e2e_ms = max(e2e_ms_dev, e2e_ms_wall)
+    if world > 1:
+        tms = torch.tensor([e2e_ms], device=device)
+        dist.all_reduce(tms, op=dist.ReduceOp.MAX)
+        e2e_ms = float(tms.item())
+    e2e_value = world * n_reads / (e2e_ms / 1e3)
+    h2d = 2 * n_reads * READ_LEN + 8 * (n_reads + 1)
+    d2h = 32 * n_reads + n_reads + 8 * used[0].value + 4 * used[1].value
+
+    # parity spot check of the e2e output against the device-resident output
+    h_aln_np = h_aln.numpy().view(capi.alignment_dt).reshape(-1)
+    same_scores = bool((h_aln_np["score"][: len(aln_np)] == aln_np["score"]).all())
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return 0
+
+    # ---- CPU baseline on a bounded sample (rank 0) ----
+    threads = os.cpu_count() or 1
+    _, flags = oracle_library()
+    sample_cap = min(n_reads, 6_000_000)
+    reads_np = h_reads[:sample_cap].numpy()
+    quals_np = h_quals[:sample_cap].numpy()
+    cpu_rate, cpu_sample, cpu_dt, cpu_res = cpu_map_rate(index, reads_np, quals_np, params, threads, target_seconds=args.cpu_seconds)
+    counters = cpu_res[4]
+    # parity of the timed GPU batch against the CPU run on the sample
+    got = (h_aln_np[:cpu_sample], h_maps.numpy().view(capi.mapping_dt).reshape(-1), h_edits.numpy().view(np.uint32), h_status.numpy()[:cpu_sample])
+    check_n = min(cpu_sample, 20000)
+    bad = H.compare_alignments(got, cpu_res, check_n)
+
+    B, terms = algorithmic_bytes_per_read(READ_LEN, counters, cpu_sample, maps_per_read, edits_per_read)
+    peaks = {}
+    try:
+        peaks = json.loads((ROOT / "MEASURED_PEAKS.json").read_text())
+    except Exception:
+        pass
+    peak = float(peaks.get("hbm_gbs", 6650.0))
+    peak_src = "measured (MEASURED_PEAKS.json hbm_gbs)" if "hbm_gbs" in peaks else "fallback 6.65 TB/s (B200_PROFILING.md)"
+    names = ["seed_kernel_pe", "extend_kernel", "align_kernel_pe", "compact"]
+    dom = int(np.argmax(last_stage))
+    chunk_reads = min(CHUNK, n_reads) if n_reads % CHUNK == 0 or n_reads < CHUNK else n_reads - (n_chunks - 1) * CHUNK
+    dom_ms = float(last_stage[dom])
+    achieved = B * chunk_reads / (dom_ms / 1e3) / 1e9 if dom_ms > 0 else None
+    traffic = None
+    try:
+        prof = json.loads((ROOT / "profiles" / "ncu_summary_r01.json").read_text())
+        traffic = prof.get(names[dom], {}).get("dram_bytes_per_launch")
+    except Exception:
+        pass
+
+    line = {
+        "metric": "giraffe reads/sec (150 bp PE, synthetic)", "value": value, "unit": "reads/s", "n_gpus": world,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": dev_ms, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "int32", "data": "synthetic",
+        "config": {
+            "workload": "configs[1]: 1 Mbp random graph, 1k SNP+indel variants, 8 haplotypes, nodes <= 32 bp, k=29 w=11; "
+                        "150 bp paired-end reads, fragment N(400,50) forced, 0.2 % substitutions",
+            "reads_per_gpu_per_step": n_reads, "pairs_per_gpu_per_step": n_reads // 2,
+            "mapper": "map_paired, vg giraffe defaults except --rescue-attempts 0 (attempt_rescue not built this round)",
+            "chunk_reads": CHUNK, "l2_policy": "inputs larger than L2 (3 GB of reads+qualities per step)",
+            "mapped_fraction": mapped_frac, "mapq60_fraction": mapq60, "status_errors": status_bad,
+            "parity_vs_cpu_sample": {"reads_checked": check_n, "mismatching_reads": len(bad)},
+            "e2e_equals_device_scores": same_scores,
+        },
+        "clocks": clocks,
+        "gpu_launches": int(launches),
+        "e2e": {"value": e2e_value, "unit": "reads/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
+                "ms_per_step": e2e_ms},
+        "roofline": {"bound": "hbm", "kernel": names[dom], "achieved": achieved, "peak": peak, "unit": "GB/s",
+                     "frac": (achieved / peak) if achieved else None, "traffic": traffic,
+                     "algorithmic_bytes_per_read": B, "terms": terms, "reads_per_launch": chunk_reads,
+                     "launch_ms": dom_ms, "peak_source": peak_src,
+                     "stage_ms_last_chunk": {n: float(x) for n, x in zip(names, last_stage)}},
+        "cpu_baseline": {"value": cpu_rate, "unit": "reads/s", "cores": threads, "kind": "port",
+                         "sample": f"{cpu_sample} reads ({cpu_sample // 2} pairs) of the same batch in {cpu_dt:.1f}s, oracle/ built {flags}, OpenMP over pairs"},
+    }
+    print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+    return 0
+
+
+if __name__ == "__main__":
+    sys.exit(main())

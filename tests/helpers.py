@@ -19,6 +19,18 @@ GOLDEN = ROOT / "tests" / "golden"
 _oracle = None
 
 
+def oracle_lib_configure(lib):
+    vp, u32 = C.c_void_p, C.c_uint32
+    lib.oracle_extend.argtypes = [C.POINTER(capi.FlatIndex), C.POINTER(capi.Scores), vp, u32, vp, u32, u32,
+                                  C.c_double, C.c_int, vp, u32, vp, u32, vp, u32]
+    lib.oracle_extend.restype = C.c_int
+    lib.oracle_bd_state.argtypes = [C.POINTER(capi.FlatIndex), u32, vp]
+    lib.oracle_bd_state.restype = C.c_int
+    lib.oracle_follow_paths.argtypes = [C.POINTER(capi.FlatIndex), vp, C.c_int, vp, C.c_int]
+    lib.oracle_follow_paths.restype = C.c_int
+    return lib
+
+
 def oracle_lib() -> C.CDLL:
     global _oracle
     if _oracle is None:
@@ -26,16 +38,7 @@ def oracle_lib() -> C.CDLL:
         if not path.exists():
             from vg_b200 import build
             build.build_oracle()
-        lib = C.CDLL(str(path))
-        vp, u32 = C.c_void_p, C.c_uint32
-        lib.oracle_extend.argtypes = [C.POINTER(capi.FlatIndex), C.POINTER(capi.Scores), vp, u32, vp, u32, u32,
-                                      C.c_double, C.c_int, vp, u32, vp, u32, vp, u32]
-        lib.oracle_extend.restype = C.c_int
-        lib.oracle_bd_state.argtypes = [C.POINTER(capi.FlatIndex), u32, vp]
-        lib.oracle_bd_state.restype = C.c_int
-        lib.oracle_follow_paths.argtypes = [C.POINTER(capi.FlatIndex), vp, C.c_int, vp, C.c_int]
-        lib.oracle_follow_paths.restype = C.c_int
-        _oracle = lib
+        _oracle = oracle_lib_configure(C.CDLL(str(path)))
     return _oracle
 
 
