@@ -179,21 +179,28 @@ def oracle_library(native=True):
 
 
 def cpu_map_rate(index, reads_np, quals_np, params, threads, target_seconds=15.0):
-    """reads/s of the CPU restatement on `threads` host threads over a bounded sample."""
+    """reads/s of the CPU restatement over a bounded sample; output buffers are allocated and touched
+    once, and the thread count is the best of {all logical CPUs, physical cores, 32, 16}."""
     import helpers as H
     n_total = reads_np.shape[0]
-    probe = min(n_total, 200_000)
+    probe = min(n_total, 400_000)
     probe -= probe % 2
-    out = None
-    t = time.time()
-    H.oracle_map_paired(index, reads_np[:probe], quals_np[:probe], params, threads=threads)
-    rate = probe / max(time.time() - t, 1e-6)
+    out = H.oracle_out_buffers(n_total, params)
+    H.oracle_map_paired(index, reads_np[:probe], quals_np[:probe], params, threads=threads, out=out)      # warm
+    best = (0.0, threads)
+    for th in sorted({threads, max(1, threads // 2), min(threads, 32), min(threads, 16)}, reverse=True):
+        t = time.time()
+        H.oracle_map_paired(index, reads_np[:probe], quals_np[:probe], params, threads=th, out=out)
+        r = probe / max(time.time() - t, 1e-6)
+        if r > best[0]:
+            best = (r, th)
+    rate, th = best
     sample = int(min(n_total, max(probe, rate * target_seconds)))
     sample -= sample % 2
     t = time.time()
-    res = H.oracle_map_paired(index, reads_np[:sample], quals_np[:sample], params, threads=threads)
+    res = H.oracle_map_paired(index, reads_np[:sample], quals_np[:sample], params, threads=th, out=out)
     dt = time.time() - t
-    return sample / dt, sample, dt, res
+    return sample / dt, sample, dt, res, th
 
 
 def algorithmic_bytes_per_read(L, counters, n_reads_sample, mappings_per_read, edits_per_read):
@@ -238,11 +245,12 @@ def main():
         threads = os.cpu_count() or 1
         sample = min(n_reads, 4_000_000)
         reads_np, quals_np = simulate_pairs_numpy(g, sample // 2, 22)
-        rate, used, dt, _ = cpu_map_rate(index, reads_np, quals_np, params, threads, target_seconds=min(args.cpu_seconds, 10.0))
+        rate, used, dt, _, threads = cpu_map_rate(index, reads_np, quals_np, params, threads, target_seconds=min(args.cpu_seconds, 10.0))
+        out = H.oracle_out_buffers(used, params)
         times = []
         for s in range(args.warmup + args.steps):
             t = time.time()
-            H.oracle_map_paired(index, reads_np[:used], quals_np[:used], params, threads=threads)
+            H.oracle_map_paired(index, reads_np[:used], quals_np[:used], params, threads=threads, out=out)
             if s >= args.warmup:
                 times.append(time.time() - t)
         ms = 1e3 * float(np.mean(times))
@@ -274,7 +282,8 @@ def main():
     dev = capi.Device(index, local_rank)
     lib = capi.load_library()
     params = H.paired_params(FRAG_MEAN, FRAG_SD)
-    stream = torch.cuda.current_stream(device)
+    stream = torch.cuda.Stream(device=device)          # the library's kernels and torch's events share this stream
+    torch.cuda.set_stream(stream)
     lib.gb_device_set_stream(dev.handle, C.c_void_p(stream.cuda_stream))
 
     t = time.time()
@@ -409,7 +418,7 @@ def main():
     sample_cap = min(n_reads, 6_000_000)
     reads_np = h_reads[:sample_cap].numpy()
     quals_np = h_quals[:sample_cap].numpy()
-    cpu_rate, cpu_sample, cpu_dt, cpu_res = cpu_map_rate(index, reads_np, quals_np, params, threads, target_seconds=args.cpu_seconds)
+    cpu_rate, cpu_sample, cpu_dt, cpu_res, threads = cpu_map_rate(index, reads_np, quals_np, params, threads, target_seconds=args.cpu_seconds)
     counters = cpu_res[4]
     # parity of the timed GPU batch against the CPU run on the sample
     got = (h_aln_np[:cpu_sample], h_maps.numpy().view(capi.mapping_dt).reshape(-1), h_edits.numpy().view(np.uint32), h_status.numpy()[:cpu_sample])
