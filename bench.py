@@ -154,6 +154,22 @@ class ClockSampler:
                 "reasons": sorted(reasons), "samples": len(sm)}
 
 
+def usable_cpus():
+    """Host CPUs this process may actually use: min(affinity, cgroup cpu.max quota)."""
+    n = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
+    note = f"{n} logical CPUs"
+    try:
+        quota, period = Path("/sys/fs/cgroup/cpu.max").read_text().split()
+        if quota != "max":
+            q = max(1, int(int(quota) / int(period)))
+            if q < n:
+                note = f"cgroup cpu.max quota {q} of {n} logical CPUs"
+                n = q
+    except Exception:
+        pass
+    return n, note
+
+
 def oracle_library(native=True):
     """liboracle.so, rebuilt with -march=native on this box when gcc is available (test infrastructure;
     only the cpu_baseline leg and --impl reference use it)."""
@@ -188,7 +204,7 @@ def cpu_map_rate(index, reads_np, quals_np, params, threads, target_seconds=15.0
     out = H.oracle_out_buffers(n_total, params)
     H.oracle_map_paired(index, reads_np[:probe], quals_np[:probe], params, threads=threads, out=out)      # warm
     best = (0.0, threads)
-    for th in sorted({threads, max(1, threads // 2), min(threads, 32), min(threads, 16)}, reverse=True):
+    for th in sorted({threads, max(1, threads // 2), 2 * threads}, reverse=True):
         t = time.time()
         H.oracle_map_paired(index, reads_np[:probe], quals_np[:probe], params, threads=th, out=out)
         r = probe / max(time.time() - t, 1e-6)
@@ -242,7 +258,7 @@ def main():
         g, index = make_graph_and_index()
         params = H.paired_params(FRAG_MEAN, FRAG_SD)
         lib, flags = oracle_library()
-        threads = os.cpu_count() or 1
+        threads, cpu_note = usable_cpus()
         sample = min(n_reads, 4_000_000)
         reads_np, quals_np = simulate_pairs_numpy(g, sample // 2, 22)
         rate, used, dt, _, threads = cpu_map_rate(index, reads_np, quals_np, params, threads, target_seconds=min(args.cpu_seconds, 10.0))
@@ -261,7 +277,7 @@ def main():
             "scaling": "weak", "vs_baseline": None, "dtype": "int32", "data": "synthetic",
             "config": {"workload": "configs[1]: 1 Mbp / 1k-variant graph, 150 bp PE reads, fragment N(400,50) forced, rescue attempts 0",
                        "reads_per_step": used, "note": "CPU restatement of vg giraffe (oracle/, OpenMP over read pairs); vg itself cannot be built in this image"},
-            "cpu_baseline": {"value": value, "unit": "reads/s", "cores": threads, "kind": "port", "sample": f"{used} reads per step, {flags}"},
+            "cpu_baseline": {"value": value, "unit": "reads/s", "cores": threads, "kind": "port", "sample": f"{used} reads per step, {flags}, {cpu_note}"},
             "e2e": {"value": value, "unit": "reads/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         }
         print(json.dumps(line), flush=True)
@@ -269,7 +285,7 @@ def main():
 
     import torch
     import torch.distributed as dist
-    from vg_b200 import capi
+    from vg_b200 import capi, shard
 
     if not torch.cuda.is_available():
         raise SystemExit("bench.py: no CUDA device (the product path has no CPU fallback)")
@@ -386,10 +402,8 @@ def main():
     for _ in range(args.steps):
         e2e_step()
         if world > 1:
-            # final alignment emission: fixed-width records gathered on rank 0 over NVLink
-            hdr = d_aln if True else None
-            gather_list = [torch.empty_like(d_aln) for _ in range(world)] if rank == 0 else None
-            dist.gather(d_aln, gather_list, dst=0)
+            # final alignment emission: fixed-width records gathered on rank 0 over NVLink (NCCL)
+            shard.gather_headers(d_aln, rank, world)
     ev2[1].record(stream)
     barrier()
     e2e_ms_dev = ev2[0].elapsed_time(ev2[1]) / args.steps
@@ -413,7 +427,7 @@ def main():
         return 0
 
     # ---- CPU baseline on a bounded sample (rank 0) ----
-    threads = os.cpu_count() or 1
+    threads, cpu_note = usable_cpus()
     _, flags = oracle_library()
     sample_cap = min(n_reads, 6_000_000)
     reads_np = h_reads[:sample_cap].numpy()
@@ -469,7 +483,7 @@ def main():
                      "launch_ms": dom_ms, "peak_source": peak_src,
                      "stage_ms_last_chunk": {n: float(x) for n, x in zip(names, last_stage)}},
         "cpu_baseline": {"value": cpu_rate, "unit": "reads/s", "cores": threads, "kind": "port",
-                         "sample": f"{cpu_sample} reads ({cpu_sample // 2} pairs) of the same batch in {cpu_dt:.1f}s, oracle/ built {flags}, OpenMP over pairs"},
+                         "sample": f"{cpu_sample} reads ({cpu_sample // 2} pairs) of the same batch in {cpu_dt:.1f}s, oracle/ built {flags}, OpenMP over pairs, {cpu_note}"},
     }
     print(json.dumps(line), flush=True)
     if world > 1:

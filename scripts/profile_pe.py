@@ -1,0 +1,29 @@
+"""Small paired-end run of the device-resident path for ncu (config-2 graph)."""
+import ctypes as C, sys
+sys.path.insert(0, "."); sys.path.insert(0, "tests")
+import numpy as np, torch
+import helpers as H, bench
+from vg_b200 import capi
+n = int(sys.argv[1]) if len(sys.argv) > 1 else 400000
+iters = int(sys.argv[2]) if len(sys.argv) > 2 else 2
+g, index = bench.make_graph_and_index()
+device = torch.device("cuda", 0)
+dev = capi.Device(index, 0)
+lib = capi.load_library()
+p = H.paired_params(400.0, 50.0)
+stream = torch.cuda.Stream(device=device); torch.cuda.set_stream(stream)
+lib.gb_device_set_stream(dev.handle, C.c_void_p(stream.cuda_stream))
+d_reads, d_quals = bench.simulate_pairs_torch(g, n // 2, 22, device)
+off = torch.arange(n + 1, dtype=torch.int64, device=device) * 150
+d_aln = torch.zeros((n, 32), dtype=torch.uint8, device=device)
+d_maps = torch.zeros((n * 14, 8), dtype=torch.uint8, device=device)
+d_edits = torch.zeros((n * 20,), dtype=torch.int32, device=device)
+d_status = torch.zeros((n,), dtype=torch.uint8, device=device)
+d_tot = torch.zeros((2,), dtype=torch.int64, device=device)
+for it in range(iters):
+    rc = lib.gb_map_batch_device(dev.handle, C.byref(p), 1, n, C.c_void_p(d_reads.data_ptr()), C.c_void_p(d_quals.data_ptr()),
+                                 C.c_void_p(off.data_ptr()), 150, C.c_void_p(d_aln.data_ptr()), C.c_void_p(d_maps.data_ptr()), n * 14,
+                                 C.c_void_p(d_edits.data_ptr()), n * 20, C.c_void_p(d_status.data_ptr()), C.c_void_p(d_tot.data_ptr()))
+    assert rc == 0
+    torch.cuda.synchronize()
+    print("stage ms", dev.stage_times(), flush=True)
