@@ -16,6 +16,8 @@ struct AlignArgs {
     uint32_t tb_cells;
     // paired-end
     const PairState* pairs; double frag_mean, frag_sd;
+    // work list written by the thread-per-pair fast path (nullptr: every pair)
+    const uint32_t* slow_list; const uint32_t* slow_count;
 };
 
 constexpr uint32_t N_SLOTS = 2 * MAX_CANDS + 8;   // candidate path slots per warp (both mates of a pair)

@@ -114,6 +114,7 @@ align_kernel(DevIndex ix, MapParamsDev P, DevScores sc, MapBatch b, AlignArgs a)
 }
 
 #include "map_paired.cuh"
+#include "align_fast.cuh"
 #include "compact.cuh"
 
 // AlignmentScorer::recover_log_base (alignment_scorer.cpp:30-99), gc 0.5, tol 1e-12.
@@ -298,7 +299,19 @@ int map_device(gb_device* d, const gb_map_params* hp, uint32_t n_reads, const ui
         a.aln = d_aln; a.maps = d_maps; a.edits = d_edits; a.status = d_status; a.tb_cells = tb_cells;
         a.pairs = paired ? d->p_pairs.ptr : nullptr; a.frag_mean = hp->fragment_mean; a.frag_sd = hp->fragment_stdev;
         MapBatch b3 = b; b3.work_counter = cur + 6;
-        if (paired) align_kernel_pe<<<grid, ALIGN_WARPS * 32, smem, d->stream>>>(d->ix, P, d->sc, b3, a);
+        a.slow_list = nullptr; a.slow_count = nullptr;
+        if (paired) {
+            // thread-per-pair fast path first; whatever it cannot finish goes to the warp-per-pair kernel
+            if ((rc = d->p_slow.reserve(n_reads / 2 + 1))) return rc;
+            FastArgs fa; fa.slow_list = d->p_slow.ptr; fa.slow_count = cur + 7;
+            const uint32_t n_pairs = n_reads / 2;
+            const uint32_t fgrid = std::max<uint32_t>(1u, std::min<uint32_t>((n_pairs + 127) / 128, (uint32_t)d->n_sms * 16));
+            align_fast_kernel_pe<<<fgrid, 128, 0, d->stream>>>(d->ix, P, d->sc, b3, a, fa);
+            d->launches++;
+            GB_CUDA(cudaGetLastError());
+            a.slow_list = d->p_slow.ptr; a.slow_count = cur + 7;
+            align_kernel_pe<<<grid, ALIGN_WARPS * 32, smem, d->stream>>>(d->ix, P, d->sc, b3, a);
+        }
         else align_kernel<<<grid, ALIGN_WARPS * 32, smem, d->stream>>>(d->ix, P, d->sc, b3, a);
         d->launches++;
         GB_CUDA(cudaGetLastError());

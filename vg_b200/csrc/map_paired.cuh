@@ -91,7 +91,10 @@ align_kernel_pe(DevIndex ix, MapParamsDev P, DevScores sc, MapBatch b, AlignArgs
 
     while (true) {
         uint32_t p = 0;
-        if (lane == 0) p = atomicAdd(b.work_counter, 1u);
+        if (lane == 0) {
+            p = atomicAdd(b.work_counter, 1u);
+            if (a.slow_list) p = p < *a.slow_count ? a.slow_list[p] : 0xffffffffu;
+        }
         p = __shfl_sync(FULL, p, 0);
         if (p >= n_pairs) break;
         ReadState rs[2] = {b.states[2 * p], b.states[2 * p + 1]};
