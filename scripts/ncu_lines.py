@@ -8,7 +8,7 @@ out = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv", "--print-so
 rows = list(csv.reader(io.StringIO(out)))
 fname = None; data = []; hdr = None
 for r in rows:
-    if len(r) >= 2 and r[0] == "File Name":
+    if len(r) >= 2 and r[0] in ("File Name", "File Path"):
         fname = r[1].split("/")[-1]; continue
     if len(r) > 8 and r[0] == "Line No":
         hdr = r; continue
@@ -23,3 +23,13 @@ tots = sum(d[1] for d in data) or 1
 print(f"kernel ~{kern}: {tot} warp instructions attributed, {tots} samples")
 for n, s, f, ln, src in sorted(data, reverse=True)[:top]:
     print(f"{100*n/tot:5.1f}% inst {100*s/tots:5.1f}% samp  {f}:{ln}  {src}")
+
+# optional 4th argument: "file:lo-hi=name,..." ranges to aggregate (phase breakdown)
+if len(sys.argv) > 4:
+    print("phase breakdown:")
+    for spec in sys.argv[4].split(","):
+        rng, name = spec.split("=")
+        f, lh = rng.split(":"); lo, hi = map(int, lh.split("-"))
+        n = sum(d[0] for d in data if d[2] == f and lo <= d[3] <= hi)
+        s = sum(d[1] for d in data if d[2] == f and lo <= d[3] <= hi)
+        print(f"{100*n/tot:5.1f}% inst {100*s/tots:5.1f}% samp  {name} ({rng})")

@@ -82,3 +82,14 @@ def test_paired_rescue_is_refused_loudly():
     with pytest.raises(capi.GbError):
         H.gpu_map(dev, rs.reads, rs.quals, p, paired=True)
     dev.close()
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("tables", ["16,1", "8,2"])
+def test_map_paired_parity_through_the_seeding_retry_pass(tables, monkeypatch):
+    """First-pass seeding tables too small for most pairs: they are retried at full size by the
+    second launch and must come out identical."""
+    monkeypatch.setenv("GIRAFFE_B200_SEED_TABLES", tables)
+    g = synth.make_variant_graph(length=100000, n_snp=160, n_ins=20, n_del=20, n_haps=8, seed=5)
+    rs = synth.simulate_pairs(g, 1200, sub_rate=0.01, seed=51)
+    _run(g, rs, H.paired_params())

@@ -82,3 +82,12 @@ def test_map_edge_cases():
     bad = H.compare_alignments(got, want, len(reads))
     assert not bad, bad[0]
     dev.close()
+
+
+@pytest.mark.gpu
+def test_map_parity_through_the_seeding_retry_pass(monkeypatch):
+    """First-pass seeding tables too small for most reads -> second launch at full size."""
+    monkeypatch.setenv("GIRAFFE_B200_SEED_TABLES", "16,1")
+    g = synth.make_variant_graph(length=100000, n_snp=160, n_ins=20, n_del=20, n_haps=8, seed=5)
+    rs = synth.simulate_reads(g, 1500, length=150, sub_rate=0.01, seed=52)
+    _run(g, rs)

@@ -1,6 +1,9 @@
 // capi.cu — C-ABI entry points of libgiraffe_b200.so (see include/giraffe_b200.h) and the
 // kernels' launch wrappers.  There is no CPU fallback anywhere in this file: without a
 // CUDA device every compute entry point returns GB_ERR_NO_DEVICE.
+#include <cstdlib>
+#include <cstdio>
+#include <algorithm>
 #include "giraffe_b200.h"
 #include "device_state.cuh"
 #include "extend.cuh"
@@ -36,7 +39,7 @@ struct ExtendBatch {
     const DevItem* items; const uint32_t* n_items_dev;
 };
 
-__global__ void __launch_bounds__(EXTEND_WARPS * 32)
+__global__ void __launch_bounds__(EXTEND_WARPS * 32, 3)
 extend_kernel(DevIndex ix, ExtendParams p, ExtendBatch b, ExtendWorkspace ws) {
     extern __shared__ __align__(16) uint8_t smem[];
     const int warp_in_block = threadIdx.x >> 5;
@@ -102,6 +105,13 @@ extern "C" int gb_device_create(const gb_flat_index* ix, int device_ordinal, gb_
     cudaDeviceProp prop;
     GB_CUDA(cudaGetDeviceProperties(&prop, device_ordinal));
     d->n_sms = prop.multiProcessorCount;
+    if (const char* env = std::getenv("GIRAFFE_B200_SEED_TABLES")) {
+        unsigned mc = 0, cc = 0;
+        if (std::sscanf(env, "%u,%u", &mc, &cc) == 2 && mc >= 2 && cc >= 1) {
+            d->seed_mc = std::min<uint32_t>(gb::MAX_MINIMIZERS, (mc + 7u) & ~7u);
+            d->seed_cc = std::min<uint32_t>(64u, cc);
+        }
+    }
     GB_CUDA(cudaStreamCreateWithFlags(&d->own_stream, cudaStreamNonBlocking));
     d->stream = d->own_stream;
     for (int i = 0; i < 5; i++) GB_CUDA(cudaEventCreate(&d->ev_stage[i]));

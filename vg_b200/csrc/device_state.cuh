@@ -60,6 +60,8 @@ struct DevBuf {
 struct gb_device {
     int device = 0;
     int n_sms = 0;
+    // first-pass seeding table sizes (minimizers, clusters per read); GIRAFFE_B200_SEED_TABLES="Mc,Cc" overrides
+    uint32_t seed_mc = 64, seed_cc = 16;
     cudaStream_t stream = nullptr, own_stream = nullptr;
     cudaEvent_t ev_stage[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
@@ -89,6 +91,7 @@ struct gb_device {
     gb::DevBuf<gb_extension> p_ext;
     gb::DevBuf<uint8_t> ws_tail, ws_cand, w_reads, w_quals;
     gb::DevBuf<gb::PairState> p_pairs;
+    gb::DevBuf<uint32_t> p_retry;         // units the first seeding pass could not fit
     gb::DevBuf<uint32_t> p_slow;          // pairs routed to the warp-per-pair align kernel
     gb::DevBuf<gb_mapping> pad_maps;
     gb::DevBuf<uint32_t> pad_edits;
@@ -104,7 +107,7 @@ struct gb_device {
         ws_queue.release(); ws_arena.release();
         t_hit.release(); t_plo.release(); t_phred.release(); p_states.release(); p_min.release(); p_seeds.release();
         p_items.release(); p_ext_seeds.release(); p_cursors.release(); p_ext_count.release(); p_path.release(); p_mism.release();
-        p_ext_status.release(); p_ext.release(); ws_tail.release(); ws_cand.release(); w_reads.release(); w_quals.release(); p_pairs.release(); p_slow.release();
+        p_ext_status.release(); p_ext.release(); ws_tail.release(); ws_cand.release(); w_reads.release(); w_quals.release(); p_pairs.release(); p_slow.release(); p_retry.release();
         pad_maps.release(); pad_edits.release(); c_map_off.release(); c_edit_off.release(); c_totals.release(); c_tmp.release();
         io_reads.release(); io_quals.release(); io_status.release(); io_read_off.release(); io_aln.release(); io_maps.release(); io_edits.release();
     }

@@ -30,19 +30,27 @@ struct MapBatch {
     ReadState* states;
     uint32_t* work_counter;
     uint32_t Lc;
+    // seeding passes: units (reads or pairs) come from in_list when set; units that overflow the
+    // first pass's small shared tables (Mc, Cc) are appended to retry_list
+    const uint32_t* in_list; const uint32_t* in_count;
+    uint32_t* retry_list; uint32_t* retry_count;
+    uint32_t Mc, Cc;
 };
 
 // ---------------------------------------------------------------------------------------
 // K1
 // ---------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(SEED_WARPS * 32)
+__global__ void __launch_bounds__(SEED_WARPS * 32, 8)
 seed_kernel(DevIndex ix, MapParamsDev P, MapBatch b, SeedPools pools) {
     extern __shared__ __align__(16) uint8_t smem[];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const SeedSmem sm = carve_seed_smem(smem + (size_t)warp * seed_smem_bytes(b.Lc), b.Lc);
+    const SeedSmem sm = carve_seed_smem(smem + (size_t)warp * seed_smem_bytes(b.Lc, b.Mc, b.Cc), b.Lc, b.Mc, b.Cc);
     while (true) {
         uint32_t r = 0;
-        if (lane == 0) r = atomicAdd(b.work_counter, 1u);
+        if (lane == 0) {
+            r = atomicAdd(b.work_counter, 1u);
+            if (b.in_list) r = r < *b.in_count ? b.in_list[r] : 0xffffffffu;
+        }
         r = __shfl_sync(FULL, r, 0);
         if (r >= b.n_reads) break;
         const uint64_t rb = b.read_off[r];
@@ -59,6 +67,11 @@ seed_kernel(DevIndex ix, MapParamsDev P, MapBatch b, SeedPools pools) {
             status = seed_phase_a(ix, P, sm, L, pools, rng, rs);
             if (status == GB_ITEM_OK) status = cluster_phase_se(ix, P, sm, L, r, pools, rng, rs);
             rs.rng = rng;
+        }
+        if (status == GB_ITEM_RETRY) {
+            if (lane == 0) b.retry_list[atomicAdd(b.retry_count, 1u)] = r;
+            __syncwarp();
+            continue;
         }
         rs.status = status;
         if (status != GB_ITEM_OK) { rs.item_cnt = 0; }
@@ -226,6 +239,7 @@ int map_device(gb_device* d, const gb_map_params* hp, uint32_t n_reads, const ui
     }
     MapBatch b; b.reads = d_reads; b.quals = d_quals; b.read_off = d_read_off; b.n_reads = n_reads;
     b.states = d->p_states.ptr; b.work_counter = cur + 0; b.Lc = Lc;
+    b.in_list = nullptr; b.in_count = nullptr; b.retry_list = nullptr; b.retry_count = nullptr; b.Mc = MAX_MINIMIZERS; b.Cc = MAX_CLUSTERS;
     SeedPools pools;
     pools.minimizers = d->p_min.ptr; pools.min_cap = (uint32_t)min_cap; pools.min_cursor = cur + 1;
     pools.seeds = d->p_seeds.ptr; pools.seed_cap = (uint32_t)seed_cap; pools.seed_cursor = cur + 2;
@@ -233,24 +247,34 @@ int map_device(gb_device* d, const gb_map_params* hp, uint32_t n_reads, const ui
     pools.ext_seeds = d->p_ext_seeds.ptr; pools.ext_cap = (uint32_t)ext_cap; pools.ext_cursor = cur + 4;
 
     GB_CUDA(cudaEventRecord(d->ev_stage[0], d->stream));
-    // ---- K1 ----
+    // ---- K1: a first pass with small shared tables (8 blocks per SM), then the units that did not
+    // fit (many minimizers or clusters) once more at the maximum table sizes ----
     {
-        const size_t smem = seed_smem_bytes(Lc) * SEED_WARPS;
-        if (smem > 48 * 1024) {
-            GB_CUDA(cudaFuncSetAttribute(seed_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-            GB_CUDA(cudaFuncSetAttribute(seed_kernel_pe, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        const uint32_t n_units = paired ? n_reads / 2 : n_reads;
+        if ((rc = d->p_retry.reserve(n_units + 1))) return rc;
+        for (int pass = 0; pass < 2; pass++) {
+            MapBatch bp = b;
+            bp.Mc = pass == 0 ? d->seed_mc : MAX_MINIMIZERS; bp.Cc = pass == 0 ? d->seed_cc : MAX_CLUSTERS;
+            bp.work_counter = pass == 0 ? cur + 0 : cur + 9;
+            bp.in_list = pass == 0 ? nullptr : d->p_retry.ptr; bp.in_count = pass == 0 ? nullptr : cur + 8;
+            bp.retry_list = d->p_retry.ptr; bp.retry_count = pass == 0 ? cur + 8 : cur + 10;
+            const size_t smem = seed_smem_bytes(Lc, bp.Mc, bp.Cc) * SEED_WARPS;
+            if (smem > 48 * 1024) {
+                GB_CUDA(cudaFuncSetAttribute(seed_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+                GB_CUDA(cudaFuncSetAttribute(seed_kernel_pe, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            }
+            int bps = 0;
+            if (paired) GB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bps, seed_kernel_pe, SEED_WARPS * 32, smem));
+            else GB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bps, seed_kernel, SEED_WARPS * 32, smem));
+            if (bps < 1) bps = 1;
+            uint32_t grid = std::min<uint32_t>((uint32_t)(d->n_sms * bps), (n_units + SEED_WARPS - 1) / SEED_WARPS);
+            if (grid == 0) grid = 1;
+            if (paired) { PairBatch pbatch; pbatch.pairs = d->p_pairs.ptr; pbatch.fragment_limit = fragment_limit;
+                          seed_kernel_pe<<<grid, SEED_WARPS * 32, smem, d->stream>>>(d->ix, P, bp, pools, pbatch); }
+            else seed_kernel<<<grid, SEED_WARPS * 32, smem, d->stream>>>(d->ix, P, bp, pools);
+            d->launches++;
+            GB_CUDA(cudaGetLastError());
         }
-        int bps = 0;
-        if (paired) GB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bps, seed_kernel_pe, SEED_WARPS * 32, smem));
-        else GB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bps, seed_kernel, SEED_WARPS * 32, smem));
-        if (bps < 1) bps = 1;
-        uint32_t grid = std::min<uint32_t>((uint32_t)(d->n_sms * bps), (n_reads + SEED_WARPS - 1) / SEED_WARPS);
-        if (grid == 0) grid = 1;
-        if (paired) { PairBatch pbatch; pbatch.pairs = d->p_pairs.ptr; pbatch.fragment_limit = fragment_limit;
-                      seed_kernel_pe<<<grid, SEED_WARPS * 32, smem, d->stream>>>(d->ix, P, b, pools, pbatch); }
-        else seed_kernel<<<grid, SEED_WARPS * 32, smem, d->stream>>>(d->ix, P, b, pools);
-        d->launches++;
-        GB_CUDA(cudaGetLastError());
     }
     GB_CUDA(cudaEventRecord(d->ev_stage[1], d->stream));
     // ---- K2: extension over the items produced on the device ----

@@ -26,15 +26,18 @@ struct PairBatch {
     int32_t fragment_limit;
 };
 
-__global__ void __launch_bounds__(SEED_WARPS * 32)
+__global__ void __launch_bounds__(SEED_WARPS * 32, 8)
 seed_kernel_pe(DevIndex ix, MapParamsDev P, MapBatch b, SeedPools pools, PairBatch pb) {
     extern __shared__ __align__(16) uint8_t smem[];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const SeedSmem sm = carve_seed_smem(smem + (size_t)warp * seed_smem_bytes(b.Lc), b.Lc);
+    const SeedSmem sm = carve_seed_smem(smem + (size_t)warp * seed_smem_bytes(b.Lc, b.Mc, b.Cc), b.Lc, b.Mc, b.Cc);
     const uint32_t n_pairs = b.n_reads / 2;
     while (true) {
         uint32_t p = 0;
-        if (lane == 0) p = atomicAdd(b.work_counter, 1u);
+        if (lane == 0) {
+            p = atomicAdd(b.work_counter, 1u);
+            if (b.in_list) p = p < *b.in_count ? b.in_list[p] : 0xffffffffu;
+        }
         p = __shfl_sync(FULL, p, 0);
         if (p >= n_pairs) break;
         ReadState rs[2]; PairState ps;
@@ -62,6 +65,11 @@ seed_kernel_pe(DevIndex ix, MapParamsDev P, MapBatch b, SeedPools pools, PairBat
             }
             if (status == GB_ITEM_OK) status = cluster_phase_pe(ix, P, sm, L[0], L[1], 2 * p, pb.fragment_limit, pools, rng, rs[0], rs[1], ps);
             rs[0].rng = rng; rs[1].rng = rng;
+        }
+        if (status == GB_ITEM_RETRY) {
+            if (lane == 0) b.retry_list[atomicAdd(b.retry_count, 1u)] = p;
+            __syncwarp();
+            continue;
         }
         rs[0].status = rs[1].status = status;
         if (status != GB_ITEM_OK) { rs[0].item_cnt = rs[1].item_cnt = 0; }

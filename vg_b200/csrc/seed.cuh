@@ -17,7 +17,8 @@
 
 namespace gb {
 
-constexpr uint32_t MAX_CLUSTERS = 64;     // read clusters per read kept in shared memory
+constexpr uint32_t MAX_CLUSTERS = 64;     // read clusters per read kept in shared memory (second-pass capacity)
+constexpr uint32_t GB_ITEM_RETRY = 100;   // internal: did not fit the small first-pass tables
 
 struct SeedPools {
     DevMinimizer* minimizers; uint32_t min_cap;  uint32_t* min_cursor;
@@ -50,51 +51,57 @@ struct SeedSmem {
     uint32_t* c_present;   // [2 * MAX_CLUSTERS * PRESENT_WORDS]
     uint8_t*  c_order;     // [2 * MAX_CLUSTERS] processing order
     uint8_t*  c_frag;      // [2 * MAX_CLUSTERS] fragment id of each read cluster
-    uint8_t*  scratch;     // [2 * MAX_CLUSTERS + MAX_MINIMIZERS]
+    uint8_t*  scratch;     // [2 * Cc + Mc]
+    // capacities of this launch: Mc minimizers per read, Cc clusters per read.  The first launch uses
+    // small tables (occupancy); units that do not fit are retried by a second launch at the maxima.
+    uint32_t Mc, Cc;
 };
 
-__host__ __device__ inline size_t seed_smem_bytes(uint32_t Lc) {
+__host__ __device__ inline size_t seed_smem_bytes(uint32_t Lc, uint32_t Mc, uint32_t Cc) {
     size_t b = 0;
     b += (size_t)Lc * 8 * 2;                            // khash, kkey
-    b += (size_t)MAX_MINIMIZERS * (8 + 8 + 8);          // m_key, m_hash, m_score
-    b += (size_t)2 * MAX_CLUSTERS * (8 + 8);            // c_score, c_cov
-    b += (size_t)MAX_MINIMIZERS * (4 + 4);              // hit_off, hit_cnt
-    b += (size_t)2 * MAX_CLUSTERS * 4 * (1 + PRESENT_WORDS);
-    b += (size_t)MAX_MINIMIZERS * (2 + 2 + 2);          // fwd, agg_start, agg_len
+    b += (size_t)Mc * (8 + 8 + 8);                      // m_key, m_hash, m_score
+    b += (size_t)2 * Cc * (8 + 8);                      // c_score, c_cov
+    b += (size_t)Mc * (4 + 4);                          // hit_off, hit_cnt
+    b += (size_t)2 * Cc * 4 * (1 + PRESENT_WORDS);
+    b += (size_t)Mc * (2 + 2 + 2);                      // fwd, agg_start, agg_len
     b += (size_t)Lc * 2;                                // read, kflag
-    b += (size_t)MAX_MINIMIZERS * 3;                    // rev, order, pass
-    b += (size_t)2 * MAX_CLUSTERS * 2;                  // c_order, c_frag
-    b += (size_t)2 * MAX_CLUSTERS + MAX_MINIMIZERS;     // scratch
+    b += (size_t)Mc * 3;                                // rev, order, pass
+    b += (size_t)2 * Cc * 2;                            // c_order, c_frag
+    b += (size_t)2 * Cc + Mc;                           // scratch
     return (b + 15) & ~(size_t)15;
 }
 
-__device__ inline SeedSmem carve_seed_smem(uint8_t* base, uint32_t Lc) {
+// Lc, Mc, Cc are multiples of 8, so every array below stays naturally aligned.
+__device__ inline SeedSmem carve_seed_smem(uint8_t* base, uint32_t Lc, uint32_t Mc, uint32_t Cc) {
     SeedSmem s;
     uint8_t* p = base;
+    s.Mc = Mc; s.Cc = Cc;
     s.khash = (uint64_t*)p; p += (size_t)Lc * 8;
     s.kkey = (uint64_t*)p; p += (size_t)Lc * 8;
-    s.m_key = (uint64_t*)p; p += MAX_MINIMIZERS * 8;
-    s.m_hash = (uint64_t*)p; p += MAX_MINIMIZERS * 8;
-    s.m_score = (double*)p; p += MAX_MINIMIZERS * 8;
-    s.c_score = (double*)p; p += 2 * MAX_CLUSTERS * 8;
-    s.c_cov = (double*)p; p += 2 * MAX_CLUSTERS * 8;
-    s.m_hit_off = (uint32_t*)p; p += MAX_MINIMIZERS * 4;
-    s.m_hit_cnt = (uint32_t*)p; p += MAX_MINIMIZERS * 4;
-    s.c_label = (uint32_t*)p; p += 2 * MAX_CLUSTERS * 4;
-    s.c_present = (uint32_t*)p; p += 2 * MAX_CLUSTERS * 4 * PRESENT_WORDS;
-    s.m_fwd = (uint16_t*)p; p += MAX_MINIMIZERS * 2;
-    s.m_agg_start = (uint16_t*)p; p += MAX_MINIMIZERS * 2;
-    s.m_agg_len = (uint16_t*)p; p += MAX_MINIMIZERS * 2;
+    s.m_key = (uint64_t*)p; p += Mc * 8;
+    s.m_hash = (uint64_t*)p; p += Mc * 8;
+    s.m_score = (double*)p; p += Mc * 8;
+    s.c_score = (double*)p; p += 2 * Cc * 8;
+    s.c_cov = (double*)p; p += 2 * Cc * 8;
+    s.m_hit_off = (uint32_t*)p; p += Mc * 4;
+    s.m_hit_cnt = (uint32_t*)p; p += Mc * 4;
+    s.c_label = (uint32_t*)p; p += 2 * Cc * 4;
+    s.c_present = (uint32_t*)p; p += 2 * Cc * 4 * PRESENT_WORDS;
+    s.m_fwd = (uint16_t*)p; p += Mc * 2;
+    s.m_agg_start = (uint16_t*)p; p += Mc * 2;
+    s.m_agg_len = (uint16_t*)p; p += Mc * 2;
     s.read = p; p += Lc;
     s.kflag = p; p += Lc;
-    s.m_rev = p; p += MAX_MINIMIZERS;
-    s.m_order = p; p += MAX_MINIMIZERS;
-    s.m_pass = p; p += MAX_MINIMIZERS;
-    s.c_order = p; p += 2 * MAX_CLUSTERS;
-    s.c_frag = p; p += 2 * MAX_CLUSTERS;
-    s.scratch = p; p += 2 * MAX_CLUSTERS + MAX_MINIMIZERS;
+    s.m_rev = p; p += Mc;
+    s.m_order = p; p += Mc;
+    s.m_pass = p; p += Mc;
+    s.c_order = p; p += 2 * Cc;
+    s.c_frag = p; p += 2 * Cc;
+    s.scratch = p; p += 2 * Cc + Mc;
     return s;
 }
+__device__ __forceinline__ uint32_t table_full(uint32_t have, uint32_t max_cap) { return have < max_cap ? GB_ITEM_RETRY : (uint32_t)GB_ITEM_OUT_FULL; }
 
 __device__ __forceinline__ uint32_t pow13(uint32_t e) {
     uint32_t r = 1, b = 13;
@@ -206,7 +213,7 @@ __device__ inline uint32_t seed_phase_a(const DevIndex& ix, const MapParamsDev& 
             }
             const uint32_t bal = __ballot_sync(FULL, is_min);
             const uint32_t cnt = __popc(bal);
-            if (M + cnt > MAX_MINIMIZERS) return GB_ITEM_OUT_FULL;
+            if (M + cnt > sm.Mc) return table_full(sm.Mc, MAX_MINIMIZERS);
             if (is_min) {
                 const uint32_t idx = M + __popc(bal & ((1u << lane) - 1u));
                 sm.m_key[idx] = sm.kkey[s]; sm.m_hash[idx] = sm.khash[s];
@@ -251,8 +258,8 @@ __device__ inline uint32_t seed_phase_a(const DevIndex& ix, const MapParamsDev& 
 
     // ---- shuffle the runs tied at the top score (sort_shuffling_ties over runs) ----------------------
     uint8_t* run_begin = reinterpret_cast<uint8_t*>(sm.khash);          // khash/kkey are dead: scratch
-    uint8_t* run_len = run_begin + MAX_MINIMIZERS;
-    uint8_t* tmp_order = run_len + MAX_MINIMIZERS;
+    uint8_t* run_len = run_begin + sm.Mc;
+    uint8_t* tmp_order = run_len + sm.Mc;
     if (lane == 0) {
         const double top = sm.m_score[sm.m_order[0]];
         uint32_t T = 0, pos = 0;
@@ -293,7 +300,11 @@ __device__ inline uint32_t seed_phase_a(const DevIndex& ix, const MapParamsDev& 
         const uint32_t num_min_by_read_len = L / P.num_bp_per_min;
         uint32_t* cov = reinterpret_cast<uint32_t*>(sm.kkey);          // read_coverage bit vector
         const uint32_t cov_words = (L + 31) / 32;
-        for (uint32_t x = 0; x < cov_words; x++) cov[x] = 0;
+        // the coverage vector is only consulted once num_minimizers reaches the cap below, which the
+        // M minimizers of this read cannot do when M <= cap: skip its upkeep then
+        const uint32_t unique_cap = max(P.max_unique_min, num_min_by_read_len);
+        const bool track_cov = M > unique_cap;
+        if (track_cov) for (uint32_t x = 0; x < cov_words; x++) cov[x] = 0;
         for (uint32_t i = 0; i < M; i++) {
             const uint32_t a = sm.m_order[i];
             if (i >= limit) {
@@ -309,8 +320,8 @@ __device__ inline uint32_t seed_phase_a(const DevIndex& ix, const MapParamsDev& 
                 const uint32_t fwd = sm.m_fwd[a];
                 const uint32_t cs = fwd < P.minimizer_coverage_flank ? 0 : fwd - P.minimizer_coverage_flank;
                 const uint32_t ce = min(L, fwd + k + P.minimizer_coverage_flank);
-                if (num_minimizers < max(P.max_unique_min, num_min_by_read_len)) {
-                    set_bit_range(cov, cs, ce);
+                if (num_minimizers < unique_cap) {
+                    if (track_cov) set_bit_range(cov, cs, ce);
                     worst_kept_hits = max(hits, worst_kept_hits);
                 } else if (hits > worst_kept_hits) {
                     passing = false;
@@ -416,7 +427,7 @@ __device__ inline uint32_t collect_clusters(const SeedSmem& sm, const DevSeed* s
         const uint32_t i = base + lane;
         const bool root = i < H && seeds[i].label == i;
         const uint32_t bal = __ballot_sync(FULL, root);
-        if (Cn + __popc(bal) > MAX_CLUSTERS) return 0xffffffffu;
+        if (Cn + __popc(bal) > sm.Cc) return 0xffffffffu;
         if (root) sm.c_label[cbase + Cn + __popc(bal & ((1u << lane) - 1u))] = i;
         Cn += __popc(bal);
     }
@@ -507,7 +518,7 @@ __device__ inline uint32_t cluster_phase_se(const DevIndex& ix, const MapParamsD
     const int32_t limit = (int32_t)max(P.distance_limit, L + 50);      // get_distance_limit, minimizer_mapper.hpp:554
     propagate_labels(seeds, H, seeds, 0, limit);
     const uint32_t Cn = collect_clusters(sm, seeds, H, mins, M, ix.k, L, 0);
-    if (Cn == 0xffffffffu) return GB_ITEM_OUT_FULL;
+    if (Cn == 0xffffffffu) return table_full(sm.Cc, MAX_CLUSTERS);
     rs.n_clusters = Cn;
     for (uint32_t c = lane; c < Cn; c += 32) sm.c_frag[c] = 0;
 
@@ -600,7 +611,7 @@ __device__ inline uint32_t cluster_phase_pe(const DevIndex& ix, const MapParamsD
         const uint32_t i = base + lane;
         const bool root = i < H0 && s0[i].label == i;
         const uint32_t bal = __ballot_sync(FULL, root);
-        if (n_roots0 + __popc(bal) > MAX_CLUSTERS) return GB_ITEM_OUT_FULL;
+        if (n_roots0 + __popc(bal) > sm.Cc) return table_full(sm.Cc, MAX_CLUSTERS);
         if (root) side[n_roots0 + __popc(bal & ((1u << lane) - 1u))] = s0[i].source >> 8;
         n_roots0 += __popc(bal);
     }
@@ -608,8 +619,8 @@ __device__ inline uint32_t cluster_phase_pe(const DevIndex& ix, const MapParamsD
         const uint32_t i = base + lane;
         const bool root = i < H1 && s1[i].label == i;
         const uint32_t bal = __ballot_sync(FULL, root);
-        if (n_roots1 + __popc(bal) > MAX_CLUSTERS) return GB_ITEM_OUT_FULL;
-        if (root) side[MAX_CLUSTERS + n_roots1 + __popc(bal & ((1u << lane) - 1u))] = s1[i].source >> 8;
+        if (n_roots1 + __popc(bal) > sm.Cc) return table_full(sm.Cc, MAX_CLUSTERS);
+        if (root) side[sm.Cc + n_roots1 + __popc(bal & ((1u << lane) - 1u))] = s1[i].source >> 8;
         n_roots1 += __popc(bal);
     }
     __syncwarp();
@@ -617,22 +628,22 @@ __device__ inline uint32_t cluster_phase_pe(const DevIndex& ix, const MapParamsD
     for (uint32_t i = lane; i < H1; i += 32) s1[i].source &= 0xffu;
     __syncwarp();
     Cn[0] = collect_clusters(sm, s0, H0, m0, rs0.min_cnt, ix.k, L0, 0);
-    Cn[1] = collect_clusters(sm, s1, H1, m1, rs1.min_cnt, ix.k, L1, MAX_CLUSTERS);
-    if (Cn[0] == 0xffffffffu || Cn[1] == 0xffffffffu) return GB_ITEM_OUT_FULL;
+    Cn[1] = collect_clusters(sm, s1, H1, m1, rs1.min_cnt, ix.k, L1, sm.Cc);
+    if (Cn[0] == 0xffffffffu || Cn[1] == 0xffffffffu) return table_full(sm.Cc, MAX_CLUSTERS);
     rs0.n_clusters = Cn[0]; rs1.n_clusters = Cn[1];
 
     // ---- fragment ids in order of first appearance; per-fragment bests; better_cluster_count --------------
-    uint8_t* kept0 = sm.scratch; uint8_t* kept1 = sm.scratch + MAX_CLUSTERS;
+    uint8_t* kept0 = sm.scratch; uint8_t* kept1 = sm.scratch + sm.Cc;
     uint32_t n_kept[2] = {0, 0};
     uint32_t status = GB_ITEM_OK;
     if (lane == 0) {
         // fragment renumbering (:129-141 of the clusterer wrapper)
         uint32_t heads[2 * MAX_CLUSTERS]; uint32_t n_frag = 0;
         for (uint32_t r = 0; r < 2; r++) for (uint32_t c = 0; c < Cn[r]; c++) {
-            const uint32_t head = side[r * MAX_CLUSTERS + c];
+            const uint32_t head = side[r * sm.Cc + c];
             uint32_t f = 0; while (f < n_frag && heads[f] != head) f++;
             if (f == n_frag) heads[n_frag++] = head;
-            sm.c_frag[r * MAX_CLUSTERS + c] = (uint8_t)f;
+            sm.c_frag[r * sm.Cc + c] = (uint8_t)f;
         }
         if (n_frag > MAX_FRAGMENTS) status = GB_ITEM_OUT_FULL;
         else {
@@ -641,9 +652,9 @@ __device__ inline uint32_t cluster_phase_pe(const DevIndex& ix, const MapParamsD
             for (uint32_t f = 0; f < n_frag; f++) { has_first[f] = has_pair[f] = false; fs[0][f] = fs[1][f] = fc[0][f] = fc[1][f] = 0.0; }
             bool found_paired_cluster = false;
             for (uint32_t c = 0; c < Cn[0]; c++) has_first[sm.c_frag[c]] = true;
-            for (uint32_t c = 0; c < Cn[1]; c++) { const uint32_t f = sm.c_frag[MAX_CLUSTERS + c]; has_pair[f] = has_first[f]; if (has_first[f]) found_paired_cluster = true; }
+            for (uint32_t c = 0; c < Cn[1]; c++) { const uint32_t f = sm.c_frag[sm.Cc + c]; has_pair[f] = has_first[f]; if (has_first[f]) found_paired_cluster = true; }
             for (uint32_t r = 0; r < 2; r++) for (uint32_t c = 0; c < Cn[r]; c++) {
-                const uint32_t t = r * MAX_CLUSTERS + c, f = sm.c_frag[t];
+                const uint32_t t = r * sm.Cc + c, f = sm.c_frag[t];
                 fs[r][f] = max(fs[r][f], sm.c_score[t]); fc[r][f] = max(fc[r][f], sm.c_cov[t]);
             }
             // better_cluster_count (:1657-1690)
@@ -669,7 +680,7 @@ __device__ inline uint32_t cluster_phase_pe(const DevIndex& ix, const MapParamsD
 
             // ---- per-read selection (:1723-1883) ------------------------------------------------------------------
             for (uint32_t r = 0; r < 2; r++) {
-                const uint32_t cb = r * MAX_CLUSTERS, Cr = Cn[r];
+                const uint32_t cb = r * sm.Cc, Cr = Cn[r];
                 double cluster_score_cutoff = 0.0, cluster_coverage_cutoff = 0.0, second_best = 0.0;
                 double best_cov = 0.0, best_cov_score = 0.0;
                 for (uint32_t c = 0; c < Cr; c++) {
@@ -725,7 +736,7 @@ __device__ inline uint32_t cluster_phase_pe(const DevIndex& ix, const MapParamsD
     if (status != GB_ITEM_OK) return status;
     uint32_t st = emit_items(ix, sm, pools, s0, H0, m0, read_idx0, kept0, n_kept[0], 0, rs0);
     if (st != GB_ITEM_OK) return st;
-    return emit_items(ix, sm, pools, s1, H1, m1, read_idx0 + 1, kept1, n_kept[1], MAX_CLUSTERS, rs1);
+    return emit_items(ix, sm, pools, s1, H1, m1, read_idx0 + 1, kept1, n_kept[1], sm.Cc, rs1);
 }
 
 } // namespace gb
