@@ -22,7 +22,8 @@ int launch_extend_device(gb_device* d, const ExtendParams& p, const uint8_t* rea
                          uint32_t* ext_count, uint8_t* status, gb_extension* ext, uint32_t* path_pool, uint32_t* mism_pool,
                          uint32_t max_read_len);
 
-constexpr int SEED_WARPS = 4;
+constexpr int SEED_WARPS = 16;          // warps per block of the seeding kernels (block-synchronised rounds)
+constexpr int SEED_BLOCKS_PER_SM = 2;
 constexpr int ALIGN_WARPS = 4;
 
 struct MapBatch {
@@ -40,43 +41,46 @@ struct MapBatch {
 // ---------------------------------------------------------------------------------------
 // K1
 // ---------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(SEED_WARPS * 32, 8)
+__global__ void __launch_bounds__(SEED_WARPS * 32, SEED_BLOCKS_PER_SM)
 seed_kernel(DevIndex ix, MapParamsDev P, MapBatch b, SeedPools pools) {
     extern __shared__ __align__(16) uint8_t smem[];
+    __shared__ uint32_t s_base;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const SeedSmem sm = carve_seed_smem(smem + (size_t)warp * seed_smem_bytes(b.Lc, b.Mc, b.Cc), b.Lc, b.Mc, b.Cc);
+    const uint32_t limit = b.in_list ? min(*b.in_count, b.n_reads) : b.n_reads;
     while (true) {
-        uint32_t r = 0;
-        if (lane == 0) {
-            r = atomicAdd(b.work_counter, 1u);
-            if (b.in_list) r = r < *b.in_count ? b.in_list[r] : 0xffffffffu;
-        }
-        r = __shfl_sync(FULL, r, 0);
-        if (r >= b.n_reads) break;
-        const uint64_t rb = b.read_off[r];
-        const uint32_t L = (uint32_t)(b.read_off[r + 1] - rb);
+        // block-synchronised rounds, see seed_kernel_pe
+        __syncthreads();
+        if (threadIdx.x == 0) s_base = atomicAdd(b.work_counter, blockDim.x >> 5);
+        __syncthreads();
+        const uint32_t base = s_base;
+        if (base >= limit) break;
+        const bool active = base + warp < limit;
+        const uint32_t r = !active ? 0u : (b.in_list ? b.in_list[base + warp] : base + warp);
         ReadState rs;
         memset(&rs, 0, sizeof(rs));
         uint32_t status = GB_ITEM_OK;
-        if (L > b.Lc) status = GB_ITEM_OUT_FULL;
-        else {
+        uint32_t L = 0; uint64_t rb = 0;
+        if (active) { rb = b.read_off[r]; L = (uint32_t)(b.read_off[r + 1] - rb); if (L > b.Lc) status = GB_ITEM_OUT_FULL; }
+        const bool work = active && status == GB_ITEM_OK;
+        DevRng rng; rng.inited = 0; rng.state = 0; rng.seed = 0;
+        if (work) {
             for (uint32_t i = lane; i < L; i += 32) sm.read[i] = b.reads[rb + i];
             __syncwarp();
-            DevRng rng; rng.inited = 0; rng.state = 0;
             rng.seed = fold_seed(0u, sm.read, L);                     // LazyRNG seed: the read sequence (:620-622)
             status = seed_phase_a(ix, P, sm, L, pools, rng, rs);
-            if (status == GB_ITEM_OK) status = cluster_phase_se(ix, P, sm, L, r, pools, rng, rs);
-            rs.rng = rng;
         }
+        __syncthreads();
+        if (work && status == GB_ITEM_OK) status = cluster_phase_se(ix, P, sm, L, r, pools, rng, rs);
+        if (!active) continue;
         if (status == GB_ITEM_RETRY) {
             if (lane == 0) b.retry_list[atomicAdd(b.retry_count, 1u)] = r;
-            __syncwarp();
             continue;
         }
+        rs.rng = rng;
         rs.status = status;
         if (status != GB_ITEM_OK) { rs.item_cnt = 0; }
         if (lane == 0) b.states[r] = rs;
-        __syncwarp();
     }
 }
 
@@ -258,20 +262,22 @@ int map_device(gb_device* d, const gb_map_params* hp, uint32_t n_reads, const ui
             bp.work_counter = pass == 0 ? cur + 0 : cur + 9;
             bp.in_list = pass == 0 ? nullptr : d->p_retry.ptr; bp.in_count = pass == 0 ? nullptr : cur + 8;
             bp.retry_list = d->p_retry.ptr; bp.retry_count = pass == 0 ? cur + 8 : cur + 10;
-            const size_t smem = seed_smem_bytes(Lc, bp.Mc, bp.Cc) * SEED_WARPS;
+            uint32_t warps = SEED_WARPS;
+            while (warps > 1 && seed_smem_bytes(Lc, bp.Mc, bp.Cc) * warps > 200 * 1024) warps >>= 1;
+            const size_t smem = seed_smem_bytes(Lc, bp.Mc, bp.Cc) * warps;
             if (smem > 48 * 1024) {
                 GB_CUDA(cudaFuncSetAttribute(seed_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
                 GB_CUDA(cudaFuncSetAttribute(seed_kernel_pe, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
             }
             int bps = 0;
-            if (paired) GB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bps, seed_kernel_pe, SEED_WARPS * 32, smem));
-            else GB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bps, seed_kernel, SEED_WARPS * 32, smem));
+            if (paired) GB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bps, seed_kernel_pe, warps * 32, smem));
+            else GB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bps, seed_kernel, warps * 32, smem));
             if (bps < 1) bps = 1;
-            uint32_t grid = std::min<uint32_t>((uint32_t)(d->n_sms * bps), (n_units + SEED_WARPS - 1) / SEED_WARPS);
+            uint32_t grid = std::min<uint32_t>((uint32_t)(d->n_sms * bps), (n_units + warps - 1) / warps);
             if (grid == 0) grid = 1;
             if (paired) { PairBatch pbatch; pbatch.pairs = d->p_pairs.ptr; pbatch.fragment_limit = fragment_limit;
-                          seed_kernel_pe<<<grid, SEED_WARPS * 32, smem, d->stream>>>(d->ix, P, bp, pools, pbatch); }
-            else seed_kernel<<<grid, SEED_WARPS * 32, smem, d->stream>>>(d->ix, P, bp, pools);
+                          seed_kernel_pe<<<grid, warps * 32, smem, d->stream>>>(d->ix, P, bp, pools, pbatch); }
+            else seed_kernel<<<grid, warps * 32, smem, d->stream>>>(d->ix, P, bp, pools);
             d->launches++;
             GB_CUDA(cudaGetLastError());
         }

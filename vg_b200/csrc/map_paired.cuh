@@ -26,29 +26,37 @@ struct PairBatch {
     int32_t fragment_limit;
 };
 
-__global__ void __launch_bounds__(SEED_WARPS * 32, 8)
+// The warps of a block take SEED_WARPS consecutive pairs per round and meet at a block barrier
+// between phases: the kernel's code is far larger than the instruction caches, and warps that
+// drift apart each stream it from L2 on their own (ncu: "no instruction" was the top stall).
+__global__ void __launch_bounds__(SEED_WARPS * 32, SEED_BLOCKS_PER_SM)
 seed_kernel_pe(DevIndex ix, MapParamsDev P, MapBatch b, SeedPools pools, PairBatch pb) {
     extern __shared__ __align__(16) uint8_t smem[];
+    __shared__ uint32_t s_base;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const SeedSmem sm = carve_seed_smem(smem + (size_t)warp * seed_smem_bytes(b.Lc, b.Mc, b.Cc), b.Lc, b.Mc, b.Cc);
     const uint32_t n_pairs = b.n_reads / 2;
+    const uint32_t limit = b.in_list ? min(*b.in_count, n_pairs) : n_pairs;
     while (true) {
-        uint32_t p = 0;
-        if (lane == 0) {
-            p = atomicAdd(b.work_counter, 1u);
-            if (b.in_list) p = p < *b.in_count ? b.in_list[p] : 0xffffffffu;
-        }
-        p = __shfl_sync(FULL, p, 0);
-        if (p >= n_pairs) break;
+        __syncthreads();
+        if (threadIdx.x == 0) s_base = atomicAdd(b.work_counter, blockDim.x >> 5);
+        __syncthreads();
+        const uint32_t base = s_base;
+        if (base >= limit) break;
+        const bool active = base + warp < limit;
+        const uint32_t p = !active ? 0u : (b.in_list ? b.in_list[base + warp] : base + warp);
         ReadState rs[2]; PairState ps;
         memset(&rs[0], 0, sizeof(ReadState)); memset(&rs[1], 0, sizeof(ReadState)); memset(&ps, 0, sizeof(ps));
         uint32_t status = GB_ITEM_OK;
-        uint32_t L[2];
-        for (uint32_t r = 0; r < 2; r++) L[r] = (uint32_t)(b.read_off[2 * p + r + 1] - b.read_off[2 * p + r]);
-        if (L[0] > b.Lc || L[1] > b.Lc) status = GB_ITEM_OUT_FULL;
-        else {
-            // LazyRNG seed: aln1.sequence() + aln2.sequence() with mate 2 already rightward (:1529-1531)
-            DevRng rng; rng.inited = 0; rng.state = 0; rng.seed = 0;
+        uint32_t L[2] = {0, 0};
+        if (active) {
+            for (uint32_t r = 0; r < 2; r++) L[r] = (uint32_t)(b.read_off[2 * p + r + 1] - b.read_off[2 * p + r]);
+            if (L[0] > b.Lc || L[1] > b.Lc) status = GB_ITEM_OUT_FULL;
+        }
+        const bool work = active && status == GB_ITEM_OK;
+        // LazyRNG seed: aln1.sequence() + aln2.sequence() with mate 2 already rightward (:1529-1531)
+        DevRng rng; rng.inited = 0; rng.state = 0; rng.seed = 0;
+        if (work) {
             for (uint32_t r = 0; r < 2; r++) {
                 const uint64_t rb = b.read_off[2 * p + r];
                 for (uint32_t i = lane; i < L[r]; i += 32) sm.read[i] = b.reads[rb + i];
@@ -56,25 +64,28 @@ seed_kernel_pe(DevIndex ix, MapParamsDev P, MapBatch b, SeedPools pools, PairBat
                 rng.seed = fold_seed(rng.seed, sm.read, L[r]);
                 __syncwarp();
             }
-            for (uint32_t r = 0; r < 2 && status == GB_ITEM_OK; r++) {
+        }
+        for (uint32_t r = 0; r < 2; r++) {
+            __syncthreads();
+            if (work && status == GB_ITEM_OK) {
                 const uint64_t rb = b.read_off[2 * p + r];
                 for (uint32_t i = lane; i < L[r]; i += 32) sm.read[i] = b.reads[rb + i];
                 __syncwarp();
                 status = seed_phase_a(ix, P, sm, L[r], pools, rng, rs[r]);
                 __syncwarp();
             }
-            if (status == GB_ITEM_OK) status = cluster_phase_pe(ix, P, sm, L[0], L[1], 2 * p, pb.fragment_limit, pools, rng, rs[0], rs[1], ps);
-            rs[0].rng = rng; rs[1].rng = rng;
         }
+        __syncthreads();
+        if (work && status == GB_ITEM_OK) status = cluster_phase_pe(ix, P, sm, L[0], L[1], 2 * p, pb.fragment_limit, pools, rng, rs[0], rs[1], ps);
+        if (!active) continue;
         if (status == GB_ITEM_RETRY) {
             if (lane == 0) b.retry_list[atomicAdd(b.retry_count, 1u)] = p;
-            __syncwarp();
             continue;
         }
+        rs[0].rng = rng; rs[1].rng = rng;
         rs[0].status = rs[1].status = status;
         if (status != GB_ITEM_OK) { rs[0].item_cnt = rs[1].item_cnt = 0; }
         if (lane == 0) { b.states[2 * p] = rs[0]; b.states[2 * p + 1] = rs[1]; pb.pairs[p] = ps; }
-        __syncwarp();
     }
 }
 

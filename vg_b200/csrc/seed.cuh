@@ -158,7 +158,7 @@ __device__ __forceinline__ bool seeds_within(const DevSeed& a, const DevSeed& b,
 // Phase A: minimizers -> score order -> filter cascade -> DevMinimizer + DevSeed records.
 // `sm.read` must already hold the read.  rng is advanced by the tie shuffle.
 // -----------------------------------------------------------------------------------------
-__device__ inline uint32_t seed_phase_a(const DevIndex& ix, const MapParamsDev& P, const SeedSmem& sm, uint32_t L,
+__device__ __noinline__ uint32_t seed_phase_a(const DevIndex& ix, const MapParamsDev& P, const SeedSmem& sm, uint32_t L,
                                         const SeedPools& pools, DevRng& rng, ReadState& rs) {
     const int lane = lane_id();
     const uint32_t k = ix.k, w = ix.w;
@@ -396,7 +396,7 @@ __device__ inline uint32_t seed_phase_a(const DevIndex& ix, const MapParamsDev& 
 }
 
 // Label propagation: every seed's label becomes the smallest label reachable within `limit`.
-__device__ inline void propagate_labels(DevSeed* seeds_a, uint32_t na, DevSeed* seeds_b, uint32_t nb, int32_t limit) {
+__device__ __noinline__ void propagate_labels(DevSeed* seeds_a, uint32_t na, DevSeed* seeds_b, uint32_t nb, int32_t limit) {
     const int lane = lane_id();
     const uint32_t n = na + nb;
     while (true) {
@@ -419,7 +419,7 @@ __device__ inline void propagate_labels(DevSeed* seeds_a, uint32_t na, DevSeed* 
 
 // Clusters of one read in order of their first seed + score_cluster (:4738-4780).
 // Cluster c of this read is stored at table index cbase + c.  Returns C, or 0xffffffff on overflow.
-__device__ inline uint32_t collect_clusters(const SeedSmem& sm, const DevSeed* seeds, uint32_t H, const DevMinimizer* mins, uint32_t M,
+__device__ __noinline__ uint32_t collect_clusters(const SeedSmem& sm, const DevSeed* seeds, uint32_t H, const DevMinimizer* mins, uint32_t M,
                                             uint32_t k, uint32_t L, uint32_t cbase) {
     const int lane = lane_id();
     uint32_t Cn = 0;
@@ -461,7 +461,7 @@ __device__ inline uint32_t collect_clusters(const SeedSmem& sm, const DevSeed* s
 }
 
 // Emit the work items of one read for the kept clusters kept[0..n_kept) (table indices cbase + c).
-__device__ inline uint32_t emit_items(const DevIndex& ix, const SeedSmem& sm, const SeedPools& pools, const DevSeed* seeds, uint32_t H,
+__device__ __noinline__ uint32_t emit_items(const DevIndex& ix, const SeedSmem& sm, const SeedPools& pools, const DevSeed* seeds, uint32_t H,
                                       const DevMinimizer* mins, uint32_t read_idx, const uint8_t* kept, uint32_t n_kept, uint32_t cbase,
                                       ReadState& rs) {
     const int lane = lane_id();
