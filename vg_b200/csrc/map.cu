@@ -262,6 +262,8 @@ int map_device(gb_device* d, const gb_map_params* hp, uint32_t n_reads, const ui
             bp.work_counter = pass == 0 ? cur + 0 : cur + 9;
             bp.in_list = pass == 0 ? nullptr : d->p_retry.ptr; bp.in_count = pass == 0 ? nullptr : cur + 8;
             bp.retry_list = d->p_retry.ptr; bp.retry_count = pass == 0 ? cur + 8 : cur + 10;
+            // the cluster phases carve their scratch from the arrays that are dead after phase A
+            while (seed_dead_bytes(Lc, bp.Mc) < cluster_scratch_bytes(bp.Cc) && bp.Mc < MAX_MINIMIZERS) bp.Mc += 8;
             uint32_t warps = SEED_WARPS;
             while (warps > 1 && seed_smem_bytes(Lc, bp.Mc, bp.Cc) * warps > 200 * 1024) warps >>= 1;
             const size_t smem = seed_smem_bytes(Lc, bp.Mc, bp.Cc) * warps;

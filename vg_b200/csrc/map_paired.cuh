@@ -45,8 +45,9 @@ seed_kernel_pe(DevIndex ix, MapParamsDev P, MapBatch b, SeedPools pools, PairBat
         if (base >= limit) break;
         const bool active = base + warp < limit;
         const uint32_t p = !active ? 0u : (b.in_list ? b.in_list[base + warp] : base + warp);
-        ReadState rs[2]; PairState ps;
-        memset(&rs[0], 0, sizeof(ReadState)); memset(&rs[1], 0, sizeof(ReadState)); memset(&ps, 0, sizeof(ps));
+        ReadState rs0, rs1;
+        memset(&rs0, 0, sizeof(ReadState)); memset(&rs1, 0, sizeof(ReadState));
+        uint32_t n_fragments = 0;
         uint32_t status = GB_ITEM_OK;
         uint32_t L[2] = {0, 0};
         if (active) {
@@ -65,27 +66,36 @@ seed_kernel_pe(DevIndex ix, MapParamsDev P, MapBatch b, SeedPools pools, PairBat
                 __syncwarp();
             }
         }
+#pragma unroll 1
         for (uint32_t r = 0; r < 2; r++) {
             __syncthreads();
             if (work && status == GB_ITEM_OK) {
                 const uint64_t rb = b.read_off[2 * p + r];
                 for (uint32_t i = lane; i < L[r]; i += 32) sm.read[i] = b.reads[rb + i];
                 __syncwarp();
-                status = seed_phase_a(ix, P, sm, L[r], pools, rng, rs[r]);
+                ReadState cur;
+                memset(&cur, 0, sizeof(ReadState));
+                status = seed_phase_a(ix, P, sm, L[r], pools, rng, cur);
+                if (r) rs1 = cur; else rs0 = cur;
                 __syncwarp();
             }
         }
         __syncthreads();
-        if (work && status == GB_ITEM_OK) status = cluster_phase_pe(ix, P, sm, L[0], L[1], 2 * p, pb.fragment_limit, pools, rng, rs[0], rs[1], ps);
+        if (work && status == GB_ITEM_OK)
+            status = cluster_phase_pe(ix, P, sm, L[0], L[1], 2 * p, pb.fragment_limit, pools, rng, rs0, rs1, pb.pairs + p, n_fragments);
         if (!active) continue;
         if (status == GB_ITEM_RETRY) {
             if (lane == 0) b.retry_list[atomicAdd(b.retry_count, 1u)] = p;
             continue;
         }
-        rs[0].rng = rng; rs[1].rng = rng;
-        rs[0].status = rs[1].status = status;
-        if (status != GB_ITEM_OK) { rs[0].item_cnt = rs[1].item_cnt = 0; }
-        if (lane == 0) { b.states[2 * p] = rs[0]; b.states[2 * p + 1] = rs[1]; pb.pairs[p] = ps; }
+        rs0.rng = rng; rs1.rng = rng;
+        rs0.status = rs1.status = status;
+        if (status != GB_ITEM_OK) { rs0.item_cnt = rs1.item_cnt = 0; }
+        if (lane == 0) {
+            b.states[2 * p] = rs0; b.states[2 * p + 1] = rs1;
+            // cluster_phase_pe fills the record when the pair has clusters
+            if (status != GB_ITEM_OK || n_fragments == 0) { pb.pairs[p].n_fragments = 0; pb.pairs[p].found_paired_cluster = 0; }
+        }
     }
 }
 

@@ -158,7 +158,7 @@ __device__ __forceinline__ bool seeds_within(const DevSeed& a, const DevSeed& b,
 // Phase A: minimizers -> score order -> filter cascade -> DevMinimizer + DevSeed records.
 // `sm.read` must already hold the read.  rng is advanced by the tie shuffle.
 // -----------------------------------------------------------------------------------------
-__device__ __noinline__ uint32_t seed_phase_a(const DevIndex& ix, const MapParamsDev& P, const SeedSmem& sm, uint32_t L,
+__device__ __forceinline__ uint32_t seed_phase_a(const DevIndex& ix, const MapParamsDev& P, const SeedSmem& sm, uint32_t L,
                                         const SeedPools& pools, DevRng& rng, ReadState& rs) {
     const int lane = lane_id();
     const uint32_t k = ix.k, w = ix.w;
@@ -396,7 +396,7 @@ __device__ __noinline__ uint32_t seed_phase_a(const DevIndex& ix, const MapParam
 }
 
 // Label propagation: every seed's label becomes the smallest label reachable within `limit`.
-__device__ __noinline__ void propagate_labels(DevSeed* seeds_a, uint32_t na, DevSeed* seeds_b, uint32_t nb, int32_t limit) {
+__device__ __forceinline__ void propagate_labels(DevSeed* seeds_a, uint32_t na, DevSeed* seeds_b, uint32_t nb, int32_t limit) {
     const int lane = lane_id();
     const uint32_t n = na + nb;
     while (true) {
@@ -417,10 +417,38 @@ __device__ __noinline__ void propagate_labels(DevSeed* seeds_a, uint32_t na, Dev
     }
 }
 
-// Clusters of one read in order of their first seed + score_cluster (:4738-4780).
-// Cluster c of this read is stored at table index cbase + c.  Returns C, or 0xffffffff on overflow.
-__device__ __noinline__ uint32_t collect_clusters(const SeedSmem& sm, const DevSeed* seeds, uint32_t H, const DevMinimizer* mins, uint32_t M,
-                                            uint32_t k, uint32_t L, uint32_t cbase) {
+// Scratch of the cluster phases, carved from the shared arrays that are dead once phase A has
+// written its records (khash .. m_score are contiguous: Lc * 16 + Mc * 24 bytes).
+struct ClusterScratch {
+    uint32_t* startbits;   // [16]   k-mer start bitmap of one cluster (coverage)
+    double* fs0; double* fs1; double* fc0; double* fc1;   // [F] per-fragment best score / coverage per read
+    uint32_t* side;        // [2 * Cc] fragment label of each read cluster
+    uint32_t* heads;       // [2 * Cc]
+    uint8_t* fo;           // [F]
+    uint8_t* has_first;    // [F]
+    uint8_t* has_pair;     // [F]
+    uint32_t F;
+};
+__host__ __device__ inline uint32_t cluster_scratch_fragments(uint32_t Cc) { return 2 * Cc < MAX_FRAGMENTS ? 2 * Cc : MAX_FRAGMENTS; }
+__host__ __device__ inline size_t cluster_scratch_bytes(uint32_t Cc) { const size_t F = cluster_scratch_fragments(Cc); return 64 + 32 * F + 16 * (size_t)Cc + 3 * F; }
+__host__ __device__ inline size_t seed_dead_bytes(uint32_t Lc, uint32_t Mc) { return (size_t)Lc * 16 + (size_t)Mc * 24; }
+__device__ __forceinline__ ClusterScratch carve_cluster_scratch(const SeedSmem& sm) {
+    ClusterScratch cs;
+    uint8_t* p = reinterpret_cast<uint8_t*>(sm.khash);
+    cs.F = cluster_scratch_fragments(sm.Cc);
+    cs.startbits = (uint32_t*)p; p += 64;
+    cs.fs0 = (double*)p; p += 8 * cs.F; cs.fs1 = (double*)p; p += 8 * cs.F;
+    cs.fc0 = (double*)p; p += 8 * cs.F; cs.fc1 = (double*)p; p += 8 * cs.F;
+    cs.side = (uint32_t*)p; p += 8 * sm.Cc; cs.heads = (uint32_t*)p; p += 8 * sm.Cc;
+    cs.fo = p; p += cs.F; cs.has_first = p; p += cs.F; cs.has_pair = p;
+    return cs;
+}
+
+// Clusters of one read in order of their first seed + score_cluster (:4738-4780), one cluster at
+// a time with the warp sharing the work.  Cluster c of this read is stored at table index
+// cbase + c.  Returns C, or 0xffffffff on overflow.
+__device__ __forceinline__ uint32_t collect_clusters(const SeedSmem& sm, const ClusterScratch& cs, const DevSeed* seeds, uint32_t H,
+                                                     const DevMinimizer* mins, uint32_t M, uint32_t k, uint32_t L, uint32_t cbase) {
     const int lane = lane_id();
     uint32_t Cn = 0;
     for (uint32_t base = 0; base < H; base += 32) {
@@ -432,39 +460,68 @@ __device__ __noinline__ uint32_t collect_clusters(const SeedSmem& sm, const DevS
         Cn += __popc(bal);
     }
     __syncwarp();
-    for (uint32_t c = lane; c < Cn; c += 32) {
+    // this lane's share of the minimizer records (score order): score and forward offset
+    double mscore[PRESENT_WORDS]; uint32_t mfwd[PRESENT_WORDS];
+#pragma unroll
+    for (uint32_t t = 0; t < PRESENT_WORDS; t++) {
+        const uint32_t j = lane + 32 * t;
+        mscore[t] = 0.0; mfwd[t] = 0;
+        if (j < M) { const DevMinimizer dm = mins[j]; mscore[t] = dm.score; mfwd[t] = dm.fwd_offset; }
+    }
+    const uint32_t n_words = (L + 31) >> 5;
+#pragma unroll 1
+    for (uint32_t c = 0; c < Cn; c++) {
         const uint32_t label = sm.c_label[cbase + c];
         uint32_t present[PRESENT_WORDS];
 #pragma unroll
         for (uint32_t x = 0; x < PRESENT_WORDS; x++) present[x] = 0;
-        for (uint32_t i = 0; i < H; i++) if (seeds[i].label == label) { const uint32_t s = seeds[i].source; present[s >> 5] |= 1u << (s & 31); }
-        double score = 0.0;
-        uint32_t covered[16];                     // up to 512 bp
+        for (uint32_t i = lane; i < H; i += 32) {
+            const DevSeed sd = seeds[i];
+            if (sd.label == label) {
+                const uint32_t bit = 1u << (sd.source & 31), wd = sd.source >> 5;
 #pragma unroll
-        for (uint32_t x = 0; x < 16; x++) covered[x] = 0;
-        for (uint32_t j = 0; j < M; j++) {
-            if (!(present[j >> 5] & (1u << (j & 31)))) continue;
-            const DevMinimizer dm = mins[j];
-            score += dm.score;
-            set_bit_range(covered, dm.fwd_offset, min(L, (uint32_t)dm.fwd_offset + k));
+                for (uint32_t x = 0; x < PRESENT_WORDS; x++) present[x] |= wd == x ? bit : 0u;
+            }
         }
+#pragma unroll
+        for (uint32_t x = 0; x < PRESENT_WORDS; x++) present[x] = __reduce_or_sync(FULL, present[x]);
+        // score: minimizer scores summed in score order (same order as the sequential loop of the reference)
+        double score = 0.0;
+#pragma unroll
+        for (uint32_t x = 0; x < PRESENT_WORDS; x++) {
+            uint32_t bits = present[x];
+            while (bits) { const int bpos = __ffs(bits) - 1; bits &= bits - 1; score += __shfl_sync(FULL, mscore[x], bpos); }
+        }
+        // coverage: a base is covered when a present minimizer's k-mer starts in (pos - k, pos]
+        if (lane < 16) cs.startbits[lane] = 0;
+        __syncwarp();
+#pragma unroll
+        for (uint32_t x = 0; x < PRESENT_WORDS; x++)
+            if ((present[x] >> lane) & 1u) atomicOr(&cs.startbits[mfwd[x] >> 5], 1u << (mfwd[x] & 31));
+        __syncwarp();
         uint32_t cnt = 0;
+        for (uint32_t wd = 0; wd < n_words; wd++) {
+            const uint32_t pos = wd * 32 + lane;
+            const bool covered = pos < L && any_bit_in_range(cs.startbits, pos + 1 > k ? pos + 1 - k : 0u, pos + 1);
+            cnt += __popc(__ballot_sync(FULL, covered));
+        }
+        if (lane == 0) {
+            sm.c_score[cbase + c] = score;
+            sm.c_cov[cbase + c] = (double)cnt / (double)L;
 #pragma unroll
-        for (uint32_t x = 0; x < 16; x++) cnt += __popc(covered[x]);
-        sm.c_score[cbase + c] = score;
-        sm.c_cov[cbase + c] = (double)cnt / (double)L;
-#pragma unroll
-        for (uint32_t x = 0; x < PRESENT_WORDS; x++) sm.c_present[(cbase + c) * PRESENT_WORDS + x] = present[x];
+            for (uint32_t x = 0; x < PRESENT_WORDS; x++) sm.c_present[(cbase + c) * PRESENT_WORDS + x] = present[x];
+        }
+        __syncwarp();
     }
-    __syncwarp();
     return Cn;
 }
 
 // Emit the work items of one read for the kept clusters kept[0..n_kept) (table indices cbase + c).
-__device__ __noinline__ uint32_t emit_items(const DevIndex& ix, const SeedSmem& sm, const SeedPools& pools, const DevSeed* seeds, uint32_t H,
-                                      const DevMinimizer* mins, uint32_t read_idx, const uint8_t* kept, uint32_t n_kept, uint32_t cbase,
-                                      ReadState& rs) {
+__device__ __forceinline__ uint32_t emit_items(const DevIndex& ix, const SeedSmem& sm, const SeedPools& pools, const DevSeed* seeds, uint32_t H,
+                                               const DevMinimizer* mins, uint32_t read_idx, const uint8_t* kept, uint32_t n_kept, uint32_t cbase,
+                                               uint32_t& item_off_out) {
     const int lane = lane_id();
+    item_off_out = 0;
     if (n_kept == 0) return GB_ITEM_OK;
     uint32_t item_off = 0;
     if (lane == 0) item_off = atomicAdd(pools.item_cursor, n_kept);
@@ -501,23 +558,24 @@ __device__ __noinline__ uint32_t emit_items(const DevIndex& ix, const SeedSmem& 
             pools.items[item_off + t] = it;
         }
     }
-    rs.item_off = item_off; rs.item_cnt = n_kept;
+    item_off_out = item_off;
     return GB_ITEM_OK;
 }
 
 // -----------------------------------------------------------------------------------------
 // Phase B, single-end: clusters, selection (minimizer_mapper.cpp:640-832), items.
 // -----------------------------------------------------------------------------------------
-__device__ inline uint32_t cluster_phase_se(const DevIndex& ix, const MapParamsDev& P, const SeedSmem& sm, uint32_t L, uint32_t read_idx,
-                                            const SeedPools& pools, DevRng& rng, ReadState& rs) {
+__device__ __forceinline__ uint32_t cluster_phase_se(const DevIndex& ix, const MapParamsDev& P, const SeedSmem& sm, uint32_t L, uint32_t read_idx,
+                                                     const SeedPools& pools, DevRng& rng, ReadState& rs) {
     const int lane = lane_id();
     const uint32_t H = rs.seed_cnt, M = rs.min_cnt;
     if (H == 0) return GB_ITEM_OK;
     DevSeed* seeds = pools.seeds + rs.seed_off;
     const DevMinimizer* mins = pools.minimizers + rs.min_off;
+    const ClusterScratch cs = carve_cluster_scratch(sm);
     const int32_t limit = (int32_t)max(P.distance_limit, L + 50);      // get_distance_limit, minimizer_mapper.hpp:554
     propagate_labels(seeds, H, seeds, 0, limit);
-    const uint32_t Cn = collect_clusters(sm, seeds, H, mins, M, ix.k, L, 0);
+    const uint32_t Cn = collect_clusters(sm, cs, seeds, H, mins, M, ix.k, L, 0);
     if (Cn == 0xffffffffu) return table_full(sm.Cc, MAX_CLUSTERS);
     rs.n_clusters = Cn;
     for (uint32_t c = lane; c < Cn; c += 32) sm.c_frag[c] = 0;
@@ -564,101 +622,100 @@ __device__ inline uint32_t cluster_phase_se(const DevIndex& ix, const MapParamsD
     n_kept = __shfl_sync(FULL, n_kept, 0);
     rng.state = __shfl_sync(FULL, rng.state, 0); rng.inited = __shfl_sync(FULL, rng.inited, 0);
     __syncwarp();
-    return emit_items(ix, sm, pools, seeds, H, mins, read_idx, kept, n_kept, 0, rs);
+    uint32_t item_off = 0;
+    const uint32_t st = emit_items(ix, sm, pools, seeds, H, mins, read_idx, kept, n_kept, 0, item_off);
+    if (st == GB_ITEM_OK) { rs.item_off = item_off; rs.item_cnt = n_kept; }
+    return st;
 }
 
 // -----------------------------------------------------------------------------------------
 // Phase B, paired-end: joint clustering (snarl_seed_clusterer.cpp:65-145), fragment bookkeeping
-// and per-read selection (minimizer_mapper.cpp:1561-1883).
+// and per-read selection (minimizer_mapper.cpp:1561-1883).  `gps` is the pair's record in HBM.
+// Everything that exists once per read runs in a two-trip loop with a single call site, so the
+// (large) helpers are instantiated once.
 // -----------------------------------------------------------------------------------------
-__device__ inline uint32_t cluster_phase_pe(const DevIndex& ix, const MapParamsDev& P, const SeedSmem& sm,
-                                            uint32_t L0, uint32_t L1, uint32_t read_idx0, int32_t fragment_limit,
-                                            const SeedPools& pools, DevRng& rng, ReadState& rs0, ReadState& rs1, PairState& ps) {
+__device__ __forceinline__ uint32_t cluster_phase_pe(const DevIndex& ix, const MapParamsDev& P, const SeedSmem& sm,
+                                                     uint32_t L0, uint32_t L1, uint32_t read_idx0, int32_t fragment_limit,
+                                                     const SeedPools& pools, DevRng& rng, ReadState& rs0, ReadState& rs1, PairState* gps,
+                                                     uint32_t& n_fragments_out) {
     const int lane = lane_id();
     DevSeed* s0 = pools.seeds + rs0.seed_off; DevSeed* s1 = pools.seeds + rs1.seed_off;
     const uint32_t H0 = rs0.seed_cnt, H1 = rs1.seed_cnt;
     const DevMinimizer* m0 = pools.minimizers + rs0.min_off; const DevMinimizer* m1 = pools.minimizers + rs1.min_off;
-    ps.n_fragments = 0; ps.found_paired_cluster = 0;
+    n_fragments_out = 0;
     if (H0 + H1 == 0) return GB_ITEM_OK;
     const int32_t read_limit = (int32_t)max(P.distance_limit, L0 + 50);
+    const ClusterScratch cs = carve_cluster_scratch(sm);
 
-    // fragment components first (labels over the concatenation), remembered in scratch arrays
-    // of the seed records' `c_out`-independent field: we keep them in a side pass:
-    // 1) fragment pass: labels = global index over both reads
-    for (uint32_t i = lane; i < H0; i += 32) s0[i].label = i;
-    for (uint32_t i = lane; i < H1; i += 32) s1[i].label = H0 + i;
-    __syncwarp();
-    propagate_labels(s0, H0, s1, H1, fragment_limit);
-    // stash fragment labels in `slot`'s high bits?  No: keep them in the id_off-free field `source`'s
-    // upper half (source < 128).
-    for (uint32_t i = lane; i < H0; i += 32) s0[i].source |= s0[i].label << 8;
-    for (uint32_t i = lane; i < H1; i += 32) s1[i].source |= s1[i].label << 8;
-    __syncwarp();
-    // 2) read passes
-    for (uint32_t i = lane; i < H0; i += 32) s0[i].label = i;
-    for (uint32_t i = lane; i < H1; i += 32) s1[i].label = i;
-    __syncwarp();
-    propagate_labels(s0, H0, s0, 0, read_limit);
-    propagate_labels(s1, H1, s1, 0, read_limit);
-    __syncwarp();
-    // un-stash: the fragment label of each read-cluster root goes to a side table living in the
-    // (dead) k-mer scratch (khash and kkey are contiguous: >= 2 * MAX_CLUSTERS words), then the
-    // `source` fields are restored.
-    uint32_t Cn[2];
-    uint32_t* side = reinterpret_cast<uint32_t*>(sm.khash);
-    uint32_t n_roots0 = 0, n_roots1 = 0;
-    for (uint32_t base = 0; base < H0; base += 32) {
-        const uint32_t i = base + lane;
-        const bool root = i < H0 && s0[i].label == i;
-        const uint32_t bal = __ballot_sync(FULL, root);
-        if (n_roots0 + __popc(bal) > sm.Cc) return table_full(sm.Cc, MAX_CLUSTERS);
-        if (root) side[n_roots0 + __popc(bal & ((1u << lane) - 1u))] = s0[i].source >> 8;
-        n_roots0 += __popc(bal);
+    // pass 0: fragment components over both reads (labels = index in the concatenation), stashed in
+    // the upper bits of `source` (source < 128); passes 1, 2: the read clusters of each read.
+#pragma unroll 1
+    for (uint32_t pass = 0; pass < 3; pass++) {
+        DevSeed* sa = pass == 2 ? s1 : s0; const uint32_t na = pass == 2 ? H1 : H0;
+        const uint32_t nb = pass == 0 ? H1 : 0u;
+        for (uint32_t i = lane; i < na; i += 32) sa[i].label = i;
+        for (uint32_t i = lane; i < nb; i += 32) s1[i].label = na + i;
+        __syncwarp();
+        propagate_labels(sa, na, s1, nb, pass == 0 ? fragment_limit : read_limit);
+        if (pass == 0) {
+            for (uint32_t i = lane; i < H0; i += 32) s0[i].source |= s0[i].label << 8;
+            for (uint32_t i = lane; i < H1; i += 32) s1[i].source |= s1[i].label << 8;
+        }
+        __syncwarp();
     }
-    for (uint32_t base = 0; base < H1; base += 32) {
-        const uint32_t i = base + lane;
-        const bool root = i < H1 && s1[i].label == i;
-        const uint32_t bal = __ballot_sync(FULL, root);
-        if (n_roots1 + __popc(bal) > sm.Cc) return table_full(sm.Cc, MAX_CLUSTERS);
-        if (root) side[sm.Cc + n_roots1 + __popc(bal & ((1u << lane) - 1u))] = s1[i].source >> 8;
-        n_roots1 += __popc(bal);
+    // the fragment label of each read-cluster root goes to the side table, then `source` is restored
+    uint32_t Cn[2] = {0, 0};
+    uint32_t overflow = 0;
+#pragma unroll 1
+    for (uint32_t r = 0; r < 2; r++) {
+        DevSeed* sr = r ? s1 : s0; const uint32_t Hr = r ? H1 : H0;
+        uint32_t n_roots = 0;
+        for (uint32_t base = 0; base < Hr && !overflow; base += 32) {
+            const uint32_t i = base + lane;
+            const bool root = i < Hr && sr[i].label == i;
+            const uint32_t bal = __ballot_sync(FULL, root);
+            if (n_roots + __popc(bal) > sm.Cc) { overflow = 1; break; }
+            if (root) cs.side[r * sm.Cc + n_roots + __popc(bal & ((1u << lane) - 1u))] = sr[i].source >> 8;
+            n_roots += __popc(bal);
+        }
+        __syncwarp();
+        for (uint32_t i = lane; i < Hr; i += 32) sr[i].source &= 0xffu;
+        __syncwarp();
+        if (!overflow) {
+            const uint32_t cn = collect_clusters(sm, cs, sr, Hr, r ? m1 : m0, r ? rs1.min_cnt : rs0.min_cnt, ix.k, r ? L1 : L0, r * sm.Cc);
+            if (cn == 0xffffffffu) overflow = 1;
+            else if (r) Cn[1] = cn; else Cn[0] = cn;
+        }
     }
-    __syncwarp();
-    for (uint32_t i = lane; i < H0; i += 32) s0[i].source &= 0xffu;
-    for (uint32_t i = lane; i < H1; i += 32) s1[i].source &= 0xffu;
-    __syncwarp();
-    Cn[0] = collect_clusters(sm, s0, H0, m0, rs0.min_cnt, ix.k, L0, 0);
-    Cn[1] = collect_clusters(sm, s1, H1, m1, rs1.min_cnt, ix.k, L1, sm.Cc);
-    if (Cn[0] == 0xffffffffu || Cn[1] == 0xffffffffu) return table_full(sm.Cc, MAX_CLUSTERS);
+    if (overflow) return table_full(sm.Cc, MAX_CLUSTERS);
     rs0.n_clusters = Cn[0]; rs1.n_clusters = Cn[1];
 
     // ---- fragment ids in order of first appearance; per-fragment bests; better_cluster_count --------------
     uint8_t* kept0 = sm.scratch; uint8_t* kept1 = sm.scratch + sm.Cc;
-    uint32_t n_kept[2] = {0, 0};
+    uint32_t n_kept0 = 0, n_kept1 = 0;
     uint32_t status = GB_ITEM_OK;
+    uint32_t n_frag = 0;
     if (lane == 0) {
         // fragment renumbering (:129-141 of the clusterer wrapper)
-        uint32_t heads[2 * MAX_CLUSTERS]; uint32_t n_frag = 0;
-        for (uint32_t r = 0; r < 2; r++) for (uint32_t c = 0; c < Cn[r]; c++) {
-            const uint32_t head = side[r * sm.Cc + c];
-            uint32_t f = 0; while (f < n_frag && heads[f] != head) f++;
-            if (f == n_frag) heads[n_frag++] = head;
+        for (uint32_t r = 0; r < 2; r++) for (uint32_t c = 0; c < (r ? Cn[1] : Cn[0]); c++) {
+            const uint32_t head = cs.side[r * sm.Cc + c];
+            uint32_t f = 0; while (f < n_frag && cs.heads[f] != head) f++;
+            if (f == n_frag) cs.heads[n_frag++] = head;
             sm.c_frag[r * sm.Cc + c] = (uint8_t)f;
         }
-        if (n_frag > MAX_FRAGMENTS) status = GB_ITEM_OUT_FULL;
+        if (n_frag > cs.F) status = table_full(sm.Cc, MAX_CLUSTERS);
         else {
-            bool has_first[MAX_FRAGMENTS], has_pair[MAX_FRAGMENTS];
-            double fs[2][MAX_FRAGMENTS], fc[2][MAX_FRAGMENTS];
-            for (uint32_t f = 0; f < n_frag; f++) { has_first[f] = has_pair[f] = false; fs[0][f] = fs[1][f] = fc[0][f] = fc[1][f] = 0.0; }
+            double* const fs[2] = {cs.fs0, cs.fs1}; double* const fc[2] = {cs.fc0, cs.fc1};
+            uint8_t* has_first = cs.has_first; uint8_t* has_pair = cs.has_pair; uint8_t* fo = cs.fo;
+            for (uint32_t f = 0; f < n_frag; f++) { has_first[f] = has_pair[f] = 0; fs[0][f] = fs[1][f] = fc[0][f] = fc[1][f] = 0.0; }
             bool found_paired_cluster = false;
-            for (uint32_t c = 0; c < Cn[0]; c++) has_first[sm.c_frag[c]] = true;
+            for (uint32_t c = 0; c < Cn[0]; c++) has_first[sm.c_frag[c]] = 1;
             for (uint32_t c = 0; c < Cn[1]; c++) { const uint32_t f = sm.c_frag[sm.Cc + c]; has_pair[f] = has_first[f]; if (has_first[f]) found_paired_cluster = true; }
-            for (uint32_t r = 0; r < 2; r++) for (uint32_t c = 0; c < Cn[r]; c++) {
+            for (uint32_t r = 0; r < 2; r++) for (uint32_t c = 0; c < (r ? Cn[1] : Cn[0]); c++) {
                 const uint32_t t = r * sm.Cc + c, f = sm.c_frag[t];
                 fs[r][f] = max(fs[r][f], sm.c_score[t]); fc[r][f] = max(fc[r][f], sm.c_cov[t]);
             }
             // better_cluster_count (:1657-1690)
-            uint8_t fo[MAX_FRAGMENTS];
             auto total = [&](uint32_t f) { return (fc[0][f] + fc[1][f]) + (fs[0][f] + fs[1][f]); };
             for (uint32_t f = 0; f < n_frag; f++) { uint32_t j = f; while (j > 0 && total(f) > total(fo[j - 1])) { fo[j] = fo[j - 1]; j--; } fo[j] = (uint8_t)f; }
             {
@@ -667,20 +724,22 @@ __device__ inline uint32_t cluster_phase_pe(const DevIndex& ix, const MapParamsD
                 for (uint32_t i = 1; i < ties; i++) { const uint32_t j = rng_next(rng) % (i + 1); const uint8_t t = fo[j]; fo[j] = fo[i]; fo[i] = t; }
             }
             double prev_score_sum = 0.0;
+            uint8_t* better = gps->better_cluster_count;
             for (int rank = (int)n_frag - 1; rank >= 0; rank--) {
                 const uint32_t f = fo[rank];
-                if (rank == (int)n_frag - 1) ps.better_cluster_count[f] = (uint8_t)(rank + 1);
+                if (rank == (int)n_frag - 1) better[f] = (uint8_t)(rank + 1);
                 else {
                     const double curr = total(f);
-                    if (curr == prev_score_sum) ps.better_cluster_count[f] = ps.better_cluster_count[fo[rank + 1]];
-                    else { ps.better_cluster_count[f] = (uint8_t)(rank + 1); prev_score_sum = curr; }
+                    if (curr == prev_score_sum) better[f] = better[fo[rank + 1]];
+                    else { better[f] = (uint8_t)(rank + 1); prev_score_sum = curr; }
                 }
             }
-            ps.n_fragments = n_frag; ps.found_paired_cluster = found_paired_cluster ? 1u : 0u;
+            gps->n_fragments = n_frag; gps->found_paired_cluster = found_paired_cluster ? 1u : 0u;
 
             // ---- per-read selection (:1723-1883) ------------------------------------------------------------------
+#pragma unroll 1
             for (uint32_t r = 0; r < 2; r++) {
-                const uint32_t cb = r * sm.Cc, Cr = Cn[r];
+                const uint32_t cb = r * sm.Cc, Cr = r ? Cn[1] : Cn[0];
                 double cluster_score_cutoff = 0.0, cluster_coverage_cutoff = 0.0, second_best = 0.0;
                 double best_cov = 0.0, best_cov_score = 0.0;
                 for (uint32_t c = 0; c < Cr; c++) {
@@ -698,7 +757,7 @@ __device__ inline uint32_t cluster_phase_pe(const DevIndex& ix, const MapParamsD
                     const uint32_t fa = sm.c_frag[cb + a], fb = sm.c_frag[cb + b];
                     const double coverage_a = fc[0][fa] + fc[1][fa], coverage_b = fc[0][fb] + fc[1][fb];
                     const double score_a = fs[0][fa] + fs[1][fa], score_b = fs[0][fb] + fs[1][fb];
-                    if (has_pair[fa] != has_pair[fb]) return has_pair[fa];
+                    if (has_pair[fa] != has_pair[fb]) return has_pair[fa] != 0;
                     else if (coverage_a != coverage_b) return coverage_a > coverage_b;
                     else if (score_a != score_b) return score_a > score_b;
                     else if (sm.c_cov[cb + a] != sm.c_cov[cb + b]) return sm.c_cov[cb + a] > sm.c_cov[cb + b];
@@ -710,7 +769,7 @@ __device__ inline uint32_t cluster_phase_pe(const DevIndex& ix, const MapParamsD
                 while (ties < Cr && !comes_before(order[0], order[ties])) ties++;
                 for (uint32_t i = 1; i < ties; i++) { const uint32_t j = rng_next(rng) % (i + 1); const uint8_t t = order[j]; order[j] = order[i]; order[i] = t; }
                 // process_until_threshold_c with threshold 0: everything is "good enough", max_extensions caps
-                uint32_t unskipped = 0, kept_cluster_count = 0;
+                uint32_t unskipped = 0, kept_cluster_count = 0, nk = 0;
                 uint8_t* kept = r == 0 ? kept0 : kept1;
                 for (uint32_t i = 0; i < Cr; i++) {
                     const uint32_t c = order[i];
@@ -723,20 +782,27 @@ __device__ inline uint32_t cluster_phase_pe(const DevIndex& ix, const MapParamsD
                         if (P.cluster_coverage_threshold != 0 && cov < cluster_coverage_cutoff && kept_cluster_count >= P.min_extensions) keep = false;
                         else if (P.cluster_score_threshold != 0 && sc < cluster_score_cutoff && kept_cluster_count >= P.min_extensions) keep = false;
                     }
-                    if (keep) { kept[n_kept[r]++] = (uint8_t)c; kept_cluster_count++; unskipped++; }
+                    if (keep) { kept[nk++] = (uint8_t)c; kept_cluster_count++; unskipped++; }
                 }
+                if (r == 0) n_kept0 = nk; else n_kept1 = nk;
             }
         }
     }
     status = __shfl_sync(FULL, status, 0);
-    n_kept[0] = __shfl_sync(FULL, n_kept[0], 0); n_kept[1] = __shfl_sync(FULL, n_kept[1], 0);
+    n_kept0 = __shfl_sync(FULL, n_kept0, 0); n_kept1 = __shfl_sync(FULL, n_kept1, 0);
     rng.state = __shfl_sync(FULL, rng.state, 0); rng.inited = __shfl_sync(FULL, rng.inited, 0);
-    ps.n_fragments = __shfl_sync(FULL, ps.n_fragments, 0); ps.found_paired_cluster = __shfl_sync(FULL, ps.found_paired_cluster, 0);
+    n_fragments_out = __shfl_sync(FULL, n_frag, 0);
     __syncwarp();
     if (status != GB_ITEM_OK) return status;
-    uint32_t st = emit_items(ix, sm, pools, s0, H0, m0, read_idx0, kept0, n_kept[0], 0, rs0);
-    if (st != GB_ITEM_OK) return st;
-    return emit_items(ix, sm, pools, s1, H1, m1, read_idx0 + 1, kept1, n_kept[1], sm.Cc, rs1);
+#pragma unroll 1
+    for (uint32_t r = 0; r < 2; r++) {
+        uint32_t item_off = 0;
+        const uint32_t nk = r ? n_kept1 : n_kept0;
+        const uint32_t st = emit_items(ix, sm, pools, r ? s1 : s0, r ? H1 : H0, r ? m1 : m0, read_idx0 + r, r ? kept1 : kept0, nk, r * sm.Cc, item_off);
+        if (st != GB_ITEM_OK) return st;
+        if (r) { rs1.item_off = item_off; rs1.item_cnt = nk; } else { rs0.item_off = item_off; rs0.item_cnt = nk; }
+    }
+    return GB_ITEM_OK;
 }
 
 } // namespace gb
