@@ -223,13 +223,13 @@ def gpu_map(dev, reads, quals=None, params=None, paired=False):
     return dev.map_arrays(rbuf, qbuf, read_off, params, paired=paired)
 
 
-def compare_alignments(got, want, n, mapq_tol=1):
+def compare_alignments(got, want, n, mapq_tol=1, indices=None):
     """got / want = (aln, maps, edits, status[, counters]).  Scores, paths and edits must be
     identical; MAPQ within +-mapq_tol (FP64 libm differences, BASELINE.json north_star)."""
     ga, gm, ge, gs = got[:4]
     wa, wm, we, ws = want[:4]
     bad = []
-    for i in range(n):
+    for i in (range(n) if indices is None else indices):
         assert gs[i] == 0, f"read {i}: GPU status {gs[i]}"
         assert ws[i] == 0
         gd = decode_alignment(ga[i], gm, ge)

@@ -93,3 +93,12 @@ def test_map_paired_parity_through_the_seeding_retry_pass(tables, monkeypatch):
     g = synth.make_variant_graph(length=100000, n_snp=160, n_ins=20, n_del=20, n_haps=8, seed=5)
     rs = synth.simulate_pairs(g, 1200, sub_rate=0.01, seed=51)
     _run(g, rs, H.paired_params())
+
+
+@pytest.mark.gpu
+def test_map_paired_parity_across_host_chunks(monkeypatch):
+    """Several double-buffered chunks per call: headers must index the caller's whole pools."""
+    monkeypatch.setenv("GIRAFFE_B200_MAP_CHUNK", "256")
+    g = synth.make_variant_graph(length=100000, n_snp=160, n_ins=20, n_del=20, n_haps=8, seed=5)
+    rs = synth.simulate_pairs(g, 1100, sub_rate=0.02, seed=53)
+    _run(g, rs, H.paired_params())

@@ -91,3 +91,11 @@ def test_map_parity_through_the_seeding_retry_pass(monkeypatch):
     g = synth.make_variant_graph(length=100000, n_snp=160, n_ins=20, n_del=20, n_haps=8, seed=5)
     rs = synth.simulate_reads(g, 1500, length=150, sub_rate=0.01, seed=52)
     _run(g, rs)
+
+
+@pytest.mark.gpu
+def test_map_parity_across_host_chunks(monkeypatch):
+    monkeypatch.setenv("GIRAFFE_B200_MAP_CHUNK", "200")
+    g = synth.make_variant_graph(length=100000, n_snp=160, n_ins=20, n_del=20, n_haps=8, seed=5)
+    rs = synth.simulate_reads(g, 1501, length=150, sub_rate=0.02, seed=54)
+    _run(g, rs)

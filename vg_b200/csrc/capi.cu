@@ -105,6 +105,10 @@ extern "C" int gb_device_create(const gb_flat_index* ix, int device_ordinal, gb_
     cudaDeviceProp prop;
     GB_CUDA(cudaGetDeviceProperties(&prop, device_ordinal));
     d->n_sms = prop.multiProcessorCount;
+    if (const char* env = std::getenv("GIRAFFE_B200_MAP_CHUNK")) {
+        const unsigned long v = std::strtoul(env, nullptr, 10);
+        if (v >= 2 && v <= (1ul << 24)) d->map_chunk = (uint32_t)(v & ~1ul);
+    }
     if (const char* env = std::getenv("GIRAFFE_B200_SEED_TABLES")) {
         unsigned mc = 0, cc = 0;
         if (std::sscanf(env, "%u,%u", &mc, &cc) == 2 && mc >= 2 && cc >= 1) {
@@ -116,6 +120,16 @@ extern "C" int gb_device_create(const gb_flat_index* ix, int device_ordinal, gb_
     d->stream = d->own_stream;
     for (int i = 0; i < 5; i++) GB_CUDA(cudaEventCreate(&d->ev_stage[i]));
     GB_CUDA(cudaEventCreate(&d->ev0)); GB_CUDA(cudaEventCreate(&d->ev1));
+    GB_CUDA(cudaStreamCreateWithFlags(&d->s_in, cudaStreamNonBlocking));
+    GB_CUDA(cudaStreamCreateWithFlags(&d->s_out, cudaStreamNonBlocking));
+    for (int i = 0; i < 2; i++) {
+        GB_CUDA(cudaEventCreateWithFlags(&d->io[i].ev_in, cudaEventDisableTiming));
+        GB_CUDA(cudaEventCreateWithFlags(&d->io[i].ev_done, cudaEventDisableTiming));
+        GB_CUDA(cudaEventCreateWithFlags(&d->io[i].ev_hdr, cudaEventDisableTiming));
+        GB_CUDA(cudaEventCreateWithFlags(&d->io[i].ev_out, cudaEventDisableTiming));
+        GB_CUDA(cudaEventCreate(&d->io[i].ev_k0)); GB_CUDA(cudaEventCreate(&d->io[i].ev_k1));
+    }
+    GB_CUDA(cudaMallocHost(&d->h_totals, 4 * sizeof(uint64_t)));
     int rc;
     if ((rc = d->nodes.upload(ix->nodes, ix->n_nodes, d->stream))) return rc;
     if ((rc = d->seq.upload(ix->seq, ix->seq_bytes, d->stream))) return rc;
@@ -141,6 +155,12 @@ extern "C" void gb_device_destroy(gb_device* d) {
     for (int i = 0; i < 5; i++) cudaEventDestroy(d->ev_stage[i]);
     cudaFree(d->work_counter);
     cudaEventDestroy(d->ev0); cudaEventDestroy(d->ev1);
+    for (int i = 0; i < 2; i++) {
+        cudaEventDestroy(d->io[i].ev_in); cudaEventDestroy(d->io[i].ev_done); cudaEventDestroy(d->io[i].ev_hdr);
+        cudaEventDestroy(d->io[i].ev_out); cudaEventDestroy(d->io[i].ev_k0); cudaEventDestroy(d->io[i].ev_k1);
+    }
+    cudaFreeHost(d->h_totals);
+    cudaStreamDestroy(d->s_in); cudaStreamDestroy(d->s_out);
     cudaStreamDestroy(d->own_stream);
     delete d;
 }

@@ -11,17 +11,19 @@ struct CountEdits { const gb_alignment* a; __host__ __device__ uint64_t operator
 __global__ void compact_gather_kernel(uint32_t n_reads, gb_alignment* aln, const gb_mapping* maps, const uint32_t* edits,
                                       uint32_t map_cap, uint32_t edit_cap, const uint64_t* map_off, const uint64_t* edit_off,
                                       gb_mapping* out_maps, uint64_t out_map_cap, uint32_t* out_edits, uint64_t out_edit_cap,
-                                      uint64_t map_base, uint64_t edit_base, uint32_t read_base, uint64_t* totals, uint8_t* status) {
+                                      const uint64_t* run_base, uint32_t read_base, uint64_t* totals, uint8_t* status) {
     const uint32_t warps_per_block = blockDim.x >> 5;
     const uint32_t lane = threadIdx.x & 31;
+    // headers carry offsets into the caller's whole pool: run_base = mappings / edits of earlier chunks
+    const uint64_t map_base = run_base ? run_base[0] : 0, edit_base = run_base ? run_base[1] : 0;
     for (uint32_t r = blockIdx.x * warps_per_block + (threadIdx.x >> 5); r < n_reads; r += gridDim.x * warps_per_block) {
         gb_alignment a = aln[r];
         const uint64_t mo = map_off[r], eo = edit_off[r];
-        const bool fits = map_base + mo + a.n_mappings <= out_map_cap && edit_base + eo + a.n_edits <= out_edit_cap;
+        const bool fits = mo + a.n_mappings <= out_map_cap && eo + a.n_edits <= out_edit_cap;
         if (fits) {
             const gb_mapping* sm = maps + (size_t)r * map_cap; const uint32_t* se = edits + (size_t)r * edit_cap;
-            for (uint32_t i = lane; i < a.n_mappings; i += 32) out_maps[map_base + mo + i] = sm[i];
-            for (uint32_t i = lane; i < a.n_edits; i += 32) out_edits[edit_base + eo + i] = se[i];
+            for (uint32_t i = lane; i < a.n_mappings; i += 32) out_maps[mo + i] = sm[i];
+            for (uint32_t i = lane; i < a.n_edits; i += 32) out_edits[eo + i] = se[i];
         }
         if (lane == 0) {
             a.mapping_off = (uint32_t)(map_base + mo); a.edit_off = (uint32_t)(edit_base + eo); a.read_id = read_base + r;
@@ -32,11 +34,18 @@ __global__ void compact_gather_kernel(uint32_t n_reads, gb_alignment* aln, const
     }
 }
 
+// After a chunk: run += totals (host-buffer calls keep the running totals on the device so chunks
+// can be queued without a host round trip).
+__global__ void advance_run_kernel(uint64_t* run, const uint64_t* totals) { run[0] += totals[0]; run[1] += totals[1]; }
+__global__ void rebase_offsets_kernel(uint64_t* off, uint32_t n, uint64_t b0) {
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) off[i] -= b0;
+}
+
 // Scans + gather on the handle's stream.  d_totals[0..1] receive the mappings / edits used by
 // this chunk.  Temporary storage comes from the handle.
 inline int compact_outputs(gb_device* d, uint32_t n_reads, gb_alignment* d_aln, const gb_mapping* d_maps, const uint32_t* d_edits,
                            uint32_t map_cap, uint32_t edit_cap, gb_mapping* out_maps, uint64_t out_map_cap, uint32_t* out_edits,
-                           uint64_t out_edit_cap, uint64_t map_base, uint64_t edit_base, uint32_t read_base, uint64_t* d_totals, uint8_t* d_status) {
+                           uint64_t out_edit_cap, const uint64_t* d_run_base, uint32_t read_base, uint64_t* d_totals, uint8_t* d_status) {
     int rc;
     if ((rc = d->c_map_off.reserve(n_reads))) return rc;
     if ((rc = d->c_edit_off.reserve(n_reads))) return rc;
@@ -54,7 +63,7 @@ inline int compact_outputs(gb_device* d, uint32_t n_reads, gb_alignment* d_aln, 
     const uint32_t grid = std::min<uint32_t>((uint32_t)d->n_sms * 8, (n_reads + 7) / 8);
     compact_gather_kernel<<<grid ? grid : 1, 256, 0, d->stream>>>(n_reads, d_aln, d_maps, d_edits, map_cap, edit_cap, d->c_map_off.ptr,
                                                                d->c_edit_off.ptr, out_maps, out_map_cap, out_edits, out_edit_cap,
-                                                               map_base, edit_base, read_base, d_totals, d_status);
+                                                               d_run_base, read_base, d_totals, d_status);
     d->launches++;
     GB_CUDA(cudaGetLastError());
     return GB_OK;

@@ -97,11 +97,21 @@ struct gb_device {
     gb::DevBuf<uint32_t> pad_edits;
     gb::DevBuf<uint64_t> c_map_off, c_edit_off, c_totals;
     gb::DevBuf<uint8_t> c_tmp;
-    gb::DevBuf<uint8_t> io_reads, io_quals, io_status;
-    gb::DevBuf<uint64_t> io_read_off;
-    gb::DevBuf<gb_alignment> io_aln;
-    gb::DevBuf<gb_mapping> io_maps;
-    gb::DevBuf<uint32_t> io_edits;
+    // host-buffer entry points: two staging sets so chunk i+1 uploads and chunk i-1 downloads while
+    // chunk i computes (streams s_in / stream / s_out)
+    struct IoSet {
+        gb::DevBuf<uint8_t> reads, quals, status;
+        gb::DevBuf<uint64_t> read_off, totals;
+        gb::DevBuf<gb_alignment> aln;
+        gb::DevBuf<gb_mapping> maps;
+        gb::DevBuf<uint32_t> edits;
+        cudaEvent_t ev_in = nullptr, ev_done = nullptr, ev_hdr = nullptr, ev_out = nullptr, ev_k0 = nullptr, ev_k1 = nullptr;
+        void release() { reads.release(); quals.release(); status.release(); read_off.release(); totals.release(); aln.release(); maps.release(); edits.release(); }
+    } io[2];
+    cudaStream_t s_in = nullptr, s_out = nullptr;
+    uint64_t* h_totals = nullptr;          // pinned, 2 per set
+    gb::DevBuf<uint64_t> c_run;            // running mapping / edit totals of a host-buffer call
+    uint32_t map_chunk = 1u << 20;         // reads per chunk; GIRAFFE_B200_MAP_CHUNK overrides
     void release_all() {
         nodes.release(); seq.release(); gbwt.release(); dist.release(); table.release(); hits.release();
         ws_queue.release(); ws_arena.release();
@@ -109,6 +119,6 @@ struct gb_device {
         p_items.release(); p_ext_seeds.release(); p_cursors.release(); p_ext_count.release(); p_path.release(); p_mism.release();
         p_ext_status.release(); p_ext.release(); ws_tail.release(); ws_cand.release(); w_reads.release(); w_quals.release(); p_pairs.release(); p_slow.release(); p_retry.release();
         pad_maps.release(); pad_edits.release(); c_map_off.release(); c_edit_off.release(); c_totals.release(); c_tmp.release();
-        io_reads.release(); io_quals.release(); io_status.release(); io_read_off.release(); io_aln.release(); io_maps.release(); io_edits.release();
+        io[0].release(); io[1].release(); c_run.release();
     }
 };

@@ -172,7 +172,7 @@ int map_device(gb_device* d, const gb_map_params* hp, uint32_t n_reads, const ui
                const uint64_t* d_read_off, uint32_t max_len, uint64_t total_bases,
                gb_alignment* d_aln, uint8_t* d_status, bool paired,
                gb_mapping* out_maps, uint64_t out_map_cap, uint32_t* out_edits, uint64_t out_edit_cap,
-               uint64_t map_base, uint64_t edit_base, uint32_t read_base, uint64_t* d_totals) {
+               const uint64_t* d_run_base, uint32_t read_base, uint64_t* d_totals) {
     int rc0;
     if ((rc0 = d->pad_maps.reserve((size_t)n_reads * hp->mapping_cap_per_read))) return rc0;
     if ((rc0 = d->pad_edits.reserve((size_t)n_reads * hp->edit_cap_per_read))) return rc0;
@@ -350,14 +350,16 @@ int map_device(gb_device* d, const gb_map_params* hp, uint32_t n_reads, const ui
     }
     GB_CUDA(cudaEventRecord(d->ev_stage[3], d->stream));
     if ((rc = compact_outputs(d, n_reads, d_aln, d_maps, d_edits, hp->mapping_cap_per_read, hp->edit_cap_per_read,
-                              out_maps, out_map_cap, out_edits, out_edit_cap, map_base, edit_base, read_base, d_totals, d_status))) return rc;
+                              out_maps, out_map_cap, out_edits, out_edit_cap, d_run_base, read_base, d_totals, d_status))) return rc;
     GB_CUDA(cudaEventRecord(d->ev_stage[4], d->stream));
     return GB_OK;
 }
 
 } // namespace gb
 
-// Host-buffer entry: chunks of <= MAP_CHUNK reads are copied in, mapped, compacted and copied out.
+// Host-buffer entry: chunks of <= map_chunk reads are copied in, mapped, compacted and copied out,
+// double-buffered over three streams: while chunk i computes, chunk i+1 uploads and chunk i-1
+// downloads.  Output offsets are global (running totals kept on the device).
 static int map_batch_host(gb_device* d, const gb_map_params* hp, bool paired,
                           uint32_t n_reads, const uint8_t* reads, const uint8_t* quals, const uint64_t* read_off,
                           gb_alignment* aln, gb_mapping* mappings, uint64_t mapping_pool_cap, uint32_t* edits, uint64_t edit_pool_cap,
@@ -367,49 +369,77 @@ static int map_batch_host(gb_device* d, const gb_map_params* hp, bool paired,
     if (n_edits_used) *n_edits_used = 0;
     if (n_reads == 0) return GB_OK;
     GB_CUDA(cudaSetDevice(d->device));
-    const uint32_t MAP_CHUNK = 1u << 20;
+    const uint32_t chunk = d->map_chunk;
     uint64_t map_used = 0, edit_used = 0;
     float kernel_ms = 0.f;
     int rc;
-    std::vector<uint64_t> local_off;
-    if ((rc = d->c_totals.reserve(2))) return rc;
-    for (uint32_t c0 = 0; c0 < n_reads; c0 += MAP_CHUNK) {
-        const uint32_t cn = std::min<uint32_t>(MAP_CHUNK, n_reads - c0);
-        const uint64_t b0 = read_off[c0], b1 = read_off[c0 + cn], total = b1 - b0;
-        uint32_t max_len = 0;
-        local_off.resize(cn + 1);
-        for (uint32_t r = 0; r <= cn; r++) local_off[r] = read_off[c0 + r] - b0;
-        for (uint32_t r = 0; r < cn; r++) max_len = std::max<uint32_t>(max_len, (uint32_t)(local_off[r + 1] - local_off[r]));
-        if ((rc = d->io_reads.upload(reads + b0, total ? total : 1, d->stream, total))) return rc;
-        if (quals) { if ((rc = d->io_quals.upload(quals + b0, total ? total : 1, d->stream, total))) return rc; }
-        if ((rc = d->io_read_off.upload(local_off.data(), cn + 1, d->stream))) return rc;
-        if ((rc = d->io_aln.reserve(cn))) return rc;
-        if ((rc = d->io_status.reserve(cn))) return rc;
-        const uint64_t chunk_map_cap = (uint64_t)cn * hp->mapping_cap_per_read, chunk_edit_cap = (uint64_t)cn * hp->edit_cap_per_read;
-        if ((rc = d->io_maps.reserve(chunk_map_cap))) return rc;
-        if ((rc = d->io_edits.reserve(chunk_edit_cap))) return rc;
-        GB_CUDA(cudaEventRecord(d->ev0, d->stream));
-        if ((rc = map_device(d, hp, cn, d->io_reads.ptr, quals ? d->io_quals.ptr : nullptr, d->io_read_off.ptr, max_len, total,
-                             d->io_aln.ptr, d->io_status.ptr, paired, d->io_maps.ptr, chunk_map_cap, d->io_edits.ptr, chunk_edit_cap,
-                             map_used, edit_used, c0, d->c_totals.ptr))) return rc;
-        GB_CUDA(cudaEventRecord(d->ev1, d->stream));
-        uint64_t totals[2] = {0, 0};
-        GB_CUDA(cudaMemcpyAsync(totals, d->c_totals.ptr, sizeof(totals), cudaMemcpyDeviceToHost, d->stream));
-        GB_CUDA(cudaMemcpyAsync(aln + c0, d->io_aln.ptr, sizeof(gb_alignment) * cn, cudaMemcpyDeviceToHost, d->stream));
-        GB_CUDA(cudaMemcpyAsync(status + c0, d->io_status.ptr, cn, cudaMemcpyDeviceToHost, d->stream));
-        GB_CUDA(cudaStreamSynchronize(d->stream));
-        if (map_used + totals[0] > mapping_pool_cap || edit_used + totals[1] > edit_pool_cap) {
+    if ((rc = d->c_run.reserve(2))) return rc;
+    GB_CUDA(cudaMemsetAsync(d->c_run.ptr, 0, 2 * sizeof(uint64_t), d->stream));
+    const uint32_t n_chunks = (n_reads + chunk - 1) / chunk;
+    bool used[2] = {false, false};
+
+    // download the dense mappings / edits of a chunk whose header copy has been queued
+    auto finish = [&](uint32_t ci) -> int {
+        gb_device::IoSet& io = d->io[ci & 1];
+        GB_CUDA(cudaEventSynchronize(io.ev_hdr));
+        const uint64_t tm = d->h_totals[2 * (ci & 1)], te = d->h_totals[2 * (ci & 1) + 1];
+        if (map_used + tm > mapping_pool_cap || edit_used + te > edit_pool_cap) {
             g_last_error = "output pool capacity too small";
             return GB_ERR_CAPACITY;
         }
-        if (totals[0]) GB_CUDA(cudaMemcpyAsync(mappings + map_used, d->io_maps.ptr, sizeof(gb_mapping) * totals[0], cudaMemcpyDeviceToHost, d->stream));
-        if (totals[1]) GB_CUDA(cudaMemcpyAsync(edits + edit_used, d->io_edits.ptr, 4 * totals[1], cudaMemcpyDeviceToHost, d->stream));
-        GB_CUDA(cudaStreamSynchronize(d->stream));
+        if (tm) GB_CUDA(cudaMemcpyAsync(mappings + map_used, io.maps.ptr, sizeof(gb_mapping) * tm, cudaMemcpyDeviceToHost, d->s_out));
+        if (te) GB_CUDA(cudaMemcpyAsync(edits + edit_used, io.edits.ptr, 4 * te, cudaMemcpyDeviceToHost, d->s_out));
+        GB_CUDA(cudaEventRecord(io.ev_out, d->s_out));
         float ms = 0.f;
-        GB_CUDA(cudaEventElapsedTime(&ms, d->ev0, d->ev1));
+        GB_CUDA(cudaEventElapsedTime(&ms, io.ev_k0, io.ev_k1));
         kernel_ms += ms;
-        map_used += totals[0]; edit_used += totals[1];
+        map_used += tm; edit_used += te;
+        return GB_OK;
+    };
+    auto drain = [&]() { cudaStreamSynchronize(d->s_in); cudaStreamSynchronize(d->stream); cudaStreamSynchronize(d->s_out); };
+
+    for (uint32_t ci = 0; ci < n_chunks; ci++) {
+        const uint32_t c0 = ci * chunk;
+        const uint32_t cn = std::min<uint32_t>(chunk, n_reads - c0);
+        gb_device::IoSet& io = d->io[ci & 1];
+        const uint64_t b0 = read_off[c0], b1 = read_off[c0 + cn], total = b1 - b0;
+        uint32_t max_len = 0;
+        for (uint32_t r = 0; r < cn; r++) max_len = std::max<uint32_t>(max_len, (uint32_t)(read_off[c0 + r + 1] - read_off[c0 + r]));
+        const uint64_t chunk_map_cap = (uint64_t)cn * hp->mapping_cap_per_read, chunk_edit_cap = (uint64_t)cn * hp->edit_cap_per_read;
+        if (used[ci & 1]) {
+            // this set's inputs were read by chunk ci-2's kernels; its outputs must have left the device
+            GB_CUDA(cudaStreamWaitEvent(d->s_in, io.ev_done, 0));
+            GB_CUDA(cudaStreamWaitEvent(d->stream, io.ev_out, 0));
+        }
+        if ((rc = io.reads.reserve(total ? total : 1)) || (quals && (rc = io.quals.reserve(total ? total : 1))) || (rc = io.read_off.reserve(cn + 1)) ||
+            (rc = io.aln.reserve(cn)) || (rc = io.status.reserve(cn)) || (rc = io.totals.reserve(2)) ||
+            (rc = io.maps.reserve(chunk_map_cap)) || (rc = io.edits.reserve(chunk_edit_cap))) { drain(); return rc; }
+        if (total) GB_CUDA(cudaMemcpyAsync(io.reads.ptr, reads + b0, total, cudaMemcpyHostToDevice, d->s_in));
+        if (quals && total) GB_CUDA(cudaMemcpyAsync(io.quals.ptr, quals + b0, total, cudaMemcpyHostToDevice, d->s_in));
+        GB_CUDA(cudaMemcpyAsync(io.read_off.ptr, read_off + c0, sizeof(uint64_t) * (cn + 1), cudaMemcpyHostToDevice, d->s_in));
+        GB_CUDA(cudaEventRecord(io.ev_in, d->s_in));
+        GB_CUDA(cudaStreamWaitEvent(d->stream, io.ev_in, 0));
+        if (b0) gb::rebase_offsets_kernel<<<(cn + 256) / 256, 256, 0, d->stream>>>(io.read_off.ptr, cn + 1, b0);
+        GB_CUDA(cudaEventRecord(io.ev_k0, d->stream));
+        if ((rc = gb::map_device(d, hp, cn, io.reads.ptr, quals ? io.quals.ptr : nullptr, io.read_off.ptr, max_len, total,
+                                 io.aln.ptr, io.status.ptr, paired, io.maps.ptr, chunk_map_cap, io.edits.ptr, chunk_edit_cap,
+                                 d->c_run.ptr, c0, io.totals.ptr))) { drain(); return rc; }
+        gb::advance_run_kernel<<<1, 1, 0, d->stream>>>(d->c_run.ptr, io.totals.ptr);
+        GB_CUDA(cudaEventRecord(io.ev_k1, d->stream));
+        GB_CUDA(cudaEventRecord(io.ev_done, d->stream));
+        used[ci & 1] = true;
+        // headers + totals of this chunk leave as soon as it is done
+        GB_CUDA(cudaStreamWaitEvent(d->s_out, io.ev_done, 0));
+        GB_CUDA(cudaMemcpyAsync(d->h_totals + 2 * (ci & 1), io.totals.ptr, 2 * sizeof(uint64_t), cudaMemcpyDeviceToHost, d->s_out));
+        GB_CUDA(cudaMemcpyAsync(aln + c0, io.aln.ptr, sizeof(gb_alignment) * cn, cudaMemcpyDeviceToHost, d->s_out));
+        GB_CUDA(cudaMemcpyAsync(status + c0, io.status.ptr, cn, cudaMemcpyDeviceToHost, d->s_out));
+        GB_CUDA(cudaEventRecord(io.ev_hdr, d->s_out));
+        // meanwhile the previous chunk's dense pools can be sized and fetched
+        if (ci > 0 && (rc = finish(ci - 1))) { drain(); return rc; }
     }
+    if ((rc = finish(n_chunks - 1))) { drain(); return rc; }
+    GB_CUDA(cudaStreamSynchronize(d->s_out));
+    GB_CUDA(cudaStreamSynchronize(d->stream));
     d->last_kernel_ms = kernel_ms;
     if (n_mappings_used) *n_mappings_used = map_used;
     if (n_edits_used) *n_edits_used = edit_used;
@@ -439,7 +469,7 @@ extern "C" int gb_map_batch_device(gb_device* d, const gb_map_params* hp, int pa
     if (n_reads == 0) return GB_OK;
     GB_CUDA(cudaSetDevice(d->device));
     return map_device(d, hp, n_reads, d_reads, d_quals, d_read_off, max_read_len, (uint64_t)n_reads * max_read_len, d_aln, d_status, paired != 0,
-                      d_mappings, mapping_pool_cap, d_edits, edit_pool_cap, 0, 0, 0, d_totals);
+                      d_mappings, mapping_pool_cap, d_edits, edit_pool_cap, nullptr, 0, d_totals);
 }
 
 extern "C" int gb_device_set_stream(gb_device* d, void* cuda_stream) {
