@@ -236,8 +236,8 @@ __device__ inline bool fast_pair(const DevIndex& ix, const MapParamsDev& P, cons
 #pragma unroll
             for (uint32_t x = 0; x < PRESENT_WORDS; x++) n_exp += __popc(explored[r][x]);
             if (n_exp > FAST_MAX_EXPLORED) return false;
-            uint8_t ord[FAST_MAX_EXPLORED]; double cbuf[FAST_MAX_EXPLORED + 1];
-            caps[r] = faster_cap(P, a.minimizers + rsp[r]->min_off, ix.k, explored[r], rsp[r]->min_cnt, quals[r], L[r], ord, cbuf);
+            uint64_t mp[FAST_MAX_EXPLORED]; double cbuf[FAST_MAX_EXPLORED + 1];
+            caps[r] = faster_cap(P, a.minimizers + rsp[r]->min_off, ix.k, explored[r], rsp[r]->min_cnt, quals[r], L[r], mp, cbuf);
         }
         const uint32_t cwin[2] = {pair_c0[wp], pair_c1[wp]};
         for (uint32_t r = 0; r < 2; r++) {

@@ -38,21 +38,27 @@ __device__ inline PathBuf slot_buf(uint8_t* cand_base, uint32_t slot, uint32_t m
 __device__ __forceinline__ uint32_t& slot_nm(const PathBuf& pb) { return ((uint32_t*)pb.maps)[2 * pb.map_cap - 2]; }
 __device__ __forceinline__ uint32_t& slot_ne(const PathBuf& pb) { return ((uint32_t*)pb.maps)[2 * pb.map_cap - 1]; }
 
-// faster_cap (minimizer_mapper.cpp:2946-3260); sequential FP64 (one lane).
+// faster_cap (minimizer_mapper.cpp:2946-3260); sequential FP64 (one thread).  The explored
+// minimizers are packed into one 64-bit word each, sorted by (agglomeration end, start):
+//   bits 0-15 agg_start, 16-31 agg_end, 32-47 forward_offset, 48-55 top byte of the hash
+// `mp` needs room for the explored minimizers, `c` for one more double than that.
 __device__ inline double faster_cap(const MapParamsDev& P, const DevMinimizer* mins, uint32_t k, const uint32_t* explored_mask, uint32_t M,
-                                    const uint8_t* qual, uint32_t L, uint8_t* ord /*[MAX_MINIMIZERS]*/, double* c /*[MAX_MINIMIZERS+1]*/) {
+                                    const uint8_t* qual, uint32_t L, uint64_t* mp, double* c) {
     if (qual == nullptr) return INFINITY;
     uint32_t n = 0;
     for (uint32_t i = 0; i < M; i++) if (explored_mask[i >> 5] & (1u << (i & 31))) {
         // stable insertion by (agglomeration end, agglomeration start)
-        const uint32_t ae = (uint32_t)mins[i].agg_start + mins[i].agg_len, as = mins[i].agg_start;
+        const DevMinimizer dm = mins[i];
+        const uint32_t as = dm.agg_start, ae = (uint32_t)dm.agg_start + dm.agg_len;
+        const uint64_t wd = (uint64_t)as | ((uint64_t)ae << 16) | ((uint64_t)dm.fwd_offset << 32) | ((dm.hash >> 56) << 48);
+        const uint32_t key = (ae << 16) | as;
         uint32_t j = n;
         while (j > 0) {
-            const DevMinimizer& o = mins[ord[j - 1]];
-            const uint32_t oe = (uint32_t)o.agg_start + o.agg_len;
-            if (ae < oe || (ae == oe && as < o.agg_start)) { ord[j] = ord[j - 1]; j--; } else break;
+            const uint64_t o = mp[j - 1];
+            const uint32_t okey = ((uint32_t)(o >> 16) << 16) | (uint32_t)(o & 0xffffu);
+            if (key < okey) { mp[j] = o; j--; } else break;
         }
-        ord[j] = (uint8_t)i; n++;
+        mp[j] = wd; n++;
     }
     for (uint32_t i = 0; i <= n; i++) c[i] = -INFINITY;
     c[0] = 0.0;
@@ -60,10 +66,11 @@ __device__ inline double faster_cap(const MapParamsDev& P, const DevMinimizer* m
     auto column_prob = [&](uint32_t begin, uint32_t end, uint32_t index) {
         double p = P.phred_prob[qual[index]];
         for (uint32_t it = begin; it != end; ++it) {
-            const DevMinimizer& m = mins[ord[it]];
-            if (!(m.fwd_offset <= index && index < (uint32_t)m.fwd_offset + k)) {
-                const uint32_t possible = min(k, min(index - m.agg_start + 1, ((uint32_t)m.agg_start + m.agg_len) - index));
-                p *= P.prob_at_least_one[((size_t)possible << 8) + (size_t)(m.hash >> 56)];
+            const uint64_t wd = mp[it];
+            const uint32_t as = (uint32_t)wd & 0xffffu, ae = (uint32_t)(wd >> 16) & 0xffffu, fwd = (uint32_t)(wd >> 32) & 0xffffu;
+            if (index - fwd >= k) {                                     // not inside the minimizer itself (unsigned: index < fwd wraps)
+                const uint32_t possible = min(k, min(index - as + 1, ae - index));
+                p *= P.prob_at_least_one[(possible << 8) + (uint32_t)(wd >> 48)];
             }
         }
         return p;
@@ -78,14 +85,15 @@ __device__ inline double faster_cap(const MapParamsDev& P, const DevMinimizer* m
         const double pv = c[bottom] + p_here;
         for (uint32_t i = bottom + 1; i < top + 1; i++) if (c[i] < pv) c[i] = pv;
     };
-    // for_each_agglomeration_interval (:3088-3161); the "stack" is the window [front, back) of ord
+    // for_each_agglomeration_interval (:3088-3161); the "stack" is the window [front, back) of mp
+    auto agg_start_of = [&](uint32_t it) { return (uint32_t)mp[it] & 0xffffu; };
+    auto agg_end_of = [&](uint32_t it) { return (uint32_t)(mp[it] >> 16) & 0xffffu; };
     uint32_t front = 0, back = 1;
-    uint32_t left = mins[ord[0]].agg_start, bottom = 0;
+    uint32_t left = agg_start_of(0), bottom = 0;
     auto emit_preceding = [&](uint32_t right) {
         while (left < right) {
             const uint32_t stack_size = back - front;
-            const DevMinimizer& f = mins[ord[front]];
-            const uint32_t stack_top_end = (uint32_t)f.agg_start + f.agg_len;
+            const uint32_t stack_top_end = agg_end_of(front);
             if (stack_top_end <= right) {
                 iteratee(left, stack_top_end, bottom, bottom + stack_size);
                 left = stack_size == 1 ? right : stack_top_end;
@@ -96,7 +104,7 @@ __device__ inline double faster_cap(const MapParamsDev& P, const DevMinimizer* m
             }
         }
     };
-    for (uint32_t it = 1; it < n; it++) { emit_preceding(mins[ord[it]].agg_start); back++; }
+    for (uint32_t it = 1; it < n; it++) { emit_preceding(agg_start_of(it)); back++; }
     emit_preceding(L);
     return -c[n] * 10;
 }
@@ -373,8 +381,8 @@ __device__ inline uint32_t finalize_se(const DevIndex& ix, const MapParamsDev& P
     double mapq = 0.0;
     if (win != 0xffffffffu) mapq = max_mapping_quality(scores_sorted, n_scores, P.log_base);
     const double escape_bonus = mapq < 2147483647.0 ? 1.0 : 2.0;
-    double* cbuf = reinterpret_cast<double*>(dps.Hp);       // DP columns are free here
-    uint8_t* ordbuf = reinterpret_cast<uint8_t*>(dps.Hc);
+    double* cbuf = reinterpret_cast<double*>(dps.Hp);       // DP columns are free here (Hp|Ep and Hc|Ec)
+    uint64_t* ordbuf = reinterpret_cast<uint64_t*>(dps.Hc);
     double cap = 0.0;
     if (lane == 0) cap = escape_bonus * faster_cap(P, a.minimizers + rs.min_off, ix.k, explored, rs.min_cnt, qual, L, ordbuf, cbuf);
     cap = __shfl_sync(FULL, cap, 0);
@@ -510,7 +518,7 @@ __device__ inline uint32_t finalize_pe(const DevIndex& ix, const MapParamsDev& P
     if (pair_better[wp] > 1) fragment_cluster_cap = -10.0 * log10(1.0 - (1.0 / (double)pair_better[wp]));
     double caps[2] = {0.0, 0.0};
     double* cbuf = reinterpret_cast<double*>(dps.Hp);
-    uint8_t* ordbuf = reinterpret_cast<uint8_t*>(dps.Hc);
+    uint64_t* ordbuf = reinterpret_cast<uint64_t*>(dps.Hc);
     if (lane == 0) {
         for (uint32_t r = 0; r < 2; r++) caps[r] = faster_cap(P, a.minimizers + rs[r].min_off, ix.k, explored[r], rs[r].min_cnt, qual[r], L[r], ordbuf, cbuf);
     }
