@@ -99,3 +99,16 @@ def test_map_parity_across_host_chunks(monkeypatch):
     g = synth.make_variant_graph(length=100000, n_snp=160, n_ins=20, n_del=20, n_haps=8, seed=5)
     rs = synth.simulate_reads(g, 1501, length=150, sub_rate=0.02, seed=54)
     _run(g, rs)
+
+
+@pytest.mark.gpu
+def test_map_parity_with_read_coverage_filter_active():
+    """max_unique_min below the minimizer count: the max-min||num-bp-per-min stage consults the
+    read-coverage vector (find_seeds :4312-4355) instead of being a pass-through."""
+    g = synth.make_variant_graph(length=100000, n_snp=160, n_ins=20, n_del=20, n_haps=8, seed=5)
+    rs = synth.simulate_reads(g, 1200, length=150, sub_rate=0.01, seed=55)
+    p = capi.default_map_params()
+    p.max_unique_min = 6
+    p.num_bp_per_min = 50
+    p.minimizer_coverage_flank = 10
+    _run(g, rs, p)

@@ -112,7 +112,7 @@ extern "C" int gb_device_create(const gb_flat_index* ix, int device_ordinal, gb_
     if (const char* env = std::getenv("GIRAFFE_B200_SEED_TABLES")) {
         unsigned mc = 0, cc = 0;
         if (std::sscanf(env, "%u,%u", &mc, &cc) == 2 && mc >= 2 && cc >= 1) {
-            d->seed_mc = std::min<uint32_t>(gb::MAX_MINIMIZERS, (mc + 7u) & ~7u);
+            d->seed_mc = std::max<uint32_t>(16u, std::min<uint32_t>(gb::MAX_MINIMIZERS, (mc + 7u) & ~7u));
             d->seed_cc = std::min<uint32_t>(64u, cc);
         }
     }

@@ -168,32 +168,47 @@ __device__ __forceinline__ uint32_t seed_phase_a(const DevIndex& ix, const MapPa
     if (L < window_bp) return GB_ITEM_OK;          // no minimizers -> no seeds
 
     // ---- canonical k-mer hashes ------------------------------------------------------------
+    // The read is packed 2 bits per base (first base in the top bits) with one warp vote per 32
+    // bases; lane s then cuts k-mer s out of two packed words, so no lane rolls through k - 1
+    // warm-up bases.  Encoding and canonical choice as gbwtgraph's minimizer key (minimizer_common.h).
     const uint32_t nk = L - k + 1;
     {
-        const uint64_t mask = (1ull << (2 * k)) - 1ull;
-        const uint32_t chunk = (nk + 31) / 32;
-        const uint32_t s0 = min(nk, lane * chunk), s1 = min(nk, s0 + chunk);
-        if (s0 < s1) {
-            uint64_t fk = 0, rk = 0; uint32_t run = 0;
-            for (uint32_t i = s0; i < s1 + k - 1; i++) {
-                const uint32_t c = gbmin::base_code(sm.read[i]);
-                if (c < 4) { fk = ((fk << 2) | c) & mask; rk = (rk >> 2) | ((uint64_t)(3 - c) << (2 * (k - 1))); run++; }
-                else { fk = 0; rk = 0; run = 0; }
-                if (i + 1 >= s0 + k) {
-                    const uint32_t s = i + 1 - k;
-                    uint8_t flag = 0; uint64_t h = ~0ull, key = 0;
-                    if (run >= k) {
-                        const uint64_t hf = gbmin::hash64(fk), hr = gbmin::hash64(rk);
-                        if (hr < hf) { h = hr; key = rk; flag = 3; } else { h = hf; key = fk; flag = 1; }
-                    }
-                    sm.khash[s] = h; sm.kkey[s] = key; sm.kflag[s] = flag;
-                }
+        uint64_t* packed = sm.m_key;                                    // [n_blocks + 1]; m_key is filled later
+        uint32_t* invalid = reinterpret_cast<uint32_t*>(sm.m_key + 17);  // [n_blocks]  (Mc >= 16: 24 * Mc bytes follow m_key)
+        const uint32_t n_blocks = (L + 31) >> 5;
+        for (uint32_t t = 0; t < n_blocks; t++) {
+            const uint32_t pos = t * 32 + lane;
+            const uint32_t ch = pos < L ? sm.read[pos] : 0u;
+            const uint32_t idx = (ch & 0xDFu) - 0x41u;                     // 'A' = 0, 'C' = 2, 'G' = 6, 'T' = 19
+            const bool ok = idx < 32u && ((0x00080045u >> idx) & 1u);
+            uint32_t code = (ch >> 1) & 3u; code ^= code >> 1;             // A 0, C 1, G 2, T 3
+            const uint32_t v = ok ? code : 0u;
+            const uint32_t hi = __reduce_or_sync(FULL, lane < 16 ? v << (30 - 2 * lane) : 0u);
+            const uint32_t lo = __reduce_or_sync(FULL, lane >= 16 ? v << (62 - 2 * lane) : 0u);
+            const uint32_t bad = __ballot_sync(FULL, !ok && pos < L);
+            if (lane == 0) { packed[t] = ((uint64_t)hi << 32) | lo; invalid[t] = bad; }
+        }
+        if (lane == 0) packed[n_blocks] = 0;
+        __syncwarp();
+        for (uint32_t s = lane; s < nk; s += 32) {
+            const uint32_t wd = s >> 5, sh = 2 * (s & 31);
+            const uint64_t x = sh ? (packed[wd] << sh) | (packed[wd + 1] >> (64 - sh)) : packed[wd];
+            uint8_t flag = 0; uint64_t h = ~0ull, key = 0;
+            if (!any_bit_in_range(invalid, s, s + k)) {
+                const uint64_t fk = x >> (64 - 2 * k);
+                uint64_t rv = __brevll((~x) >> (64 - 2 * k));              // reversed groups, bits swapped inside each group
+                rv = ((rv & 0xAAAAAAAAAAAAAAAAull) >> 1) | ((rv & 0x5555555555555555ull) << 1);
+                const uint64_t rk = rv >> (64 - 2 * k);
+                const uint64_t hf = gbmin::hash64(fk), hr = gbmin::hash64(rk);
+                if (hr < hf) { h = hr; key = rk; flag = 3; } else { h = hf; key = fk; flag = 1; }
             }
+            sm.khash[s] = h; sm.kkey[s] = key; sm.kflag[s] = flag;
         }
     }
     __syncwarp();
 
     // ---- window minima -> minimizers in read order ---------------------------------------------
+    // (invalid k-mers carry hash ~0, so they never beat a valid one)
     uint32_t M = 0;
     {
         const int32_t last_window = (int32_t)(L - window_bp);
@@ -203,10 +218,11 @@ __device__ __forceinline__ uint32_t seed_phase_a(const DevIndex& ix, const MapPa
             if (s < nk && (sm.kflag[s] & 1)) {
                 const uint64_t h = sm.khash[s];
                 int32_t l = -1000000, r = 1000000;
-                for (int32_t t = (int32_t)s - 1; t >= 0 && t > (int32_t)s - (int32_t)w; t--)
-                    if ((sm.kflag[t] & 1) && sm.khash[t] < h) { l = t; break; }
-                for (int32_t t = (int32_t)s + 1; t < (int32_t)nk && t < (int32_t)s + (int32_t)w; t++)
-                    if ((sm.kflag[t] & 1) && sm.khash[t] < h) { r = t; break; }
+                for (int32_t d = 1; d < (int32_t)w; d++) {
+                    const int32_t tl = (int32_t)s - d, tr = (int32_t)s + d;
+                    if (l < 0 && tl >= 0 && sm.khash[tl] < h) l = tl;
+                    if (r == 1000000 && tr < (int32_t)nk && sm.khash[tr] < h) r = tr;
+                }
                 lo = max(max((int32_t)s - (int32_t)w + 1, l + 1), 0);
                 hi = min(min((int32_t)s, r - (int32_t)w), last_window);
                 is_min = lo <= hi;
@@ -257,37 +273,134 @@ __device__ __forceinline__ uint32_t seed_phase_a(const DevIndex& ix, const MapPa
     __syncwarp();
 
     // ---- shuffle the runs tied at the top score (sort_shuffling_ties over runs) ----------------------
+    // Runs (equal keys, adjacent after the sort) and the top-score prefix are found by the whole warp;
+    // only the Fisher-Yates draws themselves are sequential.
     uint8_t* run_begin = reinterpret_cast<uint8_t*>(sm.khash);          // khash/kkey are dead: scratch
     uint8_t* run_len = run_begin + sm.Mc;
     uint8_t* tmp_order = run_len + sm.Mc;
-    if (lane == 0) {
-        const double top = sm.m_score[sm.m_order[0]];
-        uint32_t T = 0, pos = 0;
-        while (pos < M && sm.m_score[sm.m_order[pos]] == top) {
-            uint32_t e = pos + 1;
-            while (e < M && sm.m_key[sm.m_order[e]] == sm.m_key[sm.m_order[pos]]) e++;
-            run_begin[T] = (uint8_t)pos; run_len[T] = (uint8_t)(e - pos); T++;
-            pos = e;
+    auto run_start_words = [&](uint32_t* rsw) {
+#pragma unroll
+        for (uint32_t t = 0; t < PRESENT_WORDS; t++) {
+            const uint32_t i = lane + 32 * t;
+            bool rs = false;
+            if (i < M) rs = i == 0 || sm.m_key[sm.m_order[i - 1]] != sm.m_key[sm.m_order[i]];
+            rsw[t] = __ballot_sync(FULL, rs);
         }
-        const uint32_t tied_end = pos;
+    };
+    // first run start after position i (or `end`)
+    auto next_run_start = [&](const uint32_t* rsw, uint32_t i, uint32_t end) {
+        uint32_t nxt = end;
+        bool found = false;
+#pragma unroll
+        for (uint32_t t = 0; t < PRESENT_WORDS; t++) {
+            uint32_t m = rsw[t];
+            if (t < (i >> 5)) m = 0;
+            else if (t == (i >> 5)) m &= ~((2u << (i & 31)) - 1u);
+            if (!found && m) { nxt = 32 * t + (uint32_t)__ffs(m) - 1; found = true; }
+        }
+        return min(nxt, end);
+    };
+    uint32_t rsw[PRESENT_WORDS];
+    run_start_words(rsw);
+    {
+        const double top = sm.m_score[sm.m_order[0]];
+        uint32_t tied_end = 0, T = 0;
+        uint32_t tiew[PRESENT_WORDS];
+#pragma unroll
+        for (uint32_t t = 0; t < PRESENT_WORDS; t++) {
+            const uint32_t i = lane + 32 * t;
+            tiew[t] = __ballot_sync(FULL, i < M && sm.m_score[sm.m_order[i]] == top);
+            tied_end += __popc(tiew[t]); T += __popc(tiew[t] & rsw[t]);
+        }
         if (T > 1) {
-            for (uint32_t i = 1; i < T; i++) {
-                const uint32_t j = rng_next(rng) % (i + 1);
-                const uint8_t tb = run_begin[j], tl = run_len[j];
-                run_begin[j] = run_begin[i]; run_len[j] = run_len[i];
-                run_begin[i] = tb; run_len[i] = tl;
+            uint32_t before = 0;
+#pragma unroll
+            for (uint32_t t = 0; t < PRESENT_WORDS; t++) {
+                const uint32_t i = lane + 32 * t;
+                const uint32_t starts = tiew[t] & rsw[t];
+                if ((starts >> lane) & 1u) {
+                    const uint32_t q = before + __popc(starts & ((1u << lane) - 1u));
+                    run_begin[q] = (uint8_t)i; run_len[q] = (uint8_t)(next_run_start(rsw, i, tied_end) - i);
+                }
+                before += __popc(starts);
             }
-            uint32_t wpos = 0;
-            for (uint32_t t = 0; t < T; t++)
-                for (uint32_t x = 0; x < run_len[t]; x++) tmp_order[wpos++] = sm.m_order[run_begin[t] + x];
-            for (uint32_t x = 0; x < tied_end; x++) sm.m_order[x] = tmp_order[x];
+            __syncwarp();
+            if (lane == 0) {
+                for (uint32_t i = 1; i < T; i++) {
+                    const uint32_t j = rng_next(rng) % (i + 1);
+                    const uint8_t tb = run_begin[j], tl = run_len[j];
+                    run_begin[j] = run_begin[i]; run_len[j] = run_len[i];
+                    run_begin[i] = tb; run_len[i] = tl;
+                }
+            }
+            __syncwarp();
+            uint32_t carry = 0;
+            for (uint32_t qb = 0; qb < T; qb += 32) {
+                const uint32_t q = qb + lane;
+                const uint32_t len = q < T ? run_len[q] : 0u;
+                const uint32_t incl = (uint32_t)warp_incl_scan((int)len);
+                const uint32_t wstart = carry + incl - len;
+                if (q < T) for (uint32_t x = 0; x < len; x++) tmp_order[wstart + x] = sm.m_order[run_begin[q] + x];
+                carry += __shfl_sync(FULL, incl, 31);
+            }
+            __syncwarp();
+            for (uint32_t x = lane; x < tied_end; x += 32) sm.m_order[x] = tmp_order[x];
+            __syncwarp();
+            run_start_words(rsw);                      // runs moved as blocks: new start positions
         }
     }
     rng.state = __shfl_sync(FULL, rng.state, 0); rng.inited = __shfl_sync(FULL, rng.inited, 0);
     __syncwarp();
 
-    // ---- find_seeds filter cascade (sequential running state; lane 0) -------------------------------------
+    // ---- find_seeds filter cascade ------------------------------------------------------------------------
+    const uint32_t num_min_by_read_len_ = L / P.num_bp_per_min;
+    const bool track_cov_ = P.max_unique_min != 0 && M > max(P.max_unique_min, num_min_by_read_len_);
     uint32_t total_hits = 0;
+    if (!track_cov_) {
+        // The read-coverage stage cannot reject anything while fewer than max(max_unique_min, L / num_bp_per_min)
+        // minimizers have passed, i.e. for every read the tables can hold with default parameters.  Per-position
+        // inputs (hits, score, run hits, run start) are staged by the warp; the running-score chain stays sequential.
+        uint32_t* s_hits = reinterpret_cast<uint32_t*>(sm.khash);           // [M]
+        uint32_t* s_runhits = s_hits + M;                                    // [M]  bit 31 = run start
+        double* s_score = reinterpret_cast<double*>(sm.kkey);                // [M]
+        for (uint32_t i = lane; i < M; i += 32) { const uint32_t a = sm.m_order[i]; s_hits[i] = sm.m_hit_cnt[a]; s_score[i] = sm.m_score[a]; }
+        __syncwarp();
+#pragma unroll
+        for (uint32_t t = 0; t < PRESENT_WORDS; t++) {
+            const uint32_t i = lane + 32 * t;
+            if ((rsw[t] >> lane) & 1u) {
+                const uint32_t e = next_run_start(rsw, i, M);
+                uint32_t sum = 0;
+                for (uint32_t j = i; j < e; j++) sum += s_hits[j];
+                for (uint32_t j = i; j < e; j++) s_runhits[j] = sum | (j == i ? 0x80000000u : 0u);
+            }
+        }
+        __syncwarp();
+        if (lane == 0) {
+            double base_target_score = 0.0, target_score = 0.0, selected_score = 0.0;
+            const bool use_fraction = (P.hit_cap != 0 || P.minimizer_score_fraction != 1.0);
+            if (use_fraction) {
+                for (uint32_t i = 0; i < M; i++) base_target_score += s_score[i];
+                target_score = (base_target_score * P.minimizer_score_fraction) + 0.000001;
+            }
+            bool taking_run = false;
+            for (uint32_t i = 0; i < M; i++) {
+                const uint32_t hits = s_hits[i], rh = s_runhits[i], run_hits = rh & 0x7fffffffu;
+                if (rh >> 31) taking_run = false;
+                bool passing = hits > 0 && run_hits <= P.hard_hit_cap;             // any-hits, hard-hit-cap
+                if (passing && use_fraction) {                                      // hit-cap||score-fraction
+                    const double score = s_score[i];
+                    passing = (hits <= P.hit_cap) || (run_hits <= P.hard_hit_cap && selected_score + score <= target_score) || taking_run;
+                    if (passing) selected_score += score; else target_score = selected_score;
+                }
+                sm.m_pass[i] = passing ? 1 : 0;
+                if (passing) { taking_run = true; total_hits += hits; }
+            }
+        }
+        total_hits = __shfl_sync(FULL, total_hits, 0);
+        __syncwarp();
+    } else {
+        // general path (coverage vector in use): sequential running state on lane 0
     if (lane == 0) {
         double base_target_score = 0.0, target_score = 0.0, selected_score = 0.0;
         const bool use_fraction = (P.hit_cap != 0 || P.minimizer_score_fraction != 1.0);
@@ -340,6 +453,8 @@ __device__ __forceinline__ uint32_t seed_phase_a(const DevIndex& ix, const MapPa
     }
     total_hits = __shfl_sync(FULL, total_hits, 0);
     __syncwarp();
+
+    }
 
     // ---- minimizer records (score order) -------------------------------------------------------------------
     uint32_t min_off = 0;

@@ -323,7 +323,7 @@ __device__ inline int32_t xdrop_tree(const DevIndex& ix, const DevScores& sc, co
             if (state == 0) {
                 const uint32_t src = tbv & 3u;
                 if (src == 0) {
-                    if (j == 0) { if (lane == 0) printf("tb: diag at j=0 node %u col %u tbv %u m %u\n", node, col, (unsigned)tbv, m); overflow = true; return 0; }
+                    if (j == 0) { overflow = true; return 0; }          // corrupt traceback: refuse, never walk off the matrix
                     const uint8_t qc = q[j - 1], r = __ldg(ix.seq + tn.seq_off + col);
                     if (lane == 0) ws.steps[n_steps] = (node << 8) | ((qc == r && is_acgt(qc)) ? 0u : 1u);
                     n_steps++;
@@ -346,14 +346,7 @@ __device__ inline int32_t xdrop_tree(const DevIndex& ix, const DevScores& sc, co
             if (lane == 0) ws.steps[n_steps] = (node << 8) | 2u;
             n_steps++;
             const bool open = (tbv & 8u) != 0;
-            if (j == 0) {
-                if (lane == 0) {
-                    printf("tb: ins at j=0 node %u col %u tbv %u m %u best (%u,%u,%u) score %d t0 %u t1 %u gap %u xt %d\n", node, col, (unsigned)tbv, m, best_node, best_col, best_j, best, t0, t1, max_gap, xt);
-                    for (uint32_t i = t0; i < t1 && i < t0 + 12; i++) { const TreeNode x = ws.tree[i]; printf("  node %u parent %d v %u seq_off %u len %u depth %u computed %u tb_col %u lmax %d seq %.8s\n", i, x.parent, x.node, x.seq_off, x.len, x.depth, x.computed, x.tb_col, x.lineage_max, (const char*)(ix.seq + x.seq_off)); }
-                    printf("  q %.20s\n", (const char*)q);
-                }
-                overflow = true; return 0;
-            }
+            if (j == 0) { overflow = true; return 0; }
             j--;
             state = open ? 0 : 2;
         }
