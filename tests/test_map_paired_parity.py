@@ -85,10 +85,11 @@ def test_paired_rescue_is_refused_loudly():
 
 
 @pytest.mark.gpu
-@pytest.mark.parametrize("tables", ["16,1", "8,2"])
+@pytest.mark.parametrize("tables", ["16,1", "8,2", "64,16,8"])
 def test_map_paired_parity_through_the_seeding_retry_pass(tables, monkeypatch):
     """First-pass seeding tables too small for most pairs: they are retried at full size by the
-    second launch and must come out identical."""
+    second launch and must come out identical.  A third number caps the seed sets clustered in
+    shared memory, sending the others through label propagation over the HBM records."""
     monkeypatch.setenv("GIRAFFE_B200_SEED_TABLES", tables)
     g = synth.make_variant_graph(length=100000, n_snp=160, n_ins=20, n_del=20, n_haps=8, seed=5)
     rs = synth.simulate_pairs(g, 1200, sub_rate=0.01, seed=51)

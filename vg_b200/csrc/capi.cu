@@ -39,7 +39,7 @@ struct ExtendBatch {
     const DevItem* items; const uint32_t* n_items_dev;
 };
 
-__global__ void __launch_bounds__(EXTEND_WARPS * 32, 3)
+__global__ void __launch_bounds__(EXTEND_WARPS * 32, 4)
 extend_kernel(DevIndex ix, ExtendParams p, ExtendBatch b, ExtendWorkspace ws) {
     extern __shared__ __align__(16) uint8_t smem[];
     const int warp_in_block = threadIdx.x >> 5;
@@ -110,10 +110,11 @@ extern "C" int gb_device_create(const gb_flat_index* ix, int device_ordinal, gb_
         if (v >= 2 && v <= (1ul << 24)) d->map_chunk = (uint32_t)(v & ~1ul);
     }
     if (const char* env = std::getenv("GIRAFFE_B200_SEED_TABLES")) {
-        unsigned mc = 0, cc = 0;
-        if (std::sscanf(env, "%u,%u", &mc, &cc) == 2 && mc >= 2 && cc >= 1) {
+        unsigned mc = 0, cc = 0, ns = 64;
+        if (std::sscanf(env, "%u,%u,%u", &mc, &cc, &ns) >= 2 && mc >= 2 && cc >= 1) {
             d->seed_mc = std::max<uint32_t>(16u, std::min<uint32_t>(gb::MAX_MINIMIZERS, (mc + 7u) & ~7u));
             d->seed_cc = std::min<uint32_t>(64u, cc);
+            d->seed_ns = std::min<uint32_t>(64u, ns);
         }
     }
     GB_CUDA(cudaStreamCreateWithFlags(&d->own_stream, cudaStreamNonBlocking));

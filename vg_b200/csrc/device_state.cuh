@@ -61,7 +61,7 @@ struct gb_device {
     int device = 0;
     int n_sms = 0;
     // first-pass seeding table sizes (minimizers, clusters per read); GIRAFFE_B200_SEED_TABLES="Mc,Cc" overrides
-    uint32_t seed_mc = 64, seed_cc = 16;
+    uint32_t seed_mc = 64, seed_cc = 16, seed_ns = 64;
     cudaStream_t stream = nullptr, own_stream = nullptr;
     cudaEvent_t ev_stage[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;

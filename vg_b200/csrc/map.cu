@@ -35,7 +35,7 @@ struct MapBatch {
     // first pass's small shared tables (Mc, Cc) are appended to retry_list
     const uint32_t* in_list; const uint32_t* in_count;
     uint32_t* retry_list; uint32_t* retry_count;
-    uint32_t Mc, Cc;
+    uint32_t Mc, Cc, Ns;
 };
 
 // ---------------------------------------------------------------------------------------
@@ -243,7 +243,7 @@ int map_device(gb_device* d, const gb_map_params* hp, uint32_t n_reads, const ui
     }
     MapBatch b; b.reads = d_reads; b.quals = d_quals; b.read_off = d_read_off; b.n_reads = n_reads;
     b.states = d->p_states.ptr; b.work_counter = cur + 0; b.Lc = Lc;
-    b.in_list = nullptr; b.in_count = nullptr; b.retry_list = nullptr; b.retry_count = nullptr; b.Mc = MAX_MINIMIZERS; b.Cc = MAX_CLUSTERS;
+    b.in_list = nullptr; b.in_count = nullptr; b.retry_list = nullptr; b.retry_count = nullptr; b.Mc = MAX_MINIMIZERS; b.Cc = MAX_CLUSTERS; b.Ns = d->seed_ns;
     SeedPools pools;
     pools.minimizers = d->p_min.ptr; pools.min_cap = (uint32_t)min_cap; pools.min_cursor = cur + 1;
     pools.seeds = d->p_seeds.ptr; pools.seed_cap = (uint32_t)seed_cap; pools.seed_cursor = cur + 2;

@@ -34,7 +34,7 @@ seed_kernel_pe(DevIndex ix, MapParamsDev P, MapBatch b, SeedPools pools, PairBat
     extern __shared__ __align__(16) uint8_t smem[];
     __shared__ uint32_t s_base;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const SeedSmem sm = carve_seed_smem(smem + (size_t)warp * seed_smem_bytes(b.Lc, b.Mc, b.Cc), b.Lc, b.Mc, b.Cc);
+    const SeedSmem sm = carve_seed_smem(smem + (size_t)warp * seed_smem_bytes(b.Lc, b.Mc, b.Cc), b.Lc, b.Mc, b.Cc, b.Ns);
     const uint32_t n_pairs = b.n_reads / 2;
     const uint32_t limit = b.in_list ? min(*b.in_count, n_pairs) : n_pairs;
     while (true) {

@@ -54,7 +54,8 @@ struct SeedSmem {
     uint8_t*  scratch;     // [2 * Cc + Mc]
     // capacities of this launch: Mc minimizers per read, Cc clusters per read.  The first launch uses
     // small tables (occupancy); units that do not fit are retried by a second launch at the maxima.
-    uint32_t Mc, Cc;
+    uint32_t Mc, Cc, Lc;
+    uint32_t ns_max;       // largest pair seed set clustered in shared memory (<= 64)
 };
 
 __host__ __device__ inline size_t seed_smem_bytes(uint32_t Lc, uint32_t Mc, uint32_t Cc) {
@@ -73,10 +74,10 @@ __host__ __device__ inline size_t seed_smem_bytes(uint32_t Lc, uint32_t Mc, uint
 }
 
 // Lc, Mc, Cc are multiples of 8, so every array below stays naturally aligned.
-__device__ inline SeedSmem carve_seed_smem(uint8_t* base, uint32_t Lc, uint32_t Mc, uint32_t Cc) {
+__device__ inline SeedSmem carve_seed_smem(uint8_t* base, uint32_t Lc, uint32_t Mc, uint32_t Cc, uint32_t ns_max = 64) {
     SeedSmem s;
     uint8_t* p = base;
-    s.Mc = Mc; s.Cc = Cc;
+    s.Mc = Mc; s.Cc = Cc; s.Lc = Lc; s.ns_max = ns_max;
     s.khash = (uint64_t*)p; p += (size_t)Lc * 8;
     s.kkey = (uint64_t*)p; p += (size_t)Lc * 8;
     s.m_key = (uint64_t*)p; p += Mc * 8;
@@ -477,32 +478,42 @@ __device__ __forceinline__ uint32_t seed_phase_a(const DevIndex& ix, const MapPa
     if (seed_off + total_hits > pools.seed_cap) return GB_ITEM_OUT_FULL;
     DevSeed* seeds = pools.seeds + seed_off;
     {
-        uint32_t wpos = 0;
-        for (uint32_t i = 0; i < M; i++) {
-            if (!sm.m_pass[i]) continue;
+        // one lane per (minimizer, hit): exclusive prefix of the passing minimizers' hit counts, then
+        // each seed index finds its minimizer by binary search (seed order = score order, hit order)
+        uint32_t* pre = reinterpret_cast<uint32_t*>(sm.khash);             // [M + 1]
+        uint32_t carry = 0;
+        for (uint32_t base = 0; base < M; base += 32) {
+            const uint32_t i = base + lane;
+            const uint32_t h = (i < M && sm.m_pass[i]) ? sm.m_hit_cnt[sm.m_order[i]] : 0u;
+            const uint32_t incl = (uint32_t)warp_incl_scan((int)h);
+            if (i < M) pre[i] = carry + incl - h;
+            carry += __shfl_sync(FULL, incl, 31);
+        }
+        if (lane == 0) pre[M] = carry;
+        __syncwarp();
+        for (uint32_t idx = lane; idx < total_hits; idx += 32) {
+            uint32_t lo = 0, hi = M;                                         // last i with pre[i] <= idx
+            while (hi - lo > 1) { const uint32_t mid = (lo + hi) >> 1; if (pre[mid] <= idx) lo = mid; else hi = mid; }
+            const uint32_t i = lo, j = idx - pre[lo];
             const uint32_t a = sm.m_order[i];
-            const uint32_t hits = sm.m_hit_cnt[a], hoff = sm.m_hit_off[a];
             const bool rev = sm.m_rev[a];
-            for (uint32_t j = lane; j < hits; j += 32) {
-                const gb_hit* hp = ix.hits + hoff + j;
-                // gb_hit is 24 bytes (8-byte aligned): three 64-bit loads
-                const uint2 pw = __ldg(reinterpret_cast<const uint2*>(hp));
-                const uint2 p1 = __ldg(reinterpret_cast<const uint2*>(hp) + 1);
-                const uint2 p2 = __ldg(reinterpret_cast<const uint2*>(hp) + 2);
-                const uint64_t pos = ((uint64_t)pw.y << 32) | pw.x;
-                uint32_t node = (uint32_t)(pos >> 10), off = (uint32_t)(pos & 1023u);
-                const uint32_t nlen = load_node(ix, node).len;
-                if (rev) { node ^= 1u; off = nlen - off - 1; }          // reverse_base_pos, :4462-4465
-                const uint32_t off_f = (node & 1u) ? nlen - 1 - off : off;
-                DevSeed s;
-                s.node = node; s.offset = off; s.source = i; s.label = wpos + j;
-                s.c_in = (int32_t)p1.x + (int32_t)off_f;
-                s.c_out = (int32_t)p1.y - (int32_t)(nlen - off_f);
-                s.slot = p2.x;
-                s.id_off = ((node >> 1) << 10) | off_f;
-                seeds[wpos + j] = s;
-            }
-            wpos += hits;
+            const gb_hit* hp = ix.hits + sm.m_hit_off[a] + j;
+            // gb_hit is 24 bytes (8-byte aligned): three 64-bit loads
+            const uint2 pw = __ldg(reinterpret_cast<const uint2*>(hp));
+            const uint2 p1 = __ldg(reinterpret_cast<const uint2*>(hp) + 1);
+            const uint2 p2 = __ldg(reinterpret_cast<const uint2*>(hp) + 2);
+            const uint64_t pos = ((uint64_t)pw.y << 32) | pw.x;
+            uint32_t node = (uint32_t)(pos >> 10), off = (uint32_t)(pos & 1023u);
+            const uint32_t nlen = load_node(ix, node).len;
+            if (rev) { node ^= 1u; off = nlen - off - 1; }          // reverse_base_pos, :4462-4465
+            const uint32_t off_f = (node & 1u) ? nlen - 1 - off : off;
+            DevSeed sd;
+            sd.node = node; sd.offset = off; sd.source = i; sd.label = idx;
+            sd.c_in = (int32_t)p1.x + (int32_t)off_f;
+            sd.c_out = (int32_t)p1.y - (int32_t)(nlen - off_f);
+            sd.slot = p2.x;
+            sd.id_off = ((node >> 1) << 10) | off_f;
+            seeds[idx] = sd;
         }
     }
     rs.seed_off = seed_off; rs.seed_cnt = total_hits;
@@ -543,6 +554,11 @@ struct ClusterScratch {
     uint8_t* has_first;    // [F]
     uint8_t* has_pair;     // [F]
     uint32_t F;
+    // joint clustering of small seed sets in shared memory (whatever is left of the dead arrays)
+    uint4* seedbuf;        // [ns_cap]  (id_off, c_in, c_out, slot)
+    uint8_t* lab_frag;     // [ns_cap]  fragment label (index in the concatenation of both reads)
+    uint8_t* lab_read;     // [ns_cap]  read-cluster label (same index space)
+    uint32_t ns_cap;       // <= 64
 };
 __host__ __device__ inline uint32_t cluster_scratch_fragments(uint32_t Cc) { return 2 * Cc < MAX_FRAGMENTS ? 2 * Cc : MAX_FRAGMENTS; }
 __host__ __device__ inline size_t cluster_scratch_bytes(uint32_t Cc) { const size_t F = cluster_scratch_fragments(Cc); return 64 + 32 * F + 16 * (size_t)Cc + 3 * F; }
@@ -555,7 +571,12 @@ __device__ __forceinline__ ClusterScratch carve_cluster_scratch(const SeedSmem& 
     cs.fs0 = (double*)p; p += 8 * cs.F; cs.fs1 = (double*)p; p += 8 * cs.F;
     cs.fc0 = (double*)p; p += 8 * cs.F; cs.fc1 = (double*)p; p += 8 * cs.F;
     cs.side = (uint32_t*)p; p += 8 * sm.Cc; cs.heads = (uint32_t*)p; p += 8 * sm.Cc;
-    cs.fo = p; p += cs.F; cs.has_first = p; p += cs.F; cs.has_pair = p;
+    cs.fo = p; p += cs.F; cs.has_first = p; p += cs.F; cs.has_pair = p; p += cs.F;
+    const size_t used = ((size_t)(p - reinterpret_cast<uint8_t*>(sm.khash)) + 15) & ~(size_t)15;
+    const size_t dead = seed_dead_bytes(sm.Lc, sm.Mc);
+    cs.ns_cap = dead > used ? (uint32_t)min((size_t)min(64u, sm.ns_max), (dead - used) / 18) : 0u;
+    cs.seedbuf = reinterpret_cast<uint4*>(reinterpret_cast<uint8_t*>(sm.khash) + used);
+    cs.lab_frag = reinterpret_cast<uint8_t*>(cs.seedbuf + cs.ns_cap); cs.lab_read = cs.lab_frag + cs.ns_cap;
     return cs;
 }
 
@@ -762,45 +783,121 @@ __device__ __forceinline__ uint32_t cluster_phase_pe(const DevIndex& ix, const M
     const int32_t read_limit = (int32_t)max(P.distance_limit, L0 + 50);
     const ClusterScratch cs = carve_cluster_scratch(sm);
 
-    // pass 0: fragment components over both reads (labels = index in the concatenation), stashed in
-    // the upper bits of `source` (source < 128); passes 1, 2: the read clusters of each read.
-#pragma unroll 1
-    for (uint32_t pass = 0; pass < 3; pass++) {
-        DevSeed* sa = pass == 2 ? s1 : s0; const uint32_t na = pass == 2 ? H1 : H0;
-        const uint32_t nb = pass == 0 ? H1 : 0u;
-        for (uint32_t i = lane; i < na; i += 32) sa[i].label = i;
-        for (uint32_t i = lane; i < nb; i += 32) s1[i].label = na + i;
-        __syncwarp();
-        propagate_labels(sa, na, s1, nb, pass == 0 ? fragment_limit : read_limit);
-        if (pass == 0) {
-            for (uint32_t i = lane; i < H0; i += 32) s0[i].source |= s0[i].label << 8;
-            for (uint32_t i = lane; i < H1; i += 32) s1[i].source |= s1[i].label << 8;
-        }
-        __syncwarp();
-    }
-    // the fragment label of each read-cluster root goes to the side table, then `source` is restored
     uint32_t Cn[2] = {0, 0};
     uint32_t overflow = 0;
+    const uint32_t n_all = H0 + H1;
+    if (n_all <= cs.ns_cap) {
+        // ---- small seed sets (the usual case): one pass builds both adjacency relations as 64-bit
+        // masks in registers (lane owns seeds lane and lane + 32), components by min-label sweeps
+        // over the masks; labels live in shared memory.
+        for (uint32_t i = lane; i < n_all; i += 32) {
+            const DevSeed sd = i < H0 ? s0[i] : s1[i - H0];
+            cs.seedbuf[i] = make_uint4(sd.id_off, (uint32_t)sd.c_in, (uint32_t)sd.c_out, sd.slot);
+        }
+        __syncwarp();
+        uint4 own[2]; bool has[2]; uint64_t adj_f[2] = {0, 0}, adj_r[2] = {0, 0};
+#pragma unroll
+        for (uint32_t q = 0; q < 2; q++) { const uint32_t i = lane + 32 * q; has[q] = i < n_all; own[q] = has[q] ? cs.seedbuf[i] : make_uint4(0, 0, 0, 0); }
+        for (uint32_t j = 0; j < n_all; j++) {
+            const uint4 sj = cs.seedbuf[j];
+            const bool j_first = j < H0;
+#pragma unroll
+            for (uint32_t q = 0; q < 2; q++) {
+                const uint32_t i = lane + 32 * q;
+                if (!has[q] || i == j) continue;
+                // unoriented minimum distance through the payload, as seeds_within
+                int32_t d;
+                if ((own[q].x >> 10) == (sj.x >> 10)) { d = (int32_t)(sj.x & 1023u) - (int32_t)(own[q].x & 1023u); d = d >= 0 ? d : -d; }
+                else if (own[q].w < sj.w) d = (int32_t)sj.y - (int32_t)own[q].z;
+                else if (sj.w < own[q].w) d = (int32_t)own[q].y - (int32_t)sj.z;
+                else continue;
+                if (d <= fragment_limit) adj_f[q] |= 1ull << j;
+                if (d <= read_limit && (i < H0) == j_first) adj_r[q] |= 1ull << j;
+            }
+        }
 #pragma unroll 1
-    for (uint32_t r = 0; r < 2; r++) {
-        DevSeed* sr = r ? s1 : s0; const uint32_t Hr = r ? H1 : H0;
-        uint32_t n_roots = 0;
-        for (uint32_t base = 0; base < Hr && !overflow; base += 32) {
-            const uint32_t i = base + lane;
-            const bool root = i < Hr && sr[i].label == i;
-            const uint32_t bal = __ballot_sync(FULL, root);
-            if (n_roots + __popc(bal) > sm.Cc) { overflow = 1; break; }
-            if (root) cs.side[r * sm.Cc + n_roots + __popc(bal & ((1u << lane) - 1u))] = sr[i].source >> 8;
-            n_roots += __popc(bal);
+        for (uint32_t level = 0; level < 2; level++) {
+            uint8_t* lab = level == 0 ? cs.lab_frag : cs.lab_read;
+            uint32_t mine[2];
+#pragma unroll
+            for (uint32_t q = 0; q < 2; q++) { mine[q] = lane + 32 * q; if (has[q]) lab[mine[q]] = (uint8_t)mine[q]; }
+            __syncwarp();
+            while (true) {
+                bool changed = false;
+#pragma unroll
+                for (uint32_t q = 0; q < 2; q++) {
+                    uint64_t m = level == 0 ? adj_f[q] : adj_r[q];
+                    uint32_t best = mine[q];
+                    while (m) { const int j = __ffsll((long long)m) - 1; m &= m - 1; best = min(best, (uint32_t)lab[j]); }
+                    if (best < mine[q]) { mine[q] = best; changed = true; }
+                }
+                __syncwarp();
+#pragma unroll
+                for (uint32_t q = 0; q < 2; q++) if (has[q]) lab[lane + 32 * q] = (uint8_t)mine[q];
+                __syncwarp();
+                if (!__any_sync(FULL, changed)) break;
+            }
+        }
+        // read-cluster labels back to the records (local index space of each read)
+        for (uint32_t i = lane; i < n_all; i += 32) {
+            if (i < H0) s0[i].label = cs.lab_read[i]; else s1[i - H0].label = (uint32_t)cs.lab_read[i] - H0;
         }
         __syncwarp();
-        for (uint32_t i = lane; i < Hr; i += 32) sr[i].source &= 0xffu;
-        __syncwarp();
-        if (!overflow) {
-            const uint32_t cn = collect_clusters(sm, cs, sr, Hr, r ? m1 : m0, r ? rs1.min_cnt : rs0.min_cnt, ix.k, r ? L1 : L0, r * sm.Cc);
-            if (cn == 0xffffffffu) overflow = 1;
-            else if (r) Cn[1] = cn; else Cn[0] = cn;
+#pragma unroll 1
+        for (uint32_t r = 0; r < 2; r++) {
+            const uint32_t Hr = r ? H1 : H0, g0 = r ? H0 : 0u;
+            uint32_t n_roots = 0;
+            for (uint32_t base = 0; base < Hr && !overflow; base += 32) {
+                const uint32_t i = base + lane;
+                const bool root = i < Hr && cs.lab_read[g0 + i] == g0 + i;
+                const uint32_t bal = __ballot_sync(FULL, root);
+                if (n_roots + __popc(bal) > sm.Cc) { overflow = 1; break; }
+                if (root) cs.side[r * sm.Cc + n_roots + __popc(bal & ((1u << lane) - 1u))] = cs.lab_frag[g0 + i];
+                n_roots += __popc(bal);
+            }
         }
+        __syncwarp();
+    } else {
+        // ---- large seed sets: label propagation over the records in HBM.
+        // pass 0: fragment components over both reads (labels = index in the concatenation), stashed in
+        // the upper bits of `source` (source < 128); passes 1, 2: the read clusters of each read.
+#pragma unroll 1
+        for (uint32_t pass = 0; pass < 3; pass++) {
+            DevSeed* sa = pass == 2 ? s1 : s0; const uint32_t na = pass == 2 ? H1 : H0;
+            const uint32_t nb = pass == 0 ? H1 : 0u;
+            for (uint32_t i = lane; i < na; i += 32) sa[i].label = i;
+            for (uint32_t i = lane; i < nb; i += 32) s1[i].label = na + i;
+            __syncwarp();
+            propagate_labels(sa, na, s1, nb, pass == 0 ? fragment_limit : read_limit);
+            if (pass == 0) {
+                for (uint32_t i = lane; i < H0; i += 32) s0[i].source |= s0[i].label << 8;
+                for (uint32_t i = lane; i < H1; i += 32) s1[i].source |= s1[i].label << 8;
+            }
+            __syncwarp();
+        }
+        // the fragment label of each read-cluster root goes to the side table, then `source` is restored
+#pragma unroll 1
+        for (uint32_t r = 0; r < 2; r++) {
+            DevSeed* sr = r ? s1 : s0; const uint32_t Hr = r ? H1 : H0;
+            uint32_t n_roots = 0;
+            for (uint32_t base = 0; base < Hr && !overflow; base += 32) {
+                const uint32_t i = base + lane;
+                const bool root = i < Hr && sr[i].label == i;
+                const uint32_t bal = __ballot_sync(FULL, root);
+                if (n_roots + __popc(bal) > sm.Cc) { overflow = 1; break; }
+                if (root) cs.side[r * sm.Cc + n_roots + __popc(bal & ((1u << lane) - 1u))] = sr[i].source >> 8;
+                n_roots += __popc(bal);
+            }
+            __syncwarp();
+            for (uint32_t i = lane; i < Hr; i += 32) sr[i].source &= 0xffu;
+            __syncwarp();
+        }
+    }
+#pragma unroll 1
+    for (uint32_t r = 0; r < 2 && !overflow; r++) {
+        const uint32_t cn = collect_clusters(sm, cs, r ? s1 : s0, r ? H1 : H0, r ? m1 : m0, r ? rs1.min_cnt : rs0.min_cnt, ix.k, r ? L1 : L0, r * sm.Cc);
+        if (cn == 0xffffffffu) overflow = 1;
+        else if (r) Cn[1] = cn; else Cn[0] = cn;
     }
     if (overflow) return table_full(sm.Cc, MAX_CLUSTERS);
     rs0.n_clusters = Cn[0]; rs1.n_clusters = Cn[1];
