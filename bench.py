@@ -227,9 +227,18 @@ def algorithmic_bytes_per_read(L, counters, n_reads_sample, mappings_per_read, e
     T = counters["tail_dps"] / n_reads_sample
     St = counters["tail_bases"] / max(counters["tail_dps"], 1)
     Nt = counters["tail_nodes"] / max(counters["tail_dps"], 1)
+    per_kernel = {
+        # the seeding kernel reads the bases, one 16-B table cell per minimizer and one 24-B hit per seed
+        "seed_kernel_pe": L + 16 * M + 24 * Hh,
+        # per gapless extension: L graph bases and 16 B per node record (+1 node)
+        "extend_kernel": X * (L + 16 * -(-L // 32) + 16),
+        # align stage: qualities (MAPQ cap), tail subgraphs, the output record
+        "align_kernel_pe": L + T * (St + 16 * Nt) + 32 + 8 * mappings_per_read + 4 * edits_per_read,
+        "compact": 0.0,
+    }
     B = 2 * L + 16 * M + 24 * Hh + X * (L + 16 * -(-L // 32) + 16) + T * (St + 16 * Nt) + 32 + 8 * mappings_per_read + 4 * edits_per_read
     return B, {"M": round(M, 2), "H": round(Hh, 2), "X": round(X, 3), "T": round(T, 4), "S_t": round(St, 1), "N_t": round(Nt, 1),
-               "P": round(mappings_per_read, 2), "E": round(edits_per_read, 2)}
+               "P": round(mappings_per_read, 2), "E": round(edits_per_read, 2)}, per_kernel
 
 
 # ---------------------------------------------------------------------------------------
@@ -316,7 +325,7 @@ def main():
     d_maps = torch.zeros((n_reads * MAP_PER, 8), dtype=torch.uint8, device=device)
     d_edits = torch.zeros((n_reads * EDIT_PER,), dtype=torch.int32, device=device)
     d_status = torch.zeros((n_reads,), dtype=torch.uint8, device=device)
-    CHUNK = 1 << 20
+    CHUNK = 1_000_000 if n_reads % 1_000_000 == 0 else 1 << 20     # equal launches, so the last chunk's stage timers are typical
     n_chunks = (n_reads + CHUNK - 1) // CHUNK
     d_totals = torch.zeros((n_chunks, 2), dtype=torch.int64, device=device)
 
@@ -444,7 +453,7 @@ def main():
     check_n = len(check_idx)
     bad = H.compare_alignments(got, cpu_res, cpu_sample, indices=check_idx)
 
-    B, terms = algorithmic_bytes_per_read(READ_LEN, counters, cpu_sample, maps_per_read, edits_per_read)
+    B, terms, per_kernel = algorithmic_bytes_per_read(READ_LEN, counters, cpu_sample, maps_per_read, edits_per_read)
     peaks = {}
     try:
         peaks = json.loads((ROOT / "MEASURED_PEAKS.json").read_text())
@@ -456,11 +465,15 @@ def main():
     dom = int(np.argmax(last_stage))
     chunk_reads = min(CHUNK, n_reads) if n_reads % CHUNK == 0 or n_reads < CHUNK else n_reads - (n_chunks - 1) * CHUNK
     dom_ms = float(last_stage[dom])
-    achieved = B * chunk_reads / (dom_ms / 1e3) / 1e9 if dom_ms > 0 else None
+    # the dominant kernel's share of B(read) (its terms sum to B over the three kernels), times the reads of one launch
+    B_dom = float(per_kernel[names[dom]])
+    achieved = B_dom * chunk_reads / (dom_ms / 1e3) / 1e9 if dom_ms > 0 else None
     traffic = None
     try:
         prof = json.loads((ROOT / "profiles" / "ncu_summary_r01.json").read_text())
-        traffic = prof.get(names[dom], {}).get("dram_bytes_per_launch")
+        full = prof["kernels"][names[dom]]["ncu_full"]
+        # dram__bytes_read.sum + dram__bytes_write.sum of one launch under ncu --set full, scaled to this launch's reads
+        traffic = float(full["dram_bytes_per_launch"]) * chunk_reads / float(prof["reads_per_call"])
     except Exception:
         pass
 
@@ -484,7 +497,9 @@ def main():
                 "ms_per_step": e2e_ms},
         "roofline": {"bound": "hbm", "kernel": names[dom], "achieved": achieved, "peak": peak, "unit": "GB/s",
                      "frac": (achieved / peak) if achieved else None, "traffic": traffic,
-                     "algorithmic_bytes_per_read": B, "terms": terms, "reads_per_launch": chunk_reads,
+                     "algorithmic_bytes_per_read": B, "algorithmic_bytes_per_read_this_kernel": B_dom,
+                     "per_kernel_bytes_per_read": {k: round(float(v), 1) for k, v in per_kernel.items()},
+                     "terms": terms, "reads_per_launch": chunk_reads,
                      "launch_ms": dom_ms, "peak_source": peak_src,
                      "stage_ms_last_chunk": {n: float(x) for n, x in zip(names, last_stage)}},
         "cpu_baseline": {"value": cpu_rate, "unit": "reads/s", "cores": threads, "kind": "port",
