@@ -262,6 +262,101 @@ __device__ inline bool fast_pair(const DevIndex& ix, const MapParamsDev& P, cons
     return done;
 }
 
+// Single-end twin of fast_pair: one thread per read (minimizer_mapper.cpp:886-1188 restricted to
+// full-length extension sets).  Returns false when the read must go to the warp-per-read kernel.
+__device__ inline bool fast_read(const DevIndex& ix, const MapParamsDev& P, const DevScores& sc, const MapBatch& b, const AlignArgs& a, uint32_t r) {
+    const ReadState rs = b.states[r];
+    if (rs.status != GB_ITEM_OK) return false;
+    DevRng rng = rs.rng;
+    const uint64_t rb = b.read_off[r];
+    const uint32_t L = (uint32_t)(b.read_off[r + 1] - rb);
+    const uint8_t* read = b.reads + rb; const uint8_t* qual = b.quals ? b.quals + rb : nullptr;
+    FastCand cand[FAST_MAX_CANDS]; uint32_t n_cand = 0;
+    uint32_t explored[PRESENT_WORDS];
+#pragma unroll
+    for (uint32_t x = 0; x < PRESENT_WORDS; x++) explored[x] = 0;
+    const uint32_t S = rs.item_cnt;
+    if (S > FAST_MAX_SETS) return false;
+    int set_score[FAST_MAX_SETS]; uint8_t set_order[FAST_MAX_SETS];
+    for (uint32_t s = 0; s < S; s++) {
+        const uint32_t item = rs.item_off + s;
+        if (a.ev.ext_status[item] != GB_ITEM_OK) return false;
+        const gb_extension* ext = a.ev.ext + (size_t)item * a.ev.max_ext;
+        const uint32_t n_ext = a.ev.ext_count[item];
+        if (n_ext > 0 && ext_full(ext[0]) && ext[0].mismatches <= 4) set_score[s] = ext[0].score;
+        else set_score[s] = score_extension_group(ext, n_ext, L, sc.gap_open, sc.gap_extend);
+    }
+    for (uint32_t s = 0; s < S; s++) { uint32_t j = s; while (j > 0 && set_score[s] > set_score[set_order[j - 1]]) { set_order[j] = set_order[j - 1]; j--; } set_order[j] = (uint8_t)s; }
+    {
+        uint32_t ties = 0;
+        while (ties < S && !(set_score[set_order[0]] > set_score[set_order[ties]])) ties++;
+        for (uint32_t i = 1; i < ties; i++) { const uint32_t j = rng_next(rng) % (i + 1); const uint8_t t = set_order[j]; set_order[j] = set_order[i]; set_order[i] = t; }
+    }
+    const double set_cutoff = S == 0 ? 0.0 : (double)set_score[set_order[0]] - P.extension_set_score_threshold;
+    uint32_t unskipped = 0;
+    for (uint32_t oi = 0; oi < S; oi++) {
+        const uint32_t s = set_order[oi];
+        bool process;
+        if (P.extension_set_score_threshold != 0 && (double)set_score[s] <= set_cutoff) process = unskipped < (uint32_t)P.min_extension_sets;
+        else process = unskipped < P.max_alignments;
+        if (!process) continue;
+        if (set_score[s] < P.extension_set_min_score) continue;                    // :912-916
+        unskipped++;
+        const uint32_t item = rs.item_off + s;
+        const gb_extension* ext = a.ev.ext + (size_t)item * a.ev.max_ext;
+        const uint32_t n_ext = a.ev.ext_count[item];
+        if (!(n_ext > 0 && ext_full(ext[0]) && ext[0].mismatches <= 4)) return false;     // tail alignment needed
+        const DevItem it = a.items[item];
+        const int32_t best0 = ext[0].score;
+        bool keep = true;
+        for (uint32_t j = 0; j < n_ext && (j == 0 || ext_full(ext[j])); j++) {
+            if (keep && ext[j].score != 0 && (double)ext[j].score >= (double)best0 * 0.8) {
+                if (n_cand >= FAST_MAX_CANDS) return false;
+                cand[n_cand++] = FastCand{ext[j].score, item, (uint8_t)j, 0, 0};
+            } else keep = false;
+        }
+#pragma unroll
+        for (uint32_t x = 0; x < PRESENT_WORDS; x++) explored[x] |= it.present[x];
+    }
+    // winner (process_until_threshold_a, :1095), MAPQ (:1146-1188)
+    double scores_sorted[FAST_MAX_CANDS + 1]; uint32_t n_scores = 0; int win = -1;
+    if (n_cand == 0) { scores_sorted[0] = 0.0; n_scores = 1; }
+    else {
+        uint8_t co[FAST_MAX_CANDS];
+        for (uint32_t c = 0; c < n_cand; c++) { uint32_t j = c; while (j > 0 && cand[c].score > cand[co[j - 1]].score) { co[j] = co[j - 1]; j--; } co[j] = (uint8_t)c; }
+        uint32_t ties = 0;
+        while (ties < n_cand && !(cand[co[0]].score > cand[co[ties]].score)) ties++;
+        for (uint32_t i = 1; i < ties; i++) { const uint32_t j = rng_next(rng) % (i + 1); const uint8_t t = co[j]; co[j] = co[i]; co[i] = t; }
+        for (uint32_t c = 0; c < n_cand; c++) scores_sorted[c] = (double)cand[co[c]].score;
+        n_scores = n_cand; win = co[0];
+    }
+    double mapq = win >= 0 ? max_mapping_quality(scores_sorted, n_scores, P.log_base) : 0.0;
+    const double escape_bonus = mapq < 2147483647.0 ? 1.0 : 2.0;
+    uint32_t n_exp = 0;
+#pragma unroll
+    for (uint32_t x = 0; x < PRESENT_WORDS; x++) n_exp += __popc(explored[x]);
+    if (n_exp > FAST_MAX_EXPLORED) return false;
+    uint64_t mp[FAST_MAX_EXPLORED]; double cbuf[FAST_MAX_EXPLORED + 1];
+    const double cap = escape_bonus * faster_cap(P, a.minimizers + rs.min_off, ix.k, explored, rs.min_cnt, qual, L, mp, cbuf);
+    const double mapq_uncapped = mapq;
+    mapq = round(fmin(cap, fmin(mapq, 60.0)));
+    mapq = fmax(fmin(mapq, 60.0), 0.0);
+    gb_alignment out;
+    out.read_id = r; out.score = 0; out.mapq = (uint8_t)mapq; out.flags = 0; out.n_mappings = 0; out.n_edits = 0;
+    out.mapping_off = r * P.mapping_cap; out.edit_off = r * P.edit_cap;
+    out.mapq_uncapped = (float)mapq_uncapped; out.mapq_explored_cap = (float)cap;
+    if (win >= 0) {
+        const FastCand& c = cand[win];
+        uint32_t nm = 0, ne = 0;
+        if (!extension_to_output(ix, a.ev.ext[(size_t)c.item * a.ev.max_ext + c.ext_j], a.ev.path_pool + (size_t)c.item * a.ev.path_cap,
+                                 a.ev.mism_pool + (size_t)c.item * a.ev.mism_cap, read, L, false,
+                                 a.maps + (size_t)r * P.mapping_cap, a.edits + (size_t)r * P.edit_cap, P.mapping_cap, P.edit_cap, nm, ne)) return false;
+        out.score = c.score; out.flags = nm ? GB_ALN_MAPPED : 0; out.n_mappings = (uint16_t)nm; out.n_edits = ne;
+    }
+    a.aln[r] = out; a.status[r] = GB_ITEM_OK;
+    return true;
+}
+
 struct FastArgs { uint32_t* slow_list; uint32_t* slow_count; };
 
 __global__ void __launch_bounds__(128)
@@ -271,6 +366,16 @@ align_fast_kernel_pe(DevIndex ix, MapParamsDev P, DevScores sc, MapBatch b, Alig
         if (!fast_pair(ix, P, sc, b, a, p)) {
             const uint32_t slot = atomicAdd(fa.slow_count, 1u);
             fa.slow_list[slot] = p;
+        }
+    }
+}
+
+__global__ void __launch_bounds__(128)
+align_fast_kernel(DevIndex ix, MapParamsDev P, DevScores sc, MapBatch b, AlignArgs a, FastArgs fa) {
+    for (uint32_t r = blockIdx.x * blockDim.x + threadIdx.x; r < b.n_reads; r += gridDim.x * blockDim.x) {
+        if (!fast_read(ix, P, sc, b, a, r)) {
+            const uint32_t slot = atomicAdd(fa.slow_count, 1u);
+            fa.slow_list[slot] = r;
         }
     }
 }

@@ -106,7 +106,10 @@ align_kernel(DevIndex ix, MapParamsDev P, DevScores sc, MapBatch b, AlignArgs a)
 
     while (true) {
         uint32_t r = 0;
-        if (lane == 0) r = atomicAdd(b.work_counter, 1u);
+        if (lane == 0) {
+            r = atomicAdd(b.work_counter, 1u);
+            if (a.slow_list) r = r < *a.slow_count ? a.slow_list[r] : 0xffffffffu;
+        }
         r = __shfl_sync(FULL, r, 0);
         if (r >= b.n_reads) break;
         const uint64_t rb = b.read_off[r];
@@ -331,19 +334,18 @@ int map_device(gb_device* d, const gb_map_params* hp, uint32_t n_reads, const ui
         a.aln = d_aln; a.maps = d_maps; a.edits = d_edits; a.status = d_status; a.tb_cells = tb_cells;
         a.pairs = paired ? d->p_pairs.ptr : nullptr; a.frag_mean = hp->fragment_mean; a.frag_sd = hp->fragment_stdev;
         MapBatch b3 = b; b3.work_counter = cur + 6;
+        // thread-per-unit fast path first; whatever it cannot finish goes to the warp-per-unit kernel
+        const uint32_t n_units = paired ? n_reads / 2 : n_reads;
+        if ((rc = d->p_slow.reserve(n_units + 1))) return rc;
+        FastArgs fa; fa.slow_list = d->p_slow.ptr; fa.slow_count = cur + 7;
+        const uint32_t fgrid = std::max<uint32_t>(1u, std::min<uint32_t>((n_units + 127) / 128, (uint32_t)d->n_sms * 16));
         a.slow_list = nullptr; a.slow_count = nullptr;
-        if (paired) {
-            // thread-per-pair fast path first; whatever it cannot finish goes to the warp-per-pair kernel
-            if ((rc = d->p_slow.reserve(n_reads / 2 + 1))) return rc;
-            FastArgs fa; fa.slow_list = d->p_slow.ptr; fa.slow_count = cur + 7;
-            const uint32_t n_pairs = n_reads / 2;
-            const uint32_t fgrid = std::max<uint32_t>(1u, std::min<uint32_t>((n_pairs + 127) / 128, (uint32_t)d->n_sms * 16));
-            align_fast_kernel_pe<<<fgrid, 128, 0, d->stream>>>(d->ix, P, d->sc, b3, a, fa);
-            d->launches++;
-            GB_CUDA(cudaGetLastError());
-            a.slow_list = d->p_slow.ptr; a.slow_count = cur + 7;
-            align_kernel_pe<<<grid, ALIGN_WARPS * 32, smem, d->stream>>>(d->ix, P, d->sc, b3, a);
-        }
+        if (paired) align_fast_kernel_pe<<<fgrid, 128, 0, d->stream>>>(d->ix, P, d->sc, b3, a, fa);
+        else align_fast_kernel<<<fgrid, 128, 0, d->stream>>>(d->ix, P, d->sc, b3, a, fa);
+        d->launches++;
+        GB_CUDA(cudaGetLastError());
+        a.slow_list = d->p_slow.ptr; a.slow_count = cur + 7;
+        if (paired) align_kernel_pe<<<grid, ALIGN_WARPS * 32, smem, d->stream>>>(d->ix, P, d->sc, b3, a);
         else align_kernel<<<grid, ALIGN_WARPS * 32, smem, d->stream>>>(d->ix, P, d->sc, b3, a);
         d->launches++;
         GB_CUDA(cudaGetLastError());
