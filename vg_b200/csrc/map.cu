@@ -89,7 +89,7 @@ seed_kernel(DevIndex ix, MapParamsDev P, MapBatch b, SeedPools pools) {
 // ---------------------------------------------------------------------------------------
 #include "align_read.cuh"
 
-__global__ void __launch_bounds__(ALIGN_WARPS * 32)
+__global__ void __launch_bounds__(ALIGN_WARPS * 32, 4)
 align_kernel(DevIndex ix, MapParamsDev P, DevScores sc, MapBatch b, AlignArgs a) {
     extern __shared__ __align__(16) uint8_t smem[];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -317,7 +317,7 @@ int map_device(gb_device* d, const gb_map_params* hp, uint32_t n_reads, const ui
         if (paired) GB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bps, align_kernel_pe, ALIGN_WARPS * 32, smem));
         else GB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bps, align_kernel, ALIGN_WARPS * 32, smem));
         if (bps < 1) bps = 1;
-        if (bps > 2) bps = 2;
+        if (bps > 4) bps = 4;          // bounds the per-warp tail workspaces (about 2 MB each)
         uint32_t grid = std::min<uint32_t>((uint32_t)(d->n_sms * bps), (n_reads + ALIGN_WARPS - 1) / ALIGN_WARPS);
         if (grid == 0) grid = 1;
         const size_t n_warps = (size_t)grid * ALIGN_WARPS;
@@ -512,7 +512,7 @@ struct XdropBatch {
     uint32_t* work_counter;
 };
 
-__global__ void __launch_bounds__(ALIGN_WARPS * 32)
+__global__ void __launch_bounds__(ALIGN_WARPS * 32, 4)
 xdrop_kernel(DevIndex ix, DevScores sc, XdropBatch b) {
     extern __shared__ __align__(16) uint8_t smem[];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;

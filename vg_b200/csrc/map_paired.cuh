@@ -99,7 +99,7 @@ seed_kernel_pe(DevIndex ix, MapParamsDev P, MapBatch b, SeedPools pools, PairBat
     }
 }
 
-__global__ void __launch_bounds__(ALIGN_WARPS * 32)
+__global__ void __launch_bounds__(ALIGN_WARPS * 32, 4)
 align_kernel_pe(DevIndex ix, MapParamsDev P, DevScores sc, MapBatch b, AlignArgs a) {
     extern __shared__ __align__(16) uint8_t smem[];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;

@@ -31,7 +31,8 @@ struct TreeNode {
     uint32_t depth;
     uint32_t tb_col;       // first traceback column of this node
     int32_t lineage_max;
-    uint32_t computed;
+    uint16_t computed;
+    uint8_t band_lo, band_hi;   // live 32-cell chunks [lo, hi) of the node's last DP column
 };
 
 struct DfsFrame { uint32_t node; int32_t lo, hi; uint32_t used; uint32_t visit; };
@@ -190,42 +191,52 @@ __device__ inline int32_t xdrop_tree(const DevIndex& ix, const DevScores& sc, co
 
     int32_t best = 0; uint32_t best_node = 0, best_col = 0, best_j = 0; bool have_best = false;
     uint32_t tb_cols = 0;
+    const uint32_t n_chunks = (W + 31) >> 5;
     for (uint32_t i = t0; i < t1; i++) {
         TreeNode tn = ws.tree[i];
         int32_t run_max;
-        // previous column -> Hp/Ep
+        // Cells outside the live chunk range [plo, phi) of the previous column are dead by definition
+        // and are never read; the X-drop keeps that range a narrow band around the best diagonal.
+        uint32_t plo, phi;
         if (tn.parent < 0) {
             for (uint32_t j = lane; j < W; j += 32) {
                 int32_t h = DP_NEG;
                 if (j == 0) h = 0; else if (j <= max_gap) h = -(go + (int32_t)(j - 1) * ge);
                 dps.Hp[j] = h; dps.Ep[j] = DP_NEG;
             }
+            plo = 0; phi = min(n_chunks, (min(max_gap, m) >> 5) + 1);
             run_max = 0;
         } else {
             const TreeNode par = ws.tree[tn.parent];
-            if (!par.computed) { continue; }
-            bool live = false;
+            if (!par.computed || par.band_lo >= par.band_hi) { continue; }
+            plo = par.band_lo; phi = par.band_hi;
             const int32_t* cH = ws.colH + (size_t)par.depth * (ws.Lc + 1);
             const int32_t* cE = ws.colE + (size_t)par.depth * (ws.Lc + 1);
-            for (uint32_t j = lane; j < W; j += 32) { const int32_t h = cH[j]; dps.Hp[j] = h; dps.Ep[j] = cE[j]; live |= h > DP_NEG; }
-            if (!__any_sync(FULL, live)) { continue; }
+            for (uint32_t j = plo * 32 + lane; j < min(W, phi * 32); j += 32) { dps.Hp[j] = cH[j]; dps.Ep[j] = cE[j]; }
             run_max = par.lineage_max;
         }
         __syncwarp();
         if ((uint64_t)(tb_cols + tn.len) * W > ws.tb_cells) { overflow = true; return 0; }
         tn.tb_col = tb_cols; tn.computed = 1;
-        int32_t node_best = DP_NEG; uint32_t node_col = 0, node_j = 0;
-        for (uint32_t c = 0; c < tn.len; c++) {
+        // this lane's best cell of the node: first column, then smallest j, on ties (strict > below)
+        int32_t lane_best = DP_NEG; uint32_t lane_col = 0, lane_j = 0;
+        for (uint32_t c = 0; c < tn.len && plo < phi; c++) {
             const uint8_t r = __ldg(ix.seq + tn.seq_off + c);
             uint8_t* tbcol = ws.tb + (size_t)(tb_cols + c) * W;
             int32_t carry = INT_MIN;          // running max of (H'[i] + i*ge) over i < chunk start
             int32_t prevH_last = DP_NEG;      // H of the last cell of the previous chunk (for f_open)
-            int32_t col_best = DP_NEG; uint32_t col_best_j = 0;
-            for (uint32_t jb = 0; jb < W; jb += 32) {
-                const uint32_t j = jb + lane;
+            int32_t prev_ph_last = DP_NEG;    // previous column's H of the last cell of the previous chunk (diagonal)
+            int32_t col_max = DP_NEG;
+            uint32_t clo = n_chunks, chi = 0;
+            for (uint32_t ch = plo; ch < n_chunks; ch++) {
+                const uint32_t j = ch * 32 + lane;
                 const bool in = j < W;
-                int32_t ph = DP_NEG, pe = DP_NEG, phm1 = DP_NEG;
-                if (in) { ph = dps.Hp[j]; pe = dps.Ep[j]; if (j > 0) phm1 = dps.Hp[j - 1]; }
+                const bool pin = in && ch < phi;                  // previous column has this chunk
+                int32_t ph = DP_NEG, pe = DP_NEG;
+                if (pin) { ph = dps.Hp[j]; pe = dps.Ep[j]; }
+                int32_t phm1 = __shfl_up_sync(FULL, ph, 1);
+                if (lane == 0) phm1 = prev_ph_last;
+                prev_ph_last = __shfl_sync(FULL, ph, 31);
                 int32_t e = DP_NEG;
                 if (ph > DP_NEG) e = ph - go;
                 if (pe > DP_NEG) e = max(e, pe - ge);
@@ -262,28 +273,37 @@ __device__ inline int32_t xdrop_tree(const DevIndex& ix, const DevScores& sc, co
                 // X-drop against the best of the earlier columns
                 if (in && h > DP_NEG && h < run_max - xt) { h = DP_NEG; e = DP_NEG; }
                 if (in) { dps.Hc[j] = h; dps.Ec[j] = e; tbcol[j] = tbv; }
-                // column maximum, smallest j on ties
-                int32_t bh = in ? h : DP_NEG; uint32_t bj = j;
-#pragma unroll
-                for (int o = 16; o > 0; o >>= 1) {
-                    const int32_t oh = __shfl_xor_sync(FULL, bh, o); const uint32_t oj = __shfl_xor_sync(FULL, bj, o);
-                    if (oh > bh || (oh == bh && oj < bj)) { bh = oh; bj = oj; }
+                const bool alive = in && h > DP_NEG;
+                if (alive) {
+                    col_max = max(col_max, h);
+                    if (h > lane_best) { lane_best = h; lane_col = c; lane_j = j; }
                 }
-                if (bh > col_best) { col_best = bh; col_best_j = bj; }
+                if (__any_sync(FULL, alive || (in && e > DP_NEG))) { clo = min(clo, ch); chi = ch + 1; }
+                else if (ch >= phi) break;                // past the previous band (+1 chunk for the diagonal) and the insertion chain died
             }
             __syncwarp();
-            if (col_best > node_best) { node_best = col_best; node_col = c; node_j = col_best_j; }
-            if (col_best > run_max) run_max = col_best;
+            col_max = __reduce_max_sync(FULL, col_max);
+            if (col_max > run_max) run_max = col_max;
             // swap columns
             int32_t* t1p = dps.Hp; dps.Hp = dps.Hc; dps.Hc = t1p;
             int32_t* t2p = dps.Ep; dps.Ep = dps.Ec; dps.Ec = t2p;
+            plo = clo; phi = chi;
         }
-        // keep this node's last column for its children
-        {
+        // node maximum across lanes: highest score, then first column, then smallest query offset
+        int32_t node_best = lane_best; uint32_t node_col = lane_col, node_j = lane_j;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            const int32_t oh = __shfl_xor_sync(FULL, node_best, o);
+            const uint32_t oc = __shfl_xor_sync(FULL, node_col, o), oj = __shfl_xor_sync(FULL, node_j, o);
+            if (oh > node_best || (oh == node_best && (oc < node_col || (oc == node_col && oj < node_j)))) { node_best = oh; node_col = oc; node_j = oj; }
+        }
+        // keep this node's last column (its live band) for its children
+        if (plo < phi) {
             int32_t* cH = ws.colH + (size_t)tn.depth * (ws.Lc + 1);
             int32_t* cE = ws.colE + (size_t)tn.depth * (ws.Lc + 1);
-            for (uint32_t j = lane; j < W; j += 32) { cH[j] = dps.Hp[j]; cE[j] = dps.Ep[j]; }
+            for (uint32_t j = plo * 32 + lane; j < min(W, phi * 32); j += 32) { cH[j] = dps.Hp[j]; cE[j] = dps.Ep[j]; }
         }
+        tn.band_lo = (uint8_t)min(plo, 255u); tn.band_hi = (uint8_t)(plo < phi ? phi : min(plo, 255u));
         tn.lineage_max = run_max;
         if (lane == 0) ws.tree[i] = tn;
         tb_cols += tn.len;
