@@ -103,3 +103,37 @@ def test_map_paired_parity_across_host_chunks(monkeypatch):
     g = synth.make_variant_graph(length=100000, n_snp=160, n_ins=20, n_del=20, n_haps=8, seed=5)
     rs = synth.simulate_pairs(g, 1100, sub_rate=0.02, seed=53)
     _run(g, rs, H.paired_params())
+
+
+@pytest.mark.gpu
+def test_map_paired_edge_cases():
+    """Ragged pair lengths, mates without minimizers, N runs, an empty read, identical mates."""
+    g = synth.make_variant_graph(length=50000, n_snp=80, n_ins=10, n_del=10, n_haps=4, seed=3)
+    index = g.build_index()
+    dev = capi.Device(index)
+    hs = g.hap_seq[0]
+    rc = lambda a: bytes(synth.revcomp_bytes(np.frombuffer(a, dtype=np.uint8)))
+    f = lambda a, b: bytes(hs[a:b])
+    pairs = [
+        (f(1000, 1150), rc(f(1250, 1400))),                     # proper pair
+        (f(2000, 2100), rc(f(2300, 2420))),                     # ragged lengths
+        (f(3000, 3150), b"ACGT"),                               # mate 2 too short for a minimizer
+        (b"N" * 150, rc(f(4200, 4350))),                        # mate 1 all N
+        (f(5000, 5150).replace(b"A", b"N", 4), rc(f(5300, 5450)).replace(b"C", b"N", 2)),
+        (f(6000, 6150), rc(f(26000, 26150))),                   # far apart: no shared fragment cluster
+        (f(7000, 7150), f(7000, 7150)),                         # same strand, same place
+        (b"", rc(f(8200, 8350))),                               # empty mate
+        (f(9000, 9039), rc(f(9100, 9139))),                     # exactly k + w - 1 bases
+    ]
+    reads = [r for p in pairs for r in p]
+    quals = [bytes([30] * len(r)) for r in reads]
+    params = H.paired_params()
+    got = H.gpu_map(dev, reads, quals, params, paired=True)
+    want = H.oracle_map_paired(index, reads, quals, params)
+    bad = H.compare_alignments(got, want, len(reads))
+    assert not bad, bad[0]
+    got = H.gpu_map(dev, reads, None, params, paired=True)
+    want = H.oracle_map_paired(index, reads, None, params)
+    bad = H.compare_alignments(got, want, len(reads))
+    assert not bad, bad[0]
+    dev.close()

@@ -112,3 +112,14 @@ def test_map_parity_with_read_coverage_filter_active():
     p.num_bp_per_min = 50
     p.minimizer_coverage_flank = 10
     _run(g, rs, p)
+
+
+@pytest.mark.gpu
+def test_map_parity_tail_alignment_with_non_acgt_bases():
+    """N bases inside aligned tails: they never match (DP query staging masks them)."""
+    g = synth.make_variant_graph(length=100000, n_snp=160, n_ins=20, n_del=20, n_haps=8, seed=21)
+    rs = synth.simulate_reads(g, 1200, length=200, sub_rate=0.02, ins_rate=0.01, del_rate=0.01, seed=56)
+    rng = np.random.default_rng(4)
+    for i in rng.integers(0, rs.n, size=600):
+        rs.reads[i, rng.integers(0, rs.length, size=3)] = ord("N")
+    _run(g, rs)

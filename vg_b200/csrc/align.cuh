@@ -202,7 +202,7 @@ __device__ inline int32_t align_tail(const DevIndex& ix, const MapParamsDev& P, 
     const uint32_t gap = longest_detectable_gap(sc, L, tail_length);
     // query: the tail itself (right tail) or its reverse complement (left tail)
     for (uint32_t i = lane; i < tail_length; i += 32)
-        qbuf[i] = left_tail ? comp_base(read[tail_length - 1 - i]) : read[e.read_hi + i];
+        qbuf[i] = dp_query_base(left_tail ? comp_base(read[tail_length - 1 - i]) : read[e.read_hi + i]);
     __syncwarp();
 
     // default: pure softclip on the node we are going to

@@ -536,7 +536,7 @@ xdrop_kernel(DevIndex ix, DevScores sc, XdropBatch b) {
         out.map_cap = b.map_cap; out.edit_cap = b.edit_cap; pb_reset(out);
         if (nt == 0 || nt > TAIL_T_CAP || m > b.Lc) status = GB_ITEM_OUT_FULL;
         else {
-            for (uint32_t i = lane; i < m; i += 32) q[i] = b.query[q_begin + i];
+            for (uint32_t i = lane; i < m; i += 32) q[i] = dp_query_base(b.query[q_begin + i]);
             // materialise the tree (depths from parents)
             if (lane == 0) {
                 for (uint32_t i = 0; i < nt; i++) {

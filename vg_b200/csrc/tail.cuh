@@ -95,6 +95,9 @@ __device__ __forceinline__ uint32_t edit_word(uint32_t op, uint32_t len, uint32_
 __device__ __forceinline__ uint32_t base2(uint8_t c) { return c == 'C' ? 1u : (c == 'G' ? 2u : (c == 'T' ? 3u : 0u)); }
 __device__ __forceinline__ uint8_t comp_base(uint8_t c) { return c == 'A' ? 'T' : (c == 'C' ? 'G' : (c == 'G' ? 'C' : (c == 'T' ? 'A' : 'N'))); }
 __device__ __forceinline__ bool is_acgt(uint8_t c) { return c == 'A' || c == 'C' || c == 'G' || c == 'T'; }
+// DP queries are staged with every non-ACGT byte replaced by 0, which equals no graph base: the
+// "non-ACGT never matches" rule then costs nothing in the inner loop.
+__device__ __forceinline__ uint8_t dp_query_base(uint8_t c) { return is_acgt(c) ? c : (uint8_t)0; }
 
 // EditAlignmentScorer::longest_detectable_gap(read_length, read_pos), alignment_scorer.cpp:264-271
 __device__ __forceinline__ uint32_t longest_detectable_gap(const DevScores& s, uint32_t read_length, uint32_t read_pos) {
@@ -243,7 +246,7 @@ __device__ inline int32_t xdrop_tree(const DevIndex& ix, const DevScores& sc, co
                 int32_t d = DP_NEG;
                 if (in && j > 0 && phm1 > DP_NEG) {
                     const uint8_t qc = q[j - 1];
-                    int32_t s = (qc == r && is_acgt(qc)) ? sc.match : -sc.mismatch;
+                    int32_t s = (qc == r) ? sc.match : -sc.mismatch;
                     if (j == m) s += sc.full_length_bonus;
                     d = phm1 + s;
                 }
@@ -345,7 +348,7 @@ __device__ inline int32_t xdrop_tree(const DevIndex& ix, const DevScores& sc, co
                 if (src == 0) {
                     if (j == 0) { overflow = true; return 0; }          // corrupt traceback: refuse, never walk off the matrix
                     const uint8_t qc = q[j - 1], r = __ldg(ix.seq + tn.seq_off + col);
-                    if (lane == 0) ws.steps[n_steps] = (node << 8) | ((qc == r && is_acgt(qc)) ? 0u : 1u);
+                    if (lane == 0) ws.steps[n_steps] = (node << 8) | ((qc == r) ? 0u : 1u);
                     n_steps++;
                     j--; node = pnode; col = pcol; at_virtual = p_virtual;
                     if (at_virtual && j == 0) break;
