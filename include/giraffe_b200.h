@@ -339,6 +339,26 @@ int gb_xdrop_pinned_batch(gb_device* dev, uint32_t n,
                           int32_t* score, gb_mapping* maps, uint32_t* edits, uint32_t* n_maps, uint32_t* n_edits,
                           uint8_t* status);
 
+/* ------------------------------------------------------------------------------------
+ * B3: Aligner::align(alignment, graph, topological_order) — the full (unbanded) local alignment
+ * vg runs through GSSW                        aligner.hpp:180, aligner.cpp:571-626, :344-564
+ * (rescue fallback fix_dozeu_score minimizer_mapper.cpp:3502-3517; --rescue-algorithm gssw :3390).
+ * Problem i: oriented nodes node[node_off[i] .. node_off[i+1]) in topological order; the
+ * predecessors of the problem's u-th node are pred[pred_off[g] .. pred_off[g+1]) with
+ * g = node_off[i] + u, each an index < u into the same problem (graph edges restricted to the
+ * subgraph, at most 255 per node); query i = query[query_off[i] .. query_off[i+1]).
+ * Scoring: gb_set_scores; a pair with a non-ACGT base on either side scores 0; the full-length
+ * bonus is granted at each read end that is aligned rather than soft clipped.
+ * Outputs per problem: score (0 and no mappings when nothing scores > 0), mappings
+ * (node = index into the problem's node list), edits (soft clips are insertions on the first /
+ * last mapping), counts, status.
+ * ---------------------------------------------------------------------------------- */
+int gb_sw_batch(gb_device* dev, uint32_t n,
+                const uint32_t* node, const uint64_t* node_off, const uint32_t* pred, const uint64_t* pred_off,
+                const uint8_t* query, const uint64_t* query_off, uint32_t map_cap, uint32_t edit_cap,
+                int32_t* score, gb_mapping* maps, uint32_t* edits, uint32_t* n_maps, uint32_t* n_edits,
+                uint8_t* status);
+
 /* Kernel-only timing of the last gb_*_batch call on this handle, milliseconds
  * (CUDA events on the handle's stream around the kernels, copies excluded). */
 float gb_last_kernel_ms(const gb_device* dev);

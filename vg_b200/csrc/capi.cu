@@ -139,6 +139,8 @@ extern "C" int gb_device_create(const gb_flat_index* ix, int device_ordinal, gb_
     if ((rc = d->table.upload(ix->table, ix->table_cells, d->stream))) return rc;
     if ((rc = d->hits.upload(ix->hits, ix->n_hits ? ix->n_hits : 1, d->stream, ix->n_hits))) return rc;
     GB_CUDA(cudaStreamSynchronize(d->stream));
+    d->h_node_len.resize(ix->n_nodes);
+    for (uint32_t v = 0; v < ix->n_nodes; v++) d->h_node_len[v] = ix->nodes[v].len;
     d->ix.nodes = d->nodes.ptr; d->ix.seq = d->seq.ptr; d->ix.gbwt = d->gbwt.ptr; d->ix.dist = d->dist.ptr;
     d->ix.table = d->table.ptr; d->ix.hits = d->hits.ptr;
     d->ix.table_mask = ix->table_cells - 1; d->ix.n_nodes = ix->n_nodes; d->ix.k = ix->k; d->ix.w = ix->w;

@@ -7,6 +7,7 @@
 
 #include <cuda_runtime.h>
 #include <string>
+#include <vector>
 
 namespace gb {
 
@@ -60,6 +61,7 @@ struct DevBuf {
 struct gb_device {
     int device = 0;
     int n_sms = 0;
+    std::vector<uint32_t> h_node_len;      // host copy of the node lengths (workspace sizing of the DP seams)
     // first-pass seeding table sizes (minimizers, clusters per read); GIRAFFE_B200_SEED_TABLES="Mc,Cc" overrides
     uint32_t seed_mc = 64, seed_cc = 16, seed_ns = 64;
     cudaStream_t stream = nullptr, own_stream = nullptr;
