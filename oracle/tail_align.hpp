@@ -37,6 +37,9 @@ struct PinnedAlignment {
     std::vector<Mapping> path;   // Mapping.node = tree index + 1 (TreeSubgraph id), offsets in trimmed coordinates
 };
 
+// Result of the DAG aligners (xdrop_dag.cpp): Mapping.node = index into the problem's node list.
+struct LocalAlignmentResult { int32_t score = 0; std::vector<Mapping> path; };
+
 // The X-drop DP contract (see tail_align.cpp for the full statement).
 PinnedAlignment xdrop_pinned(const Graph& g, const gb_scores& scores, const TailTree& tree,
                              const std::string& sequence, uint32_t max_gap_length, uint64_t* cells = nullptr);
