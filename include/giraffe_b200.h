@@ -359,6 +359,26 @@ int gb_sw_batch(gb_device* dev, uint32_t n,
                 int32_t* score, gb_mapping* maps, uint32_t* edits, uint32_t* n_maps, uint32_t* n_edits,
                 uint8_t* status);
 
+/* ------------------------------------------------------------------------------------
+ * B3: Aligner::align_xdrop(alignment, graph, order, mems, reverse_complemented = false, max_gap)
+ * — the seeded two-pass X-drop alignment of mate rescue     aligner.hpp:200, aligner.cpp:833-855,
+ *                                                           DozeuInterface::align dozeu_interface.cpp:608-685
+ * Problems are posed like gb_sw_batch (nodes in topological order + predecessor CSR).  seed holds
+ * three words per problem: the index of the seed node in the problem's list (0xffffffff: no seed,
+ * the last 15 query bases are scanned for their best local match instead, dozeu_interface.cpp:143-208),
+ * the offset in that node and the query offset where the seed match begins (the best gapless
+ * extension in attempt_rescue, minimizer_mapper.cpp:3345-3358).  Pass 1 extends the query suffix to
+ * the right of the seed and fixes the head; pass 2 aligns the query prefix leftwards from the head
+ * with traceback; the query right of the head is a soft clip.  score is the score of pass 2 (vg
+ * rescores the path afterwards, fix_dozeu_score minimizer_mapper.cpp:3502).
+ * ---------------------------------------------------------------------------------- */
+int gb_xdrop_dag_batch(gb_device* dev, uint32_t n,
+                       const uint32_t* node, const uint64_t* node_off, const uint32_t* pred, const uint64_t* pred_off,
+                       const uint8_t* query, const uint64_t* query_off, const uint32_t* seed, const uint32_t* max_gap,
+                       uint32_t map_cap, uint32_t edit_cap,
+                       int32_t* score, gb_mapping* maps, uint32_t* edits, uint32_t* n_maps, uint32_t* n_edits,
+                       uint8_t* status);
+
 /* Kernel-only timing of the last gb_*_batch call on this handle, milliseconds
  * (CUDA events on the handle's stream around the kernels, copies excluded). */
 float gb_last_kernel_ms(const gb_device* dev);

@@ -138,6 +138,8 @@ def load_library() -> C.CDLL:
     lib.gb_xdrop_pinned_batch.restype = C.c_int
     lib.gb_sw_batch.argtypes = [vp, u32, vp, vp, vp, vp, vp, vp, u32, u32, vp, vp, vp, vp, vp, vp]
     lib.gb_sw_batch.restype = C.c_int
+    lib.gb_xdrop_dag_batch.argtypes = [vp, u32, vp, vp, vp, vp, vp, vp, vp, vp, u32, u32, vp, vp, vp, vp, vp, vp]
+    lib.gb_xdrop_dag_batch.restype = C.c_int
     lib.gb_last_kernel_ms.argtypes = [vp]
     lib.gb_last_kernel_ms.restype = C.c_float
     lib.gb_launch_count.argtypes = [vp]
@@ -341,6 +343,45 @@ class Device:
                              map_cap, edit_cap, ptr(score), ptr(maps), ptr(edits), ptr(nm), ptr(ne), ptr(status))
         if rc != GB_OK:
             raise GbError(rc, "gb_sw_batch")
+        out = []
+        for i in range(n):
+            assert status[i] == GB_ITEM_OK, f"problem {i}: status {status[i]}"
+            path, e = [], i * edit_cap
+            for k in range(int(nm[i])):
+                m = maps[i * map_cap + k]
+                ed = []
+                for _ in range(int(m["n_edits"])):
+                    w = int(edits[e]); e += 1
+                    ed.append(["MSID"[w & 3], w >> 4, "ACGT"[(w >> 2) & 3] if (w & 3) == 1 else ""])
+                path.append([int(m["node"]), int(m["offset"]), ed])
+            out.append((int(score[i]), path))
+        return out
+
+    def xdrop_dag_batch(self, problems, map_cap=512, edit_cap=2048):
+        """gb_xdrop_dag_batch.  problems: list of (nodes, preds, query bytes, seed or None, max_gap) with
+        seed = (node index, node offset, query offset).  Returns list of (score, path) like sw_batch."""
+        lib = load_library()
+        n = len(problems)
+        node_off = np.zeros(n + 1, dtype=np.uint64)
+        node_off[1:] = np.cumsum([len(p[0]) for p in problems])
+        query_off = np.zeros(n + 1, dtype=np.uint64)
+        query_off[1:] = np.cumsum([len(p[2]) for p in problems])
+        nodes = np.concatenate([np.asarray(p[0], dtype=np.uint32) for p in problems])
+        pred = np.asarray([x for p in problems for ps in p[1] for x in ps] + [0], dtype=np.uint32)
+        pred_off = np.zeros(len(nodes) + 1, dtype=np.uint64)
+        pred_off[1:] = np.cumsum([len(ps) for p in problems for ps in p[1]])
+        q = np.frombuffer(b"".join(bytes(p[2]) for p in problems) + b"\0", dtype=np.uint8).copy()
+        seed = np.array([(0xFFFFFFFF, 0, 0) if p[3] is None else p[3] for p in problems], dtype=np.uint32).reshape(-1)
+        gap = np.array([p[4] for p in problems], dtype=np.uint32)
+        score = np.zeros(n, dtype=np.int32)
+        maps = np.zeros(n * map_cap, dtype=mapping_dt)
+        edits = np.zeros(n * edit_cap, dtype=np.uint32)
+        nm = np.zeros(n, dtype=np.uint32); ne = np.zeros(n, dtype=np.uint32)
+        status = np.zeros(n, dtype=np.uint8)
+        rc = lib.gb_xdrop_dag_batch(self._h, n, ptr(nodes), ptr(node_off), ptr(pred), ptr(pred_off), ptr(q), ptr(query_off),
+                                    ptr(seed), ptr(gap), map_cap, edit_cap, ptr(score), ptr(maps), ptr(edits), ptr(nm), ptr(ne), ptr(status))
+        if rc != GB_OK:
+            raise GbError(rc, "gb_xdrop_dag_batch")
         out = []
         for i in range(n):
             assert status[i] == GB_ITEM_OK, f"problem {i}: status {status[i]}"
