@@ -379,6 +379,24 @@ int gb_xdrop_dag_batch(gb_device* dev, uint32_t n,
                        int32_t* score, gb_mapping* maps, uint32_t* edits, uint32_t* n_maps, uint32_t* n_edits,
                        uint8_t* status);
 
+/* ------------------------------------------------------------------------------------
+ * B2: WFAExtender::connect / suffix / prefix      gbwt_extender.hpp:386-470, gbwt_extender.cpp:2052-2263
+ * (haplotype-consistent gap-affine wavefront alignment; called by the chaining route,
+ * minimizer_mapper_from_chains.cpp:2574, :2625, :2955, :3169).
+ * Problem i: sequence seq[seq_off[i] .. seq_off[i+1]); mode[i] = 0 connect(from, to), 1 suffix(from),
+ * 2 prefix(to); pos holds 4 words per problem: from node, from offset, to node, to offset (oriented
+ * nodes; the unused end is ignored).  error_model: 12 numbers {per_base, min, max} for mismatches,
+ * gaps, gap length, distance (WFAExtender::ErrorModel, gbwt_extender.hpp:340-385), NULL = defaults.
+ * Outputs per problem, as the fields of WFAAlignment (gbwt_extender.hpp:233-307): ok (0: no
+ * alignment, 1: alignment, -1: workspace capacity exceeded), score, node_offset, seq_offset, length,
+ * path (oriented nodes, at most path_cap), edits as (length << 2) | op with op 0 match, 1 mismatch,
+ * 2 insertion, 3 deletion (at most edit_cap).
+ * ---------------------------------------------------------------------------------- */
+int gb_wfa_batch(gb_device* dev, uint32_t n, const uint8_t* seq, const uint64_t* seq_off, const uint32_t* mode,
+                 const uint32_t* pos, const double* error_model, uint32_t path_cap, uint32_t edit_cap,
+                 int32_t* ok, int32_t* score, uint32_t* node_offset, uint32_t* seq_offset, uint32_t* length,
+                 uint32_t* path, uint32_t* n_path, uint32_t* edits, uint32_t* n_edits);
+
 /* Kernel-only timing of the last gb_*_batch call on this handle, milliseconds
  * (CUDA events on the handle's stream around the kernels, copies excluded). */
 float gb_last_kernel_ms(const gb_device* dev);

@@ -144,3 +144,68 @@ def verify(case, aln):
 @pytest.mark.parametrize("case", GOLD["cases"], ids=[f'{c["line"]}:{c["section"]}' for c in GOLD["cases"]])
 def test_oracle_wfa_matches_reference_vectors(case):
     verify(case, oracle_wfa(index_of(case["graph"]), case))
+
+
+def _problem_of(case):
+    frm = None if case["from"] is None else oriented(case["from"])
+    to = None if case["to"] is None else oriented(case["to"])
+    return (MODE[case["call"]], case["sequence"].encode(), frm, to)
+
+
+@pytest.mark.gpu
+def test_cuda_wfa_matches_reference_vectors_and_oracle():
+    by_key = {}
+    for case in GOLD["cases"]:
+        key = (case["graph"], None if case["error_model"] is None else tuple(case["error_model"]))
+        by_key.setdefault(key, []).append(case)
+    for (graph, em), cases in by_key.items():
+        index = index_of(graph)
+        dev = capi.Device(index, scores=capi.Scores(*SCORES))
+        got = dev.wfa_batch([_problem_of(c) for c in cases], error_model=None if em is None else list(em))
+        for c, g in zip(cases, got):
+            want = oracle_wfa(index, c)
+            assert g == want, (c["line"], c["section"], g, want)
+            verify(c, g)
+        dev.close()
+
+
+@pytest.mark.gpu
+def test_cuda_wfa_parity_random_problems_on_a_variant_graph():
+    from vg_b200 import synth
+    g = synth.make_variant_graph(length=20000, n_snp=60, n_ins=8, n_del=8, n_haps=6, seed=9)
+    index = g.build_index()
+    rng = np.random.default_rng(17)
+    problems, cases = [], []
+    for _ in range(400):
+        h = int(rng.integers(0, len(g.paths)))
+        hs = g.hap_seq[h]
+        a = int(rng.integers(50, len(hs) - 300)); ln = int(rng.integers(0, 90))
+        seq = hs[a + 1:a + 1 + ln].copy()
+        for i in range(len(seq)):
+            if rng.random() < 0.03:
+                seq[i] = synth.BASES[int(rng.integers(0, 4))]
+        seq = bytes(seq)
+        if rng.random() < 0.2 and len(seq) > 10:
+            k = int(rng.integers(2, len(seq) - 2)); seq = seq[:k] + seq[k + int(rng.integers(1, 4)):]
+        if rng.random() < 0.2 and len(seq) > 10:
+            k = int(rng.integers(2, len(seq) - 2)); seq = seq[:k] + b"ACGT"[: int(rng.integers(1, 4))] + seq[k:]
+        frm = (2 * int(g.hap_node[h][a]), int(g.hap_off[h][a]))
+        b = a + 1 + ln
+        to = (2 * int(g.hap_node[h][b]), int(g.hap_off[h][b]))
+        mode = int(rng.integers(0, 3))
+        if rng.random() < 0.15:       # other strand
+            seq = H_revcomp(seq.decode()).encode()
+            nlen = lambda v: len(g.node_seqs[v // 2 - 1])
+            frm, to = (to[0] ^ 1, nlen(to[0]) - 1 - to[1]), (frm[0] ^ 1, nlen(frm[0]) - 1 - frm[1])
+        problems.append((mode, seq, frm if mode != 2 else None, to if mode != 1 else None))
+        cases.append({"call": ["connect", "suffix", "prefix"][mode], "sequence": seq.decode(), "error_model": None,
+                      "from": None if mode == 2 else [frm[0] >> 1, bool(frm[0] & 1), frm[1]], "to": None if mode == 1 else [to[0] >> 1, bool(to[0] & 1), to[1]]})
+    dev = capi.Device(index, scores=capi.Scores(*SCORES))
+    got = dev.wfa_batch(problems)
+    n_ok = 0
+    for c, gt in zip(cases, got):
+        want = oracle_wfa(index, c)
+        assert gt == want, (c, gt, want)
+        n_ok += want["ok"]
+    assert n_ok > 200
+    dev.close()

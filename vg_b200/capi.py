@@ -140,6 +140,8 @@ def load_library() -> C.CDLL:
     lib.gb_sw_batch.restype = C.c_int
     lib.gb_xdrop_dag_batch.argtypes = [vp, u32, vp, vp, vp, vp, vp, vp, vp, vp, u32, u32, vp, vp, vp, vp, vp, vp]
     lib.gb_xdrop_dag_batch.restype = C.c_int
+    lib.gb_wfa_batch.argtypes = [vp, u32, vp, vp, vp, vp, vp, u32, u32, vp, vp, vp, vp, vp, vp, vp, vp, vp]
+    lib.gb_wfa_batch.restype = C.c_int
     lib.gb_last_kernel_ms.argtypes = [vp]
     lib.gb_last_kernel_ms.restype = C.c_float
     lib.gb_launch_count.argtypes = [vp]
@@ -394,6 +396,33 @@ class Device:
                     ed.append(["MSID"[w & 3], w >> 4, "ACGT"[(w >> 2) & 3] if (w & 3) == 1 else ""])
                 path.append([int(m["node"]), int(m["offset"]), ed])
             out.append((int(score[i]), path))
+        return out
+
+    def wfa_batch(self, problems, error_model=None, path_cap=512, edit_cap=512):
+        """gb_wfa_batch.  problems: list of (mode, sequence bytes, (from node, from offset) or None,
+        (to node, to offset) or None) with mode 0 connect / 1 suffix / 2 prefix and oriented nodes.
+        Returns list of dicts with the WFAAlignment fields (edits as (op letter, length), ops "MXID")."""
+        lib = load_library()
+        n = len(problems)
+        seq_off = np.zeros(n + 1, dtype=np.uint64)
+        seq_off[1:] = np.cumsum([len(p[1]) for p in problems])
+        seq = np.frombuffer(b"".join(bytes(p[1]) for p in problems) + b"\0", dtype=np.uint8).copy()
+        mode = np.array([p[0] for p in problems], dtype=np.uint32)
+        pos = np.array([list(p[2] or (0, 0)) + list(p[3] or (0, 0)) for p in problems], dtype=np.uint32).reshape(-1)
+        em = None if error_model is None else np.asarray(error_model, dtype=np.float64)
+        ok = np.zeros(n, dtype=np.int32); score = np.zeros(n, dtype=np.int32)
+        noff, soff, length, npath, nedits = (np.zeros(n, dtype=np.uint32) for _ in range(5))
+        path = np.zeros(n * path_cap, dtype=np.uint32); edits = np.zeros(n * edit_cap, dtype=np.uint32)
+        rc = lib.gb_wfa_batch(self._h, n, ptr(seq), ptr(seq_off), ptr(mode), ptr(pos), None if em is None else ptr(em), path_cap, edit_cap,
+                              ptr(ok), ptr(score), ptr(noff), ptr(soff), ptr(length), ptr(path), ptr(npath), ptr(edits), ptr(nedits))
+        if rc != GB_OK:
+            raise GbError(rc, "gb_wfa_batch")
+        out = []
+        for i in range(n):
+            assert ok[i] >= 0, f"problem {i}: workspace capacity exceeded"
+            out.append({"ok": bool(ok[i]), "score": int(score[i]), "node_offset": int(noff[i]), "seq_offset": int(soff[i]), "length": int(length[i]),
+                        "path": [int(x) for x in path[i * path_cap: i * path_cap + int(npath[i])]],
+                        "edits": [("MXID"[int(w) & 3], int(w) >> 2) for w in edits[i * edit_cap: i * edit_cap + int(nedits[i])]]})
         return out
 
     def map_arrays(self, rbuf, qbuf, read_off, params=None, paired=False, out=None):
