@@ -46,3 +46,30 @@ out = {"problems": n, "cells": int(cells), "gpu_kernel_ms": best, "gpu_gcups": c
        "cpu_1thread_gcups_incl_ctypes": sub_cells / dt / 1e9, "parity_mismatches": bad, "checked": len(sub)}
 print(json.dumps(out))
 json.dump(out, open("gpurun_out/bench_seams.json", "w"), indent=1)
+
+# ---- gb_wfa_batch: suffix / connect problems cut from haplotype 0 -------------------------------------------
+import test_wfa_golden as TW
+wprobs, wcases = [], []
+for _ in range(20000):
+    a = int(rng.integers(50, len(hs) - 300)); ln = int(rng.integers(20, 100))
+    seq = hs[a + 1:a + 1 + ln].copy()
+    mut = rng.random(ln) < 0.02
+    seq[mut] = synth.BASES[rng.integers(0, 4, size=int(mut.sum()))]
+    frm = (2 * int(g.hap_node[0][a]), int(g.hap_off[0][a])); b_ = a + 1 + ln
+    to = (2 * int(g.hap_node[0][b_]), int(g.hap_off[0][b_]))
+    mode = int(rng.integers(0, 2))
+    wprobs.append((mode, bytes(seq), frm, to if mode == 0 else None))
+    wcases.append({"call": ["connect", "suffix"][mode], "sequence": bytes(seq).decode(), "error_model": None,
+                   "from": [frm[0] >> 1, False, frm[1]], "to": None if mode == 1 else [to[0] >> 1, False, to[1]]})
+wbest = None
+for rep in range(3):
+    wgot = dev.wfa_batch(wprobs)
+    ms = dev.kernel_ms(); wbest = ms if wbest is None else min(wbest, ms)
+t = time.time()
+wwant = [TW.oracle_wfa(index, c) for c in wcases[:500]]
+wdt = time.time() - t
+wbad = sum(1 for i in range(500) if wgot[i] != wwant[i])
+out["wfa"] = {"problems": len(wprobs), "gpu_kernel_ms": wbest, "gpu_problems_per_s": len(wprobs) / (wbest / 1e3),
+              "cpu_1thread_problems_per_s_incl_ctypes": 500 / wdt, "parity_mismatches": wbad, "checked": 500}
+print(json.dumps(out["wfa"]))
+json.dump(out, open("gpurun_out/bench_seams.json", "w"), indent=1)
