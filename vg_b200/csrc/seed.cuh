@@ -818,25 +818,39 @@ __device__ __forceinline__ uint32_t cluster_phase_pe(const DevIndex& ix, const M
 #pragma unroll 1
         for (uint32_t level = 0; level < 2; level++) {
             uint8_t* lab = level == 0 ? cs.lab_frag : cs.lab_read;
+            // Components by min-label sweeps on the masks.  A label starts as the smallest index among the
+            // seed and its neighbours; a sweep then lets every seed take the smallest label found among its
+            // neighbours, label by label: one pair of warp votes tells which seeds carry label L, and a seed
+            // adopts the first (smallest) L whose carriers intersect its row.  Same fixed point as seed-by-seed
+            // propagation (the smallest index of the component), in a handful of votes for the usual 1-3 clusters.
             uint32_t mine[2];
 #pragma unroll
-            for (uint32_t q = 0; q < 2; q++) { mine[q] = lane + 32 * q; if (has[q]) lab[mine[q]] = (uint8_t)mine[q]; }
-            __syncwarp();
+            for (uint32_t q = 0; q < 2; q++) {
+                const uint64_t row = level == 0 ? adj_f[q] : adj_r[q];
+                const uint32_t i = lane + 32 * q;
+                mine[q] = row ? min(i, (uint32_t)(__ffsll((long long)row) - 1)) : i;
+            }
             while (true) {
+                const uint32_t p_lo = __reduce_or_sync(FULL, (has[0] && mine[0] < 32 ? 1u << mine[0] : 0u) | (has[1] && mine[1] < 32 ? 1u << mine[1] : 0u));
+                const uint32_t p_hi = __reduce_or_sync(FULL, (has[0] && mine[0] >= 32 ? 1u << (mine[0] - 32) : 0u) | (has[1] && mine[1] >= 32 ? 1u << (mine[1] - 32) : 0u));
+                uint64_t present = ((uint64_t)p_hi << 32) | p_lo;
+                uint32_t next[2] = {mine[0], mine[1]};
                 bool changed = false;
+                while (present) {
+                    const uint32_t L = (uint32_t)(__ffsll((long long)present) - 1); present &= present - 1;
+                    const uint64_t carriers = (uint64_t)__ballot_sync(FULL, has[0] && mine[0] == L) | ((uint64_t)__ballot_sync(FULL, has[1] && mine[1] == L) << 32);
 #pragma unroll
-                for (uint32_t q = 0; q < 2; q++) {
-                    uint64_t m = level == 0 ? adj_f[q] : adj_r[q];
-                    uint32_t best = mine[q];
-                    while (m) { const int j = __ffsll((long long)m) - 1; m &= m - 1; best = min(best, (uint32_t)lab[j]); }
-                    if (best < mine[q]) { mine[q] = best; changed = true; }
+                    for (uint32_t q = 0; q < 2; q++) {
+                        const uint64_t row = level == 0 ? adj_f[q] : adj_r[q];
+                        if (has[q] && L < next[q] && (row & carriers)) { next[q] = L; changed = true; }
+                    }
                 }
-                __syncwarp();
-#pragma unroll
-                for (uint32_t q = 0; q < 2; q++) if (has[q]) lab[lane + 32 * q] = (uint8_t)mine[q];
-                __syncwarp();
+                mine[0] = next[0]; mine[1] = next[1];
                 if (!__any_sync(FULL, changed)) break;
             }
+#pragma unroll
+            for (uint32_t q = 0; q < 2; q++) if (has[q]) lab[lane + 32 * q] = (uint8_t)mine[q];
+            __syncwarp();
         }
         // read-cluster labels back to the records (local index space of each read)
         for (uint32_t i = lane; i < n_all; i += 32) {
