@@ -798,22 +798,31 @@ __device__ __forceinline__ uint32_t cluster_phase_pe(const DevIndex& ix, const M
         uint4 own[2]; bool has[2]; uint64_t adj_f[2] = {0, 0}, adj_r[2] = {0, 0};
 #pragma unroll
         for (uint32_t q = 0; q < 2; q++) { const uint32_t i = lane + 32 * q; has[q] = i < n_all; own[q] = has[q] ? cs.seedbuf[i] : make_uint4(0, 0, 0, 0); }
+        // unoriented minimum distance through the payload, as seeds_within; INT_MAX when unreachable
+        auto seed_dist = [](const uint4& a, const uint4& c) -> int32_t {
+            if ((a.x >> 10) == (c.x >> 10)) { const int32_t d = (int32_t)(c.x & 1023u) - (int32_t)(a.x & 1023u); return d >= 0 ? d : -d; }
+            if (a.w < c.w) return (int32_t)c.y - (int32_t)a.z;
+            if (c.w < a.w) return (int32_t)a.y - (int32_t)c.z;
+            return INT_MAX;
+        };
+        // rows of seeds 0..31: lane i walks all j
         for (uint32_t j = 0; j < n_all; j++) {
             const uint4 sj = cs.seedbuf[j];
-            const bool j_first = j < H0;
-#pragma unroll
-            for (uint32_t q = 0; q < 2; q++) {
-                const uint32_t i = lane + 32 * q;
-                if (!has[q] || i == j) continue;
-                // unoriented minimum distance through the payload, as seeds_within
-                int32_t d;
-                if ((own[q].x >> 10) == (sj.x >> 10)) { d = (int32_t)(sj.x & 1023u) - (int32_t)(own[q].x & 1023u); d = d >= 0 ? d : -d; }
-                else if (own[q].w < sj.w) d = (int32_t)sj.y - (int32_t)own[q].z;
-                else if (sj.w < own[q].w) d = (int32_t)own[q].y - (int32_t)sj.z;
-                else continue;
-                if (d <= fragment_limit) adj_f[q] |= 1ull << j;
-                if (d <= read_limit && (i < H0) == j_first) adj_r[q] |= 1ull << j;
-            }
+            if (!has[0] || (uint32_t)lane == j) continue;
+            const int32_t d = seed_dist(own[0], sj);
+            if (d == INT_MAX) continue;
+            if (d <= fragment_limit) adj_f[0] |= 1ull << j;
+            if (d <= read_limit && ((uint32_t)lane < H0) == (j < H0)) adj_r[0] |= 1ull << j;
+        }
+        // rows of the few seeds beyond 32: the warp evaluates one row at a time, lane = column, rows by vote
+        for (uint32_t i = 32; i < n_all; i++) {
+            const uint4 si = cs.seedbuf[i];
+            bool f_lo = false, r_lo = false, f_hi = false, r_hi = false;
+            if (has[0]) { const int32_t d = seed_dist(si, own[0]); f_lo = d <= fragment_limit && d != INT_MAX; r_lo = d <= read_limit && d != INT_MAX && ((uint32_t)lane < H0) == (i < H0); }
+            if (has[1] && lane + 32 != (int)i) { const int32_t d = seed_dist(si, own[1]); f_hi = d <= fragment_limit && d != INT_MAX; r_hi = d <= read_limit && d != INT_MAX && ((uint32_t)lane + 32 < H0) == (i < H0); }
+            const uint64_t row_f = (uint64_t)__ballot_sync(FULL, f_lo) | ((uint64_t)__ballot_sync(FULL, f_hi) << 32);
+            const uint64_t row_r = (uint64_t)__ballot_sync(FULL, r_lo) | ((uint64_t)__ballot_sync(FULL, r_hi) << 32);
+            if ((uint32_t)lane + 32 == i) { adj_f[1] = row_f; adj_r[1] = row_r; }
         }
 #pragma unroll 1
         for (uint32_t level = 0; level < 2; level++) {
