@@ -272,6 +272,9 @@ typedef struct gb_map_params {
     double   rescue_subgraph_stdevs;     /* 4.0  */
     uint32_t max_rescue_attempts;        /* 15   */
     uint32_t max_fragment_length;        /* 2000 */
+    uint32_t rescue_seed_limit;          /* 100  (minimizer_mapper.hpp:459)                  */
+    uint32_t reserved0;
+    double   rescue_likelihood_limit;    /* 0.05 (minimizer_mapper.hpp:475)                  */
     /* output capacities per read */
     uint32_t mapping_cap_per_read;
     uint32_t edit_cap_per_read;

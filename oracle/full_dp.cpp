@@ -30,16 +30,6 @@
 
 namespace oracle {
 
-struct DagProblem {
-    std::vector<uint32_t> node;                 // oriented graph nodes, topological order
-    std::vector<std::vector<uint32_t>> pred;    // indices into `node`, each < own index
-};
-
-struct LocalAlignment {
-    int32_t score = 0;
-    std::vector<Mapping> path;                  // Mapping.node = index into the problem's node list
-};
-
 static inline bool is_acgt(char c) { return c == 'A' || c == 'C' || c == 'G' || c == 'T'; }
 
 // Recurrence (cell = graph base c of node u x query prefix j, 0 <= j <= m):
@@ -52,11 +42,11 @@ static inline bool is_acgt(char c) { return c == 'A' || c == 'C' || c == 'G' || 
 // predecessors' last columns (first predecessor on ties; H and E merged independently).
 // End of the alignment: max over all cells of H, and of d(., m) + bonus at j = m (on a tie with H
 // the attached end is taken); first maximum in (u, c, j) order.
-LocalAlignment sw_local_dag(const Graph& g, const gb_scores& sc, const DagProblem& P, const std::string& q, uint64_t* cells) {
+LocalAlignmentResult sw_local_dag(const Graph& g, const gb_scores& sc, const DagProblem& P, const std::string& q, uint64_t* cells) {
     constexpr int32_t NEG = INT_MIN / 4;
     const size_t N = P.node.size(), m = q.size(), W = m + 1;
     const int32_t go = sc.gap_open, ge = sc.gap_extend, bonus = sc.full_length_bonus;
-    LocalAlignment out;
+    LocalAlignmentResult out;
     if (N == 0 || m == 0) return out;
     auto subst = [&](char a, char b) -> int32_t {
         if (!is_acgt(a) || !is_acgt(b)) return 0;
@@ -202,7 +192,7 @@ extern "C" int oracle_sw_local(const gb_flat_index* ix, const gb_scores* scores,
     P.node.assign(node, node + n_nodes); P.pred.resize(n_nodes);
     for (uint32_t u = 0; u < n_nodes; u++) P.pred[u].assign(pred + pred_off[u], pred + pred_off[u + 1]);
     uint64_t cells = 0;
-    oracle::LocalAlignment a = oracle::sw_local_dag(g, *scores, P, std::string((const char*)query, qlen), &cells);
+    oracle::LocalAlignmentResult a = oracle::sw_local_dag(g, *scores, P, std::string((const char*)query, qlen), &cells);
     if (cells_out) *cells_out = cells;
     *score_out = a.score;
     if (a.path.size() > mapping_cap) return -1;

@@ -77,6 +77,30 @@ double maximum_mapping_quality_exact(const std::vector<double>& scaled) {
     return std::isinf(direct) ? (double)std::numeric_limits<int32_t>::max() : direct;
 }
 
+// maximum_mapping_quality_exact with multiplicities (:26-67), used when every pair was found by rescue
+double maximum_mapping_quality_exact(const std::vector<double>& scaled, const std::vector<double>* multiplicities) {
+    const double quality_scale_factor = 10.0 / std::log(10.0);
+    double log_sum_exp = std::numeric_limits<double>::lowest();
+    double to_score = std::numeric_limits<double>::lowest();
+    for (int64_t i = (int64_t)scaled.size() - 1; i >= 0; --i) {
+        double score = scaled[i];
+        if (score >= to_score) to_score = score;
+        if (multiplicities && (*multiplicities)[i] > 1.0) score += std::log((*multiplicities)[i]);
+        log_sum_exp = add_log(log_sum_exp, score);
+    }
+    if (scaled.size() == 1) {
+        if (multiplicities && (*multiplicities)[0] <= 1.0) log_sum_exp = add_log(log_sum_exp, 0.0);
+        else if (!multiplicities) log_sum_exp = add_log(log_sum_exp, 0.0);
+    }
+    double direct = -quality_scale_factor * subtract_log(0.0, to_score - log_sum_exp);
+    return std::isinf(direct) ? (double)std::numeric_limits<int32_t>::max() : direct;
+}
+int32_t compute_max_mapping_quality(const std::vector<double>& scores, double log_base, const std::vector<double>* multiplicities) {
+    std::vector<double> scaled(scores.size());
+    for (size_t i = 0; i < scores.size(); i++) scaled[i] = log_base * scores[i];
+    return (int32_t)maximum_mapping_quality_exact(scaled, multiplicities);
+}
+
 // compute_max_mapping_quality :355-364 (returns int32_t)
 int32_t compute_max_mapping_quality(const std::vector<double>& scores, double log_base) {
     std::vector<double> scaled(scores.size());
@@ -675,6 +699,7 @@ extern "C" void oracle_map_params_default(gb_map_params* p) {
     p->max_dozeu_cells = (uint32_t)(1.5 * 1024 * 1024); p->do_dp = 1;
     p->fragment_mean = 0; p->fragment_stdev = 0; p->paired_distance_stdevs = 2.0; p->paired_rescue_score_limit = 0.9;
     p->rescue_subgraph_stdevs = 4.0; p->max_rescue_attempts = 15; p->max_fragment_length = 2000;
+    p->rescue_seed_limit = 100; p->reserved0 = 0; p->rescue_likelihood_limit = 0.05;
     p->mapping_cap_per_read = 96; p->edit_cap_per_read = 160;
 }
 

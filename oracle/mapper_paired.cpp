@@ -1,8 +1,8 @@
 // ORACLE — TEST INFRASTRUCTURE ONLY.  CPU restatement of MinimizerMapper::map_paired with a
 // finalized (forced) fragment length distribution, src/minimizer_mapper.cpp:1462-2942 @ fd49b9a9,
-// for the configuration max_rescue_attempts = 0 (`vg giraffe --rescue-attempts 0`): the
-// rescue branch (:2338-2457, attempt_rescue :3264-3565) is NOT restated in this round
-// (SURVEY.md §8 row a17); the no-rescue branches (:2238-2287) are.
+// including the rescue branch (:2288-2457; attempt_rescue itself is oracle/rescue.cpp) and the
+// no-rescue branch for max_rescue_attempts = 0 (:2238-2287).  Not restated: supplementary
+// alignments (find_supplementaries, off by default).
 //   joint clustering: SnarlDistanceIndexClusterer::cluster_seeds snarl_seed_clusterer.cpp:65-145
 //   pair score:       score_alignment_pair :6017-6028, distance_between :3879-3903
 #include "mapper_common.hpp"
@@ -20,6 +20,9 @@ namespace oracle {
 // from mapper.cpp
 double recover_log_base(const gb_scores& s);
 int32_t compute_max_mapping_quality(const std::vector<double>& scores, double log_base);
+int32_t compute_max_mapping_quality(const std::vector<double>& scores, double log_base, const std::vector<double>* multiplicities);
+Alignment attempt_rescue(const gb_flat_index* ix, const gb_scores& sc, const gb_map_params& P, const Alignment& anchor,
+                         const std::string& sequence, const std::vector<Minimizer>& minimizers, bool rescue_forward, MapCounters* counters);
 std::vector<Minimizer> find_minimizers(const gb_flat_index* ix, const gb_map_params& P, const std::string& sequence);
 std::vector<size_t> sort_minimizers_by_score(const std::vector<Minimizer>& minimizers, LazyRNG& rng);
 std::vector<Seed> find_seeds(const gb_flat_index* ix, const gb_map_params& P, const std::vector<Minimizer>& minimizers, size_t read_len);
@@ -297,46 +300,105 @@ PairResult map_paired(const gb_flat_index* ix, const gb_scores& scores, const gb
         double worse = std::min(a1.score, a2.score);
         return std::max(score, worse);
     };
-    for (size_t f = 0; f < alignments.size(); f++) {
+    enum PairType { PT_PAIRED, PT_UNPAIRED, PT_RESCUED_FROM_FIRST, PT_RESCUED_FROM_SECOND };
+    std::vector<PairType> pair_types;
+    std::array<size_t, 2> unpaired_count{0, 0}, rescued_count{0, 0};
+    // distance_between(aln1, aln2): initial_position(aln1) -> final_position(aln2) (:3895-3903)
+    auto distance_between = [&](const Alignment& a0, const Alignment& a1) -> int64_t {
+        const Mapping& last = a1.path.back();
+        uint32_t used = 0; for (const Edit& e : last.edits) used += e.from_length;
+        return oriented_distance(ix, a0.path.front().node, a0.path.front().offset, last.node, last.offset + used);
+    };
+    const size_t n_cluster_fragments = alignments.size() - 1;        // the last entry collects rescued alignments
+    for (size_t f = 0; f < n_cluster_fragments; f++) {
         auto& fa = alignments[f];
         if (!fa[0].empty() && !fa[1].empty()) {
             found_pair = true;
             for (size_t i0 = 0; i0 < fa[0].size(); i0++) for (size_t i1 = 0; i1 < fa[1].size(); i1++) {
                 const Alignment& a0 = fa[0][i0]; const Alignment& a1 = fa[1][i1];
-                // distance_between(aln1, aln2): initial_position(aln1) -> final_position(aln2) (:3895-3903)
-                const Mapping& last = a1.path.back();
-                uint32_t used = 0; for (const Edit& e : last.edits) used += e.from_length;
-                int64_t dist = oriented_distance(ix, a0.path.front().node, a0.path.front().offset, last.node, last.offset + used);
+                int64_t dist = distance_between(a0, a1);
                 paired_alignments.push_back({Idx{f, i0}, Idx{f, i1}});
                 paired_scores.push_back(score_alignment_pair(a0, a1, dist));
                 fragment_distances.push_back(dist);
                 better_cluster_count_by_pairs.push_back(better_cluster_count[f]);
+                pair_types.push_back(PT_PAIRED);
             }
         } else {
-            for (int r : {0, 1}) for (size_t i = 0; i < fa[r].size(); i++) unpaired_alignments.push_back(UIdx{f, i, r});
+            for (int r : {0, 1}) for (size_t i = 0; i < fa[r].size(); i++) { unpaired_alignments.push_back(UIdx{f, i, r}); unpaired_count[r]++; }
         }
     }
     auto finish_read2 = [&](Alignment& a) { reverse_complement_path(a.path, g); };
+    std::array<std::vector<double>, 2> unpaired_scores;
 
-    if (!unpaired_alignments.empty() && !found_pair) {
-        // max_rescue_attempts == 0 branch (:2227-2287): best alignment of each end, MAPQ 1
-        std::array<int64_t, 2> best_index{-1, -1}; std::array<int32_t, 2> best_score{0, 0};
-        for (size_t u = 0; u < unpaired_alignments.size(); u++) {
-            const UIdx& index = unpaired_alignments[u];
-            const Alignment& alignment = alignments[index.fragment][index.read][index.index];
-            if (deterministic_beats(alignment.score, best_score[index.read], rng)) { best_index[index.read] = (int64_t)u; best_score[index.read] = alignment.score; }
+    if (!unpaired_alignments.empty()) {
+        if (!found_pair) {
+            std::array<int64_t, 2> best_index{-1, -1}; std::array<int32_t, 2> best_score{0, 0};
+            for (size_t u = 0; u < unpaired_alignments.size(); u++) {
+                const UIdx& index = unpaired_alignments[u];
+                const Alignment& alignment = alignments[index.fragment][index.read][index.index];
+                unpaired_scores[index.read].push_back(alignment.score);
+                if (deterministic_beats(alignment.score, best_score[index.read], rng)) { best_index[index.read] = (int64_t)u; best_score[index.read] = alignment.score; }
+            }
+            if (P.max_rescue_attempts == 0) {
+                // best alignment of each end, MAPQ 1 (:2238-2287)
+                for (int r : {0, 1}) {
+                    if (best_index[r] >= 0) { const UIdx& index = unpaired_alignments[(size_t)best_index[r]]; result.aln[r] = alignments[index.fragment][index.read][index.index]; }
+                    else result.aln[r] = Alignment();
+                }
+                finish_read2(result.aln[1]);
+                for (int r : {0, 1}) result.aln[r].mapq = 1;
+                return result;
+            } else if (best_score[0] != 0 && best_score[1] != 0) {
+                // keep the best alignments as a potential (unpaired) pair, distance "infinite" (:2288-2334)
+                const UIdx& u0 = unpaired_alignments[(size_t)best_index[0]]; const UIdx& u1 = unpaired_alignments[(size_t)best_index[1]];
+                paired_alignments.push_back({Idx{u0.fragment, u0.index}, Idx{u1.fragment, u1.index}});
+                paired_scores.push_back(score_alignment_pair(alignments[u0.fragment][0][u0.index], alignments[u1.fragment][1][u1.index], std::numeric_limits<int64_t>::max()));
+                fragment_distances.push_back(std::numeric_limits<int64_t>::max());
+                better_cluster_count_by_pairs.push_back(0);
+                pair_types.push_back(PT_UNPAIRED);
+            }
         }
-        for (int r : {0, 1}) {
-            if (best_index[r] >= 0) { const UIdx& index = unpaired_alignments[(size_t)best_index[r]]; result.aln[r] = alignments[index.fragment][index.read][index.index]; }
-            else result.aln[r] = Alignment();
+        if (P.max_rescue_attempts != 0) {
+            // rescue from the best unpaired alignments (:2338-2457)
+            process_until_threshold_e<double>(unpaired_alignments.size(),
+                [&](size_t i) -> double { const UIdx& u = unpaired_alignments[i]; return (double)alignments[u.fragment][u.read][u.index].score; },
+                [&](size_t a, size_t b) -> bool {
+                    const UIdx& ua = unpaired_alignments[a]; const UIdx& ub = unpaired_alignments[b];
+                    return alignments[ua.fragment][ua.read][ua.index].score > alignments[ub.fragment][ub.read][ub.index].score;
+                },
+                [&](size_t) -> bool { return false; },
+                0, 1, P.max_rescue_attempts, rng,
+                [&](size_t i, size_t, bool) -> bool {
+                    const UIdx index = unpaired_alignments[i];
+                    const Alignment mapped_aln = alignments[index.fragment][index.read][index.index];
+                    if (found_pair && (double)mapped_aln.score < (double)best_alignment_scores[index.read] * P.paired_rescue_score_limit) return true;
+                    const int other = 1 - index.read;
+                    Alignment rescued_aln = attempt_rescue(ix, scores, P, mapped_aln, seqs[other], minimizers_by_read[other], index.read == 0, counters);
+                    rescued_aln.rescued = true;
+                    int64_t fragment_dist; double score;
+                    if (!rescued_aln.path.empty()) {
+                        fragment_dist = index.read == 0 ? distance_between(mapped_aln, rescued_aln) : distance_between(rescued_aln, mapped_aln);
+                        score = score_alignment_pair(mapped_aln, rescued_aln, fragment_dist);
+                    } else { score = mapped_aln.score; fragment_dist = std::numeric_limits<int64_t>::max(); }
+                    const size_t rf = alignments.size() - 1;
+                    std::array<Idx, 2> index_pair;
+                    index_pair[index.read] = Idx{index.fragment, index.index};
+                    index_pair[other] = Idx{rf, alignments[rf][other].size()};
+                    alignments[rf][other].push_back(std::move(rescued_aln));
+                    rescued_count[index.read]++;
+                    paired_alignments.push_back(index_pair);
+                    fragment_distances.push_back(fragment_dist);
+                    paired_scores.push_back(score);
+                    pair_types.push_back(index.read == 0 ? PT_RESCUED_FROM_FIRST : PT_RESCUED_FROM_SECOND);
+                    better_cluster_count_by_pairs.push_back(better_cluster_count[index.fragment]);
+                    return true;
+                },
+                [&](size_t) {}, [&](size_t) {});
         }
-        finish_read2(result.aln[1]);
-        for (int r : {0, 1}) result.aln[r].mapq = 1;
-        return result;
     }
 
     // ---- winner (:2505-2598) and MAPQ (:2606-2777) --------------------------------------------------
-    std::vector<double> out_scores; std::vector<int64_t> distances; std::vector<size_t> better_cluster_count_by_mappings;
+    std::vector<double> out_scores; std::vector<int64_t> distances; std::vector<size_t> better_cluster_count_by_mappings; std::vector<PairType> types;
     std::array<std::vector<Alignment>, 2> mappings;
     process_until_threshold_e<double>(paired_alignments.size(),
         [&](size_t i) -> double { return paired_scores[i]; },
@@ -344,18 +406,31 @@ PairResult map_paired(const gb_flat_index* ix, const gb_scores& scores, const gb
         [&](size_t) -> bool { return false; },
         0, 1, P.max_multimaps, rng,
         [&](size_t n, size_t, bool) -> bool {
-            out_scores.push_back(paired_scores[n]); distances.push_back(fragment_distances[n]);
+            out_scores.push_back(paired_scores[n]); distances.push_back(fragment_distances[n]); types.push_back(pair_types[n]);
             better_cluster_count_by_mappings.push_back(better_cluster_count_by_pairs[n]);
             for (int r : {0, 1}) mappings[r].push_back(alignments[paired_alignments[n][r].fragment][r][paired_alignments[n][r].index]);
             finish_read2(mappings[1].back());
             return true;
         },
-        [&](size_t n) { out_scores.push_back(paired_scores[n]); distances.push_back(fragment_distances[n]); better_cluster_count_by_mappings.push_back(better_cluster_count_by_pairs[n]); },
+        [&](size_t n) { out_scores.push_back(paired_scores[n]); distances.push_back(fragment_distances[n]); types.push_back(pair_types[n]); better_cluster_count_by_mappings.push_back(better_cluster_count_by_pairs[n]); },
         [&](size_t) {});
 
     if (mappings[0].empty()) { result.aln[0] = Alignment(); result.aln[1] = Alignment(); return result; }
 
-    double uncapped_mapq = out_scores[0] == 0 ? 0 : compute_max_mapping_quality(out_scores, log_base);
+    // multiplicities when every pair was found by rescue (:2661-2690)
+    std::array<double, 2> estimated_multiplicity_from;
+    for (int r : {0, 1}) estimated_multiplicity_from[r] = unpaired_count[r] > 0 ? (double)unpaired_count[r] / (double)std::min<size_t>(rescued_count[r], P.max_rescue_attempts) : 1.0;
+    bool all_rescued = true; std::vector<double> paired_multiplicities;
+    for (PairType t : types) {
+        switch (t) {
+        case PT_PAIRED: paired_multiplicities.push_back(1.0); all_rescued = false; break;
+        case PT_UNPAIRED: paired_multiplicities.push_back(1.0); break;
+        case PT_RESCUED_FROM_FIRST: paired_multiplicities.push_back(estimated_multiplicity_from[0]); break;
+        case PT_RESCUED_FROM_SECOND: paired_multiplicities.push_back(estimated_multiplicity_from[1]); break;
+        }
+    }
+    const std::vector<double>* multiplicities = all_rescued ? &paired_multiplicities : nullptr;
+    double uncapped_mapq = out_scores[0] == 0 ? 0 : compute_max_mapping_quality(out_scores, log_base, multiplicities);
     double fragment_cluster_cap = std::numeric_limits<float>::infinity();
     if (better_cluster_count_by_mappings.front() > 1)
         fragment_cluster_cap = -10.0 * std::log10(1.0 - (1.0 / (double)better_cluster_count_by_mappings.front()));   // prob_to_phred
@@ -368,6 +443,7 @@ PairResult map_paired(const gb_flat_index* ix, const gb_scores& scores, const gb
     for (int r : {0, 1}) {
         double escape_bonus = uncapped_mapq < std::numeric_limits<int32_t>::max() ? 1.0 : 2.0;
         double mapq_cap = std::min(fragment_cluster_cap, ((mapq_explored_caps[0] + mapq_explored_caps[1]) * escape_bonus));
+        if (types.front() == PT_UNPAIRED) mapq_cap = std::min(mapq_cap, (double)compute_max_mapping_quality(unpaired_scores[r], log_base));   // :2735-2739
         double read_mapq = uncapped_mapq;
         double capped_mapq = std::min(mapq_cap, read_mapq);
         if (distances.front() == std::numeric_limits<int64_t>::max()) capped_mapq = capped_mapq / 2.0;
@@ -388,7 +464,7 @@ extern "C" int oracle_map_paired_batch(const gb_flat_index* ix, const gb_scores*
                                        uint32_t n_reads, const uint8_t* reads, const uint8_t* quals, const uint64_t* read_off,
                                        gb_alignment* aln, gb_mapping* mappings, uint32_t* edits, uint8_t* status,
                                        int n_threads, uint64_t* counters_out) {
-    if (n_reads % 2 != 0 || p->max_rescue_attempts != 0) return -2;
+    if (n_reads % 2 != 0) return -2;
     oracle::MapCounters total;
     int failed = 0;
 #pragma omp parallel num_threads(n_threads > 0 ? n_threads : 1)

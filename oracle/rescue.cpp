@@ -1,0 +1,216 @@
+// ORACLE — TEST INFRASTRUCTURE ONLY.  Mate rescue:
+//   MinimizerMapper::attempt_rescue            minimizer_mapper.cpp:3264-3482
+//   seeds_in_subgraph                          :3484-3500
+//   fix_dozeu_score / fix_dozeu_end_deletions  :3502-3565
+//   subgraph_in_distance_range                 snarl_distance_index.cpp:1875-2052 (contract: "the set of nodes in the
+//                                              graph for which the minimum distance from the position to any
+//                                              position in the node is within the given distance range")
+//   EditAlignmentScorer::score_contiguous_alignment  alignment_scorer.cpp:158-246
+// for rescue_algorithm = dozeu (the default) on DAG subgraphs (gbwtgraph::topological_order non-empty;
+// the dagify branch :3404-3445 is not restated: the synthetic graphs of this repository are DAGs).
+//
+// PARITY UNPINNED where absent libraries decide: libbdsg's snarl walk (which nodes on the range boundary
+// are collected) is replaced by the stated contract evaluated through the distance payload;
+// gbwtgraph::topological_order is replaced by chain-slot order (both orientations: the forward strand in
+// ascending slot order, then its mirror); the DP itself is oracle/xdrop_dag.cpp / oracle/full_dp.cpp.
+#include "tail_align.hpp"
+#include <cmath>
+#include <map>
+#include <set>
+
+namespace oracle {
+
+std::vector<Mapping> extension_to_path(const Graph& g, const GaplessExtension& e, const std::string& sequence);
+
+namespace {
+
+struct RescueGraph { DagProblem dag; size_t bases = 0; };
+
+// nodes (ids) with a base whose minimum distance from the origin lies in [min_distance, max_distance];
+// the origin is (node, offset) on the strand the walk follows.
+std::vector<uint32_t> subgraph_in_distance_range(const gb_flat_index* ix, uint32_t start_node, int64_t to_end,
+                                                 int64_t min_distance, int64_t max_distance) {
+    std::vector<uint32_t> ids;
+    const uint32_t start_id = start_node >> 1; const bool rev = start_node & 1u;
+    const gb_dist_payload& ps = ix->dist[start_id];
+    if (to_end > min_distance) ids.push_back(start_id);
+    const uint32_t n_ids = ix->n_nodes / 2;
+    for (uint32_t id = 1; id < n_ids; id++) {
+        if (id == start_id || ix->nodes[2 * id].len == 0) continue;
+        const gb_dist_payload& pv = ix->dist[id];
+        if (pv.component != ps.component) continue;
+        int64_t d0;     // distance from the origin to the first base of the node in walk direction
+        if (!rev) { if (!(ps.slot < pv.slot)) continue; d0 = to_end + ((int64_t)pv.x_in - (int64_t)ps.x_out); }
+        else { if (!(pv.slot < ps.slot)) continue; d0 = to_end + ((int64_t)ps.x_in - (int64_t)pv.x_out); }
+        const int64_t len = ix->nodes[2 * id].len;
+        if (d0 <= max_distance && d0 + len > min_distance) ids.push_back(id);
+    }
+    return ids;
+}
+
+// both orientations of the subgraph in a topological order, and the edges among them
+RescueGraph rescue_dag(const Graph& g, const gb_flat_index* ix, std::vector<uint32_t> ids) {
+    RescueGraph out;
+    std::sort(ids.begin(), ids.end(), [&](uint32_t a, uint32_t b) {
+        const gb_dist_payload& pa = ix->dist[a]; const gb_dist_payload& pb = ix->dist[b];
+        if (pa.component != pb.component) return pa.component < pb.component;
+        if (pa.slot != pb.slot) return pa.slot < pb.slot;
+        return a < b;
+    });
+    for (uint32_t id : ids) out.dag.node.push_back(2 * id);
+    for (auto it = ids.rbegin(); it != ids.rend(); ++it) out.dag.node.push_back(2 * *it + 1);
+    std::map<uint32_t, uint32_t> index_of;
+    for (uint32_t i = 0; i < out.dag.node.size(); i++) index_of[out.dag.node[i]] = i;
+    out.dag.pred.resize(out.dag.node.size());
+    for (uint32_t i = 0; i < out.dag.node.size(); i++) {
+        const uint32_t v = out.dag.node[i];
+        out.bases += g.get_length(v);
+        Graph::Record rec = g.record(v);
+        for (uint32_t r = 0; r < rec.n_edges; r++) {
+            const uint32_t to = rec.successor(r);
+            if (to == 0) continue;
+            auto it = index_of.find(to);
+            if (it != index_of.end() && it->second > i) out.dag.pred[it->second].push_back(i);
+        }
+    }
+    for (auto& p : out.dag.pred) { std::sort(p.begin(), p.end()); p.erase(std::unique(p.begin(), p.end()), p.end()); }
+    return out;
+}
+
+bool softclip_start(const std::vector<Mapping>& path) { return !path.empty() && !path.front().edits.empty() && path.front().edits.front().from_length == 0 && path.front().edits.front().to_length > 0; }
+bool softclip_end(const std::vector<Mapping>& path) { return !path.empty() && !path.back().edits.empty() && path.back().edits.back().from_length == 0 && path.back().edits.back().to_length > 0; }
+
+} // namespace
+
+// score_contiguous_alignment(aln) with both bonuses allowed (alignment_scorer.cpp:154-246)
+int32_t score_contiguous_alignment(const gb_scores& sc, const std::vector<Mapping>& path) {
+    int32_t score = 0; bool last_was_deletion = false;
+    for (size_t i = 0; i < path.size(); i++) {
+        for (size_t j = 0; j < path[i].edits.size(); j++) {
+            const Edit& e = path[i].edits[j];
+            if (e.from_length == e.to_length && e.sequence.empty()) { score += sc.match * (int32_t)e.to_length; last_was_deletion = false; }
+            else if (e.from_length == e.to_length) { score -= sc.mismatch * (int32_t)e.to_length; last_was_deletion = false; }
+            else if (e.to_length == 0) {
+                if (last_was_deletion) score -= (int32_t)e.from_length * sc.gap_extend;
+                else score -= e.from_length ? sc.gap_open + ((int32_t)e.from_length - 1) * sc.gap_extend : 0;
+                if (e.from_length) last_was_deletion = true;
+            } else if (e.from_length == 0 && !((i == 0 && j == 0) || (i + 1 == path.size() && j + 1 == path[i].edits.size()))) {
+                score -= e.to_length ? sc.gap_open + ((int32_t)e.to_length - 1) * sc.gap_extend : 0;
+                last_was_deletion = false;
+            } else last_was_deletion = false;
+        }
+    }
+    if (!softclip_start(path)) score += sc.full_length_bonus;
+    if (!softclip_end(path)) score += sc.full_length_bonus;
+    return score;
+}
+
+// fix_dozeu_end_deletions (:3519-3565)
+void fix_dozeu_end_deletions(std::vector<Mapping>& path) {
+    size_t i = 0, j = 0;
+    for (; i < path.size(); ++i) {
+        for (j = 0; j < path[i].edits.size(); ++j) if (path[i].edits[j].to_length != 0) break;
+        if (j != path[i].edits.size()) break;
+    }
+    if (i == path.size()) { path.clear(); }
+    else if (i != 0 || j != 0) {
+        // (the reference indexes the mapping to trim with j; both indices select the same mapping in every
+        //  case dozeu produces, a deletion prefix on the first aligned mapping)
+        uint32_t removed = 0;
+        for (size_t k = 0; k < j; ++k) removed += path[i].edits[k].from_length;
+        path[i].edits.erase(path[i].edits.begin(), path[i].edits.begin() + j);
+        path.erase(path.begin(), path.begin() + i);
+        path[0].offset += removed;
+    }
+    for (int64_t k = (int64_t)path.size() - 1; k >= 0; --k) {
+        auto& edits = path[k].edits;
+        while (!edits.empty() && edits.back().to_length == 0) edits.pop_back();
+        if (edits.empty()) path.pop_back(); else break;
+    }
+}
+
+// attempt_rescue.  `anchor` is the mapped mate's alignment (rightward orientation, as both reads are
+// inside map_paired); returns the rescued alignment in problem-free graph space (oriented nodes), empty
+// path when nothing significant was found.
+Alignment attempt_rescue(const gb_flat_index* ix, const gb_scores& sc, const gb_map_params& P, const Alignment& anchor,
+                         const std::string& sequence, const std::vector<Minimizer>& minimizers, bool rescue_forward, MapCounters* counters) {
+    Graph g(ix);
+    Alignment rescued;
+    if (anchor.path.empty() || sequence.empty()) return rescued;
+    if (counters) counters->rescues++;
+    const int64_t min_distance = (int64_t)std::max(0.0, P.fragment_mean - (double)sequence.size() - P.rescue_subgraph_stdevs * P.fragment_stdev);
+    const int64_t max_distance = (int64_t)(P.fragment_mean + P.rescue_subgraph_stdevs * P.fragment_stdev);
+    // origin: the start of the anchor looking forward, or its end looking backward (snarl_distance_index.cpp:1883-1893)
+    // (initial_position; or final_position seen from the other strand, reverse_base_pos: one base past the alignment)
+    uint32_t start_node; int64_t to_end;          // bases from the origin (included) to the end of its node in walk direction
+    if (rescue_forward) { start_node = anchor.path.front().node; to_end = (int64_t)g.get_length(start_node) - (int64_t)anchor.path.front().offset; }
+    else {
+        const Mapping& last = anchor.path.back();
+        uint32_t used = 0; for (const Edit& e : last.edits) used += e.from_length;
+        start_node = last.node ^ 1u; to_end = (int64_t)(last.offset + used) + 1;
+    }
+    std::vector<uint32_t> rescue_ids = subgraph_in_distance_range(ix, start_node, to_end, min_distance, max_distance);
+    if (rescue_ids.empty()) return rescued;
+
+    // seeds_in_subgraph: every hit of every minimizer of the read that lies on a subgraph node
+    std::set<uint32_t> id_set(rescue_ids.begin(), rescue_ids.end());
+    std::set<std::pair<uint32_t, int64_t>> seed_set;
+    for (const Minimizer& m : minimizers) {
+        for (size_t j = 0; j < m.hit_cnt; j++) {
+            const gb_hit& occ = ix->hits[m.hit_off + j];
+            uint32_t node = (uint32_t)(occ.pos >> 10), off = (uint32_t)(occ.pos & 1023u);
+            if (!id_set.count(node >> 1)) continue;
+            if (m.is_reverse) { const uint32_t node_length = ix->nodes[node].len; node ^= 1u; off = node_length - off - 1; }
+            seed_set.insert({node, (int64_t)m.offset - (int64_t)off});        // GaplessExtender::to_seed
+        }
+    }
+    if (seed_set.size() > P.rescue_seed_limit) return rescued;
+    std::vector<std::pair<uint32_t, int64_t>> seeds(seed_set.begin(), seed_set.end());
+    std::vector<GaplessExtension> extensions = extend(g, sc, seeds, sequence, 4, 0.8, true);
+    if (!extensions.empty() && extensions.front().full() && extensions.front().mismatch_positions.size() <= 4) {
+        rescued.path = extension_to_path(g, extensions.front(), sequence);
+        rescued.score = extensions.front().score;
+        rescued.identity = path_identity(rescued.path);
+        return rescued;
+    }
+    size_t best = extensions.size();
+    for (size_t i = 0; i < extensions.size(); i++) if (best >= extensions.size() || extensions[i].score > extensions[best].score) best = i;
+    if (best < extensions.size()) for (uint32_t h : extensions[best].path) id_set.insert(h >> 1);
+    RescueGraph rg = rescue_dag(g, ix, std::vector<uint32_t>(id_set.begin(), id_set.end()));
+    const size_t subgraph_size = rg.bases;
+    if (rg.bases * sequence.size() > P.max_dozeu_cells) return rescued;
+    bool has_seed = false; uint32_t seed_u = 0, seed_o = 0, seed_q = 0;
+    if (best < extensions.size()) {
+        const GaplessExtension& e = extensions[best];
+        for (uint32_t i = 0; i < rg.dag.node.size(); i++) if (rg.dag.node[i] == e.path.front()) { seed_u = i; has_seed = true; break; }
+        seed_o = (uint32_t)e.offset; seed_q = (uint32_t)e.read_interval.first;
+    }
+    const uint32_t gap_limit = (uint32_t)longest_detectable_gap(sc, sequence.size(), sequence.size() / 2);
+    uint64_t cells = 0;
+    LocalAlignmentResult a = align_xdrop_dag(g, sc, rg.dag, sequence, has_seed, seed_u, seed_o, seed_q, gap_limit, &cells);
+    auto to_graph = [&](LocalAlignmentResult& r) { for (Mapping& m : r.path) m.node = rg.dag.node[m.node]; };
+    to_graph(a);
+    rescued.path = std::move(a.path);
+    // fix_dozeu_score (:3502-3517)
+    const int32_t rescored = rescued.path.empty() ? 0 : score_contiguous_alignment(sc, rescued.path);
+    if (rescored > 0) rescued.score = rescored;
+    else {
+        LocalAlignmentResult b = sw_local_dag(g, sc, rg.dag, sequence, &cells);
+        to_graph(b);
+        rescued.path = std::move(b.path); rescued.score = b.score;
+    }
+    fix_dozeu_end_deletions(rescued.path);
+    if (rescued.path.empty()) rescued.score = 0;
+    if (counters) counters->tail_cells += cells;
+    // chance filter (:3451-3481)
+    const int64_t effective_matches = rescued.score / sc.match;
+    if (effective_matches <= (int64_t)sequence.size() && effective_matches <= (int64_t)subgraph_size) {
+        const double by_chance_likelihood = 1.0 - std::pow(1.0 - std::pow(0.25, (double)effective_matches),
+                                                           (double)((sequence.size() - effective_matches + 1) * (subgraph_size - effective_matches + 1)));
+        if (by_chance_likelihood > P.rescue_likelihood_limit) { rescued.path.clear(); rescued.score = 0; }
+    }
+    rescued.identity = rescued.path.empty() ? 0 : path_identity(rescued.path);
+    return rescued;
+}
+
+} // namespace oracle

@@ -54,6 +54,8 @@ std::string reverse_complement(const std::string& s) {
     return r;
 }
 
+} // namespace
+
 // EditAlignmentScorer::longest_detectable_gap(read_length, read_pos), alignment_scorer.cpp:264-271
 size_t longest_detectable_gap(const gb_scores& s, size_t read_length, size_t read_pos) {
     int64_t overhang_length = std::min(read_pos, read_length - read_pos);
@@ -61,8 +63,6 @@ size_t longest_detectable_gap(const gb_scores& s, size_t read_length, size_t rea
     int64_t gap_length = (numer - s.gap_open) / s.gap_extend + 1;
     return gap_length >= 0 && overhang_length > 0 ? (size_t)gap_length : 0;
 }
-
-} // namespace
 
 // ---------------------------------------------------------------------------------------
 // xdrop_pinned

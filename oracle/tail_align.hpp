@@ -37,8 +37,14 @@ struct PinnedAlignment {
     std::vector<Mapping> path;   // Mapping.node = tree index + 1 (TreeSubgraph id), offsets in trimmed coordinates
 };
 
-// Result of the DAG aligners (xdrop_dag.cpp): Mapping.node = index into the problem's node list.
+// A read-vs-DAG alignment problem (full_dp.cpp, xdrop_dag.cpp): oriented graph nodes in topological order
+// and, per node, the indices of its predecessors.  Results carry Mapping.node = index into `node`.
+struct DagProblem { std::vector<uint32_t> node; std::vector<std::vector<uint32_t>> pred; };
 struct LocalAlignmentResult { int32_t score = 0; std::vector<Mapping> path; };
+LocalAlignmentResult sw_local_dag(const Graph& g, const gb_scores& sc, const DagProblem& P, const std::string& q, uint64_t* cells);
+LocalAlignmentResult align_xdrop_dag(const Graph& g, const gb_scores& sc, const DagProblem& P, const std::string& query,
+                                     bool has_seed, uint32_t seed_u, uint32_t seed_o, uint32_t seed_q, uint32_t max_gap, uint64_t* cells);
+size_t longest_detectable_gap(const gb_scores& s, size_t read_length, size_t read_pos);
 
 // The X-drop DP contract (see tail_align.cpp for the full statement).
 PinnedAlignment xdrop_pinned(const Graph& g, const gb_scores& scores, const TailTree& tree,

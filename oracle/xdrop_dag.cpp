@@ -227,10 +227,9 @@ PassResult scan_local(const OrientedDag& dag, const gb_scores& sc, const std::st
 } // namespace xd
 using namespace xd;
 
-struct DagProblem2 { std::vector<uint32_t> node; std::vector<std::vector<uint32_t>> pred; };
 
 // Returns score 0 and an empty path when nothing aligns.
-LocalAlignmentResult align_xdrop_dag(const Graph& g, const gb_scores& sc, const DagProblem2& P, const std::string& query,
+LocalAlignmentResult align_xdrop_dag(const Graph& g, const gb_scores& sc, const DagProblem& P, const std::string& query,
                                      bool has_seed, uint32_t seed_u, uint32_t seed_o, uint32_t seed_q, uint32_t max_gap, uint64_t* cells) {
     LocalAlignmentResult out;
     const size_t N = P.node.size(), m = query.size();
@@ -330,7 +329,7 @@ extern "C" int oracle_xdrop_dag(const gb_flat_index* ix, const gb_scores* scores
                                 int32_t* score_out, gb_mapping* mappings, uint32_t mapping_cap, uint32_t* n_mappings,
                                 uint32_t* edits, uint32_t edit_cap, uint32_t* n_edits, uint64_t* cells_out) {
     oracle::Graph g(ix);
-    oracle::DagProblem2 P;
+    oracle::DagProblem P;
     P.node.assign(node, node + n_nodes); P.pred.resize(n_nodes);
     for (uint32_t u = 0; u < n_nodes; u++) P.pred[u].assign(pred + pred_off[u], pred + pred_off[u + 1]);
     uint64_t cells = 0;

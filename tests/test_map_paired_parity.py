@@ -31,15 +31,46 @@ def test_oracle_pairs_map_to_their_origin():
     assert (strands[0::2] != strands[1::2]).all()
 
 
-def test_paired_refuses_rescue_configuration():
-    g = synth.make_tiny_graph()
+def _wrecked_pairs(n_pairs=300, seed=61):
+    g = synth.make_variant_graph(length=100000, n_snp=160, n_ins=20, n_del=20, n_haps=8, seed=5)
+    rs = synth.simulate_pairs(g, n_pairs, sub_rate=0.01, seed=seed)
+    rng = np.random.default_rng(2)
+    wrecked = np.arange(1, rs.n, 6)                 # mate 2 of every third pair gets 12 % substitutions: few or no seeds
+    for i in wrecked:
+        m = rng.random(rs.length) < 0.12
+        rs.reads[i, m] = synth.BASES[rng.integers(0, 4, size=int(m.sum()))]
+    return g, rs, wrecked
+
+
+def test_oracle_rescue_recovers_mates_without_seeds():
+    """attempt_rescue (minimizer_mapper.cpp:3264-3482) in the oracle: mates too noisy to seed are found next to
+    their partner; the rescued records are internally consistent."""
+    g, rs, wrecked = _wrecked_pairs()
     index = g.build_index()
-    rs = synth.simulate_pairs(g, 4, frag_mean=300, frag_sd=20, sub_rate=0.0, seed=1)
-    p = H.paired_params(300, 20)
-    p.max_rescue_attempts = 15
-    lib = H.oracle_lib()
-    with pytest.raises(AssertionError):
-        H.oracle_map_paired(index, rs.reads, rs.quals, p)
+    p0 = H.paired_params(); p15 = H.paired_params(); p15.max_rescue_attempts = 15
+    a0 = H.oracle_map_paired(index, rs.reads, rs.quals, p0, threads=8)
+    a15 = H.oracle_map_paired(index, rs.reads, rs.quals, p15, threads=8)
+    m0, m15 = (a0[0]["flags"] & 1), (a15[0]["flags"] & 1)
+    assert m0[wrecked].mean() < 0.5 and m15[wrecked].mean() > 0.85
+    rescued = np.nonzero(a15[0]["flags"] & capi.GB_ALN_RESCUED)[0]
+    assert len(rescued) >= 50 and a15[4]["rescues"] >= len(rescued)
+    for i in rescued:
+        score, mapq, path = H.decode_alignment(a15[0][i], a15[1], a15[2])
+        if not path:
+            continue
+        assert sum(e[1] for m in path for e in m[2] if e[0] in "MSI") == rs.length
+        if score < 50:
+            continue          # short chance matches pass the reference's likelihood filter too (:3451-3481)
+        # a real rescue: the partner is mapped on the other strand nearby
+        mate = i ^ 1
+        assert a15[0][mate]["flags"] & 1
+        _, _, mpath = H.decode_alignment(a15[0][mate], a15[1], a15[2])
+        assert (path[0][0] & 1) != (mpath[0][0] & 1)
+        assert abs((path[0][0] >> 1) - (mpath[0][0] >> 1)) < 200          # node ids grow along the chain
+    # pairs that needed no rescue come out the same with and without it
+    clean = [i for i in range(rs.n) if (i | 1) not in set(wrecked.tolist())]
+    same = sum(H.decode_alignment(a0[0][i], a0[1], a0[2]) == H.decode_alignment(a15[0][i], a15[1], a15[2]) for i in clean)
+    assert same >= 0.97 * len(clean)
 
 
 @pytest.mark.gpu

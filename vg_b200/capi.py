@@ -18,6 +18,7 @@ GB_OK = 0
 GB_ERR_ARG, GB_ERR_CUDA, GB_ERR_NO_DEVICE, GB_ERR_CAPACITY, GB_ERR_FORMAT = -1, -2, -3, -4, -5
 GB_ITEM_OK, GB_ITEM_QUEUE_FULL, GB_ITEM_OUT_FULL, GB_ITEM_DP_REFUSED = 0, 1, 2, 3
 GB_EXT_LEFT_FULL, GB_EXT_RIGHT_FULL = 1, 2
+GB_ALN_MAPPED, GB_ALN_SECONDARY, GB_ALN_PAIRED, GB_ALN_RESCUED = 1, 2, 4, 8
 
 # numpy mirrors of the ABI structs
 node_rec_dt = np.dtype([("seq_off", "<u4"), ("rec_off", "<u4"), ("len", "<u4"), ("size", "<u4")])
@@ -82,6 +83,7 @@ class MapParams(C.Structure):
         ("fragment_mean", C.c_double), ("fragment_stdev", C.c_double), ("paired_distance_stdevs", C.c_double),
         ("paired_rescue_score_limit", C.c_double), ("rescue_subgraph_stdevs", C.c_double),
         ("max_rescue_attempts", C.c_uint32), ("max_fragment_length", C.c_uint32),
+        ("rescue_seed_limit", C.c_uint32), ("reserved0", C.c_uint32), ("rescue_likelihood_limit", C.c_double),
         ("mapping_cap_per_read", C.c_uint32), ("edit_cap_per_read", C.c_uint32),
     ]
 

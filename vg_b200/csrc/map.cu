@@ -165,6 +165,7 @@ extern "C" void gb_map_params_default(gb_map_params* p) {
     p->max_dozeu_cells = (uint32_t)(1.5 * 1024 * 1024); p->do_dp = 1;
     p->paired_distance_stdevs = 2.0; p->paired_rescue_score_limit = 0.9; p->rescue_subgraph_stdevs = 4.0;
     p->max_rescue_attempts = 15; p->max_fragment_length = 2000;
+    p->rescue_seed_limit = 100; p->reserved0 = 0; p->rescue_likelihood_limit = 0.05;
     p->mapping_cap_per_read = 96; p->edit_cap_per_read = 160;
 }
 
