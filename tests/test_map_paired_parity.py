@@ -1,4 +1,4 @@
-"""MinimizerMapper::map_paired parity (forced fragment distribution, rescue attempts 0):
+"""MinimizerMapper::map_paired parity (forced fragment distribution, with and without mate rescue):
 gb_map_paired_batch on the GPU vs the oracle restatement, BASELINE.json configs[1] family."""
 import numpy as np
 import pytest
@@ -103,16 +103,24 @@ def test_map_paired_parity_branchy_graph():
 
 
 @pytest.mark.gpu
-def test_paired_rescue_is_refused_loudly():
-    g = synth.make_tiny_graph()
-    index = g.build_index()
-    dev = capi.Device(index)
-    rs = synth.simulate_pairs(g, 4, frag_mean=300, frag_sd=20, sub_rate=0.0, seed=1)
-    p = H.paired_params(300, 20)
-    p.max_rescue_attempts = 15
-    with pytest.raises(capi.GbError):
-        H.gpu_map(dev, rs.reads, rs.quals, p, paired=True)
-    dev.close()
+@pytest.mark.parametrize("attempts", [15, 2])
+def test_map_paired_parity_with_mate_rescue(attempts):
+    """max_rescue_attempts != 0: attempt_rescue (minimizer_mapper.cpp:3264-3482) and the rescue branch of
+    map_paired (:2288-2457, multiplicities :2661-2690) on the GPU vs the oracle."""
+    g, rs, wrecked = _wrecked_pairs()
+    p = H.paired_params(); p.max_rescue_attempts = attempts
+    got, want = _run(g, rs, p)
+    assert ((got[0]["flags"] & capi.GB_ALN_RESCUED) == (want[0]["flags"] & capi.GB_ALN_RESCUED)).all()
+    assert (got[0]["flags"] & capi.GB_ALN_RESCUED).sum() >= 50
+
+
+@pytest.mark.gpu
+def test_map_paired_rescue_on_clean_pairs_matches_no_rescue_path():
+    """Pairs whose mates both cluster go through the thread-per-pair fast path even with rescue enabled."""
+    g = synth.make_variant_graph(length=200000, n_snp=320, n_ins=40, n_del=40, n_haps=8, seed=2)
+    rs = synth.simulate_pairs(g, 2000, sub_rate=0.02, seed=23)
+    p = H.paired_params(); p.max_rescue_attempts = 15
+    _run(g, rs, p)
 
 
 @pytest.mark.gpu

@@ -202,6 +202,7 @@ __device__ inline bool fast_pair(const DevIndex& ix, const MapParamsDev& P, cons
         }
     }
     bool done = false;
+    if (n_unpaired > 0 && P.max_rescue_attempts != 0) return false;     // mate rescue is warp work
     if (n_unpaired > 0 && !found_pair) {
         int best_c[2] = {-1, -1}; int32_t best_score[2] = {0, 0};
         for (uint32_t u = 0; u < n_unpaired; u++) {

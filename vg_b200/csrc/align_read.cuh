@@ -18,9 +18,11 @@ struct AlignArgs {
     const PairState* pairs; double frag_mean, frag_sd;
     // work list written by the thread-per-pair fast path (nullptr: every pair)
     const uint32_t* slow_list; const uint32_t* slow_count;
+    // mate rescue (max_rescue_attempts != 0): per-warp workspace
+    uint8_t* rescue_base; size_t rescue_stride;
 };
 
-constexpr uint32_t N_SLOTS = 2 * MAX_CANDS + 8;   // candidate path slots per warp (both mates of a pair)
+constexpr uint32_t N_SLOTS = 2 * MAX_CANDS + 8 + 32;   // candidate path slots per warp (both mates of a pair, + rescued alignments)
 constexpr uint32_t N_TEMP_SLOTS = 4;              // res_left, res_right, scratch, middle
 
 __device__ __forceinline__ double d_add_log(double x, double y) { return x > y ? x + log1p(exp(y - x)) : y + log1p(exp(x - y)); }
@@ -126,10 +128,10 @@ __device__ inline double max_mapping_quality(const double* scores, uint32_t n, d
 }
 
 struct CandList {
-    int32_t score[2 * MAX_CANDS];
-    uint8_t slot[2 * MAX_CANDS];
-    uint8_t frag[2 * MAX_CANDS];
-    uint8_t read[2 * MAX_CANDS];
+    int32_t score[2 * MAX_CANDS + 32];       // + rescued alignments
+    uint8_t slot[2 * MAX_CANDS + 32];
+    uint8_t frag[2 * MAX_CANDS + 32];
+    uint8_t read[2 * MAX_CANDS + 32];
     uint32_t n;
 };
 

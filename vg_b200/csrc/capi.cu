@@ -139,6 +139,20 @@ extern "C" int gb_device_create(const gb_flat_index* ix, int device_ordinal, gb_
     if ((rc = d->table.upload(ix->table, ix->table_cells, d->stream))) return rc;
     if ((rc = d->hits.upload(ix->hits, ix->n_hits ? ix->n_hits : 1, d->stream, ix->n_hits))) return rc;
     GB_CUDA(cudaStreamSynchronize(d->stream));
+    {
+        // ids in chain order (the rescue subgraph is cut from it, minimizer_mapper.cpp:3364)
+        std::vector<uint32_t> order;
+        for (uint32_t id = 1; id < ix->n_nodes / 2; id++) if (ix->nodes[2 * id].len > 0) order.push_back(id);
+        std::sort(order.begin(), order.end(), [&](uint32_t a, uint32_t b) {
+            const gb_dist_payload& pa = ix->dist[a]; const gb_dist_payload& pb = ix->dist[b];
+            if (pa.component != pb.component) return pa.component < pb.component;
+            if (pa.slot != pb.slot) return pa.slot < pb.slot;
+            return a < b;
+        });
+        if ((rc = d->slot_order.upload(order.data(), order.size() ? order.size() : 1, d->stream, order.size()))) return rc;
+        GB_CUDA(cudaStreamSynchronize(d->stream));
+        d->ix.slot_order = d->slot_order.ptr; d->ix.n_ids = (uint32_t)order.size();
+    }
     d->h_node_len.resize(ix->n_nodes);
     for (uint32_t v = 0; v < ix->n_nodes; v++) d->h_node_len[v] = ix->nodes[v].len;
     d->ix.nodes = d->nodes.ptr; d->ix.seq = d->seq.ptr; d->ix.gbwt = d->gbwt.ptr; d->ix.dist = d->dist.ptr;

@@ -26,6 +26,8 @@ struct DevIndex {
     const gb_hit* hits;
     uint64_t table_mask;
     uint32_t n_nodes, k, w;
+    const uint32_t* slot_order;      // node ids sorted by (component, slot, id): a topological order of each chain
+    uint32_t n_ids;
 };
 
 struct DevScores { int match, mismatch, gap_open, gap_extend, full_length_bonus; };

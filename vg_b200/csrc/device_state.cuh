@@ -75,6 +75,7 @@ struct gb_device {
     gb::DevBuf<gb_dist_payload> dist;
     gb::DevBuf<gb_min_cell> table;
     gb::DevBuf<gb_hit> hits;
+    gb::DevBuf<uint32_t> slot_order;
     gb::DevBuf<gb::QEntry> ws_queue;
     gb::DevBuf<gb::ArenaNode> ws_arena;
     uint32_t* work_counter = nullptr;
@@ -91,7 +92,7 @@ struct gb_device {
     gb::DevBuf<uint32_t> p_cursors, p_ext_count, p_path, p_mism;
     gb::DevBuf<uint8_t> p_ext_status;
     gb::DevBuf<gb_extension> p_ext;
-    gb::DevBuf<uint8_t> ws_tail, ws_cand, w_reads, w_quals;
+    gb::DevBuf<uint8_t> ws_tail, ws_cand, w_reads, w_quals, ws_rescue;
     gb::DevBuf<gb::PairState> p_pairs;
     gb::DevBuf<uint32_t> p_retry;         // units the first seeding pass could not fit
     gb::DevBuf<uint32_t> p_slow;          // pairs routed to the warp-per-pair align kernel
@@ -115,11 +116,11 @@ struct gb_device {
     gb::DevBuf<uint64_t> c_run;            // running mapping / edit totals of a host-buffer call
     uint32_t map_chunk = 1u << 20;         // reads per chunk; GIRAFFE_B200_MAP_CHUNK overrides
     void release_all() {
-        nodes.release(); seq.release(); gbwt.release(); dist.release(); table.release(); hits.release();
+        nodes.release(); seq.release(); gbwt.release(); dist.release(); table.release(); hits.release(); slot_order.release();
         ws_queue.release(); ws_arena.release();
         t_hit.release(); t_plo.release(); t_phred.release(); p_states.release(); p_min.release(); p_seeds.release();
         p_items.release(); p_ext_seeds.release(); p_cursors.release(); p_ext_count.release(); p_path.release(); p_mism.release();
-        p_ext_status.release(); p_ext.release(); ws_tail.release(); ws_cand.release(); w_reads.release(); w_quals.release(); p_pairs.release(); p_slow.release(); p_retry.release();
+        p_ext_status.release(); p_ext.release(); ws_tail.release(); ws_cand.release(); ws_rescue.release(); w_reads.release(); w_quals.release(); p_pairs.release(); p_slow.release(); p_retry.release();
         pad_maps.release(); pad_edits.release(); c_map_off.release(); c_edit_off.release(); c_totals.release(); c_tmp.release();
         io[0].release(); io[1].release(); c_run.release();
     }

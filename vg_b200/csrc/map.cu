@@ -7,6 +7,8 @@
 #include "device_state.cuh"
 #include "seed.cuh"
 #include "align.cuh"
+#include "extend.cuh"
+#include "dag_dp.cuh"
 
 #include <algorithm>
 #include <cfloat>
@@ -133,6 +135,7 @@ align_kernel(DevIndex ix, MapParamsDev P, DevScores sc, MapBatch b, AlignArgs a)
     }
 }
 
+#include "rescue.cuh"
 #include "map_paired.cuh"
 #include "align_fast.cuh"
 #include "compact.cuh"
@@ -183,7 +186,7 @@ int map_device(gb_device* d, const gb_map_params* hp, uint32_t n_reads, const ui
     gb_mapping* d_maps = d->pad_maps.ptr; uint32_t* d_edits = d->pad_edits.ptr;
     if (paired) {
         if (n_reads % 2 != 0) { g_last_error = "paired mapping needs an even number of reads"; return GB_ERR_ARG; }
-        if (hp->max_rescue_attempts != 0) { g_last_error = "paired mapping is built for max_rescue_attempts = 0 (vg giraffe --rescue-attempts 0); rescue is not implemented"; return GB_ERR_ARG; }
+        if (hp->max_rescue_attempts != 0 && hp->rescue_seed_limit >= RESCUE_SEEDS) { g_last_error = "rescue_seed_limit must be below 128"; return GB_ERR_ARG; }
         if (!(hp->fragment_stdev > 0)) { g_last_error = "paired mapping needs a forced fragment length distribution"; return GB_ERR_ARG; }
     }
     if (hp->max_multimaps != 1) { g_last_error = "only max_multimaps = 1 is supported"; return GB_ERR_ARG; }
@@ -216,6 +219,9 @@ int map_device(gb_device* d, const gb_map_params* hp, uint32_t n_reads, const ui
     P.max_extension_mismatches = hp->max_extension_mismatches; P.max_dozeu_cells = hp->max_dozeu_cells; P.do_dp = hp->do_dp;
     P.mapping_cap = hp->mapping_cap_per_read; P.edit_cap = hp->edit_cap_per_read;
     P.log_base = recover_log_base(d->sc);
+    P.max_rescue_attempts = paired ? hp->max_rescue_attempts : 0; P.rescue_seed_limit = hp->rescue_seed_limit;
+    P.paired_rescue_score_limit = hp->paired_rescue_score_limit; P.rescue_subgraph_stdevs = hp->rescue_subgraph_stdevs;
+    P.rescue_likelihood_limit = hp->rescue_likelihood_limit;
     P.hit_score_table = d->t_hit.ptr; P.prob_at_least_one = d->t_plo.ptr; P.phred_prob = d->t_phred.ptr;
 
     // ---- pools ----
@@ -312,13 +318,17 @@ int map_device(gb_device* d, const gb_map_params* hp, uint32_t n_reads, const ui
         const size_t smem = per_warp * ALIGN_WARPS;
         if (smem > 48 * 1024) {
             GB_CUDA(cudaFuncSetAttribute(align_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-            GB_CUDA(cudaFuncSetAttribute(align_kernel_pe, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            GB_CUDA(cudaFuncSetAttribute(align_kernel_pe<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            GB_CUDA(cudaFuncSetAttribute(align_kernel_pe<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         }
         int bps = 0;
-        if (paired) GB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bps, align_kernel_pe, ALIGN_WARPS * 32, smem));
+        const bool rescue = paired && hp->max_rescue_attempts != 0;
+        if (rescue) GB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bps, align_kernel_pe<true>, ALIGN_WARPS * 32, smem));
+        else if (paired) GB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bps, align_kernel_pe<false>, ALIGN_WARPS * 32, smem));
         else GB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bps, align_kernel, ALIGN_WARPS * 32, smem));
         if (bps < 1) bps = 1;
         if (bps > 4) bps = 4;          // bounds the per-warp tail workspaces (about 2 MB each)
+        if (rescue && bps > 2) bps = 2;   // + the rescue workspaces (about 2 MB each)
         uint32_t grid = std::min<uint32_t>((uint32_t)(d->n_sms * bps), (n_reads + ALIGN_WARPS - 1) / ALIGN_WARPS);
         if (grid == 0) grid = 1;
         const size_t n_warps = (size_t)grid * ALIGN_WARPS;
@@ -328,6 +338,12 @@ int map_device(gb_device* d, const gb_map_params* hp, uint32_t n_reads, const ui
         if ((rc = d->ws_tail.reserve(ws_stride * n_warps))) return rc;
         if ((rc = d->ws_cand.reserve(cand_stride * n_warps))) return rc;
         AlignArgs a;
+        a.rescue_base = nullptr; a.rescue_stride = 0;
+        if (rescue) {
+            a.rescue_stride = (rescue_ws_bytes(Lc) + 255) & ~(size_t)255;
+            if ((rc = d->ws_rescue.reserve(a.rescue_stride * n_warps))) return rc;
+            a.rescue_base = d->ws_rescue.ptr;
+        }
         a.items = d->p_items.ptr; a.minimizers = d->p_min.ptr;
         a.ev.ext_count = d->p_ext_count.ptr; a.ev.ext_status = d->p_ext_status.ptr; a.ev.ext = d->p_ext.ptr;
         a.ev.path_pool = d->p_path.ptr; a.ev.mism_pool = d->p_mism.ptr; a.ev.max_ext = max_ext; a.ev.path_cap = path_cap; a.ev.mism_cap = mism_cap;
@@ -346,7 +362,8 @@ int map_device(gb_device* d, const gb_map_params* hp, uint32_t n_reads, const ui
         d->launches++;
         GB_CUDA(cudaGetLastError());
         a.slow_list = d->p_slow.ptr; a.slow_count = cur + 7;
-        if (paired) align_kernel_pe<<<grid, ALIGN_WARPS * 32, smem, d->stream>>>(d->ix, P, d->sc, b3, a);
+        if (rescue) align_kernel_pe<true><<<grid, ALIGN_WARPS * 32, smem, d->stream>>>(d->ix, P, d->sc, b3, a);
+        else if (paired) align_kernel_pe<false><<<grid, ALIGN_WARPS * 32, smem, d->stream>>>(d->ix, P, d->sc, b3, a);
         else align_kernel<<<grid, ALIGN_WARPS * 32, smem, d->stream>>>(d->ix, P, d->sc, b3, a);
         d->launches++;
         GB_CUDA(cudaGetLastError());

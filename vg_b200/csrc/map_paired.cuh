@@ -99,7 +99,8 @@ seed_kernel_pe(DevIndex ix, MapParamsDev P, MapBatch b, SeedPools pools, PairBat
     }
 }
 
-__global__ void __launch_bounds__(ALIGN_WARPS * 32, 4)
+template <bool RESCUE>
+__global__ void __launch_bounds__(ALIGN_WARPS * 32, RESCUE ? 2 : 4)
 align_kernel_pe(DevIndex ix, MapParamsDev P, DevScores sc, MapBatch b, AlignArgs a) {
     extern __shared__ __align__(16) uint8_t smem[];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -155,7 +156,11 @@ align_kernel_pe(DevIndex ix, MapParamsDev P, DevScores sc, MapBatch b, AlignArgs
             if (status == GB_ITEM_OK) {
                 const uint8_t* sr[2] = {sread[0], sread[1]};
                 const uint8_t* sq[2] = {b.quals ? squal[0] : nullptr, b.quals ? squal[1] : nullptr};
-                status = finalize_pe(ix, P, rs, ps, a, cl, explored, rng, sr, sq, L, 2 * p, dps, cand_base, out, out_maps, out_edits);
+                if constexpr (RESCUE) {
+                    const RescueWs rw = carve_rescue_ws(a.rescue_base + (size_t)gwarp * a.rescue_stride, b.Lc);
+                    status = finalize_pe_rescue(ix, P, sc, rs, ps, a, cl, explored, rng, sr, sq, L, 2 * p, dps, qbuf, cand_base, slot_used, rw, b.Lc, out, out_maps, out_edits);
+                } else
+                    status = finalize_pe(ix, P, rs, ps, a, cl, explored, rng, sr, sq, L, 2 * p, dps, cand_base, out, out_maps, out_edits);
             }
         }
         for (uint32_t r = 0; r < 2; r++) {

@@ -94,6 +94,8 @@ struct MapParamsDev {
     int32_t  extension_score_threshold, min_extension_sets, extension_set_min_score;
     uint32_t max_alignments, max_extension_mismatches, max_dozeu_cells, do_dp;
     uint32_t mapping_cap, edit_cap;
+    uint32_t max_rescue_attempts, rescue_seed_limit;
+    double   paired_rescue_score_limit, rescue_subgraph_stdevs, rescue_likelihood_limit;
     double   log_base;
     const double* hit_score_table;        // [hard_hit_cap + 1]: score for a hit count (host libm)
     const double* prob_at_least_one;      // [(32 + 1) * 256]   (statistics.cpp:525-560)

@@ -465,7 +465,7 @@ __device__ __forceinline__ uint32_t seed_phase_a(const DevIndex& ix, const MapPa
     for (uint32_t i = lane; i < M; i += 32) {
         const uint32_t a = sm.m_order[i];
         DevMinimizer dm; dm.hash = sm.m_hash[a]; dm.score = sm.m_score[a]; dm.fwd_offset = sm.m_fwd[a];
-        dm.agg_start = sm.m_agg_start[a]; dm.agg_len = sm.m_agg_len[a]; dm.is_reverse = sm.m_rev[a]; dm.pad[0] = dm.pad[1] = 0;
+        dm.agg_start = sm.m_agg_start[a]; dm.agg_len = sm.m_agg_len[a]; dm.is_reverse = sm.m_rev[a]; dm.pad[0] = sm.m_hit_off[a]; dm.pad[1] = sm.m_hit_cnt[a];     // hit list (seeds_in_subgraph of mate rescue)
         pools.minimizers[min_off + i] = dm;
     }
     rs.min_off = min_off; rs.min_cnt = M;
