@@ -115,6 +115,49 @@ def test_map_paired_parity_with_mate_rescue(attempts):
 
 
 @pytest.mark.gpu
+def test_map_paired_rescue_parity_with_indels_odd_fragments_and_garbage_mates():
+    """Rescue alignments that need the gapped aligner (indels in the rescued mate), improper fragments
+    (rescue window misses) and random mates (rescue finds nothing / chance matches)."""
+    g = synth.make_variant_graph(length=100000, n_snp=160, n_ins=20, n_del=20, n_haps=8, seed=21)
+    rs = synth.simulate_pairs(g, 1500, frag_mean=400, frag_sd=150, sub_rate=0.01, seed=9)
+    rng = np.random.default_rng(3)
+    for i in rng.integers(0, rs.n, size=400):
+        p = int(rng.integers(10, 140))
+        rs.reads[i, p:-1] = rs.reads[i, p + 1:]
+        m = rng.random(rs.length) < 0.08                       # and too noisy to seed
+        rs.reads[i, m] = synth.BASES[rng.integers(0, 4, size=int(m.sum()))]
+    for i in rng.integers(0, rs.n, size=60):
+        rs.reads[i] = synth.BASES[rng.integers(0, 4, size=rs.length)]
+    p = H.paired_params(); p.max_rescue_attempts = 15
+    got, want = _run(g, rs, p)
+    assert (got[0]["flags"] & capi.GB_ALN_RESCUED).sum() >= 100
+
+
+@pytest.mark.gpu
+def test_map_paired_rescue_parity_branchy_graph():
+    """Short nodes, many alleles: big rescue subgraphs.  Pairs whose subgraph exceeds the per-warp rescue
+    workspace report GB_ITEM_OUT_FULL (the caller re-maps those on the CPU); everything else is identical."""
+    g = synth.make_branchy_graph(n_layers=4000, n_haps=16, seed=4)
+    rs = synth.simulate_pairs(g, 600, sub_rate=0.005, seed=44)
+    rng = np.random.default_rng(5)
+    for i in range(1, rs.n, 4):
+        m = rng.random(rs.length) < 0.12
+        rs.reads[i, m] = synth.BASES[rng.integers(0, 4, size=int(m.sum()))]
+    index = g.build_index()
+    dev = capi.Device(index)
+    p = H.paired_params(); p.max_rescue_attempts = 15
+    got = H.gpu_map(dev, rs.reads, rs.quals, p, paired=True)
+    want = H.oracle_map_paired(index, rs.reads, rs.quals, p, threads=8)
+    dev.close()
+    assert set(np.unique(got[3]).tolist()) <= {0, capi.GB_ITEM_OUT_FULL}
+    ok = np.nonzero(got[3] == 0)[0]
+    assert len(ok) >= 0.9 * rs.n
+    bad = H.compare_alignments(got, want, rs.n, indices=ok.tolist())
+    assert not bad, f"{len(bad)} of {len(ok)} reads differ; first: read {bad[0][0]}\n got={bad[0][1]}\nwant={bad[0][2]}"
+    assert (got[0]["flags"][ok] & capi.GB_ALN_RESCUED).sum() >= 20
+
+
+@pytest.mark.gpu
 def test_map_paired_rescue_on_clean_pairs_matches_no_rescue_path():
     """Pairs whose mates both cluster go through the thread-per-pair fast path even with rescue enabled."""
     g = synth.make_variant_graph(length=200000, n_snp=320, n_ins=40, n_del=40, n_haps=8, seed=2)
