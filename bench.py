@@ -250,6 +250,7 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--reads", type=int, default=10_000_000, help="reads (not pairs) per GPU per step")
     ap.add_argument("--cpu-seconds", type=float, default=15.0)
+    ap.add_argument("--rescue-attempts", type=int, default=15, help="MinimizerMapper::max_rescue_attempts (vg giraffe default 15)")
     args = ap.parse_args()
 
     rank = int(os.environ.get("RANK", "0"))
@@ -266,6 +267,7 @@ def main():
             return 0
         g, index = make_graph_and_index()
         params = H.paired_params(FRAG_MEAN, FRAG_SD)
+        params.max_rescue_attempts = args.rescue_attempts
         lib, flags = oracle_library()
         threads, cpu_note = usable_cpus()
         sample = min(n_reads, 4_000_000)
@@ -284,7 +286,7 @@ def main():
             "impl": "reference", "metric": "giraffe reads/sec (150 bp PE, synthetic)", "value": value, "unit": "reads/s",
             "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "int32", "data": "synthetic",
-            "config": {"workload": "configs[1]: 1 Mbp / 1k-variant graph, 150 bp PE reads, fragment N(400,50) forced, rescue attempts 0",
+            "config": {"workload": "configs[1]: 1 Mbp / 1k-variant graph, 150 bp PE reads, fragment N(400,50) forced, rescue attempts " + str(args.rescue_attempts),
                        "reads_per_step": used, "note": "CPU restatement of vg giraffe (oracle/, OpenMP over read pairs); vg itself cannot be built in this image"},
             "cpu_baseline": {"value": value, "unit": "reads/s", "cores": threads, "kind": "port", "sample": f"{used} reads per step, {flags}, {cpu_note}"},
             "e2e": {"value": value, "unit": "reads/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
@@ -309,6 +311,7 @@ def main():
     dev = capi.Device(index, local_rank)
     lib = capi.load_library()
     params = H.paired_params(FRAG_MEAN, FRAG_SD)
+    params.max_rescue_attempts = args.rescue_attempts
     stream = torch.cuda.Stream(device=device)          # the library's kernels and torch's events share this stream
     torch.cuda.set_stream(stream)
     lib.gb_device_set_stream(dev.handle, C.c_void_p(stream.cuda_stream))
@@ -485,7 +488,7 @@ def main():
             "workload": "configs[1]: 1 Mbp random graph, 1k SNP+indel variants, 8 haplotypes, nodes <= 32 bp, k=29 w=11; "
                         "150 bp paired-end reads, fragment N(400,50) forced, 0.2 % substitutions",
             "reads_per_gpu_per_step": n_reads, "pairs_per_gpu_per_step": n_reads // 2,
-            "mapper": "map_paired, vg giraffe defaults except --rescue-attempts 0 (attempt_rescue not built this round)",
+            "mapper": f"map_paired, vg giraffe defaults (--rescue-attempts {args.rescue_attempts}), forced fragment distribution",
             "chunk_reads": CHUNK, "l2_policy": "inputs larger than L2 (3 GB of reads+qualities per step)",
             "mapped_fraction": mapped_frac, "mapq60_fraction": mapq60, "status_errors": status_bad,
             "parity_vs_cpu_sample": {"reads_checked": check_n, "mismatching_reads": len(bad)},

@@ -299,9 +299,12 @@ int gb_map_batch(gb_device* dev, const gb_map_params* p,
  * (`vg giraffe --fragment-mean M --fragment-stdev S`).  Reads are interleaved: read 2i is
  * mate 1 and read 2i+1 mate 2 of pair i, both in sequencer (inward) orientation; outputs are
  * per read as in gb_map_batch, mate 2 reported in its input orientation, flags |= GB_ALN_PAIRED.
- * This round builds the configuration p->max_rescue_attempts == 0 (`--rescue-attempts 0`,
- * reference branch :2238-2287); any other value is refused with GB_ERR_ARG because
- * attempt_rescue (:3264-3565) is not implemented yet. */
+ * p->max_rescue_attempts == 0 takes the reference branch :2238-2287; otherwise unpaired
+ * alignments rescue their mates (attempt_rescue :3264-3565 with rescue_algorithm dozeu and the
+ * full-DP fallback of fix_dozeu_score; pairing / multiplicities / caps :2288-2777) and rescued
+ * records carry GB_ALN_RESCUED.  A rescue subgraph larger than the per-warp workspace (320 nodes,
+ * 6144 bases of both orientations, 127 seeds) sets status GB_ITEM_OUT_FULL for both mates of that
+ * pair; rescue_seed_limit must be below 128. */
 int gb_map_paired_batch(gb_device* dev, const gb_map_params* p,
                         uint32_t n_reads, const uint8_t* reads, const uint8_t* quals, const uint64_t* read_off,
                         gb_alignment* aln, gb_mapping* mappings, uint64_t mapping_pool_cap, uint32_t* edits, uint64_t edit_pool_cap,
