@@ -310,6 +310,42 @@ int gb_map_paired_batch(gb_device* dev, const gb_map_params* p,
                         gb_alignment* aln, gb_mapping* mappings, uint64_t mapping_pool_cap, uint32_t* edits, uint64_t edit_pool_cap,
                         uint8_t* status, uint64_t* n_mappings_used, uint64_t* n_edits_used);
 
+/* ---- fragment length distribution and the whole paired job --------------------------------
+ * FragmentLengthDistribution (mapper.hpp:83-139, mapper.cpp:5231-5333): robust running estimate
+ * of the fragment length; MinimizerMapper owns one as fragment_length_distr(1000, 1000, 0.95)
+ * (minimizer_mapper.cpp:72).  Host-side state, no device work. */
+typedef struct gb_fragment_distribution gb_fragment_distribution;
+gb_fragment_distribution* gb_fragment_create(uint64_t maximum_sample_size, uint64_t reestimation_frequency,
+                                             double robust_estimation_fraction);
+void     gb_fragment_destroy(gb_fragment_distribution* f);
+void     gb_fragment_force(gb_fragment_distribution* f, double mean, double stdev);   /* force_parameters, mapper.cpp:5250 */
+void     gb_fragment_register(gb_fragment_distribution* f, int64_t length);           /* register_fragment_length, :5256  */
+void     gb_fragment_finalize(gb_fragment_distribution* f);     /* finalize_fragment_length_distr, minimizer_mapper.hpp:539 */
+double   gb_fragment_mean(const gb_fragment_distribution* f);
+double   gb_fragment_stdev(const gb_fragment_distribution* f);
+int      gb_fragment_is_finalized(const gb_fragment_distribution* f);
+uint64_t gb_fragment_sample_size(const gb_fragment_distribution* f);
+
+#define GB_PAIR_PAIRED   0u   /* map_paired with the finalized distribution                              */
+#define GB_PAIR_TRAINING 1u   /* both ends mapped single-ended, their distance registered (:1303-1386)   */
+#define GB_PAIR_BUFFERED 2u   /* ambiguous while training (ambiguous_pair_buffer), mapped paired at end  */
+
+/* The paired job as `vg giraffe` runs it without --fragment-mean/--fragment-stdev
+ * (giraffe_main.cpp:2246-2400): while `f` is not finalized, pairs are taken in input order through
+ * MinimizerMapper::map_paired(aln1, aln2, ambiguous_pair_buffer) (minimizer_mapper.cpp:1303-1395) —
+ * both ends mapped single-ended on the GPU (training_window pairs per gb_map_batch call; pairs of a
+ * window behind the finalizing pair are not consumed), pairs whose ends are both MAPQ 60 with score >=
+ * 0.85 * match * length and whose distance is below max_fragment_length register it and keep their
+ * single-ended records, every other pair is buffered; once finalized (or, at the end of the input,
+ * finalized by force as giraffe_main.cpp:2283-2296 does) all remaining and all buffered pairs go through
+ * gb_map_paired_batch with the estimated mean / stdev (p->fragment_mean / p->fragment_stdev are
+ * ignored; `f` carries the distribution across calls).  Outputs as gb_map_paired_batch;
+ * pair_route[n_reads / 2] receives GB_PAIR_* (may be NULL).  training_window 0 selects 2048. */
+int gb_map_paired_job(gb_device* dev, const gb_map_params* p, gb_fragment_distribution* f, uint32_t training_window,
+                      uint32_t n_reads, const uint8_t* reads, const uint8_t* quals, const uint64_t* read_off,
+                      gb_alignment* aln, gb_mapping* mappings, uint64_t mapping_pool_cap, uint32_t* edits, uint64_t edit_pool_cap,
+                      uint8_t* status, uint8_t* pair_route, uint64_t* n_mappings_used, uint64_t* n_edits_used);
+
 /* Device-pointer variant of both (paired != 0 selects map_paired): every pointer is a DEVICE
  * address (inputs already resident in HBM, outputs stay in HBM); all reads are at most
  * max_read_len long; d_totals[2] (device) receives {mappings used, edits used}.  The call only

@@ -5,6 +5,7 @@
 // alignments (find_supplementaries, off by default).
 //   joint clustering: SnarlDistanceIndexClusterer::cluster_seeds snarl_seed_clusterer.cpp:65-145
 //   pair score:       score_alignment_pair :6017-6028, distance_between :3879-3903
+#include "fragment.hpp"
 #include "mapper_common.hpp"
 #include "tail_align.hpp"
 
@@ -30,6 +31,8 @@ int64_t unoriented_distance(const gb_flat_index* ix, const Seed& a, const Seed& 
 void score_cluster(Cluster& cluster, const std::vector<Minimizer>& minimizers, const std::vector<Seed>& seeds, size_t seq_length);
 int score_extension_group(size_t seq_len, const std::vector<GaplessExtension>& ext, int max_mismatches, int gap_open_penalty, int gap_extend_penalty);
 double faster_cap(const std::vector<Minimizer>& minimizers, std::vector<size_t>& explored, const std::string& sequence, const std::string& quality);
+Alignment map_from_extensions(const gb_flat_index* ix, const gb_scores& scores, const gb_map_params& P,
+                              const std::string& sequence, const std::string& quality, MapCounters* counters);
 int pack_alignment(const Alignment& a, uint32_t read_id, gb_alignment* rec, gb_mapping* mappings, uint32_t mapping_cap,
                    uint32_t* edits, uint32_t edit_cap, uint32_t mapping_base, uint32_t edit_base);
 
@@ -496,5 +499,89 @@ extern "C" int oracle_map_paired_batch(const gb_flat_index* ix, const gb_scores*
         total.add(local);
     }
     if (counters_out) total.store(counters_out);
+    return failed ? -1 : 0;
+}
+
+
+// ---- the whole paired job: fragment-length training, then map_paired, then the ambiguous buffer -----------------
+// giraffe_main.cpp:2246-2400 drives MinimizerMapper::map_paired(aln1, aln2, ambiguous_pair_buffer)
+// (minimizer_mapper.cpp:1303-1395) single-threaded until the distribution is finalized, maps the rest with the
+// finalized distribution, finalizes by force at the end of input (finalize_fragment_length_distr,
+// minimizer_mapper.hpp:539-543) and maps the buffered pairs last.  route[pair]: GB_PAIR_TRAINING (both ends mapped
+// single-ended, distance registered), GB_PAIR_PAIRED, GB_PAIR_BUFFERED (ambiguous during training, mapped paired
+// at the end).  frag_out = {mean, stdev, samples registered}.
+extern "C" int oracle_map_paired_job(const gb_flat_index* ix, const gb_scores* scores, const gb_map_params* p_in,
+                                     uint64_t maximum_sample_size, uint64_t reestimation_frequency, double robust_estimation_fraction,
+                                     uint32_t n_reads, const uint8_t* reads, const uint8_t* quals, const uint64_t* read_off,
+                                     gb_alignment* aln, gb_mapping* mappings, uint32_t* edits, uint8_t* status, uint8_t* route,
+                                     int n_threads, double* frag_out) {
+    if (n_reads % 2 != 0) return -2;
+    using namespace oracle;
+    gb_map_params P = *p_in;
+    FragmentLengthDistribution distr(maximum_sample_size, reestimation_frequency, robust_estimation_fraction);
+    if (P.fragment_stdev > 0) distr.force_parameters(P.fragment_mean, P.fragment_stdev);
+    Graph g(ix);
+    MapCounters local;
+    const int64_t n_pairs = n_reads / 2;
+    int failed = 0;
+    auto read_of = [&](int64_t ri, std::string& s, std::string& q) {
+        const uint64_t b = read_off[ri], e = read_off[ri + 1];
+        s.assign((const char*)reads + b, (size_t)(e - b));
+        if (quals) q.assign((const char*)quals + b, (size_t)(e - b)); else q.clear();
+    };
+    auto emit = [&](const Alignment& a, int64_t ri, bool paired) {
+        int rc = pack_alignment(a, (uint32_t)ri, aln + ri, mappings + (size_t)ri * P.mapping_cap_per_read, P.mapping_cap_per_read,
+                                edits + (size_t)ri * P.edit_cap_per_read, P.edit_cap_per_read,
+                                (uint32_t)(ri * P.mapping_cap_per_read), (uint32_t)(ri * P.edit_cap_per_read));
+        if (paired) aln[ri].flags |= GB_ALN_PAIRED;
+        status[ri] = rc == 0 ? GB_ITEM_OK : GB_ITEM_OUT_FULL;
+        if (rc) {
+#pragma omp atomic
+            failed++;
+        }
+    };
+    std::vector<int64_t> ambiguous_pair_buffer;
+    int64_t pi = 0;
+    for (; pi < n_pairs && !distr.is_finalized(); pi++) {
+        std::string s[2], q[2];
+        Alignment single[2];
+        bool both_perfect_unique = true;
+        for (int r = 0; r < 2; r++) {
+            read_of(2 * pi + r, s[r], q[r]);
+            single[r] = map_from_extensions(ix, *scores, P, s[r], q[r], &local);
+            const int32_t max_score_aln = scores->match * (int32_t)s[r].size();                    // score_exact_match
+            both_perfect_unique = both_perfect_unique && !single[r].path.empty() && single[r].mapq == 60 && single[r].score >= max_score_aln * 0.85;
+        }
+        bool keep = false;
+        if (both_perfect_unique) {
+            Alignment flipped = single[1];
+            reverse_complement_path(flipped.path, g);
+            const Mapping& last = flipped.path.back();
+            uint32_t used = 0; for (const Edit& e : last.edits) used += e.from_length;
+            const int64_t dist = oriented_distance(ix, single[0].path.front().node, single[0].path.front().offset, last.node, last.offset + used);
+            if (!(dist == std::numeric_limits<int64_t>::max() || dist >= (int64_t)P.max_fragment_length)) {
+                distr.register_fragment_length(dist);
+                keep = true;
+            }
+        }
+        if (keep) { route[pi] = GB_PAIR_TRAINING; for (int r = 0; r < 2; r++) emit(single[r], 2 * pi + r, false); }
+        else { route[pi] = GB_PAIR_BUFFERED; ambiguous_pair_buffer.push_back(pi); }
+    }
+    const int64_t first_paired = pi;
+    if (!distr.is_finalized()) distr.force_parameters(distr.mean(), distr.std_dev());
+    P.fragment_mean = distr.mean(); P.fragment_stdev = distr.std_dev();
+    frag_out[0] = distr.mean(); frag_out[1] = distr.std_dev(); frag_out[2] = (double)distr.curr_sample_size();
+    std::vector<int64_t> todo;
+    for (int64_t x = first_paired; x < n_pairs; x++) { route[x] = GB_PAIR_PAIRED; todo.push_back(x); }
+    todo.insert(todo.end(), ambiguous_pair_buffer.begin(), ambiguous_pair_buffer.end());
+#pragma omp parallel for schedule(dynamic, 64) num_threads(n_threads > 0 ? n_threads : 1)
+    for (int64_t t = 0; t < (int64_t)todo.size(); t++) {
+        const int64_t x = todo[t];
+        std::string s[2], q[2];
+        for (int r = 0; r < 2; r++) read_of(2 * x + r, s[r], q[r]);
+        MapCounters mine;
+        PairResult res = map_paired(ix, *scores, P, s[0], q[0], s[1], q[1], &mine);
+        for (int r = 0; r < 2; r++) emit(res.aln[r], 2 * x + r, true);
+    }
     return failed ? -1 : 0;
 }

@@ -277,3 +277,37 @@ def paired_params(mean=400.0, stdev=50.0):
     p.fragment_stdev = stdev
     p.max_rescue_attempts = 0
     return p
+
+
+def oracle_fragment_estimate(lengths, maximum_sample_size=1000, reestimation_frequency=1000, fraction=0.95):
+    """Register `lengths` in order in the oracle's FragmentLengthDistribution; (mean, stdev, finalized, samples)."""
+    lib = oracle_lib()
+    lib.oracle_fragment_estimate.argtypes = [C.c_void_p, C.c_uint64, C.c_uint64, C.c_uint64, C.c_double, C.POINTER(C.c_double),
+                                             C.POINTER(C.c_double), C.POINTER(C.c_int), C.POINTER(C.c_uint64)]
+    lib.oracle_fragment_estimate.restype = None
+    arr = np.ascontiguousarray(lengths, dtype=np.int64)
+    mean, sd, fin, n = C.c_double(), C.c_double(), C.c_int(), C.c_uint64()
+    lib.oracle_fragment_estimate(capi.ptr(arr), len(arr), maximum_sample_size, reestimation_frequency, fraction,
+                                 C.byref(mean), C.byref(sd), C.byref(fin), C.byref(n))
+    return mean.value, sd.value, bool(fin.value), int(n.value)
+
+
+def oracle_map_paired_job(index, reads, quals, params, maximum_sample_size=1000, reestimation_frequency=1000, fraction=0.95, threads=1):
+    """giraffe_main's paired job on the CPU: training, map_paired, ambiguous buffer.
+    Returns (aln, maps, edits, status, route, (mean, stdev, samples))."""
+    lib = oracle_lib()
+    lib.oracle_map_paired_job.argtypes = [C.POINTER(capi.FlatIndex), C.POINTER(capi.Scores), C.POINTER(MapParams), C.c_uint64, C.c_uint64,
+                                          C.c_double, C.c_uint32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
+                                          C.c_void_p, C.c_void_p, C.c_int, C.c_void_p]
+    lib.oracle_map_paired_job.restype = C.c_int
+    p = params
+    rbuf, qbuf, read_off = pack_reads(reads, quals)
+    n = len(read_off) - 1
+    aln, maps, edits, status = oracle_out_buffers(n, p)
+    route = np.zeros(n // 2, dtype=np.uint8)
+    frag = np.zeros(3, dtype=np.float64)
+    rc = lib.oracle_map_paired_job(C.byref(index.view), C.byref(capi.DEFAULT_SCORES), C.byref(p), maximum_sample_size, reestimation_frequency, fraction,
+                                   n, capi.ptr(rbuf), capi.ptr(qbuf) if qbuf is not None else None, capi.ptr(read_off), capi.ptr(aln),
+                                   capi.ptr(maps), capi.ptr(edits), capi.ptr(status), capi.ptr(route), threads, capi.ptr(frag))
+    assert rc == 0, f"oracle_map_paired_job rc {rc}"
+    return aln, maps, edits, status, route, (float(frag[0]), float(frag[1]), int(frag[2]))

@@ -144,6 +144,26 @@ def load_library() -> C.CDLL:
     lib.gb_xdrop_dag_batch.restype = C.c_int
     lib.gb_wfa_batch.argtypes = [vp, u32, vp, vp, vp, vp, vp, u32, u32, vp, vp, vp, vp, vp, vp, vp, vp, vp]
     lib.gb_wfa_batch.restype = C.c_int
+    lib.gb_fragment_create.argtypes = [u64, u64, C.c_double]
+    lib.gb_fragment_create.restype = vp
+    lib.gb_fragment_destroy.argtypes = [vp]
+    lib.gb_fragment_destroy.restype = None
+    lib.gb_fragment_force.argtypes = [vp, C.c_double, C.c_double]
+    lib.gb_fragment_force.restype = None
+    lib.gb_fragment_register.argtypes = [vp, C.c_int64]
+    lib.gb_fragment_register.restype = None
+    lib.gb_fragment_finalize.argtypes = [vp]
+    lib.gb_fragment_finalize.restype = None
+    lib.gb_fragment_mean.argtypes = [vp]
+    lib.gb_fragment_mean.restype = C.c_double
+    lib.gb_fragment_stdev.argtypes = [vp]
+    lib.gb_fragment_stdev.restype = C.c_double
+    lib.gb_fragment_is_finalized.argtypes = [vp]
+    lib.gb_fragment_is_finalized.restype = C.c_int
+    lib.gb_fragment_sample_size.argtypes = [vp]
+    lib.gb_fragment_sample_size.restype = u64
+    lib.gb_map_paired_job.argtypes = [vp, C.POINTER(MapParams), vp, u32, u32, vp, vp, vp, vp, vp, u64, vp, u64, vp, vp, vp, vp]
+    lib.gb_map_paired_job.restype = C.c_int
     lib.gb_last_kernel_ms.argtypes = [vp]
     lib.gb_last_kernel_ms.restype = C.c_float
     lib.gb_launch_count.argtypes = [vp]
@@ -211,6 +231,51 @@ class HostIndex:
     def close(self):
         if getattr(self, "_h", None):
             load_library().gb_index_free(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+GB_PAIR_PAIRED, GB_PAIR_TRAINING, GB_PAIR_BUFFERED = 0, 1, 2
+
+
+class FragmentDistribution:
+    """FragmentLengthDistribution (mapper.hpp:83-139) behind gb_fragment_*; MinimizerMapper's own is
+    (1000, 1000, 0.95) (minimizer_mapper.cpp:72).  Host-side state: usable without a GPU."""
+
+    def __init__(self, maximum_sample_size=1000, reestimation_frequency=1000, robust_estimation_fraction=0.95):
+        self._h = load_library().gb_fragment_create(maximum_sample_size, reestimation_frequency, robust_estimation_fraction)
+        if not self._h:
+            raise GbError(GB_ERR_ARG, "gb_fragment_create")
+
+    def register_fragment_length(self, length):
+        load_library().gb_fragment_register(self._h, int(length))
+
+    def force_parameters(self, mean, stdev):
+        load_library().gb_fragment_force(self._h, mean, stdev)
+
+    def finalize(self):
+        load_library().gb_fragment_finalize(self._h)
+
+    def mean(self):
+        return load_library().gb_fragment_mean(self._h)
+
+    def std_dev(self):
+        return load_library().gb_fragment_stdev(self._h)
+
+    def is_finalized(self):
+        return bool(load_library().gb_fragment_is_finalized(self._h))
+
+    def curr_sample_size(self):
+        return int(load_library().gb_fragment_sample_size(self._h))
+
+    def close(self):
+        if getattr(self, "_h", None):
+            load_library().gb_fragment_destroy(self._h)
             self._h = None
 
     def __del__(self):
@@ -453,6 +518,26 @@ class Device:
             raise GbError(rc, "gb_map_paired_batch" if paired else "gb_map_batch")
         self.last_used = (used[0].value, used[1].value)
         return aln, maps, edits, status
+
+    def map_paired_job(self, rbuf, qbuf, read_off, distribution, params=None, training_window=0):
+        """gb_map_paired_job: fragment-length training + map_paired + the ambiguous buffer.
+        Returns (aln, mappings, edits, status, pair_route)."""
+        lib = load_library()
+        p = params or default_map_params()
+        n = len(read_off) - 1
+        aln = np.zeros(n, dtype=alignment_dt)
+        maps = np.zeros(n * p.mapping_cap_per_read, dtype=mapping_dt)
+        edits = np.zeros(n * p.edit_cap_per_read, dtype=np.uint32)
+        status = np.zeros(n, dtype=np.uint8)
+        route = np.zeros(n // 2, dtype=np.uint8)
+        used = (C.c_uint64(), C.c_uint64())
+        rc = lib.gb_map_paired_job(self._h, C.byref(p), distribution._h, training_window, n, ptr(rbuf), ptr(qbuf) if qbuf is not None else None,
+                                   ptr(read_off), ptr(aln), ptr(maps), len(maps), ptr(edits), len(edits), ptr(status), ptr(route),
+                                   C.byref(used[0]), C.byref(used[1]))
+        if rc != GB_OK:
+            raise GbError(rc, "gb_map_paired_job")
+        self.last_used = (used[0].value, used[1].value)
+        return aln, maps, edits, status, route
 
     def stage_times(self):
         ms = (C.c_float * 4)()

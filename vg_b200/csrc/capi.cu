@@ -154,6 +154,7 @@ extern "C" int gb_device_create(const gb_flat_index* ix, int device_ordinal, gb_
         d->ix.slot_order = d->slot_order.ptr; d->ix.n_ids = (uint32_t)order.size();
     }
     d->h_node_len.resize(ix->n_nodes);
+    d->h_dist.assign(ix->dist, ix->dist + ix->n_nodes / 2);
     for (uint32_t v = 0; v < ix->n_nodes; v++) d->h_node_len[v] = ix->nodes[v].len;
     d->ix.nodes = d->nodes.ptr; d->ix.seq = d->seq.ptr; d->ix.gbwt = d->gbwt.ptr; d->ix.dist = d->dist.ptr;
     d->ix.table = d->table.ptr; d->ix.hits = d->hits.ptr;
