@@ -100,8 +100,13 @@ PairResult map_paired(const gb_flat_index* ix, const gb_scores& scores, const gb
     std::array<std::string, 2> seqs{seq1, reverse_complement(seq2_in)};
     std::array<std::string, 2> quals{qual1, std::string(qual2_in.rbegin(), qual2_in.rend())};
     size_t read_limit = std::max<size_t>(P.distance_limit, seqs[0].size() + 50);
-    // (the reference falls back to single-end mapping when fragment_distance_limit < read_limit, :1471-1496;
-    //  not reachable with the forced distributions used here: caller must ensure it)
+    if (fragment_distance_limit < (int64_t)std::max<size_t>(P.distance_limit, seq1.size() + 50)) {
+        // a distribution the clusterer cannot use: both ends single-ended, emitted as a pair (:1471-1496)
+        PairResult fallback;
+        fallback.aln[0] = map_from_extensions(ix, scores, P, seq1, qual1, counters);
+        fallback.aln[1] = map_from_extensions(ix, scores, P, seq2_in, qual2_in, counters);
+        return fallback;
+    }
 
     LazyRNG rng([&]() { return seqs[0] + seqs[1]; });
 

@@ -219,3 +219,21 @@ def test_map_paired_edge_cases():
     bad = H.compare_alignments(got, want, len(reads))
     assert not bad, bad[0]
     dev.close()
+
+
+@pytest.mark.gpu
+def test_unusable_fragment_distribution_falls_back_to_single_end():
+    """fragment limit (mean + 2 sd) below the read limit max(200, L + 50): map_paired maps both ends
+    single-ended and emits them as a pair (minimizer_mapper.cpp:1469-1496)."""
+    g = synth.make_variant_graph(length=60000, n_snp=100, n_ins=10, n_del=10, n_haps=4, seed=8)
+    rs = synth.simulate_pairs(g, 300, sub_rate=0.01, seed=5)
+    index = g.build_index()
+    dev = capi.Device(index)
+    p = H.paired_params(100.0, 20.0)                       # limit 140 < 200
+    got = H.gpu_map(dev, rs.reads, rs.quals, p, paired=True)
+    want = H.oracle_map_paired(index, rs.reads, rs.quals, p, threads=8)
+    assert not H.compare_alignments(got, want, rs.n)
+    se = H.gpu_map(dev, rs.reads, rs.quals, H.default_map_params())
+    assert not H.compare_alignments(got, se, rs.n, mapq_tol=0)
+    assert ((got[0]["flags"] & capi.GB_ALN_PAIRED) != 0).all() and ((se[0]["flags"] & capi.GB_ALN_PAIRED) == 0).all()
+    dev.close()
