@@ -33,3 +33,23 @@ def gather_headers(headers, rank: int, world: int, dst: int = 0):
     if rank != dst:
         return None
     return [o[: int(s.item())] for o, s in zip(out, sizes)]
+
+
+def share_fragment_distribution(distribution, rank: int, world: int, src: int = 0, device=None):
+    """The one piece of shared state of a paired job (minimizer_mapper.hpp:696): rank `src` learns the
+    fragment length distribution from the head of the input (gb_map_paired_job stops training after
+    maximum_sample_size unambiguous pairs) and broadcasts (mean, stdev) as two doubles; every other rank
+    forces its own gb_fragment_distribution to them (force_parameters, mapper.cpp:5250), after which all
+    ranks map their shards independently.  Returns (mean, stdev).  Raises if `src` has not finalized."""
+    import torch
+    import torch.distributed as dist
+    t = torch.zeros(3, dtype=torch.float64, device=device)
+    if rank == src:
+        t[0], t[1], t[2] = distribution.mean(), distribution.std_dev(), 1.0 if distribution.is_finalized() else 0.0
+    dist.broadcast(t, src=src)
+    mean, stdev, finalized = (float(x) for x in t.cpu())
+    if finalized != 1.0:
+        raise RuntimeError("share_fragment_distribution: the source rank's distribution is not finalized")
+    if rank != src:
+        distribution.force_parameters(mean, stdev)
+    return mean, stdev
