@@ -214,3 +214,22 @@ Alignment attempt_rescue(const gb_flat_index* ix, const gb_scores& sc, const gb_
 }
 
 } // namespace oracle
+
+// fix_dozeu_end_deletions on a flat path (test entry): edits are (from_length, to_length) pairs, edit_count[i]
+// of them per mapping; the result overwrites the arrays and its mapping count is returned.
+extern "C" uint32_t oracle_fix_end_deletions(uint32_t n_mappings, uint32_t* node, uint32_t* offset, uint32_t* edit_count,
+                                             uint32_t* from_length, uint32_t* to_length) {
+    std::vector<oracle::Mapping> path(n_mappings);
+    size_t e = 0;
+    for (uint32_t i = 0; i < n_mappings; i++) {
+        path[i].node = node[i]; path[i].offset = offset[i];
+        for (uint32_t j = 0; j < edit_count[i]; j++, e++) { oracle::Edit ed; ed.from_length = from_length[e]; ed.to_length = to_length[e]; path[i].edits.push_back(ed); }
+    }
+    oracle::fix_dozeu_end_deletions(path);
+    e = 0;
+    for (size_t i = 0; i < path.size(); i++) {
+        node[i] = path[i].node; offset[i] = path[i].offset; edit_count[i] = (uint32_t)path[i].edits.size();
+        for (const oracle::Edit& ed : path[i].edits) { from_length[e] = ed.from_length; to_length[e] = ed.to_length; e++; }
+    }
+    return (uint32_t)path.size();
+}

@@ -42,6 +42,24 @@ def _wrecked_pairs(n_pairs=300, seed=61):
     return g, rs, wrecked
 
 
+def test_oracle_fix_end_deletions_reference_vector():
+    """unittest/minimizer_mapper.cpp:1130-1181 "can fix up alignments with deletions on the ends": node 1 (+3) [2D],
+    node 2 (+0) [2D 1M 1D], node 3 (+0) [1D]  ->  node 2 (+2) [1M]."""
+    import ctypes as C
+    lib = H.oracle_lib()
+    lib.oracle_fix_end_deletions.argtypes = [C.c_uint32] + [C.c_void_p] * 5
+    lib.oracle_fix_end_deletions.restype = C.c_uint32
+    node = np.array([1, 2, 3], dtype=np.uint32); offset = np.array([3, 0, 0], dtype=np.uint32)
+    count = np.array([1, 3, 1], dtype=np.uint32)
+    frm = np.array([2, 2, 1, 1, 1], dtype=np.uint32); to = np.array([0, 0, 1, 0, 0], dtype=np.uint32)
+    n = lib.oracle_fix_end_deletions(3, capi.ptr(node), capi.ptr(offset), capi.ptr(count), capi.ptr(frm), capi.ptr(to))
+    assert n == 1 and node[0] == 2 and offset[0] == 2 and count[0] == 1 and (frm[0], to[0]) == (1, 1)
+    # an alignment that is all deletion is cleared
+    node = np.array([1], dtype=np.uint32); offset = np.array([0], dtype=np.uint32); count = np.array([1], dtype=np.uint32)
+    frm = np.array([4], dtype=np.uint32); to = np.array([0], dtype=np.uint32)
+    assert lib.oracle_fix_end_deletions(1, capi.ptr(node), capi.ptr(offset), capi.ptr(count), capi.ptr(frm), capi.ptr(to)) == 0
+
+
 def test_oracle_rescue_recovers_mates_without_seeds():
     """attempt_rescue (minimizer_mapper.cpp:3264-3482) in the oracle: mates too noisy to seed are found next to
     their partner; the rescued records are internally consistent."""
