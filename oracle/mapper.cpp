@@ -734,3 +734,21 @@ extern "C" int oracle_map_batch(const gb_flat_index* ix, const gb_scores* scores
     if (counters_out) total.store(counters_out);
     return failed ? -1 : 0;
 }
+
+// faster_cap on explicit minimizers (test entry for the reference's MAPQ-cap unit tests,
+// unittest/minimizer_mapper.cpp:112-252): minimizer i has core [offset, offset + length), agglomeration
+// [agg_start, agg_start + agg_len), forward strand, key = `length` Gs (hash = gbwtgraph key hash); all are explored.
+extern "C" double oracle_faster_cap_all_g(uint32_t n, const uint32_t* offset, const uint32_t* length, const uint32_t* agg_start,
+                                          const uint32_t* agg_len, uint32_t read_len, uint8_t quality) {
+    std::vector<oracle::Minimizer> minimizers(n);
+    std::vector<size_t> explored(n);
+    for (uint32_t i = 0; i < n; i++) {
+        oracle::Minimizer& m = minimizers[i];
+        uint64_t key = 0;
+        for (uint32_t b = 0; b < length[i]; b++) key = (key << 2) | 2u;          // G = 2
+        m.key = key; m.hash = oracle::wang_hash_64(key); m.offset = offset[i]; m.is_reverse = false; m.length = (int32_t)length[i];
+        m.agglomeration_start = agg_start[i]; m.agglomeration_length = agg_len[i]; m.hit_cnt = 1; m.score = 1;
+        explored[i] = i;
+    }
+    return oracle::faster_cap(minimizers, explored, std::string(read_len, 'G'), std::string(read_len, (char)quality));
+}
