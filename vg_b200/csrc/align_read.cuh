@@ -77,37 +77,48 @@ __device__ inline double faster_cap(const MapParamsDev& P, const DevMinimizer* m
         }
         return p;
     };
-    auto iteratee = [&](uint32_t left, uint32_t right, uint32_t bottom, uint32_t top) {
-        double p_here = 0.0;
-        if (left != right) {
-            double p = column_prob(bottom, top, left);
-            for (uint32_t i = left + 1; i < right; i++) { const double col_p = column_prob(bottom, top, i); p = (p + col_p - (p * col_p)); }
-            p_here = log10(p);
-        }
-        const double pv = c[bottom] + p_here;
-        for (uint32_t i = bottom + 1; i < top + 1; i++) if (c[i] < pv) c[i] = pv;
-    };
-    // for_each_agglomeration_interval (:3088-3161); the "stack" is the window [front, back) of mp
+    // for_each_agglomeration_interval (:3088-3161) turned inside out: the sweep ("stack" = window
+    // [front, back) of mp) hands out one interval (left, right, bottom, top) at a time and the loop below
+    // evaluates ONE read column per trip, so that the threads of a warp that run this for different reads
+    // stay in step (the nested sweep / interval / column loops of the reference diverge badly under SIMT).
+    // The floating-point operations and their order are those of the nested form.
     auto agg_start_of = [&](uint32_t it) { return (uint32_t)mp[it] & 0xffffu; };
     auto agg_end_of = [&](uint32_t it) { return (uint32_t)(mp[it] >> 16) & 0xffffu; };
-    uint32_t front = 0, back = 1;
-    uint32_t left = agg_start_of(0), bottom = 0;
-    auto emit_preceding = [&](uint32_t right) {
-        while (left < right) {
-            const uint32_t stack_size = back - front;
-            const uint32_t stack_top_end = agg_end_of(front);
-            if (stack_top_end <= right) {
-                iteratee(left, stack_top_end, bottom, bottom + stack_size);
-                left = stack_size == 1 ? right : stack_top_end;
-                bottom += 1; front++;
-            } else {
-                iteratee(left, right, bottom, bottom + stack_size);
-                left = right;
+    uint32_t front = 0, back = 1, left = agg_start_of(0), bottom = 0, it = 1;
+    bool final_phase = n == 1;
+    uint32_t pending_right = final_phase ? L : agg_start_of(1);       // emit_preceding(pending_right) in progress
+    uint32_t col = 0, right = 0, ib = 0, itop = 0;
+    double p = 0.0;
+    bool open = false, first = true, done = false;
+    auto close_interval = [&](double p_here) {
+        const double pv = c[ib] + p_here;
+        for (uint32_t i = ib + 1; i < itop + 1; i++) if (c[i] < pv) c[i] = pv;
+    };
+    while (true) {
+        while (!open && !done) {
+            if (left < pending_right) {
+                const uint32_t stack_size = back - front, stack_top_end = agg_end_of(front);
+                ib = bottom; itop = bottom + stack_size; col = left;
+                if (stack_top_end <= pending_right) {
+                    right = stack_top_end;
+                    left = stack_size == 1 ? pending_right : stack_top_end;
+                    bottom += 1; front++;
+                } else { right = pending_right; left = pending_right; }
+                if (col == right) close_interval(0.0);                 // empty interval (two agglomerations ending together)
+                else { open = true; first = true; }
+            } else if (final_phase) done = true;
+            else {
+                back++; it++;
+                if (it < n) pending_right = agg_start_of(it); else { pending_right = L; final_phase = true; }
             }
         }
-    };
-    for (uint32_t it = 1; it < n; it++) { emit_preceding(agg_start_of(it)); back++; }
-    emit_preceding(L);
+        if (done) break;
+        const double col_p = column_prob(ib, itop, col);
+        p = first ? col_p : (p + col_p - (p * col_p));
+        first = false;
+        col++;
+        if (col == right) { close_interval(log10(p)); open = false; }
+    }
     return -c[n] * 10;
 }
 
