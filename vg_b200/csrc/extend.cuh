@@ -144,6 +144,7 @@ __device__ __forceinline__ QEntry q_load(const QEntry* slot) {
 
 __device__ inline QEntry q_pop(QEntry* queue, uint32_t& qn) {
     const int lane = lane_id();
+    if (qn == 1) { QEntry only = q_load(queue); qn = 0; __syncwarp(); return only; }      // a linear walk keeps one entry
     long long best = LLONG_MIN; uint32_t best_idx = 0;
     for (uint32_t j = lane; j < qn; j += 32) {
         const long long key = (long long)queue[j].score * 4294967296LL + (long long)queue[j].number;
@@ -384,9 +385,14 @@ __device__ inline uint32_t extend_item(const DevIndex& ix, const ExtendParams& p
 
     // canonical seed order: ascending (node, diag), duplicates collapsed
     unsigned long long last_key = 0; bool have_last = false;
+    // bit c of `dead`: my seed of chunk c (seed lane + 32 c) lies on the exact full-length best alignment
+    // (gbwt_extender.cpp:553-557), decided for all seeds at once when that alignment appears
+    uint32_t dead = 0;
+    const bool dead_ok = n_seeds <= 1024;
     while (true) {
         unsigned long long mine = ~0ull;
-        for (uint32_t j = lane; j < n_seeds; j += 32) {
+        for (uint32_t j = lane, c = 0; j < n_seeds; j += 32, c++) {
+            if (dead_ok && ((dead >> c) & 1u)) continue;
             const gb_seed s = seeds[j];
             const unsigned long long key = ((unsigned long long)s.node << 32) | (uint32_t)(s.diag ^ 0x80000000);
             if ((!have_last || key > last_key) && key < mine) mine = key;
@@ -403,7 +409,7 @@ __device__ inline uint32_t extend_item(const DevIndex& ix, const ExtendParams& p
         if (seed_node < 2 || seed_node >= ix.n_nodes) continue;
 
         // gbwt_extender.cpp:553-557: skip seeds contained in an exact full-length alignment
-        if (best_alignment != NONE && best_alignment_mm == 0) {
+        if (!dead_ok && best_alignment != NONE && best_alignment_mm == 0) {
             if (ext_contains(ix, ext[best_alignment], path_pool, seed_node, seed_diag)) continue;
         }
 
@@ -562,8 +568,33 @@ __device__ inline uint32_t extend_item(const DevIndex& ix, const ExtendParams& p
             if (full && (best_alignment == NONE || best.internal_score < best_alignment_mm)) {
                 best_alignment = n_res; best_alignment_mm = best.internal_score;
             }
+            const bool newly_exact = full && best_alignment == n_res && best.internal_score == 0;
             path_used += plen; n_res++;
             __syncwarp();
+            if (newly_exact && dead_ok) {
+                // GaplessExtension::contains (gbwt_extender.cpp:41-53) for every seed at once: lanes hold the
+                // (node, read offset - node offset) of up to 32 path nodes, every lane tests its own seeds
+                uint32_t read_offset = best.read_lo;
+                for (uint32_t pb = 0; pb < plen; pb += 32) {
+                    const uint32_t i = pb + lane;
+                    uint32_t h = 0, len = 0;
+                    if (i < plen) { h = path_pool[path_used - plen + i]; len = load_node(ix, h).len - (i == 0 ? best.offset : 0u); }
+                    const uint32_t incl = (uint32_t)warp_incl_scan((int)len);
+                    const int32_t diag = (int32_t)(read_offset + incl - len) - (int32_t)(i == 0 ? best.offset : 0u);
+                    const uint32_t cnt = min(32u, plen - pb);
+                    for (uint32_t j = lane, c = 0; c * 32 < n_seeds; j += 32, c++) {
+                        gb_seed sd; sd.node = 0; sd.diag = 0;
+                        if (j < n_seeds) sd = seeds[j];
+                        bool hit = false;
+                        for (uint32_t x = 0; x < cnt; x++) {
+                            const uint32_t hn = __shfl_sync(FULL, h, x); const int32_t dg = __shfl_sync(FULL, diag, x);
+                            hit |= sd.node == hn && sd.diag == dg;
+                        }
+                        if (hit && j < n_seeds) dead |= 1u << c;
+                    }
+                    read_offset += __shfl_sync(FULL, incl, 31);
+                }
+            }
         }
     }
 
