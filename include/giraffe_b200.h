@@ -346,6 +346,24 @@ int gb_map_paired_job(gb_device* dev, const gb_map_params* p, gb_fragment_distri
                       gb_alignment* aln, gb_mapping* mappings, uint64_t mapping_pool_cap, uint32_t* edits, uint64_t edit_pool_cap,
                       uint8_t* status, uint8_t* pair_route, uint64_t* n_mappings_used, uint64_t* n_edits_used);
 
+/* ---- emission (host side, no device work) ---------------------------------------------------
+ * giraffe_main.cpp:2209-2226 hands alignments to a vg::io::AlignmentEmitter (libvgio @ d029989,
+ * absent from the reference tree).  These two write the same information as text, one line per
+ * record, into `out` (GB_ERR_CAPACITY if it does not fit; *out_used = bytes written):
+ *   gb_emit_gaf   GAF: name, length, query start / end (soft clips excluded), '+', path as >id / <id
+ *                 steps, path length, start / end on the path, matches, block length, MAPQ, then
+ *                 AS:i, bq:Z (when quals), cs:Z (":n" "*rq" "+q" "-r"), dv:f, fn:Z / fp:Z for mates
+ *   gb_emit_json  one protobuf-JSON Alignment per line with vg.proto's field names, as `vg view -aj`
+ *                 prints them (64-bit integers as strings, default values omitted, quality base64)
+ * names / name_off may be NULL (reads are then called read<i>); records may be any subset / order
+ * (read_id selects the read). */
+int gb_emit_gaf(const gb_flat_index* ix, uint32_t n, const gb_alignment* aln, const gb_mapping* mappings, const uint32_t* edits,
+                const uint8_t* reads, const uint8_t* quals, const uint64_t* read_off, const uint8_t* names, const uint64_t* name_off,
+                char* out, uint64_t out_cap, uint64_t* out_used);
+int gb_emit_json(const gb_flat_index* ix, uint32_t n, const gb_alignment* aln, const gb_mapping* mappings, const uint32_t* edits,
+                 const uint8_t* reads, const uint8_t* quals, const uint64_t* read_off, const uint8_t* names, const uint64_t* name_off,
+                 char* out, uint64_t out_cap, uint64_t* out_used);
+
 /* Device-pointer variant of both (paired != 0 selects map_paired): every pointer is a DEVICE
  * address (inputs already resident in HBM, outputs stay in HBM); all reads are at most
  * max_read_len long; d_totals[2] (device) receives {mappings used, edits used}.  The call only

@@ -10,7 +10,7 @@ g, index = bench.make_graph_and_index()
 device = torch.device("cuda", 0)
 dev = capi.Device(index, 0)
 lib = capi.load_library()
-p = H.paired_params(400.0, 50.0)
+p = H.paired_params(400.0, 50.0); p.max_rescue_attempts = 15          # the bench configuration (vg default)
 stream = torch.cuda.Stream(device=device); torch.cuda.set_stream(stream)
 lib.gb_device_set_stream(dev.handle, C.c_void_p(stream.cuda_stream))
 d_reads, d_quals = bench.simulate_pairs_torch(g, n // 2, 22, device)

@@ -164,6 +164,9 @@ def load_library() -> C.CDLL:
     lib.gb_fragment_sample_size.restype = u64
     lib.gb_map_paired_job.argtypes = [vp, C.POINTER(MapParams), vp, u32, u32, vp, vp, vp, vp, vp, u64, vp, u64, vp, vp, vp, vp]
     lib.gb_map_paired_job.restype = C.c_int
+    for fn in (lib.gb_emit_gaf, lib.gb_emit_json):
+        fn.argtypes = [C.POINTER(FlatIndex), u32, vp, vp, vp, vp, vp, vp, vp, vp, vp, u64, vp]
+        fn.restype = C.c_int
     lib.gb_last_kernel_ms.argtypes = [vp]
     lib.gb_last_kernel_ms.restype = C.c_float
     lib.gb_launch_count.argtypes = [vp]
@@ -241,6 +244,28 @@ class HostIndex:
 
 
 GB_PAIR_PAIRED, GB_PAIR_TRAINING, GB_PAIR_BUFFERED = 0, 1, 2
+
+
+def emit_text(kind, flat_index, aln, maps, edits, rbuf, qbuf, read_off, names=None):
+    """gb_emit_gaf / gb_emit_json (kind = "gaf" | "json") over records `aln`; returns the text.
+    names: optional list of read names (str)."""
+    lib = load_library()
+    fn = {"gaf": lib.gb_emit_gaf, "json": lib.gb_emit_json}[kind]
+    nbuf = noff = None
+    if names is not None:
+        enc = [s.encode() for s in names]
+        noff = np.zeros(len(enc) + 1, dtype=np.uint64)
+        noff[1:] = np.cumsum([len(b) for b in enc])
+        nbuf = np.frombuffer(b"".join(enc) + b"\0", dtype=np.uint8).copy()
+    aln = np.ascontiguousarray(aln)
+    cap = 4096 + len(aln) * 4096
+    out = np.zeros(cap, dtype=np.uint8)
+    used = C.c_uint64()
+    rc = fn(C.byref(flat_index), len(aln), ptr(aln), ptr(maps), ptr(edits), ptr(rbuf), ptr(qbuf) if qbuf is not None else None, ptr(read_off),
+            ptr(nbuf) if nbuf is not None else None, ptr(noff) if noff is not None else None, ptr(out), cap, C.byref(used))
+    if rc != GB_OK:
+        raise GbError(rc, "gb_emit_" + kind)
+    return out[: used.value].tobytes().decode()
 
 
 class FragmentDistribution:
