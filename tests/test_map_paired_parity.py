@@ -176,6 +176,19 @@ def test_map_paired_rescue_parity_branchy_graph():
 
 
 @pytest.mark.gpu
+def test_rescue_seed_limit_beyond_the_workspace_is_refused_loudly():
+    g = synth.make_tiny_graph()
+    index = g.build_index()
+    dev = capi.Device(index)
+    rs = synth.simulate_pairs(g, 4, frag_mean=300, frag_sd=20, sub_rate=0.0, seed=1)
+    p = H.paired_params(300, 20)
+    p.max_rescue_attempts = 15; p.rescue_seed_limit = 500
+    with pytest.raises(capi.GbError):
+        H.gpu_map(dev, rs.reads, rs.quals, p, paired=True)
+    dev.close()
+
+
+@pytest.mark.gpu
 def test_map_paired_rescue_on_clean_pairs_matches_no_rescue_path():
     """Pairs whose mates both cluster go through the thread-per-pair fast path even with rescue enabled."""
     g = synth.make_variant_graph(length=200000, n_snp=320, n_ins=40, n_del=40, n_haps=8, seed=2)
