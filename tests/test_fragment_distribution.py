@@ -95,6 +95,37 @@ def _job_inputs(n_pairs, seed):
     return g, rs
 
 
+def test_oracle_job_routes_and_records_are_consistent_with_its_parts():
+    """The job restatement against its own building blocks: training pairs are exactly the first `max_n` pairs (input
+    order) whose ends both map uniquely and near-perfectly, their records are the single-end results; every other pair
+    carries the paired result under the learned distribution; pairs seen while training that did not qualify are buffered."""
+    n_pairs, max_n = 700, 200
+    g, rs = _job_inputs(n_pairs, seed=77)
+    index = g.build_index()
+    p = H.default_map_params(); p.fragment_mean = 0.0; p.fragment_stdev = 0.0
+    aln, maps, edits, status, route, (mean, sd, n) = H.oracle_map_paired_job(index, rs.reads, rs.quals, p, max_n, 50, 0.95, threads=8)
+    assert n == max_n and (route == capi.GB_PAIR_TRAINING).sum() == max_n
+    last_training = int(np.nonzero(route == capi.GB_PAIR_TRAINING)[0][-1])
+    assert (route[last_training + 1:] == capi.GB_PAIR_PAIRED).all()                 # nothing is trained on or buffered after finalization
+    assert set(np.unique(route[:last_training + 1]).tolist()) <= {capi.GB_PAIR_TRAINING, capi.GB_PAIR_BUFFERED}
+    assert (route[:last_training + 1] == capi.GB_PAIR_BUFFERED).sum() >= 10
+    se = H.oracle_map(index, rs.reads, rs.quals, threads=8)
+    p2 = H.default_map_params(); p2.fragment_mean = mean; p2.fragment_stdev = sd
+    pe = H.oracle_map_paired(index, rs.reads, rs.quals, p2, threads=8)
+    got = (aln, maps, edits, status)
+    train_reads = np.nonzero(np.repeat(route == capi.GB_PAIR_TRAINING, 2))[0].tolist()
+    other_reads = np.nonzero(np.repeat(route != capi.GB_PAIR_TRAINING, 2))[0].tolist()
+    assert not H.compare_alignments(got, se, rs.n, mapq_tol=0, indices=train_reads)
+    assert not H.compare_alignments(got, pe, rs.n, mapq_tol=0, indices=other_reads)
+    # the qualifying rule itself (minimizer_mapper.cpp:1316-1322): MAPQ 60 and score >= 0.85 * match * L on both ends
+    for pair in range(last_training + 1):
+        perfect = all((se[0][2 * pair + r]["flags"] & 1) and se[0][2 * pair + r]["mapq"] == 60 and se[0][2 * pair + r]["score"] >= 0.85 * rs.length
+                      for r in range(2))
+        if route[pair] == capi.GB_PAIR_TRAINING:
+            assert perfect
+    assert abs(mean - 380) < 20 and abs(sd - 45) < 15
+
+
 @pytest.mark.gpu
 @pytest.mark.parametrize("n_pairs,max_n,freq,window", [(2500, 1000, 1000, 0), (1500, 300, 100, 128), (400, 1000, 1000, 64)])
 def test_paired_job_with_fragment_length_training(n_pairs, max_n, freq, window):
