@@ -34,6 +34,7 @@ sys.path.insert(0, str(ROOT / "tests"))
 READ_LEN = 150
 FRAG_MEAN, FRAG_SD = 400.0, 50.0
 SUB_RATE = 0.002
+INDEL_RATE = 0.0002        # per base; at most one 1-bp insertion or deletion per read, half each
 GRAPH_SEED = 2
 
 
@@ -55,7 +56,8 @@ def make_graph_and_index():
 
 
 def simulate_pairs_torch(g, n_pairs, seed, device):
-    """GPU version of synth.simulate_pairs (inward 150 bp pairs, fragment N(400, 50), 0.2 % substitutions)."""
+    """GPU version of synth.simulate_pairs (inward 150 bp pairs, fragment N(400, 50), 0.2 % substitutions,
+    0.02 % indels)."""
     import torch
     gen = torch.Generator(device=device)
     gen.manual_seed(seed)
@@ -74,15 +76,30 @@ def simulate_pairs_torch(g, n_pairs, seed, device):
         frag = torch.clamp(torch.round(torch.randn(cn, generator=gen, device=device) * FRAG_SD + FRAG_MEAN), min=READ_LEN).long()
         start = (torch.rand(cn, generator=gen, device=device) * (min_len - 1000)).long()
         flip = torch.rand(cn, generator=gen, device=device) < 0.5
+        # one 1-bp indel per read with probability 1 - (1 - INDEL_RATE)^L: a deletion skips haplotype base p,
+        # an insertion puts a random base at p and shifts the rest (both in haplotype coordinates of the window)
+        def indel_events():
+            hit = torch.rand(cn, generator=gen, device=device) < 1.0 - (1.0 - INDEL_RATE) ** READ_LEN
+            kind = torch.where(hit, torch.randint(1, 3, (cn,), generator=gen, device=device), torch.zeros(cn, dtype=torch.long, device=device))
+            pos = torch.randint(1, READ_LEN - 1, (cn,), generator=gen, device=device)
+            ins = bases[torch.randint(0, 4, (cn,), generator=gen, device=device)]
+            off = (kind[:, None] == 1).long() * (ar[None, :] >= pos[:, None]).long() - (kind[:, None] == 2).long() * (ar[None, :] > pos[:, None]).long()
+            return kind, pos, ins, off
+        kind_l, pos_l, ins_l, off_l = indel_events()
+        kind_r, pos_r, ins_r, off_r = indel_events()
         left = torch.empty((cn, READ_LEN), dtype=torch.uint8, device=device)
         right = torch.empty((cn, READ_LEN), dtype=torch.uint8, device=device)
         for h in range(len(haps)):
             sel = (hap == h).nonzero(as_tuple=True)[0]
             if sel.numel() == 0:
                 continue
-            left[sel] = haps[h][start[sel, None] + ar[None, :]]
             rs = start[sel] + frag[sel] - READ_LEN
-            right[sel] = comp[haps[h][rs[:, None] + ar[None, :]].long()].flip(1)
+            lwin = haps[h][start[sel, None] + ar[None, :] + off_l[sel]]
+            rwin = haps[h][rs[:, None] + ar[None, :] + off_r[sel]]
+            lwin = torch.where((kind_l[sel, None] == 2) & (ar[None, :] == pos_l[sel, None]), ins_l[sel, None], lwin)
+            rwin = torch.where((kind_r[sel, None] == 2) & (ar[None, :] == pos_r[sel, None]), ins_r[sel, None], rwin)
+            left[sel] = lwin
+            right[sel] = comp[rwin.long()].flip(1)
         m1 = torch.where(flip[:, None], right, left)
         m2 = torch.where(flip[:, None], left, right)
         reads[2 * c0: 2 * (c0 + cn): 2] = m1
@@ -103,7 +120,7 @@ def simulate_pairs_torch(g, n_pairs, seed, device):
 
 def simulate_pairs_numpy(g, n_pairs, seed):
     from vg_b200 import synth
-    rs = synth.simulate_pairs(g, n_pairs, length=READ_LEN, frag_mean=FRAG_MEAN, frag_sd=FRAG_SD, sub_rate=SUB_RATE, seed=seed)
+    rs = synth.simulate_pairs(g, n_pairs, length=READ_LEN, frag_mean=FRAG_MEAN, frag_sd=FRAG_SD, sub_rate=SUB_RATE, indel_rate=INDEL_RATE, seed=seed)
     return rs.reads, rs.quals
 
 
@@ -286,7 +303,7 @@ def main():
             "impl": "reference", "metric": "giraffe reads/sec (150 bp PE, synthetic)", "value": value, "unit": "reads/s",
             "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "int32", "data": "synthetic",
-            "config": {"workload": "configs[1]: 1 Mbp / 1k-variant graph, 150 bp PE reads, fragment N(400,50) forced, rescue attempts " + str(args.rescue_attempts),
+            "config": {"workload": "configs[1]: 1 Mbp / 1k-variant graph, 150 bp PE reads, fragment N(400,50) forced, 0.2 % substitutions, 0.02 % indels, rescue attempts " + str(args.rescue_attempts),
                        "reads_per_step": used, "note": "CPU restatement of vg giraffe (oracle/, OpenMP over read pairs); vg itself cannot be built in this image"},
             "cpu_baseline": {"value": value, "unit": "reads/s", "cores": threads, "kind": "port", "sample": f"{used} reads per step, {flags}, {cpu_note}"},
             "e2e": {"value": value, "unit": "reads/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
@@ -486,7 +503,7 @@ def main():
         "vs_baseline": None, "dtype": "int32", "data": "synthetic",
         "config": {
             "workload": "configs[1]: 1 Mbp random graph, 1k SNP+indel variants, 8 haplotypes, nodes <= 32 bp, k=29 w=11; "
-                        "150 bp paired-end reads, fragment N(400,50) forced, 0.2 % substitutions",
+                        "150 bp paired-end reads, fragment N(400,50) forced, 0.2 % substitutions, 0.02 % indels (SURVEY §8(d) config 2)",
             "reads_per_gpu_per_step": n_reads, "pairs_per_gpu_per_step": n_reads // 2,
             "mapper": f"map_paired, vg giraffe defaults (--rescue-attempts {args.rescue_attempts}), forced fragment distribution",
             "chunk_reads": CHUNK, "l2_policy": "inputs larger than L2 (3 GB of reads+qualities per step)",

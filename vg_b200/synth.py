@@ -238,8 +238,10 @@ def simulate_reads(g: SynthGraph, n: int, length=150, sub_rate=0.01, ins_rate=0.
 
 
 def simulate_pairs(g: SynthGraph, n_pairs: int, length=150, frag_mean=400.0, frag_sd=50.0,
-                   sub_rate=0.002, seed=22, qual=30) -> ReadSet:
-    """Paired-end reads, inward orientation: reads[2i] is mate 1, reads[2i+1] mate 2."""
+                   sub_rate=0.002, seed=22, qual=30, indel_rate=0.0) -> ReadSet:
+    """Paired-end reads, inward orientation: reads[2i] is mate 1, reads[2i+1] mate 2.
+    indel_rate (per base): at most one 1-bp insertion or deletion per read, half each, applied in
+    haplotype coordinates of the read's window (a deletion skips a base, an insertion adds a random one)."""
     rng = np.random.default_rng(seed)
     hap = rng.integers(0, len(g.paths), size=n_pairs)
     frag = np.clip(np.rint(rng.normal(frag_mean, frag_sd, size=n_pairs)).astype(np.int64), length, None)
@@ -252,9 +254,23 @@ def simulate_pairs(g: SynthGraph, n_pairs: int, length=150, frag_mean=400.0, fra
             continue
         hs = g.hap_seq[h]
         start = rng.integers(0, len(hs) - frag[sel].max() - 1, size=len(sel))
-        left = hs[start[:, None] + np.arange(length)[None, :]]
         rstart = start + frag[sel] - length
-        right = revcomp_bytes(hs[rstart[:, None] + np.arange(length)[None, :]])
+        ar = np.arange(length)[None, :]
+        if indel_rate > 0:
+            wins = []
+            for w0 in (start, rstart):
+                hit = rng.random(len(sel)) < 1.0 - (1.0 - indel_rate) ** length
+                kind = np.where(hit, rng.integers(1, 3, size=len(sel)), 0)
+                p = rng.integers(1, length - 1, size=len(sel))
+                ins = BASES[rng.integers(0, 4, size=len(sel))]
+                off = ((kind[:, None] == 1) & (ar >= p[:, None])).astype(np.int64) - ((kind[:, None] == 2) & (ar > p[:, None])).astype(np.int64)
+                win = hs[w0[:, None] + ar + off]
+                win = np.where((kind[:, None] == 2) & (ar == p[:, None]), ins[:, None], win)
+                wins.append(win)
+            left, right = wins[0], revcomp_bytes(wins[1])
+        else:
+            left = hs[start[:, None] + ar]
+            right = revcomp_bytes(hs[rstart[:, None] + ar])
         f = flip[sel]
         m1 = np.where(f[:, None], right, left)
         m2 = np.where(f[:, None], left, right)
