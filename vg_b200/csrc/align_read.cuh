@@ -18,8 +18,9 @@ struct AlignArgs {
     const PairState* pairs; double frag_mean, frag_sd;
     // work list written by the thread-per-pair fast path (nullptr: every pair)
     const uint32_t* slow_list; const uint32_t* slow_count;
-    // mate rescue (max_rescue_attempts != 0): per-warp workspace
+    // mate rescue (max_rescue_attempts != 0): per-warp workspace; pairs found to need it by the plain kernel
     uint8_t* rescue_base; size_t rescue_stride;
+    uint32_t* rescue_list; uint32_t* rescue_count;
 };
 
 constexpr uint32_t N_SLOTS = 2 * MAX_CANDS + 8 + 32;   // candidate path slots per warp (both mates of a pair, + rescued alignments)
@@ -491,6 +492,7 @@ __device__ inline uint32_t finalize_pe(const DevIndex& ix, const MapParamsDev& P
         }
     }
     if (status != GB_ITEM_OK) return status;
+    if (n_unpaired > 0 && P.max_rescue_attempts != 0) return GB_ITEM_RETRY;     // needs mate rescue: the rescue kernel redoes this pair
 
     if (n_unpaired > 0 && !found_pair) {
         // max_rescue_attempts == 0 (:2227-2287): best alignment of each end, MAPQ 1

@@ -97,6 +97,7 @@ struct gb_device {
     gb::DevBuf<gb::PairState> p_pairs;
     gb::DevBuf<uint32_t> p_retry;         // units the first seeding pass could not fit
     gb::DevBuf<uint32_t> p_slow;          // pairs routed to the warp-per-pair align kernel
+    gb::DevBuf<uint32_t> p_rescue;        // pairs the plain kernel defers to the rescue instantiation
     gb::DevBuf<gb_mapping> pad_maps;
     gb::DevBuf<uint32_t> pad_edits;
     gb::DevBuf<uint64_t> c_map_off, c_edit_off, c_totals;
@@ -121,7 +122,7 @@ struct gb_device {
         ws_queue.release(); ws_arena.release();
         t_hit.release(); t_plo.release(); t_phred.release(); p_states.release(); p_min.release(); p_seeds.release();
         p_items.release(); p_ext_seeds.release(); p_cursors.release(); p_ext_count.release(); p_path.release(); p_mism.release();
-        p_ext_status.release(); p_ext.release(); ws_tail.release(); ws_cand.release(); ws_rescue.release(); w_reads.release(); w_quals.release(); p_pairs.release(); p_slow.release(); p_retry.release();
+        p_ext_status.release(); p_ext.release(); ws_tail.release(); ws_cand.release(); ws_rescue.release(); w_reads.release(); w_quals.release(); p_pairs.release(); p_slow.release(); p_rescue.release(); p_retry.release();
         pad_maps.release(); pad_edits.release(); c_map_off.release(); c_edit_off.release(); c_totals.release(); c_tmp.release();
         io[0].release(); io[1].release(); c_run.release();
     }

@@ -323,15 +323,17 @@ int map_device(gb_device* d, const gb_map_params* hp, uint32_t n_reads, const ui
         }
         int bps = 0;
         const bool rescue = paired && hp->max_rescue_attempts != 0;
-        if (rescue) GB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bps, align_kernel_pe<true>, ALIGN_WARPS * 32, smem));
-        else if (paired) GB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bps, align_kernel_pe<false>, ALIGN_WARPS * 32, smem));
+        int bps_rescue = 0;
+        if (rescue) GB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bps_rescue, align_kernel_pe<true>, ALIGN_WARPS * 32, smem));
+        if (paired) GB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bps, align_kernel_pe<false>, ALIGN_WARPS * 32, smem));
         else GB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bps, align_kernel, ALIGN_WARPS * 32, smem));
         if (bps < 1) bps = 1;
         if (bps > 4) bps = 4;          // bounds the per-warp tail workspaces (about 2 MB each)
-        if (rescue && bps > 2) bps = 2;   // + the rescue workspaces (about 2 MB each)
-        uint32_t grid = std::min<uint32_t>((uint32_t)(d->n_sms * bps), (n_reads + ALIGN_WARPS - 1) / ALIGN_WARPS);
-        if (grid == 0) grid = 1;
-        const size_t n_warps = (size_t)grid * ALIGN_WARPS;
+        uint32_t grid_plain = std::min<uint32_t>((uint32_t)(d->n_sms * bps), (n_reads + ALIGN_WARPS - 1) / ALIGN_WARPS);
+        if (grid_plain == 0) grid_plain = 1;
+        bps_rescue = std::max(1, std::min(bps_rescue, 2));     // + the rescue workspaces (about 2 MB each)
+        uint32_t grid = rescue ? std::min<uint32_t>((uint32_t)(d->n_sms * bps_rescue), grid_plain) : grid_plain;
+        const size_t n_warps = (size_t)grid_plain * ALIGN_WARPS;
         const uint32_t tb_cells = hp->max_dozeu_cells + hp->max_dozeu_cells / 4 + 4096;
         const size_t ws_stride = tail_ws_bytes(Lc, tb_cells);
         const size_t cand_stride = (((size_t)hp->mapping_cap_per_read * sizeof(gb_mapping) + (size_t)hp->edit_cap_per_read * 4) * (N_SLOTS + N_TEMP_SLOTS) + 255) & ~(size_t)255;
@@ -341,7 +343,8 @@ int map_device(gb_device* d, const gb_map_params* hp, uint32_t n_reads, const ui
         a.rescue_base = nullptr; a.rescue_stride = 0;
         if (rescue) {
             a.rescue_stride = (rescue_ws_bytes(Lc) + 255) & ~(size_t)255;
-            if ((rc = d->ws_rescue.reserve(a.rescue_stride * n_warps))) return rc;
+            if ((rc = d->ws_rescue.reserve(a.rescue_stride * (size_t)grid * ALIGN_WARPS))) return rc;
+            if ((rc = d->p_rescue.reserve(n_reads / 2 + 1))) return rc;
             a.rescue_base = d->ws_rescue.ptr;
         }
         a.items = d->p_items.ptr; a.minimizers = d->p_min.ptr;
@@ -362,8 +365,19 @@ int map_device(gb_device* d, const gb_map_params* hp, uint32_t n_reads, const ui
         d->launches++;
         GB_CUDA(cudaGetLastError());
         a.slow_list = d->p_slow.ptr; a.slow_count = cur + 7;
-        if (rescue) align_kernel_pe<true><<<grid, ALIGN_WARPS * 32, smem, d->stream>>>(d->ix, P, d->sc, b3, a);
-        else if (paired) align_kernel_pe<false><<<grid, ALIGN_WARPS * 32, smem, d->stream>>>(d->ix, P, d->sc, b3, a);
+        if (paired) {
+            // the plain kernel takes every listed pair; with rescue enabled it defers the pairs that turn out to have
+            // unpaired alignments to a second list, which the (larger, lower-occupancy) rescue instantiation redoes
+            a.rescue_list = d->p_rescue.ptr; a.rescue_count = cur + 11;
+            align_kernel_pe<false><<<grid_plain, ALIGN_WARPS * 32, smem, d->stream>>>(d->ix, P, d->sc, b3, a);
+            if (rescue) {
+                d->launches++;
+                GB_CUDA(cudaGetLastError());
+                b3.work_counter = cur + 12;
+                a.slow_list = d->p_rescue.ptr; a.slow_count = cur + 11;
+                align_kernel_pe<true><<<grid, ALIGN_WARPS * 32, smem, d->stream>>>(d->ix, P, d->sc, b3, a);
+            }
+        }
         else align_kernel<<<grid, ALIGN_WARPS * 32, smem, d->stream>>>(d->ix, P, d->sc, b3, a);
         d->launches++;
         GB_CUDA(cudaGetLastError());

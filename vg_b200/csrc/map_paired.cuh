@@ -163,6 +163,12 @@ align_kernel_pe(DevIndex ix, MapParamsDev P, DevScores sc, MapBatch b, AlignArgs
                     status = finalize_pe(ix, P, rs, ps, a, cl, explored, rng, sr, sq, L, 2 * p, dps, cand_base, out, out_maps, out_edits);
             }
         }
+        if (!RESCUE && status == GB_ITEM_RETRY) {
+            // unpaired alignments and rescue enabled: hand the pair to the rescue instantiation of this kernel
+            if (lane == 0) a.rescue_list[atomicAdd(a.rescue_count, 1u)] = p;
+            __syncwarp();
+            continue;
+        }
         for (uint32_t r = 0; r < 2; r++) {
             const uint32_t ri = 2 * p + r;
             out[r].mapping_off = ri * P.mapping_cap; out[r].edit_off = ri * P.edit_cap;
