@@ -12,6 +12,8 @@ rep = next((a for a in sys.argv[3:] if a.endswith(".ncu-rep")), None)
 reads = int(sys.argv[sys.argv.index("--reads") + 1]) if "--reads" in sys.argv else None
 
 def short(name):
+    t = re.search(r"(?:gb::)?(\w+)<\(bool\)(\d)>\(", name)          # align_kernel_pe<(bool)1>(...) = the rescue instantiation
+    if t: return t.group(1) + ("<rescue>" if t.group(2) == "1" else "")
     m = re.search(r"(?:gb::)?(\w+)\(", name)
     if "DeviceScan" in name: return "cub::DeviceScan"
     if "at::" in name or "at_cuda_detail" in name: return "torch (input synthesis)"
