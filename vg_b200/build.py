@@ -49,7 +49,8 @@ def build(force: bool = False, verbose: bool = False) -> Path:
     digest = _digest()
     if not force and LIB.exists() and STAMP.exists() and STAMP.read_text() == digest:
         return LIB
-    cmd = [_nvcc(), *NVCC_FLAGS, "-shared", "-o", str(LIB), "-I", str(ROOT / "include"), "-I", str(CSRC)]
+    tmp = LIB.with_suffix(".so.tmp")          # link to a scratch name, then rename: a reader never sees a torn library
+    cmd = [_nvcc(), *NVCC_FLAGS, "-shared", "-o", str(tmp), "-I", str(ROOT / "include"), "-I", str(CSRC)]
     if os.path.exists("/usr/bin/g++"):
         cmd += ["-ccbin", "/usr/bin/g++"]
     if verbose:
@@ -61,6 +62,7 @@ def build(force: bool = False, verbose: bool = False) -> Path:
         raise RuntimeError("nvcc failed")
     if verbose:
         sys.stderr.write(res.stdout + res.stderr)
+    os.replace(tmp, LIB)
     STAMP.write_text(digest)
     return LIB
 

@@ -265,9 +265,16 @@ __device__ inline uint32_t align_sets(const DevIndex& ix, const MapParamsDev& P,
                 }
                 int32_t left_score = 0, right_score = 0;
                 pb_reset(res_left); pb_reset(res_right);
-                if (!(e.flags & GB_EXT_LEFT_FULL)) left_score = align_tail(ix, P, sc, ws, dps, e, path_pool, sread, L, true, qbuf, rng, res_left, scratch, status);
-                if (status != GB_ITEM_OK) break;
-                if (!(e.flags & GB_EXT_RIGHT_FULL)) right_score = align_tail(ix, P, sc, ws, dps, e, path_pool, sread, L, false, qbuf, rng, res_right, scratch, status);
+                // one call site for both tails (left first): the forest / DP / traceback code exists once per kernel, so
+                // warps working on different tails share the instruction cache (the align kernels are fetch-bound)
+#pragma unroll 1
+                for (uint32_t side = 0; side < 2 && status == GB_ITEM_OK; side++) {
+                    const bool left_tail = side == 0;
+                    if (e.flags & (left_tail ? GB_EXT_LEFT_FULL : GB_EXT_RIGHT_FULL)) continue;
+                    PathBuf* res = left_tail ? &res_left : &res_right;
+                    const int32_t tail_score = align_tail(ix, P, sc, ws, dps, e, path_pool, sread, L, left_tail, qbuf, rng, *res, scratch, status);
+                    if (left_tail) left_score = tail_score; else right_score = tail_score;
+                }
                 if (status != GB_ITEM_OK) break;
                 const int32_t total_score = e.score + left_score + right_score;
                 const uint32_t first_node = path_pool[e.path_off], last_node = path_pool[e.path_off + e.path_len - 1];

@@ -151,7 +151,8 @@ align_kernel_pe(DevIndex ix, MapParamsDev P, DevScores sc, MapBatch b, AlignArgs
             for (uint32_t i = 0; i < N_SLOTS; i++) slot_used[i] = false;
             CandList cl; cl.n = 0;
             uint32_t explored[2][PRESENT_WORDS];
-            for (uint32_t r = 0; r < 2 && status == GB_ITEM_OK; r++)
+#pragma unroll 1
+            for (uint32_t r = 0; r < 2 && status == GB_ITEM_OK; r++)          // one copy of align_sets per kernel (instruction cache)
                 status = align_sets(ix, P, sc, rs[r], a, sread[r], L[r], ws, dps, qbuf, cand_base, slot_used, rng, true, r, cl, explored[r]);
             if (status == GB_ITEM_OK) {
                 const uint8_t* sr[2] = {sread[0], sread[1]};
