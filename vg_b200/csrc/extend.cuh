@@ -225,7 +225,7 @@ __device__ __forceinline__ bool ext_equal(const gb_extension& a, const gb_extens
 }
 
 // Stable insertion sort + dedupe of the output records by lane 0 (n is small).
-__device__ inline uint32_t remove_duplicates(gb_extension* ext, uint32_t n) {
+static __device__ __noinline__ uint32_t remove_duplicates(gb_extension* ext, uint32_t n) {
     if (lane_id() == 0) {
         for (uint32_t i = 1; i < n; i++) {
             gb_extension key = ext[i];
@@ -447,89 +447,66 @@ __device__ inline uint32_t extend_item(const DevIndex& ix, const ExtendParams& p
         while (qn > 0) {
             QEntry curr = q_pop(queue, qn);
 
-            if (!(curr.flags & F_RIGHT_MAX)) {
-                // Case 1: extend to the right (gbwt_extender.cpp:602-643)
-                uint32_t num_extensions = 0;
+            // Cases 1 and 2 (gbwt_extender.cpp:602-643 right, :646-686 left) share one body: the kernel is
+            // instruction-fetch bound, so the walk over the GBWT edges exists once and the direction is data.
+            const bool go_right = !(curr.flags & F_RIGHT_MAX);
+            if (go_right || !(curr.flags & F_LEFT_MAX)) {
+                uint32_t num_extensions = 0; bool found_extension = false;
                 const uint32_t limit = mismatch_limit_of(p.max_mismatches, curr.old_score);
                 BdState cs; cs.fnode = curr.fnode; cs.flo = curr.flo; cs.fhi = curr.fhi; cs.bnode = curr.bnode; cs.blo = curr.blo; cs.bhi = curr.bhi;
-                const gb_node_rec crec = load_node(ix, cs.fnode);
-                const EdgeFan fan = record_fan(ix, crec, cs.flo, cs.fhi);
+                const BdState walk = go_right ? cs : bd_flip(cs);
+                const gb_node_rec crec = load_node(ix, walk.fnode);
+                const EdgeFan fan = record_fan(ix, crec, walk.flo, walk.fhi);
                 for (uint32_t e = 0; e < fan.n_edges; e++) {
                     uint32_t to; int32_t first, cnt, rev;
                     if (fan.n_edges <= 32) {
                         to = __shfl_sync(FULL, fan.to, e); first = __shfl_sync(FULL, fan.first, e);
                         cnt = __shfl_sync(FULL, fan.cnt, e); rev = __shfl_sync(FULL, fan.rev, e);
                     } else {
-                        record_edge_generic(ix, crec, cs.flo, cs.fhi, e, to, first, cnt, rev);
+                        record_edge_generic(ix, crec, walk.flo, walk.fhi, e, to, first, cnt, rev);
                     }
                     if (to == 0 || cnt <= 0) continue;
-                    const BdState ns = bd_apply(cs, to, first, cnt, rev);
-                    const gb_node_rec nrec = load_node(ix, to);
-                    QEntry next = curr;
-                    next.fnode = ns.fnode; next.flo = ns.flo; next.fhi = ns.fhi; next.bnode = ns.bnode; next.blo = ns.blo; next.bhi = ns.bhi;
-                    uint32_t internal = curr.internal_score;
-                    const uint32_t count = min(read_len - curr.read_hi, nrec.len);
-                    const uint32_t node_offset = match_fwd(sread, curr.read_hi, ix.seq + nrec.seq_off, 0, count, internal, limit);
-                    if (node_offset == 0) continue;
-                    next.read_hi = curr.read_hi + node_offset; next.internal_score = internal;
-                    if (an >= a_cap || qn + 1 >= q_cap) { status = GB_ITEM_QUEUE_FULL; break; }
-                    if (lane == 0) arena[an] = ArenaNode{to, curr.right_tail};
-                    next.right_tail = an++;
-                    if (next.read_hi >= read_len) { next.flags |= F_RIGHT_FULL | F_RIGHT_MAX; next.old_score = next.internal_score; }
-                    else if (node_offset < nrec.len) { next.flags |= F_RIGHT_MAX; next.old_score = next.internal_score; }
-                    set_score(next, p.sc);
-                    num_extensions += (uint32_t)cnt;
-                    next.number = number++;
-                    q_store(queue + qn, next); qn++;
-                }
-                if (status != GB_ITEM_OK) break;
-                if (num_extensions < (uint32_t)cs.size()) {
-                    curr.flags |= F_RIGHT_MAX; curr.old_score = curr.internal_score; curr.number = number++;
-                    if (qn + 1 >= q_cap) { status = GB_ITEM_QUEUE_FULL; break; }
-                    q_store(queue + qn, curr); qn++;
-                }
-                __syncwarp();
-                continue;
-            }
-
-            if (!(curr.flags & F_LEFT_MAX)) {
-                // Case 2: extend to the left (gbwt_extender.cpp:646-686)
-                bool found_extension = false;
-                const uint32_t limit = mismatch_limit_of(p.max_mismatches, curr.old_score);
-                BdState cs; cs.fnode = curr.fnode; cs.flo = curr.flo; cs.fhi = curr.fhi; cs.bnode = curr.bnode; cs.blo = curr.blo; cs.bhi = curr.bhi;
-                const BdState fs = bd_flip(cs);
-                const gb_node_rec crec = load_node(ix, fs.fnode);
-                const EdgeFan fan = record_fan(ix, crec, fs.flo, fs.fhi);
-                for (uint32_t e = 0; e < fan.n_edges; e++) {
-                    uint32_t to; int32_t first, cnt, rev;
-                    if (fan.n_edges <= 32) {
-                        to = __shfl_sync(FULL, fan.to, e); first = __shfl_sync(FULL, fan.first, e);
-                        cnt = __shfl_sync(FULL, fan.cnt, e); rev = __shfl_sync(FULL, fan.rev, e);
-                    } else {
-                        record_edge_generic(ix, crec, fs.flo, fs.fhi, e, to, first, cnt, rev);
-                    }
-                    if (to == 0 || cnt <= 0) continue;
-                    const BdState ns = bd_flip(bd_apply(fs, to, first, cnt, rev));
-                    const uint32_t handle = to ^ 1u;      // gbwt_extender.cpp:653
+                    BdState ns = bd_apply(walk, to, first, cnt, rev);
+                    if (!go_right) ns = bd_flip(ns);
+                    const uint32_t handle = go_right ? to : (to ^ 1u);      // gbwt_extender.cpp:653
                     const gb_node_rec nrec = load_node(ix, handle);
                     QEntry next = curr;
                     next.fnode = ns.fnode; next.flo = ns.flo; next.fhi = ns.fhi; next.bnode = ns.bnode; next.blo = ns.blo; next.bhi = ns.bhi;
                     uint32_t internal = curr.internal_score;
-                    const uint32_t count = min(curr.read_lo, nrec.len);
-                    const uint32_t used = match_bwd(sread, curr.read_lo, ix.seq + nrec.seq_off, nrec.len, count, internal, limit);
-                    if (used == 0) continue;               // next.offset >= node_length
-                    next.read_lo = curr.read_lo - used; next.offset = nrec.len - used; next.internal_score = internal;
+                    uint32_t used;
+                    if (go_right) used = match_fwd(sread, curr.read_hi, ix.seq + nrec.seq_off, 0, min(read_len - curr.read_hi, nrec.len), internal, limit);
+                    else used = match_bwd(sread, curr.read_lo, ix.seq + nrec.seq_off, nrec.len, min(curr.read_lo, nrec.len), internal, limit);
+                    if (used == 0) continue;               // no base matched within the mismatch budget
+                    next.internal_score = internal;
                     if (an >= a_cap || qn + 1 >= q_cap) { status = GB_ITEM_QUEUE_FULL; break; }
-                    if (lane == 0) arena[an] = ArenaNode{handle, curr.left_head};
-                    next.left_head = an++;
-                    if (next.read_lo == 0) next.flags |= F_LEFT_FULL | F_LEFT_MAX;
-                    else if (next.offset > 0) next.flags |= F_LEFT_MAX;
+                    if (lane == 0) arena[an] = ArenaNode{handle, go_right ? curr.right_tail : curr.left_head};
+                    if (go_right) {
+                        next.read_hi = curr.read_hi + used;
+                        next.right_tail = an++;
+                        if (next.read_hi >= read_len) { next.flags |= F_RIGHT_FULL | F_RIGHT_MAX; next.old_score = next.internal_score; }
+                        else if (used < nrec.len) { next.flags |= F_RIGHT_MAX; next.old_score = next.internal_score; }
+                        num_extensions += (uint32_t)cnt;
+                    } else {
+                        next.read_lo = curr.read_lo - used; next.offset = nrec.len - used;
+                        next.left_head = an++;
+                        if (next.read_lo == 0) next.flags |= F_LEFT_FULL | F_LEFT_MAX;
+                        else if (next.offset > 0) next.flags |= F_LEFT_MAX;
+                        found_extension = true;
+                    }
                     set_score(next, p.sc);
                     next.number = number++;
                     q_store(queue + qn, next); qn++;
-                    found_extension = true;
                 }
                 if (status != GB_ITEM_OK) break;
+                if (go_right) {
+                    if (num_extensions < (uint32_t)cs.size()) {
+                        curr.flags |= F_RIGHT_MAX; curr.old_score = curr.internal_score; curr.number = number++;
+                        if (qn + 1 >= q_cap) { status = GB_ITEM_QUEUE_FULL; break; }
+                        q_store(queue + qn, curr); qn++;
+                    }
+                    __syncwarp();
+                    continue;
+                }
                 __syncwarp();
                 if (!found_extension) curr.flags |= F_LEFT_MAX;
                 else continue;
@@ -602,7 +579,8 @@ __device__ inline uint32_t extend_item(const DevIndex& ix, const ExtendParams& p
     __syncwarp();
 
     uint32_t mism_used = 0;
-    if (best_alignment != NONE && best_alignment_mm <= p.max_mismatches) {
+    const bool full_length_branch = best_alignment != NONE && best_alignment_mm <= p.max_mismatches;
+    if (full_length_branch) {
         // handle_full_length (gbwt_extender.cpp:301-329), stable
         if (lane == 0) {
             for (uint32_t i = 1; i < n_res; i++) {
@@ -634,20 +612,17 @@ __device__ inline uint32_t extend_item(const DevIndex& ix, const ExtendParams& p
         }
         n_res = __shfl_sync(FULL, n_res, 0);
         __syncwarp();
-        for (uint32_t i = 0; i < n_res; i++) {
-            gb_extension e = ext[i];
-            if (!find_mismatches(ix, e, sread, path_pool, mism_pool, mism_used, p.mism_cap)) { status = GB_ITEM_OUT_FULL; break; }
-            __syncwarp();
-            if (lane == 0) ext[i] = e;
-        }
     } else {
         n_res = remove_duplicates(ext, n_res);
-        for (uint32_t i = 0; i < n_res; i++) {
-            gb_extension e = ext[i];
-            if (!find_mismatches(ix, e, sread, path_pool, mism_pool, mism_used, p.mism_cap)) { status = GB_ITEM_OUT_FULL; break; }
-            __syncwarp();
-            if (lane == 0) ext[i] = e;
-        }
+    }
+    // find_mismatches for every surviving extension (one call site for both branches)
+    for (uint32_t i = 0; i < n_res; i++) {
+        gb_extension e = ext[i];
+        if (!find_mismatches(ix, e, sread, path_pool, mism_pool, mism_used, p.mism_cap)) { status = GB_ITEM_OUT_FULL; break; }
+        __syncwarp();
+        if (lane == 0) ext[i] = e;
+    }
+    if (!full_length_branch) {
         __syncwarp();
         if (status == GB_ITEM_OK && p.trim) {
             bool trimmed = false;
