@@ -12,7 +12,7 @@ rep = next((a for a in sys.argv[3:] if a.endswith(".ncu-rep")), None)
 reads = int(sys.argv[sys.argv.index("--reads") + 1]) if "--reads" in sys.argv else None
 
 def short(name):
-    t = re.search(r"(?:gb::)?(\w+)<\(bool\)(\d)>\(", name)          # align_kernel_pe<(bool)1>(...) = the rescue instantiation
+    t = re.search(r"(?:gb::)?(\w+)<(?:\(bool\))?(\d)>\(", name)    # align_kernel_pe<1>(...) / <(bool)1>(...) = the rescue instantiation
     if t: return t.group(1) + ("<rescue>" if t.group(2) == "1" else "")
     m = re.search(r"(?:gb::)?(\w+)\(", name)
     if "DeviceScan" in name: return "cub::DeviceScan"

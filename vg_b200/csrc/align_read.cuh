@@ -123,6 +123,93 @@ __device__ inline double faster_cap(const MapParamsDev& P, const DevMinimizer* m
     return -c[n] * 10;
 }
 
+// faster_cap for the warp-per-read kernels: the same sweep, all lanes in step (mp / c in shared memory),
+// with the column probabilities of an interval evaluated 32 columns at a time and folded in column
+// order (p + q - p q is not associative, so the fold stays sequential: every lane folds the shuffled
+// values itself and all lanes hold the same p).  Bit-identical to faster_cap.
+__device__ inline double faster_cap_warp(const MapParamsDev& P, const DevMinimizer* mins, uint32_t k, const uint32_t* explored_mask, uint32_t M,
+                                         const uint8_t* qual, uint32_t L, uint64_t* mp, double* c) {
+    if (qual == nullptr) return INFINITY;
+    const int lane = lane_id();
+    uint32_t n = 0;
+    if (lane == 0) {
+        for (uint32_t i = 0; i < M; i++) if (explored_mask[i >> 5] & (1u << (i & 31))) {
+            const DevMinimizer dm = mins[i];
+            const uint32_t as = dm.agg_start, ae = (uint32_t)dm.agg_start + dm.agg_len;
+            const uint64_t wd = (uint64_t)as | ((uint64_t)ae << 16) | ((uint64_t)dm.fwd_offset << 32) | ((dm.hash >> 56) << 48);
+            const uint32_t key = (ae << 16) | as;
+            uint32_t j = n;
+            while (j > 0) {
+                const uint64_t o = mp[j - 1];
+                const uint32_t okey = ((uint32_t)(o >> 16) << 16) | (uint32_t)(o & 0xffffu);
+                if (key < okey) { mp[j] = o; j--; } else break;
+            }
+            mp[j] = wd; n++;
+        }
+    }
+    n = __shfl_sync(FULL, n, 0);
+    for (uint32_t i = lane; i <= n; i += 32) c[i] = i == 0 ? 0.0 : -INFINITY;
+    __syncwarp();
+    if (n == 0) return -c[n] * 10;
+    auto column_prob = [&](uint32_t begin, uint32_t end, uint32_t index) {
+        double p = P.phred_prob[qual[index]];
+        for (uint32_t it = begin; it != end; ++it) {
+            const uint64_t wd = mp[it];
+            const uint32_t as = (uint32_t)wd & 0xffffu, ae = (uint32_t)(wd >> 16) & 0xffffu, fwd = (uint32_t)(wd >> 32) & 0xffffu;
+            if (index - fwd >= k) {
+                const uint32_t possible = min(k, min(index - as + 1, ae - index));
+                p *= P.prob_at_least_one[(possible << 8) + (uint32_t)(wd >> 48)];
+            }
+        }
+        return p;
+    };
+    auto agg_start_of = [&](uint32_t it) { return (uint32_t)mp[it] & 0xffffu; };
+    auto agg_end_of = [&](uint32_t it) { return (uint32_t)(mp[it] >> 16) & 0xffffu; };
+    uint32_t front = 0, back = 1, left = agg_start_of(0), bottom = 0, it = 1;
+    bool final_phase = n == 1;
+    uint32_t pending_right = final_phase ? L : agg_start_of(1);
+    // all lanes walk the sweep identically; lane 0 applies the updates of c
+    auto close_interval = [&](uint32_t ib, uint32_t itop, double p_here) {
+        __syncwarp();
+        if (lane == 0) {
+            const double pv = c[ib] + p_here;
+            for (uint32_t i = ib + 1; i < itop + 1; i++) if (c[i] < pv) c[i] = pv;
+        }
+        __syncwarp();
+    };
+    while (true) {
+        if (left < pending_right) {
+            const uint32_t stack_size = back - front, stack_top_end = agg_end_of(front);
+            const uint32_t ib = bottom, itop = bottom + stack_size, col0 = left;
+            uint32_t right;
+            if (stack_top_end <= pending_right) {
+                right = stack_top_end;
+                left = stack_size == 1 ? pending_right : stack_top_end;
+                bottom += 1; front++;
+            } else { right = pending_right; left = pending_right; }
+            if (col0 == right) { close_interval(ib, itop, 0.0); continue; }
+            double p = 0.0; bool first = true;
+            for (uint32_t base = col0; base < right; base += 32) {
+                const uint32_t idx = base + lane;
+                const double cp = idx < right ? column_prob(ib, itop, idx) : 0.0;
+                const uint32_t cnt = min(32u, right - base);
+                for (uint32_t x = 0; x < cnt; x++) {
+                    const double col_p = __shfl_sync(FULL, cp, x);
+                    p = first ? col_p : (p + col_p - (p * col_p));
+                    first = false;
+                }
+            }
+            close_interval(ib, itop, log10(p));
+        } else if (final_phase) break;
+        else {
+            back++; it++;
+            if (it < n) pending_right = agg_start_of(it); else { pending_right = L; final_phase = true; }
+        }
+    }
+    __syncwarp();
+    return -c[n] * 10;
+}
+
 // MappingQualityCalculator::compute_max_mapping_quality (exact, no multiplicities),
 // mapping_quality_calculator.cpp:26-67, :355-364.  Returns the int32-truncated value as double.
 __device__ inline double max_mapping_quality(const double* scores, uint32_t n, double log_base) {
@@ -405,8 +492,7 @@ __device__ inline uint32_t finalize_se(const DevIndex& ix, const MapParamsDev& P
     double* cbuf = reinterpret_cast<double*>(dps.Hp);       // DP columns are free here (Hp|Ep and Hc|Ec)
     uint64_t* ordbuf = reinterpret_cast<uint64_t*>(dps.Hc);
     double cap = 0.0;
-    if (lane == 0) cap = escape_bonus * faster_cap(P, a.minimizers + rs.min_off, ix.k, explored, rs.min_cnt, qual, L, ordbuf, cbuf);
-    cap = __shfl_sync(FULL, cap, 0);
+    cap = escape_bonus * faster_cap_warp(P, a.minimizers + rs.min_off, ix.k, explored, rs.min_cnt, qual, L, ordbuf, cbuf);
     const double mapq_uncapped = mapq;
     mapq = round(fmin(cap, fmin(mapq, 60.0)));
     mapq = fmax(fmin(mapq, 60.0), 0.0);
@@ -541,10 +627,8 @@ __device__ inline uint32_t finalize_pe(const DevIndex& ix, const MapParamsDev& P
     double caps[2] = {0.0, 0.0};
     double* cbuf = reinterpret_cast<double*>(dps.Hp);
     uint64_t* ordbuf = reinterpret_cast<uint64_t*>(dps.Hc);
-    if (lane == 0) {
-        for (uint32_t r = 0; r < 2; r++) caps[r] = faster_cap(P, a.minimizers + rs[r].min_off, ix.k, explored[r], rs[r].min_cnt, qual[r], L[r], ordbuf, cbuf);
-    }
-    caps[0] = __shfl_sync(FULL, caps[0], 0); caps[1] = __shfl_sync(FULL, caps[1], 0);
+#pragma unroll 1
+    for (uint32_t r = 0; r < 2; r++) caps[r] = faster_cap_warp(P, a.minimizers + rs[r].min_off, ix.k, explored[r], rs[r].min_cnt, qual[r], L[r], ordbuf, cbuf);
     const uint32_t cwin[2] = {pair_c0[wp], pair_c1[wp]};
     for (uint32_t r = 0; r < 2; r++) {
         const double escape_bonus = uncapped_mapq < 2147483647.0 ? 1.0 : 2.0;

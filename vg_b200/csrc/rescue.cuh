@@ -515,8 +515,8 @@ __device__ inline uint32_t finalize_pe_rescue(const DevIndex& ix, const MapParam
     double caps[2] = {0.0, 0.0};
     double* cbuf = reinterpret_cast<double*>(dps.Hp);
     uint64_t* ordbuf = reinterpret_cast<uint64_t*>(dps.Hc);
-    if (lane == 0) for (uint32_t r = 0; r < 2; r++) caps[r] = faster_cap(P, a.minimizers + rs[r].min_off, ix.k, explored[r], rs[r].min_cnt, qual[r], L[r], ordbuf, cbuf);
-    caps[0] = __shfl_sync(FULL, caps[0], 0); caps[1] = __shfl_sync(FULL, caps[1], 0);
+#pragma unroll 1
+    for (uint32_t r = 0; r < 2; r++) caps[r] = faster_cap_warp(P, a.minimizers + rs[r].min_off, ix.k, explored[r], rs[r].min_cnt, qual[r], L[r], ordbuf, cbuf);
     const uint32_t cwin[2] = {pair_c0[wp], pair_c1[wp]};
     for (uint32_t r = 0; r < 2; r++) {
         const double escape_bonus = uncapped_mapq < 2147483647.0 ? 1.0 : 2.0;
