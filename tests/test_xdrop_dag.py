@@ -165,3 +165,69 @@ def test_cuda_xdrop_dag_linear_properties():
     for p, g in zip(problems, got):
         assert g == oracle_xdrop_dag(index, p[0], p[1], p[2].decode(), sc, p[3], p[4])
     dev.close()
+
+
+# ---- the reference's own align_xdrop vectors (src/unittest/xdrop_aligner.cpp:21-265, forward mode) ----------------
+# graph of :27-38 (a SNP bubble) and of :218-228 (a long homopolymer node in front of the true locus)
+_BUBBLE = {"nodes": ["AGTG", "C", "A", "TGAAGT"], "paths": [[1, 2, 4], [1, 3, 4]]}
+_BUBBLE_PREDS = [[], [0], [0], [1, 2]]
+_PINNED = {"nodes": ["GAAAAAAAAAAAAAAAAAAAAA", "C", "A", "TGATTACAT"], "paths": [[1, 2, 4], [1, 3, 4]]}
+
+
+def _ref_align_xdrop(case, read, scores, seed, max_gap=40):
+    index = TS.case_index(case)
+    nodes = [2 * (i + 1) for i in range(len(case["nodes"]))]
+    return oracle_xdrop_dag(index, nodes, _BUBBLE_PREDS, read, capi.Scores(*scores), seed, max_gap)
+
+
+def test_reference_align_xdrop_with_no_mems():
+    """:21-56 "can compute an alignment with no MEMs": score = read length, path n0, n1, n3."""
+    read = "AGTGCTGAAGT"
+    score, path = _ref_align_xdrop(_BUBBLE, read, (1, 4, 6, 1, 0), None)
+    assert score == len(read)
+    assert [m[0] for m in path] == [0, 1, 3]           # positions in the topological order: n0, n1, n3
+
+
+def test_reference_align_xdrop_with_a_mem_in_the_middle():
+    """:101-141: a MEM on the "GT" of the first node (read offset 1, node offset 1) seeds the same alignment."""
+    read = "AGTGCTGAAGT"
+    score, path = _ref_align_xdrop(_BUBBLE, read, (1, 4, 6, 1, 0), (0, 1, 1))
+    assert score == len(read)
+    assert [m[0] for m in path] == [0, 1, 3]           # positions in the topological order: n0, n1, n3
+
+
+@pytest.mark.parametrize("seed", [(0, 1, 1), None], ids=["with a MEM", "no MEM"])
+def test_reference_align_xdrop_applies_the_full_length_bonus_at_one_end_only(seed):
+    """:143-209 "still incorrectly applies the full length bonus at only one end": read length + ONE bonus of 10."""
+    read = "AGTGCTGAAGT"
+    score, _ = _ref_align_xdrop(_BUBBLE, read, (1, 4, 6, 1, 10), seed)
+    assert score == len(read) + 10
+
+
+def test_reference_align_xdrop_can_be_induced_to_pin_with_mems():
+    """:211-265: without a MEM the optimal alignment (one mapping on the last node, score 7) is found; a MEM on the
+    initial G of the homopolymer node forces the alignment onto that node."""
+    read = "GATTACA"
+    score, path = _ref_align_xdrop(_PINNED, read, (1, 4, 6, 1, 0), None)
+    assert score == len(read) and [m[0] for m in path] == [3]
+    score, path = _ref_align_xdrop(_PINNED, read, (1, 4, 6, 1, 0), (0, 0, 0))
+    assert [m[0] for m in path] == [0]
+
+
+def test_reference_align_xdrop_hard_to_find_a_seed_does_not_crash():
+    """:764-779: a 150 bp read against 27 TA-rich 32 bp nodes in a line, no MEMs: any outcome, no crash."""
+    seqs = ["ATTTATATATATATTTATATATATATTTATAT", "ATATATTTATATATTTTTATATATTATATATT", "TATATATATATTTATATATTATATATATATTT", "ATATATTTATATATATATTTATATATATTTAT",
+            "ATATATATTTATATATATTTATATATATATTT", "ATATATATATATTTATATATATTTATATATTA", "TTTATATATATTTATATATATATTTATATATA", "TTTATATATATATATTTATATATATATATTTA",
+            "TATATATATTTATATATATATTTATATATATA", "TTTATATATATATTTATATATATATTTATATA", "TATATTTATATATATATATTATATATATATAT", "TTATATATATATTTATATATATATTTATATAT",
+            "ATATATATATATTTATATATATATTTATATAT", "ATATTTATATATATATATTTATATATATATTT", "ATATATATATTTATATATATATTATTTATATA", "TATATTTATATATATATTATATATATATTTAT",
+            "ATATATATATTATATATATATTTATATATATA", "TTTATATATATATTTATATATATATATTATAT", "ATATATTTATATATATATTTATATATATATTT", "ATATATATATTTATATATATATTTATATATAT",
+            "ATTTATATATATATTTATATATATATTTATAT", "ATATATTATATATATATTTATATATATATTTA", "TATATATATTTATATATATATTTATATATATA", "TTTATATATATTTATATATATATTTATATATA",
+            "TATTTATATATATATTTATATATATTTATATA", "TATATTTATATATATATATATATATTTATATA", "TATATTTATATATATTTATATATATATTTATA"]
+    case = {"nodes": seqs, "paths": [list(range(1, len(seqs) + 1))]}
+    read = ("CAGCACTTTGGGAGGCCAAGGTGGGTGGATCATCTGAGGTCAGGAGTTTGAGACCAGCCTGACCAACATGGTGAAATCCTGTCTCTACTGAAAATACTAAAATTAGCCAGGCGTGGCGGCCAGTGCCTGTAATCCCGGCTACTGGGGAGG")
+    index = TS.case_index(case)
+    nodes = [2 * (i + 1) for i in range(len(seqs))]
+    preds = [[]] + [[i] for i in range(len(seqs) - 1)]
+    score, path = oracle_xdrop_dag(index, nodes, preds, read, capi.Scores(1, 4, 6, 1, 10), None, 40)
+    if path:
+        assert sum(ed[1] for m in path for ed in m[2] if ed[0] in "MSI") == len(read)
