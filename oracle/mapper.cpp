@@ -752,3 +752,23 @@ extern "C" double oracle_faster_cap_all_g(uint32_t n, const uint32_t* offset, co
     }
     return oracle::faster_cap(minimizers, explored, std::string(read_len, 'G'), std::string(read_len, (char)quality));
 }
+
+// cluster_seeds on explicit positions (test entry for the reference's clusterer unit tests,
+// unittest/snarl_seed_clusterer.cpp): seed i = (oriented node, offset on that strand) of read read_of[i];
+// read clusters = components of "unoriented minimum distance <= read_limit" among the seeds of one read,
+// fragment clusters = components at fragment_limit over all seeds (snarl_seed_clusterer.hpp:15-50).
+// Labels are the smallest seed index of the component.
+extern "C" void oracle_cluster_positions(const gb_flat_index* ix, uint32_t n, const uint32_t* node, const uint32_t* offset, const uint32_t* read_of,
+                                         uint32_t read_limit, uint32_t fragment_limit, uint32_t* read_label, uint32_t* fragment_label) {
+    std::vector<oracle::Seed> seeds(n);
+    for (uint32_t i = 0; i < n; i++) seeds[i] = oracle::Seed{node[i], offset[i], 0, ix->dist[node[i] >> 1]};
+    oracle::UnionFind reads(n), frags(n);
+    for (uint32_t i = 0; i < n; i++)
+        for (uint32_t j = 0; j < i; j++) {
+            const int64_t d = oracle::unoriented_distance(ix, seeds[i], seeds[j]);
+            if (d == oracle::INF_DIST) continue;
+            if (read_of[i] == read_of[j] && d <= (int64_t)read_limit) reads.unite(i, j);
+            if (fragment_limit && d <= (int64_t)fragment_limit) frags.unite(i, j);
+        }
+    for (uint32_t i = 0; i < n; i++) { read_label[i] = (uint32_t)reads.find(i); fragment_label[i] = (uint32_t)frags.find(i); }
+}
