@@ -361,3 +361,22 @@ extern "C" int oracle_extend(const gb_flat_index* ix, const gb_scores* scores,
     }
     return (int)result.size();
 }
+
+// GaplessExtension helpers on hand-built extensions (test entries for unittest/gbwt_extender.cpp:576-820).
+static oracle::GaplessExtension make_test_extension(const uint32_t* path, uint32_t n, uint32_t offset, uint32_t read_lo, uint32_t read_hi) {
+    oracle::GaplessExtension e;
+    e.path.assign(path, path + n); e.offset = offset; e.read_interval = {read_lo, read_hi};
+    return e;
+}
+extern "C" uint64_t oracle_extension_overlap(const gb_flat_index* ix, const uint32_t* path_a, uint32_t n_a, uint32_t offset_a, uint32_t lo_a, uint32_t hi_a,
+                                             const uint32_t* path_b, uint32_t n_b, uint32_t offset_b, uint32_t lo_b, uint32_t hi_b) {
+    oracle::Graph g(ix);
+    return make_test_extension(path_a, n_a, offset_a, lo_a, hi_a).overlap(g, make_test_extension(path_b, n_b, offset_b, lo_b, hi_b));
+}
+// out = {start node, start offset, tail node, tail offset}
+extern "C" void oracle_extension_positions(const gb_flat_index* ix, const uint32_t* path, uint32_t n, uint32_t offset, uint32_t read_lo, uint32_t read_hi, uint32_t* out) {
+    oracle::Graph g(ix);
+    const oracle::GaplessExtension e = make_test_extension(path, n, offset, read_lo, read_hi);
+    const auto s = e.starting_position(g), t = e.tail_position(g);
+    out[0] = s.first; out[1] = (uint32_t)s.second; out[2] = t.first; out[3] = (uint32_t)t.second;
+}

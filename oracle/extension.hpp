@@ -36,6 +36,15 @@ struct GaplessExtension {
         return false;
     }
 
+    // starting_position / tail_position, gbwt_extender.cpp:55-87: (oriented node, offset) of the first aligned base and
+    // of the position just past the last one (the offset may equal the node length)
+    std::pair<uint32_t, size_t> starting_position(const Graph&) const { return {path.front(), offset}; }
+    std::pair<uint32_t, size_t> tail_position(const Graph& g) const {
+        size_t tail_off = offset + length();
+        for (size_t i = 0; i + 1 < path.size(); i++) tail_off -= g.get_length(path[i]);
+        return {path.back(), tail_off};
+    }
+
     // gbwt_extender.cpp:89-117
     size_t overlap(const Graph& g, const GaplessExtension& another) const {
         size_t result = 0;

@@ -279,16 +279,16 @@ std::vector<TailTree> get_tail_forest(const Graph& g, const gb_scores& scores, c
     uint32_t from_node; size_t from_offset; size_t tail_length; const SearchState* base_state;
     if (left_tails) {
         // starting_position reversed: reverse(Position, node_length), position.cpp:41-46
-        from_node = ext.path.front() ^ 1u;
-        from_offset = g.get_length(ext.path.front()) - ext.offset;
+        const auto start = ext.starting_position(g);
+        from_node = start.first ^ 1u;
+        from_offset = g.get_length(start.first) - start.second;
         base_state = &ext.state.backward;
         tail_length = ext.read_interval.first;
     } else {
         // tail_position, gbwt_extender.cpp:68-87
-        from_node = ext.path.back();
-        size_t tail_off = ext.offset + ext.length();
-        for (size_t i = 0; i + 1 < ext.path.size(); i++) tail_off -= g.get_length(ext.path[i]);
-        from_offset = tail_off;
+        const auto tail = ext.tail_position(g);
+        from_node = tail.first;
+        from_offset = tail.second;
         base_state = &ext.state.forward;
         tail_length = read_length - ext.read_interval.second;
     }

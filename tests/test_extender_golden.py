@@ -1,6 +1,7 @@
 """Pin the oracle against the reference's own GaplessExtender unit vectors
 (src/unittest/gbwt_extender.cpp:822-1156, transcribed in tests/golden/gapless_extender.json),
 and — on a GPU — the CUDA path against the same vectors through the C-ABI."""
+import numpy as np
 import pytest
 
 import helpers as H
@@ -91,3 +92,47 @@ def test_cuda_matches_reference_vectors():
                                    overlap_threshold=case.get("overlap_threshold", 0.8))
             assert result == want, case["name"]
         dev.close()
+
+
+# ---- GaplessExtension helpers on hand-built extensions (unittest/gbwt_extender.cpp:576-820, the "toy" graph) ---------
+def _ext_args(path_ids, offset, lo, hi):
+    import ctypes as C
+    p = np.array([2 * i for i in path_ids], dtype=np.uint32)
+    return p, (capi.ptr(p), len(p), offset, lo, hi)
+
+
+@pytest.mark.parametrize("path,offset,interval,start,tail", [
+    ([1, 4], 0, (0, 4), (1, 0), (4, 3)),        # starts and ends at node boundaries   :583-599
+    ([4, 5], 1, (0, 3), (4, 1), (5, 1)),        # starts in the middle                 :601-617
+    ([1, 4], 0, (0, 3), (1, 0), (4, 2)),        # ends in the middle                   :619-635
+    ([4], 1, (0, 1), (4, 1), (4, 2)),           # starts and ends in the middle        :637-652
+])
+def test_extension_positions_reference_vectors(path, offset, interval, start, tail):
+    import ctypes as C
+    index = H.golden_graph_index(GOLD["graphs"]["toy"])
+    lib = H.oracle_lib()
+    lib.oracle_extension_positions.argtypes = [C.POINTER(capi.FlatIndex), C.c_void_p, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32, C.c_void_p]
+    lib.oracle_extension_positions.restype = None
+    keep, args = _ext_args(path, offset, *interval)
+    out = np.zeros(4, dtype=np.uint32)
+    lib.oracle_extension_positions(C.byref(index.view), *args, capi.ptr(out))
+    assert (int(out[0]) >> 1, int(out[1])) == start and (int(out[2]) >> 1, int(out[3])) == tail and not (out[0] & 1) and not (out[2] & 1)
+
+
+@pytest.mark.parametrize("a,b,expected", [
+    (([1, 4], 0, (0, 4)), ([5, 6, 8, 9], 0, (0, 4)), 0),            # unrelated extensions          :660-685
+    (([1, 4], 0, (0, 4)), ([1, 4], 0, (0, 4)), 4),                  # identical extensions          :686-701
+    (([5, 6, 7, 9], 0, (0, 4)), ([5, 6, 8, 9], 0, (0, 4)), 3),      # one difference                :702-731
+    (([4, 5, 6, 8], 2, (0, 4)), ([5, 6, 8, 9], 0, (1, 5)), 3),      # partial overlap               :732-760
+    (([4, 5, 6, 8, 9], 2, (0, 5)), ([5, 6, 8, 9], 0, (0, 4)), 0),   # shifted by one                :761-790
+    (([1, 2, 4, 5], 0, (0, 6)), ([1, 4, 5], 0, (1, 6)), 4),         # paths of different lengths    :791-819
+])
+def test_extension_overlap_reference_vectors(a, b, expected):
+    import ctypes as C
+    index = H.golden_graph_index(GOLD["graphs"]["toy"])
+    lib = H.oracle_lib()
+    lib.oracle_extension_overlap.argtypes = [C.POINTER(capi.FlatIndex)] + [C.c_void_p, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32] * 2
+    lib.oracle_extension_overlap.restype = C.c_uint64
+    ka, aa = _ext_args(a[0], a[1], *a[2]); kb, ab = _ext_args(b[0], b[1], *b[2])
+    assert lib.oracle_extension_overlap(C.byref(index.view), *aa, *ab) == expected
+    assert lib.oracle_extension_overlap(C.byref(index.view), *ab, *aa) == expected          # symmetric
