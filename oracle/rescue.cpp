@@ -233,3 +233,18 @@ extern "C" uint32_t oracle_fix_end_deletions(uint32_t n_mappings, uint32_t* node
     }
     return (uint32_t)path.size();
 }
+
+// score_contiguous_alignment on a flat path (test entry for unittest/aligner.cpp:347-369): edits are (from_length,
+// to_length, is_substitution) triples, edit_count[i] per mapping.
+extern "C" int32_t oracle_score_contiguous(const gb_scores* sc, uint32_t n_mappings, const uint32_t* edit_count,
+                                           const uint32_t* from_length, const uint32_t* to_length, const uint8_t* is_sub) {
+    std::vector<oracle::Mapping> path(n_mappings);
+    size_t e = 0;
+    for (uint32_t i = 0; i < n_mappings; i++)
+        for (uint32_t j = 0; j < edit_count[i]; j++, e++) {
+            oracle::Edit ed; ed.from_length = from_length[e]; ed.to_length = to_length[e];
+            if (is_sub[e] || (ed.from_length == 0 && ed.to_length > 0)) ed.sequence = std::string(ed.to_length, 'N');
+            path[i].edits.push_back(ed);
+        }
+    return oracle::score_contiguous_alignment(*sc, path);
+}

@@ -60,6 +60,25 @@ def test_oracle_fix_end_deletions_reference_vector():
     assert lib.oracle_fix_end_deletions(1, capi.ptr(node), capi.ptr(offset), capi.ptr(count), capi.ptr(frm), capi.ptr(to)) == 0
 
 
+def test_oracle_score_contiguous_alignment_reference_vector():
+    """unittest/aligner.cpp:347-369 "Full-length bonus is applied to both ends by rescoring": the 12-mapping alignment with a
+    3-bp deletion split over two mappings and a 3-bp insertion scores 129 without and 139 with a bonus of 5
+    (fix_dozeu_score re-scores rescued alignments with this function, minimizer_mapper.cpp:3502-3517)."""
+    import ctypes as C
+    lib = H.oracle_lib()
+    lib.oracle_score_contiguous.argtypes = [C.POINTER(capi.Scores), C.c_uint32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
+    lib.oracle_score_contiguous.restype = C.c_int32
+    mappings = [[(4, 4)], [(1, 1)], [(3, 3)], [(1, 1)], [(32, 32)], [(32, 32)], [(8, 8)], [(1, 1)], [(24, 24)], [(1, 0)],
+                [(2, 0), (3, 3), (0, 3), (27, 27)], [(9, 9)]]
+    count = np.array([len(m) for m in mappings], dtype=np.uint32)
+    frm = np.array([e[0] for m in mappings for e in m], dtype=np.uint32); to = np.array([e[1] for m in mappings for e in m], dtype=np.uint32)
+    sub = np.zeros(len(frm), dtype=np.uint8)
+    assert int(to.sum()) == 148                          # the read of the vector
+    for bonus, want in ((0, 129), (5, 139)):
+        sc = capi.Scores(1, 4, 6, 1, bonus)
+        assert lib.oracle_score_contiguous(C.byref(sc), len(mappings), capi.ptr(count), capi.ptr(frm), capi.ptr(to), capi.ptr(sub)) == want
+
+
 def test_oracle_rescue_recovers_mates_without_seeds():
     """attempt_rescue (minimizer_mapper.cpp:3264-3482) in the oracle: mates too noisy to seed are found next to
     their partner; the rescued records are internally consistent."""
