@@ -350,9 +350,12 @@ int gb_map_paired_job(gb_device* dev, const gb_map_params* p, gb_fragment_distri
  * giraffe_main.cpp:2209-2226 hands alignments to a vg::io::AlignmentEmitter (libvgio @ d029989,
  * absent from the reference tree).  These two write the same information as text, one line per
  * record, into `out` (GB_ERR_CAPACITY if it does not fit; *out_used = bytes written):
- *   gb_emit_gaf   GAF: name, length, query start / end (soft clips excluded), '+', path as >id / <id
- *                 steps, path length, start / end on the path, matches, block length, MAPQ, then
- *                 AS:i, bq:Z (when quals), cs:Z (":n" "*rq" "+q" "-r"), dv:f, fn:Z / fp:Z for mates
+ *   gb_emit_gaf   GAF: name, length, query start / end (the whole read: soft clips are insertions in cs),
+ *                 '+', path as >id / <id steps (mappings that only carry an insertion are left out), path
+ *                 length, start / end on the path, matches, block length, MAPQ, then AS:i, bq:Z (when quals),
+ *                 cs:Z (":n" "*RQ" "+Q" "-R", match runs merged across mappings), dv:f, fn:Z / fp:Z for
+ *                 mates; unaligned reads: empty path ('*') and cs "+<read>" — the conventions the reference's
+ *                 own tests fix (unittest/alignment.cpp:398-470, :793-820)
  *   gb_emit_json  one protobuf-JSON Alignment per line with vg.proto's field names, as `vg view -aj`
  *                 prints them (64-bit integers as strings, default values omitted, quality base64)
  * names / name_off may be NULL (reads are then called read<i>); records may be any subset / order

@@ -45,41 +45,77 @@ def _check_gaf(g, rs, res, text, paired, names):
         f = line.split("\t")
         read = bytes(rs.reads[i]).decode()
         assert f[0] == names[i] and int(f[1]) == rs.length
+        assert (int(f[2]), int(f[3])) == (0, rs.length)                  # the whole read, soft clips included
         score, mapq, path = H.decode_alignment(res[0][i], res[1], res[2])
         tags = {t[:2]: t[5:] for t in f[12:]}
         if paired:
             assert tags["fn" if i % 2 == 0 else "fp"] == names[i ^ 1]
         if not path:
-            assert f[2:12] == ["*"] * 9 + ["255"]
+            assert f[4:12] == ["*"] * 7 + ["255"] and tags["cs"] == "+" + read
             continue
-        qs, qe = int(f[2]), int(f[3])
         assert f[4] == "+" and int(f[11]) == mapq and int(tags["AS"]) == score
         steps = [(int(x[1:]) << 1) | (x[0] == "<") for x in re.findall(r"[<>]\d+", f[5])]
-        assert steps == [m[0] for m in path]
+        assert steps == [m[0] for m in path if any(e[0] != "I" for e in m[2])]
         ref = "".join(_oriented_seq(g, v) for v in steps)
         assert int(f[6]) == len(ref)
-        pos, q, matches, block = int(f[7]), qs, 0, 0
-        assert pos == path[0][1]
+        pos, matches, block = int(f[7]), 0, 0
         query = []
         tokens = [(m[0] or m[2] or m[4] or m[6], m[1] or m[3] or m[5] or m[7])
-                  for m in re.findall(r"(:)(\d+)|(\*)([a-z]{2})|(\+)([a-z]+)|(-)([a-z]+)", tags["cs"])]
+                  for m in re.findall(r"(:)(\d+)|(\*)([A-Z]{2})|(\+)([A-Z]+)|(-)([A-Z]+)", tags["cs"])]
+        assert "".join(op + arg for op, arg in tokens) == tags["cs"]
+        assert not any(a[0] == ":" and b[0] == ":" for a, b in zip(tokens, tokens[1:]))     # match runs are merged
         for op, arg in tokens:
             if op == ":":
                 n = int(arg); query.append(ref[pos:pos + n]); pos += n; matches += n; block += n
             elif op == "*":
-                assert ref[pos].lower() == arg[0] and arg[0] != arg[1]
-                query.append(arg[1].upper()); pos += 1; block += 1
+                assert ref[pos] == arg[0] and arg[0] != arg[1]
+                query.append(arg[1]); pos += 1; block += 1
             elif op == "+":
-                query.append(arg.upper()); block += len(arg); n_indel += 1
+                query.append(arg); block += len(arg); n_indel += 1
             else:
-                assert ref[pos:pos + len(arg)].lower() == arg
+                assert ref[pos:pos + len(arg)] == arg
                 pos += len(arg); block += len(arg); n_indel += 1
-        assert "".join(query) == read[qs:qe], (i, line)
+        assert "".join(query) == read, (i, line)
         assert pos == int(f[8]) and matches == int(f[9]) and block == int(f[10])
         assert tags["bq"] == "".join(chr(int(c) + 33) for c in rs.quals[i])
         assert abs(float(tags["dv"]) - (1 - matches / block)) < 1e-5
-        n_clipped += (qs > 0) or (qe < rs.length)
+        n_clipped += tokens[0][0] == "+" or tokens[-1][0] == "+"
     return n_clipped, n_indel
+
+
+def _hand_record(mappings):
+    """mappings: [(oriented node, offset, [(op, length, base2)...])] -> (aln[1], maps, edits) as the library lays them out."""
+    aln = np.zeros(1, dtype=capi.alignment_dt)
+    maps = np.zeros(len(mappings), dtype=capi.mapping_dt)
+    words = []
+    for i, (node, off, eds) in enumerate(mappings):
+        maps[i]["node"] = node; maps[i]["offset"] = off; maps[i]["n_edits"] = len(eds)
+        for op, ln, base in eds:
+            words.append((ln << 4) | (base << 2) | "MSID".index(op))
+    aln[0]["read_id"] = 0; aln[0]["flags"] = capi.GB_ALN_MAPPED if mappings else 0
+    aln[0]["n_mappings"] = len(mappings); aln[0]["n_edits"] = len(words); aln[0]["score"] = 7; aln[0]["mapq"] = 60
+    return aln, maps if len(maps) else np.zeros(1, dtype=capi.mapping_dt), np.array(words + [0], dtype=np.uint32)
+
+
+def test_gaf_reference_vector_unused_final_node_is_removed():
+    """unittest/alignment.cpp:398-470: GATTACA -> CAT -> GATTA, read TACACTTAC = TACA on 1:3, C *AT T on 2:0, AC soft-clipped
+    onto node 3: query 0..9, path >1>2 of length 10, start 3, end 10, cs ":5*AT:1+AC"."""
+    index = capi.HostIndex(["GATTACA", "CAT", "GATTA"], [[2, 4, 6]], None, k=5, w=3)
+    aln, maps, edits = _hand_record([(2, 3, [("M", 4, 0)]), (4, 0, [("M", 1, 0), ("S", 1, 3), ("M", 1, 0)]), (6, 0, [("I", 2, 0)])])
+    rbuf, qbuf, read_off = H.pack_reads(np.frombuffer(b"TACACTTAC", dtype=np.uint8).reshape(1, -1).copy(), None)
+    f = capi.emit_text("gaf", index.view, aln, maps, edits, rbuf, None, read_off, ["softclip-at-end"]).rstrip("\n").split("\t")
+    assert f[:9] == ["softclip-at-end", "9", "0", "9", "+", ">1>2", "10", "3", "10"]
+    assert dict(t.split(":", 2)[::2] for t in f[12:])["cs"] == ":5*AT:1+AC"
+
+
+def test_gaf_reference_vector_unaligned_read():
+    """unittest/alignment.cpp:793-820: no path, query 0..9, cs "+TACACTTAC"."""
+    index = capi.HostIndex(["GATTACA", "CAT", "GATTA"], [[2, 4, 6]], None, k=5, w=3)
+    aln, maps, edits = _hand_record([])
+    rbuf, qbuf, read_off = H.pack_reads(np.frombuffer(b"TACACTTAC", dtype=np.uint8).reshape(1, -1).copy(), None)
+    f = capi.emit_text("gaf", index.view, aln, maps, edits, rbuf, None, read_off, ["unaligned"]).rstrip("\n").split("\t")
+    assert f[:4] == ["unaligned", "9", "0", "9"] and f[5] == "*"
+    assert dict(t.split(":", 2)[::2] for t in f[12:])["cs"] == "+TACACTTAC"
 
 
 def test_gaf_lines_replay_to_the_reads_single_end():

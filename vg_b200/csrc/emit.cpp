@@ -1,7 +1,8 @@
 // emit.cpp — host-side emission of alignment records (no device work):
 //   GAF lines   the text format `vg giraffe -o gaf` writes (alignment_to_gaf lives in libvgio @ d029989,
 //               ABSENT from the reference tree; columns follow the published GAF specification and the
-//               cs difference string of minimap2: ":n" matches, "*rq" substitution, "+q" insertion, "-r" deletion)
+//               cs difference string of minimap2: ":n" matches, "*RQ" substitution, "+Q" insertion, "-R" deletion; the
+//               conventions the reference's tests fix, unittest/alignment.cpp:398-470 and :793-820, are followed)
 //   JSON lines  the protobuf JSON of vg.proto's Alignment as `vg view -aj` prints it (field names as used at
 //               gbwt_extender.cpp:119-156, aligner.cpp:120-241, minimizer_mapper.cpp:1146-1216: sequence, path.mapping[]
 //               {position{node_id, offset, is_reverse}, edit[]{from_length, to_length, sequence}, rank}, name, quality
@@ -26,7 +27,6 @@ struct Out {
     void real(double v) { char t[40]; const int k = snprintf(t, sizeof t, "%.6g", v); put(t, (size_t)k); }
 };
 
-inline char lower(char c) { return (c >= 'A' && c <= 'Z') ? (char)(c + 32) : c; }
 
 // base i of oriented node v (gb_flat_index stores the sequence of both orientations)
 inline char node_base(const gb_flat_index* ix, uint32_t v, uint32_t i) {
@@ -72,35 +72,41 @@ extern "C" int gb_emit_gaf(const gb_flat_index* ix, uint32_t n, const gb_alignme
         const uint8_t* seq = reads + read_off[r];
         const uint32_t L = (uint32_t)(read_off[r + 1] - read_off[r]);
         o.str(read_name(names, name_off, r)); o.ch('\t'); o.num(L); o.ch('\t');
+        // Conventions pinned by the reference's own GAF tests (unittest/alignment.cpp:398-470, :793-820): the query
+        // interval is the whole read (soft clips stay in the difference string as insertions), cs bases are upper
+        // case, match runs merge across edits and mappings, a mapping that only carries an insertion (a soft clip
+        // parked on an unused node) is left out of the path, an unaligned read has an empty path and cs "+<read>".
         if (!(a.flags & GB_ALN_MAPPED) || a.n_mappings == 0) {
-            o.str("*\t*\t*\t*\t*\t*\t*\t*\t*\t255");
+            o.num(0); o.ch('\t'); o.num(L); o.str("\t*\t*\t*\t*\t*\t*\t*\t255");
+            o.str("\tcs:Z:+"); o.put((const char*)seq, L);
         } else {
             const gb_mapping* m = mappings + a.mapping_off;
             const uint32_t* e = edits + a.edit_off;
-            // soft clips = insertions at the two ends; the query interval excludes them
-            uint32_t qs = 0, qe = L;
-            uint32_t first_edit = 0, last_edit = a.n_edits;
-            if (a.n_edits && (e[0] & 3u) == GB_EDIT_INS) { qs = e[0] >> 4; first_edit = 1; }
-            if (a.n_edits > first_edit && (e[a.n_edits - 1] & 3u) == GB_EDIT_INS) { qe = L - (e[a.n_edits - 1] >> 4); last_edit = a.n_edits - 1; }
             std::string path, cs;
-            uint64_t path_len = 0, matches = 0, block = 0, ref_used_total = 0;
-            uint32_t q = 0, ei = 0;
+            uint64_t path_len = 0, matches = 0, block = 0, ref_used_total = 0, pstart = 0;
+            uint32_t q = 0, ei = 0, run = 0;
+            bool have_start = false;
+            auto flush_run = [&]() { if (run) { cs += ':'; cs += std::to_string(run); run = 0; } };
             for (uint32_t i = 0; i < a.n_mappings; i++) {
                 const uint32_t v = m[i].node;
-                path += (v & 1u) ? '<' : '>'; path += std::to_string(v >> 1);
-                path_len += ix->nodes[v].len;
+                bool uses_node = false;
+                for (uint32_t j = 0; j < m[i].n_edits; j++) uses_node |= (e[ei + j] & 3u) != GB_EDIT_INS;
+                if (uses_node) {
+                    path += (v & 1u) ? '<' : '>'; path += std::to_string(v >> 1);
+                    path_len += ix->nodes[v].len;
+                    if (!have_start) { pstart = m[i].offset; have_start = true; }
+                }
                 uint32_t off = m[i].offset;
                 for (uint32_t j = 0; j < m[i].n_edits; j++, ei++) {
                     const uint32_t wd = e[ei], op = wd & 3u, len = op == GB_EDIT_SUB ? 1u : wd >> 4;
-                    const bool clipped = ei < first_edit || ei >= last_edit;
-                    if (op == GB_EDIT_MATCH) { cs += ':'; cs += std::to_string(len); matches += len; block += len; q += len; off += len; ref_used_total += len; }
-                    else if (op == GB_EDIT_SUB) { cs += '*'; cs += lower(node_base(ix, v, off)); cs += lower((char)seq[q]); block += 1; q += 1; off += 1; ref_used_total += 1; }
-                    else if (op == GB_EDIT_INS) { if (!clipped) { cs += '+'; for (uint32_t t = 0; t < len; t++) cs += lower((char)seq[q + t]); block += len; } q += len; }
-                    else { cs += '-'; for (uint32_t t = 0; t < len; t++) cs += lower(node_base(ix, v, off + t)); block += len; off += len; ref_used_total += len; }
+                    if (op == GB_EDIT_MATCH) { run += len; matches += len; block += len; q += len; off += len; ref_used_total += len; }
+                    else if (op == GB_EDIT_SUB) { flush_run(); cs += '*'; cs += node_base(ix, v, off); cs += (char)seq[q]; block += 1; q += 1; off += 1; ref_used_total += 1; }
+                    else if (op == GB_EDIT_INS) { flush_run(); cs += '+'; cs.append((const char*)seq + q, len); block += len; q += len; }
+                    else { flush_run(); cs += '-'; for (uint32_t t = 0; t < len; t++) cs += node_base(ix, v, off + t); block += len; off += len; ref_used_total += len; }
                 }
             }
-            const uint64_t pstart = m[0].offset;
-            o.num(qs); o.ch('\t'); o.num(qe); o.str("\t+\t"); o.str(path); o.ch('\t'); o.num((long long)path_len); o.ch('\t');
+            flush_run();
+            o.num(0); o.ch('\t'); o.num(L); o.str("\t+\t"); o.str(path.empty() ? std::string("*") : path); o.ch('\t'); o.num((long long)path_len); o.ch('\t');
             o.num((long long)pstart); o.ch('\t'); o.num((long long)(pstart + ref_used_total)); o.ch('\t');
             o.num((long long)matches); o.ch('\t'); o.num((long long)block); o.ch('\t'); o.num(a.mapq);
             o.str("\tAS:i:"); o.num(a.score);
