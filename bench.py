@@ -126,6 +126,23 @@ def simulate_pairs_numpy(g, n_pairs, seed):
 
 # ---------------------------------------------------------------------------------------
 # helpers
+
+def split_align_stage(last_stage, summary_path=None):
+    """Per-kernel times from the four stage timers: the align stage (index 2) is three launches, so its dominant
+    kernel (the warp-per-pair align_kernel_pe) gets the stage time times its share in the committed ncu launch list.
+    Returns (kernel_ms[4], split or None)."""
+    kernel_ms = np.array(last_stage, dtype=np.float64)
+    align_split = None
+    try:
+        kern = json.loads(Path(summary_path or (ROOT / "profiles" / "ncu_summary_r01.json")).read_text())["kernels"]
+        parts = {k: float(kern[k]["total_ms"]) for k in ("align_fast_kernel_pe", "align_kernel_pe", "align_kernel_pe<rescue>") if k in kern and "total_ms" in kern[k]}
+        if "align_kernel_pe" in parts and sum(parts.values()) > 0:
+            align_split = {k: v / sum(parts.values()) for k, v in parts.items()}
+            kernel_ms[2] = float(last_stage[2]) * align_split["align_kernel_pe"]
+    except Exception:
+        pass
+    return kernel_ms, align_split
+
 # ---------------------------------------------------------------------------------------
 class ClockSampler:
     """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md recipe)."""
@@ -486,16 +503,7 @@ def main():
     # kernel, its rescue instantiation).  To name the dominant KERNEL, the align stage is split by the per-kernel
     # times of the committed ncu launch list of this command (profiles/ncu_summary_r01.json); the other stages are
     # one kernel each (the second seeding launch only sees the few units that overflowed the small tables).
-    kernel_ms = np.array(last_stage, dtype=np.float64)
-    align_split = None
-    try:
-        kern = json.loads((ROOT / "profiles" / "ncu_summary_r01.json").read_text())["kernels"]
-        parts = {k: float(kern[k]["total_ms"]) for k in ("align_fast_kernel_pe", "align_kernel_pe", "align_kernel_pe<rescue>") if k in kern and "total_ms" in kern[k]}
-        if "align_kernel_pe" in parts and sum(parts.values()) > 0:
-            align_split = {k: v / sum(parts.values()) for k, v in parts.items()}
-            kernel_ms[2] = float(last_stage[2]) * align_split["align_kernel_pe"]
-    except Exception:
-        pass
+    kernel_ms, align_split = split_align_stage(last_stage)
     dom = int(np.argmax(kernel_ms))
     chunk_reads = min(CHUNK, n_reads) if n_reads % CHUNK == 0 or n_reads < CHUNK else n_reads - (n_chunks - 1) * CHUNK
     dom_ms = float(kernel_ms[dom])
