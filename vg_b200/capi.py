@@ -164,7 +164,7 @@ def load_library() -> C.CDLL:
     lib.gb_fragment_sample_size.restype = u64
     lib.gb_map_paired_job.argtypes = [vp, C.POINTER(MapParams), vp, u32, u32, vp, vp, vp, vp, vp, u64, vp, u64, vp, vp, vp, vp]
     lib.gb_map_paired_job.restype = C.c_int
-    for fn in (lib.gb_emit_gaf, lib.gb_emit_json):
+    for fn in (lib.gb_emit_gaf, lib.gb_emit_json, lib.gb_emit_gam):
         fn.argtypes = [C.POINTER(FlatIndex), u32, vp, vp, vp, vp, vp, vp, vp, vp, vp, u64, vp]
         fn.restype = C.c_int
     lib.gb_last_kernel_ms.argtypes = [vp]
@@ -247,10 +247,10 @@ GB_PAIR_PAIRED, GB_PAIR_TRAINING, GB_PAIR_BUFFERED = 0, 1, 2
 
 
 def emit_text(kind, flat_index, aln, maps, edits, rbuf, qbuf, read_off, names=None):
-    """gb_emit_gaf / gb_emit_json (kind = "gaf" | "json") over records `aln`; returns the text.
+    """gb_emit_gaf / gb_emit_json / gb_emit_gam (kind = "gaf" | "json" | "gam") over records `aln`; returns the text (bytes for GAM).
     names: optional list of read names (str)."""
     lib = load_library()
-    fn = {"gaf": lib.gb_emit_gaf, "json": lib.gb_emit_json}[kind]
+    fn = {"gaf": lib.gb_emit_gaf, "json": lib.gb_emit_json, "gam": lib.gb_emit_gam}[kind]
     nbuf = noff = None
     if names is not None:
         enc = [s.encode() for s in names]
@@ -265,7 +265,8 @@ def emit_text(kind, flat_index, aln, maps, edits, rbuf, qbuf, read_off, names=No
             ptr(nbuf) if nbuf is not None else None, ptr(noff) if noff is not None else None, ptr(out), cap, C.byref(used))
     if rc != GB_OK:
         raise GbError(rc, "gb_emit_" + kind)
-    return out[: used.value].tobytes().decode()
+    data = out[: used.value].tobytes()
+    return data if kind == "gam" else data.decode()
 
 
 class FragmentDistribution:

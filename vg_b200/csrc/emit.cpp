@@ -11,6 +11,7 @@
 // records to vg::Alignment itself.  PARITY UNPINNED: no libvgio here to compare bytes with.
 #include "giraffe_b200.h"
 
+#include <algorithm>
 #include <cstdio>
 #include <cstring>
 #include <string>
@@ -173,6 +174,96 @@ extern "C" int gb_emit_json(const gb_flat_index* ix, uint32_t n, const gb_alignm
         if (a.mapq_explored_cap > 1e30f) o.str("\"Infinity\""); else o.real(a.mapq_explored_cap);
         if (a.flags & GB_ALN_RESCUED) o.str(", \"rescued\": true");
         o.str("}}\n");
+    }
+    *out_used = o.n;
+    return o.overflow ? GB_ERR_CAPACITY : GB_OK;
+}
+
+// ---- GAM: vg.proto Alignment messages in vg::io's group framing -------------------------------------------------
+// libvgio (vg.proto, the stream framing) is absent from the reference tree; the wire layout is read off GAM files vg
+// itself wrote, kept as fixtures in tests/golden/gam/ (test/surject/perpendicular.gam is Giraffe output):
+//   stream    groups of [varint n] [varint 3]["GAM"] then n-1 x [varint len][Alignment]      (type-tagged groups)
+//   Alignment 1 sequence, 2 path, 3 name, 4 quality (raw phred bytes), 5 mapping_quality, 6 score,
+//             11 fragment_prev / 12 fragment_next (an Alignment carrying only 3 name), 16 identity (double),
+//             100 annotation (google.protobuf.Struct: 1 fields{1 key, 2 Value{2 number_value, 4 bool_value}})
+//   Path      2 mapping;   Mapping 1 position, 2 edit, 5 rank;   Position 1 node_id, 2 offset, 4 is_reverse;
+//   Edit      1 from_length, 2 to_length, 3 sequence.   proto3: zero / false / empty fields are not written.
+// The stream is written uncompressed (vg::io reads plain, gzip and BGZF streams alike).
+namespace {
+
+void pb_varint(std::string& s, uint64_t v) { while (v >= 0x80) { s.push_back((char)(v | 0x80)); v >>= 7; } s.push_back((char)v); }
+void pb_tag(std::string& s, uint32_t field, uint32_t wire) { pb_varint(s, ((uint64_t)field << 3) | wire); }
+void pb_uint(std::string& s, uint32_t field, uint64_t v) { if (v) { pb_tag(s, field, 0); pb_varint(s, v); } }
+void pb_bytes(std::string& s, uint32_t field, const char* p, size_t n) { pb_tag(s, field, 2); pb_varint(s, n); s.append(p, n); }
+void pb_msg(std::string& s, uint32_t field, const std::string& m) { pb_bytes(s, field, m.data(), m.size()); }
+void pb_double(std::string& s, uint32_t field, double v) { pb_tag(s, field, 1); char b[8]; memcpy(b, &v, 8); s.append(b, 8); }
+void pb_annotation(std::string& st, const char* key, const std::string& value_msg) {
+    std::string entry; pb_bytes(entry, 1, key, strlen(key)); pb_msg(entry, 2, value_msg);
+    pb_msg(st, 1, entry);
+}
+
+} // namespace
+
+extern "C" int gb_emit_gam(const gb_flat_index* ix, uint32_t n, const gb_alignment* aln, const gb_mapping* mappings, const uint32_t* edits,
+                           const uint8_t* reads, const uint8_t* quals, const uint64_t* read_off, const uint8_t* names, const uint64_t* name_off,
+                           char* out, uint64_t out_cap, uint64_t* out_used) {
+    if (!ix || !aln || !reads || !read_off || !out || !out_used) return GB_ERR_ARG;
+    Out o{out, out_cap, 0, false};
+    const uint32_t GROUP = 1000;                 // messages per group
+    for (uint32_t g0 = 0; g0 < n; g0 += GROUP) {
+        const uint32_t gn = std::min(GROUP, n - g0);
+        std::string group;
+        pb_varint(group, (uint64_t)gn + 1); pb_varint(group, 3); group += "GAM";
+        for (uint32_t x = g0; x < g0 + gn; x++) {
+            const gb_alignment& a = aln[x];
+            const uint32_t r = a.read_id;
+            const char* seq = (const char*)reads + read_off[r];
+            const uint32_t L = (uint32_t)(read_off[r + 1] - read_off[r]);
+            std::string msg;
+            pb_bytes(msg, 1, seq, L);
+            uint64_t matches = 0;
+            if ((a.flags & GB_ALN_MAPPED) && a.n_mappings) {
+                const gb_mapping* m = mappings + a.mapping_off;
+                const uint32_t* e = edits + a.edit_off;
+                std::string path;
+                uint32_t q = 0, ei = 0;
+                for (uint32_t i = 0; i < a.n_mappings; i++) {
+                    std::string mp, pos;
+                    pb_uint(pos, 1, m[i].node >> 1); pb_uint(pos, 2, m[i].offset); pb_uint(pos, 4, m[i].node & 1u);
+                    pb_msg(mp, 1, pos);
+                    for (uint32_t j = 0; j < m[i].n_edits; j++, ei++) {
+                        const uint32_t wd = e[ei], op = wd & 3u, len = op == GB_EDIT_SUB ? 1u : wd >> 4;
+                        std::string ed;
+                        if (op == GB_EDIT_MATCH) { pb_uint(ed, 1, len); pb_uint(ed, 2, len); matches += len; q += len; }
+                        else if (op == GB_EDIT_SUB) { pb_uint(ed, 1, 1); pb_uint(ed, 2, 1); pb_bytes(ed, 3, seq + q, 1); q += 1; }
+                        else if (op == GB_EDIT_INS) { pb_uint(ed, 2, len); pb_bytes(ed, 3, seq + q, len); q += len; }
+                        else pb_uint(ed, 1, len);
+                        pb_msg(mp, 2, ed);
+                    }
+                    pb_uint(mp, 5, i + 1);
+                    pb_msg(path, 2, mp);
+                }
+                pb_msg(msg, 2, path);
+            }
+            const std::string nm = read_name(names, name_off, r);
+            pb_bytes(msg, 3, nm.data(), nm.size());
+            if (quals && L) pb_bytes(msg, 4, (const char*)quals + read_off[r], L);
+            pb_uint(msg, 5, a.mapq);
+            pb_uint(msg, 6, (uint64_t)(uint32_t)a.score);          // int32 as varint; scores on this path are never negative
+            if (a.flags & GB_ALN_PAIRED) {
+                const std::string mate = read_name(names, name_off, r ^ 1u);
+                std::string frag; pb_bytes(frag, 3, mate.data(), mate.size());
+                pb_msg(msg, (r & 1u) ? 11 : 12, frag);
+            }
+            if ((a.flags & GB_ALN_MAPPED) && L) pb_double(msg, 16, (double)matches / (double)L);
+            std::string st, v;
+            v.clear(); pb_double(v, 2, (double)a.mapq_uncapped); pb_annotation(st, "mapq_uncapped", v);
+            v.clear(); pb_double(v, 2, (double)a.mapq_explored_cap); pb_annotation(st, "mapq_explored_cap", v);
+            if (a.flags & GB_ALN_RESCUED) { v.clear(); pb_tag(v, 4, 0); pb_varint(v, 1); pb_annotation(st, "rescued", v); }
+            pb_msg(msg, 100, st);
+            pb_varint(group, msg.size()); group += msg;
+        }
+        o.put(group.data(), group.size());
     }
     *out_used = o.n;
     return o.overflow ? GB_ERR_CAPACITY : GB_OK;
