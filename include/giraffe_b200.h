@@ -128,6 +128,12 @@ int gb_index_build(uint32_t n_node_ids, const uint8_t* node_seq, const uint64_t*
 void gb_index_free(gb_host_index* ix);
 /* Borrowed view; valid until gb_index_free. */
 int gb_index_view(const gb_host_index* ix, gb_flat_index* out);
+/* The flat index as one file (what giraffe_main.cpp:1825-1881 does for GBZ / .min / .dist): a 64-byte header
+ * ("GBFLAT1", n_nodes, k, w, n_paths, seq_bytes, gbwt_words, table_cells, n_hits) and the six arrays of gb_flat_index
+ * back to back, each padded to 16 bytes, little endian.  gb_index_load checks sizes and offsets and returns
+ * GB_ERR_FORMAT for anything that is not such a file; the result is freed with gb_index_free. */
+int gb_index_save(const gb_flat_index* ix, const char* path);
+int gb_index_load(const char* path, gb_host_index** out);
 
 /* ------------------------------------------------------------------------------------
  * Device handle

@@ -111,3 +111,40 @@ def test_distance_payload_matches_bruteforce_shortest_paths():
         for v, d in best.items():
             if dist[v]["slot"] > dist[u]["slot"]:
                 assert int(dist[v]["x_in"]) - int(dist[u]["x_out"]) == d, (u, v)
+
+
+def test_flat_index_file_roundtrip(tmp_path):
+    """gb_index_save / gb_index_load: the arrays come back bit-identical, a loaded index maps like the built one,
+    and files that are not flat indexes are refused."""
+    import helpers as H
+    from vg_b200 import synth
+    g = synth.make_variant_graph(length=20000, n_snp=30, n_ins=4, n_del=4, n_haps=4, seed=9)
+    built = g.build_index()
+    path = tmp_path / "graph.gbflat"
+    built.save(path)
+    loaded = capi.HostIndex.load(path)
+    assert (loaded.view.n_nodes, loaded.view.k, loaded.view.w, loaded.view.n_paths) == (built.view.n_nodes, built.view.k, built.view.w, built.view.n_paths)
+    for name in ("nodes", "seq", "gbwt", "dist", "table", "hits"):
+        a, b = built.array(name), loaded.array(name)
+        assert a.dtype == b.dtype and a.shape == b.shape and a.tobytes() == b.tobytes(), name
+    rs = synth.simulate_reads(g, 200, length=150, sub_rate=0.01, seed=3)
+    want = H.oracle_map(built, rs.reads, rs.quals, threads=4)
+    got = H.oracle_map(loaded, rs.reads, rs.quals, threads=4)
+    assert not H.compare_alignments(got, want, rs.n, mapq_tol=0)
+    # refused: a truncated file, a foreign file, a missing file
+    raw = path.read_bytes()
+    (tmp_path / "short.gbflat").write_bytes(raw[: len(raw) // 2])
+    (tmp_path / "foreign.gbflat").write_bytes(b"GBZ" + raw[3:])
+    for bad in ("short.gbflat", "foreign.gbflat", "missing.gbflat"):
+        with pytest.raises(capi.GbError):
+            capi.HostIndex.load(tmp_path / bad)
+    # refused: an offset pointing outside the hit array
+    corrupt = bytearray(raw)
+    header = np.frombuffer(raw[:64], dtype=np.uint8)
+    n_hits = int(np.frombuffer(raw[48:56], dtype=np.uint64)[0])
+    assert n_hits == built.view.n_hits
+    corrupt[48:56] = np.uint64(max(1, n_hits // 2)).tobytes()          # claim fewer hits than the table refers to
+    (tmp_path / "corrupt.gbflat").write_bytes(bytes(corrupt))
+    with pytest.raises(capi.GbError):
+        capi.HostIndex.load(tmp_path / "corrupt.gbflat")
+    loaded.close(); built.close()

@@ -118,6 +118,10 @@ def load_library() -> C.CDLL:
     lib.gb_device_destroy.restype = None
     lib.gb_last_error.argtypes = []
     lib.gb_last_error.restype = C.c_char_p
+    lib.gb_index_save.argtypes = [C.POINTER(FlatIndex), C.c_char_p]
+    lib.gb_index_save.restype = C.c_int
+    lib.gb_index_load.argtypes = [C.c_char_p, vp]
+    lib.gb_index_load.restype = C.c_int
     lib.gb_set_scores.argtypes = [vp, C.POINTER(Scores)]
     lib.gb_set_scores.restype = C.c_int
     lib.gb_extend_batch.argtypes = [vp, C.POINTER(ExtendParams), u32, vp, vp, u32, vp, vp, vp, vp, vp, vp, vp, vp]
@@ -216,6 +220,30 @@ class HostIndex:
         self.node_seqs = list(node_seqs)
         self.paths = [list(p) for p in paths]
         self.k, self.w = k, w
+
+    def save(self, path):
+        """gb_index_save: the flat index as one file."""
+        rc = load_library().gb_index_save(C.byref(self.view), str(path).encode())
+        if rc != GB_OK:
+            raise GbError(rc, "gb_index_save")
+
+    @classmethod
+    def load(cls, path):
+        """gb_index_load: an index written by save()."""
+        lib = load_library()
+        h = C.c_void_p()
+        rc = lib.gb_index_load(str(path).encode(), C.byref(h))
+        if rc != GB_OK:
+            raise GbError(rc, "gb_index_load")
+        self = cls.__new__(cls)
+        self._h = h
+        self.view = FlatIndex()
+        rc = lib.gb_index_view(h, C.byref(self.view))
+        if rc != GB_OK:
+            raise GbError(rc, "gb_index_view")
+        self.node_seqs, self.paths = None, None
+        self.k, self.w = int(self.view.k), int(self.view.w)
+        return self
 
     def array(self, name: str) -> np.ndarray:
         v = self.view

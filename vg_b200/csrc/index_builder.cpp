@@ -14,6 +14,7 @@
 #include "minimizer_common.h"
 
 #include <algorithm>
+#include <cstdio>
 #include <cstring>
 #include <numeric>
 #include <string>
@@ -260,5 +261,82 @@ extern "C" int gb_index_view(const gb_host_index* ix, gb_flat_index* out) {
     out->dist = ix->dist.data();
     out->table = ix->table.data(); out->table_cells = ix->table.size();
     out->hits = ix->hits.data(); out->n_hits = ix->hits.size();
+    return GB_OK;
+}
+
+// ---- the flat index on disk ("GBZ-flat" file) ----------------------------------------------------------------
+// What giraffe_main.cpp:1825-1881 does for GBZ / .min / .dist files, for the library's own layout: one file,
+// a 64-byte header and the six arrays of gb_flat_index back to back, each padded to 16 bytes.  Little endian.
+//   header: magic "GBFLAT1\0", n_nodes, k, w, n_paths (u32 each), seq_bytes, gbwt_words, table_cells, n_hits (u64 each), 8 B zero
+namespace {
+
+struct FlatFileHeader {
+    char magic[8];
+    uint32_t n_nodes, k, w, n_paths;
+    uint64_t seq_bytes, gbwt_words, table_cells, n_hits;
+    uint64_t reserved;
+};
+static_assert(sizeof(FlatFileHeader) == 64, "flat file header is 64 bytes");
+
+bool write_padded(FILE* f, const void* p, size_t bytes) {
+    static const char zero[16] = {0};
+    if (bytes && fwrite(p, 1, bytes, f) != bytes) return false;
+    const size_t pad = (16 - bytes % 16) % 16;
+    return pad == 0 || fwrite(zero, 1, pad, f) == pad;
+}
+template <class T> bool read_padded(FILE* f, std::vector<T>& v, size_t count) {
+    v.resize(count);
+    const size_t bytes = count * sizeof(T);
+    if (bytes && fread(v.data(), 1, bytes, f) != bytes) return false;
+    const size_t pad = (16 - bytes % 16) % 16;
+    char skip[16];
+    return pad == 0 || fread(skip, 1, pad, f) == pad;
+}
+
+} // namespace
+
+extern "C" int gb_index_save(const gb_flat_index* ix, const char* path) {
+    if (!ix || !path) return GB_ERR_ARG;
+    FILE* f = fopen(path, "wb");
+    if (!f) return GB_ERR_FORMAT;
+    FlatFileHeader h; memset(&h, 0, sizeof h);
+    memcpy(h.magic, "GBFLAT1", 8);
+    h.n_nodes = ix->n_nodes; h.k = ix->k; h.w = ix->w; h.n_paths = ix->n_paths;
+    h.seq_bytes = ix->seq_bytes; h.gbwt_words = ix->gbwt_words; h.table_cells = ix->table_cells; h.n_hits = ix->n_hits;
+    bool ok = fwrite(&h, 1, sizeof h, f) == sizeof h
+        && write_padded(f, ix->nodes, (size_t)ix->n_nodes * sizeof(gb_node_rec))
+        && write_padded(f, ix->seq, ix->seq_bytes)
+        && write_padded(f, ix->gbwt, ix->gbwt_words * 4)
+        && write_padded(f, ix->dist, (size_t)(ix->n_nodes / 2) * sizeof(gb_dist_payload))
+        && write_padded(f, ix->table, ix->table_cells * sizeof(gb_min_cell))
+        && write_padded(f, ix->hits, ix->n_hits * sizeof(gb_hit));
+    ok = (fclose(f) == 0) && ok;
+    return ok ? GB_OK : GB_ERR_FORMAT;
+}
+
+extern "C" int gb_index_load(const char* path, gb_host_index** out) {
+    if (!path || !out) return GB_ERR_ARG;
+    *out = nullptr;
+    FILE* f = fopen(path, "rb");
+    if (!f) return GB_ERR_FORMAT;
+    FlatFileHeader h;
+    if (fread(&h, 1, sizeof h, f) != sizeof h || memcmp(h.magic, "GBFLAT1", 8) != 0) { fclose(f); return GB_ERR_FORMAT; }
+    // plausibility before allocating: a power-of-two table, an even number of oriented nodes, sizes the file can hold
+    fseek(f, 0, SEEK_END); const uint64_t file_bytes = (uint64_t)ftell(f); fseek(f, (long)sizeof h, SEEK_SET);
+    const uint64_t need = (uint64_t)h.n_nodes * sizeof(gb_node_rec) + h.seq_bytes + h.gbwt_words * 4 + (uint64_t)(h.n_nodes / 2) * sizeof(gb_dist_payload)
+                        + h.table_cells * sizeof(gb_min_cell) + h.n_hits * sizeof(gb_hit);
+    if (h.n_nodes % 2 != 0 || h.table_cells == 0 || (h.table_cells & (h.table_cells - 1)) != 0 || h.k == 0 || h.k > 31 || need > file_bytes) { fclose(f); return GB_ERR_FORMAT; }
+    gb_host_index* ix = new gb_host_index();
+    ix->n_nodes = h.n_nodes; ix->k = h.k; ix->w = h.w; ix->n_paths = h.n_paths;
+    const bool ok = read_padded(f, ix->nodes, h.n_nodes) && read_padded(f, ix->seq, h.seq_bytes) && read_padded(f, ix->gbwt, h.gbwt_words)
+                 && read_padded(f, ix->dist, h.n_nodes / 2) && read_padded(f, ix->table, h.table_cells) && read_padded(f, ix->hits, h.n_hits);
+    fclose(f);
+    if (!ok) { delete ix; return GB_ERR_FORMAT; }
+    // offsets must stay inside the arrays (a truncated or foreign file must not make the kernels read out of bounds)
+    for (const gb_node_rec& r : ix->nodes)
+        if ((uint64_t)r.seq_off + r.len > h.seq_bytes || (r.size && r.rec_off >= h.gbwt_words)) { delete ix; return GB_ERR_FORMAT; }
+    for (const gb_min_cell& c : ix->table)
+        if (c.key != GB_NO_KEY && (uint64_t)c.hit_off + c.hit_cnt > h.n_hits) { delete ix; return GB_ERR_FORMAT; }
+    *out = ix;
     return GB_OK;
 }
