@@ -1,0 +1,93 @@
+"""AddressSanitizer / UBSan pass over the library's host-only C++ (emit.cpp, index_builder.cpp): builds the two files
+with g++ -fsanitize=address,undefined into gpurun_out/libhost_asan.so and drives index build / save / load (including
+truncated and corrupted files) and the three emitters (including output buffers that are too small) through ctypes.
+usage: python scripts/host_sanitize.py        (re-executes itself under LD_PRELOAD=libasan.so)"""
+import ctypes as C, os, subprocess, sys, tempfile
+from pathlib import Path
+
+ROOT = Path(__file__).resolve().parents[1]
+LIB = ROOT / "gpurun_out" / "libhost_asan.so"
+
+if os.environ.get("HOST_SANITIZE_CHILD") != "1":
+    LIB.parent.mkdir(exist_ok=True)
+    src = [str(ROOT / "vg_b200" / "csrc" / f) for f in ("emit.cpp", "index_builder.cpp")]
+    subprocess.run(["g++", "-O1", "-g", "-std=c++17", "-fPIC", "-shared", "-fsanitize=address,undefined", "-fno-omit-frame-pointer",
+                    "-I", str(ROOT / "include"), "-I", str(ROOT / "vg_b200" / "csrc"), "-o", str(LIB)] + src, check=True)
+    asan = subprocess.run(["g++", "-print-file-name=libasan.so"], capture_output=True, text=True).stdout.strip()
+    env = dict(os.environ, HOST_SANITIZE_CHILD="1", LD_PRELOAD=asan, ASAN_OPTIONS="detect_leaks=0:halt_on_error=1", UBSAN_OPTIONS="halt_on_error=1:print_stacktrace=1")
+    sys.exit(subprocess.run([sys.executable, __file__], env=env).returncode)
+
+sys.path.insert(0, str(ROOT)); sys.path.insert(0, str(ROOT / "tests"))
+import numpy as np
+from vg_b200 import capi, synth
+import helpers as H
+
+lib = C.CDLL(str(LIB))
+vp, u32, u64 = C.c_void_p, C.c_uint32, C.c_uint64
+lib.gb_index_build.argtypes = [u32, vp, vp, u32, vp, vp, vp, u32, u32, C.POINTER(vp)]
+lib.gb_index_view.argtypes = [vp, C.POINTER(capi.FlatIndex)]
+lib.gb_index_free.argtypes = [vp]
+lib.gb_index_save.argtypes = [C.POINTER(capi.FlatIndex), C.c_char_p]
+lib.gb_index_load.argtypes = [C.c_char_p, C.POINTER(vp)]
+for fn in (lib.gb_emit_gaf, lib.gb_emit_json, lib.gb_emit_gam):
+    fn.argtypes = [C.POINTER(capi.FlatIndex), u32, vp, vp, vp, vp, vp, vp, vp, vp, vp, u64, vp]
+
+g = synth.make_variant_graph(length=30000, n_snp=48, n_ins=6, n_del=6, n_haps=4, seed=3)
+node_off = np.zeros(len(g.node_seqs) + 1, dtype=np.uint64); node_off[1:] = np.cumsum([len(s) for s in g.node_seqs])
+seq = np.frombuffer("".join(g.node_seqs).encode(), dtype=np.uint8).copy()
+path_off = np.zeros(len(g.paths) + 1, dtype=np.uint64); path_off[1:] = np.cumsum([len(p) for p in g.paths])
+flat = np.concatenate([np.asarray(p, dtype=np.uint32) for p in g.paths])
+dist = np.ascontiguousarray(g.dist, dtype=capi.dist_dt)
+h = vp()
+assert lib.gb_index_build(len(g.node_seqs), capi.ptr(seq), capi.ptr(node_off), len(g.paths), capi.ptr(flat), capi.ptr(path_off), capi.ptr(dist), 29, 11, C.byref(h)) == 0
+view = capi.FlatIndex(); assert lib.gb_index_view(h, C.byref(view)) == 0
+
+with tempfile.TemporaryDirectory() as tmp:
+    p = os.path.join(tmp, "x.gbflat").encode()
+    assert lib.gb_index_save(C.byref(view), p) == 0
+    h2 = vp(); assert lib.gb_index_load(p, C.byref(h2)) == 0
+    lib.gb_index_free(h2)
+    raw = open(p, "rb").read()
+    rng = np.random.default_rng(1)
+    refused = 0
+    for t in range(200):                                    # truncations and random corruptions of header / offsets
+        b = bytearray(raw)
+        if t % 2 == 0:
+            b = b[: int(rng.integers(0, len(b)))]
+        else:
+            for _ in range(int(rng.integers(1, 6))):
+                pos = int(rng.integers(0, min(len(b), 64 + 16 * view.n_nodes)))
+                b[pos] = int(rng.integers(0, 256))
+        q = os.path.join(tmp, "bad.gbflat")
+        open(q, "wb").write(bytes(b))
+        hb = vp(); rc = lib.gb_index_load(q.encode(), C.byref(hb))
+        if rc == 0:
+            lib.gb_index_free(hb)
+        else:
+            refused += 1
+    print("corrupted files refused:", refused, "of 200 (the rest still passed every check)")
+
+# records from the oracle (tail alignments, soft clips, unmapped reads, pairs), through all three emitters
+index = g.build_index()
+rs = synth.simulate_pairs(g, 120, sub_rate=0.02, seed=5, indel_rate=0.002)
+rng = np.random.default_rng(2)
+for i in rng.integers(0, rs.n, size=12):
+    rs.reads[i, :15] = synth.BASES[rng.integers(0, 4, size=15)]
+rs.reads[9] = synth.BASES[rng.integers(0, 4, size=rs.length)]
+res = H.oracle_map_paired(index, rs.reads, rs.quals, H.paired_params(), threads=4)
+rbuf, qbuf, read_off = H.pack_reads(rs.reads, rs.quals)
+aln = np.ascontiguousarray(res[0])
+for fn in (lib.gb_emit_gaf, lib.gb_emit_json, lib.gb_emit_gam):
+    for quals in (qbuf, None):
+        need = None
+        for cap in (1 << 22, 0, 1, 17, 1000, 40000):
+            out = np.zeros(max(cap, 1), dtype=np.uint8); used = u64()
+            rc = fn(C.byref(view), len(aln), capi.ptr(aln), capi.ptr(res[1]), capi.ptr(res[2]), capi.ptr(rbuf), capi.ptr(quals) if quals is not None else None,
+                    capi.ptr(read_off), None, None, capi.ptr(out), cap, C.byref(used))
+            if cap == 1 << 22:
+                assert rc == 0; need = used.value
+            else:
+                assert (rc == 0) == (cap >= need), (cap, need, rc)
+                assert used.value <= cap
+lib.gb_index_free(h)
+print("host sanitizer pass: no AddressSanitizer / UBSan report")

@@ -333,8 +333,18 @@ extern "C" int gb_index_load(const char* path, gb_host_index** out) {
     fclose(f);
     if (!ok) { delete ix; return GB_ERR_FORMAT; }
     // offsets must stay inside the arrays (a truncated or foreign file must not make the kernels read out of bounds)
-    for (const gb_node_rec& r : ix->nodes)
-        if ((uint64_t)r.seq_off + r.len > h.seq_bytes || (r.size && r.rec_off >= h.gbwt_words)) { delete ix; return GB_ERR_FORMAT; }
+    for (const gb_node_rec& r : ix->nodes) {
+        if ((uint64_t)r.seq_off + r.len > h.seq_bytes) { delete ix; return GB_ERR_FORMAT; }
+        if (r.size == 0) continue;
+        // GBWT record: n_edges, n_runs, n_edges x {to, offset}, n_runs x {(len << 10) | outrank}; everything inside the blob
+        if ((uint64_t)r.rec_off + 2 > h.gbwt_words) { delete ix; return GB_ERR_FORMAT; }
+        const uint32_t* rec = ix->gbwt.data() + r.rec_off;
+        const uint64_t n_edges = rec[0], n_runs = rec[1];
+        if ((uint64_t)r.rec_off + 2 + 2 * n_edges + n_runs > h.gbwt_words) { delete ix; return GB_ERR_FORMAT; }
+        for (uint64_t e = 0; e < n_edges; e++) if (rec[2 + 2 * e] >= h.n_nodes) { delete ix; return GB_ERR_FORMAT; }
+        for (uint64_t t = 0; t < n_runs; t++) if ((rec[2 + 2 * n_edges + t] & 1023u) >= n_edges) { delete ix; return GB_ERR_FORMAT; }
+    }
+    for (const gb_hit& hit : ix->hits) if ((hit.pos >> 10) >= h.n_nodes) { delete ix; return GB_ERR_FORMAT; }
     for (const gb_min_cell& c : ix->table)
         if (c.key != GB_NO_KEY && (uint64_t)c.hit_off + c.hit_cnt > h.n_hits) { delete ix; return GB_ERR_FORMAT; }
     *out = ix;
