@@ -132,6 +132,12 @@ int gb_index_view(const gb_host_index* ix, gb_flat_index* out);
  * ("GBFLAT1", n_nodes, k, w, n_paths, seq_bytes, gbwt_words, table_cells, n_hits) and the six arrays of gb_flat_index
  * back to back, each padded to 16 bytes, little endian.  gb_index_load checks sizes and offsets and returns
  * GB_ERR_FORMAT for anything that is not such a file; the result is freed with gb_index_free. */
+/* Build the flat index from a GBZ file (gbwtgraph::GBZ, what `vg giraffe -Z` loads, giraffe_main.cpp:1825-1881): node
+ * sequences from the GBWTGraph, haplotype paths by walking the bidirectional GBWT, the distance payload from the
+ * chain-of-bubbles decomposition of those paths, minimizers (k, w) by the library's own builder.  GBZ version 1 /
+ * GBWT version 5 / GBWTGraph version 3 in simple-sds serialization.  GB_ERR_FORMAT for anything else, and for graphs
+ * outside the index model (nested or overlapping sites, alleles of several nodes, reversing haplotypes). */
+int gb_index_from_gbz(const char* path, uint32_t k, uint32_t w, gb_host_index** out);
 int gb_index_save(const gb_flat_index* ix, const char* path);
 int gb_index_load(const char* path, gb_host_index** out);
 

@@ -1,4 +1,4 @@
-"""AddressSanitizer / UBSan pass over the library's host-only C++ (emit.cpp, index_builder.cpp): builds the two files
+"""AddressSanitizer / UBSan pass over the library's host-only C++ (emit.cpp, index_builder.cpp, gbz_reader.cpp): builds the files
 with g++ -fsanitize=address,undefined into gpurun_out/libhost_asan.so and drives index build / save / load (including
 truncated and corrupted files) and the three emitters (including output buffers that are too small) through ctypes.
 usage: python scripts/host_sanitize.py        (re-executes itself under LD_PRELOAD=libasan.so)"""
@@ -10,7 +10,7 @@ LIB = ROOT / "gpurun_out" / "libhost_asan.so"
 
 if os.environ.get("HOST_SANITIZE_CHILD") != "1":
     LIB.parent.mkdir(exist_ok=True)
-    src = [str(ROOT / "vg_b200" / "csrc" / f) for f in ("emit.cpp", "index_builder.cpp")]
+    src = [str(ROOT / "vg_b200" / "csrc" / f) for f in ("emit.cpp", "index_builder.cpp", "gbz_reader.cpp")]
     subprocess.run(["g++", "-O1", "-g", "-std=c++17", "-fPIC", "-shared", "-fsanitize=address,undefined", "-fno-omit-frame-pointer",
                     "-I", str(ROOT / "include"), "-I", str(ROOT / "vg_b200" / "csrc"), "-o", str(LIB)] + src, check=True)
     asan = subprocess.run(["g++", "-print-file-name=libasan.so"], capture_output=True, text=True).stdout.strip()
@@ -66,6 +66,26 @@ with tempfile.TemporaryDirectory() as tmp:
         else:
             refused += 1
     print("corrupted files refused:", refused, "of 200 (the rest still passed every check)")
+
+# the GBZ reader on the reference's test GBZ: intact, truncated, and with random bytes overwritten (must refuse or build, never fault)
+lib.gb_index_from_gbz.argtypes = [C.c_char_p, u32, u32, C.POINTER(vp)]
+gbz = (ROOT / "tests" / "golden" / "gbz" / "y.giraffe.gbz").read_bytes()
+with tempfile.TemporaryDirectory() as tmp:
+    q = os.path.join(tmp, "y.gbz"); open(q, "wb").write(gbz)
+    hg = vp(); assert lib.gb_index_from_gbz(q.encode(), 29, 11, C.byref(hg)) == 0; lib.gb_index_free(hg)
+    rng = np.random.default_rng(3); built = 0
+    for t in range(400):
+        b = bytearray(gbz)
+        if t % 4 == 0:
+            b = b[: 8 * int(rng.integers(0, len(b) // 8))]
+        else:
+            for _ in range(int(rng.integers(1, 4))):
+                b[int(rng.integers(0, len(b)))] = int(rng.integers(0, 256))
+        open(q, "wb").write(bytes(b))
+        hg = vp()
+        if lib.gb_index_from_gbz(q.encode(), 29, 11, C.byref(hg)) == 0:
+            built += 1; lib.gb_index_free(hg)
+    print("damaged GBZ files: refused", 400 - built, "built", built)
 
 # records from the oracle (tail alignments, soft clips, unmapped reads, pairs), through all three emitters
 index = g.build_index()

@@ -1,0 +1,195 @@
+"""gb_index_from_gbz on the GBZ the reference ships as test data (test/primers/y.giraffe.gbz, copied to
+tests/golden/gbz/): 66 nodes, 1012 bp, 3 haplotypes.  An independent reader of the published simple-sds / GBWT /
+GBWTGraph layout (below, Python) must agree with the library's reader on every array of the flat index, the
+distance payload must be consistent with the haplotypes, and reads drawn from the haplotypes must map back."""
+import struct
+from pathlib import Path
+
+import numpy as np
+import pytest
+
+import helpers as H
+from vg_b200 import capi, synth
+
+GBZ = Path(__file__).parent / "golden" / "gbz" / "y.giraffe.gbz"
+
+
+def read_gbz(path):
+    """-> (node sequences by id order, forward haplotype paths as GBWT nodes, header facts)."""
+    raw = path.read_bytes()
+    W = struct.unpack("<%dQ" % (len(raw) // 8), raw)
+    pos = [0]
+
+    def u():
+        pos[0] += 1
+        return W[pos[0] - 1]
+
+    def raw_vector():
+        bits, n = u(), u()
+        return bits, [u() for _ in range(n)]
+
+    def skip_optional():
+        n = u()
+        pos[0] += n
+
+    def int_vector():
+        n, width = u(), u()
+        bits, words = raw_vector()
+        big = 0
+        for k, x in enumerate(words):
+            big |= x << (64 * k)
+        return [(big >> (k * width)) & ((1 << width) - 1) for k in range(n)], width
+
+    def sparse_values():
+        universe, ones = u(), u()
+        bits, words = raw_vector()
+        skip_optional(); skip_optional(); skip_optional()
+        low, width = int_vector()
+        ones_at = [p for p in range(bits) if (words[p >> 6] >> (p & 63)) & 1]
+        assert len(ones_at) == ones == len(low)
+        return [((p - i) << width) | low[i] for i, p in enumerate(ones_at)], universe
+
+    def vector_u8():
+        n = u()
+        b = raw[pos[0] * 8: pos[0] * 8 + n]
+        pos[0] += (n + 7) // 8
+        return b
+
+    def string_array():
+        starts, _ = sparse_values()
+        alphabet = vector_u8()
+        ranks, _ = int_vector()
+        s = "".join(chr(alphabet[c]) for c in ranks)
+        return [s[a:b] for a, b in zip(starts, starts[1:] + [len(s)])]
+
+    h = u(); u()
+    assert h & 0xFFFFFFFF == 0x205A4247 and h >> 32 == 1
+    gbz_tags = string_array()
+    g = u()
+    assert g & 0xFFFFFFFF == 0x6B376B37 and g >> 32 == 5
+    sequences, size, offset, sigma, flags = u(), u(), u(), u(), u()
+    gbwt_tags = string_array()
+    starts, universe = sparse_values()
+    data = vector_u8()
+    assert universe == len(data) and len(starts) == sigma - offset
+    skip_optional(); skip_optional()
+    gg = u()
+    assert gg & 0xFFFFFFFF == 0x6B3764AF and gg >> 32 == 3
+    n_nodes = u(); u()
+    seqs = string_array()
+    assert len(seqs) == n_nodes
+
+    def bytecode(b, i):
+        v = s = 0
+        while True:
+            c = b[i]; i += 1; v |= (c & 0x7F) << s; s += 7
+            if not c & 0x80:
+                return v, i
+
+    records = []
+    for k in range(len(starts)):
+        b = data[starts[k]: starts[k + 1] if k + 1 < len(starts) else len(data)]
+        edges, runs, i = [], [], 0
+        if b:
+            deg, i = bytecode(b, i); prev = 0
+            for _ in range(deg):
+                d, i = bytecode(b, i); o, i = bytecode(b, i); prev += d; edges.append((prev, o))
+            cont = 256 // deg if 0 < deg < 255 else 0
+            while i < len(b):
+                if deg >= 255:
+                    v, i = bytecode(b, i); ln, i = bytecode(b, i); ln += 1
+                else:
+                    c = b[i]; i += 1; v, ln = c % deg, c // deg + 1
+                    if ln == cont:
+                        extra, i = bytecode(b, i); ln += extra
+                runs.append((v, ln))
+        records.append((edges, runs))
+
+    def lf(comp, p):
+        edges, runs = records[comp]
+        seen, at = [0] * len(edges), 0
+        for v, ln in runs:
+            if p < at + ln:
+                return edges[v][0], edges[v][1] + seen[v] + (p - at)
+            seen[v] += ln; at += ln
+        raise IndexError
+
+    paths, total = [], 0
+    for s in range(sequences):
+        node, p = lf(0, s); walk = []
+        while node:
+            walk.append(node); node, p = lf(node - offset, p)
+        total += len(walk) + 1
+        if s % 2 == 0:
+            paths.append(walk)
+    return seqs, paths, {"sequences": sequences, "size": size, "total": total, "tags": gbz_tags + gbwt_tags}
+
+
+def test_independent_reader_agrees_with_the_file_header():
+    seqs, paths, facts = read_gbz(GBZ)
+    assert facts["sequences"] == 6 and facts["total"] == facts["size"] == 322          # every BWT position is walked exactly once
+    assert len(seqs) == 66 and sum(map(len, seqs)) == 1012 and max(map(len, seqs)) <= 32
+    assert "jltsiren/gbwtgraph" in facts["tags"] and "reference_samples" in facts["tags"]
+    assert len(paths) == 3 and all(v % 2 == 0 for p in paths for v in p)
+
+
+def test_library_reader_builds_the_same_index_as_the_independent_reader():
+    seqs, paths, _ = read_gbz(GBZ)
+    from_gbz = capi.HostIndex.from_gbz(GBZ)
+    assert (from_gbz.view.n_nodes, from_gbz.view.n_paths, from_gbz.view.k, from_gbz.view.w) == (2 * 67, 3, 29, 11)
+    rebuilt = capi.HostIndex(seqs, paths, from_gbz.array("dist").copy(), k=29, w=11)            # same payload, everything else independent
+    for name in ("nodes", "seq", "gbwt", "table", "hits"):
+        assert from_gbz.array(name).tobytes() == rebuilt.array(name).tobytes(), name
+    from_gbz.close(); rebuilt.close()
+
+
+def test_payload_is_consistent_with_the_haplotypes():
+    seqs, paths, _ = read_gbz(GBZ)
+    index = capi.HostIndex.from_gbz(GBZ)
+    dist = index.array("dist")
+    length = {i + 1: len(s) for i, s in enumerate(seqs)}
+    on_all = set.intersection(*[set(v >> 1 for v in p) for p in paths])
+    for p in paths:
+        ids = [v >> 1 for v in p]
+        assert [int(dist[i]["slot"]) for i in ids] == sorted(int(dist[i]["slot"]) for i in ids)          # slots grow along every haplotype
+        assert len(set(int(dist[i]["slot"]) for i in ids)) == len(ids)
+        for a in range(len(ids)):
+            walked = 0
+            for b in range(a + 1, len(ids)):
+                d = int(dist[ids[b]]["x_in"]) - int(dist[ids[a]]["x_out"])
+                assert 0 <= d <= walked                                                                 # the payload distance is a minimum over haplotypes
+                if b == a + 1:
+                    assert d == 0                                                                       # neighbours on a haplotype touch
+                walked += length[ids[b]]
+    for i in on_all:
+        assert int(dist[i]["allele"]) == 0xFFFF                                                         # backbone nodes are single-allele slots
+    index.close()
+
+
+def test_reads_from_the_haplotypes_map_back():
+    seqs, paths, _ = read_gbz(GBZ)
+    index = capi.HostIndex.from_gbz(GBZ)
+    rng = np.random.default_rng(7)
+    haps = ["".join(seqs[(v >> 1) - 1] for v in p) for p in paths]
+    reads = []
+    for _ in range(60):
+        h = haps[int(rng.integers(0, len(haps)))]
+        s = int(rng.integers(0, len(h) - 150))
+        r = np.frombuffer(h[s:s + 150].encode(), dtype=np.uint8).copy()
+        if rng.random() < 0.5:
+            r = synth.revcomp_bytes(r[None, :])[0]
+        reads.append(r)
+    reads = np.stack(reads); quals = np.full(reads.shape, 30, dtype=np.uint8)
+    res = H.oracle_map(index, reads, quals, threads=4)
+    assert (res[0]["flags"] & 1).all() and (res[0]["score"] == 160).all()                              # exact, full length, both bonuses
+    index.close()
+
+
+def test_foreign_and_truncated_files_are_refused(tmp_path):
+    raw = GBZ.read_bytes()
+    (tmp_path / "short.gbz").write_bytes(raw[:1000])
+    (tmp_path / "other.gbz").write_bytes(b"\\x00" * 8 + raw[8:])
+    (tmp_path / "odd.gbz").write_bytes(raw[:-3])
+    for name in ("short.gbz", "other.gbz", "odd.gbz", "missing.gbz"):
+        with pytest.raises(capi.GbError):
+            capi.HostIndex.from_gbz(tmp_path / name)

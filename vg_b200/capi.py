@@ -118,6 +118,8 @@ def load_library() -> C.CDLL:
     lib.gb_device_destroy.restype = None
     lib.gb_last_error.argtypes = []
     lib.gb_last_error.restype = C.c_char_p
+    lib.gb_index_from_gbz.argtypes = [C.c_char_p, u32, u32, vp]
+    lib.gb_index_from_gbz.restype = C.c_int
     lib.gb_index_save.argtypes = [C.POINTER(FlatIndex), C.c_char_p]
     lib.gb_index_save.restype = C.c_int
     lib.gb_index_load.argtypes = [C.c_char_p, vp]
@@ -226,6 +228,24 @@ class HostIndex:
         rc = load_library().gb_index_save(C.byref(self.view), str(path).encode())
         if rc != GB_OK:
             raise GbError(rc, "gb_index_save")
+
+    @classmethod
+    def from_gbz(cls, path, k=29, w=11):
+        """gb_index_from_gbz: the flat index of a GBZ file (graphs that are chains of bubbles)."""
+        lib = load_library()
+        h = C.c_void_p()
+        rc = lib.gb_index_from_gbz(str(path).encode(), k, w, C.byref(h))
+        if rc != GB_OK:
+            raise GbError(rc, "gb_index_from_gbz")
+        self = cls.__new__(cls)
+        self._h = h
+        self.view = FlatIndex()
+        rc = lib.gb_index_view(h, C.byref(self.view))
+        if rc != GB_OK:
+            raise GbError(rc, "gb_index_view")
+        self.node_seqs, self.paths = None, None
+        self.k, self.w = k, w
+        return self
 
     @classmethod
     def load(cls, path):

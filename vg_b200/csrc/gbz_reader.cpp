@@ -1,0 +1,287 @@
+// gbz_reader.cpp — read a GBZ file (what `vg giraffe -Z` loads, giraffe_main.cpp:1825-1881) and build the flat index
+// from it: node sequences from the GBWTGraph, haplotype paths by walking the GBWT, the 16-byte distance payload from
+// the chain-of-bubbles decomposition of those paths, minimizers by the library's own index builder.
+//
+// gbwt (jltsiren/gbwt @ c2e0199), gbwtgraph (@ e27bc43) and simple-sds are ABSENT from the reference tree; the layout
+// below is their published serialization format, checked against the GBZ the reference ships as test data
+// (test/primers/y.giraffe.gbz, kept as tests/golden/gbz/y.giraffe.gbz): 66 nodes, 1012 bp, 3 haplotypes, BWT size 322.
+//   simple-sds      little-endian 64-bit elements; Vector<T> = len + items padded to 8 B; RawVector = bit length +
+//                   Vector<u64>; BitVector = ones + RawVector + 3 optional supports (each: size in elements + data);
+//                   IntVector = len + width + RawVector; SparseVector (Elias-Fano) = len + high BitVector + low
+//                   IntVector, value i = ((position of the i-th one - i) << width) | low[i];
+//                   StringArray = SparseVector of string starts + alphabet Vector<u8> + IntVector of alphabet ranks
+//   GBZ             tag "GBZ " / version 1, flags, Tags (StringArray), GBWT, GBWTGraph
+//   GBWT            tag 0x6B376B37 / version 5, sequences, size, offset, alphabet size, flags; Tags; BWT = SparseVector
+//                   of record starts + Vector<u8>; optional DA samples; optional metadata
+//   GBWT record     ByteCode outdegree, outdegree x (ByteCode successor delta, ByteCode offset), runs: for outdegree
+//                   sigma < 255 one byte c = rank + sigma (len - 1), len == 256 / sigma continues with a ByteCode;
+//                   otherwise ByteCode rank + ByteCode (len - 1)
+//   GBWTGraph       tag 0x6B3764AF / version 3, nodes, flags, forward sequences (StringArray), node-to-segment translation
+// Only what this path needs is kept; anything the reader does not understand is GB_ERR_FORMAT, never a guess.
+#include "giraffe_b200.h"
+
+#include <algorithm>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <map>
+#include <set>
+#include <string>
+#include <vector>
+
+namespace {
+
+struct Reader {
+    const std::vector<uint64_t>& w; const std::vector<uint8_t>& bytes; size_t i = 0; bool ok = true;
+    uint64_t u() { if (i >= w.size()) { ok = false; return 0; } return w[i++]; }
+    void skip(uint64_t n) { if (n > w.size() - i) { ok = false; i = w.size(); } else i += n; }
+};
+
+bool raw_vector(Reader& r, uint64_t& bits, std::vector<uint64_t>& words) {
+    bits = r.u(); const uint64_t n = r.u();
+    if (!r.ok || n > r.w.size() - r.i || bits > n * 64) return r.ok = false;
+    words.assign(r.w.begin() + r.i, r.w.begin() + r.i + n); r.i += n;
+    return true;
+}
+void skip_optional(Reader& r) { r.skip(r.u()); }
+
+bool int_vector(Reader& r, std::vector<uint64_t>& out, uint64_t* width_out = nullptr) {
+    const uint64_t n = r.u(), width = r.u();
+    uint64_t bits; std::vector<uint64_t> words;
+    if (!raw_vector(r, bits, words) || width == 0 || width > 64 || n > bits / width + 1 || n * width > bits) return r.ok = false;
+    out.resize(n);
+    for (uint64_t k = 0; k < n; k++) {
+        const uint64_t b = k * width, wd = b >> 6, sh = b & 63;
+        uint64_t v = words[wd] >> sh;
+        if (sh + width > 64) v |= words[wd + 1] << (64 - sh);
+        out[k] = width == 64 ? v : v & ((1ull << width) - 1);
+    }
+    if (width_out) *width_out = width;
+    return true;
+}
+
+bool sparse_values(Reader& r, std::vector<uint64_t>& values, uint64_t& universe) {
+    universe = r.u();
+    const uint64_t ones = r.u();
+    uint64_t bits; std::vector<uint64_t> words;
+    if (!raw_vector(r, bits, words)) return false;
+    skip_optional(r); skip_optional(r); skip_optional(r);
+    std::vector<uint64_t> low; uint64_t width = 0;
+    if (!r.ok || !int_vector(r, low, &width) || low.size() != ones) return r.ok = false;
+    values.clear();
+    for (uint64_t p = 0; p < bits; p++) if ((words[p >> 6] >> (p & 63)) & 1) {
+        const uint64_t idx = values.size();
+        if (idx >= ones || p < idx) return r.ok = false;
+        values.push_back(((p - idx) << width) | low[idx]);
+    }
+    return values.size() == ones ? true : (r.ok = false);
+}
+
+bool vector_u8(Reader& r, std::vector<uint8_t>& out) {
+    const uint64_t n = r.u();
+    const uint64_t start = (uint64_t)r.i * 8;
+    if (!r.ok || n > r.bytes.size() - start) return r.ok = false;
+    out.assign(r.bytes.begin() + start, r.bytes.begin() + start + n);
+    r.skip((n + 7) / 8);
+    return r.ok;
+}
+
+bool string_array(Reader& r, std::vector<std::string>& out) {
+    std::vector<uint64_t> starts, ranks; uint64_t universe; std::vector<uint8_t> alphabet;
+    if (!sparse_values(r, starts, universe) || !vector_u8(r, alphabet) || !int_vector(r, ranks)) return false;
+    std::string all(ranks.size(), '\0');
+    for (size_t k = 0; k < ranks.size(); k++) { if (ranks[k] >= alphabet.size()) return r.ok = false; all[k] = (char)alphabet[ranks[k]]; }
+    out.clear();
+    for (size_t s = 0; s < starts.size(); s++) {
+        const uint64_t a = starts[s], b = s + 1 < starts.size() ? starts[s + 1] : all.size();
+        if (a > b || b > all.size()) return r.ok = false;
+        out.push_back(all.substr(a, b - a));
+    }
+    return true;
+}
+
+uint64_t bytecode(const std::vector<uint8_t>& b, size_t& i, size_t end, bool& ok) {
+    uint64_t v = 0; int shift = 0;
+    while (true) {
+        if (i >= end || shift > 56) { ok = false; return 0; }
+        const uint8_t c = b[i++]; v |= (uint64_t)(c & 0x7F) << shift; shift += 7;
+        if (!(c & 0x80)) return v;
+    }
+}
+
+struct Record { std::vector<std::pair<uint64_t, uint64_t>> edges; std::vector<std::pair<uint32_t, uint64_t>> runs; };
+
+int fail(const char* why) { if (getenv("GB_GBZ_DEBUG")) fprintf(stderr, "gbz reader: %s\n", why); return GB_ERR_FORMAT; }
+
+} // namespace
+
+extern "C" int gb_index_from_gbz(const char* path, uint32_t k, uint32_t w, gb_host_index** out) {
+    if (!path || !out) return GB_ERR_ARG;
+    *out = nullptr;
+    FILE* f = fopen(path, "rb");
+    if (!f) return fail("open");
+    std::vector<uint8_t> bytes;
+    { uint8_t buf[65536]; size_t n; while ((n = fread(buf, 1, sizeof buf, f)) > 0) bytes.insert(bytes.end(), buf, buf + n); }
+    fclose(f);
+    if (bytes.size() < 64 || bytes.size() % 8 != 0) return fail("size");
+    std::vector<uint64_t> words(bytes.size() / 8);
+    memcpy(words.data(), bytes.data(), bytes.size());
+    Reader r{words, bytes};
+
+    // ---- GBZ header, tags ----
+    const uint64_t h0 = r.u(); r.u();
+    if ((uint32_t)h0 != 0x205A4247u || (h0 >> 32) != 1) return fail("not a GBZ version 1 file");
+    std::vector<std::string> tags;
+    if (!string_array(r, tags)) return fail("gbz tags");
+    // ---- GBWT ----
+    const uint64_t g0 = r.u();
+    if ((uint32_t)g0 != 0x6B376B37u || (g0 >> 32) != 5) return fail("gbwt header");
+    const uint64_t sequences = r.u(), size = r.u(), offset = r.u(), alphabet_size = r.u(), gflags = r.u();
+    if (!r.ok || !(gflags & 1) || !(gflags & 4) || alphabet_size <= offset + 1 || sequences % 2 != 0) return fail("gbwt must be bidirectional simple-sds");
+    if (size > (1ull << 31) || sequences > size) return fail("gbwt too large for this reader");
+    if (!string_array(r, tags)) return fail("gbwt tags");
+    std::vector<uint64_t> rec_start; uint64_t universe; std::vector<uint8_t> data;
+    if (!sparse_values(r, rec_start, universe) || !vector_u8(r, data) || universe != data.size() || rec_start.size() != alphabet_size - offset) return fail("bwt");
+    skip_optional(r); skip_optional(r);          // document-array samples, metadata
+    // ---- GBWTGraph ----
+    const uint64_t gg = r.u(), n_graph_nodes = r.u(); r.u();
+    if (!r.ok || (uint32_t)gg != 0x6B3764AFu || (gg >> 32) != 3) return fail("gbwtgraph header");
+    std::vector<std::string> seqs;
+    if (!string_array(r, seqs) || seqs.size() != n_graph_nodes) return fail("sequences");
+
+    // ---- records ----
+    std::vector<Record> records(rec_start.size());
+    for (size_t c = 0; c < rec_start.size(); c++) {
+        size_t i = rec_start[c]; const size_t end = c + 1 < rec_start.size() ? rec_start[c + 1] : data.size();
+        if (i > end || end > data.size()) return fail("record bounds");
+        if (i == end) continue;
+        bool ok = true;
+        const uint64_t sigma = bytecode(data, i, end, ok);
+        uint64_t prev = 0;
+        for (uint64_t e = 0; e < sigma && ok; e++) { prev += bytecode(data, i, end, ok); const uint64_t o = bytecode(data, i, end, ok); records[c].edges.push_back({prev, o}); }
+        if (!ok) return fail("record edges");
+        const uint64_t run_continues = sigma && sigma < 255 ? 256 / sigma : 0;
+        while (i < end && sigma) {
+            uint64_t rank, len;
+            if (sigma >= 255) { rank = bytecode(data, i, end, ok); len = bytecode(data, i, end, ok) + 1; }
+            else { const uint8_t cb = data[i++]; rank = cb % sigma; len = cb / sigma + 1; if (len == run_continues) len += bytecode(data, i, end, ok); }
+            if (!ok || rank >= sigma) return fail("record runs");
+            records[c].runs.push_back({(uint32_t)rank, len});
+        }
+    }
+    // LF(record, position) -> (successor node, position in its record)
+    auto lf = [&](uint64_t comp, uint64_t pos, uint64_t& node, uint64_t& next) -> bool {
+        if (comp >= records.size()) return false;
+        const Record& rc = records[comp];
+        std::vector<uint64_t> seen(rc.edges.size(), 0);
+        uint64_t p = 0;
+        for (const auto& run : rc.runs) {
+            if (pos < p + run.second) { node = rc.edges[run.first].first; next = rc.edges[run.first].second + seen[run.first] + (pos - p); return true; }
+            seen[run.first] += run.second; p += run.second;
+        }
+        return false;
+    };
+    // ---- haplotype paths: the forward orientation of each bidirectional sequence pair ----
+    // GBWT node = 2 * id + orientation; graph sequence s belongs to id first_id + s
+    const uint64_t first_id = (offset + 1) / 2;
+    const uint64_t n_ids = first_id + n_graph_nodes - 1;               // ids 1 .. n_ids are addressable; those below first_id stay empty
+    if (n_ids == 0 || n_ids > (1u << 26)) return fail("node ids");
+    std::vector<std::vector<uint32_t>> paths;
+    uint64_t walked = 0;
+    for (uint64_t s = 0; s < sequences; s += 2) {
+        uint64_t node, pos;
+        if (!lf(0, s, node, pos)) return fail("endmarker");
+        std::vector<uint32_t> p;
+        while (node != 0) {
+            if (node <= offset || node >= alphabet_size || (node >> 1) > n_ids || walked++ > size) return fail("walk");
+            p.push_back((uint32_t)node);
+            uint64_t nn, np;
+            if (!lf(node - offset, pos, nn, np)) return fail("lf");
+            node = nn; pos = np;
+        }
+        paths.push_back(p);                     // identical haplotypes stay: GBWT record sizes count visits
+    }
+    // ---- node sequences ----
+    std::vector<uint8_t> node_seq; std::vector<uint64_t> node_off(n_ids + 1, 0);
+    std::vector<uint32_t> len(n_ids + 1, 0);
+    for (uint64_t id = 1; id <= n_ids; id++) {
+        if (id >= first_id) { const std::string& s = seqs[id - first_id]; node_seq.insert(node_seq.end(), s.begin(), s.end()); len[id] = (uint32_t)s.size(); }
+        node_off[id] = node_seq.size();
+    }
+    // ---- chain of bubbles -> distance payload ------------------------------------------------------------
+    // All haplotypes are walked in step.  Where they stand on the same node, that node is a backbone slot; where they
+    // differ, each runs to the next node common to all of them and what it passed in between is its allele: at most
+    // one node (an empty allele is a deletion).  Anything else (nested or overlapping sites, multi-node alleles,
+    // reverse-strand steps, haplotypes that do not span the chain) is outside the index model.
+    std::vector<std::vector<uint32_t>> walks;
+    for (const auto& p : paths) {
+        std::vector<uint32_t> ids;
+        for (uint32_t v : p) { if (v & 1u) return fail("reverse step on a haplotype"); ids.push_back(v >> 1); }
+        if (ids.empty()) return fail("empty haplotype");
+        if (std::find(walks.begin(), walks.end(), ids) == walks.end()) walks.push_back(ids);
+    }
+    std::vector<std::vector<uint32_t>> slots;              // allele node ids, 0 = empty allele
+    std::vector<size_t> at(walks.size(), 0);
+    while (true) {
+        bool all_end = true, any_end = false;
+        for (size_t h = 0; h < walks.size(); h++) { if (at[h] < walks[h].size()) all_end = false; else any_end = true; }
+        if (all_end) break;
+        if (any_end) return fail("haplotypes of different extent");
+        bool same = true;
+        for (size_t h = 1; h < walks.size(); h++) same &= walks[h][at[h]] == walks[0][at[0]];
+        if (same) { slots.push_back({walks[0][at[0]]}); for (size_t& a : at) a++; continue; }
+        // next node common to all haplotypes: the first node of haplotype 0 ahead that every other haplotype also has ahead
+        size_t meet0 = walks[0].size(); std::vector<size_t> meet(walks.size(), 0);
+        for (size_t x = at[0]; x < walks[0].size() && meet0 == walks[0].size(); x++) {
+            bool everywhere = true;
+            for (size_t h = 1; h < walks.size() && everywhere; h++) {
+                auto it = std::find(walks[h].begin() + at[h], walks[h].end(), walks[0][x]);
+                if (it == walks[h].end()) everywhere = false; else meet[h] = (size_t)(it - walks[h].begin());
+            }
+            if (everywhere) { meet0 = x; meet[0] = x; }
+        }
+        const bool tail_bubble = meet0 == walks[0].size();   // a site at the very end of the chain: alleles run to the end
+        std::vector<size_t> stop(walks.size());
+        size_t longest = 0, shortest = (size_t)-1;
+        for (size_t h = 0; h < walks.size(); h++) {
+            stop[h] = tail_bubble ? walks[h].size() : meet[h];
+            longest = std::max(longest, stop[h] - at[h]); shortest = std::min(shortest, stop[h] - at[h]);
+        }
+        // one site (alleles of at most one node, possibly empty), or several adjacent sites with no backbone node between
+        // them (every haplotype crosses the same number of nodes: one slot per position)
+        if (longest > 1 && shortest != longest) return fail("an allele spans several nodes");
+        const size_t n_sites = std::max<size_t>(longest, 1);
+        for (size_t j = 0; j < n_sites; j++) {
+            std::vector<uint32_t> alleles;
+            for (size_t h = 0; h < walks.size(); h++) {
+                const uint32_t a = at[h] + j < stop[h] ? walks[h][at[h] + j] : 0u;
+                if (std::find(alleles.begin(), alleles.end(), a) == alleles.end()) alleles.push_back(a);
+            }
+            if (alleles.size() < 2 && longest <= 1) return fail("degenerate site");
+            std::sort(alleles.begin(), alleles.end(), [](uint32_t a, uint32_t b) { return (a == 0) != (b == 0) ? b == 0 : a < b; });   // empty allele last
+            slots.push_back(alleles);
+        }
+        for (size_t h = 0; h < walks.size(); h++) at[h] = stop[h];
+    }
+    std::vector<gb_dist_payload> dist(n_ids + 1, gb_dist_payload{0, 0, 0, 0xFFFF, 0});
+    std::vector<bool> placed(n_ids + 1, false);
+    uint64_t prefix = 0;
+    for (size_t s = 0; s < slots.size(); s++) {
+        uint32_t slot_min = 0xFFFFFFFFu;
+        for (uint32_t a : slots[s]) slot_min = std::min(slot_min, a ? len[a] : 0u);
+        for (size_t a = 0; a < slots[s].size(); a++) {
+            const uint32_t id = slots[s][a];
+            if (!id) continue;
+            if (placed[id] || prefix + slot_min > 0xFFFFFFFFull) return fail("a node occurs twice along the chain");
+            placed[id] = true;
+            dist[id].x_in = (uint32_t)prefix; dist[id].x_out = (uint32_t)(prefix + slot_min); dist[id].slot = (uint32_t)s;
+            dist[id].allele = slots[s].size() == 1 ? 0xFFFF : (uint16_t)a; dist[id].component = 0;
+        }
+        prefix += slot_min;
+    }
+    // ---- build ----
+    std::vector<uint32_t> flat; std::vector<uint64_t> path_off{0};
+    for (const auto& p : paths) { flat.insert(flat.end(), p.begin(), p.end()); path_off.push_back(flat.size()); }
+    if (node_seq.empty()) node_seq.push_back(0);
+    return gb_index_build((uint32_t)n_ids, node_seq.data(), node_off.data(), (uint32_t)paths.size(), flat.data(), path_off.data(), dist.data(), k, w, out);
+}
