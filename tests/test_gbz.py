@@ -193,3 +193,29 @@ def test_foreign_and_truncated_files_are_refused(tmp_path):
     for name in ("short.gbz", "other.gbz", "odd.gbz", "missing.gbz"):
         with pytest.raises(capi.GbError):
             capi.HostIndex.from_gbz(tmp_path / name)
+
+
+def test_minimizer_table_equals_the_reference_min_file():
+    """test/primers/y.min is the gbwtgraph minimizer index vg built for the same GBZ (k = 31, w = 50, 62 unique keys,
+    32-byte cells: key, encoded position, 16-byte payload; empty key 2^63 - 1).  gbwtgraph is absent from the reference
+    tree, so this file is the ground truth for find_minimizers' definition of a minimizer (hash order, canonical strand,
+    windows, position convention id << 11 | is_reverse << 10 | offset): the library's builder must select exactly the
+    same k-mers at exactly the same positions."""
+    raw = (GBZ.parent / "y.min").read_bytes()
+    W = struct.unpack("<%dQ" % (len(raw) // 8), raw[: len(raw) // 8 * 8])
+    assert W[0] & 0xFFFFFFFF == 0x31513151
+    k, w, n_keys, capacity = W[1], W[2], W[3], W[9]
+    assert (k, w, n_keys, capacity) == (31, 50, 62, 1024) and len(raw) == 8 * 10 + 32 * capacity + (len(raw) - 8 * 10 - 32 * capacity)
+    cells = {}
+    for c in range(capacity):
+        key, pos = W[10 + 4 * c], W[11 + 4 * c]
+        if key != 0x7FFFFFFFFFFFFFFF:
+            cells[key] = pos
+    assert len(cells) == n_keys
+    index = capi.HostIndex.from_gbz(GBZ, k=k, w=w)
+    table, hits = index.array("table"), index.array("hits")
+    mine = {int(c["key"]): sorted(int(hits[int(c["hit_off"]) + i]["pos"]) for i in range(int(c["hit_cnt"])))
+            for c in table if int(c["key"]) != 0xFFFFFFFFFFFFFFFF}
+    assert set(mine) == set(cells)
+    assert all(mine[key] == [pos] for key, pos in cells.items())
+    index.close()
