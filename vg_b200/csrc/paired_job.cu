@@ -137,6 +137,7 @@ extern "C" int gb_map_paired_job(gb_device* d, const gb_map_params* hp, gb_fragm
     if (n_reads % 2 != 0) { g_last_error = "paired mapping needs an even number of reads"; return GB_ERR_ARG; }
     if (training_window == 0) training_window = 2048;
     const uint32_t n_pairs = n_reads / 2;
+    if (n_pairs == 0) { if (n_mappings_used) *n_mappings_used = 0; if (n_edits_used) *n_edits_used = 0; return GB_OK; }     // nothing to map: the distribution stays as it is
     uint64_t nm = 0, ne = 0;
     int rc;
     std::vector<uint32_t> buffered;               // ambiguous_pair_buffer (pair indices)
