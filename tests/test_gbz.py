@@ -219,3 +219,41 @@ def test_minimizer_table_equals_the_reference_min_file():
     assert set(mine) == set(cells)
     assert all(mine[key] == [pos] for key, pos in cells.items())
     index.close()
+
+
+def test_distance_payload_equals_vgs_prefix_sums():
+    """The 16-byte payload of y.min's cells is vg's zipcode (zip_code.cpp:1943-2010: byte count, the zipcode's varints,
+    then decoder offsets).  For a node of the top-level chain it reads [1, component, chain component, connectivity]
+    (zip_code.cpp:57-100) + [prefix sum + 1, length + 1, is_reversed, chain component] (:105-111): the prefix sum is the
+    chain coordinate vg's distance index gives the node.  The payload derived from the GBZ's haplotypes must give every
+    such node the same coordinate (x_in), i.e. the two distance models agree on this graph."""
+    raw = (GBZ.parent / "y.min").read_bytes()
+    W = struct.unpack("<%dQ" % (len(raw) // 8), raw[: len(raw) // 8 * 8])
+    index = capi.HostIndex.from_gbz(GBZ, k=31, w=50)
+    dist, nodes = index.array("dist"), index.array("nodes")
+
+    def varints(bs):
+        out, v, s = [], 0, 0
+        for b in bs:
+            v |= (b & 0x7F) << s; s += 7
+            if not b & 0x80:
+                out.append(v); v = s = 0
+        return out
+
+    checked = set()
+    for c in range(1024):
+        key, pos, p0, p1 = W[10 + 4 * c: 14 + 4 * c]
+        if key == 0x7FFFFFFFFFFFFFFF:
+            continue
+        b = list(p0.to_bytes(8, "little") + p1.to_bytes(8, "little"))
+        zc = varints(b[1: 1 + b[0]])
+        if len(zc) != 8 or zc[0] != 1:
+            continue                              # nodes inside bubbles carry longer codes (or oversized ones, byte count 0)
+        nid = pos >> 11
+        prefix_sum, length = zc[4] - 1, zc[5] - 1
+        assert length == int(nodes[2 * nid]["len"])
+        assert prefix_sum == int(dist[nid]["x_in"]) and prefix_sum + length == int(dist[nid]["x_out"])
+        assert int(dist[nid]["allele"]) == 0xFFFF and zc[6] == 0
+        checked.add(nid)
+    assert len(checked) >= 20                     # most minimizers of this graph sit on backbone nodes
+    index.close()
