@@ -256,4 +256,39 @@ def test_distance_payload_equals_vgs_prefix_sums():
         assert int(dist[nid]["allele"]) == 0xFFFF and zc[6] == 0
         checked.add(nid)
     assert len(checked) >= 20                     # most minimizers of this graph sit on backbone nodes
+
+    # nodes inside sites: their zipcodes do not fit 15 bytes and live in y.zipcodes ("SPIZ", version, then per zipcode
+    # a varint byte count, the zipcode, its decoder; zip_code.cpp:2111-2170), the cell's payload being (0, index).
+    # A site is a snarl code after the root chain: [is_regular, offset in chain + 1, minimum length + 1, ...] (:128-147);
+    # the offset is the coordinate right after the site's start node, i.e. x_in of its alleles.
+    zraw = (GBZ.parent / "y.zipcodes").read_bytes()
+    assert zraw[:4] == b"SPIZ"
+    codes, i = [], 8
+
+    def varint_at(j):
+        v = sh = 0
+        while True:
+            c = zraw[j]; j += 1; v |= (c & 0x7F) << sh; sh += 7
+            if not c & 0x80:
+                return v, j
+
+    while i < len(zraw):
+        n, i = varint_at(i)
+        codes.append(varints(zraw[i: i + n])); i += n
+        dn, i = varint_at(i); i += dn                          # the decoder (is_chain, offset pairs): not needed here
+    in_sites = 0
+    for c in range(1024):
+        key, pos, p0, p1 = W[10 + 4 * c: 14 + 4 * c]
+        if key == 0x7FFFFFFFFFFFFFFF or (p0 & 0xFF) != 0:
+            continue
+        zc = codes[p1]; nid = pos >> 11
+        assert zc[:4] == [1, 0, 0, 0]
+        assert zc[5] - 1 == int(dist[nid]["x_in"]) and int(dist[nid]["allele"]) != 0xFFFF          # site offset = x_in of its alleles
+        if zc[4] == 1:                                                                              # regular snarl: one site
+            assert zc[6] - 1 == int(dist[nid]["x_out"]) - int(dist[nid]["x_in"])                    # minimum length across the site
+            assert zc[11] - 1 == int(nodes[2 * nid]["len"])                                         # the child chain is the allele node
+        else:                                                                                       # irregular snarl: adjacent sites, one slot each here
+            assert zc[6] - 1 >= int(dist[nid]["x_out"]) - int(dist[nid]["x_in"]) and zc[15] - 1 == int(nodes[2 * nid]["len"])
+        in_sites += 1
+    assert in_sites == 2
     index.close()
