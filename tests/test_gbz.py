@@ -122,7 +122,7 @@ def read_gbz(path):
         total += len(walk) + 1
         if s % 2 == 0:
             paths.append(walk)
-    return seqs, paths, {"sequences": sequences, "size": size, "total": total, "tags": gbz_tags + gbwt_tags}
+    return seqs, paths, {"sequences": sequences, "size": size, "total": total, "tags": gbz_tags + gbwt_tags, "records": records, "offset": offset}
 
 
 def test_independent_reader_agrees_with_the_file_header():
@@ -291,4 +291,27 @@ def test_distance_payload_equals_vgs_prefix_sums():
             assert zc[6] - 1 >= int(dist[nid]["x_out"]) - int(dist[nid]["x_in"]) and zc[15] - 1 == int(nodes[2 * nid]["len"])
         in_sites += 1
     assert in_sites == 2
+    index.close()
+
+
+def test_flat_gbwt_records_equal_the_files_gbwt_records():
+    """The flat index keeps its own GBWT (built from the haplotype paths, both orientations).  Decoded record by record
+    it must be the GBWT of the file: the same (successor, offset) edges and the same body — the sequence of successor
+    ranks in BWT order — for every oriented node.  gbwt is absent from the reference tree; this file is its output."""
+    seqs, paths, facts = read_gbz(GBZ)
+    index = capi.HostIndex.from_gbz(GBZ)
+    nodes, gbwt = index.array("nodes"), index.array("gbwt")
+    compared = 0
+    for comp in range(1, len(facts["records"])):
+        v = comp + facts["offset"]
+        edges, runs = facts["records"][comp]
+        rec = gbwt[int(nodes[v]["rec_off"]):]
+        n_edges, n_runs = int(rec[0]), int(rec[1])
+        mine_edges = [(int(rec[2 + 2 * e]), int(rec[3 + 2 * e])) for e in range(n_edges)]
+        mine_body = [w & 1023 for w in map(int, rec[2 + 2 * n_edges: 2 + 2 * n_edges + n_runs]) for _ in range(w >> 10)]
+        body = [r for r, ln in runs for _ in range(ln)]
+        assert mine_edges == edges and mine_body == body, v
+        assert int(nodes[v]["size"]) == len(body)
+        compared += 1
+    assert compared == 132
     index.close()
