@@ -772,3 +772,17 @@ extern "C" void oracle_cluster_positions(const gb_flat_index* ix, uint32_t n, co
         }
     for (uint32_t i = 0; i < n; i++) { read_label[i] = (uint32_t)reads.find(i); fragment_label[i] = (uint32_t)frags.find(i); }
 }
+
+// minimizer_regions of one sequence (test entry): up to `cap` minimizers as (key, forward offset, is_reverse, agglomeration start,
+// agglomeration length); returns their number.
+extern "C" uint32_t oracle_minimizer_regions(const uint8_t* seq, uint32_t len, uint32_t k, uint32_t w, uint32_t cap,
+                                             uint64_t* key, uint32_t* fwd_offset, uint8_t* is_reverse, uint32_t* agg_start, uint32_t* agg_len) {
+    const std::vector<oracle::Minimizer> ms = oracle::minimizer_regions(std::string((const char*)seq, len), k, w);
+    uint32_t n = 0;
+    for (const oracle::Minimizer& m : ms) {
+        if (n >= cap) break;
+        key[n] = m.key; fwd_offset[n] = (uint32_t)m.forward_offset(); is_reverse[n] = m.is_reverse ? 1 : 0;
+        agg_start[n] = (uint32_t)m.agglomeration_start; agg_len[n] = (uint32_t)m.agglomeration_length; n++;
+    }
+    return (uint32_t)ms.size();
+}

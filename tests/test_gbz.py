@@ -315,3 +315,37 @@ def test_flat_gbwt_records_equal_the_files_gbwt_records():
         compared += 1
     assert compared == 132
     index.close()
+
+
+def test_oracle_minimizer_regions_find_exactly_the_keys_of_the_reference_min_file():
+    """The oracle's own (brute force over windows) definition of a minimizer, run over the three haplotype sequences of
+    the GBZ with k = 31, w = 50, must select the k-mers of y.min and no others, and each at the haplotype position the
+    file's graph position corresponds to."""
+    import ctypes as C
+    seqs, paths, _ = read_gbz(GBZ)
+    raw = (GBZ.parent / "y.min").read_bytes()
+    W = struct.unpack("<%dQ" % (len(raw) // 8), raw[: len(raw) // 8 * 8])
+    file_cells = {W[10 + 4 * c]: W[11 + 4 * c] for c in range(1024) if W[10 + 4 * c] != 0x7FFFFFFFFFFFFFFF}
+    lib = H.oracle_lib()
+    lib.oracle_minimizer_regions.argtypes = [C.c_void_p, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32] + [C.c_void_p] * 5
+    lib.oracle_minimizer_regions.restype = C.c_uint32
+    found = {}
+    for p in paths:
+        hap = "".join(seqs[(v >> 1) - 1] for v in p)
+        starts = np.cumsum([0] + [len(seqs[(v >> 1) - 1]) for v in p])
+        s = np.frombuffer(hap.encode(), dtype=np.uint8).copy()
+        cap = 4096
+        key = np.zeros(cap, dtype=np.uint64); fwd = np.zeros(cap, dtype=np.uint32); rev = np.zeros(cap, dtype=np.uint8)
+        a0 = np.zeros(cap, dtype=np.uint32); a1 = np.zeros(cap, dtype=np.uint32)
+        n = lib.oracle_minimizer_regions(capi.ptr(s), len(s), 31, 50, cap, capi.ptr(key), capi.ptr(fwd), capi.ptr(rev), capi.ptr(a0), capi.ptr(a1))
+        assert 0 < n <= cap
+        for i in range(n):
+            # graph position of the minimizer: first base of the k-mer on its strand (forward: offset; reverse: last base, other strand)
+            at = int(fwd[i]) + (30 if rev[i] else 0)
+            j = int(np.searchsorted(starts, at, side="right") - 1)
+            nid, off = p[j] >> 1, at - int(starts[j])
+            if rev[i]:
+                off = len(seqs[nid - 1]) - 1 - off
+            found.setdefault(int(key[i]), set()).add((nid << 11) | (int(rev[i]) << 10) | off)
+    assert set(found) == set(file_cells)
+    assert all(found[k] == {pos} for k, pos in file_cells.items())
