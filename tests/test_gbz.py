@@ -349,3 +349,36 @@ def test_oracle_minimizer_regions_find_exactly_the_keys_of_the_reference_min_fil
             found.setdefault(int(key[i]), set()).add((nid << 11) | (int(rev[i]) << 10) | off)
     assert set(found) == set(file_cells)
     assert all(found[k] == {pos} for k, pos in file_cells.items())
+
+
+@pytest.mark.gpu
+@pytest.mark.xfail(reason="written after the round's GPU budget was spent: never run on a GPU yet (scripts/gpu_check_gbz.py is the same check); "
+                          "drop this marker once it has passed on a B200", strict=False)
+def test_cuda_path_equals_oracle_on_the_reference_gbz_graph():
+    """Single-end and paired mapping (rescue on) on the graph vg built: CUDA path vs oracle."""
+    seqs, paths, _ = read_gbz(GBZ)
+    index = capi.HostIndex.from_gbz(GBZ)
+    haps = ["".join(seqs[(v >> 1) - 1] for v in p) for p in paths]
+    rng = np.random.default_rng(11)
+    reads = []
+    for _ in range(300):
+        h = haps[int(rng.integers(0, len(haps)))]
+        s = int(rng.integers(0, len(h) - 150))
+        r = np.frombuffer(h[s:s + 150].encode(), dtype=np.uint8).copy()
+        m = rng.random(150) < 0.02
+        r[m] = synth.BASES[rng.integers(0, 4, size=int(m.sum()))]
+        reads.append(synth.revcomp_bytes(r[None, :])[0] if rng.random() < 0.5 else r)
+    reads = np.stack(reads); quals = np.full(reads.shape, 30, dtype=np.uint8)
+    dev = capi.Device(index)
+    assert not H.compare_alignments(H.gpu_map(dev, reads, quals), H.oracle_map(index, reads, quals, threads=8), len(reads))
+    pairs = []
+    for _ in range(150):
+        h = haps[int(rng.integers(0, len(haps)))]
+        frag = int(np.clip(rng.normal(400, 50), 160, len(h) - 1)); s = int(rng.integers(0, len(h) - frag))
+        a = np.frombuffer(h[s:s + 150].encode(), dtype=np.uint8).copy()
+        b = synth.revcomp_bytes(np.frombuffer(h[s + frag - 150:s + frag].encode(), dtype=np.uint8).copy()[None, :])[0]
+        pairs += [a, b] if rng.random() < 0.5 else [b, a]
+    pairs = np.stack(pairs); pq = np.full(pairs.shape, 30, dtype=np.uint8)
+    p = H.paired_params(); p.max_rescue_attempts = 15
+    assert not H.compare_alignments(H.gpu_map(dev, pairs, pq, p, paired=True), H.oracle_map_paired(index, pairs, pq, p, threads=8), len(pairs))
+    dev.close(); index.close()
