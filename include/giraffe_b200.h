@@ -371,21 +371,22 @@ int gb_map_paired_job(gb_device* dev, const gb_map_params* p, gb_fragment_distri
  *   gb_emit_json  one protobuf-JSON Alignment per line with vg.proto's field names, as `vg view -aj`
  *                 prints them (64-bit integers as strings, default values omitted, quality base64)
  * names / name_off may be NULL (reads are then called read<i>); records may be any subset / order
- * (read_id selects the read). */
-int gb_emit_gaf(const gb_flat_index* ix, uint32_t n, const gb_alignment* aln, const gb_mapping* mappings, const uint32_t* edits,
-                const uint8_t* reads, const uint8_t* quals, const uint64_t* read_off, const uint8_t* names, const uint64_t* name_off,
-                char* out, uint64_t out_cap, uint64_t* out_used);
-int gb_emit_json(const gb_flat_index* ix, uint32_t n, const gb_alignment* aln, const gb_mapping* mappings, const uint32_t* edits,
-                 const uint8_t* reads, const uint8_t* quals, const uint64_t* read_off, const uint8_t* names, const uint64_t* name_off,
-                 char* out, uint64_t out_cap, uint64_t* out_used);
+ * (read_id selects the read among n_reads).  Records are validated against mapping_pool_len / edit_pool_len / n_reads,
+ * the graph and the read length before anything is written: GB_ERR_ARG for a record that points outside them. */
+int gb_emit_gaf(const gb_flat_index* ix, uint32_t n, const gb_alignment* aln, const gb_mapping* mappings, uint64_t mapping_pool_len,
+                const uint32_t* edits, uint64_t edit_pool_len, uint32_t n_reads, const uint8_t* reads, const uint8_t* quals, const uint64_t* read_off,
+                const uint8_t* names, const uint64_t* name_off, char* out, uint64_t out_cap, uint64_t* out_used);
+int gb_emit_json(const gb_flat_index* ix, uint32_t n, const gb_alignment* aln, const gb_mapping* mappings, uint64_t mapping_pool_len,
+                 const uint32_t* edits, uint64_t edit_pool_len, uint32_t n_reads, const uint8_t* reads, const uint8_t* quals, const uint64_t* read_off,
+                 const uint8_t* names, const uint64_t* name_off, char* out, uint64_t out_cap, uint64_t* out_used);
 /* GAM: the same records as vg.proto Alignment messages in vg::io's type-tagged group framing (uncompressed; vg reads
  * plain, gzip and BGZF streams).  libvgio is absent from the reference tree: field numbers and framing are read off GAM
  * files written by vg itself (reference test data, tests/golden/gam/): sequence 1, path 2 {mapping 2 {position 1
  * {node_id 1, offset 2, is_reverse 4}, edit 2 {from_length 1, to_length 2, sequence 3}, rank 5}}, name 3, quality 4,
  * mapping_quality 5, score 6, fragment_prev 11 / fragment_next 12, identity 16, annotation 100 (Struct). */
-int gb_emit_gam(const gb_flat_index* ix, uint32_t n, const gb_alignment* aln, const gb_mapping* mappings, const uint32_t* edits,
-                const uint8_t* reads, const uint8_t* quals, const uint64_t* read_off, const uint8_t* names, const uint64_t* name_off,
-                char* out, uint64_t out_cap, uint64_t* out_used);
+int gb_emit_gam(const gb_flat_index* ix, uint32_t n, const gb_alignment* aln, const gb_mapping* mappings, uint64_t mapping_pool_len,
+                const uint32_t* edits, uint64_t edit_pool_len, uint32_t n_reads, const uint8_t* reads, const uint8_t* quals, const uint64_t* read_off,
+                const uint8_t* names, const uint64_t* name_off, char* out, uint64_t out_cap, uint64_t* out_used);
 
 /* Device-pointer variant of both (paired != 0 selects map_paired): every pointer is a DEVICE
  * address (inputs already resident in HBM, outputs stay in HBM); all reads are at most

@@ -30,7 +30,7 @@ lib.gb_index_free.argtypes = [vp]
 lib.gb_index_save.argtypes = [C.POINTER(capi.FlatIndex), C.c_char_p]
 lib.gb_index_load.argtypes = [C.c_char_p, C.POINTER(vp)]
 for fn in (lib.gb_emit_gaf, lib.gb_emit_json, lib.gb_emit_gam):
-    fn.argtypes = [C.POINTER(capi.FlatIndex), u32, vp, vp, vp, vp, vp, vp, vp, vp, vp, u64, vp]
+    fn.argtypes = [C.POINTER(capi.FlatIndex), u32, vp, vp, u64, vp, u64, u32, vp, vp, vp, vp, vp, vp, u64, vp]
 
 g = synth.make_variant_graph(length=30000, n_snp=48, n_ins=6, n_del=6, n_haps=4, seed=3)
 node_off = np.zeros(len(g.node_seqs) + 1, dtype=np.uint64); node_off[1:] = np.cumsum([len(s) for s in g.node_seqs])
@@ -102,12 +102,25 @@ for fn in (lib.gb_emit_gaf, lib.gb_emit_json, lib.gb_emit_gam):
         need = None
         for cap in (1 << 22, 0, 1, 17, 1000, 40000):
             out = np.zeros(max(cap, 1), dtype=np.uint8); used = u64()
-            rc = fn(C.byref(view), len(aln), capi.ptr(aln), capi.ptr(res[1]), capi.ptr(res[2]), capi.ptr(rbuf), capi.ptr(quals) if quals is not None else None,
-                    capi.ptr(read_off), None, None, capi.ptr(out), cap, C.byref(used))
+            rc = fn(C.byref(view), len(aln), capi.ptr(aln), capi.ptr(res[1]), len(res[1]), capi.ptr(res[2]), len(res[2]), rs.n, capi.ptr(rbuf),
+                    capi.ptr(quals) if quals is not None else None, capi.ptr(read_off), None, None, capi.ptr(out), cap, C.byref(used))
             if cap == 1 << 22:
                 assert rc == 0; need = used.value
             else:
                 assert (rc == 0) == (cap >= need), (cap, need, rc)
                 assert used.value <= cap
+# damaged records: random bytes overwritten in the 32-byte headers; every emitter must refuse or write, never fault
+rng = np.random.default_rng(5); refused = 0
+out = np.zeros(1 << 22, dtype=np.uint8)
+for t in range(300):
+    bad = aln.copy(); raw_view = bad.view(np.uint8).reshape(-1)
+    for _ in range(int(rng.integers(1, 5))):
+        raw_view[int(rng.integers(0, len(raw_view)))] = int(rng.integers(0, 256))
+    for fn in (lib.gb_emit_gaf, lib.gb_emit_json, lib.gb_emit_gam):
+        used = u64()
+        rc = fn(C.byref(view), len(bad), capi.ptr(bad), capi.ptr(res[1]), len(res[1]), capi.ptr(res[2]), len(res[2]), rs.n, capi.ptr(rbuf), capi.ptr(qbuf),
+                capi.ptr(read_off), None, None, capi.ptr(out), len(out), C.byref(used))
+        refused += rc != 0
+print("damaged record batches refused:", refused, "of 900 emitter calls")
 lib.gb_index_free(h)
 print("host sanitizer pass: no AddressSanitizer / UBSan report")

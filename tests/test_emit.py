@@ -183,6 +183,32 @@ def test_emit_reports_a_short_buffer():
     g, index, rs, res = _records(paired=False)
     rbuf, qbuf, read_off = H.pack_reads(rs.reads, rs.quals)
     out = np.zeros(64, dtype=np.uint8); used = C.c_uint64()
-    rc = capi.load_library().gb_emit_gaf(C.byref(index.view), 10, capi.ptr(res[0]), capi.ptr(res[1]), capi.ptr(res[2]), capi.ptr(rbuf), capi.ptr(qbuf),
-                                         capi.ptr(read_off), None, None, capi.ptr(out), 64, C.byref(used))
-    assert rc == capi.GB_ERR_CAPACITY
+    lib = capi.load_library()
+    args = lambda aln, n_maps, n_edits, n_reads: (C.byref(index.view), len(aln), capi.ptr(aln), capi.ptr(res[1]), n_maps, capi.ptr(res[2]), n_edits, n_reads,
+                                                  capi.ptr(rbuf), capi.ptr(qbuf), capi.ptr(read_off), None, None, capi.ptr(out), 64, C.byref(used))
+    ten = np.ascontiguousarray(res[0][:10])
+    assert lib.gb_emit_gaf(*args(ten, len(res[1]), len(res[2]), rs.n)) == capi.GB_ERR_CAPACITY
+
+
+def test_emit_refuses_records_that_point_outside_their_pools():
+    import ctypes as C
+    g, index, rs, res = _records(paired=False)
+    rbuf, qbuf, read_off = H.pack_reads(rs.reads, rs.quals)
+    lib = capi.load_library()
+    out = np.zeros(1 << 20, dtype=np.uint8); used = C.c_uint64()
+
+    def emit(fn, aln, n_maps=len(res[1]), n_edits=len(res[2]), n_reads=rs.n):
+        aln = np.ascontiguousarray(aln)
+        return fn(C.byref(index.view), len(aln), capi.ptr(aln), capi.ptr(res[1]), n_maps, capi.ptr(res[2]), n_edits, n_reads, capi.ptr(rbuf), capi.ptr(qbuf),
+                  capi.ptr(read_off), None, None, capi.ptr(out), len(out), C.byref(used))
+
+    mapped = res[0][(res[0]["flags"] & 1) != 0][:20]
+    for fn in (lib.gb_emit_gaf, lib.gb_emit_json, lib.gb_emit_gam):
+        assert emit(fn, mapped) == capi.GB_OK
+        assert emit(fn, mapped, n_maps=int(mapped["mapping_off"].max())) == capi.GB_ERR_ARG                  # mapping pool shorter than a record needs
+        assert emit(fn, mapped, n_edits=int(mapped["edit_off"].max())) == capi.GB_ERR_ARG
+        assert emit(fn, mapped, n_reads=int(mapped["read_id"].max())) == capi.GB_ERR_ARG                     # read id outside the batch
+        bad = mapped.copy(); bad[3]["n_edits"] += 1                                                          # edits no longer add up to the read
+        assert emit(fn, bad) == capi.GB_ERR_ARG
+        bad = mapped.copy(); bad[5]["mapping_off"] = bad[6]["mapping_off"]                                   # another record's mappings
+        assert emit(fn, bad) == capi.GB_ERR_ARG

@@ -171,7 +171,7 @@ def load_library() -> C.CDLL:
     lib.gb_map_paired_job.argtypes = [vp, C.POINTER(MapParams), vp, u32, u32, vp, vp, vp, vp, vp, u64, vp, u64, vp, vp, vp, vp]
     lib.gb_map_paired_job.restype = C.c_int
     for fn in (lib.gb_emit_gaf, lib.gb_emit_json, lib.gb_emit_gam):
-        fn.argtypes = [C.POINTER(FlatIndex), u32, vp, vp, vp, vp, vp, vp, vp, vp, vp, u64, vp]
+        fn.argtypes = [C.POINTER(FlatIndex), u32, vp, vp, u64, vp, u64, u32, vp, vp, vp, vp, vp, vp, u64, vp]
         fn.restype = C.c_int
     lib.gb_last_kernel_ms.argtypes = [vp]
     lib.gb_last_kernel_ms.restype = C.c_float
@@ -309,8 +309,9 @@ def emit_text(kind, flat_index, aln, maps, edits, rbuf, qbuf, read_off, names=No
     cap = 4096 + len(aln) * 4096
     out = np.zeros(cap, dtype=np.uint8)
     used = C.c_uint64()
-    rc = fn(C.byref(flat_index), len(aln), ptr(aln), ptr(maps), ptr(edits), ptr(rbuf), ptr(qbuf) if qbuf is not None else None, ptr(read_off),
-            ptr(nbuf) if nbuf is not None else None, ptr(noff) if noff is not None else None, ptr(out), cap, C.byref(used))
+    rc = fn(C.byref(flat_index), len(aln), ptr(aln), ptr(maps), len(maps), ptr(edits), len(edits), len(read_off) - 1, ptr(rbuf),
+            ptr(qbuf) if qbuf is not None else None, ptr(read_off), ptr(nbuf) if nbuf is not None else None, ptr(noff) if noff is not None else None,
+            ptr(out), cap, C.byref(used))
     if rc != GB_OK:
         raise GbError(rc, "gb_emit_" + kind)
     data = out[: used.value].tobytes()

@@ -60,12 +60,41 @@ void json_string(Out& o, const std::string& s) {
     o.ch('"');
 }
 
+// Every record must stay inside what the caller handed over: its read, its slice of the two pools, the graph, and the
+// read length its edits consume.  The emitters index with these fields, so a damaged record is refused here.
+bool records_valid(const gb_flat_index* ix, uint32_t n, const gb_alignment* aln, const gb_mapping* mappings, uint64_t mapping_pool_len,
+                   const uint32_t* edits, uint64_t edit_pool_len, uint32_t n_reads, const uint64_t* read_off) {
+    for (uint32_t x = 0; x < n; x++) {
+        const gb_alignment& a = aln[x];
+        if (a.read_id >= n_reads || read_off[a.read_id + 1] < read_off[a.read_id]) return false;
+        if ((a.flags & GB_ALN_PAIRED) && (a.read_id ^ 1u) >= n_reads) return false;
+        if (!(a.flags & GB_ALN_MAPPED) || a.n_mappings == 0) continue;
+        if (!mappings || !edits || (uint64_t)a.mapping_off + a.n_mappings > mapping_pool_len || (uint64_t)a.edit_off + a.n_edits > edit_pool_len) return false;
+        const uint64_t L = read_off[a.read_id + 1] - read_off[a.read_id];
+        uint64_t ei = 0, q = 0;
+        for (uint32_t i = 0; i < a.n_mappings; i++) {
+            const gb_mapping& m = mappings[a.mapping_off + i];
+            if (m.node >= ix->n_nodes || ei + m.n_edits > a.n_edits) return false;
+            uint64_t off = m.offset;
+            for (uint32_t j = 0; j < m.n_edits; j++, ei++) {
+                const uint32_t wd = edits[a.edit_off + ei], op = wd & 3u, len = op == GB_EDIT_SUB ? 1u : wd >> 4;
+                if (op != GB_EDIT_DEL) q += len;
+                if (op != GB_EDIT_INS) off += len;
+            }
+            if (off > ix->nodes[m.node].len || q > L) return false;
+        }
+        if (ei != a.n_edits || q != L) return false;
+    }
+    return true;
+}
+
 } // namespace
 
-extern "C" int gb_emit_gaf(const gb_flat_index* ix, uint32_t n, const gb_alignment* aln, const gb_mapping* mappings, const uint32_t* edits,
-                           const uint8_t* reads, const uint8_t* quals, const uint64_t* read_off, const uint8_t* names, const uint64_t* name_off,
-                           char* out, uint64_t out_cap, uint64_t* out_used) {
+extern "C" int gb_emit_gaf(const gb_flat_index* ix, uint32_t n, const gb_alignment* aln, const gb_mapping* mappings, uint64_t mapping_pool_len,
+                           const uint32_t* edits, uint64_t edit_pool_len, uint32_t n_reads, const uint8_t* reads, const uint8_t* quals, const uint64_t* read_off,
+                           const uint8_t* names, const uint64_t* name_off, char* out, uint64_t out_cap, uint64_t* out_used) {
     if (!ix || !aln || !reads || !read_off || !out || !out_used) return GB_ERR_ARG;
+    if (!records_valid(ix, n, aln, mappings, mapping_pool_len, edits, edit_pool_len, n_reads, read_off)) return GB_ERR_ARG;
     Out o{out, out_cap, 0, false};
     for (uint32_t x = 0; x < n; x++) {
         const gb_alignment& a = aln[x];
@@ -126,10 +155,11 @@ extern "C" int gb_emit_gaf(const gb_flat_index* ix, uint32_t n, const gb_alignme
     return o.overflow ? GB_ERR_CAPACITY : GB_OK;
 }
 
-extern "C" int gb_emit_json(const gb_flat_index* ix, uint32_t n, const gb_alignment* aln, const gb_mapping* mappings, const uint32_t* edits,
-                            const uint8_t* reads, const uint8_t* quals, const uint64_t* read_off, const uint8_t* names, const uint64_t* name_off,
-                            char* out, uint64_t out_cap, uint64_t* out_used) {
+extern "C" int gb_emit_json(const gb_flat_index* ix, uint32_t n, const gb_alignment* aln, const gb_mapping* mappings, uint64_t mapping_pool_len,
+                            const uint32_t* edits, uint64_t edit_pool_len, uint32_t n_reads, const uint8_t* reads, const uint8_t* quals, const uint64_t* read_off,
+                            const uint8_t* names, const uint64_t* name_off, char* out, uint64_t out_cap, uint64_t* out_used) {
     if (!ix || !aln || !reads || !read_off || !out || !out_used) return GB_ERR_ARG;
+    if (!records_valid(ix, n, aln, mappings, mapping_pool_len, edits, edit_pool_len, n_reads, read_off)) return GB_ERR_ARG;
     Out o{out, out_cap, 0, false};
     for (uint32_t x = 0; x < n; x++) {
         const gb_alignment& a = aln[x];
@@ -204,10 +234,11 @@ void pb_annotation(std::string& st, const char* key, const std::string& value_ms
 
 } // namespace
 
-extern "C" int gb_emit_gam(const gb_flat_index* ix, uint32_t n, const gb_alignment* aln, const gb_mapping* mappings, const uint32_t* edits,
-                           const uint8_t* reads, const uint8_t* quals, const uint64_t* read_off, const uint8_t* names, const uint64_t* name_off,
-                           char* out, uint64_t out_cap, uint64_t* out_used) {
+extern "C" int gb_emit_gam(const gb_flat_index* ix, uint32_t n, const gb_alignment* aln, const gb_mapping* mappings, uint64_t mapping_pool_len,
+                           const uint32_t* edits, uint64_t edit_pool_len, uint32_t n_reads, const uint8_t* reads, const uint8_t* quals, const uint64_t* read_off,
+                           const uint8_t* names, const uint64_t* name_off, char* out, uint64_t out_cap, uint64_t* out_used) {
     if (!ix || !aln || !reads || !read_off || !out || !out_used) return GB_ERR_ARG;
+    if (!records_valid(ix, n, aln, mappings, mapping_pool_len, edits, edit_pool_len, n_reads, read_off)) return GB_ERR_ARG;
     Out o{out, out_cap, 0, false};
     const uint32_t GROUP = 1000;                 // messages per group
     for (uint32_t g0 = 0; g0 < n; g0 += GROUP) {
