@@ -218,7 +218,8 @@ extern "C" int gb_emit_json(const gb_flat_index* ix, uint32_t n, const gb_alignm
 //             100 annotation (google.protobuf.Struct: 1 fields{1 key, 2 Value{2 number_value, 4 bool_value}})
 //   Path      2 mapping;   Mapping 1 position, 2 edit, 5 rank;   Position 1 node_id, 2 offset, 4 is_reverse;
 //   Edit      1 from_length, 2 to_length, 3 sequence.   proto3: zero / false / empty fields are not written.
-// The stream is written uncompressed (vg::io reads plain, gzip and BGZF streams alike).
+// The stream is written uncompressed: vg::io's BlockedGzipInputStream reads uncompressed, gzip and BGZF data alike
+// (unittest/blocked_gzip_input_stream.cpp:136, :364, :400).
 namespace {
 
 void pb_varint(std::string& s, uint64_t v) { while (v >= 0x80) { s.push_back((char)(v | 0x80)); v >>= 7; } s.push_back((char)v); }
