@@ -1,7 +1,7 @@
 """Secondary workloads of BASELINE.json (not the bench line): config 4 (branchy graph, 150 bp SE)
 and config 5 (config-2 graph, 250 bp SE with 5 % errors: every read takes the tail-DP path).
 Prints kernel-time throughput, stage times, the CPU oracle rate on the same reads and a parity count.
-usage: python scripts/bench_configs.py [n_reads]"""
+usage: python tests/tools/bench_configs.py [n_reads]"""
 import os, sys, time, json
 sys.path.insert(0, "."); sys.path.insert(0, "tests")
 import numpy as np

@@ -1,6 +1,6 @@
 """Secondary workload: config-2 pairs with a share of mates too noisy to seed, mate rescue on
 (vg giraffe default --rescue-attempts 15).  Kernel-time throughput, CPU oracle rate, parity count.
-usage: python scripts/bench_rescue.py [n_pairs] [wrecked_every]"""
+usage: python tests/tools/bench_rescue.py [n_pairs] [wrecked_every]"""
 import os, sys, time, json
 sys.path.insert(0, "."); sys.path.insert(0, "tests")
 import numpy as np

@@ -1,6 +1,6 @@
 """Throughput of the DP stage seams on rescue-sized problems: gb_sw_batch (full local DP over a DAG)
 and the CPU oracle on the same problems.  Reports cell updates per second (CUPS).
-usage: python scripts/bench_seams.py [n_problems]"""
+usage: python tests/tools/bench_seams.py [n_problems]"""
 import sys, time, json
 sys.path.insert(0, "."); sys.path.insert(0, "tests")
 import numpy as np

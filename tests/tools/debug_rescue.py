@@ -1,7 +1,8 @@
 """Mate-rescue parity triage: status histogram and the first differing pairs (GPU vs oracle)."""
 import sys, os
 import numpy as np
-sys.path.insert(0, os.path.join(os.path.dirname(__file__), "..", "tests"))
+sys.path.insert(0, os.path.join(os.path.dirname(__file__), "..", ".."))
+sys.path.insert(0, os.path.join(os.path.dirname(__file__), ".."))
 import helpers as H
 import test_map_paired_parity as T
 from vg_b200 import capi

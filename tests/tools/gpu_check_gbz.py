@@ -1,10 +1,10 @@
 """GPU parity on a graph vg built: the reference's test GBZ (tests/golden/gbz/y.giraffe.gbz) read by gb_index_from_gbz,
 single-end and paired reads drawn from its three haplotypes (with errors), CUDA path vs oracle.  Not part of the pytest
 suite yet (written when no GPU time was left in round 1): run it first in round 2, then turn it into a test.
-usage: python scripts/gpu_check_gbz.py"""
+usage: python tests/tools/gpu_check_gbz.py"""
 import sys
 from pathlib import Path
-ROOT = Path(__file__).resolve().parents[1]
+ROOT = Path(__file__).resolve().parents[2]
 sys.path.insert(0, str(ROOT)); sys.path.insert(0, str(ROOT / "tests"))
 import numpy as np
 import helpers as H

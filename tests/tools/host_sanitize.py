@@ -1,11 +1,11 @@
 """AddressSanitizer / UBSan pass over the library's host-only C++ (emit.cpp, index_builder.cpp, gbz_reader.cpp): builds the files
 with g++ -fsanitize=address,undefined into gpurun_out/libhost_asan.so and drives index build / save / load (including
 truncated and corrupted files) and the three emitters (including output buffers that are too small) through ctypes.
-usage: python scripts/host_sanitize.py        (re-executes itself under LD_PRELOAD=libasan.so)"""
+usage: python tests/tools/host_sanitize.py        (re-executes itself under LD_PRELOAD=libasan.so)"""
 import ctypes as C, os, subprocess, sys, tempfile
 from pathlib import Path
 
-ROOT = Path(__file__).resolve().parents[1]
+ROOT = Path(__file__).resolve().parents[2]
 LIB = ROOT / "gpurun_out" / "libhost_asan.so"
 
 if os.environ.get("HOST_SANITIZE_CHILD") != "1":
