@@ -388,6 +388,12 @@ int gb_emit_gam(const gb_flat_index* ix, uint32_t n, const gb_alignment* aln, co
                 const uint32_t* edits, uint64_t edit_pool_len, uint32_t n_reads, const uint8_t* reads, const uint8_t* quals, const uint64_t* read_off,
                 const uint8_t* names, const uint64_t* name_off, char* out, uint64_t out_cap, uint64_t* out_used);
 
+/* BGZF, the blocked gzip container vg::io's emitters write GAM in (giraffe_main.cpp:2209-2226; libvgio's
+ * BlockedGzipOutputStream over htslib bgzf): `in` is cut into blocks of at most 0xff00 bytes, each a complete gzip
+ * member carrying the 'BC' extra subfield (block size - 1), followed by the 28-byte empty EOF block.  level 0-9 (zlib).
+ * GB_ERR_CAPACITY when `out` is too small (in_bytes + 128 * (in_bytes / 0xff00 + 2) always suffices). */
+int gb_bgzf_compress(const void* in, uint64_t in_bytes, int level, void* out, uint64_t out_cap, uint64_t* out_used);
+
 /* Device-pointer variant of both (paired != 0 selects map_paired): every pointer is a DEVICE
  * address (inputs already resident in HBM, outputs stay in HBM); all reads are at most
  * max_read_len long; d_totals[2] (device) receives {mappings used, edits used}.  The call only
@@ -397,6 +403,35 @@ int gb_map_batch_device(gb_device* dev, const gb_map_params* p, int paired, uint
                         const uint8_t* d_reads, const uint8_t* d_quals, const uint64_t* d_read_off, uint32_t max_read_len,
                         gb_alignment* d_aln, gb_mapping* d_mappings, uint64_t mapping_pool_cap, uint32_t* d_edits, uint64_t edit_pool_cap,
                         uint8_t* d_status, uint64_t* d_totals);
+
+/* Intermediate pools (minimizer, seed, work-item records between the kernels) are sized from per-read averages
+ * (48 minimizers, 64 seeds, 3 kept clusters per read) times a scale that starts at 1 (GIRAFFE_B200_POOL_SCALE overrides).
+ * gb_map_batch / gb_map_paired_batch / gb_map_paired_job notice a chunk that ran out, double the scale and redo that
+ * chunk, so the limit never shows in their results.  gb_map_batch_device only enqueues work: after it, this call
+ * synchronises and reports whether the batch overflowed (its reads then carry GB_ITEM_OUT_FULL); if so the scale has
+ * been doubled and the caller submits the batch again. */
+int gb_device_pool_overflow(gb_device* dev, int* overflowed);
+
+/* ---- stage-level dump for parity tests -------------------------------------------------------------------------
+ * Runs only the seeding stage (find_minimizers / sort_minimizers_by_score / find_seeds / cluster_seeds / score_cluster /
+ * cluster selection / extend_seed_group packing; minimizer_mapper.cpp:3918-4517, :4738-4850, :655-832, :1568-1883,
+ * snarl_seed_clusterer.cpp:28-145) on host buffers and returns what the seeding kernels hand to the extension kernel,
+ * per read, so tests can compare every intermediate with the oracle's.  paired != 0: reads are interleaved mates and
+ * mate 2 is seeded on its reverse complement, as map_paired does (:1503-1506).
+ *   minimizers  in score order (after the tie shuffle); seeds in (minimizer, hit) order, each with the index of its
+ *   read cluster; clusters in order of their first seed; items = kept clusters in processing order, each with its
+ *   (node, read_offset - node_offset) seeds in item_seeds.
+ * Offsets in gb_stage_read index the flat output arrays; GB_ERR_CAPACITY when one is too small. */
+typedef struct gb_stage_minimizer { uint64_t hash; double score; uint32_t fwd_offset, agg_start, agg_len, is_reverse, hits, reserved; } gb_stage_minimizer;
+typedef struct gb_stage_seed { uint32_t node, offset, source, cluster; } gb_stage_seed;
+typedef struct gb_stage_cluster { double score, coverage; uint32_t first_seed, n_seeds, fragment, kept_rank; } gb_stage_cluster;   /* kept_rank 0xffffffff: not kept */
+typedef struct gb_stage_item { uint32_t cluster, fragment, seed_off, seed_cnt; } gb_stage_item;
+typedef struct gb_stage_read { uint32_t min_off, min_cnt, seed_off, seed_cnt, cluster_off, cluster_cnt, item_off, item_cnt, status, reserved[3]; } gb_stage_read;
+int gb_debug_seed_stage(gb_device* dev, const gb_map_params* p, int paired,
+                        uint32_t n_reads, const uint8_t* reads, const uint8_t* quals, const uint64_t* read_off,
+                        gb_stage_read* out_reads, gb_stage_minimizer* mins, uint64_t min_cap, gb_stage_seed* seeds, uint64_t seed_cap,
+                        gb_stage_cluster* clusters, uint64_t cluster_cap, gb_stage_item* items, uint64_t item_cap,
+                        gb_seed* item_seeds, uint64_t item_seed_cap);
 
 /* Run this handle's work on the caller's CUDA stream (cudaStream_t; NULL = the handle's own). */
 int gb_device_set_stream(gb_device* dev, void* cuda_stream);

@@ -526,6 +526,8 @@ double faster_cap(const std::vector<Minimizer>& minimizers, std::vector<size_t>&
 // ---------------------------------------------------------------------------------------
 // map_from_extensions, minimizer_mapper.cpp:608-1284 (max_multimaps 1, find_supplementaries off)
 // ---------------------------------------------------------------------------------------
+thread_local StageTrace* g_stage_trace = nullptr;
+
 Alignment map_from_extensions(const gb_flat_index* ix, const gb_scores& scores, const gb_map_params& P,
                               const std::string& sequence, const std::string& quality, MapCounters* counters) {
     Graph g(ix);
@@ -552,6 +554,7 @@ Alignment map_from_extensions(const gb_flat_index* ix, const gb_scores& scores, 
     double cluster_score_cutoff = best_cluster_score - P.cluster_score_threshold;
     if (cluster_score_cutoff - P.pad_cluster_score_threshold < second_best_cluster_score)
         cluster_score_cutoff = std::min(cluster_score_cutoff, second_best_cluster_score);
+    if (g_stage_trace) { auto& t = g_stage_trace->reads[0]; t.minimizers = minimizers; t.seeds = seeds; t.clusters = clusters; }
 
     std::vector<std::vector<GaplessExtension>> cluster_extensions;
     std::vector<std::vector<size_t>> minimizer_extended_cluster_count;
@@ -578,6 +581,7 @@ Alignment map_from_extensions(const gb_flat_index* ix, const gb_scores& scores, 
                 seed_matchings.emplace_back(seed.node, (int64_t)minimizers[seed.source].offset - (int64_t)seed.offset);
                 minimizer_extended_cluster_count.back()[seed.source]++;
             }
+            if (g_stage_trace) g_stage_trace->reads[0].items.push_back(StageTrace::Item{cluster_num, cluster.fragment, seed_matchings});
             cluster_extensions.emplace_back(extend(g, scores, seed_matchings, sequence, P.max_extension_mismatches, 0.8, true));
             if (counters) counters->extend_calls++;
             kept_cluster_count++;

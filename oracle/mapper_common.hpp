@@ -126,4 +126,13 @@ struct Minimizer {
 struct Seed { uint32_t node; uint32_t offset; size_t source; gb_dist_payload payload; };   // pos_t + source + zipcode
 struct Cluster { std::vector<size_t> seeds; size_t fragment = 0; double score = 0, coverage = 0; };
 
+// Stage trace for the stage-level parity tests (oracle_seed_stage): when the thread-local pointer is set, map_from_extensions
+// / map_paired record what they computed up to the extension calls, per read of the unit.
+struct StageTrace {
+    struct Item { size_t cluster, fragment; std::vector<std::pair<uint32_t, int64_t>> seeds; };
+    struct Read { std::vector<Minimizer> minimizers; std::vector<Seed> seeds; std::vector<Cluster> clusters; std::vector<Item> items; };
+    Read reads[2];
+};
+extern thread_local StageTrace* g_stage_trace;
+
 } // namespace oracle

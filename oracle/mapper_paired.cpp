@@ -193,6 +193,8 @@ PairResult map_paired(const gb_flat_index* ix, const gb_scores& scores, const gb
         }
     }
 
+    if (g_stage_trace) for (int r : {0, 1}) { auto& t = g_stage_trace->reads[r]; t.minimizers = minimizers_by_read[r]; t.seeds = seeds_by_read[r]; t.clusters = all_clusters[r]; }
+
     std::array<std::vector<bool>, 2> minimizer_explored_by_read;
     std::vector<std::array<std::vector<Alignment>, 2>> alignments(max_fragment_num + 2);
     std::array<int, 2> best_alignment_scores{0, 0};
@@ -248,6 +250,7 @@ PairResult map_paired(const gb_flat_index* ix, const gb_scores& scores, const gb
                         seed_matchings.emplace_back(seed.node, (int64_t)minimizers[seed.source].offset - (int64_t)seed.offset);
                         minimizer_kept_cluster_count.back()[seed.source]++;
                     }
+                    if (g_stage_trace) g_stage_trace->reads[read_num].items.push_back(StageTrace::Item{cluster_num, cluster.fragment, seed_matchings});
                     cluster_extensions.emplace_back(extend(g, scores, seed_matchings, sequence, P.max_extension_mismatches, 0.8, true), cluster.fragment);
                     if (counters) counters->extend_calls++;
                     kept_cluster_count++;
@@ -569,7 +572,7 @@ extern "C" int oracle_map_paired_job(const gb_flat_index* ix, const gb_scores* s
                 keep = true;
             }
         }
-        if (keep) { route[pi] = GB_PAIR_TRAINING; for (int r = 0; r < 2; r++) emit(single[r], 2 * pi + r, false); }
+        if (keep) { route[pi] = GB_PAIR_TRAINING; for (int r = 0; r < 2; r++) emit(single[r], 2 * pi + r, true); }   // pair_all(mapped_pair), minimizer_mapper.cpp:1345-1350
         else { route[pi] = GB_PAIR_BUFFERED; ambiguous_pair_buffer.push_back(pi); }
     }
     const int64_t first_paired = pi;
@@ -589,4 +592,55 @@ extern "C" int oracle_map_paired_job(const gb_flat_index* ix, const gb_scores* s
         for (int r = 0; r < 2; r++) emit(res.aln[r], 2 * x + r, true);
     }
     return failed ? -1 : 0;
+}
+
+
+// ---- stage dump for the stage-level parity tests: everything the mapper computes before the first extension call,
+// per read, in the layout of gb_debug_seed_stage (include/giraffe_b200.h).  Sequential (the trace is thread-local).
+extern "C" int oracle_seed_stage(const gb_flat_index* ix, const gb_scores* scores, const gb_map_params* p, int paired,
+                                 uint32_t n_reads, const uint8_t* reads, const uint8_t* quals, const uint64_t* read_off,
+                                 gb_stage_read* out_reads, gb_stage_minimizer* mins, uint64_t min_cap, gb_stage_seed* seeds, uint64_t seed_cap,
+                                 gb_stage_cluster* clusters, uint64_t cluster_cap, gb_stage_item* items, uint64_t item_cap,
+                                 gb_seed* item_seeds, uint64_t item_seed_cap) {
+    using namespace oracle;
+    uint64_t nm = 0, ns = 0, nc = 0, ni = 0, ne = 0;
+    auto read_of = [&](uint64_t ri, std::string& s, std::string& q) {
+        const uint64_t b = read_off[ri], e = read_off[ri + 1];
+        s.assign((const char*)reads + b, (size_t)(e - b));
+        if (quals) q.assign((const char*)quals + b, (size_t)(e - b)); else q.clear();
+    };
+    const uint32_t step = paired ? 2 : 1;
+    for (uint32_t u = 0; u + step <= n_reads; u += step) {
+        StageTrace trace;
+        g_stage_trace = &trace;
+        std::string s[2], q[2];
+        read_of(u, s[0], q[0]);
+        if (paired) { read_of(u + 1, s[1], q[1]); (void)map_paired(ix, *scores, *p, s[0], q[0], s[1], q[1], nullptr); }
+        else (void)map_from_extensions(ix, *scores, *p, s[0], q[0], nullptr);
+        g_stage_trace = nullptr;
+        for (uint32_t r = 0; r < step; r++) {
+            const StageTrace::Read& t = trace.reads[r];
+            gb_stage_read& o = out_reads[u + r];
+            memset(&o, 0, sizeof o);
+            if (nm + t.minimizers.size() > min_cap || ns + t.seeds.size() > seed_cap || nc + t.clusters.size() > cluster_cap || ni + t.items.size() > item_cap) return -1;
+            o.min_off = (uint32_t)nm; o.seed_off = (uint32_t)ns; o.cluster_off = (uint32_t)nc; o.item_off = (uint32_t)ni;
+            o.min_cnt = (uint32_t)t.minimizers.size(); o.seed_cnt = (uint32_t)t.seeds.size(); o.cluster_cnt = (uint32_t)t.clusters.size(); o.item_cnt = (uint32_t)t.items.size();
+            for (const Minimizer& m : t.minimizers)
+                mins[nm++] = gb_stage_minimizer{m.hash, m.score, (uint32_t)m.forward_offset(), (uint32_t)m.agglomeration_start, (uint32_t)m.agglomeration_length, m.is_reverse ? 1u : 0u, m.hit_cnt, 0};
+            std::vector<uint32_t> cluster_of(t.seeds.size(), 0xffffffffu);
+            for (size_t c = 0; c < t.clusters.size(); c++) for (size_t si : t.clusters[c].seeds) cluster_of[si] = (uint32_t)c;
+            for (size_t i = 0; i < t.seeds.size(); i++) seeds[ns++] = gb_stage_seed{t.seeds[i].node, t.seeds[i].offset, (uint32_t)t.seeds[i].source, cluster_of[i]};
+            for (size_t c = 0; c < t.clusters.size(); c++) {
+                uint32_t rank = 0xffffffffu;
+                for (size_t x = 0; x < t.items.size(); x++) if (t.items[x].cluster == c) rank = (uint32_t)x;
+                clusters[nc++] = gb_stage_cluster{t.clusters[c].score, t.clusters[c].coverage, (uint32_t)t.clusters[c].seeds.front(), (uint32_t)t.clusters[c].seeds.size(), (uint32_t)t.clusters[c].fragment, rank};
+            }
+            for (const StageTrace::Item& it : t.items) {
+                if (ne + it.seeds.size() > item_seed_cap) return -1;
+                items[ni++] = gb_stage_item{(uint32_t)it.cluster, (uint32_t)it.fragment, (uint32_t)ne, (uint32_t)it.seeds.size()};
+                for (const auto& sd : it.seeds) item_seeds[ne++] = gb_seed{sd.first, (int32_t)sd.second};
+            }
+        }
+    }
+    return 0;
 }

@@ -311,3 +311,63 @@ def oracle_map_paired_job(index, reads, quals, params, maximum_sample_size=1000,
                                    capi.ptr(maps), capi.ptr(edits), capi.ptr(status), capi.ptr(route), threads, capi.ptr(frag))
     assert rc == 0, f"oracle_map_paired_job rc {rc}"
     return aln, maps, edits, status, route, (float(frag[0]), float(frag[1]), int(frag[2]))
+
+
+def oracle_seed_stage(index, reads, quals=None, params=None, paired=False, scores=None):
+    """The oracle's stage dump (oracle_seed_stage in oracle/mapper_paired.cpp), same layout as Device.seed_stage."""
+    lib = oracle_lib()
+    vp, u64 = C.c_void_p, C.c_uint64
+    lib.oracle_seed_stage.argtypes = [C.POINTER(capi.FlatIndex), C.POINTER(capi.Scores), C.POINTER(MapParams), C.c_int, C.c_uint32, vp, vp, vp,
+                                      vp, vp, u64, vp, u64, vp, u64, vp, u64, vp, u64]
+    lib.oracle_seed_stage.restype = C.c_int
+    p = params or default_map_params()
+    scores = scores or capi.DEFAULT_SCORES
+    rbuf, qbuf, read_off = pack_reads(reads, quals)
+    n = len(read_off) - 1
+    outs = capi.stage_buffers(n)
+    rc = lib.oracle_seed_stage(C.byref(index.view), C.byref(scores), C.byref(p), 1 if paired else 0, n, capi.ptr(rbuf), capi.ptr(qbuf) if qbuf is not None else None,
+                               capi.ptr(read_off), capi.ptr(outs[0]), capi.ptr(outs[1]), len(outs[1]), capi.ptr(outs[2]), len(outs[2]), capi.ptr(outs[3]), len(outs[3]),
+                               capi.ptr(outs[4]), len(outs[4]), capi.ptr(outs[5]), len(outs[5]))
+    assert rc == 0, "oracle stage dump: capacity"
+    return outs
+
+
+def compare_stage_dumps(got, want, n):
+    """Field-by-field, bit-exact (scores and coverages are IEEE doubles built from the same host tables).
+    Returns a list of (read, stage, detail) for the first difference of each read."""
+    bad = []
+    gr, gm, gs, gc, gi, ge = got
+    wr, wm, ws, wc, wi, we = want
+    for r in range(n):
+        a, b = gr[r], wr[r]
+        if int(a["status"]) != 0:
+            bad.append((r, "status", int(a["status"]))); continue
+        for stage, cnt in (("a1 minimizer count", "min_cnt"), ("a3 seed count", "seed_cnt"), ("a4 cluster count", "cluster_cnt"), ("a6 item count", "item_cnt")):
+            if int(a[cnt]) != int(b[cnt]):
+                bad.append((r, stage, (int(a[cnt]), int(b[cnt])))); break
+        else:
+            x = gm[int(a["min_off"]): int(a["min_off"]) + int(a["min_cnt"])]; y = wm[int(b["min_off"]): int(b["min_off"]) + int(b["min_cnt"])]
+            if x.tobytes() != y.tobytes():
+                # a1 = which minimizers (as a set), a2 = their order after the score sort and tie shuffle
+                same_set = sorted(x.tolist()) == sorted(y.tolist())
+                bad.append((r, "a2 minimizer order" if same_set else "a1 minimizers", None)); continue
+            x = gs[int(a["seed_off"]): int(a["seed_off"]) + int(a["seed_cnt"])]; y = ws[int(b["seed_off"]): int(b["seed_off"]) + int(b["seed_cnt"])]
+            if x[["node", "offset", "source"]].tobytes() != y[["node", "offset", "source"]].tobytes():
+                bad.append((r, "a3 seeds", None)); continue
+            if (x["cluster"] != y["cluster"]).any():
+                bad.append((r, "a4 cluster membership", None)); continue
+            x = gc[int(a["cluster_off"]): int(a["cluster_off"]) + int(a["cluster_cnt"])]; y = wc[int(b["cluster_off"]): int(b["cluster_off"]) + int(b["cluster_cnt"])]
+            if x[["score", "coverage", "first_seed", "n_seeds"]].tobytes() != y[["score", "coverage", "first_seed", "n_seeds"]].tobytes():
+                bad.append((r, "a5 cluster score / coverage", (x.tolist(), y.tolist()))); continue
+            if (x["fragment"] != y["fragment"]).any():
+                bad.append((r, "a19 fragment clusters", (x["fragment"].tolist(), y["fragment"].tolist()))); continue
+            if (x["kept_rank"] != y["kept_rank"]).any():
+                bad.append((r, "a6 cluster selection / order", (x["kept_rank"].tolist(), y["kept_rank"].tolist()))); continue
+            x = gi[int(a["item_off"]): int(a["item_off"]) + int(a["item_cnt"])]; y = wi[int(b["item_off"]): int(b["item_off"]) + int(b["item_cnt"])]
+            if (x["cluster"] != y["cluster"]).any() or (x["fragment"] != y["fragment"]).any() or (x["seed_cnt"] != y["seed_cnt"]).any():
+                bad.append((r, "a7 work items", None)); continue
+            for t in range(len(x)):
+                sx = ge[int(x[t]["seed_off"]): int(x[t]["seed_off"]) + int(x[t]["seed_cnt"])]; sy = we[int(y[t]["seed_off"]): int(y[t]["seed_off"]) + int(y[t]["seed_cnt"])]
+                if sx.tobytes() != sy.tobytes():
+                    bad.append((r, "a7 item seeds (node, diagonal)", t)); break
+    return bad

@@ -147,4 +147,20 @@ def test_flat_index_file_roundtrip(tmp_path):
     (tmp_path / "corrupt.gbflat").write_bytes(bytes(corrupt))
     with pytest.raises(capi.GbError):
         capi.HostIndex.load(tmp_path / "corrupt.gbflat")
+    # refused, not crashed: headers whose counts would wrap the size sum or ask for absurd allocations (each count is
+    # bounded by the file size on its own), a zero window, node records reaching into the sequence padding
+    for field, value in (((40, 48), 1 << 60), ((24, 32), (1 << 64) - 16), ((32, 40), 1 << 62), ((48, 56), (1 << 64) // 24)):
+        crafted = bytearray(raw); crafted[field[0]:field[1]] = np.uint64(value).tobytes()
+        (tmp_path / "crafted.gbflat").write_bytes(bytes(crafted))
+        with pytest.raises(capi.GbError):
+            capi.HostIndex.load(tmp_path / "crafted.gbflat")
+    (tmp_path / "tiny.gbflat").write_bytes(raw[:64])                       # header only, table_cells = 2^60
+    tiny = bytearray(raw[:64]); tiny[40:48] = np.uint64(1 << 60).tobytes()
+    (tmp_path / "tiny.gbflat").write_bytes(bytes(tiny))
+    with pytest.raises(capi.GbError):
+        capi.HostIndex.load(tmp_path / "tiny.gbflat")
+    zero_w = bytearray(raw); zero_w[16:20] = np.uint32(0).tobytes()
+    (tmp_path / "w0.gbflat").write_bytes(bytes(zero_w))
+    with pytest.raises(capi.GbError):
+        capi.HostIndex.load(tmp_path / "w0.gbflat")
     loaded.close(); built.close()

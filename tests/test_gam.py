@@ -152,3 +152,72 @@ def test_gam_groups_hold_a_thousand_messages():
     msgs, tagged = read_stream(data)
     assert len(msgs) == len(many) and tagged == 3
     assert decode_alignment(msgs[0])["name"] == "read0" and "fragment_next" not in decode_alignment(msgs[0])
+
+
+def _bgzf_blocks(raw):
+    """Split a BGZF stream into (header16, bsize, payload bytes) per block, checking htslib's layout."""
+    i, out = 0, []
+    while i < len(raw):
+        head = raw[i:i + 16]
+        assert head[:4] == b"\x1f\x8b\x08\x04" and head[10:12] == b"\x06\x00" and head[12:16] == b"BC\x02\x00"
+        bsize = struct.unpack("<H", raw[i + 16:i + 18])[0] + 1
+        block = raw[i:i + bsize]
+        payload = zlib.decompress(block[18:-8], -15)
+        crc, isize = struct.unpack("<II", block[-8:])
+        assert crc == zlib.crc32(payload) and isize == len(payload)
+        out.append((head, bsize, payload)); i += bsize
+    assert i == len(raw)
+    return out
+
+
+def test_bgzf_container_is_the_one_vg_writes():
+    """gb_bgzf_compress against the GAM files vg wrote: same 16 header bytes on every block, the same 28-byte EOF block,
+    and any gzip reader (zlib, as vg::io's BlockedGzipInputStream / htslib do) inflates it back to the input."""
+    vg_raw = (GAM_DIR / "perpendicular.gam").read_bytes()
+    vg_blocks = _bgzf_blocks(vg_raw)
+    assert vg_blocks[-1][2] == b"" and len(vg_blocks) >= 2
+    rng = np.random.default_rng(5)
+    for size, level in ((0, 6), (1, 6), (1000, 1), (0xff00, 6), (0xff00 + 1, 9), (300000, 6), (70000, 0)):
+        data = bytes(rng.integers(0, 4, size=size, dtype=np.uint8) + 65) if size != 300000 else bytes(rng.integers(0, 256, size=size, dtype=np.uint8))
+        raw = capi.bgzf_compress(data, level)
+        blocks = _bgzf_blocks(raw)
+        assert all(b[0] == vg_blocks[0][0] for b in blocks)                   # byte-identical block headers
+        assert raw[-28:] == vg_raw[-28:]                                      # the EOF marker block
+        assert all(len(b[2]) <= 0xff00 and b[1] <= 0x10000 for b in blocks)
+        assert len(blocks) == (size + 0xff00 - 1) // 0xff00 + 1
+        assert b"".join(b[2] for b in blocks) == data and _inflate(raw) == data
+
+
+def test_library_gam_in_bgzf_reads_back_like_vgs_files():
+    """The whole emission path a drop-in needs: records -> GAM messages -> BGZF, read back with the reader used on vg's files."""
+    g, index, rs, res = TE._records(paired=True)
+    rbuf, qbuf, read_off = H.pack_reads(rs.reads, rs.quals)
+    plain = capi.emit_text("gam", index.view, res[0], res[1], res[2], rbuf, qbuf, read_off)
+    msgs, tagged = read_stream(_inflate(capi.bgzf_compress(plain)))
+    assert tagged == 1 and len(msgs) == rs.n and [decode_alignment(m)["score"] for m in msgs] == [int(a["score"]) for a in res[0]]
+
+
+def test_gam_negative_score_is_a_sign_extended_varint():
+    """proto3 int32: a negative score is written as the 10-byte two's-complement varint protobuf parsers expect."""
+    g, index, rs, res = TE._records(paired=False)
+    rbuf, qbuf, read_off = H.pack_reads(rs.reads, rs.quals)
+    aln = res[0][:1].copy(); aln["score"] = -7
+    msgs, _ = read_stream(capi.emit_text("gam", index.view, aln, res[1], res[2], rbuf, qbuf, read_off))
+    raw = _one(_fields(msgs[0]), 6)
+    assert raw == (1 << 64) - 7
+
+
+def test_emitters_refuse_decreasing_name_offsets():
+    g, index, rs, res = TE._records(paired=False)
+    rbuf, qbuf, read_off = H.pack_reads(rs.reads, rs.quals)
+    lib = capi.load_library()
+    import ctypes as C
+    names = np.frombuffer(b"abcdefgh" * rs.n, dtype=np.uint8).copy()
+    noff = np.arange(rs.n + 1, dtype=np.uint64) * 8
+    noff[3] = 1                                                  # offset 3 below offset 2
+    out = np.zeros(1 << 20, dtype=np.uint8); used = C.c_uint64()
+    aln = np.ascontiguousarray(res[0])
+    for fn in (lib.gb_emit_gaf, lib.gb_emit_json, lib.gb_emit_gam):
+        rc = fn(C.byref(index.view), len(aln), capi.ptr(aln), capi.ptr(res[1]), len(res[1]), capi.ptr(res[2]), len(res[2]), rs.n, capi.ptr(rbuf), capi.ptr(qbuf),
+                capi.ptr(read_off), capi.ptr(names), capi.ptr(noff), capi.ptr(out), len(out), C.byref(used))
+        assert rc == capi.GB_ERR_ARG

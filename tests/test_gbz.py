@@ -352,8 +352,6 @@ def test_oracle_minimizer_regions_find_exactly_the_keys_of_the_reference_min_fil
 
 
 @pytest.mark.gpu
-@pytest.mark.xfail(reason="written after the round's GPU budget was spent: never run on a GPU yet (tests/tools/gpu_check_gbz.py is the same check); "
-                          "drop this marker once it has passed on a B200", strict=False)
 def test_cuda_path_equals_oracle_on_the_reference_gbz_graph():
     """Single-end and paired mapping (rescue on) on the graph vg built: CUDA path vs oracle."""
     seqs, paths, _ = read_gbz(GBZ)

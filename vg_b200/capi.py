@@ -65,6 +65,13 @@ alignment_dt = np.dtype([("read_id", "<u4"), ("score", "<i4"), ("mapq", "u1"), (
                          ("mapping_off", "<u4"), ("edit_off", "<u4"), ("n_edits", "<u4"),
                          ("mapq_uncapped", "<f4"), ("mapq_explored_cap", "<f4")])
 mapping_dt = np.dtype([("node", "<u4"), ("offset", "<u2"), ("n_edits", "<u2")])
+# gb_debug_seed_stage records
+stage_minimizer_dt = np.dtype([("hash", "<u8"), ("score", "<f8"), ("fwd_offset", "<u4"), ("agg_start", "<u4"), ("agg_len", "<u4"), ("is_reverse", "<u4"), ("hits", "<u4"), ("reserved", "<u4")])
+stage_seed_dt = np.dtype([("node", "<u4"), ("offset", "<u4"), ("source", "<u4"), ("cluster", "<u4")])
+stage_cluster_dt = np.dtype([("score", "<f8"), ("coverage", "<f8"), ("first_seed", "<u4"), ("n_seeds", "<u4"), ("fragment", "<u4"), ("kept_rank", "<u4")])
+stage_item_dt = np.dtype([("cluster", "<u4"), ("fragment", "<u4"), ("seed_off", "<u4"), ("seed_cnt", "<u4")])
+stage_read_dt = np.dtype([("min_off", "<u4"), ("min_cnt", "<u4"), ("seed_off", "<u4"), ("seed_cnt", "<u4"), ("cluster_off", "<u4"), ("cluster_cnt", "<u4"),
+                          ("item_off", "<u4"), ("item_cnt", "<u4"), ("status", "<u4"), ("reserved", "<u4", (3,))])
 assert alignment_dt.itemsize == 32 and mapping_dt.itemsize == 8
 
 
@@ -173,6 +180,12 @@ def load_library() -> C.CDLL:
     for fn in (lib.gb_emit_gaf, lib.gb_emit_json, lib.gb_emit_gam):
         fn.argtypes = [C.POINTER(FlatIndex), u32, vp, vp, u64, vp, u64, u32, vp, vp, vp, vp, vp, vp, u64, vp]
         fn.restype = C.c_int
+    lib.gb_debug_seed_stage.argtypes = [vp, C.POINTER(MapParams), C.c_int, u32, vp, vp, vp, vp, vp, u64, vp, u64, vp, u64, vp, u64, vp, u64]
+    lib.gb_debug_seed_stage.restype = C.c_int
+    lib.gb_device_pool_overflow.argtypes = [vp, C.POINTER(C.c_int)]
+    lib.gb_device_pool_overflow.restype = C.c_int
+    lib.gb_bgzf_compress.argtypes = [vp, u64, C.c_int, vp, u64, vp]
+    lib.gb_bgzf_compress.restype = C.c_int
     lib.gb_last_kernel_ms.argtypes = [vp]
     lib.gb_last_kernel_ms.restype = C.c_float
     lib.gb_launch_count.argtypes = [vp]
@@ -316,6 +329,25 @@ def emit_text(kind, flat_index, aln, maps, edits, rbuf, qbuf, read_off, names=No
         raise GbError(rc, "gb_emit_" + kind)
     data = out[: used.value].tobytes()
     return data if kind == "gam" else data.decode()
+
+
+def bgzf_compress(data: bytes, level: int = 6) -> bytes:
+    """gb_bgzf_compress: the BGZF container vg::io writes GAM streams in."""
+    lib = load_library()
+    src = np.frombuffer(data, dtype=np.uint8) if len(data) else np.zeros(1, dtype=np.uint8)
+    cap = len(data) + 128 * (len(data) // 0xff00 + 2)
+    out = np.zeros(cap, dtype=np.uint8)
+    used = C.c_uint64()
+    rc = lib.gb_bgzf_compress(ptr(src), len(data), level, ptr(out), cap, C.byref(used))
+    if rc != GB_OK:
+        raise GbError(rc, "gb_bgzf_compress")
+    return out[: used.value].tobytes()
+
+
+def stage_buffers(n, per_read=(160, 1024, 64, 64, 1024)):
+    """Output arrays of gb_debug_seed_stage / the oracle's twin for n reads."""
+    return (np.zeros(n, dtype=stage_read_dt), np.zeros(n * per_read[0] + 16, dtype=stage_minimizer_dt), np.zeros(n * per_read[1] + 16, dtype=stage_seed_dt),
+            np.zeros(n * per_read[2] + 16, dtype=stage_cluster_dt), np.zeros(n * per_read[3] + 16, dtype=stage_item_dt), np.zeros(n * per_read[4] + 16, dtype=seed_dt))
 
 
 class FragmentDistribution:
@@ -613,6 +645,26 @@ class Device:
             raise GbError(rc, "gb_map_paired_job")
         self.last_used = (used[0].value, used[1].value)
         return aln, maps, edits, status, route
+
+    def seed_stage(self, rbuf, qbuf, read_off, params=None, paired=False, per_read=(160, 1024, 64, 64, 1024)):
+        """gb_debug_seed_stage: (reads, minimizers, seeds, clusters, items, item_seeds) as structured arrays."""
+        lib = load_library()
+        p = params or default_map_params()
+        n = len(read_off) - 1
+        outs = stage_buffers(n, per_read)
+        rc = lib.gb_debug_seed_stage(self._h, C.byref(p), 1 if paired else 0, n, ptr(rbuf), ptr(qbuf) if qbuf is not None else None, ptr(read_off),
+                                     ptr(outs[0]), ptr(outs[1]), len(outs[1]), ptr(outs[2]), len(outs[2]), ptr(outs[3]), len(outs[3]),
+                                     ptr(outs[4]), len(outs[4]), ptr(outs[5]), len(outs[5]))
+        if rc != GB_OK:
+            raise GbError(rc, "gb_debug_seed_stage")
+        return outs
+
+    def pool_overflow(self) -> bool:
+        flag = C.c_int()
+        rc = load_library().gb_device_pool_overflow(self._h, C.byref(flag))
+        if rc != GB_OK:
+            raise GbError(rc, "gb_device_pool_overflow")
+        return bool(flag.value)
 
     def stage_times(self):
         ms = (C.c_float * 4)()

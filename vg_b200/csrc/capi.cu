@@ -109,6 +109,10 @@ extern "C" int gb_device_create(const gb_flat_index* ix, int device_ordinal, gb_
         const unsigned long v = std::strtoul(env, nullptr, 10);
         if (v >= 2 && v <= (1ul << 24)) d->map_chunk = (uint32_t)(v & ~1ul);
     }
+    if (const char* env = std::getenv("GIRAFFE_B200_POOL_SCALE")) {
+        const double v = std::strtod(env, nullptr);
+        if (v > 0.0 && v <= 1024.0) d->pool_scale = v;
+    }
     if (const char* env = std::getenv("GIRAFFE_B200_SEED_TABLES")) {
         unsigned mc = 0, cc = 0, ns = 64;
         if (std::sscanf(env, "%u,%u,%u", &mc, &cc, &ns) >= 2 && mc >= 2 && cc >= 1) {
@@ -130,7 +134,7 @@ extern "C" int gb_device_create(const gb_flat_index* ix, int device_ordinal, gb_
         GB_CUDA(cudaEventCreateWithFlags(&d->io[i].ev_out, cudaEventDisableTiming));
         GB_CUDA(cudaEventCreate(&d->io[i].ev_k0)); GB_CUDA(cudaEventCreate(&d->io[i].ev_k1));
     }
-    GB_CUDA(cudaMallocHost(&d->h_totals, 4 * sizeof(uint64_t)));
+    GB_CUDA(cudaMallocHost(&d->h_totals, 6 * sizeof(uint64_t)));
     int rc;
     if ((rc = d->nodes.upload(ix->nodes, ix->n_nodes, d->stream))) return rc;
     if ((rc = d->seq.upload(ix->seq, ix->seq_bytes, d->stream))) return rc;

@@ -4,6 +4,7 @@
 #include "device_index.cuh"
 #include "extend.cuh"
 #include "map_state.cuh"
+namespace gb { struct DbgCluster; }
 
 #include <cuda_runtime.h>
 #include <string>
@@ -114,7 +115,10 @@ struct gb_device {
         void release() { reads.release(); quals.release(); status.release(); read_off.release(); totals.release(); aln.release(); maps.release(); edits.release(); }
     } io[2];
     cudaStream_t s_in = nullptr, s_out = nullptr;
-    uint64_t* h_totals = nullptr;          // pinned, 2 per set
+    uint64_t* h_totals = nullptr;          // pinned, 3 per set: mappings, edits, pool-overflow flag
+    double pool_scale = 1.0;               // intermediate pools = per-read averages x this; doubled when a chunk overflows (GIRAFFE_B200_POOL_SCALE)
+    uint32_t pool_reruns = 0;              // chunks redone because of it
+    gb::DbgCluster* dbg_clusters = nullptr; bool debug_stop_after_seed = false;     // gb_debug_seed_stage
     gb::DevBuf<uint64_t> c_run;            // running mapping / edit totals of a host-buffer call
     uint32_t map_chunk = 1u << 20;         // reads per chunk; GIRAFFE_B200_MAP_CHUNK overrides
     void release_all() {

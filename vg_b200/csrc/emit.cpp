@@ -63,7 +63,10 @@ void json_string(Out& o, const std::string& s) {
 // Every record must stay inside what the caller handed over: its read, its slice of the two pools, the graph, and the
 // read length its edits consume.  The emitters index with these fields, so a damaged record is refused here.
 bool records_valid(const gb_flat_index* ix, uint32_t n, const gb_alignment* aln, const gb_mapping* mappings, uint64_t mapping_pool_len,
-                   const uint32_t* edits, uint64_t edit_pool_len, uint32_t n_reads, const uint64_t* read_off) {
+                   const uint32_t* edits, uint64_t edit_pool_len, uint32_t n_reads, const uint64_t* read_off,
+                   const uint8_t* names, const uint64_t* name_off) {
+    // names are addressed like reads: n_reads + 1 non-decreasing offsets
+    if (names && name_off) for (uint32_t r = 0; r < n_reads; r++) if (name_off[r + 1] < name_off[r]) return false;
     for (uint32_t x = 0; x < n; x++) {
         const gb_alignment& a = aln[x];
         if (a.read_id >= n_reads || read_off[a.read_id + 1] < read_off[a.read_id]) return false;
@@ -90,11 +93,11 @@ bool records_valid(const gb_flat_index* ix, uint32_t n, const gb_alignment* aln,
 
 } // namespace
 
-extern "C" int gb_emit_gaf(const gb_flat_index* ix, uint32_t n, const gb_alignment* aln, const gb_mapping* mappings, uint64_t mapping_pool_len,
+static int gb_emit_gaf_impl(const gb_flat_index* ix, uint32_t n, const gb_alignment* aln, const gb_mapping* mappings, uint64_t mapping_pool_len,
                            const uint32_t* edits, uint64_t edit_pool_len, uint32_t n_reads, const uint8_t* reads, const uint8_t* quals, const uint64_t* read_off,
                            const uint8_t* names, const uint64_t* name_off, char* out, uint64_t out_cap, uint64_t* out_used) {
     if (!ix || !aln || !reads || !read_off || !out || !out_used) return GB_ERR_ARG;
-    if (!records_valid(ix, n, aln, mappings, mapping_pool_len, edits, edit_pool_len, n_reads, read_off)) return GB_ERR_ARG;
+    if (!records_valid(ix, n, aln, mappings, mapping_pool_len, edits, edit_pool_len, n_reads, read_off, names, name_off)) return GB_ERR_ARG;
     Out o{out, out_cap, 0, false};
     for (uint32_t x = 0; x < n; x++) {
         const gb_alignment& a = aln[x];
@@ -155,11 +158,11 @@ extern "C" int gb_emit_gaf(const gb_flat_index* ix, uint32_t n, const gb_alignme
     return o.overflow ? GB_ERR_CAPACITY : GB_OK;
 }
 
-extern "C" int gb_emit_json(const gb_flat_index* ix, uint32_t n, const gb_alignment* aln, const gb_mapping* mappings, uint64_t mapping_pool_len,
+static int gb_emit_json_impl(const gb_flat_index* ix, uint32_t n, const gb_alignment* aln, const gb_mapping* mappings, uint64_t mapping_pool_len,
                             const uint32_t* edits, uint64_t edit_pool_len, uint32_t n_reads, const uint8_t* reads, const uint8_t* quals, const uint64_t* read_off,
                             const uint8_t* names, const uint64_t* name_off, char* out, uint64_t out_cap, uint64_t* out_used) {
     if (!ix || !aln || !reads || !read_off || !out || !out_used) return GB_ERR_ARG;
-    if (!records_valid(ix, n, aln, mappings, mapping_pool_len, edits, edit_pool_len, n_reads, read_off)) return GB_ERR_ARG;
+    if (!records_valid(ix, n, aln, mappings, mapping_pool_len, edits, edit_pool_len, n_reads, read_off, names, name_off)) return GB_ERR_ARG;
     Out o{out, out_cap, 0, false};
     for (uint32_t x = 0; x < n; x++) {
         const gb_alignment& a = aln[x];
@@ -235,11 +238,11 @@ void pb_annotation(std::string& st, const char* key, const std::string& value_ms
 
 } // namespace
 
-extern "C" int gb_emit_gam(const gb_flat_index* ix, uint32_t n, const gb_alignment* aln, const gb_mapping* mappings, uint64_t mapping_pool_len,
+static int gb_emit_gam_impl(const gb_flat_index* ix, uint32_t n, const gb_alignment* aln, const gb_mapping* mappings, uint64_t mapping_pool_len,
                            const uint32_t* edits, uint64_t edit_pool_len, uint32_t n_reads, const uint8_t* reads, const uint8_t* quals, const uint64_t* read_off,
                            const uint8_t* names, const uint64_t* name_off, char* out, uint64_t out_cap, uint64_t* out_used) {
     if (!ix || !aln || !reads || !read_off || !out || !out_used) return GB_ERR_ARG;
-    if (!records_valid(ix, n, aln, mappings, mapping_pool_len, edits, edit_pool_len, n_reads, read_off)) return GB_ERR_ARG;
+    if (!records_valid(ix, n, aln, mappings, mapping_pool_len, edits, edit_pool_len, n_reads, read_off, names, name_off)) return GB_ERR_ARG;
     Out o{out, out_cap, 0, false};
     const uint32_t GROUP = 1000;                 // messages per group
     for (uint32_t g0 = 0; g0 < n; g0 += GROUP) {
@@ -281,7 +284,7 @@ extern "C" int gb_emit_gam(const gb_flat_index* ix, uint32_t n, const gb_alignme
             pb_bytes(msg, 3, nm.data(), nm.size());
             if (quals && L) pb_bytes(msg, 4, (const char*)quals + read_off[r], L);
             pb_uint(msg, 5, a.mapq);
-            pb_uint(msg, 6, (uint64_t)(uint32_t)a.score);          // int32 as varint; scores on this path are never negative
+            pb_uint(msg, 6, (uint64_t)(int64_t)a.score);           // proto3 int32: a negative value is a sign-extended 10-byte varint
             if (a.flags & GB_ALN_PAIRED) {
                 const std::string mate = read_name(names, name_off, r ^ 1u);
                 std::string frag; pb_bytes(frag, 3, mate.data(), mate.size());
@@ -299,4 +302,63 @@ extern "C" int gb_emit_gam(const gb_flat_index* ix, uint32_t n, const gb_alignme
     }
     *out_used = o.n;
     return o.overflow ? GB_ERR_CAPACITY : GB_OK;
+}
+
+
+// ---- the C ABI: no exception leaves the library (std::string growth can throw) -----------------------------------
+#define GB_EMIT_ENTRY(NAME)                                                                                                        \
+    extern "C" int NAME(const gb_flat_index* ix, uint32_t n, const gb_alignment* aln, const gb_mapping* mappings, uint64_t mapping_pool_len, \
+                        const uint32_t* edits, uint64_t edit_pool_len, uint32_t n_reads, const uint8_t* reads, const uint8_t* quals,         \
+                        const uint64_t* read_off, const uint8_t* names, const uint64_t* name_off, char* out, uint64_t out_cap, uint64_t* out_used) { \
+        try { return NAME##_impl(ix, n, aln, mappings, mapping_pool_len, edits, edit_pool_len, n_reads, reads, quals, read_off, names, name_off, out, out_cap, out_used); } \
+        catch (...) { return GB_ERR_CAPACITY; }                                                                                    \
+    }
+GB_EMIT_ENTRY(gb_emit_gaf)
+GB_EMIT_ENTRY(gb_emit_json)
+GB_EMIT_ENTRY(gb_emit_gam)
+
+// ---- BGZF: the blocked gzip container vg::io writes GAM in (giraffe_main.cpp:2209-2226 -> vg::io::ProtobufEmitter over a
+// BlockedGzipOutputStream; htslib's bgzf.c layout).  Every block is a complete gzip member of at most 64 KiB with the
+// extra subfield 'B','C' = total block size - 1, so readers can seek by (block offset, offset in block); the stream ends
+// with the 28-byte empty block.  Input is cut every 0xff00 bytes as htslib does.
+#include <zlib.h>
+extern "C" int gb_bgzf_compress(const void* in, uint64_t in_bytes, int level, void* out, uint64_t out_cap, uint64_t* out_used) {
+    if ((!in && in_bytes) || !out || !out_used || level < 0 || level > 9) return GB_ERR_ARG;
+    const uint8_t* src = (const uint8_t*)in; uint8_t* dst = (uint8_t*)out;
+    uint64_t o = 0;
+    const uint64_t BLOCK = 0xff00;
+    auto block = [&](const uint8_t* p, uint32_t len) -> int {
+        uint8_t buf[0x10000];
+        z_stream zs; memset(&zs, 0, sizeof zs);
+        if (deflateInit2(&zs, len ? level : Z_DEFAULT_COMPRESSION, Z_DEFLATED, -15, 8, Z_DEFAULT_STRATEGY) != Z_OK) return GB_ERR_ARG;
+        zs.next_in = const_cast<uint8_t*>(p); zs.avail_in = len; zs.next_out = buf + 18; zs.avail_out = sizeof buf - 18 - 8;
+        int zr = deflate(&zs, Z_FINISH);
+        if (zr != Z_STREAM_END) {                       // incompressible data at this level: store it (always fits: 0xff00 + 5)
+            deflateEnd(&zs);
+            memset(&zs, 0, sizeof zs);
+            if (deflateInit2(&zs, 0, Z_DEFLATED, -15, 8, Z_DEFAULT_STRATEGY) != Z_OK) return GB_ERR_ARG;
+            zs.next_in = const_cast<uint8_t*>(p); zs.avail_in = len; zs.next_out = buf + 18; zs.avail_out = sizeof buf - 18 - 8;
+            zr = deflate(&zs, Z_FINISH);
+            if (zr != Z_STREAM_END) { deflateEnd(&zs); return GB_ERR_ARG; }
+        }
+        const uint32_t clen = (uint32_t)zs.total_out;
+        deflateEnd(&zs);
+        const uint32_t total = 18 + clen + 8;
+        static const uint8_t head[16] = {0x1f, 0x8b, 8, 4, 0, 0, 0, 0, 0, 0xff, 6, 0, 'B', 'C', 2, 0};
+        memcpy(buf, head, 16);
+        buf[16] = (uint8_t)((total - 1) & 0xff); buf[17] = (uint8_t)((total - 1) >> 8);
+        const uint32_t crc = (uint32_t)crc32(crc32(0L, Z_NULL, 0), p, len);
+        for (int i = 0; i < 4; i++) { buf[18 + clen + i] = (uint8_t)(crc >> (8 * i)); buf[22 + clen + i] = (uint8_t)(len >> (8 * i)); }
+        if (o + total > out_cap) return GB_ERR_CAPACITY;
+        memcpy(dst + o, buf, total); o += total;
+        return GB_OK;
+    };
+    for (uint64_t at = 0; at < in_bytes; at += BLOCK) {
+        const int rc = block(src + at, (uint32_t)std::min<uint64_t>(BLOCK, in_bytes - at));
+        if (rc) return rc;
+    }
+    const int rc = block(src, 0);                       // the EOF marker block
+    if (rc) return rc;
+    *out_used = o;
+    return GB_OK;
 }

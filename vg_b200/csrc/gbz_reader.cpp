@@ -115,7 +115,7 @@ int fail(const char* why) { if (getenv("GB_GBZ_DEBUG")) fprintf(stderr, "gbz rea
 
 } // namespace
 
-extern "C" int gb_index_from_gbz(const char* path, uint32_t k, uint32_t w, gb_host_index** out) {
+static int index_from_gbz_impl(const char* path, uint32_t k, uint32_t w, gb_host_index** out) {
     if (!path || !out) return GB_ERR_ARG;
     *out = nullptr;
     FILE* f = fopen(path, "rb");
@@ -284,4 +284,9 @@ extern "C" int gb_index_from_gbz(const char* path, uint32_t k, uint32_t w, gb_ho
     for (const auto& p : paths) { flat.insert(flat.end(), p.begin(), p.end()); path_off.push_back(flat.size()); }
     if (node_seq.empty()) node_seq.push_back(0);
     return gb_index_build((uint32_t)n_ids, node_seq.data(), node_off.data(), (uint32_t)paths.size(), flat.data(), path_off.data(), dist.data(), k, w, out);
+}
+
+extern "C" int gb_index_from_gbz(const char* path, uint32_t k, uint32_t w, gb_host_index** out) {
+    try { return index_from_gbz_impl(path, k, w, out); }          // no exception crosses the ABI
+    catch (...) { if (out) *out = nullptr; return GB_ERR_FORMAT; }
 }

@@ -16,6 +16,7 @@
 #include <algorithm>
 #include <cstdio>
 #include <cstring>
+#include <new>
 #include <numeric>
 #include <string>
 #include <unordered_map>
@@ -100,12 +101,15 @@ void gbwt_visit_order(const std::vector<std::vector<uint32_t>>& seqs,
 
 } // namespace
 
-extern "C" int gb_index_build(uint32_t n_node_ids, const uint8_t* node_seq, const uint64_t* node_off,
-                              uint32_t n_paths, const uint32_t* path_nodes, const uint64_t* path_off,
-                              const gb_dist_payload* dist, uint32_t k, uint32_t w,
-                              gb_host_index** out) {
+static int index_build_impl(uint32_t n_node_ids, const uint8_t* node_seq, const uint64_t* node_off,
+                            uint32_t n_paths, const uint32_t* path_nodes, const uint64_t* path_off,
+                            const gb_dist_payload* dist, uint32_t k, uint32_t w,
+                            gb_host_index** out) {
     if (!node_seq || !node_off || !out || (n_paths && (!path_nodes || !path_off))) return GB_ERR_ARG;
     if (k == 0 || k > 31 || w == 0) return GB_ERR_ARG;
+    // offsets into seq / gbwt / hits are 32-bit (gb_node_rec, gb_min_cell): both orientations at 1 B/base bound the
+    // graph at 2 Gbp; larger inputs are refused instead of wrapping
+    if (n_node_ids >= 0x7ffffff0u || 2 * node_off[n_node_ids] + 64 > 0xffffffffull) return GB_ERR_FORMAT;
     auto* ix = new gb_host_index();
     ix->k = k; ix->w = w; ix->n_paths = n_paths;
     ix->n_nodes = 2 * (n_node_ids + 1);
@@ -174,6 +178,7 @@ extern "C" int gb_index_build(uint32_t n_node_ids, const uint8_t* node_seq, cons
         succ.erase(std::unique(succ.begin(), succ.end()), succ.end());
         if (succ.size() >= 1024) { delete ix; return GB_ERR_FORMAT; }
         if (ix->gbwt.size() & 1) ix->gbwt.push_back(0);   // 8-byte align the edge pairs
+        if (ix->gbwt.size() > 0xfffffff0ull) { delete ix; return GB_ERR_FORMAT; }
         ix->nodes[v].rec_off = (uint32_t)ix->gbwt.size();
         ix->gbwt.push_back((uint32_t)succ.size());
         size_t nruns_at = ix->gbwt.size();
@@ -229,6 +234,7 @@ extern "C" int gb_index_build(uint32_t n_node_ids, const uint8_t* node_seq, cons
     }
     std::sort(kps.begin(), kps.end(), [](const KP& a, const KP& b) { return a.key != b.key ? a.key < b.key : a.pos < b.pos; });
     kps.erase(std::unique(kps.begin(), kps.end(), [](const KP& a, const KP& b) { return a.key == b.key && a.pos == b.pos; }), kps.end());
+    if (kps.size() > 0xfffffff0ull) { delete ix; return GB_ERR_FORMAT; }          // hit_off / hit_cnt are 32-bit
     size_t nkeys = 0;
     for (size_t i = 0; i < kps.size(); i++) if (i == 0 || kps[i].key != kps[i - 1].key) nkeys++;
     uint64_t cells = 16; while (cells < 2 * nkeys + 1) cells *= 2;
@@ -248,6 +254,16 @@ extern "C" int gb_index_build(uint32_t n_node_ids, const uint8_t* node_seq, cons
     }
     *out = ix;
     return GB_OK;
+}
+
+// No exception crosses the ABI: allocation failures and the like come back as status codes.
+extern "C" int gb_index_build(uint32_t n_node_ids, const uint8_t* node_seq, const uint64_t* node_off,
+                              uint32_t n_paths, const uint32_t* path_nodes, const uint64_t* path_off,
+                              const gb_dist_payload* dist, uint32_t k, uint32_t w,
+                              gb_host_index** out) {
+    try { return index_build_impl(n_node_ids, node_seq, node_off, n_paths, path_nodes, path_off, dist, k, w, out); }
+    catch (const std::bad_alloc&) { return GB_ERR_CAPACITY; }
+    catch (...) { return GB_ERR_ARG; }
 }
 
 extern "C" void gb_index_free(gb_host_index* ix) { delete ix; }
@@ -314,7 +330,7 @@ extern "C" int gb_index_save(const gb_flat_index* ix, const char* path) {
     return ok ? GB_OK : GB_ERR_FORMAT;
 }
 
-extern "C" int gb_index_load(const char* path, gb_host_index** out) {
+static int index_load_impl(const char* path, gb_host_index** out) {
     if (!path || !out) return GB_ERR_ARG;
     *out = nullptr;
     FILE* f = fopen(path, "rb");
@@ -323,9 +339,13 @@ extern "C" int gb_index_load(const char* path, gb_host_index** out) {
     if (fread(&h, 1, sizeof h, f) != sizeof h || memcmp(h.magic, "GBFLAT1", 8) != 0) { fclose(f); return GB_ERR_FORMAT; }
     // plausibility before allocating: a power-of-two table, an even number of oriented nodes, sizes the file can hold
     fseek(f, 0, SEEK_END); const uint64_t file_bytes = (uint64_t)ftell(f); fseek(f, (long)sizeof h, SEEK_SET);
-    const uint64_t need = (uint64_t)h.n_nodes * sizeof(gb_node_rec) + h.seq_bytes + h.gbwt_words * 4 + (uint64_t)(h.n_nodes / 2) * sizeof(gb_dist_payload)
+    // every count is bounded by the file size on its own first (a crafted header must not wrap the sum), then the sum
+    const bool counts_ok = h.seq_bytes <= file_bytes && h.gbwt_words <= file_bytes / 4 && h.table_cells <= file_bytes / sizeof(gb_min_cell)
+                        && h.n_hits <= file_bytes / sizeof(gb_hit) && (uint64_t)h.n_nodes <= file_bytes / sizeof(gb_node_rec);
+    const uint64_t need = !counts_ok ? ~0ull : (uint64_t)h.n_nodes * sizeof(gb_node_rec) + h.seq_bytes + h.gbwt_words * 4 + (uint64_t)(h.n_nodes / 2) * sizeof(gb_dist_payload)
                         + h.table_cells * sizeof(gb_min_cell) + h.n_hits * sizeof(gb_hit);
-    if (h.n_nodes % 2 != 0 || h.table_cells == 0 || (h.table_cells & (h.table_cells - 1)) != 0 || h.k == 0 || h.k > 31 || need > file_bytes) { fclose(f); return GB_ERR_FORMAT; }
+    if (!counts_ok || h.n_nodes % 2 != 0 || h.n_nodes < 2 || h.table_cells == 0 || (h.table_cells & (h.table_cells - 1)) != 0 || h.k == 0 || h.k > 31 || h.w == 0
+        || h.seq_bytes < 16 || h.seq_bytes > 0xffffffffull || h.gbwt_words > 0xffffffffull || h.n_hits > 0xffffffffull || need > file_bytes) { fclose(f); return GB_ERR_FORMAT; }
     gb_host_index* ix = new gb_host_index();
     ix->n_nodes = h.n_nodes; ix->k = h.k; ix->w = h.w; ix->n_paths = h.n_paths;
     const bool ok = read_padded(f, ix->nodes, h.n_nodes) && read_padded(f, ix->seq, h.seq_bytes) && read_padded(f, ix->gbwt, h.gbwt_words)
@@ -333,8 +353,10 @@ extern "C" int gb_index_load(const char* path, gb_host_index** out) {
     fclose(f);
     if (!ok) { delete ix; return GB_ERR_FORMAT; }
     // offsets must stay inside the arrays (a truncated or foreign file must not make the kernels read out of bounds)
+    // the kernels read 16 bytes past a node's last base (vector loads): the sequence keeps >= 16 zero bytes of tail padding
+    for (uint64_t i = h.seq_bytes - 16; i < h.seq_bytes; i++) if (ix->seq[i] != 0) { delete ix; return GB_ERR_FORMAT; }
     for (const gb_node_rec& r : ix->nodes) {
-        if ((uint64_t)r.seq_off + r.len > h.seq_bytes) { delete ix; return GB_ERR_FORMAT; }
+        if ((uint64_t)r.seq_off + r.len + 16 > h.seq_bytes || r.len > 1024) { delete ix; return GB_ERR_FORMAT; }
         if (r.size == 0) continue;
         // GBWT record: n_edges, n_runs, n_edges x {to, offset}, n_runs x {(len << 10) | outrank}; everything inside the blob
         if ((uint64_t)r.rec_off + 2 > h.gbwt_words) { delete ix; return GB_ERR_FORMAT; }
@@ -349,4 +371,9 @@ extern "C" int gb_index_load(const char* path, gb_host_index** out) {
         if (c.key != GB_NO_KEY && (uint64_t)c.hit_off + c.hit_cnt > h.n_hits) { delete ix; return GB_ERR_FORMAT; }
     *out = ix;
     return GB_OK;
+}
+
+extern "C" int gb_index_load(const char* path, gb_host_index** out) {
+    try { return index_load_impl(path, out); }
+    catch (...) { if (out) *out = nullptr; return GB_ERR_FORMAT; }
 }

@@ -179,7 +179,7 @@ int map_device(gb_device* d, const gb_map_params* hp, uint32_t n_reads, const ui
                const uint64_t* d_read_off, uint32_t max_len, uint64_t total_bases,
                gb_alignment* d_aln, uint8_t* d_status, bool paired,
                gb_mapping* out_maps, uint64_t out_map_cap, uint32_t* out_edits, uint64_t out_edit_cap,
-               const uint64_t* d_run_base, uint32_t read_base, uint64_t* d_totals) {
+               const uint64_t* d_run_base, uint32_t read_base, uint64_t* d_totals, uint32_t* d_overflow) {
     int rc0;
     if ((rc0 = d->pad_maps.reserve((size_t)n_reads * hp->mapping_cap_per_read))) return rc0;
     if ((rc0 = d->pad_edits.reserve((size_t)n_reads * hp->edit_cap_per_read))) return rc0;
@@ -225,8 +225,13 @@ int map_device(gb_device* d, const gb_map_params* hp, uint32_t n_reads, const ui
     P.hit_score_table = d->t_hit.ptr; P.prob_at_least_one = d->t_plo.ptr; P.phred_prob = d->t_phred.ptr;
 
     // ---- pools ----
-    const size_t min_cap = (size_t)n_reads * 48 + 1024, seed_cap = (size_t)n_reads * 64 + 4096;
-    const size_t item_cap = (size_t)n_reads * 3 + 1024, ext_cap = seed_cap;
+    // Sized from per-read averages (48 minimizers, 64 seeds, 3 kept clusters) times d->pool_scale.  A chunk that needs
+    // more sets the sticky overflow word (cursor 13); the host-buffer entry points then double the scale and rerun the
+    // chunk (map_batch_host), gb_map_batch_device reports it through gb_device_pool_overflow.  Capacities stay below
+    // 2^32 records (the cursors are 32-bit; pool_claim never lets one wrap).
+    const double ps = d->pool_scale;
+    const size_t min_cap = std::min<size_t>((size_t)((double)n_reads * 48 * ps) + 1024, 0xfffffff0u), seed_cap = std::min<size_t>((size_t)((double)n_reads * 64 * ps) + 4096, 0xfffffff0u);
+    const size_t item_cap = std::min<size_t>((size_t)((double)n_reads * 3 * ps) + 1024, 0x7ffffff0u / 48), ext_cap = seed_cap;
     if ((rc = d->p_states.reserve(n_reads))) return rc;
     if ((rc = d->p_min.reserve(min_cap))) return rc;
     if ((rc = d->p_seeds.reserve(seed_cap))) return rc;
@@ -255,6 +260,7 @@ int map_device(gb_device* d, const gb_map_params* hp, uint32_t n_reads, const ui
     b.states = d->p_states.ptr; b.work_counter = cur + 0; b.Lc = Lc;
     b.in_list = nullptr; b.in_count = nullptr; b.retry_list = nullptr; b.retry_count = nullptr; b.Mc = MAX_MINIMIZERS; b.Cc = MAX_CLUSTERS; b.Ns = d->seed_ns;
     SeedPools pools;
+    pools.dbg_clusters = d->dbg_clusters; pools.overflow = cur + 13;
     pools.minimizers = d->p_min.ptr; pools.min_cap = (uint32_t)min_cap; pools.min_cursor = cur + 1;
     pools.seeds = d->p_seeds.ptr; pools.seed_cap = (uint32_t)seed_cap; pools.seed_cursor = cur + 2;
     pools.items = d->p_items.ptr; pools.item_cap = (uint32_t)item_cap; pools.item_cursor = cur + 3;
@@ -295,6 +301,7 @@ int map_device(gb_device* d, const gb_map_params* hp, uint32_t n_reads, const ui
         }
     }
     GB_CUDA(cudaEventRecord(d->ev_stage[1], d->stream));
+    if (d->debug_stop_after_seed) return GB_OK;              // gb_debug_seed_stage reads the pools as the seeding kernels left them
     // ---- K2: extension over the items produced on the device ----
     const uint32_t max_ext = 48, path_cap = 384, mism_cap = 192;
     if ((rc = d->p_ext_count.reserve(item_cap))) return rc;
@@ -385,6 +392,7 @@ int map_device(gb_device* d, const gb_map_params* hp, uint32_t n_reads, const ui
     GB_CUDA(cudaEventRecord(d->ev_stage[3], d->stream));
     if ((rc = compact_outputs(d, n_reads, d_aln, d_maps, d_edits, hp->mapping_cap_per_read, hp->edit_cap_per_read,
                               out_maps, out_map_cap, out_edits, out_edit_cap, d_run_base, read_base, d_totals, d_status))) return rc;
+    if (d_overflow) GB_CUDA(cudaMemcpyAsync(d_overflow, cur + 13, sizeof(uint32_t), cudaMemcpyDeviceToDevice, d->stream));
     GB_CUDA(cudaEventRecord(d->ev_stage[4], d->stream));
     return GB_OK;
 }
@@ -429,12 +437,14 @@ static int map_batch_host(gb_device* d, const gb_map_params* hp, bool paired,
     GB_CUDA(cudaMemsetAsync(d->c_run.ptr, 0, 2 * sizeof(uint64_t), d->stream));
     const uint32_t n_chunks = (n_reads + chunk - 1) / chunk;
     bool used[2] = {false, false};
+    constexpr int RERUN = 1000;                   // internal: the chunk overflowed the intermediate pools
 
     // download the dense mappings / edits of a chunk whose header copy has been queued
     auto finish = [&](uint32_t ci) -> int {
         gb_device::IoSet& io = d->io[ci & 1];
         GB_CUDA(cudaEventSynchronize(io.ev_hdr));
-        const uint64_t tm = d->h_totals[2 * (ci & 1)], te = d->h_totals[2 * (ci & 1) + 1];
+        const uint64_t tm = d->h_totals[3 * (ci & 1)], te = d->h_totals[3 * (ci & 1) + 1];
+        if (d->h_totals[3 * (ci & 1) + 2] != 0) return RERUN;
         if (map_used + tm > mapping_pool_cap || edit_used + te > edit_pool_cap) {
             g_last_error = "output pool capacity too small";
             return GB_ERR_CAPACITY;
@@ -450,7 +460,7 @@ static int map_batch_host(gb_device* d, const gb_map_params* hp, bool paired,
     };
     auto drain = [&]() { cudaStreamSynchronize(d->s_in); cudaStreamSynchronize(d->stream); cudaStreamSynchronize(d->s_out); };
 
-    for (uint32_t ci = 0; ci < n_chunks; ci++) {
+    auto launch = [&](uint32_t ci) -> int {
         const uint32_t c0 = ci * chunk;
         const uint32_t cn = std::min<uint32_t>(chunk, n_reads - c0);
         gb_device::IoSet& io = d->io[ci & 1];
@@ -464,8 +474,8 @@ static int map_batch_host(gb_device* d, const gb_map_params* hp, bool paired,
             GB_CUDA(cudaStreamWaitEvent(d->stream, io.ev_out, 0));
         }
         if ((rc = io.reads.reserve(total ? total : 1)) || (quals && (rc = io.quals.reserve(total ? total : 1))) || (rc = io.read_off.reserve(cn + 1)) ||
-            (rc = io.aln.reserve(cn)) || (rc = io.status.reserve(cn)) || (rc = io.totals.reserve(2)) ||
-            (rc = io.maps.reserve(chunk_map_cap)) || (rc = io.edits.reserve(chunk_edit_cap))) { drain(); return rc; }
+            (rc = io.aln.reserve(cn)) || (rc = io.status.reserve(cn)) || (rc = io.totals.reserve(3)) ||
+            (rc = io.maps.reserve(chunk_map_cap)) || (rc = io.edits.reserve(chunk_edit_cap))) return rc;
         if (total) GB_CUDA(cudaMemcpyAsync(io.reads.ptr, reads + b0, total, cudaMemcpyHostToDevice, d->s_in));
         if (quals && total) GB_CUDA(cudaMemcpyAsync(io.quals.ptr, quals + b0, total, cudaMemcpyHostToDevice, d->s_in));
         GB_CUDA(cudaMemcpyAsync(io.read_off.ptr, read_off + c0, sizeof(uint64_t) * (cn + 1), cudaMemcpyHostToDevice, d->s_in));
@@ -473,23 +483,44 @@ static int map_batch_host(gb_device* d, const gb_map_params* hp, bool paired,
         GB_CUDA(cudaStreamWaitEvent(d->stream, io.ev_in, 0));
         if (b0) gb::rebase_offsets_kernel<<<(cn + 256) / 256, 256, 0, d->stream>>>(io.read_off.ptr, cn + 1, b0);
         GB_CUDA(cudaEventRecord(io.ev_k0, d->stream));
+        GB_CUDA(cudaMemsetAsync(io.totals.ptr + 2, 0, sizeof(uint64_t), d->stream));
         if ((rc = gb::map_device(d, hp, cn, io.reads.ptr, quals ? io.quals.ptr : nullptr, io.read_off.ptr, max_len, total,
                                  io.aln.ptr, io.status.ptr, paired, io.maps.ptr, chunk_map_cap, io.edits.ptr, chunk_edit_cap,
-                                 d->c_run.ptr, c0, io.totals.ptr))) { drain(); return rc; }
+                                 d->c_run.ptr, c0, io.totals.ptr, reinterpret_cast<uint32_t*>(io.totals.ptr + 2)))) return rc;
         gb::advance_run_kernel<<<1, 1, 0, d->stream>>>(d->c_run.ptr, io.totals.ptr);
         GB_CUDA(cudaEventRecord(io.ev_k1, d->stream));
         GB_CUDA(cudaEventRecord(io.ev_done, d->stream));
         used[ci & 1] = true;
         // headers + totals of this chunk leave as soon as it is done
         GB_CUDA(cudaStreamWaitEvent(d->s_out, io.ev_done, 0));
-        GB_CUDA(cudaMemcpyAsync(d->h_totals + 2 * (ci & 1), io.totals.ptr, 2 * sizeof(uint64_t), cudaMemcpyDeviceToHost, d->s_out));
+        GB_CUDA(cudaMemcpyAsync(d->h_totals + 3 * (ci & 1), io.totals.ptr, 3 * sizeof(uint64_t), cudaMemcpyDeviceToHost, d->s_out));
         GB_CUDA(cudaMemcpyAsync(aln + c0, io.aln.ptr, sizeof(gb_alignment) * cn, cudaMemcpyDeviceToHost, d->s_out));
         GB_CUDA(cudaMemcpyAsync(status + c0, io.status.ptr, cn, cudaMemcpyDeviceToHost, d->s_out));
         GB_CUDA(cudaEventRecord(io.ev_hdr, d->s_out));
-        // meanwhile the previous chunk's dense pools can be sized and fetched
-        if (ci > 0 && (rc = finish(ci - 1))) { drain(); return rc; }
+        return GB_OK;
+    };
+
+    // chunk ci computes while chunk ci-1's dense pools are sized and fetched; a chunk that ran out of intermediate pool
+    // space is redone (it and everything queued behind it) with the pools doubled, so capacity never shows in a result
+    uint32_t next = 0, finished = 0;
+    while (finished < n_chunks) {
+        if (next < n_chunks) { if ((rc = launch(next))) { drain(); return rc; } next++; }
+        if (next - finished == 2 || next == n_chunks) {
+            rc = finish(finished);
+            if (rc == RERUN) {
+                drain();
+                if (d->pool_scale >= 1024.0) { g_last_error = "intermediate pools overflow even at 1024x the per-read averages; use a smaller GIRAFFE_B200_MAP_CHUNK"; return GB_ERR_CAPACITY; }
+                d->pool_scale *= 2.0; d->pool_reruns++;
+                const uint64_t run[2] = {map_used, edit_used};
+                GB_CUDA(cudaMemcpy(d->c_run.ptr, run, sizeof run, cudaMemcpyHostToDevice));
+                used[0] = used[1] = false;
+                next = finished;
+                continue;
+            }
+            if (rc) { drain(); return rc; }
+            finished++;
+        }
     }
-    if ((rc = finish(n_chunks - 1))) { drain(); return rc; }
     GB_CUDA(cudaStreamSynchronize(d->s_out));
     GB_CUDA(cudaStreamSynchronize(d->stream));
     d->last_kernel_ms = kernel_ms;
@@ -521,7 +552,106 @@ extern "C" int gb_map_batch_device(gb_device* d, const gb_map_params* hp, int pa
     if (n_reads == 0) return GB_OK;
     GB_CUDA(cudaSetDevice(d->device));
     return map_device(d, hp, n_reads, d_reads, d_quals, d_read_off, max_read_len, (uint64_t)n_reads * max_read_len, d_aln, d_status, paired != 0,
-                      d_mappings, mapping_pool_cap, d_edits, edit_pool_cap, nullptr, 0, d_totals);
+                      d_mappings, mapping_pool_cap, d_edits, edit_pool_cap, nullptr, 0, d_totals, nullptr);
+}
+
+// gb_map_batch_device cannot rerun a batch by itself (it only enqueues work): after synchronising, this tells whether the
+// last batch ran out of intermediate pool space (reads then carry GB_ITEM_OUT_FULL) and, if so, doubles the pools for the
+// next call, so the caller simply submits the batch again.
+extern "C" int gb_device_pool_overflow(gb_device* d, int* overflowed) {
+    if (!d || !overflowed) return GB_ERR_ARG;
+    *overflowed = 0;
+    if (!d->p_cursors.ptr) return GB_OK;
+    GB_CUDA(cudaSetDevice(d->device));
+    GB_CUDA(cudaStreamSynchronize(d->stream));
+    uint32_t flag = 0;
+    GB_CUDA(cudaMemcpy(&flag, d->p_cursors.ptr + 13, sizeof flag, cudaMemcpyDeviceToHost));
+    if (flag) { *overflowed = 1; if (d->pool_scale < 1024.0) d->pool_scale *= 2.0; d->pool_reruns++; }
+    return GB_OK;
+}
+
+// Stage dump for the parity tests: the seeding kernels only, then the pools as they left them, converted on the host.
+extern "C" int gb_debug_seed_stage(gb_device* d, const gb_map_params* hp, int paired,
+                                   uint32_t n_reads, const uint8_t* reads, const uint8_t* quals, const uint64_t* read_off,
+                                   gb_stage_read* out_reads, gb_stage_minimizer* mins, uint64_t min_cap, gb_stage_seed* seeds, uint64_t seed_cap,
+                                   gb_stage_cluster* clusters, uint64_t cluster_cap, gb_stage_item* items, uint64_t item_cap,
+                                   gb_seed* item_seeds, uint64_t item_seed_cap) {
+    if (!d || !hp || !reads || !read_off || !out_reads || !mins || !seeds || !clusters || !items || !item_seeds) return GB_ERR_ARG;
+    if (n_reads == 0) return GB_OK;
+    try {
+        GB_CUDA(cudaSetDevice(d->device));
+        const uint64_t total = read_off[n_reads];
+        uint32_t max_len = 0;
+        for (uint32_t r = 0; r < n_reads; r++) max_len = std::max<uint32_t>(max_len, (uint32_t)(read_off[r + 1] - read_off[r]));
+        DevBuf<uint8_t> d_reads, d_quals, d_status; DevBuf<uint64_t> d_off, d_totals; DevBuf<gb_alignment> d_aln; DevBuf<DbgCluster> d_dbg;
+        int rc;
+        if ((rc = d_reads.upload(reads, total + 16, d->stream, total)) || (quals && (rc = d_quals.upload(quals, total + 16, d->stream, total))) ||
+            (rc = d_off.upload(read_off, n_reads + 1, d->stream)) || (rc = d_status.reserve(n_reads)) || (rc = d_totals.reserve(2)) ||
+            (rc = d_aln.reserve(n_reads)) || (rc = d_dbg.reserve((size_t)n_reads * MAX_CLUSTERS))) return rc;
+        GB_CUDA(cudaMemsetAsync(d_dbg.ptr, 0, sizeof(DbgCluster) * (size_t)n_reads * MAX_CLUSTERS, d->stream));
+        std::vector<ReadState> st(n_reads);
+        uint32_t cursors[16];
+        for (int attempt = 0;; attempt++) {
+            d->dbg_clusters = d_dbg.ptr; d->debug_stop_after_seed = true;
+            rc = map_device(d, hp, n_reads, d_reads.ptr, quals ? d_quals.ptr : nullptr, d_off.ptr, max_len, total, d_aln.ptr, d_status.ptr, paired != 0,
+                            nullptr, 0, nullptr, 0, nullptr, 0, d_totals.ptr, nullptr);
+            d->dbg_clusters = nullptr; d->debug_stop_after_seed = false;
+            if (rc) return rc;
+            GB_CUDA(cudaStreamSynchronize(d->stream));
+            GB_CUDA(cudaMemcpy(cursors, d->p_cursors.ptr, sizeof cursors, cudaMemcpyDeviceToHost));
+            if (!cursors[13]) break;
+            if (attempt >= 10) { g_last_error = "seed stage: pools overflow"; return GB_ERR_CAPACITY; }
+            d->pool_scale *= 2.0; d->pool_reruns++;
+        }
+        GB_CUDA(cudaMemcpy(st.data(), d->p_states.ptr, sizeof(ReadState) * n_reads, cudaMemcpyDeviceToHost));
+        std::vector<DevMinimizer> hm(cursors[1]); std::vector<DevSeed> hs(cursors[2]); std::vector<DevItem> hi(cursors[3]); std::vector<gb_seed> he(cursors[4]);
+        std::vector<DbgCluster> hc((size_t)n_reads * MAX_CLUSTERS);
+        if (!hm.empty()) GB_CUDA(cudaMemcpy(hm.data(), d->p_min.ptr, sizeof(DevMinimizer) * hm.size(), cudaMemcpyDeviceToHost));
+        if (!hs.empty()) GB_CUDA(cudaMemcpy(hs.data(), d->p_seeds.ptr, sizeof(DevSeed) * hs.size(), cudaMemcpyDeviceToHost));
+        if (!hi.empty()) GB_CUDA(cudaMemcpy(hi.data(), d->p_items.ptr, sizeof(DevItem) * hi.size(), cudaMemcpyDeviceToHost));
+        if (!he.empty()) GB_CUDA(cudaMemcpy(he.data(), d->p_ext_seeds.ptr, sizeof(gb_seed) * he.size(), cudaMemcpyDeviceToHost));
+        GB_CUDA(cudaMemcpy(hc.data(), d_dbg.ptr, sizeof(DbgCluster) * hc.size(), cudaMemcpyDeviceToHost));
+        uint64_t nm = 0, ns = 0, nc = 0, ni = 0, ne = 0;
+        for (uint32_t r = 0; r < n_reads; r++) {
+            const ReadState& rs = st[r];
+            gb_stage_read& o = out_reads[r];
+            memset(&o, 0, sizeof o);
+            o.status = rs.status;
+            o.min_off = (uint32_t)nm; o.seed_off = (uint32_t)ns; o.cluster_off = (uint32_t)nc; o.item_off = (uint32_t)ni;
+            if (rs.status != GB_ITEM_OK) continue;
+            if (nm + rs.min_cnt > min_cap || ns + rs.seed_cnt > seed_cap || nc + rs.n_clusters > cluster_cap || ni + rs.item_cnt > item_cap) { g_last_error = "stage dump: output too small"; return GB_ERR_CAPACITY; }
+            for (uint32_t i = 0; i < rs.min_cnt; i++) {
+                const DevMinimizer& m = hm[rs.min_off + i];
+                mins[nm + i] = gb_stage_minimizer{m.hash, m.score, m.fwd_offset, m.agg_start, m.agg_len, m.is_reverse, m.pad[1], 0};
+            }
+            // clusters in order of their first seed; a seed's label is the index of the first seed of its cluster
+            std::vector<uint32_t> cluster_of_label(rs.seed_cnt, 0xffffffffu);
+            for (uint32_t c = 0; c < rs.n_clusters; c++) {
+                const DbgCluster& dc = hc[(size_t)r * MAX_CLUSTERS + c];
+                if (!dc.valid || dc.first_seed >= rs.seed_cnt) { g_last_error = "stage dump: cluster record missing"; return GB_ERR_CUDA; }
+                clusters[nc + c] = gb_stage_cluster{dc.score, dc.coverage, dc.first_seed, 0, dc.fragment, dc.kept_rank};
+                cluster_of_label[dc.first_seed] = c;
+            }
+            for (uint32_t i = 0; i < rs.seed_cnt; i++) {
+                const DevSeed& sd = hs[rs.seed_off + i];
+                const uint32_t c = sd.label < rs.seed_cnt ? cluster_of_label[sd.label] : 0xffffffffu;
+                seeds[ns + i] = gb_stage_seed{sd.node, sd.offset, sd.source, c};
+                if (c != 0xffffffffu) clusters[nc + c].n_seeds++;
+            }
+            for (uint32_t t = 0; t < rs.item_cnt; t++) {
+                const DevItem& it = hi[rs.item_off + t];
+                if (ne + it.seed_cnt > item_seed_cap) { g_last_error = "stage dump: output too small"; return GB_ERR_CAPACITY; }
+                uint32_t cl = 0xffffffffu;
+                for (uint32_t c = 0; c < rs.n_clusters; c++) if (clusters[nc + c].kept_rank == t) cl = c;
+                items[ni + t] = gb_stage_item{cl, it.fragment, (uint32_t)ne, it.seed_cnt};
+                for (uint32_t x = 0; x < it.seed_cnt; x++) item_seeds[ne + x] = he[it.seed_off + x];
+                ne += it.seed_cnt;
+            }
+            o.min_cnt = rs.min_cnt; o.seed_cnt = rs.seed_cnt; o.cluster_cnt = rs.n_clusters; o.item_cnt = rs.item_cnt;
+            nm += rs.min_cnt; ns += rs.seed_cnt; nc += rs.n_clusters; ni += rs.item_cnt;
+        }
+        return GB_OK;
+    } catch (...) { g_last_error = "stage dump: out of host memory"; return GB_ERR_CAPACITY; }
 }
 
 extern "C" int gb_device_set_stream(gb_device* d, void* cuda_stream) {

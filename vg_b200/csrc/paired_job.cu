@@ -115,13 +115,14 @@ int64_t host_oriented_distance(const gb_device* d, uint32_t node_a, uint32_t off
 // Copy the records of reads [first, first + count) of a sub-batch into the caller's pools at the running
 // totals and store their headers under the caller's read ids.
 int append_records(const gb_alignment* sub_aln, const gb_mapping* sub_maps, const uint32_t* sub_edits, const uint8_t* sub_status,
-                   uint32_t sub_index, uint32_t read_id, gb_alignment* aln, gb_mapping* mappings, uint64_t mapping_pool_cap,
+                   uint32_t sub_index, uint32_t read_id, uint8_t extra_flags, gb_alignment* aln, gb_mapping* mappings, uint64_t mapping_pool_cap,
                    uint32_t* edits, uint64_t edit_pool_cap, uint8_t* status, uint64_t& nm, uint64_t& ne) {
     gb_alignment rec = sub_aln[sub_index];
     if (nm + rec.n_mappings > mapping_pool_cap || ne + rec.n_edits > edit_pool_cap) { g_last_error = "gb_map_paired_job: output pool too small"; return GB_ERR_CAPACITY; }
     if (rec.n_mappings) memcpy(mappings + nm, sub_maps + rec.mapping_off, (size_t)rec.n_mappings * sizeof(gb_mapping));
     if (rec.n_edits) memcpy(edits + ne, sub_edits + rec.edit_off, (size_t)rec.n_edits * 4);
     rec.read_id = read_id; rec.mapping_off = (uint32_t)nm; rec.edit_off = (uint32_t)ne;
+    rec.flags |= extra_flags;
     nm += rec.n_mappings; ne += rec.n_edits;
     aln[read_id] = rec; status[read_id] = sub_status[sub_index];
     return GB_OK;
@@ -174,7 +175,8 @@ extern "C" int gb_map_paired_job(gb_device* d, const gb_map_params* hp, gb_fragm
             }
             if (keep) {
                 for (uint32_t r = 0; r < 2; r++)
-                    if ((rc = append_records(sa.data(), sm.data(), se.data(), ss.data(), 2 * i + r, 2 * pair + r, aln, mappings, mapping_pool_cap,
+                    // pair_all(mapped_pair) links the two single-ended records as mates (minimizer_mapper.cpp:1345-1350)
+                    if ((rc = append_records(sa.data(), sm.data(), se.data(), ss.data(), 2 * i + r, 2 * pair + r, GB_ALN_PAIRED, aln, mappings, mapping_pool_cap,
                                              edits, edit_pool_cap, status, nm, ne))) return rc;
                 if (pair_route) pair_route[pair] = GB_PAIR_TRAINING;
             } else {
@@ -226,7 +228,7 @@ extern "C" int gb_map_paired_job(gb_device* d, const gb_map_params* hp, gb_fragm
         if ((rc = gb_map_paired_batch(d, &P, br, br_reads.data(), quals ? br_quals.data() : nullptr, off.data(), sa.data(), sm.data(), sm.size(),
                                       se.data(), se.size(), ss.data(), &um, &ue))) return rc;
         for (uint32_t i = 0; i < buffered.size(); i++) for (uint32_t r = 0; r < 2; r++)
-            if ((rc = append_records(sa.data(), sm.data(), se.data(), ss.data(), 2 * i + r, 2 * buffered[i] + r, aln, mappings, mapping_pool_cap,
+            if ((rc = append_records(sa.data(), sm.data(), se.data(), ss.data(), 2 * i + r, 2 * buffered[i] + r, 0, aln, mappings, mapping_pool_cap,
                                      edits, edit_pool_cap, status, nm, ne))) return rc;
     }
     if (n_mappings_used) *n_mappings_used = nm;

@@ -20,7 +20,13 @@ namespace gb {
 constexpr uint32_t MAX_CLUSTERS = 64;     // read clusters per read kept in shared memory (second-pass capacity)
 constexpr uint32_t GB_ITEM_RETRY = 100;   // internal: did not fit the small first-pass tables
 
+// Stage-parity debugging (gb_debug_seed_stage): every cluster of every read with its score, coverage,
+// fragment and rank among the read's work items; [n_reads * MAX_CLUSTERS], null in production runs.
+struct DbgCluster { double score, coverage; uint32_t first_seed, fragment, kept_rank, valid; };
+
 struct SeedPools {
+    DbgCluster* dbg_clusters;
+    uint32_t* overflow;       // sticky: a pool ran out; the host grows the pools and reruns the chunk
     DevMinimizer* minimizers; uint32_t min_cap;  uint32_t* min_cursor;
     DevSeed* seeds;           uint32_t seed_cap; uint32_t* seed_cursor;
     DevItem* items;           uint32_t item_cap; uint32_t* item_cursor;
@@ -103,6 +109,33 @@ __device__ inline SeedSmem carve_seed_smem(uint8_t* base, uint32_t Lc, uint32_t 
     return s;
 }
 __device__ __forceinline__ uint32_t table_full(uint32_t have, uint32_t max_cap) { return have < max_cap ? GB_ITEM_RETRY : (uint32_t)GB_ITEM_OUT_FULL; }
+
+// Claim `n` records of an HBM pool (warp-uniform).  Once any pool has run out the sticky flag stops every later
+// claim before it touches the cursor, so a cursor can never wrap; the host sees the flag, grows the pools and
+// reruns the whole chunk (map.cu), so which reads happened to fail never shows in a result.
+__device__ __forceinline__ bool pool_claim(uint32_t* cursor, uint32_t n, uint32_t cap, uint32_t* overflow, uint32_t& off) {
+    uint32_t o = 0xffffffffu;
+    if (lane_id() == 0) {
+        if (*(volatile uint32_t*)overflow == 0) {
+            o = atomicAdd(cursor, n);
+            if (o > cap || n > cap - o) { atomicExch(overflow, 1u); o = 0xffffffffu; }
+        }
+    }
+    off = __shfl_sync(FULL, o, 0);
+    return off != 0xffffffffu;
+}
+
+// dump the cluster table of one read for the stage-parity tests
+__device__ __forceinline__ void dbg_dump_clusters(const SeedPools& pools, const SeedSmem& sm, uint32_t read_idx, uint32_t cbase, uint32_t Cn,
+                                                  const uint8_t* kept, uint32_t n_kept) {
+    if (!pools.dbg_clusters) return;
+    for (uint32_t c = lane_id(); c < Cn; c += 32) {
+        DbgCluster dc; dc.score = sm.c_score[cbase + c]; dc.coverage = sm.c_cov[cbase + c]; dc.first_seed = sm.c_label[cbase + c];
+        dc.fragment = sm.c_frag[cbase + c]; dc.kept_rank = 0xffffffffu; dc.valid = 1;
+        for (uint32_t t = 0; t < n_kept; t++) if (kept[t] == c) dc.kept_rank = t;
+        pools.dbg_clusters[(size_t)read_idx * MAX_CLUSTERS + c] = dc;
+    }
+}
 
 __device__ __forceinline__ uint32_t pow13(uint32_t e) {
     uint32_t r = 1, b = 13;
@@ -459,9 +492,7 @@ __device__ __forceinline__ uint32_t seed_phase_a(const DevIndex& ix, const MapPa
 
     // ---- minimizer records (score order) -------------------------------------------------------------------
     uint32_t min_off = 0;
-    if (lane == 0) min_off = atomicAdd(pools.min_cursor, M);
-    min_off = __shfl_sync(FULL, min_off, 0);
-    if (min_off + M > pools.min_cap) return GB_ITEM_OUT_FULL;
+    if (!pool_claim(pools.min_cursor, M, pools.min_cap, pools.overflow, min_off)) return GB_ITEM_OUT_FULL;
     for (uint32_t i = lane; i < M; i += 32) {
         const uint32_t a = sm.m_order[i];
         DevMinimizer dm; dm.hash = sm.m_hash[a]; dm.score = sm.m_score[a]; dm.fwd_offset = sm.m_fwd[a];
@@ -473,9 +504,7 @@ __device__ __forceinline__ uint32_t seed_phase_a(const DevIndex& ix, const MapPa
 
     // ---- seeds ----------------------------------------------------------------------------------------------
     uint32_t seed_off = 0;
-    if (lane == 0) seed_off = atomicAdd(pools.seed_cursor, total_hits);
-    seed_off = __shfl_sync(FULL, seed_off, 0);
-    if (seed_off + total_hits > pools.seed_cap) return GB_ITEM_OUT_FULL;
+    if (!pool_claim(pools.seed_cursor, total_hits, pools.seed_cap, pools.overflow, seed_off)) return GB_ITEM_OUT_FULL;
     DevSeed* seeds = pools.seeds + seed_off;
     {
         // one lane per (minimizer, hit): exclusive prefix of the passing minimizers' hit counts, then
@@ -660,9 +689,7 @@ __device__ __forceinline__ uint32_t emit_items(const DevIndex& ix, const SeedSme
     item_off_out = 0;
     if (n_kept == 0) return GB_ITEM_OK;
     uint32_t item_off = 0;
-    if (lane == 0) item_off = atomicAdd(pools.item_cursor, n_kept);
-    item_off = __shfl_sync(FULL, item_off, 0);
-    if (item_off + n_kept > pools.item_cap) return GB_ITEM_OUT_FULL;
+    if (!pool_claim(pools.item_cursor, n_kept, pools.item_cap, pools.overflow, item_off)) return GB_ITEM_OUT_FULL;
     for (uint32_t t = 0; t < n_kept; t++) {
         const uint32_t c = kept[t];
         const uint32_t label = sm.c_label[cbase + c];
@@ -670,9 +697,7 @@ __device__ __forceinline__ uint32_t emit_items(const DevIndex& ix, const SeedSme
         for (uint32_t i = lane; i < H; i += 32) cnt += seeds[i].label == label ? 1u : 0u;
         cnt = (uint32_t)warp_sum((int)cnt);
         uint32_t eoff = 0;
-        if (lane == 0) eoff = atomicAdd(pools.ext_cursor, cnt);
-        eoff = __shfl_sync(FULL, eoff, 0);
-        if (eoff + cnt > pools.ext_cap) return GB_ITEM_OUT_FULL;
+        if (!pool_claim(pools.ext_cursor, cnt, pools.ext_cap, pools.overflow, eoff)) return GB_ITEM_OUT_FULL;
         uint32_t wpos = 0;
         for (uint32_t base = 0; base < H; base += 32) {
             const uint32_t i = base + lane;
@@ -758,6 +783,7 @@ __device__ __forceinline__ uint32_t cluster_phase_se(const DevIndex& ix, const M
     n_kept = __shfl_sync(FULL, n_kept, 0);
     rng.state = __shfl_sync(FULL, rng.state, 0); rng.inited = __shfl_sync(FULL, rng.inited, 0);
     __syncwarp();
+    dbg_dump_clusters(pools, sm, read_idx, 0, Cn, kept, n_kept);
     uint32_t item_off = 0;
     const uint32_t st = emit_items(ix, sm, pools, seeds, H, mins, read_idx, kept, n_kept, 0, item_off);
     if (st == GB_ITEM_OK) { rs.item_off = item_off; rs.item_cnt = n_kept; }
@@ -1033,6 +1059,7 @@ __device__ __forceinline__ uint32_t cluster_phase_pe(const DevIndex& ix, const M
     for (uint32_t r = 0; r < 2; r++) {
         uint32_t item_off = 0;
         const uint32_t nk = r ? n_kept1 : n_kept0;
+        dbg_dump_clusters(pools, sm, read_idx0 + r, r * sm.Cc, r ? Cn[1] : Cn[0], r ? kept1 : kept0, nk);
         const uint32_t st = emit_items(ix, sm, pools, r ? s1 : s0, r ? H1 : H0, r ? m1 : m0, read_idx0 + r, r ? kept1 : kept0, nk, r * sm.Cc, item_off);
         if (st != GB_ITEM_OK) return st;
         if (r) { rs1.item_off = item_off; rs1.item_cnt = nk; } else { rs0.item_off = item_off; rs0.item_cnt = nk; }

@@ -62,11 +62,19 @@ def _chop(seq: np.ndarray, max_node: int):
 
 
 def make_variant_graph(length=1_000_000, n_snp=800, n_ins=100, n_del=100, n_haps=8, seed=2,
-                       max_node=32, min_spacing=50, name="variants") -> SynthGraph:
+                       max_node=32, min_spacing=50, name="variants", repeat_unit=0, repeat_copies=0) -> SynthGraph:
     """Config 1/2 graph: random backbone, SNP/insertion/deletion sites >= min_spacing apart,
-    haplotypes pick the alt allele with p = 0.5 per site, nodes chopped to <= max_node bp."""
+    haplotypes pick the alt allele with p = 0.5 per site, nodes chopped to <= max_node bp.
+    repeat_unit / repeat_copies: the backbone carries that many exact copies of one random unit (minimizers with
+    several hits, several clusters per read, ties for the shuffles) — test graphs only."""
     rng = np.random.default_rng(seed)
     ref = BASES[rng.integers(0, 4, size=length)]
+    if repeat_unit and repeat_copies:
+        unit = BASES[np.random.default_rng(seed + 1000).integers(0, 4, size=repeat_unit)]
+        stride = length // repeat_copies
+        for c in range(repeat_copies):
+            at = c * stride + stride // 3
+            ref[at:at + repeat_unit] = unit
     n_var = n_snp + n_ins + n_del
     # variant positions at least min_spacing apart, away from the ends
     sites = []
