@@ -421,6 +421,10 @@ int gb_device_pool_overflow(gb_device* dev, int* overflowed);
  *   minimizers  in score order (after the tie shuffle); seeds in (minimizer, hit) order, each with the index of its
  *   read cluster; clusters in order of their first seed; items = kept clusters in processing order, each with its
  *   (node, read_offset - node_offset) seeds in item_seeds.
+ * gb_stage_read.reserved[0] > 1 marks a mate 2 whose clusters tie at the top of the processing order: the reference
+ * shuffles them with the pair's LazyRNG after mate 1's alignments have drawn from it (minimizer_mapper.cpp:1723-2043), so
+ * the align stage does that shuffle and the keep loop; such a read lists ALL its clusters as items, in comparator order
+ * before the shuffle, and reserved[0] is the length of the tied prefix.
  * Offsets in gb_stage_read index the flat output arrays; GB_ERR_CAPACITY when one is too small. */
 typedef struct gb_stage_minimizer { uint64_t hash; double score; uint32_t fwd_offset, agg_start, agg_len, is_reverse, hits, reserved; } gb_stage_minimizer;
 typedef struct gb_stage_seed { uint32_t node, offset, source, cluster; } gb_stage_seed;

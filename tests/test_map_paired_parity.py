@@ -287,3 +287,35 @@ def test_unusable_fragment_distribution_falls_back_to_single_end():
     assert not H.compare_alignments(got, se, rs.n, mapq_tol=0)
     assert ((got[0]["flags"] & capi.GB_ALN_PAIRED) != 0).all() and ((se[0]["flags"] & capi.GB_ALN_PAIRED) == 0).all()
     dev.close()
+
+
+def _repeat_graph():
+    return synth.make_variant_graph(length=24000, n_snp=40, n_ins=4, n_del=4, n_haps=4, seed=23, repeat_unit=600, repeat_copies=6)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("rescue", [0, 15])
+def test_pairs_in_repeats_draw_the_pair_rng_in_reference_order(rescue):
+    """Six exact copies of a 600-bp unit: reads inside it have six tied clusters per mate, six tied fragment clusters and
+    six tied extension sets, so every tie shuffle of map_paired fires.  The shuffles share one LazyRNG per pair and the
+    reference interleaves them read by read (clusters of read 1, its extension sets and tails, then clusters of read 2,
+    minimizer_mapper.cpp:1723-2043); which copy becomes the primary placement depends on that order."""
+    g = _repeat_graph()
+    rs = synth.simulate_pairs(g, 1500, sub_rate=0.01, seed=35)
+    p = H.paired_params(); p.max_rescue_attempts = rescue
+    got, want = _run(g, rs, p)
+    multi = int((want[0]["mapq"] < 60).sum())
+    assert multi > 50                                   # the repeat really produced ambiguous placements
+
+
+@pytest.mark.gpu
+def test_single_end_reads_in_repeats():
+    g = _repeat_graph()
+    index = g.build_index()
+    dev = capi.Device(index)
+    rs = synth.simulate_reads(g, 2000, length=150, sub_rate=0.01, seed=36)
+    got = H.gpu_map(dev, rs.reads, rs.quals)
+    want = H.oracle_map(index, rs.reads, rs.quals, threads=8)
+    bad = H.compare_alignments(got, want, rs.n)
+    assert not bad, f"{len(bad)} of {rs.n} reads differ; first: read {bad[0][0]}\n got={bad[0][1]}\nwant={bad[0][2]}"
+    dev.close(); index.close()

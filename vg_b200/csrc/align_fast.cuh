@@ -91,6 +91,7 @@ __device__ inline bool fast_pair(const DevIndex& ix, const MapParamsDev& P, cons
     const ReadState rs0 = b.states[2 * p], rs1 = b.states[2 * p + 1];
     const ReadState* rsp[2] = {&rs0, &rs1};
     if (rs0.status != GB_ITEM_OK) return false;                 // let the slow kernel report it
+    if (rs1.pad[0] > 1) return false;                           // deferred cluster selection of read 2 (rare: tied clusters): warp kernel
     const PairState ps = a.pairs[p];
     if (ps.n_fragments + 1 > MAX_FRAGMENTS) return false;
     DevRng rng = rs0.rng;

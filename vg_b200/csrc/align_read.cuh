@@ -226,6 +226,32 @@ __device__ inline double max_mapping_quality(const double* scores, uint32_t n, d
     return (double)(int32_t)mq;
 }
 
+// Deferred cluster selection of read 2 of a pair (see cluster_phase_pe): the seeding kernel left every cluster of the read
+// as a work item in comparator order with the keep-decision inputs in DevItem::fragment bits 8-10 and the length of the
+// tied prefix in ReadState::pad[0].  Here, at the point of the per-read loop where the reference does it
+// (minimizer_mapper.cpp:1780-1883, after read 1's alignments), the tied prefix is shuffled with the pair's LazyRNG and the
+// order-dependent keep loop (process_until_threshold_c with its kept_cluster_count tests) picks the items.
+// Returns false when the read is not deferred (sel untouched).
+__device__ inline bool deferred_cluster_selection(const MapParamsDev& P, const ReadState& rs, const DevItem* items, DevRng& rng, uint8_t* sel, uint32_t& S) {
+    const uint32_t ties = rs.pad[0];
+    if (ties <= 1) return false;
+    const uint32_t Cr = rs.item_cnt;
+    uint8_t order[MAX_SETS];
+    for (uint32_t i = 0; i < Cr; i++) order[i] = (uint8_t)i;
+    for (uint32_t i = 1; i < ties && i < Cr; i++) { const uint32_t j = rng_next(rng) % (i + 1); const uint8_t t = order[j]; order[j] = order[i]; order[i] = t; }
+    uint32_t unskipped = 0, kept_cluster_count = 0, nk = 0;
+    for (uint32_t i = 0; i < Cr; i++) {
+        if (unskipped >= P.max_extensions) continue;
+        const uint32_t fl = items[rs.item_off + order[i]].fragment >> 8;
+        bool keep = (fl & 1u) != 0;
+        if (keep && (fl & 2u) && kept_cluster_count >= P.min_extensions) keep = false;
+        else if (keep && (fl & 4u) && kept_cluster_count >= P.min_extensions) keep = false;
+        if (keep) { sel[nk++] = order[i]; kept_cluster_count++; unskipped++; }
+    }
+    S = nk;
+    return true;
+}
+
 struct CandList {
     int32_t score[2 * MAX_CANDS + 32];       // + rescued alignments
     uint8_t slot[2 * MAX_CANDS + 32];
@@ -243,8 +269,10 @@ __device__ inline uint32_t align_sets(const DevIndex& ix, const MapParamsDev& P,
                                       CandList& cl, uint32_t* explored) {
     const int lane = lane_id();
     uint32_t status = GB_ITEM_OK;
-    const uint32_t S = rs.item_cnt;
+    uint32_t S = rs.item_cnt;
     if (S > MAX_SETS) return GB_ITEM_OUT_FULL;
+    uint8_t sel[MAX_SETS];                        // work items of this read in processing order (indices into its item list)
+    if (!deferred_cluster_selection(P, rs, a.items, rng, sel, S)) for (uint32_t s = 0; s < S; s++) sel[s] = (uint8_t)s;
     const uint32_t map_cap = P.mapping_cap, edit_cap = P.edit_cap;
     auto alloc_slot = [&]() -> uint32_t { for (uint32_t i = 0; i < N_SLOTS; i++) if (!slot_used[i]) { slot_used[i] = true; return i; } return 0xffffffffu; };
 #pragma unroll
@@ -252,7 +280,7 @@ __device__ inline uint32_t align_sets(const DevIndex& ix, const MapParamsDev& P,
 
     int set_score[MAX_SETS]; uint8_t set_order[MAX_SETS];
     for (uint32_t s = 0; s < S; s++) {
-        const uint32_t item = rs.item_off + s;
+        const uint32_t item = rs.item_off + sel[s];
         if (a.ev.ext_status[item] != GB_ITEM_OK) return a.ev.ext_status[item];
         set_score[s] = score_extension_group(a.ev.ext + (size_t)item * a.ev.max_ext, a.ev.ext_count[item], L, sc.gap_open, sc.gap_extend);
     }
@@ -279,7 +307,7 @@ __device__ inline uint32_t align_sets(const DevIndex& ix, const MapParamsDev& P,
         if (!process) continue;
         if (!paired && set_score[s] < P.extension_set_min_score) continue;           // single-end only (:912-916)
         unskipped++;
-        const uint32_t item = rs.item_off + s;
+        const uint32_t item = rs.item_off + sel[s];
         const gb_extension* ext = a.ev.ext + (size_t)item * a.ev.max_ext;
         const uint32_t n_ext = a.ev.ext_count[item];
         const uint32_t* path_pool = a.ev.path_pool + (size_t)item * a.ev.path_cap;

@@ -648,6 +648,7 @@ extern "C" int gb_debug_seed_stage(gb_device* d, const gb_map_params* hp, int pa
                 ne += it.seed_cnt;
             }
             o.min_cnt = rs.min_cnt; o.seed_cnt = rs.seed_cnt; o.cluster_cnt = rs.n_clusters; o.item_cnt = rs.item_cnt;
+            o.reserved[0] = rs.pad[0];          // > 1: cluster selection of this read (mate 2) is deferred to the align stage; items = all clusters in comparator order
             nm += rs.min_cnt; ns += rs.seed_cnt; nc += rs.n_clusters; ni += rs.item_cnt;
         }
         return GB_OK;

@@ -127,11 +127,11 @@ __device__ __forceinline__ bool pool_claim(uint32_t* cursor, uint32_t n, uint32_
 
 // dump the cluster table of one read for the stage-parity tests
 __device__ __forceinline__ void dbg_dump_clusters(const SeedPools& pools, const SeedSmem& sm, uint32_t read_idx, uint32_t cbase, uint32_t Cn,
-                                                  const uint8_t* kept, uint32_t n_kept) {
+                                                  const uint8_t* kept, uint32_t n_kept, bool deferred = false) {
     if (!pools.dbg_clusters) return;
     for (uint32_t c = lane_id(); c < Cn; c += 32) {
         DbgCluster dc; dc.score = sm.c_score[cbase + c]; dc.coverage = sm.c_cov[cbase + c]; dc.first_seed = sm.c_label[cbase + c];
-        dc.fragment = sm.c_frag[cbase + c]; dc.kept_rank = 0xffffffffu; dc.valid = 1;
+        dc.fragment = sm.c_frag[cbase + c]; dc.kept_rank = 0xffffffffu; dc.valid = deferred ? 2u : 1u;
         for (uint32_t t = 0; t < n_kept; t++) if (kept[t] == c) dc.kept_rank = t;
         pools.dbg_clusters[(size_t)read_idx * MAX_CLUSTERS + c] = dc;
     }
@@ -684,7 +684,7 @@ __device__ __forceinline__ uint32_t collect_clusters(const SeedSmem& sm, const C
 // Emit the work items of one read for the kept clusters kept[0..n_kept) (table indices cbase + c).
 __device__ __forceinline__ uint32_t emit_items(const DevIndex& ix, const SeedSmem& sm, const SeedPools& pools, const DevSeed* seeds, uint32_t H,
                                                const DevMinimizer* mins, uint32_t read_idx, const uint8_t* kept, uint32_t n_kept, uint32_t cbase,
-                                               uint32_t& item_off_out) {
+                                               uint32_t& item_off_out, const uint8_t* cflags = nullptr) {
     const int lane = lane_id();
     item_off_out = 0;
     if (n_kept == 0) return GB_ITEM_OK;
@@ -713,7 +713,8 @@ __device__ __forceinline__ uint32_t emit_items(const DevIndex& ix, const SeedSme
             wpos += __popc(bal);
         }
         if (lane == 0) {
-            DevItem it; it.read = read_idx; it.seed_off = eoff; it.seed_cnt = cnt; it.fragment = sm.c_frag[cbase + c];
+            DevItem it; it.read = read_idx; it.seed_off = eoff; it.seed_cnt = cnt;
+            it.fragment = sm.c_frag[cbase + c] | (cflags ? (uint32_t)cflags[c] << 8 : 0u);         // deferred selection flags, see cluster_phase_pe
 #pragma unroll
             for (uint32_t x = 0; x < PRESENT_WORDS; x++) it.present[x] = sm.c_present[(cbase + c) * PRESENT_WORDS + x];
             pools.items[item_off + t] = it;
@@ -953,7 +954,8 @@ __device__ __forceinline__ uint32_t cluster_phase_pe(const DevIndex& ix, const M
 
     // ---- fragment ids in order of first appearance; per-fragment bests; better_cluster_count --------------
     uint8_t* kept0 = sm.scratch; uint8_t* kept1 = sm.scratch + sm.Cc;
-    uint32_t n_kept0 = 0, n_kept1 = 0;
+    uint8_t* cflags1 = sm.scratch + 2 * sm.Cc;                   // [Cc <= Mc] keep-decision flags of read 2's clusters (deferred selection)
+    uint32_t n_kept0 = 0, n_kept1 = 0, defer_ties = 0;
     uint32_t status = GB_ITEM_OK;
     uint32_t n_frag = 0;
     if (lane == 0) {
@@ -1028,10 +1030,29 @@ __device__ __forceinline__ uint32_t cluster_phase_pe(const DevIndex& ix, const M
                 for (uint32_t c = 0; c < Cr; c++) { uint32_t j = c; while (j > 0 && comes_before(c, order[j - 1])) { order[j] = order[j - 1]; j--; } order[j] = (uint8_t)c; }
                 uint32_t ties = 0;
                 while (ties < Cr && !comes_before(order[0], order[ties])) ties++;
+                uint8_t* kept = r == 0 ? kept0 : kept1;
+                if (r == 1 && ties > 1) {
+                    // The reference draws the tie shuffle of read 2's clusters from the pair's LazyRNG only AFTER read 1's
+                    // extension sets and tails have drawn theirs (the per-read loop, :1723-2043).  The draws of that stage
+                    // are not known here, so the shuffle and the order-dependent keep loop move to the align stage: every
+                    // cluster becomes a work item, in comparator order, carrying the order-independent inputs of the keep
+                    // decision as flags (bit 0 eligible, bit 1 below the coverage cutoff, bit 2 below the score cutoff).
+                    for (uint32_t i = 0; i < Cr; i++) {
+                        const uint32_t c = order[i];
+                        const uint32_t f = sm.c_frag[cb + c];
+                        const double cov = sm.c_cov[cb + c], sc = sm.c_score[cb + c];
+                        uint8_t fl = 0;
+                        if (!found_paired_cluster || has_pair[f] || (cov == best_cov && sc == best_cov_score)) fl |= 1;
+                        if (P.cluster_coverage_threshold != 0 && cov < cluster_coverage_cutoff) fl |= 2;
+                        if (P.cluster_score_threshold != 0 && sc < cluster_score_cutoff) fl |= 4;
+                        cflags1[c] = fl; kept[i] = (uint8_t)c;
+                    }
+                    n_kept1 = Cr; defer_ties = ties;
+                    continue;
+                }
                 for (uint32_t i = 1; i < ties; i++) { const uint32_t j = rng_next(rng) % (i + 1); const uint8_t t = order[j]; order[j] = order[i]; order[i] = t; }
                 // process_until_threshold_c with threshold 0: everything is "good enough", max_extensions caps
                 uint32_t unskipped = 0, kept_cluster_count = 0, nk = 0;
-                uint8_t* kept = r == 0 ? kept0 : kept1;
                 for (uint32_t i = 0; i < Cr; i++) {
                     const uint32_t c = order[i];
                     if (unskipped >= P.max_extensions) continue;
@@ -1050,17 +1071,19 @@ __device__ __forceinline__ uint32_t cluster_phase_pe(const DevIndex& ix, const M
         }
     }
     status = __shfl_sync(FULL, status, 0);
-    n_kept0 = __shfl_sync(FULL, n_kept0, 0); n_kept1 = __shfl_sync(FULL, n_kept1, 0);
+    n_kept0 = __shfl_sync(FULL, n_kept0, 0); n_kept1 = __shfl_sync(FULL, n_kept1, 0); defer_ties = __shfl_sync(FULL, defer_ties, 0);
     rng.state = __shfl_sync(FULL, rng.state, 0); rng.inited = __shfl_sync(FULL, rng.inited, 0);
     n_fragments_out = __shfl_sync(FULL, n_frag, 0);
+    rs1.pad[0] = defer_ties;
     __syncwarp();
     if (status != GB_ITEM_OK) return status;
 #pragma unroll 1
     for (uint32_t r = 0; r < 2; r++) {
         uint32_t item_off = 0;
         const uint32_t nk = r ? n_kept1 : n_kept0;
-        dbg_dump_clusters(pools, sm, read_idx0 + r, r * sm.Cc, r ? Cn[1] : Cn[0], r ? kept1 : kept0, nk);
-        const uint32_t st = emit_items(ix, sm, pools, r ? s1 : s0, r ? H1 : H0, r ? m1 : m0, read_idx0 + r, r ? kept1 : kept0, nk, r * sm.Cc, item_off);
+        dbg_dump_clusters(pools, sm, read_idx0 + r, r * sm.Cc, r ? Cn[1] : Cn[0], r ? kept1 : kept0, nk, r && defer_ties);
+        const uint32_t st = emit_items(ix, sm, pools, r ? s1 : s0, r ? H1 : H0, r ? m1 : m0, read_idx0 + r, r ? kept1 : kept0, nk, r * sm.Cc, item_off,
+                                       r && defer_ties ? cflags1 : nullptr);
         if (st != GB_ITEM_OK) return st;
         if (r) { rs1.item_off = item_off; rs1.item_cnt = nk; } else { rs0.item_off = item_off; rs0.item_cnt = nk; }
     }
