@@ -442,6 +442,9 @@ int gb_device_set_stream(gb_device* dev, void* cuda_stream);
 int gb_device_synchronize(gb_device* dev);
 /* Device time of the four stages of the last mapping call (seed+cluster, extend, align, compact), ms. */
 int gb_stage_times(gb_device* dev, float* ms4);
+/* Device time of every kernel of the last mapping call (its last chunk), in launch order: names[i * 48 ..] (NUL
+ * terminated) and ms[i]; at most cap entries, *n receives the count.  CUDA events recorded between the launches. */
+int gb_kernel_times(gb_device* dev, uint32_t cap, char* names, float* ms, uint32_t* n);
 
 /* ------------------------------------------------------------------------------------
  * B3: Aligner::align_pinned(alignment, graph, pin_left = true, xdrop = true, max_gap),

@@ -38,6 +38,7 @@ def _sources():
 
 def _digest() -> str:
     h = hashlib.sha256()
+    h.update(os.environ.get("GB_TILE_DEBUG", "").encode())
     for p in sorted(list(CSRC.glob("*")) + [ROOT / "include" / "giraffe_b200.h", Path(__file__)]):
         if p.is_file():
             h.update(p.name.encode())
@@ -68,11 +69,13 @@ def build(force: bool = False, verbose: bool = False) -> Path:
         base += ["-ccbin", "/usr/bin/g++"]
     if verbose:
         base += ["-Xptxas", "-v"]
+    if os.environ.get("GB_TILE_DEBUG"):
+        base += ["-DGB_TILE_DEBUG"]
 
     def compile_one(src: Path):
         obj = objdir / (src.name + ".o")
         stamp = objdir / (src.name + ".stamp")
-        want = hashlib.sha256(src.read_bytes() + hd.encode()).hexdigest()
+        want = hashlib.sha256(src.read_bytes() + hd.encode() + os.environ.get("GB_TILE_DEBUG", "").encode()).hexdigest()
         if not force and not verbose and obj.exists() and stamp.exists() and stamp.read_text() == want:
             return obj, None
         res = subprocess.run(base + ["-c", "-o", str(obj), str(src)], capture_output=True, text=True)

@@ -9,6 +9,7 @@
 #pragma once
 #include "map_state.cuh"
 #include "tail.cuh"
+#include "xdrop_tile.cuh"
 
 namespace gb {
 
@@ -177,7 +178,8 @@ __device__ inline int32_t flank_penalty(uint32_t length, const Pareto* f, uint32
 // get_best_alignment_against_any_tree, minimizer_mapper.cpp:5626-5743.
 __device__ inline int32_t align_tail(const DevIndex& ix, const MapParamsDev& P, const DevScores& sc, const TailWs& ws, DpSmem dps,
                                      const gb_extension& e, const uint32_t* path_pool, const uint8_t* read, uint32_t L,
-                                     bool left_tail, uint8_t* qbuf, DevRng& rng, PathBuf& res, PathBuf& scratch, uint32_t& status) {
+                                     bool left_tail, uint8_t* qbuf, DevRng& rng, PathBuf& res, PathBuf& scratch, uint32_t& status,
+                                     const TailLookup& tl) {
     const int lane = lane_id();
     uint32_t from_node, from_offset, tail_length; int32_t lo, hi;
     const uint32_t first = path_pool[e.path_off], last = path_pool[e.path_off + e.path_len - 1];
@@ -199,6 +201,38 @@ __device__ inline int32_t align_tail(const DevIndex& ix, const MapParamsDev& P, 
     }
     pb_reset(res);
     if (tail_length == 0) return 0;
+    // ---- planned tail: its DPs already ran in xdrop_tile_kernel; pick the winner among the trees in the same order, with
+    // the same LazyRNG draws on ties, as the in-place loop below (get_best_alignment_against_any_tree, :5626-5743)
+    if (tl.pv) {
+        const TailPlanEntry* pe = nullptr;
+        for (uint32_t x = 0; x < tl.count; x++) if (tl.pv->entries[tl.base + x].key == tl.key) { pe = tl.pv->entries + tl.base + x; break; }
+        if (pe) {
+            int32_t best_score = 0;
+            if (lane == 0) { pb_add_mapping(res, default_node, default_offset); pb_add_edit(res, edit_word(GB_EDIT_INS, tail_length, 0)); }
+            __syncwarp();
+            res.n_maps = 1; res.n_edits = 1;
+            for (uint32_t t = 0; t < pe->n_trees; t++) {
+                const uint32_t ti = pe->first_tile + t;
+                if (tl.pv->tile_off[ti] == TILE_REFUSED) continue;            // subgraph too large for max_dozeu_cells (:5694-5701)
+                const TileResult tr = tl.pv->results[ti];
+                if (tr.status != GB_TILE_ST_OK) { status = GB_ITEM_OUT_FULL; return 0; }
+                bool beats = false;
+                if (tr.score > best_score) beats = true;
+                else if (tr.score == best_score) beats = (rng_next(rng) % 2) != 0;
+                if (beats) {
+                    best_score = tr.score;
+                    if (tr.n_maps > res.map_cap || tr.n_edits > res.edit_cap) { status = GB_ITEM_OUT_FULL; return 0; }
+                    const gb_mapping* gm = reinterpret_cast<const gb_mapping*>(tl.pv->path_pool + tr.path_off);
+                    const uint32_t* gedits = tl.pv->path_pool + tr.path_off + 2 * tr.n_maps;
+                    for (uint32_t i = lane; i < tr.n_maps; i += 32) res.maps[i] = gm[i];
+                    for (uint32_t i = lane; i < tr.n_edits; i += 32) res.edits[i] = gedits[i];
+                    __syncwarp();
+                    res.n_maps = tr.n_maps; res.n_edits = tr.n_edits; res.overflow = false;
+                }
+            }
+            return best_score;
+        }
+    }
     const uint32_t gap = longest_detectable_gap(sc, L, tail_length);
     // query: the tail itself (right tail) or its reverse complement (left tail)
     for (uint32_t i = lane; i < tail_length; i += 32)

@@ -21,6 +21,8 @@ struct AlignArgs {
     // mate rescue (max_rescue_attempts != 0): per-warp workspace; pairs found to need it by the plain kernel
     uint8_t* rescue_base; size_t rescue_stride;
     uint32_t* rescue_list; uint32_t* rescue_count;
+    // tails whose DPs ran in xdrop_tile_kernel (entries == nullptr: none, every tail is aligned in place)
+    PlanView plan;
 };
 
 constexpr uint32_t N_SLOTS = 2 * MAX_CANDS + 8 + 32;   // candidate path slots per warp (both mates of a pair, + rescued alignments)
@@ -266,10 +268,12 @@ struct CandList {
 __device__ inline uint32_t align_sets(const DevIndex& ix, const MapParamsDev& P, const DevScores& sc, const ReadState& rs,
                                       const AlignArgs& a, const uint8_t* sread, uint32_t L, const TailWs& ws, DpSmem dps, uint8_t* qbuf,
                                       uint8_t* cand_base, bool* slot_used, DevRng& rng, bool paired, uint32_t read_num,
-                                      CandList& cl, uint32_t* explored) {
+                                      CandList& cl, uint32_t* explored, uint32_t unit) {
     const int lane = lane_id();
     uint32_t status = GB_ITEM_OK;
     uint32_t S = rs.item_cnt;
+    TailLookup tl; tl.pv = nullptr; tl.base = tl.count = tl.key = 0;
+    if (a.plan.entries) { const uint32_t pb0 = a.plan.unit_base[unit]; if (pb0 != 0xffffffffu) { tl.pv = &a.plan; tl.base = pb0; tl.count = a.plan.unit_count[unit]; } }
     if (S > MAX_SETS) return GB_ITEM_OUT_FULL;
     uint8_t sel[MAX_SETS];                        // work items of this read in processing order (indices into its item list)
     if (!deferred_cluster_selection(P, rs, a.items, rng, sel, S)) for (uint32_t s = 0; s < S; s++) sel[s] = (uint8_t)s;
@@ -387,7 +391,8 @@ __device__ inline uint32_t align_sets(const DevIndex& ix, const MapParamsDev& P,
                     const bool left_tail = side == 0;
                     if (e.flags & (left_tail ? GB_EXT_LEFT_FULL : GB_EXT_RIGHT_FULL)) continue;
                     PathBuf* res = left_tail ? &res_left : &res_right;
-                    const int32_t tail_score = align_tail(ix, P, sc, ws, dps, e, path_pool, sread, L, left_tail, qbuf, rng, *res, scratch, status);
+                    tl.key = tail_key(sel[s], read_num, eo[xi], left_tail);
+                    const int32_t tail_score = align_tail(ix, P, sc, ws, dps, e, path_pool, sread, L, left_tail, qbuf, rng, *res, scratch, status, tl);
                     if (left_tail) left_score = tail_score; else right_score = tail_score;
                 }
                 if (status != GB_ITEM_OK) break;
@@ -686,7 +691,7 @@ __device__ inline uint32_t align_read(const DevIndex& ix, const MapParamsDev& P,
     for (uint32_t i = 0; i < N_SLOTS; i++) slot_used[i] = false;
     CandList cl; cl.n = 0;
     uint32_t explored[PRESENT_WORDS];
-    uint32_t status = align_sets(ix, P, sc, rs, a, sread, L, ws, dps, qbuf, cand_base, slot_used, rng, false, 0, cl, explored);
+    uint32_t status = align_sets(ix, P, sc, rs, a, sread, L, ws, dps, qbuf, cand_base, slot_used, rng, false, 0, cl, explored, read_idx);
     if (status != GB_ITEM_OK) return status;
     return finalize_se(ix, P, rs, a, cl, explored, rng, sread, qual, L, read_idx, dps, cand_base, out, out_maps, out_edits);
 }

@@ -109,6 +109,7 @@ extern "C" int gb_device_create(const gb_flat_index* ix, int device_ordinal, gb_
         const unsigned long v = std::strtoul(env, nullptr, 10);
         if (v >= 2 && v <= (1ul << 24)) d->map_chunk = (uint32_t)(v & ~1ul);
     }
+    if (const char* env = std::getenv("GIRAFFE_B200_TILES")) d->use_tiles = std::atoi(env) != 0;
     if (const char* env = std::getenv("GIRAFFE_B200_POOL_SCALE")) {
         const double v = std::strtod(env, nullptr);
         if (v > 0.0 && v <= 1024.0) d->pool_scale = v;

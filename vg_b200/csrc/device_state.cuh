@@ -4,6 +4,7 @@
 #include "device_index.cuh"
 #include "extend.cuh"
 #include "map_state.cuh"
+#include "xdrop_tile.cuh"
 namespace gb { struct DbgCluster; }
 
 #include <cuda_runtime.h>
@@ -119,6 +120,25 @@ struct gb_device {
     double pool_scale = 1.0;               // intermediate pools = per-read averages x this; doubled when a chunk overflows (GIRAFFE_B200_POOL_SCALE)
     uint32_t pool_reruns = 0;              // chunks redone because of it
     gb::DbgCluster* dbg_clusters = nullptr; bool debug_stop_after_seed = false;     // gb_debug_seed_stage
+    // tail plan + DP tiles (xdrop_tile.cuh); GIRAFFE_B200_TILES=0 keeps every tail DP in the align kernels (int32 sweep)
+    bool use_tiles = true; uint32_t last_tile_problems = 0;
+    gb::DevBuf<gb::TailPlanEntry> pl_entries;
+    gb::DevBuf<uint32_t> pl_unit_base, pl_unit_count, pl_tile_off, pl_lists, pl_paths;
+    gb::DevBuf<uint8_t> pl_tiles, ws_tile;
+    gb::DevBuf<gb::TileResult> pl_results;
+    gb::DevBuf<uint64_t> pl_stats;
+    // per-kernel device times of the last map_device call (events between the launches)
+    static constexpr int KT_MAX = 24;
+    cudaEvent_t kt_ev[KT_MAX] = {}; const char* kt_name[KT_MAX] = {}; int kt_n = 0;
+    void kt_reset() { kt_n = 0; }
+    int kt_mark(const char* name) {
+        if (kt_n >= KT_MAX) return GB_OK;
+        if (!kt_ev[kt_n]) { cudaError_t e = cudaEventCreate(&kt_ev[kt_n]); if (e != cudaSuccess) return gb::fail_cuda(e, "cudaEventCreate"); }
+        cudaError_t e = cudaEventRecord(kt_ev[kt_n], stream);
+        if (e != cudaSuccess) return gb::fail_cuda(e, "cudaEventRecord");
+        kt_name[kt_n++] = name;
+        return GB_OK;
+    }
     gb::DevBuf<uint64_t> c_run;            // running mapping / edit totals of a host-buffer call
     uint32_t map_chunk = 1u << 20;         // reads per chunk; GIRAFFE_B200_MAP_CHUNK overrides
     void release_all() {
@@ -129,5 +149,6 @@ struct gb_device {
         p_ext_status.release(); p_ext.release(); ws_tail.release(); ws_cand.release(); ws_rescue.release(); w_reads.release(); w_quals.release(); p_pairs.release(); p_slow.release(); p_rescue.release(); p_retry.release();
         pad_maps.release(); pad_edits.release(); c_map_off.release(); c_edit_off.release(); c_totals.release(); c_tmp.release();
         io[0].release(); io[1].release(); c_run.release();
+        pl_entries.release(); pl_unit_base.release(); pl_unit_count.release(); pl_tile_off.release(); pl_lists.release(); pl_paths.release(); pl_tiles.release(); ws_tile.release(); pl_results.release(); pl_stats.release();
     }
 };

@@ -138,6 +138,7 @@ align_kernel(DevIndex ix, MapParamsDev P, DevScores sc, MapBatch b, AlignArgs a)
 #include "rescue.cuh"
 #include "map_paired.cuh"
 #include "align_fast.cuh"
+#include "tail_plan.cuh"
 #include "compact.cuh"
 
 // AlignmentScorer::recover_log_base (alignment_scorer.cpp:30-99), gc 0.5, tol 1e-12.
@@ -173,6 +174,35 @@ extern "C" void gb_map_params_default(gb_map_params* p) {
 }
 
 namespace gb {
+
+// The three size classes of xdrop_tile_kernel over their work lists (lists[c * list_cap ..], counts on the device).
+template <int R>
+static int launch_tile_class(gb_device* d, int cls, const uint8_t* tiles, const uint32_t* tile_off, const uint32_t* lists, size_t list_cap,
+                             const uint32_t* list_count, uint32_t* work, TileResult* results, uint32_t* paths, uint32_t path_cap, uint32_t* path_cursor) {
+    const size_t smem = tile_smem_per_warp<R>() * TILE_WARPS;
+    GB_CUDA(cudaFuncSetAttribute(xdrop_tile_kernel<R>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    int bps = 0;
+    GB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bps, xdrop_tile_kernel<R>, TILE_WARPS * 32, smem));
+    bps = std::max(1, std::min(bps, 2));
+    const uint32_t grid = (uint32_t)(d->n_sms * bps);
+    int rc;
+    if ((rc = d->ws_tile.reserve(tile_ws_bytes() * (size_t)d->n_sms * 2 * TILE_WARPS))) return rc;
+    TileBatch tb;
+    tb.tiles = tiles; tb.tile_off = tile_off; tb.list = lists + (size_t)cls * list_cap; tb.list_count = list_count + cls; tb.list_cap = (uint32_t)list_cap;
+    tb.work_counter = work + cls; tb.results = results; tb.path_pool = paths; tb.path_cap = path_cap; tb.path_cursor = path_cursor;
+    tb.ws_base = d->ws_tile.ptr; tb.ws_stride = tile_ws_bytes();
+    xdrop_tile_kernel<R><<<grid, TILE_WARPS * 32, smem, d->stream>>>(d->sc, tb);
+    d->launches++;
+    GB_CUDA(cudaGetLastError());
+    return d->kt_mark(R == 4 ? "xdrop_tile_kernel<4>" : (R == 8 ? "xdrop_tile_kernel<8>" : "xdrop_tile_kernel<16>"));
+}
+int launch_tile_kernels(gb_device* d, const uint8_t* tiles, const uint32_t* tile_off, const uint32_t* lists, size_t list_cap,
+                        const uint32_t* list_count, uint32_t* work, TileResult* results, uint32_t* paths, uint32_t path_cap, uint32_t* path_cursor) {
+    int rc;
+    if ((rc = launch_tile_class<4>(d, 0, tiles, tile_off, lists, list_cap, list_count, work, results, paths, path_cap, path_cursor))) return rc;
+    if ((rc = launch_tile_class<8>(d, 1, tiles, tile_off, lists, list_cap, list_count, work, results, paths, path_cap, path_cursor))) return rc;
+    return launch_tile_class<16>(d, 2, tiles, tile_off, lists, list_cap, list_count, work, results, paths, path_cap, path_cursor);
+}
 
 // Device-resident mapping of a batch whose reads are already in HBM.
 int map_device(gb_device* d, const gb_map_params* hp, uint32_t n_reads, const uint8_t* d_reads, const uint8_t* d_quals,
@@ -237,9 +267,12 @@ int map_device(gb_device* d, const gb_map_params* hp, uint32_t n_reads, const ui
     if ((rc = d->p_seeds.reserve(seed_cap))) return rc;
     if ((rc = d->p_items.reserve(item_cap))) return rc;
     if ((rc = d->p_ext_seeds.reserve(ext_cap))) return rc;
-    if ((rc = d->p_cursors.reserve(16))) return rc;
-    GB_CUDA(cudaMemsetAsync(d->p_cursors.ptr, 0, 16 * sizeof(uint32_t), d->stream));
-    uint32_t* cur = d->p_cursors.ptr;   // 0 seed work, 1 min, 2 seed, 3 item, 4 ext, 5 extend work, 6 align work
+    if ((rc = d->p_cursors.reserve(48))) return rc;
+    GB_CUDA(cudaMemsetAsync(d->p_cursors.ptr, 0, 48 * sizeof(uint32_t), d->stream));
+    // 0 seed work, 1 min, 2 seed, 3 item, 4 ext, 5 extend work, 6 align work, 7 slow count, 8-10 seeding retry, 11-12 rescue, 13 pool overflow,
+    // 14 plan work, 16 tiles, 17 tile bytes / 16, 18-20 tile list counts, 21-23 tile work, 24 result path words
+    uint32_t* cur = d->p_cursors.ptr;
+    d->kt_reset();
 
     int32_t fragment_limit = 0;
     if (paired) {
@@ -267,6 +300,7 @@ int map_device(gb_device* d, const gb_map_params* hp, uint32_t n_reads, const ui
     pools.ext_seeds = d->p_ext_seeds.ptr; pools.ext_cap = (uint32_t)ext_cap; pools.ext_cursor = cur + 4;
 
     GB_CUDA(cudaEventRecord(d->ev_stage[0], d->stream));
+    if ((rc = d->kt_mark("start"))) return rc;
     // ---- K1: a first pass with small shared tables (8 blocks per SM), then the units that did not
     // fit (many minimizers or clusters) once more at the maximum table sizes ----
     {
@@ -298,6 +332,7 @@ int map_device(gb_device* d, const gb_map_params* hp, uint32_t n_reads, const ui
             else seed_kernel<<<grid, warps * 32, smem, d->stream>>>(d->ix, P, bp, pools);
             d->launches++;
             GB_CUDA(cudaGetLastError());
+            if ((rc = d->kt_mark(pass == 0 ? (paired ? "seed_kernel_pe" : "seed_kernel") : "seed_kernel(retry tables)"))) return rc;
         }
     }
     GB_CUDA(cudaEventRecord(d->ev_stage[1], d->stream));
@@ -316,6 +351,7 @@ int map_device(gb_device* d, const gb_map_params* hp, uint32_t n_reads, const ui
         if ((rc = launch_extend_device(d, ep, d_reads, d_read_off, nullptr, d->p_ext_seeds.ptr, nullptr, d->p_items.ptr, cur + 3,
                                        (uint32_t)item_cap, d->p_ext_count.ptr, d->p_ext_status.ptr, d->p_ext.ptr, d->p_path.ptr,
                                        d->p_mism.ptr, Lc))) return rc;
+        if ((rc = d->kt_mark("extend_kernel"))) return rc;
     }
     GB_CUDA(cudaEventRecord(d->ev_stage[2], d->stream));
     // ---- K3 ----
@@ -347,6 +383,7 @@ int map_device(gb_device* d, const gb_map_params* hp, uint32_t n_reads, const ui
         if ((rc = d->ws_tail.reserve(ws_stride * n_warps))) return rc;
         if ((rc = d->ws_cand.reserve(cand_stride * n_warps))) return rc;
         AlignArgs a;
+        a.plan.entries = nullptr; a.plan.unit_base = nullptr; a.plan.unit_count = nullptr; a.plan.tile_off = nullptr; a.plan.results = nullptr; a.plan.path_pool = nullptr;
         a.rescue_base = nullptr; a.rescue_stride = 0;
         if (rescue) {
             a.rescue_stride = (rescue_ws_bytes(Lc) + 255) & ~(size_t)255;
@@ -371,7 +408,35 @@ int map_device(gb_device* d, const gb_map_params* hp, uint32_t n_reads, const ui
         else align_fast_kernel<<<fgrid, 128, 0, d->stream>>>(d->ix, P, d->sc, b3, a, fa);
         d->launches++;
         GB_CUDA(cudaGetLastError());
+        if ((rc = d->kt_mark(paired ? "align_fast_kernel_pe" : "align_fast_kernel"))) return rc;
         a.slow_list = d->p_slow.ptr; a.slow_count = cur + 7;
+        // ---- tails of the slow units: plan (forests -> tiles), then the DP of every tile in its own compact kernel ----
+        if (hp->do_dp && d->use_tiles) {
+            const size_t tile_cap = (size_t)n_reads * 4 + 4096;
+            const size_t unit_cap = std::min<size_t>((size_t)n_reads * 128 + (1u << 20), 0xfffffff0u);
+            const size_t path_cap = std::min<size_t>(tile_cap * 32, 0xfffffff0u);
+            if ((rc = d->pl_entries.reserve((size_t)n_units * PLAN_PER_UNIT)) || (rc = d->pl_unit_base.reserve(n_units)) || (rc = d->pl_unit_count.reserve(n_units)) ||
+                (rc = d->pl_tiles.reserve(unit_cap * 16)) || (rc = d->pl_tile_off.reserve(tile_cap)) || (rc = d->pl_results.reserve(tile_cap)) ||
+                (rc = d->pl_lists.reserve(3 * tile_cap)) || (rc = d->pl_paths.reserve(path_cap)) || (rc = d->pl_stats.reserve(4))) return rc;
+            GB_CUDA(cudaMemsetAsync(d->pl_stats.ptr, 0, 4 * sizeof(uint64_t), d->stream));
+            PlanPools pp;
+            pp.entries = d->pl_entries.ptr; pp.unit_base = d->pl_unit_base.ptr; pp.unit_count = d->pl_unit_count.ptr;
+            pp.tiles = d->pl_tiles.ptr; pp.tile_units_cap = (uint32_t)unit_cap; pp.tile_units_cursor = cur + 17;
+            pp.tile_off = d->pl_tile_off.ptr; pp.tile_cap = (uint32_t)tile_cap; pp.tile_cursor = cur + 16;
+            pp.results = d->pl_results.ptr;
+            for (int c = 0; c < 3; c++) pp.lists[c] = d->pl_lists.ptr + (size_t)c * tile_cap;
+            pp.list_count = cur + 18; pp.stats = d->pl_stats.ptr;
+            MapBatch bpl = b3; bpl.work_counter = cur + 14;
+            if (paired) tail_plan_kernel<true><<<grid_plain, ALIGN_WARPS * 32, 0, d->stream>>>(d->ix, P, d->sc, bpl, a, pp);
+            else tail_plan_kernel<false><<<grid_plain, ALIGN_WARPS * 32, 0, d->stream>>>(d->ix, P, d->sc, bpl, a, pp);
+            d->launches++;
+            GB_CUDA(cudaGetLastError());
+            if ((rc = d->kt_mark("tail_plan_kernel"))) return rc;
+            if ((rc = launch_tile_kernels(d, d->pl_tiles.ptr, d->pl_tile_off.ptr, d->pl_lists.ptr, tile_cap, cur + 18, cur + 21, d->pl_results.ptr,
+                                          d->pl_paths.ptr, (uint32_t)path_cap, cur + 24))) return rc;
+            a.plan.entries = d->pl_entries.ptr; a.plan.unit_base = d->pl_unit_base.ptr; a.plan.unit_count = d->pl_unit_count.ptr;
+            a.plan.tile_off = d->pl_tile_off.ptr; a.plan.results = d->pl_results.ptr; a.plan.path_pool = d->pl_paths.ptr;
+        }
         if (paired) {
             // the plain kernel takes every listed pair; with rescue enabled it defers the pairs that turn out to have
             // unpaired alignments to a second list, which the (larger, lower-occupancy) rescue instantiation redoes
@@ -380,6 +445,7 @@ int map_device(gb_device* d, const gb_map_params* hp, uint32_t n_reads, const ui
             if (rescue) {
                 d->launches++;
                 GB_CUDA(cudaGetLastError());
+                if ((rc = d->kt_mark("align_kernel_pe"))) return rc;
                 b3.work_counter = cur + 12;
                 a.slow_list = d->p_rescue.ptr; a.slow_count = cur + 11;
                 align_kernel_pe<true><<<grid, ALIGN_WARPS * 32, smem, d->stream>>>(d->ix, P, d->sc, b3, a);
@@ -388,10 +454,12 @@ int map_device(gb_device* d, const gb_map_params* hp, uint32_t n_reads, const ui
         else align_kernel<<<grid, ALIGN_WARPS * 32, smem, d->stream>>>(d->ix, P, d->sc, b3, a);
         d->launches++;
         GB_CUDA(cudaGetLastError());
+        if ((rc = d->kt_mark(!paired ? "align_kernel" : (rescue ? "align_kernel_pe<rescue>" : "align_kernel_pe")))) return rc;
     }
     GB_CUDA(cudaEventRecord(d->ev_stage[3], d->stream));
     if ((rc = compact_outputs(d, n_reads, d_aln, d_maps, d_edits, hp->mapping_cap_per_read, hp->edit_cap_per_read,
                               out_maps, out_map_cap, out_edits, out_edit_cap, d_run_base, read_base, d_totals, d_status))) return rc;
+    if ((rc = d->kt_mark("compact (2 scans + gather)"))) return rc;
     if (d_overflow) GB_CUDA(cudaMemcpyAsync(d_overflow, cur + 13, sizeof(uint32_t), cudaMemcpyDeviceToDevice, d->stream));
     GB_CUDA(cudaEventRecord(d->ev_stage[4], d->stream));
     return GB_OK;
@@ -677,6 +745,21 @@ extern "C" int gb_stage_times(gb_device* d, float* ms4) {
     return GB_OK;
 }
 
+// Device time of every kernel of the last mapping call on this handle (one chunk; CUDA events between the launches).
+extern "C" int gb_kernel_times(gb_device* d, uint32_t cap, char* names, float* ms, uint32_t* n_out) {
+    if (!d || !names || !ms || !n_out) return GB_ERR_ARG;
+    GB_CUDA(cudaSetDevice(d->device));
+    *n_out = 0;
+    if (d->kt_n < 2) return GB_OK;
+    GB_CUDA(cudaEventSynchronize(d->kt_ev[d->kt_n - 1]));
+    for (int i = 1; i < d->kt_n && *n_out < cap; i++) {
+        GB_CUDA(cudaEventElapsedTime(&ms[*n_out], d->kt_ev[i - 1], d->kt_ev[i]));
+        std::strncpy(names + (size_t)*n_out * 48, d->kt_name[i], 47); names[(size_t)*n_out * 48 + 47] = 0;
+        (*n_out)++;
+    }
+    return GB_OK;
+}
+
 // ---------------------------------------------------------------------------------------
 // B3 stage seam: Aligner::align_pinned(xdrop = true), batched over explicit haplotype trees
 // (aligner.cpp:628-686 -> DozeuInterface::align_pinned dozeu_interface.cpp:724-766).
@@ -691,7 +774,25 @@ struct XdropBatch {
     uint32_t map_cap, edit_cap;
     uint8_t* ws_base; size_t ws_stride; uint32_t tb_cells;
     uint32_t* work_counter;
+    const uint8_t* skip;             // [n] 1: the problem runs on xdrop_tile_kernel instead
 };
+
+// results of the tile kernel -> the seam's output arrays
+__global__ void unpack_tile_results_kernel(XdropBatch b, const TileResult* results, const uint32_t* path_pool) {
+    const uint32_t p = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    const int lane = threadIdx.x & 31;
+    if (p >= b.n || !b.skip[p]) return;
+    const TileResult tr = results[p];
+    uint32_t status = tr.status == GB_TILE_ST_OK ? (uint32_t)GB_ITEM_OK : (uint32_t)GB_ITEM_OUT_FULL;
+    if (status == GB_ITEM_OK && (tr.n_maps > b.map_cap || tr.n_edits > b.edit_cap)) status = GB_ITEM_OUT_FULL;
+    if (status == GB_ITEM_OK) {
+        const gb_mapping* gm = reinterpret_cast<const gb_mapping*>(path_pool + tr.path_off);
+        const uint32_t* ge = path_pool + tr.path_off + 2 * tr.n_maps;
+        for (uint32_t i = lane; i < tr.n_maps; i += 32) b.maps[(size_t)p * b.map_cap + i] = gm[i];
+        for (uint32_t i = lane; i < tr.n_edits; i += 32) b.edits[(size_t)p * b.edit_cap + i] = ge[i];
+    }
+    if (lane == 0) { b.score[p] = status == GB_ITEM_OK ? tr.score : 0; b.n_maps[p] = status == GB_ITEM_OK ? tr.n_maps : 0; b.n_edits[p] = status == GB_ITEM_OK ? tr.n_edits : 0; b.status[p] = (uint8_t)status; }
+}
 
 __global__ void __launch_bounds__(ALIGN_WARPS * 32, 4)
 xdrop_kernel(DevIndex ix, DevScores sc, XdropBatch b) {
@@ -710,6 +811,7 @@ xdrop_kernel(DevIndex ix, DevScores sc, XdropBatch b) {
         if (lane == 0) p = atomicAdd(b.work_counter, 1u);
         p = __shfl_sync(FULL, p, 0);
         if (p >= b.n) break;
+        if (b.skip && b.skip[p]) continue;
         const uint64_t t_begin = b.tree_off[p]; const uint32_t nt = (uint32_t)(b.tree_off[p + 1] - t_begin);
         const uint64_t q_begin = b.query_off[p]; const uint32_t m = (uint32_t)(b.query_off[p + 1] - q_begin);
         uint32_t status = GB_ITEM_OK; int32_t score = 0;
@@ -786,10 +888,56 @@ extern "C" int gb_xdrop_pinned_batch(gb_device* d, uint32_t n,
     b.score = d_score.ptr; b.maps = d_maps.ptr; b.edits = d_edits.ptr; b.n_maps = d_nm.ptr; b.n_edits = d_ne.ptr; b.status = d_status.ptr;
     b.map_cap = map_cap; b.edit_cap = edit_cap; b.ws_base = d_ws.ptr; b.ws_stride = ws_stride; b.tb_cells = tb_cells;
     b.work_counter = d_counter.ptr;
+    // ---- problems the int16 tile kernel can hold run there (the production path of the tails); the rest on the int32 sweep ----
+    std::vector<uint8_t> elig(n, 0); std::vector<uint32_t> toff(n, 0);
+    uint64_t units = 0; uint32_t n_elig = 0;
+    if (d->use_tiles) {
+        for (uint32_t i = 0; i < n; i++) {
+            const uint64_t t0 = tree_off[i]; const uint32_t ntree = (uint32_t)(tree_off[i + 1] - t0), m = (uint32_t)(query_off[i + 1] - query_off[i]);
+            if (ntree == 0 || ntree > TILE_MAX_NODES) continue;
+            uint64_t bases = 0; uint32_t max_depth = 0; bool ok = true;
+            std::vector<uint32_t> depth(ntree, 0);
+            for (uint32_t x = 0; x < ntree && ok; x++) {
+                const uint32_t v = tree_node[t0 + x]; const int32_t par = tree_parent[t0 + x];
+                if (v >= d->h_node_len.size() || par >= (int32_t)x) { ok = false; break; }
+                const uint32_t len = d->h_node_len[v];
+                if (par < 0) { if (root_trim[i] >= len) { ok = false; break; } bases += len - root_trim[i]; }
+                else { bases += len; depth[x] = depth[par] + 1; max_depth = std::max(max_depth, depth[x]); }
+            }
+            if (!ok || tree_parent[t0] >= 0) continue;
+            if (!tile_eligible(d->sc, m, std::max(max_gap[i], 1u), ntree, (uint32_t)std::min<uint64_t>(bases, 0xffffffffu), max_depth)) continue;
+            elig[i] = 1; toff[i] = (uint32_t)units; units += tile_bytes(ntree, (uint32_t)bases, m) / 16; n_elig++;
+        }
+    }
+    DevBuf<uint8_t> d_elig, d_tiles; DevBuf<uint32_t> d_tileoff, d_lists, d_tc, d_paths; DevBuf<TileResult> d_res;
     GB_CUDA(cudaEventRecord(d->ev0, d->stream));
-    xdrop_kernel<<<grid, ALIGN_WARPS * 32, smem, d->stream>>>(d->ix, d->sc, b);
-    d->launches++;
-    GB_CUDA(cudaGetLastError());
+    if (n_elig) {
+        const uint32_t path_cap = (uint32_t)std::min<uint64_t>((uint64_t)n * (2 * TILE_MAP_CAP + TILE_EDIT_CAP), 0xfffffff0ull);
+        if ((rc = d_elig.upload(elig.data(), n, d->stream)) || (rc = d_tileoff.upload(toff.data(), n, d->stream)) || (rc = d_tiles.reserve(units * 16 + 16)) ||
+            (rc = d_lists.reserve(3 * (size_t)n)) || (rc = d_tc.reserve(16)) || (rc = d_res.reserve(n)) || (rc = d_paths.reserve(path_cap))) return rc;
+        GB_CUDA(cudaMemsetAsync(d_tc.ptr, 0, 64, d->stream));
+        GB_CUDA(cudaMemsetAsync(d_res.ptr, 0xff, sizeof(TileResult) * (size_t)n, d->stream));
+        PackBatch pk;
+        pk.tree_parent = d_par.ptr; pk.tree_node = d_node.ptr; pk.tree_off = d_toff.ptr; pk.root_trim = d_trim.ptr;
+        pk.query = d_q.ptr; pk.query_off = d_qoff.ptr; pk.max_gap = d_gap.ptr; pk.n = n; pk.tiles = d_tiles.ptr; pk.tile_off = d_tileoff.ptr;
+        for (int c = 0; c < 3; c++) pk.lists[c] = d_lists.ptr + (size_t)c * n;
+        pk.list_count = d_tc.ptr; pk.eligible = d_elig.ptr;
+        pack_tiles_kernel<<<(n + 7) / 8, 256, 0, d->stream>>>(d->ix, d->sc, pk);
+        d->launches++;
+        GB_CUDA(cudaGetLastError());
+        d->kt_reset();
+        if ((rc = launch_tile_kernels(d, d_tiles.ptr, d_tileoff.ptr, d_lists.ptr, n, d_tc.ptr, d_tc.ptr + 4, d_res.ptr, d_paths.ptr, path_cap, d_tc.ptr + 8))) return rc;
+        b.skip = d_elig.ptr;
+        unpack_tile_results_kernel<<<(n + 7) / 8, 256, 0, d->stream>>>(b, d_res.ptr, d_paths.ptr);
+        d->launches++;
+        GB_CUDA(cudaGetLastError());
+    } else b.skip = nullptr;
+    if (n_elig < n) {
+        xdrop_kernel<<<grid, ALIGN_WARPS * 32, smem, d->stream>>>(d->ix, d->sc, b);
+        d->launches++;
+        GB_CUDA(cudaGetLastError());
+    }
+    d->last_tile_problems = n_elig;
     GB_CUDA(cudaEventRecord(d->ev1, d->stream));
     GB_CUDA(cudaMemcpyAsync(score, d_score.ptr, 4 * (size_t)n, cudaMemcpyDeviceToHost, d->stream));
     GB_CUDA(cudaMemcpyAsync(n_maps, d_nm.ptr, 4 * (size_t)n, cudaMemcpyDeviceToHost, d->stream));

@@ -153,7 +153,7 @@ align_kernel_pe(DevIndex ix, MapParamsDev P, DevScores sc, MapBatch b, AlignArgs
             uint32_t explored[2][PRESENT_WORDS];
 #pragma unroll 1
             for (uint32_t r = 0; r < 2 && status == GB_ITEM_OK; r++)          // one copy of align_sets per kernel (instruction cache)
-                status = align_sets(ix, P, sc, rs[r], a, sread[r], L[r], ws, dps, qbuf, cand_base, slot_used, rng, true, r, cl, explored[r]);
+                status = align_sets(ix, P, sc, rs[r], a, sread[r], L[r], ws, dps, qbuf, cand_base, slot_used, rng, true, r, cl, explored[r], p);
             if (status == GB_ITEM_OK) {
                 const uint8_t* sr[2] = {sread[0], sread[1]};
                 const uint8_t* sq[2] = {b.quals ? squal[0] : nullptr, b.quals ? squal[1] : nullptr};
