@@ -405,6 +405,9 @@ def main():
     clocks = sampler.stop()
     launches = (dev.launches() - launches0) // max(args.steps, 1)
     last_stage = np.array(dev.stage_times())
+    kernel_times = dev.kernel_times()                  # every kernel of the last chunk, CUDA events between the launches
+    plan_stats = dev.plan_stats()
+    pool_overflow = dev.pool_overflow()                # the device entry cannot rerun a batch: an overflow would void the numbers
     if world > 1:
         tms = torch.tensor([dev_ms], device=device)
         dist.all_reduce(tms, op=dist.ReduceOp.MAX)
@@ -499,23 +502,26 @@ def main():
     peak = float(peaks.get("hbm_gbs", 6650.0))
     peak_src = "measured (MEASURED_PEAKS.json hbm_gbs)" if "hbm_gbs" in peaks else "fallback 6.65 TB/s (B200_PROFILING.md)"
     names = ["seed_kernel_pe", "extend_kernel", "align_kernel_pe", "compact"]
-    # The live timers are per stage; the align stage is three launches (thread-per-pair fast path, warp-per-pair
-    # kernel, its rescue instantiation).  To name the dominant KERNEL, the align stage is split by the per-kernel
-    # times of the committed ncu launch list of this command (profiles/ncu_summary_r01.json); the other stages are
-    # one kernel each (the second seeding launch only sees the few units that overflowed the small tables).
-    kernel_ms, align_split = split_align_stage(last_stage)
-    dom = int(np.argmax(kernel_ms))
+    # Per-kernel device times are measured live by the library (CUDA events between the launches of the last chunk,
+    # gb_kernel_times); the dominant KERNEL is the longest of them.  Its algorithmic bytes are the term of B(read) its
+    # stage touches (the align-stage kernels share one term: qualities, tail subgraphs, the output record).
+    kdict = {}
+    for kname, kms in kernel_times:
+        kdict[kname] = kdict.get(kname, 0.0) + kms
+    dom_name = max(kdict, key=kdict.get)
+    term = "seed_kernel_pe" if dom_name.startswith("seed_kernel") else ("extend_kernel" if dom_name.startswith("extend") else ("compact" if dom_name.startswith("compact") else "align_kernel_pe"))
     chunk_reads = min(CHUNK, n_reads) if n_reads % CHUNK == 0 or n_reads < CHUNK else n_reads - (n_chunks - 1) * CHUNK
-    dom_ms = float(kernel_ms[dom])
-    # the dominant kernel's share of B(read) (its terms sum to B over the three kernels), times the reads of one launch
-    B_dom = float(per_kernel[names[dom]])
+    dom_ms = float(kdict[dom_name])
+    B_dom = float(per_kernel[term])
     achieved = B_dom * chunk_reads / (dom_ms / 1e3) / 1e9 if dom_ms > 0 else None
-    traffic = None
+    # dram__bytes_read.sum + dram__bytes_write.sum of that kernel's launch from the committed ncu --set full capture of THIS
+    # command (profiles/ncu_summary_r02.json, keyed by kernel name and stamped with the commit it was taken at)
+    traffic, traffic_commit = None, None
     try:
-        prof = json.loads((ROOT / "profiles" / "ncu_summary_r01.json").read_text())
-        full = prof["kernels"][names[dom]]["ncu_full"]
-        # dram__bytes_read.sum + dram__bytes_write.sum of one launch under ncu --set full, scaled to this launch's reads
-        traffic = float(full["dram_bytes_per_launch"]) * chunk_reads / float(prof["reads_per_call"])
+        prof = json.loads((ROOT / "profiles" / "ncu_summary_r02.json").read_text())
+        full = prof["kernels"][dom_name]
+        traffic = float(full["dram_bytes_per_launch"]) * chunk_reads / float(prof["reads_per_launch"])
+        traffic_commit = prof.get("commit")
     except Exception:
         pass
 
@@ -537,14 +543,15 @@ def main():
         "gpu_launches": int(launches),
         "e2e": {"value": e2e_value, "unit": "reads/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
                 "ms_per_step": e2e_ms},
-        "roofline": {"bound": "hbm", "kernel": names[dom], "achieved": achieved, "peak": peak, "unit": "GB/s",
-                     "frac": (achieved / peak) if achieved else None, "traffic": traffic,
+        "roofline": {"bound": "hbm", "kernel": dom_name, "achieved": achieved, "peak": peak, "unit": "GB/s",
+                     "frac": (achieved / peak) if achieved else None, "traffic": traffic, "traffic_profile_commit": traffic_commit,
+                     "kernel_ms_last_chunk": {k: round(v, 4) for k, v in kdict.items()},
+                     "tail_plan": plan_stats, "pool_overflow": pool_overflow,
                      "algorithmic_bytes_per_read": B, "algorithmic_bytes_per_read_this_kernel": B_dom,
                      "per_kernel_bytes_per_read": {k: round(float(v), 1) for k, v in per_kernel.items()},
                      "terms": terms, "reads_per_launch": chunk_reads,
                      "launch_ms": dom_ms, "peak_source": peak_src,
-                     "stage_ms_last_chunk": {n: float(x) for n, x in zip(names, last_stage)},
-                     "align_stage_split": align_split},
+                     "stage_ms_last_chunk": {n: float(x) for n, x in zip(names, last_stage)}},
         "cpu_baseline": {"value": cpu_rate, "unit": "reads/s", "cores": threads, "kind": "port",
                          "sample": f"{cpu_sample} reads ({cpu_sample // 2} pairs) of the same batch in {cpu_dt:.1f}s, oracle/ built {flags}, OpenMP over pairs, {cpu_note}"},
     }

@@ -186,6 +186,8 @@ def load_library() -> C.CDLL:
     lib.gb_device_pool_overflow.restype = C.c_int
     lib.gb_kernel_times.argtypes = [vp, u32, vp, vp, vp]
     lib.gb_kernel_times.restype = C.c_int
+    lib.gb_plan_stats.argtypes = [vp, vp]
+    lib.gb_plan_stats.restype = C.c_int
     lib.gb_bgzf_compress.argtypes = [vp, u64, C.c_int, vp, u64, vp]
     lib.gb_bgzf_compress.restype = C.c_int
     lib.gb_last_kernel_ms.argtypes = [vp]
@@ -670,12 +672,19 @@ class Device:
 
     def kernel_times(self):
         """Per-kernel device time of the last mapping call's last chunk: list of (kernel name, ms)."""
-        cap = 24
+        cap = 32
         names = C.create_string_buffer(cap * 48); ms = (C.c_float * cap)(); n = C.c_uint32()
         rc = load_library().gb_kernel_times(self._h, cap, names, ms, C.byref(n))
         if rc != GB_OK:
             raise GbError(rc, "gb_kernel_times")
         return [(names.raw[i * 48:(i + 1) * 48].split(b"\0")[0].decode(), float(ms[i])) for i in range(n.value)]
+
+    def plan_stats(self):
+        out = (C.c_uint64 * 4)()
+        rc = load_library().gb_plan_stats(self._h, out)
+        if rc != GB_OK:
+            raise GbError(rc, "gb_plan_stats")
+        return {"tails": int(out[0]), "trees": int(out[1]), "cells": int(out[3])}
 
     def stage_times(self):
         ms = (C.c_float * 4)()

@@ -128,7 +128,7 @@ struct gb_device {
     gb::DevBuf<gb::TileResult> pl_results;
     gb::DevBuf<uint64_t> pl_stats;
     // per-kernel device times of the last map_device call (events between the launches)
-    static constexpr int KT_MAX = 24;
+    static constexpr int KT_MAX = 32;
     cudaEvent_t kt_ev[KT_MAX] = {}; const char* kt_name[KT_MAX] = {}; int kt_n = 0;
     void kt_reset() { kt_n = 0; }
     int kt_mark(const char* name) {

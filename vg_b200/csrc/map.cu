@@ -194,14 +194,17 @@ static int launch_tile_class(gb_device* d, int cls, const uint8_t* tiles, const 
     xdrop_tile_kernel<R><<<grid, TILE_WARPS * 32, smem, d->stream>>>(d->sc, tb);
     d->launches++;
     GB_CUDA(cudaGetLastError());
-    return d->kt_mark(R == 4 ? "xdrop_tile_kernel<4>" : (R == 8 ? "xdrop_tile_kernel<8>" : "xdrop_tile_kernel<16>"));
+    return d->kt_mark(R == 2 ? "xdrop_tile_kernel<2>" : R == 4 ? "xdrop_tile_kernel<4>" : R == 6 ? "xdrop_tile_kernel<6>" : R == 8 ? "xdrop_tile_kernel<8>" : R == 12 ? "xdrop_tile_kernel<12>" : "xdrop_tile_kernel<16>");
 }
 int launch_tile_kernels(gb_device* d, const uint8_t* tiles, const uint32_t* tile_off, const uint32_t* lists, size_t list_cap,
                         const uint32_t* list_count, uint32_t* work, TileResult* results, uint32_t* paths, uint32_t path_cap, uint32_t* path_cursor) {
     int rc;
-    if ((rc = launch_tile_class<4>(d, 0, tiles, tile_off, lists, list_cap, list_count, work, results, paths, path_cap, path_cursor))) return rc;
-    if ((rc = launch_tile_class<8>(d, 1, tiles, tile_off, lists, list_cap, list_count, work, results, paths, path_cap, path_cursor))) return rc;
-    return launch_tile_class<16>(d, 2, tiles, tile_off, lists, list_cap, list_count, work, results, paths, path_cap, path_cursor);
+    if ((rc = launch_tile_class<2>(d, 0, tiles, tile_off, lists, list_cap, list_count, work, results, paths, path_cap, path_cursor))) return rc;
+    if ((rc = launch_tile_class<4>(d, 1, tiles, tile_off, lists, list_cap, list_count, work, results, paths, path_cap, path_cursor))) return rc;
+    if ((rc = launch_tile_class<6>(d, 2, tiles, tile_off, lists, list_cap, list_count, work, results, paths, path_cap, path_cursor))) return rc;
+    if ((rc = launch_tile_class<8>(d, 3, tiles, tile_off, lists, list_cap, list_count, work, results, paths, path_cap, path_cursor))) return rc;
+    if ((rc = launch_tile_class<12>(d, 4, tiles, tile_off, lists, list_cap, list_count, work, results, paths, path_cap, path_cursor))) return rc;
+    return launch_tile_class<16>(d, 5, tiles, tile_off, lists, list_cap, list_count, work, results, paths, path_cap, path_cursor);
 }
 
 // Device-resident mapping of a batch whose reads are already in HBM.
@@ -270,7 +273,7 @@ int map_device(gb_device* d, const gb_map_params* hp, uint32_t n_reads, const ui
     if ((rc = d->p_cursors.reserve(48))) return rc;
     GB_CUDA(cudaMemsetAsync(d->p_cursors.ptr, 0, 48 * sizeof(uint32_t), d->stream));
     // 0 seed work, 1 min, 2 seed, 3 item, 4 ext, 5 extend work, 6 align work, 7 slow count, 8-10 seeding retry, 11-12 rescue, 13 pool overflow,
-    // 14 plan work, 16 tiles, 17 tile bytes / 16, 18-20 tile list counts, 21-23 tile work, 24 result path words
+    // 14 plan work, 16 tiles, 17 tile bytes / 16, 18-23 tile list counts, 25 result path words, 26-31 tile work
     uint32_t* cur = d->p_cursors.ptr;
     d->kt_reset();
 
@@ -417,14 +420,14 @@ int map_device(gb_device* d, const gb_map_params* hp, uint32_t n_reads, const ui
             const size_t path_cap = std::min<size_t>(tile_cap * 32, 0xfffffff0u);
             if ((rc = d->pl_entries.reserve((size_t)n_units * PLAN_PER_UNIT)) || (rc = d->pl_unit_base.reserve(n_units)) || (rc = d->pl_unit_count.reserve(n_units)) ||
                 (rc = d->pl_tiles.reserve(unit_cap * 16)) || (rc = d->pl_tile_off.reserve(tile_cap)) || (rc = d->pl_results.reserve(tile_cap)) ||
-                (rc = d->pl_lists.reserve(3 * tile_cap)) || (rc = d->pl_paths.reserve(path_cap)) || (rc = d->pl_stats.reserve(4))) return rc;
+                (rc = d->pl_lists.reserve(TILE_CLASSES * tile_cap)) || (rc = d->pl_paths.reserve(path_cap)) || (rc = d->pl_stats.reserve(4))) return rc;
             GB_CUDA(cudaMemsetAsync(d->pl_stats.ptr, 0, 4 * sizeof(uint64_t), d->stream));
             PlanPools pp;
             pp.entries = d->pl_entries.ptr; pp.unit_base = d->pl_unit_base.ptr; pp.unit_count = d->pl_unit_count.ptr;
             pp.tiles = d->pl_tiles.ptr; pp.tile_units_cap = (uint32_t)unit_cap; pp.tile_units_cursor = cur + 17;
             pp.tile_off = d->pl_tile_off.ptr; pp.tile_cap = (uint32_t)tile_cap; pp.tile_cursor = cur + 16;
             pp.results = d->pl_results.ptr;
-            for (int c = 0; c < 3; c++) pp.lists[c] = d->pl_lists.ptr + (size_t)c * tile_cap;
+            for (int c = 0; c < TILE_CLASSES; c++) pp.lists[c] = d->pl_lists.ptr + (size_t)c * tile_cap;
             pp.list_count = cur + 18; pp.stats = d->pl_stats.ptr;
             MapBatch bpl = b3; bpl.work_counter = cur + 14;
             if (paired) tail_plan_kernel<true><<<grid_plain, ALIGN_WARPS * 32, 0, d->stream>>>(d->ix, P, d->sc, bpl, a, pp);
@@ -432,8 +435,8 @@ int map_device(gb_device* d, const gb_map_params* hp, uint32_t n_reads, const ui
             d->launches++;
             GB_CUDA(cudaGetLastError());
             if ((rc = d->kt_mark("tail_plan_kernel"))) return rc;
-            if ((rc = launch_tile_kernels(d, d->pl_tiles.ptr, d->pl_tile_off.ptr, d->pl_lists.ptr, tile_cap, cur + 18, cur + 21, d->pl_results.ptr,
-                                          d->pl_paths.ptr, (uint32_t)path_cap, cur + 24))) return rc;
+            if ((rc = launch_tile_kernels(d, d->pl_tiles.ptr, d->pl_tile_off.ptr, d->pl_lists.ptr, tile_cap, cur + 18, cur + 26, d->pl_results.ptr,
+                                          d->pl_paths.ptr, (uint32_t)path_cap, cur + 25))) return rc;
             a.plan.entries = d->pl_entries.ptr; a.plan.unit_base = d->pl_unit_base.ptr; a.plan.unit_count = d->pl_unit_count.ptr;
             a.plan.tile_off = d->pl_tile_off.ptr; a.plan.results = d->pl_results.ptr; a.plan.path_pool = d->pl_paths.ptr;
         }
@@ -745,6 +748,17 @@ extern "C" int gb_stage_times(gb_device* d, float* ms4) {
     return GB_OK;
 }
 
+// Counters of the tail plan of the last mapping call (its last chunk): tails planned, trees, (unused), DP cells of the tiles.
+extern "C" int gb_plan_stats(gb_device* d, uint64_t* out4) {
+    if (!d || !out4) return GB_ERR_ARG;
+    for (int i = 0; i < 4; i++) out4[i] = 0;
+    if (!d->pl_stats.ptr) return GB_OK;
+    GB_CUDA(cudaSetDevice(d->device));
+    GB_CUDA(cudaStreamSynchronize(d->stream));
+    GB_CUDA(cudaMemcpy(out4, d->pl_stats.ptr, 4 * sizeof(uint64_t), cudaMemcpyDeviceToHost));
+    return GB_OK;
+}
+
 // Device time of every kernel of the last mapping call on this handle (one chunk; CUDA events between the launches).
 extern "C" int gb_kernel_times(gb_device* d, uint32_t cap, char* names, float* ms, uint32_t* n_out) {
     if (!d || !names || !ms || !n_out) return GB_ERR_ARG;
@@ -914,19 +928,19 @@ extern "C" int gb_xdrop_pinned_batch(gb_device* d, uint32_t n,
     if (n_elig) {
         const uint32_t path_cap = (uint32_t)std::min<uint64_t>((uint64_t)n * (2 * TILE_MAP_CAP + TILE_EDIT_CAP), 0xfffffff0ull);
         if ((rc = d_elig.upload(elig.data(), n, d->stream)) || (rc = d_tileoff.upload(toff.data(), n, d->stream)) || (rc = d_tiles.reserve(units * 16 + 16)) ||
-            (rc = d_lists.reserve(3 * (size_t)n)) || (rc = d_tc.reserve(16)) || (rc = d_res.reserve(n)) || (rc = d_paths.reserve(path_cap))) return rc;
-        GB_CUDA(cudaMemsetAsync(d_tc.ptr, 0, 64, d->stream));
+            (rc = d_lists.reserve(TILE_CLASSES * (size_t)n)) || (rc = d_tc.reserve(32)) || (rc = d_res.reserve(n)) || (rc = d_paths.reserve(path_cap))) return rc;
+        GB_CUDA(cudaMemsetAsync(d_tc.ptr, 0, 128, d->stream));
         GB_CUDA(cudaMemsetAsync(d_res.ptr, 0xff, sizeof(TileResult) * (size_t)n, d->stream));
         PackBatch pk;
         pk.tree_parent = d_par.ptr; pk.tree_node = d_node.ptr; pk.tree_off = d_toff.ptr; pk.root_trim = d_trim.ptr;
         pk.query = d_q.ptr; pk.query_off = d_qoff.ptr; pk.max_gap = d_gap.ptr; pk.n = n; pk.tiles = d_tiles.ptr; pk.tile_off = d_tileoff.ptr;
-        for (int c = 0; c < 3; c++) pk.lists[c] = d_lists.ptr + (size_t)c * n;
+        for (int c = 0; c < TILE_CLASSES; c++) pk.lists[c] = d_lists.ptr + (size_t)c * n;
         pk.list_count = d_tc.ptr; pk.eligible = d_elig.ptr;
         pack_tiles_kernel<<<(n + 7) / 8, 256, 0, d->stream>>>(d->ix, d->sc, pk);
         d->launches++;
         GB_CUDA(cudaGetLastError());
         d->kt_reset();
-        if ((rc = launch_tile_kernels(d, d_tiles.ptr, d_tileoff.ptr, d_lists.ptr, n, d_tc.ptr, d_tc.ptr + 4, d_res.ptr, d_paths.ptr, path_cap, d_tc.ptr + 8))) return rc;
+        if ((rc = launch_tile_kernels(d, d_tiles.ptr, d_tileoff.ptr, d_lists.ptr, n, d_tc.ptr, d_tc.ptr + 8, d_res.ptr, d_paths.ptr, path_cap, d_tc.ptr + 16))) return rc;
         b.skip = d_elig.ptr;
         unpack_tile_results_kernel<<<(n + 7) / 8, 256, 0, d->stream>>>(b, d_res.ptr, d_paths.ptr);
         d->launches++;

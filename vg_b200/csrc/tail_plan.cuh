@@ -14,7 +14,7 @@ struct PlanPools {
     uint8_t* tiles; uint32_t tile_units_cap; uint32_t* tile_units_cursor;      // 16-byte units
     uint32_t* tile_off; uint32_t tile_cap; uint32_t* tile_cursor;
     TileResult* results;
-    uint32_t* lists[3]; uint32_t* list_count;                                  // [3]
+    uint32_t* lists[TILE_CLASSES]; uint32_t* list_count;                       // [TILE_CLASSES]
     uint64_t* stats;                                                           // [4] tails planned, trees, tiles, cells upper bound
 };
 

@@ -74,7 +74,14 @@ struct __align__(16) TileResult {
 };
 
 // rows per lane needed for a query of length m
-__host__ __device__ inline int tile_class(uint32_t m) { return m + 1 <= 128 ? 0 : (m + 1 <= 256 ? 1 : 2); }    // R = 4, 8, 16
+constexpr int TILE_CLASSES = 6;
+__host__ __device__ inline int tile_class(uint32_t m) {                    // R = 2, 4, 6, 8, 12, 16 rows per lane
+    const uint32_t rows = m + 1;
+    return rows <= 64 ? 0 : (rows <= 128 ? 1 : (rows <= 192 ? 2 : (rows <= 256 ? 3 : (rows <= 384 ? 4 : 5))));
+}
+__host__ __device__ constexpr int tile_class_rows(int cls) { return cls == 0 ? 2 : (cls == 1 ? 4 : (cls == 2 ? 6 : (cls == 3 ? 8 : (cls == 4 ? 12 : 16)))); }
+// traceback bytes per lane and column for P = R / 2 packed registers (padded so one store serves a lane)
+__host__ __device__ constexpr int tile_tb_stride(int P) { return P == 1 ? 1 : (P == 2 ? 2 : (P <= 4 ? 4 : 8)); }
 
 // The int16 ranges hold for these scores and this query length (see the header comment).
 __host__ __device__ inline bool tile_scores_fit_int16(const DevScores& s, uint32_t m, uint32_t max_gap) {
@@ -156,8 +163,8 @@ __device__ inline TileWs carve_tile_ws(uint8_t* base) {
 __host__ __device__ inline bool tile_eligible(const DevScores& s, uint32_t m, uint32_t max_gap, uint32_t n_nodes, uint32_t n_bases, uint32_t max_depth) {
     if (!tile_scores_fit_int16(s, m, max_gap)) return false;
     if (n_nodes == 0 || n_nodes > TILE_MAX_NODES || max_depth >= TILE_D_CAP || n_bases == 0 || n_bases > 0xffffu) return false;
-    const uint32_t R = 4u << tile_class(m);
-    return (uint64_t)n_bases * 32u * (R / 2) <= TILE_TB_BYTES;           // R/2 traceback bytes per lane and column
+    const int R = tile_class_rows(tile_class(m));
+    return (uint64_t)n_bases * 32u * (uint32_t)tile_tb_stride(R / 2) <= TILE_TB_BYTES;
 }
 
 // -----------------------------------------------------------------------------------------------------------------
@@ -170,6 +177,7 @@ __device__ __noinline__ int32_t xdrop_tile_dp(const DevScores& sc, const uint8_t
                                               uint32_t& map_base_out, uint32_t& edit_base_out, uint32_t& status_out, uint64_t& cells_out) {
     constexpr int P = R / 2;
     constexpr int HALF = 16 * R;
+    constexpr int TBS = tile_tb_stride(P);
     const int lane = lane_id();
     const TileHeader hd = *reinterpret_cast<const TileHeader*>(tile);
     const TileNode* nodes = reinterpret_cast<const TileNode*>(tile + 32);
@@ -237,9 +245,10 @@ __device__ __noinline__ int32_t xdrop_tile_dp(const DevScores& sc, const uint8_t
             run_max = ws.node_lin[tn.parent];
         }
         if (lane == 0) { ws.node_col[ni] = tb_cols; ws.node_depth[ni] = (uint16_t)depth; }
-        uint32_t bestv[P], bestc[P];
+        // best cell of the node: the first column whose maximum beats every earlier column of the node, kept as a snapshot
+        uint32_t snap[P]; int node_best = NEG16; uint32_t node_best_col = 0;
 #pragma unroll
-        for (int i = 0; i < P; i++) { bestv[i] = NEG16x2; bestc[i] = 0; }
+        for (int i = 0; i < P; i++) snap[i] = NEG16x2;
         // diagonal feed of the first register: previous lane's last register (rows wrap from the low half into the high half)
         uint32_t up = __shfl_sync(FULL, Hp[P - 1], (lane + 31) & 31);
         if (lane == 0) up = (up << 16) | 0xC000u;
@@ -249,6 +258,11 @@ __device__ __noinline__ int32_t xdrop_tile_dp(const DevScores& sc, const uint8_t
         for (; c < tn.len; c++) {
             // fold the previous column's maximum into the lineage maximum (the X-drop looks at EARLIER columns only)
             if (col_max_prev != 0x7fffffff) {
+                if (col_max_prev > node_best) {   // Hp still holds that column
+                    node_best = col_max_prev; node_best_col = c - 1;
+#pragma unroll
+                    for (int i = 0; i < P; i++) snap[i] = Hp[i];
+                }
                 if (col_max_prev > run_max) run_max = col_max_prev;
                 alive_prev = col_max_prev > ALIVE_FLOOR;
             }
@@ -293,10 +307,6 @@ __device__ __noinline__ int32_t xdrop_tile_dp(const DevScores& sc, const uint8_t
                 Hp[i] = (h[i] & ~dead) | (NEG16x2 & dead);
                 Ep[i] = (e[i] & ~dead) | (NEG16x2 & dead);
                 cm = __vmaxs2(cm, Hp[i]);
-                // best cell per row: strictly greater keeps the first column
-                const uint32_t gt = sign_mask2(__vsub2(bestv[i], Hp[i]));
-                bestv[i] = __vmaxs2(bestv[i], Hp[i]);
-                bestc[i] = (bestc[i] & ~gt) | (pk1((int)c) & gt);
             }
 #ifdef GB_TILE_DEBUG
 #pragma unroll
@@ -320,33 +330,36 @@ __device__ __noinline__ int32_t xdrop_tile_dp(const DevScores& sc, const uint8_t
                 t = (t | (t >> 20)) & 0x0000ff00u;                 // byte 1: low-half cell in bits 12-15, high-half cell in bits 8-11
                 tbw[i / 4] |= (t >> 8) << (8 * (i % 4));
             }
-            // one store per lane and column: P bytes at tb[(col * 32 + lane) * P]
+            // one store per lane and column: P bytes (padded to TBS) at tb[(col * 32 + lane) * TBS]
             {
-                uint8_t* dst = tb + ((size_t)(tb_cols + c) * 32 + lane) * P;
-                if constexpr (P == 2) *reinterpret_cast<uint16_t*>(dst) = (uint16_t)tbw[0];
-                else if constexpr (P == 4) *reinterpret_cast<uint32_t*>(dst) = tbw[0];
+                uint8_t* dst = tb + ((size_t)(tb_cols + c) * 32 + lane) * TBS;
+                if constexpr (TBS == 1) *dst = (uint8_t)tbw[0];
+                else if constexpr (TBS == 2) *reinterpret_cast<uint16_t*>(dst) = (uint16_t)tbw[0];
+                else if constexpr (TBS == 4) *reinterpret_cast<uint32_t*>(dst) = tbw[0];
                 else *reinterpret_cast<uint2*>(dst) = make_uint2(tbw[0], tbw[1]);
             }
             col_max_prev = __reduce_max_sync(FULL, max(lo16(cm), hi16(cm)));
         }
         cells += (uint64_t)c * (uint64_t)(m + 1);
-        if (col_max_prev != 0x7fffffff) { if (col_max_prev > run_max) run_max = col_max_prev; alive_prev = col_max_prev > ALIVE_FLOOR; }
-        // node maximum: highest score, then first column, then smallest row (rows live in (lane, register, half))
-        {
-            uint32_t vb = NEG16x2;
+        if (col_max_prev != 0x7fffffff) {
+            if (col_max_prev > node_best) {
+                node_best = col_max_prev; node_best_col = c - 1;
 #pragma unroll
-            for (int i = 0; i < P; i++) vb = __vmaxs2(vb, bestv[i]);
-            const int node_best = __reduce_max_sync(FULL, max(lo16(vb), hi16(vb)));
-            if (node_best > best) {
-                uint32_t key = 0xffffffffu;                          // (column << 16) | row, smallest wins
-#pragma unroll
-                for (int i = 0; i < P; i++) {
-                    if (lo16(bestv[i]) == node_best) key = min(key, ((bestc[i] & 0xffffu) << 16) | (uint32_t)(lane * P + i));
-                    if (hi16(bestv[i]) == node_best) key = min(key, ((bestc[i] >> 16) << 16) | (uint32_t)(HALF + lane * P + i));
-                }
-                key = __reduce_min_sync(FULL, key);
-                best = node_best; best_node = ni; best_col = key >> 16; best_row = key & 0xffffu; have_best = true;
+                for (int i = 0; i < P; i++) snap[i] = Hp[i];
             }
+            if (col_max_prev > run_max) run_max = col_max_prev;
+            alive_prev = col_max_prev > ALIVE_FLOOR;
+        }
+        // node maximum: highest score, then first column (the snapshot), then smallest row (rows live in (lane, register, half))
+        if (node_best > best) {
+            uint32_t key = 0xffffffffu;
+#pragma unroll
+            for (int i = 0; i < P; i++) {
+                if (lo16(snap[i]) == node_best) key = min(key, (uint32_t)(lane * P + i));
+                if (hi16(snap[i]) == node_best) key = min(key, (uint32_t)(HALF + lane * P + i));
+            }
+            key = __reduce_min_sync(FULL, key);
+            best = node_best; best_node = ni; best_col = node_best_col; best_row = key; have_best = true;
         }
         // the node's last column for its children
         const bool live = alive_prev && c == tn.len;
@@ -425,7 +438,7 @@ __device__ __noinline__ int32_t xdrop_tile_dp(const DevScores& sc, const uint8_t
                     pf_byte = 0;
                     if ((uint32_t)lane <= col && (uint32_t)lane <= j) {
                         const uint32_t jl = j - lane, hl = jl >= (uint32_t)HALF ? 1u : 0u, jj = jl - hl * HALF;
-                        pf_byte = tb[((size_t)(ws.node_col[node] + col - lane) * 32 + jj / P) * P + jj % P];
+                        pf_byte = tb[((size_t)(ws.node_col[node] + col - lane) * 32 + jj / P) * TBS + jj % P];
                     }
                     byte = __shfl_sync(FULL, pf_byte, 0);
                 }
@@ -616,7 +629,7 @@ struct PackBatch {
     const int32_t* tree_parent; const uint32_t* tree_node; const uint64_t* tree_off; const uint32_t* root_trim;
     const uint8_t* query; const uint64_t* query_off; const uint32_t* max_gap; uint32_t n;
     uint8_t* tiles; const uint32_t* tile_off;      // precomputed on the host
-    uint32_t* lists[3]; uint32_t* list_count;      // [3]
+    uint32_t* lists[TILE_CLASSES]; uint32_t* list_count;      // [TILE_CLASSES]
     uint8_t* eligible;                              // [n] 0: not a tile problem (host falls back to the int32 kernel)
 };
 static __global__ void pack_tiles_kernel(DevIndex ix, DevScores sc, PackBatch b) {
