@@ -285,12 +285,21 @@ def main():
     ap.add_argument("--reads", type=int, default=10_000_000, help="reads (not pairs) per GPU per step")
     ap.add_argument("--cpu-seconds", type=float, default=15.0)
     ap.add_argument("--rescue-attempts", type=int, default=15, help="MinimizerMapper::max_rescue_attempts (vg giraffe default 15)")
+    ap.add_argument("--scaling", default="weak", choices=["weak", "strong"],
+                    help="weak: --reads per GPU (configs[1]); strong: --total-reads split over the GPUs, identical total input for every N (configs[2])")
+    ap.add_argument("--total-reads", type=int, default=100_000_000, help="strong scaling: reads of the whole job (BASELINE.json configs[2]: 100M)")
     args = ap.parse_args()
 
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     n_reads = args.reads - args.reads % 2
+    BLOCK_PAIRS = 500_000                       # strong scaling: the job is a fixed sequence of seeded blocks, a rank takes a contiguous run
+    if args.scaling == "strong":
+        n_blocks = max(world, args.total_reads // (2 * BLOCK_PAIRS))
+        from vg_b200 import shard as _sh
+        blk_lo, blk_hi = _sh.shard_pairs(n_blocks, rank, world)
+        n_reads = 2 * BLOCK_PAIRS * (blk_hi - blk_lo)
 
     import helpers as H
 
@@ -351,7 +360,14 @@ def main():
     lib.gb_device_set_stream(dev.handle, C.c_void_p(stream.cuda_stream))
 
     t = time.time()
-    d_reads, d_quals = simulate_pairs_torch(g, n_reads // 2, 22 + rank, device)
+    if args.scaling == "strong":
+        d_reads = torch.empty((n_reads, READ_LEN), dtype=torch.uint8, device=device)
+        for bi in range(blk_lo, blk_hi):          # block bi is the same reads whatever the number of GPUs
+            r_blk, _ = simulate_pairs_torch(g, BLOCK_PAIRS, 1000 + bi, device)
+            d_reads[2 * BLOCK_PAIRS * (bi - blk_lo): 2 * BLOCK_PAIRS * (bi - blk_lo + 1)] = r_blk
+        d_quals = torch.full_like(d_reads, 30)
+    else:
+        d_reads, d_quals = simulate_pairs_torch(g, n_reads // 2, 22 + rank, device)
     torch.cuda.synchronize()
     log(f"[bench] rank {rank}: {n_reads} reads generated on the GPU in {time.time() - t:.1f}s")
     d_read_off = (torch.arange(n_reads + 1, dtype=torch.int64, device=device) * READ_LEN)
@@ -412,7 +428,8 @@ def main():
         tms = torch.tensor([dev_ms], device=device)
         dist.all_reduce(tms, op=dist.ReduceOp.MAX)
         dev_ms = float(tms.item())
-    value = world * n_reads / (dev_ms / 1e3)
+    job_reads = 2 * BLOCK_PAIRS * n_blocks if args.scaling == "strong" else world * n_reads      # all ranks together
+    value = job_reads / (dev_ms / 1e3)
 
     totals = d_totals.cpu().numpy()
     status_bad = int((d_status != 0).sum().item())
@@ -443,20 +460,68 @@ def main():
         if rc != 0:
             raise capi.GbError(rc, "gb_map_paired_batch")
 
+    # ---- multi-GPU emission: whole records (headers + mappings + edits) to rank 0 over NCCL / NVLink ----
+    # The host-buffer call leaves its records in HBM too (output mirror); their gather runs on a side stream while the next
+    # step maps, exact sizes, no padding, sizes exchanged on a host-side gloo group (no device sync); rank 0 lands every
+    # rank's records in pinned host memory (what an AlignmentEmitter would consume).
+    emit = None
+    if world > 1:
+        side = torch.cuda.Stream(device=device)
+        gloo = dist.new_group(backend="gloo")
+        m_aln = torch.zeros((n_reads, 32), dtype=torch.uint8, device=device)
+        m_maps = torch.zeros((n_reads * MAP_PER, 8), dtype=torch.uint8, device=device)
+        m_edits = torch.zeros((n_reads * EDIT_PER,), dtype=torch.int32, device=device)
+        rcm = lib.gb_device_set_output_mirror(dev.handle, C.c_void_p(m_aln.data_ptr()), C.c_void_p(m_maps.data_ptr()), n_reads * MAP_PER,
+                                              C.c_void_p(m_edits.data_ptr()), n_reads * EDIT_PER)
+        assert rcm == 0
+        caps = [torch.zeros(1, dtype=torch.int64) for _ in range(world)]
+        dist.all_gather(caps, torch.tensor([n_reads], dtype=torch.int64), group=gloo)
+        recv = host_all = None
+        if rank == 0:
+            recv = [None if r == 0 else (torch.empty((int(c), 32), dtype=torch.uint8, device=device), torch.empty((int(c) * MAP_PER, 8), dtype=torch.uint8, device=device),
+                                         torch.empty((int(c) * EDIT_PER,), dtype=torch.int32, device=device)) for r, c in enumerate(caps)]
+            host_all = [None if r == 0 else (torch.empty((int(c), 32), dtype=torch.uint8, pin_memory=True), torch.empty((int(c) * MAP_PER, 8), dtype=torch.uint8, pin_memory=True),
+                                             torch.empty((int(c) * EDIT_PER,), dtype=torch.int32, pin_memory=True)) for r, c in enumerate(caps)]
+        emitted = {"records": 0, "mappings": 0}
+
+        def emit():
+            """gather of the step that just finished; returns immediately (work is queued on the side stream)"""
+            side.wait_stream(stream)
+            with torch.cuda.stream(side):
+                nm, ne = int(used[0].value), int(used[1].value)
+                reqs, parts = shard.gather_records(m_aln, m_maps[:nm], m_edits[:ne], rank, world, counts_group=gloo, out=recv)
+                for rq in reqs:
+                    rq.wait()                      # stream-ordered for NCCL: the side stream waits, the host does not
+                if rank == 0:
+                    for r in range(1, world):
+                        for src, dst in zip(parts[r], host_all[r]):
+                            dst[: src.shape[0]].copy_(src, non_blocking=True)
+                    emitted["records"] = sum(int(pt[0].shape[0]) for pt in parts)
+                    emitted["mappings"] = sum(int(pt[1].shape[0]) for pt in parts)
+
     e2e_warm = min(args.warmup, 3)
     for _ in range(e2e_warm):
         e2e_step()
+        if emit:
+            emit()
     barrier()
+    if emit:
+        side.synchronize()
     ev2 = [torch.cuda.Event(enable_timing=True) for _ in range(2)]
     t0 = time.time()
     ev2[0].record(stream)
     for _ in range(args.steps):
+        if emit:
+            side.synchronize()                     # the mirror is about to be overwritten: the previous step's gather must have left
         e2e_step()
-        if world > 1:
-            # final alignment emission: fixed-width records gathered on rank 0 over NVLink (NCCL)
-            shard.gather_headers(d_aln, rank, world)
+        if emit:
+            emit()
+    if emit:
+        stream.wait_stream(side)                   # the last gather is inside the timed region
     ev2[1].record(stream)
     barrier()
+    if emit:
+        side.synchronize()
     e2e_ms_dev = ev2[0].elapsed_time(ev2[1]) / args.steps
     e2e_ms_wall = 1e3 * (time.time() - t0) / args.steps
     e2e_ms = max(e2e_ms_dev, e2e_ms_wall)
@@ -464,7 +529,7 @@ def main():
         tms = torch.tensor([e2e_ms], device=device)
         dist.all_reduce(tms, op=dist.ReduceOp.MAX)
         e2e_ms = float(tms.item())
-    e2e_value = world * n_reads / (e2e_ms / 1e3)
+    e2e_value = job_reads / (e2e_ms / 1e3)
     h2d = 2 * n_reads * READ_LEN + 8 * (n_reads + 1)
     d2h = 32 * n_reads + n_reads + 8 * used[0].value + 4 * used[1].value
 
@@ -527,12 +592,15 @@ def main():
 
     line = {
         "metric": "giraffe reads/sec (150 bp PE, synthetic)", "value": value, "unit": "reads/s", "n_gpus": world,
-        "steps": args.steps, "warmup": args.warmup, "ms_per_step": dev_ms, "higher_is_better": True, "scaling": "weak",
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": dev_ms, "higher_is_better": True, "scaling": args.scaling,
         "vs_baseline": None, "dtype": "int32", "data": "synthetic",
         "config": {
             "workload": "configs[1]: 1 Mbp random graph, 1k SNP+indel variants, 8 haplotypes, nodes <= 32 bp, k=29 w=11; "
                         "150 bp paired-end reads, fragment N(400,50) forced, 0.2 % substitutions, 0.02 % indels (SURVEY §8(d) config 2)",
             "reads_per_gpu_per_step": n_reads, "pairs_per_gpu_per_step": n_reads // 2,
+            "total_reads_per_step": job_reads,
+            "emission": (None if world == 1 else {"what": "whole records (32 B header + mappings + edits) of every rank gathered on rank 0 over NCCL, exact sizes, side stream overlapped with the next step, then to pinned host memory",
+                                                   "records_on_rank0": emitted["records"], "mappings_on_rank0": emitted["mappings"]}),
             "mapper": f"map_paired, vg giraffe defaults (--rescue-attempts {args.rescue_attempts}), forced fragment distribution",
             "chunk_reads": CHUNK, "l2_policy": "inputs larger than L2 (3 GB of reads+qualities per step)",
             "mapped_fraction": mapped_frac, "mapq60_fraction": mapq60, "status_errors": status_bad,

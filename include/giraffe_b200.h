@@ -437,6 +437,12 @@ int gb_debug_seed_stage(gb_device* dev, const gb_map_params* p, int paired,
                         gb_stage_cluster* clusters, uint64_t cluster_cap, gb_stage_item* items, uint64_t item_cap,
                         gb_seed* item_seeds, uint64_t item_seed_cap);
 
+/* Multi-GPU emission (giraffe_main.cpp:2209-2226 on rank 0): after this call gb_map_batch /
+ * gb_map_paired_batch also leave the records of every call in the caller's DEVICE buffers — headers d_aln[n_reads], dense
+ * mappings / edits with the same offsets as the host outputs — so the ranks can gather whole records over NCCL / NVLink
+ * without a second PCIe trip.  The copies are ordered before the call returns.  d_aln = NULL switches it off. */
+int gb_device_set_output_mirror(gb_device* dev, gb_alignment* d_aln, gb_mapping* d_maps, uint64_t map_cap, uint32_t* d_edits, uint64_t edit_cap);
+
 /* Run this handle's work on the caller's CUDA stream (cudaStream_t; NULL = the handle's own). */
 int gb_device_set_stream(gb_device* dev, void* cuda_stream);
 int gb_device_synchronize(gb_device* dev);

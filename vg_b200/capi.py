@@ -186,6 +186,8 @@ def load_library() -> C.CDLL:
     lib.gb_device_pool_overflow.restype = C.c_int
     lib.gb_kernel_times.argtypes = [vp, u32, vp, vp, vp]
     lib.gb_kernel_times.restype = C.c_int
+    lib.gb_device_set_output_mirror.argtypes = [vp, vp, vp, u64, vp, u64]
+    lib.gb_device_set_output_mirror.restype = C.c_int
     lib.gb_plan_stats.argtypes = [vp, vp]
     lib.gb_plan_stats.restype = C.c_int
     lib.gb_bgzf_compress.argtypes = [vp, u64, C.c_int, vp, u64, vp]

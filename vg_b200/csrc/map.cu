@@ -320,18 +320,22 @@ int map_device(gb_device* d, const gb_map_params* hp, uint32_t n_reads, const ui
             uint32_t warps = SEED_WARPS;
             while (warps > 1 && seed_smem_bytes(Lc, bp.Mc, bp.Cc) * warps > 200 * 1024) warps >>= 1;
             const size_t smem = seed_smem_bytes(Lc, bp.Mc, bp.Cc) * warps;
+            const bool fixed_layout = paired && Lc == 160 && bp.Mc == 64 && bp.Cc == 16;
             if (smem > 48 * 1024) {
                 GB_CUDA(cudaFuncSetAttribute(seed_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-                GB_CUDA(cudaFuncSetAttribute(seed_kernel_pe, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+                GB_CUDA(cudaFuncSetAttribute(seed_kernel_pe<0, 0, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+                GB_CUDA(cudaFuncSetAttribute(seed_kernel_pe<160, 64, 16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
             }
             int bps = 0;
-            if (paired) GB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bps, seed_kernel_pe, warps * 32, smem));
+            if (paired && fixed_layout) GB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bps, seed_kernel_pe<160, 64, 16>, warps * 32, smem));
+            else if (paired) GB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bps, seed_kernel_pe<0, 0, 0>, warps * 32, smem));
             else GB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bps, seed_kernel, warps * 32, smem));
             if (bps < 1) bps = 1;
             uint32_t grid = std::min<uint32_t>((uint32_t)(d->n_sms * bps), (n_units + warps - 1) / warps);
             if (grid == 0) grid = 1;
             if (paired) { PairBatch pbatch; pbatch.pairs = d->p_pairs.ptr; pbatch.fragment_limit = fragment_limit;
-                          seed_kernel_pe<<<grid, warps * 32, smem, d->stream>>>(d->ix, P, bp, pools, pbatch); }
+                          if (fixed_layout) seed_kernel_pe<160, 64, 16><<<grid, warps * 32, smem, d->stream>>>(d->ix, P, bp, pools, pbatch);
+                          else seed_kernel_pe<0, 0, 0><<<grid, warps * 32, smem, d->stream>>>(d->ix, P, bp, pools, pbatch); }
             else seed_kernel<<<grid, warps * 32, smem, d->stream>>>(d->ix, P, bp, pools);
             d->launches++;
             GB_CUDA(cudaGetLastError());
@@ -522,6 +526,12 @@ static int map_batch_host(gb_device* d, const gb_map_params* hp, bool paired,
         }
         if (tm) GB_CUDA(cudaMemcpyAsync(mappings + map_used, io.maps.ptr, sizeof(gb_mapping) * tm, cudaMemcpyDeviceToHost, d->s_out));
         if (te) GB_CUDA(cudaMemcpyAsync(edits + edit_used, io.edits.ptr, 4 * te, cudaMemcpyDeviceToHost, d->s_out));
+        if (d->mirror_aln) {
+            // the same records stay in HBM for the caller's emission gather (gb_device_set_output_mirror)
+            if (map_used + tm > d->mirror_map_cap || edit_used + te > d->mirror_edit_cap) { g_last_error = "output mirror too small"; return GB_ERR_CAPACITY; }
+            if (tm) GB_CUDA(cudaMemcpyAsync(d->mirror_maps + map_used, io.maps.ptr, sizeof(gb_mapping) * tm, cudaMemcpyDeviceToDevice, d->s_out));
+            if (te) GB_CUDA(cudaMemcpyAsync(d->mirror_edits + edit_used, io.edits.ptr, 4 * te, cudaMemcpyDeviceToDevice, d->s_out));
+        }
         GB_CUDA(cudaEventRecord(io.ev_out, d->s_out));
         float ms = 0.f;
         GB_CUDA(cudaEventElapsedTime(&ms, io.ev_k0, io.ev_k1));
@@ -567,6 +577,7 @@ static int map_batch_host(gb_device* d, const gb_map_params* hp, bool paired,
         GB_CUDA(cudaMemcpyAsync(d->h_totals + 3 * (ci & 1), io.totals.ptr, 3 * sizeof(uint64_t), cudaMemcpyDeviceToHost, d->s_out));
         GB_CUDA(cudaMemcpyAsync(aln + c0, io.aln.ptr, sizeof(gb_alignment) * cn, cudaMemcpyDeviceToHost, d->s_out));
         GB_CUDA(cudaMemcpyAsync(status + c0, io.status.ptr, cn, cudaMemcpyDeviceToHost, d->s_out));
+        if (d->mirror_aln) GB_CUDA(cudaMemcpyAsync(d->mirror_aln + c0, io.aln.ptr, sizeof(gb_alignment) * cn, cudaMemcpyDeviceToDevice, d->s_out));
         GB_CUDA(cudaEventRecord(io.ev_hdr, d->s_out));
         return GB_OK;
     };
@@ -724,6 +735,15 @@ extern "C" int gb_debug_seed_stage(gb_device* d, const gb_map_params* hp, int pa
         }
         return GB_OK;
     } catch (...) { g_last_error = "stage dump: out of host memory"; return GB_ERR_CAPACITY; }
+}
+
+// Multi-GPU emission: gb_map_batch / gb_map_paired_batch additionally leave the records of the whole call in the caller's
+// DEVICE buffers (same layout and offsets as the host outputs), so an NCCL gather can ship them without a second trip over
+// PCIe.  NULL d_aln switches the mirror off.
+extern "C" int gb_device_set_output_mirror(gb_device* d, gb_alignment* d_aln, gb_mapping* d_maps, uint64_t map_cap, uint32_t* d_edits, uint64_t edit_cap) {
+    if (!d || (d_aln && (!d_maps || !d_edits))) return GB_ERR_ARG;
+    d->mirror_aln = d_aln; d->mirror_maps = d_maps; d->mirror_edits = d_edits; d->mirror_map_cap = map_cap; d->mirror_edit_cap = edit_cap;
+    return GB_OK;
 }
 
 extern "C" int gb_device_set_stream(gb_device* d, void* cuda_stream) {

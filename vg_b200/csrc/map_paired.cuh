@@ -29,12 +29,17 @@ struct PairBatch {
 // The warps of a block take SEED_WARPS consecutive pairs per round and meet at a block barrier
 // between phases: the kernel's code is far larger than the instruction caches, and warps that
 // drift apart each stream it from L2 on their own (ncu: "no instruction" was the top stall).
+// LC / MC / CC != 0 fix the shared-memory layout at compile time (the usual launch: 150 bp reads, first-pass tables), so the
+// twenty table pointers are immediates on one base register instead of being rebuilt from (Lc, Mc, Cc) at every use (the
+// 64-register budget cannot hold them; ncu attributed 8 % of the kernel's instructions to that arithmetic).
+template <int LC, int MC, int CC>
 __global__ void __launch_bounds__(SEED_WARPS * 32, SEED_BLOCKS_PER_SM)
 seed_kernel_pe(DevIndex ix, MapParamsDev P, MapBatch b, SeedPools pools, PairBatch pb) {
     extern __shared__ __align__(16) uint8_t smem[];
     __shared__ uint32_t s_base;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const SeedSmem sm = carve_seed_smem(smem + (size_t)warp * seed_smem_bytes(b.Lc, b.Mc, b.Cc), b.Lc, b.Mc, b.Cc, b.Ns);
+    const uint32_t lay_L = LC ? (uint32_t)LC : b.Lc, lay_M = MC ? (uint32_t)MC : b.Mc, lay_C = CC ? (uint32_t)CC : b.Cc;
+    const SeedSmem sm = carve_seed_smem(smem + (size_t)warp * seed_smem_bytes(lay_L, lay_M, lay_C), lay_L, lay_M, lay_C, b.Ns);
     const uint32_t n_pairs = b.n_reads / 2;
     const uint32_t limit = b.in_list ? min(*b.in_count, n_pairs) : n_pairs;
     while (true) {

@@ -28,7 +28,11 @@ __device__ __forceinline__ uint32_t rng_next(DevRng& r) {
         r.state = x == 0 ? 1u : x;
         r.inited = 1;
     }
-    r.state = (uint32_t)(((uint64_t)r.state * 48271ull) % 2147483647ull);
+    // x * 48271 mod (2^31 - 1) without a 64-bit division: 2^31 = 1 (mod M), so the product folds as low 31 bits + the rest
+    const uint64_t p = (uint64_t)r.state * 48271ull;                 // < 2^47
+    uint32_t s = (uint32_t)(p & 0x7fffffffu) + (uint32_t)(p >> 31);  // < 2^31 + 2^16
+    if (s >= 2147483647u) s -= 2147483647u;
+    r.state = s;
     return r.state;
 }
 
