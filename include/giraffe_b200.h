@@ -63,14 +63,22 @@ typedef struct gb_node_rec {
  * Edges are sorted by `to`.  LF(i, r) = edge[r].offset + |{ j < i : body[j] == r }|.
  * (restates jltsiren/gbwt @ c2e0199 CompressedRecord; absent from /root/reference) */
 
-/* Distance payload (16 B) — the zipcode-equivalent for "chain of slots" graphs
- * (vg: ZipCode::payload_type, zip_code.hpp:74-75; consumed by the clusterer).
- * A graph is a series composition of slots; every node lies in exactly one slot on one
- * allele (allele 0xFFFF = the slot is a single backbone node).
- *   x_in  = min distance from the chain start to the first base of the node
- *   x_out = (min chain coordinate of the slot end) - (min distance from node end to slot end)
- * For nodes u before v in different slots:  d(end of u -> start of v) = x_in[v] - x_out[u].
- * In the same slot, v is reachable from u only on the same allele. */
+/* Distance payload (16 B) — what the clusterer needs of the snarl-tree distance index, flattened
+ * (vg: ZipCode::payload_type, zip_code.hpp:74-75, consumed by snarl_seed_clusterer.cpp; minimum_distance
+ * minimizer_mapper.cpp:3879-3903).  Every connected component of the graph is a chain of SLOTS: a slot is a cut node
+ * (every source-to-sink walk of the component passes through it: the backbone) or a SITE, the subgraph between two
+ * consecutive cut nodes — any DAG: nested bubbles, alleles of several nodes, adjacent or overlapping variants.
+ *   x_in  = minimum distance from the chain start to the first base of the node
+ *   x_out = x_in of the cut node behind the node's slot - minimum distance from the node's end to that cut node
+ *           (a cut node: x_in + its length)
+ *   slot  = index of the slot along the chain;  allele = index of the node inside its site in topological order
+ *           (0xFFFF: cut node);  component = the chain
+ * For u before v in different slots:  d(end of u -> start of v) = x_in[v] - x_out[u]  (every walk crosses the cut nodes
+ * between them).  Inside one site the minimum distance from the end of u to the start of v is the site's table entry
+ * site_dist[slots[slot].table_off + allele_u * slots[slot].n + allele_v] (0xFFFF: not reachable).
+ * Hand-made payloads (gb_index_build with dist != NULL, the synthetic benchmark graphs) may leave a multi-node slot
+ * without a table (table_off 0xFFFFFFFF): its nodes are then parallel single-node alleles, reachable only from
+ * themselves, and consecutive slots count as fully connected. */
 typedef struct gb_dist_payload {
     uint32_t x_in;
     uint32_t x_out;
@@ -98,6 +106,11 @@ typedef struct gb_hit {
     gb_dist_payload payload;
 } gb_hit;
 
+typedef struct gb_slot_rec {         /* one slot of a chain (see gb_dist_payload)           */
+    uint32_t table_off;              /* first entry of the site's n x n table in site_dist; 0xFFFFFFFF: no table */
+    uint32_t n;                      /* nodes in the slot (1 for a cut node)                */
+} gb_slot_rec;
+
 typedef struct gb_flat_index {
     uint32_t n_nodes;                /* number of oriented-node slots = 2*(max_id+1)        */
     uint32_t k, w;                   /* minimizer parameters (vg default 29 / 11)           */
@@ -108,6 +121,8 @@ typedef struct gb_flat_index {
     const gb_dist_payload* dist;     /* [n_nodes/2], indexed by node id                     */
     const gb_min_cell* table; uint64_t table_cells;  /* power of two                       */
     const gb_hit* hits;   uint64_t n_hits;
+    const gb_slot_rec* slots; uint64_t n_slots;      /* slots of all chains, indexed by gb_dist_payload.slot (may be empty: no tables) */
+    const uint16_t* site_dist; uint64_t site_dist_len;   /* site tables, see gb_dist_payload */
 } gb_flat_index;
 
 /* ------------------------------------------------------------------------------------
@@ -119,24 +134,28 @@ typedef struct gb_host_index gb_host_index;
 
 /* node i (1-based id) has forward sequence node_seq[node_off[i-1] .. node_off[i]).
  * path p is path_nodes[path_off[p] .. path_off[p+1]) in GBWT node encoding.
- * dist may be NULL (payload zero, single slot chain not available -> clustering by
- * payload is then undefined; the extension / alignment stages do not need it). */
+ * dist == NULL: the builder derives the distance payload and the site tables itself from the graph the paths span
+ * (chains of cut nodes and sites, see gb_dist_payload) — any graph whose haplotypes walk forward through a DAG;
+ * a cycle, a reversing step or a site of more than 4096 nodes leaves the index WITHOUT a distance model
+ * (gb_index_has_distance_model() == 0: extension / DP / WFA seams work on it, mapping needs the model).
+ * dist != NULL: a hand-made payload indexed by node id (slots without tables). */
 int gb_index_build(uint32_t n_node_ids, const uint8_t* node_seq, const uint64_t* node_off,
                    uint32_t n_paths, const uint32_t* path_nodes, const uint64_t* path_off,
                    const gb_dist_payload* dist, uint32_t k, uint32_t w,
                    gb_host_index** out);
 void gb_index_free(gb_host_index* ix);
+int gb_index_has_distance_model(const gb_host_index* ix);
 /* Borrowed view; valid until gb_index_free. */
 int gb_index_view(const gb_host_index* ix, gb_flat_index* out);
 /* The flat index as one file (what giraffe_main.cpp:1825-1881 does for GBZ / .min / .dist): a 64-byte header
- * ("GBFLAT1", n_nodes, k, w, n_paths, seq_bytes, gbwt_words, table_cells, n_hits) and the six arrays of gb_flat_index
+ * ("GBFLAT2", n_nodes, k, w, n_paths, seq_bytes, gbwt_words, table_cells, n_hits, then n_slots, site_dist_len in a second 16-byte line) and the eight arrays of gb_flat_index
  * back to back, each padded to 16 bytes, little endian.  gb_index_load checks sizes and offsets and returns
  * GB_ERR_FORMAT for anything that is not such a file; the result is freed with gb_index_free. */
 /* Build the flat index from a GBZ file (gbwtgraph::GBZ, what `vg giraffe -Z` loads, giraffe_main.cpp:1825-1881): node
  * sequences from the GBWTGraph, haplotype paths by walking the bidirectional GBWT, the distance payload from the
  * chain-of-bubbles decomposition of those paths, minimizers (k, w) by the library's own builder.  GBZ version 1 /
  * GBWT version 5 / GBWTGraph version 3 in simple-sds serialization.  GB_ERR_FORMAT for anything else, and for graphs
- * outside the index model (nested or overlapping sites, alleles of several nodes, reversing haplotypes). */
+ * outside the index model (haplotypes that step onto a reverse strand, cycles, a site of more than 4096 nodes). */
 int gb_index_from_gbz(const char* path, uint32_t k, uint32_t w, gb_host_index** out);
 int gb_index_save(const gb_flat_index* ix, const char* path);
 int gb_index_load(const char* path, gb_host_index** out);

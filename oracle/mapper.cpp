@@ -315,7 +315,11 @@ static int64_t directed_distance(const gb_flat_index* ix, uint32_t id_a, uint32_
         int64_t len_a = ix->nodes[2 * id_a].len;
         return (len_a - (int64_t)off_a) + ((int64_t)pb.x_in - (int64_t)pa.x_out) + (int64_t)off_b;
     }
-    return INF_DIST;   // same slot on different alleles, or b is upstream of a
+    if (pa.slot == pb.slot) {
+        const int64_t t = site_distance(ix, pa, pb);           // inside one site: its all-pairs table
+        if (t >= 0) return ((int64_t)ix->nodes[2 * id_a].len - (int64_t)off_a) + t + (int64_t)off_b;
+    }
+    return INF_DIST;   // unreachable inside the site, or b is upstream of a
 }
 
 int64_t unoriented_distance(const gb_flat_index* ix, const Seed& a, const Seed& b) {

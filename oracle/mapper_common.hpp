@@ -126,6 +126,16 @@ struct Minimizer {
 struct Seed { uint32_t node; uint32_t offset; size_t source; gb_dist_payload payload; };   // pos_t + source + zipcode
 struct Cluster { std::vector<size_t> seeds; size_t fragment = 0; double score = 0, coverage = 0; };
 
+// Minimum distance from the END of node a to the START of node b inside one site (gb_dist_payload); -1: not reachable or
+// no table (hand-made payloads: parallel single-node alleles).
+inline int64_t site_distance(const gb_flat_index* ix, const gb_dist_payload& pa, const gb_dist_payload& pb) {
+    if (pa.slot != pb.slot || pa.slot >= ix->n_slots) return -1;
+    const gb_slot_rec& sr = ix->slots[pa.slot];
+    if (sr.table_off == 0xFFFFFFFFu || pa.allele >= sr.n || pb.allele >= sr.n) return -1;
+    const uint16_t t = ix->site_dist[sr.table_off + (size_t)pa.allele * sr.n + pb.allele];
+    return t == 0xFFFF ? -1 : (int64_t)t;
+}
+
 // Stage trace for the stage-level parity tests (oracle_seed_stage): when the thread-local pointer is set, map_from_extensions
 // / map_paired record what they computed up to the extension calls, per read of the unit.
 struct StageTrace {

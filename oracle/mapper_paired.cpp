@@ -81,6 +81,7 @@ int64_t oriented_distance(const gb_flat_index* ix, uint32_t node_a, uint32_t off
     if (ps.component != pd.component) return UNREACHABLE;
     if (src_id == dst_id) return dst_off >= src_off ? dst_off - src_off : UNREACHABLE;
     if (ps.slot < pd.slot) return (src_len - src_off) + ((int64_t)pd.x_in - (int64_t)ps.x_out) + dst_off;
+    if (ps.slot == pd.slot) { const int64_t t = site_distance(ix, ps, pd); if (t >= 0) return (src_len - src_off) + t + dst_off; }
     return UNREACHABLE;
 }
 

@@ -40,8 +40,15 @@ std::vector<uint32_t> subgraph_in_distance_range(const gb_flat_index* ix, uint32
         const gb_dist_payload& pv = ix->dist[id];
         if (pv.component != ps.component) continue;
         int64_t d0;     // distance from the origin to the first base of the node in walk direction
-        if (!rev) { if (!(ps.slot < pv.slot)) continue; d0 = to_end + ((int64_t)pv.x_in - (int64_t)ps.x_out); }
-        else { if (!(pv.slot < ps.slot)) continue; d0 = to_end + ((int64_t)ps.x_in - (int64_t)pv.x_out); }
+        if (!rev) {
+            if (ps.slot < pv.slot) d0 = to_end + ((int64_t)pv.x_in - (int64_t)ps.x_out);
+            else if (ps.slot == pv.slot) { const int64_t t = site_distance(ix, ps, pv); if (t < 0) continue; d0 = to_end + t; }
+            else continue;
+        } else {
+            if (pv.slot < ps.slot) d0 = to_end + ((int64_t)ps.x_in - (int64_t)pv.x_out);
+            else if (ps.slot == pv.slot) { const int64_t t = site_distance(ix, pv, ps); if (t < 0) continue; d0 = to_end + t; }
+            else continue;
+        }
         const int64_t len = ix->nodes[2 * id].len;
         if (d0 <= max_distance && d0 + len > min_distance) ids.push_back(id);
     }
@@ -55,6 +62,7 @@ RescueGraph rescue_dag(const Graph& g, const gb_flat_index* ix, std::vector<uint
         const gb_dist_payload& pa = ix->dist[a]; const gb_dist_payload& pb = ix->dist[b];
         if (pa.component != pb.component) return pa.component < pb.component;
         if (pa.slot != pb.slot) return pa.slot < pb.slot;
+        if (pa.allele != pb.allele) return pa.allele < pb.allele;      // place inside the site = topological
         return a < b;
     });
     for (uint32_t id : ids) out.dag.node.push_back(2 * id);

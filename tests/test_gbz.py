@@ -144,25 +144,39 @@ def test_library_reader_builds_the_same_index_as_the_independent_reader():
 
 
 def test_payload_is_consistent_with_the_haplotypes():
+    """The derived chain model on the graph vg built: slots never decrease along a haplotype, the payload distance between
+    two nodes of a haplotype is a minimum over all walks (never more than the haplotype's own), neighbours touch, and the
+    cut nodes lie on every haplotype."""
     seqs, paths, _ = read_gbz(GBZ)
     index = capi.HostIndex.from_gbz(GBZ)
-    dist = index.array("dist")
+    dist, slots, table = index.array("dist"), index.array("slots"), index.array("site_dist")
     length = {i + 1: len(s) for i, s in enumerate(seqs)}
     on_all = set.intersection(*[set(v >> 1 for v in p) for p in paths])
+
+    def payload_distance(u, v):
+        pu, pv = dist[u], dist[v]
+        if int(pu["slot"]) != int(pv["slot"]):
+            return int(pv["x_in"]) - int(pu["x_out"])
+        sr = slots[int(pu["slot"])]
+        t = int(table[int(sr["table_off"]) + int(pu["allele"]) * int(sr["n"]) + int(pv["allele"])])
+        assert t != 0xFFFF, "nodes of one haplotype reach each other"
+        return t
+    n_same_site = 0
     for p in paths:
         ids = [v >> 1 for v in p]
-        assert [int(dist[i]["slot"]) for i in ids] == sorted(int(dist[i]["slot"]) for i in ids)          # slots grow along every haplotype
-        assert len(set(int(dist[i]["slot"]) for i in ids)) == len(ids)
+        assert [int(dist[i]["slot"]) for i in ids] == sorted(int(dist[i]["slot"]) for i in ids)          # slots never decrease along a haplotype
         for a in range(len(ids)):
             walked = 0
             for b in range(a + 1, len(ids)):
-                d = int(dist[ids[b]]["x_in"]) - int(dist[ids[a]]["x_out"])
-                assert 0 <= d <= walked                                                                 # the payload distance is a minimum over haplotypes
+                d = payload_distance(ids[a], ids[b])
+                assert 0 <= d <= walked                                                                 # a minimum over all walks
                 if b == a + 1:
                     assert d == 0                                                                       # neighbours on a haplotype touch
+                n_same_site += int(dist[ids[a]]["slot"]) == int(dist[ids[b]]["slot"])
                 walked += length[ids[b]]
-    for i in on_all:
-        assert int(dist[i]["allele"]) == 0xFFFF                                                         # backbone nodes are single-allele slots
+    cut = {i for i in range(1, len(seqs) + 1) if int(dist[i]["allele"]) == 0xFFFF}
+    assert cut and cut <= on_all                                                                        # every walk passes a cut node, so every haplotype does
+    assert all(int(slots[int(dist[i]["slot"])]["n"]) == 1 for i in cut)
     index.close()
 
 

@@ -25,6 +25,7 @@ node_rec_dt = np.dtype([("seq_off", "<u4"), ("rec_off", "<u4"), ("len", "<u4"), 
 dist_dt = np.dtype([("x_in", "<u4"), ("x_out", "<u4"), ("slot", "<u4"), ("allele", "<u2"), ("component", "<u2")])
 min_cell_dt = np.dtype([("key", "<u8"), ("hit_off", "<u4"), ("hit_cnt", "<u4")])
 hit_dt = np.dtype([("pos", "<u8"), ("payload", dist_dt)])
+slot_dt = np.dtype([("table_off", "<u4"), ("n", "<u4")])
 seed_dt = np.dtype([("node", "<u4"), ("diag", "<i4")])
 extension_dt = np.dtype([
     ("path_off", "<u4"), ("path_len", "<u4"), ("mism_off", "<u4"), ("mism_len", "<u4"),
@@ -45,6 +46,8 @@ class FlatIndex(C.Structure):
         ("dist", C.c_void_p),
         ("table", C.c_void_p), ("table_cells", C.c_uint64),
         ("hits", C.c_void_p), ("n_hits", C.c_uint64),
+        ("slots", C.c_void_p), ("n_slots", C.c_uint64),
+        ("site_dist", C.c_void_p), ("site_dist_len", C.c_uint64),
     ]
 
 
@@ -290,6 +293,7 @@ class HostIndex:
             "nodes": (v.nodes, v.n_nodes, node_rec_dt), "seq": (v.seq, v.seq_bytes, np.uint8),
             "gbwt": (v.gbwt, v.gbwt_words, np.uint32), "dist": (v.dist, v.n_nodes // 2, dist_dt),
             "table": (v.table, v.table_cells, min_cell_dt), "hits": (v.hits, v.n_hits, hit_dt),
+            "slots": (v.slots, v.n_slots, slot_dt), "site_dist": (v.site_dist, v.site_dist_len, np.uint16),
         }[name]
         addr, n, dt = spec
         dt = np.dtype(dt)

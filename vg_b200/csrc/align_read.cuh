@@ -560,6 +560,7 @@ __device__ inline int64_t oriented_distance(const DevIndex& ix, uint32_t node_a,
     if ((ps.w >> 16) != (pd.w >> 16)) return UNREACHABLE;               // component
     if ((src >> 1) == (dst >> 1)) return dst_off >= src_off ? dst_off - src_off : UNREACHABLE;
     if (ps.z < pd.z) return (src_len - src_off) + ((int64_t)pd.x - (int64_t)ps.y) + dst_off;
+    if (ps.z == pd.z) { const int64_t t = site_distance(ix, ps, pd); if (t >= 0) return (src_len - src_off) + t + dst_off; }
     return UNREACHABLE;
 }
 

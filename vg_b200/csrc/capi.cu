@@ -152,12 +152,21 @@ extern "C" int gb_device_create(const gb_flat_index* ix, int device_ordinal, gb_
             const gb_dist_payload& pa = ix->dist[a]; const gb_dist_payload& pb = ix->dist[b];
             if (pa.component != pb.component) return pa.component < pb.component;
             if (pa.slot != pb.slot) return pa.slot < pb.slot;
+            if (pa.allele != pb.allele) return pa.allele < pb.allele;      // place inside the site = topological
             return a < b;
         });
         if ((rc = d->slot_order.upload(order.data(), order.size() ? order.size() : 1, d->stream, order.size()))) return rc;
         GB_CUDA(cudaStreamSynchronize(d->stream));
         d->ix.slot_order = d->slot_order.ptr; d->ix.n_ids = (uint32_t)order.size();
     }
+    if (ix->n_slots) {
+        if ((rc = d->slots.upload(ix->slots, ix->n_slots, d->stream))) return rc;
+        if ((rc = d->site_dist.upload(ix->site_dist, ix->site_dist_len ? ix->site_dist_len : 1, d->stream, ix->site_dist_len))) return rc;
+        GB_CUDA(cudaStreamSynchronize(d->stream));
+        d->h_slots.assign(ix->slots, ix->slots + ix->n_slots);
+        d->h_site_dist.assign(ix->site_dist, ix->site_dist + ix->site_dist_len);
+    }
+    d->ix.slots = ix->n_slots ? d->slots.ptr : nullptr; d->ix.n_slots = (uint32_t)ix->n_slots; d->ix.site_dist = ix->n_slots ? d->site_dist.ptr : nullptr;
     d->h_node_len.resize(ix->n_nodes);
     d->h_dist.assign(ix->dist, ix->dist + ix->n_nodes / 2);
     for (uint32_t v = 0; v < ix->n_nodes; v++) d->h_node_len[v] = ix->nodes[v].len;

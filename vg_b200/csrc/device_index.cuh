@@ -26,9 +26,23 @@ struct DevIndex {
     const gb_hit* hits;
     uint64_t table_mask;
     uint32_t n_nodes, k, w;
-    const uint32_t* slot_order;      // node ids sorted by (component, slot, id): a topological order of each chain
+    const uint32_t* slot_order;      // node ids sorted by (component, slot, place in the site): a topological order of each chain
     uint32_t n_ids;
+    const gb_slot_rec* slots; uint32_t n_slots;      // site tables (gb_dist_payload); n_slots == 0: none
+    const uint16_t* site_dist;
 };
+
+// Minimum distance from the END of node id_u to the START of node id_v when both lie in the same slot (forward strand);
+// -1: not reachable.  pu / pv are their payloads as uint4 (x_in, x_out, slot, allele | component << 16).
+__device__ __forceinline__ int64_t site_distance(const DevIndex& ix, const uint4& pu, const uint4& pv) {
+    const uint32_t slot = pu.z;
+    if (slot >= ix.n_slots) return -1;
+    const gb_slot_rec sr = ix.slots[slot];
+    const uint32_t a = pu.w & 0xFFFFu, b = pv.w & 0xFFFFu;
+    if (sr.table_off == 0xFFFFFFFFu || a >= sr.n || b >= sr.n) return -1;
+    const uint16_t d = __ldg(ix.site_dist + sr.table_off + (size_t)a * sr.n + b);
+    return d == 0xFFFFu ? -1 : (int64_t)d;
+}
 
 struct DevScores { int match, mismatch, gap_open, gap_extend, full_length_bonus; };
 

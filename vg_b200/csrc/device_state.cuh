@@ -79,6 +79,8 @@ struct gb_device {
     gb::DevBuf<gb_min_cell> table;
     gb::DevBuf<gb_hit> hits;
     gb::DevBuf<uint32_t> slot_order;
+    gb::DevBuf<gb_slot_rec> slots; gb::DevBuf<uint16_t> site_dist;
+    std::vector<gb_slot_rec> h_slots; std::vector<uint16_t> h_site_dist;      // host copies (fragment-length training)
     gb::DevBuf<gb::QEntry> ws_queue;
     gb::DevBuf<gb::ArenaNode> ws_arena;
     uint32_t* work_counter = nullptr;
@@ -143,7 +145,7 @@ struct gb_device {
     gb::DevBuf<uint64_t> c_run;            // running mapping / edit totals of a host-buffer call
     uint32_t map_chunk = 1u << 20;         // reads per chunk; GIRAFFE_B200_MAP_CHUNK overrides
     void release_all() {
-        nodes.release(); seq.release(); gbwt.release(); dist.release(); table.release(); hits.release(); slot_order.release();
+        nodes.release(); seq.release(); gbwt.release(); dist.release(); table.release(); hits.release(); slot_order.release(); slots.release(); site_dist.release();
         ws_queue.release(); ws_arena.release();
         t_hit.release(); t_plo.release(); t_phred.release(); p_states.release(); p_min.release(); p_seeds.release();
         p_items.release(); p_ext_seeds.release(); p_cursors.release(); p_ext_count.release(); p_path.release(); p_mism.release();

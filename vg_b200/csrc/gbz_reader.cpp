@@ -1,6 +1,6 @@
 // gbz_reader.cpp — read a GBZ file (what `vg giraffe -Z` loads, giraffe_main.cpp:1825-1881) and build the flat index
-// from it: node sequences from the GBWTGraph, haplotype paths by walking the GBWT, the 16-byte distance payload from
-// the chain-of-bubbles decomposition of those paths, minimizers by the library's own index builder.
+// from it: node sequences from the GBWTGraph, haplotype paths by walking the GBWT; the distance payload (chains of cut
+// nodes and sites) and the minimizers come from the library's own index builder.
 //
 // gbwt (jltsiren/gbwt @ c2e0199), gbwtgraph (@ e27bc43) and simple-sds are ABSENT from the reference tree; the layout
 // below is their published serialization format, checked against the GBZ the reference ships as test data
@@ -208,82 +208,16 @@ static int index_from_gbz_impl(const char* path, uint32_t k, uint32_t w, gb_host
         if (id >= first_id) { const std::string& s = seqs[id - first_id]; node_seq.insert(node_seq.end(), s.begin(), s.end()); len[id] = (uint32_t)s.size(); }
         node_off[id] = node_seq.size();
     }
-    // ---- chain of bubbles -> distance payload ------------------------------------------------------------
-    // All haplotypes are walked in step.  Where they stand on the same node, that node is a backbone slot; where they
-    // differ, each runs to the next node common to all of them and what it passed in between is its allele: at most
-    // one node (an empty allele is a deletion).  Anything else (nested or overlapping sites, multi-node alleles,
-    // reverse-strand steps, haplotypes that do not span the chain) is outside the index model.
-    std::vector<std::vector<uint32_t>> walks;
-    for (const auto& p : paths) {
-        std::vector<uint32_t> ids;
-        for (uint32_t v : p) { if (v & 1u) return fail("reverse step on a haplotype"); ids.push_back(v >> 1); }
-        if (ids.empty()) return fail("empty haplotype");
-        if (std::find(walks.begin(), walks.end(), ids) == walks.end()) walks.push_back(ids);
-    }
-    std::vector<std::vector<uint32_t>> slots;              // allele node ids, 0 = empty allele
-    std::vector<size_t> at(walks.size(), 0);
-    while (true) {
-        bool all_end = true, any_end = false;
-        for (size_t h = 0; h < walks.size(); h++) { if (at[h] < walks[h].size()) all_end = false; else any_end = true; }
-        if (all_end) break;
-        if (any_end) return fail("haplotypes of different extent");
-        bool same = true;
-        for (size_t h = 1; h < walks.size(); h++) same &= walks[h][at[h]] == walks[0][at[0]];
-        if (same) { slots.push_back({walks[0][at[0]]}); for (size_t& a : at) a++; continue; }
-        // next node common to all haplotypes: the first node of haplotype 0 ahead that every other haplotype also has ahead
-        size_t meet0 = walks[0].size(); std::vector<size_t> meet(walks.size(), 0);
-        for (size_t x = at[0]; x < walks[0].size() && meet0 == walks[0].size(); x++) {
-            bool everywhere = true;
-            for (size_t h = 1; h < walks.size() && everywhere; h++) {
-                auto it = std::find(walks[h].begin() + at[h], walks[h].end(), walks[0][x]);
-                if (it == walks[h].end()) everywhere = false; else meet[h] = (size_t)(it - walks[h].begin());
-            }
-            if (everywhere) { meet0 = x; meet[0] = x; }
-        }
-        const bool tail_bubble = meet0 == walks[0].size();   // a site at the very end of the chain: alleles run to the end
-        std::vector<size_t> stop(walks.size());
-        size_t longest = 0, shortest = (size_t)-1;
-        for (size_t h = 0; h < walks.size(); h++) {
-            stop[h] = tail_bubble ? walks[h].size() : meet[h];
-            longest = std::max(longest, stop[h] - at[h]); shortest = std::min(shortest, stop[h] - at[h]);
-        }
-        // one site (alleles of at most one node, possibly empty), or several adjacent sites with no backbone node between
-        // them (every haplotype crosses the same number of nodes: one slot per position)
-        if (longest > 1 && shortest != longest) return fail("an allele spans several nodes");
-        const size_t n_sites = std::max<size_t>(longest, 1);
-        for (size_t j = 0; j < n_sites; j++) {
-            std::vector<uint32_t> alleles;
-            for (size_t h = 0; h < walks.size(); h++) {
-                const uint32_t a = at[h] + j < stop[h] ? walks[h][at[h] + j] : 0u;
-                if (std::find(alleles.begin(), alleles.end(), a) == alleles.end()) alleles.push_back(a);
-            }
-            if (alleles.size() < 2 && longest <= 1) return fail("degenerate site");
-            std::sort(alleles.begin(), alleles.end(), [](uint32_t a, uint32_t b) { return (a == 0) != (b == 0) ? b == 0 : a < b; });   // empty allele last
-            slots.push_back(alleles);
-        }
-        for (size_t h = 0; h < walks.size(); h++) at[h] = stop[h];
-    }
-    std::vector<gb_dist_payload> dist(n_ids + 1, gb_dist_payload{0, 0, 0, 0xFFFF, 0});
-    std::vector<bool> placed(n_ids + 1, false);
-    uint64_t prefix = 0;
-    for (size_t s = 0; s < slots.size(); s++) {
-        uint32_t slot_min = 0xFFFFFFFFu;
-        for (uint32_t a : slots[s]) slot_min = std::min(slot_min, a ? len[a] : 0u);
-        for (size_t a = 0; a < slots[s].size(); a++) {
-            const uint32_t id = slots[s][a];
-            if (!id) continue;
-            if (placed[id] || prefix + slot_min > 0xFFFFFFFFull) return fail("a node occurs twice along the chain");
-            placed[id] = true;
-            dist[id].x_in = (uint32_t)prefix; dist[id].x_out = (uint32_t)(prefix + slot_min); dist[id].slot = (uint32_t)s;
-            dist[id].allele = slots[s].size() == 1 ? 0xFFFF : (uint16_t)a; dist[id].component = 0;
-        }
-        prefix += slot_min;
-    }
+    // ---- distance payload: derived by the builder from the graph these paths span (chains of cut nodes and sites with
+    // all-pairs tables, see gb_dist_payload): nested bubbles, multi-node alleles and adjacent variants are all fine ----
+    for (const auto& p : paths) if (p.empty()) return fail("empty haplotype");
     // ---- build ----
     std::vector<uint32_t> flat; std::vector<uint64_t> path_off{0};
     for (const auto& p : paths) { flat.insert(flat.end(), p.begin(), p.end()); path_off.push_back(flat.size()); }
     if (node_seq.empty()) node_seq.push_back(0);
-    return gb_index_build((uint32_t)n_ids, node_seq.data(), node_off.data(), (uint32_t)paths.size(), flat.data(), path_off.data(), dist.data(), k, w, out);
+    const int rc = gb_index_build((uint32_t)n_ids, node_seq.data(), node_off.data(), (uint32_t)paths.size(), flat.data(), path_off.data(), nullptr, k, w, out);
+    if (rc == GB_OK && !gb_index_has_distance_model(*out)) { gb_index_free(*out); *out = nullptr; return fail("graph outside the chain model (cycle, reversing haplotype or oversized site)"); }
+    return rc;
 }
 
 extern "C" int gb_index_from_gbz(const char* path, uint32_t k, uint32_t w, gb_host_index** out) {

@@ -16,6 +16,8 @@
 #include <algorithm>
 #include <cstdio>
 #include <cstring>
+#include <functional>
+#include <map>
 #include <new>
 #include <numeric>
 #include <string>
@@ -30,6 +32,9 @@ struct gb_host_index {
     std::vector<gb_dist_payload> dist;
     std::vector<gb_min_cell> table;
     std::vector<gb_hit> hits;
+    std::vector<gb_slot_rec> slots;
+    std::vector<uint16_t> site_dist;
+    bool model_ok = true;            // the distance payload is valid (given by the caller or derived)
 };
 
 namespace {
@@ -99,6 +104,154 @@ void gbwt_visit_order(const std::vector<std::vector<uint32_t>>& seqs,
     rank_out = rank;
 }
 
+// ---- distance payload from the graph itself -------------------------------------------------------------------------
+// (what vg's SnarlDistanceIndex + zipcodes give the clusterer, snarl_seed_clusterer.cpp / zip_code.cpp, for DAGs.)
+// The graph is the forward-strand edges the haplotype paths use.  Per connected component: topological order; cut nodes
+// (every walk from a source to a sink passes them) split the order into slots — a cut node, or the site between two
+// consecutive cut nodes; x_in = minimum distance from the component's sources to the node start; x_out = x_in of the next
+// cut node minus the minimum distance from the node's end to it; per site the all-pairs table end(u) -> start(v).
+// Returns false for anything outside that model (a reverse step, a cycle, an oversized site).
+constexpr uint32_t MAX_SITE_NODES = 4096;
+
+bool derive_distance_payload(uint32_t n_node_ids, const std::vector<uint32_t>& len /* by id */, const std::vector<std::vector<uint32_t>>& fwd_paths,
+                             std::vector<gb_dist_payload>& dist, std::vector<gb_slot_rec>& slots, std::vector<uint16_t>& site_dist) {
+    const uint32_t N = n_node_ids + 1;
+    std::vector<std::vector<uint32_t>> succ(N), pred(N);
+    std::vector<bool> used(N, false);
+    {
+        std::vector<std::pair<uint32_t, uint32_t>> edges;
+        for (const auto& p : fwd_paths) {
+            for (size_t i = 0; i < p.size(); i++) {
+                if (p[i] & 1u) return false;                      // a haplotype steps onto a reverse strand
+                used[p[i] >> 1] = true;
+                if (i) edges.emplace_back(p[i - 1] >> 1, p[i] >> 1);
+            }
+        }
+        std::sort(edges.begin(), edges.end());
+        edges.erase(std::unique(edges.begin(), edges.end()), edges.end());
+        for (const auto& e : edges) { succ[e.first].push_back(e.second); pred[e.second].push_back(e.first); }
+    }
+    dist.assign(N, gb_dist_payload{0, 0, 0, 0xFFFF, 0});
+    slots.clear(); site_dist.clear();
+    // components (undirected)
+    std::vector<int32_t> comp(N, -1);
+    uint32_t n_comp = 0;
+    for (uint32_t s = 1; s < N; s++) {
+        if (!used[s] || comp[s] >= 0) continue;
+        std::vector<uint32_t> stack{s}; comp[s] = (int32_t)n_comp;
+        while (!stack.empty()) {
+            const uint32_t v = stack.back(); stack.pop_back();
+            for (uint32_t w : succ[v]) if (comp[w] < 0) { comp[w] = (int32_t)n_comp; stack.push_back(w); }
+            for (uint32_t w : pred[v]) if (comp[w] < 0) { comp[w] = (int32_t)n_comp; stack.push_back(w); }
+        }
+        n_comp++;
+    }
+    if (n_comp > 0xFFFF) return false;
+    // one topological order over everything (Kahn, smallest id first: deterministic)
+    std::vector<uint32_t> indeg(N, 0), order;
+    for (uint32_t v = 1; v < N; v++) indeg[v] = (uint32_t)pred[v].size();
+    {
+        std::vector<uint32_t> ready;
+        for (uint32_t v = N; v-- > 1;) if (used[v] && indeg[v] == 0) ready.push_back(v);       // descending: pop_back yields the smallest
+        while (!ready.empty()) {
+            const uint32_t v = ready.back(); ready.pop_back();
+            order.push_back(v);
+            bool pushed = false;
+            for (uint32_t w : succ[v]) if (--indeg[w] == 0) { ready.push_back(w); pushed = true; }
+            if (pushed) std::sort(ready.begin(), ready.end(), std::greater<uint32_t>());
+        }
+        size_t n_used = 0; for (uint32_t v = 1; v < N; v++) n_used += used[v];
+        if (order.size() != n_used) return false;                 // a cycle
+    }
+    // per component: the nodes in topological order
+    std::vector<std::vector<uint32_t>> comp_order(n_comp);
+    for (uint32_t v : order) comp_order[(size_t)comp[v]].push_back(v);
+    const uint64_t INF = ~0ull;
+    std::vector<uint64_t> dS(N, INF);          // min distance from the component's sources to the node start
+    std::vector<uint64_t> dX(N, 0);
+    for (uint32_t c = 0; c < n_comp; c++) {
+        const auto& ord = comp_order[c];
+        for (uint32_t v : ord) {
+            if (pred[v].empty()) dS[v] = 0;
+            for (uint32_t p : pred[v]) dS[v] = std::min(dS[v], dS[p] + len[p]);
+            if (dS[v] > 0xFFFFFFF0ull) return false;
+        }
+        // cut nodes: every walk from a source to a sink passes them.  Sweep the order counting open edges (tail placed, head
+        // not), with one virtual edge into every source and one out of every sink: v is a cut node exactly when all open
+        // edges point at v as it comes up (an earlier sink keeps its virtual edge open for good, a waiting source too).
+        std::vector<bool> is_cut(ord.size(), false);
+        {
+            uint64_t open = 0;
+            for (uint32_t v : ord) open += pred[v].empty();
+            for (size_t i = 0; i < ord.size(); i++) {
+                const uint32_t v = ord[i];
+                const uint64_t into_v = pred[v].empty() ? 1 : pred[v].size();
+                is_cut[i] = (open == into_v);
+                open -= into_v;
+                open += succ[v].empty() ? 1 : succ[v].size();
+            }
+        }
+        // slots along the chain
+        size_t i = 0;
+        while (i < ord.size()) {
+            const uint32_t slot = (uint32_t)slots.size();
+            if (is_cut[i]) {
+                const uint32_t v = ord[i];
+                dist[v] = gb_dist_payload{(uint32_t)dS[v], (uint32_t)(dS[v] + len[v]), slot, 0xFFFF, (uint16_t)c};
+                slots.push_back(gb_slot_rec{0xFFFFFFFFu, 1u});
+                i++;
+                continue;
+            }
+            size_t j = i;
+            while (j < ord.size() && !is_cut[j]) j++;
+            const uint32_t n = (uint32_t)(j - i);
+            if (n > MAX_SITE_NODES) return false;
+            // exit coordinate: the next cut node's start, or (no cut node behind the site) the end of the chain
+            uint64_t exit_coord;
+            if (j < ord.size()) exit_coord = dS[ord[j]];
+            else { exit_coord = 0; bool any = false; for (size_t x = i; x < j; x++) if (succ[ord[x]].empty()) { const uint64_t e = dS[ord[x]] + len[ord[x]]; exit_coord = any ? std::min(exit_coord, e) : e; any = true; } }
+            // distance from each node's end to the exit (reverse order); nodes that cannot reach it keep INF
+            std::vector<uint64_t> to_exit(n, INF);
+            std::vector<uint32_t> local(n);
+            std::map<uint32_t, uint32_t> li_of;
+            for (uint32_t x = 0; x < n; x++) { local[x] = ord[i + x]; li_of[local[x]] = x; }
+            for (uint32_t x = n; x-- > 0;) {
+                const uint32_t v = local[x];
+                if (succ[v].empty()) { to_exit[x] = 0; continue; }                 // ends the chain here
+                for (uint32_t w : succ[v]) {
+                    if (j < ord.size() && w == ord[j]) to_exit[x] = 0;
+                    else { auto it = li_of.find(w); if (it != li_of.end() && to_exit[it->second] != INF) to_exit[x] = std::min(to_exit[x], to_exit[it->second] + len[w]); }
+                }
+            }
+            const uint32_t table_off = (uint32_t)site_dist.size();
+            if ((uint64_t)table_off + (uint64_t)n * n > 0xFFFFFFF0ull) return false;
+            site_dist.resize((size_t)table_off + (size_t)n * n, 0xFFFF);
+            for (uint32_t a = 0; a < n; a++) {
+                // D[a][b]: min distance from the end of a to the start of b, forward in topological order
+                std::vector<uint64_t> row(n, INF);
+                for (uint32_t b = a + 1; b < n; b++) {
+                    for (uint32_t p : pred[local[b]]) {
+                        auto it = li_of.find(p);
+                        if (it == li_of.end()) continue;
+                        const uint32_t pl = it->second;
+                        if (pl == a) row[b] = 0;
+                        else if (pl > a && row[pl] != INF) row[b] = std::min(row[b], row[pl] + len[p]);
+                    }
+                    if (row[b] != INF) { if (row[b] >= 0xFFFF) return false; site_dist[(size_t)table_off + (size_t)a * n + b] = (uint16_t)row[b]; }
+                }
+            }
+            for (uint32_t x = 0; x < n; x++) {
+                const uint32_t v = local[x];
+                const uint64_t xo = to_exit[x] == INF ? dS[v] + len[v] : exit_coord - std::min(exit_coord, to_exit[x]);
+                dist[v] = gb_dist_payload{(uint32_t)dS[v], (uint32_t)xo, slot, (uint16_t)x, (uint16_t)c};
+            }
+            slots.push_back(gb_slot_rec{table_off, n});
+            i = j;
+        }
+    }
+    return true;
+}
+
 } // namespace
 
 static int index_build_impl(uint32_t n_node_ids, const uint8_t* node_seq, const uint64_t* node_off,
@@ -132,6 +285,20 @@ static int index_build_impl(uint32_t n_node_ids, const uint8_t* node_seq, const 
 
     ix->dist.assign(n_node_ids + 1, gb_dist_payload{0, 0, 0, 0xFFFF, 0});
     if (dist) for (uint32_t id = 1; id <= n_node_ids; id++) ix->dist[id] = dist[id];
+    else {
+        std::vector<uint32_t> len_by_id(n_node_ids + 1, 0);
+        for (uint32_t id = 1; id <= n_node_ids; id++) len_by_id[id] = (uint32_t)(node_off[id] - node_off[id - 1]);
+        std::vector<std::vector<uint32_t>> fwd(n_paths);
+        for (uint32_t p = 0; p < n_paths; p++) fwd[p].assign(path_nodes + path_off[p], path_nodes + path_off[p + 1]);
+        for (const auto& f : fwd) for (uint32_t v : f) if (v < 2 || v >= ix->n_nodes) { delete ix; return GB_ERR_FORMAT; }
+        if (!derive_distance_payload(n_node_ids, len_by_id, fwd, ix->dist, ix->slots, ix->site_dist)) {
+            // outside the chain model (a cycle, a reversing haplotype, an oversized site): the graph, GBWT and minimizers are
+            // still built, so the stage seams work on it (the reference's cyclic WFA test graphs), but there is no
+            // distance payload: gb_index_has_distance_model() says so and gb_index_from_gbz refuses such a file
+            ix->dist.assign(n_node_ids + 1, gb_dist_payload{0, 0, 0, 0xFFFF, 0});
+            ix->slots.clear(); ix->site_dist.clear(); ix->model_ok = false;
+        }
+    }
 
     // --- bidirectional GBWT ---
     std::vector<std::vector<uint32_t>> seqs(2 * (size_t)n_paths);
@@ -267,6 +434,7 @@ extern "C" int gb_index_build(uint32_t n_node_ids, const uint8_t* node_seq, cons
 }
 
 extern "C" void gb_index_free(gb_host_index* ix) { delete ix; }
+extern "C" int gb_index_has_distance_model(const gb_host_index* ix) { return ix && ix->model_ok ? 1 : 0; }
 
 extern "C" int gb_index_view(const gb_host_index* ix, gb_flat_index* out) {
     if (!ix || !out) return GB_ERR_ARG;
@@ -277,13 +445,16 @@ extern "C" int gb_index_view(const gb_host_index* ix, gb_flat_index* out) {
     out->dist = ix->dist.data();
     out->table = ix->table.data(); out->table_cells = ix->table.size();
     out->hits = ix->hits.data(); out->n_hits = ix->hits.size();
+    out->slots = ix->slots.data(); out->n_slots = ix->slots.size();
+    out->site_dist = ix->site_dist.data(); out->site_dist_len = ix->site_dist.size();
     return GB_OK;
 }
 
 // ---- the flat index on disk ("GBZ-flat" file) ----------------------------------------------------------------
 // What giraffe_main.cpp:1825-1881 does for GBZ / .min / .dist files, for the library's own layout: one file,
 // a 64-byte header and the six arrays of gb_flat_index back to back, each padded to 16 bytes.  Little endian.
-//   header: magic "GBFLAT1\0", n_nodes, k, w, n_paths (u32 each), seq_bytes, gbwt_words, table_cells, n_hits (u64 each), 8 B zero
+//   header: magic "GBFLAT2\0", n_nodes, k, w, n_paths (u32 each), seq_bytes, gbwt_words, table_cells, n_hits (u64 each), 8 B zero,
+//           n_slots, site_dist_len (u64 each); then nodes, seq, gbwt, dist, table, hits, slots, site_dist
 namespace {
 
 struct FlatFileHeader {
@@ -291,8 +462,9 @@ struct FlatFileHeader {
     uint32_t n_nodes, k, w, n_paths;
     uint64_t seq_bytes, gbwt_words, table_cells, n_hits;
     uint64_t reserved;
+    uint64_t n_slots, site_dist_len;
 };
-static_assert(sizeof(FlatFileHeader) == 64, "flat file header is 64 bytes");
+static_assert(sizeof(FlatFileHeader) == 80, "flat file header is 80 bytes");
 
 bool write_padded(FILE* f, const void* p, size_t bytes) {
     static const char zero[16] = {0};
@@ -316,16 +488,19 @@ extern "C" int gb_index_save(const gb_flat_index* ix, const char* path) {
     FILE* f = fopen(path, "wb");
     if (!f) return GB_ERR_FORMAT;
     FlatFileHeader h; memset(&h, 0, sizeof h);
-    memcpy(h.magic, "GBFLAT1", 8);
+    memcpy(h.magic, "GBFLAT2", 8);
     h.n_nodes = ix->n_nodes; h.k = ix->k; h.w = ix->w; h.n_paths = ix->n_paths;
     h.seq_bytes = ix->seq_bytes; h.gbwt_words = ix->gbwt_words; h.table_cells = ix->table_cells; h.n_hits = ix->n_hits;
+    h.n_slots = ix->n_slots; h.site_dist_len = ix->site_dist_len;
     bool ok = fwrite(&h, 1, sizeof h, f) == sizeof h
         && write_padded(f, ix->nodes, (size_t)ix->n_nodes * sizeof(gb_node_rec))
         && write_padded(f, ix->seq, ix->seq_bytes)
         && write_padded(f, ix->gbwt, ix->gbwt_words * 4)
         && write_padded(f, ix->dist, (size_t)(ix->n_nodes / 2) * sizeof(gb_dist_payload))
         && write_padded(f, ix->table, ix->table_cells * sizeof(gb_min_cell))
-        && write_padded(f, ix->hits, ix->n_hits * sizeof(gb_hit));
+        && write_padded(f, ix->hits, ix->n_hits * sizeof(gb_hit))
+        && write_padded(f, ix->slots, ix->n_slots * sizeof(gb_slot_rec))
+        && write_padded(f, ix->site_dist, ix->site_dist_len * sizeof(uint16_t));
     ok = (fclose(f) == 0) && ok;
     return ok ? GB_OK : GB_ERR_FORMAT;
 }
@@ -336,20 +511,22 @@ static int index_load_impl(const char* path, gb_host_index** out) {
     FILE* f = fopen(path, "rb");
     if (!f) return GB_ERR_FORMAT;
     FlatFileHeader h;
-    if (fread(&h, 1, sizeof h, f) != sizeof h || memcmp(h.magic, "GBFLAT1", 8) != 0) { fclose(f); return GB_ERR_FORMAT; }
+    if (fread(&h, 1, sizeof h, f) != sizeof h || memcmp(h.magic, "GBFLAT2", 8) != 0) { fclose(f); return GB_ERR_FORMAT; }
     // plausibility before allocating: a power-of-two table, an even number of oriented nodes, sizes the file can hold
     fseek(f, 0, SEEK_END); const uint64_t file_bytes = (uint64_t)ftell(f); fseek(f, (long)sizeof h, SEEK_SET);
     // every count is bounded by the file size on its own first (a crafted header must not wrap the sum), then the sum
     const bool counts_ok = h.seq_bytes <= file_bytes && h.gbwt_words <= file_bytes / 4 && h.table_cells <= file_bytes / sizeof(gb_min_cell)
-                        && h.n_hits <= file_bytes / sizeof(gb_hit) && (uint64_t)h.n_nodes <= file_bytes / sizeof(gb_node_rec);
+                        && h.n_hits <= file_bytes / sizeof(gb_hit) && (uint64_t)h.n_nodes <= file_bytes / sizeof(gb_node_rec)
+                        && h.n_slots <= file_bytes / sizeof(gb_slot_rec) && h.site_dist_len <= file_bytes / sizeof(uint16_t);
     const uint64_t need = !counts_ok ? ~0ull : (uint64_t)h.n_nodes * sizeof(gb_node_rec) + h.seq_bytes + h.gbwt_words * 4 + (uint64_t)(h.n_nodes / 2) * sizeof(gb_dist_payload)
-                        + h.table_cells * sizeof(gb_min_cell) + h.n_hits * sizeof(gb_hit);
+                        + h.table_cells * sizeof(gb_min_cell) + h.n_hits * sizeof(gb_hit) + h.n_slots * sizeof(gb_slot_rec) + h.site_dist_len * sizeof(uint16_t);
     if (!counts_ok || h.n_nodes % 2 != 0 || h.n_nodes < 2 || h.table_cells == 0 || (h.table_cells & (h.table_cells - 1)) != 0 || h.k == 0 || h.k > 31 || h.w == 0
         || h.seq_bytes < 16 || h.seq_bytes > 0xffffffffull || h.gbwt_words > 0xffffffffull || h.n_hits > 0xffffffffull || need > file_bytes) { fclose(f); return GB_ERR_FORMAT; }
     gb_host_index* ix = new gb_host_index();
     ix->n_nodes = h.n_nodes; ix->k = h.k; ix->w = h.w; ix->n_paths = h.n_paths;
     const bool ok = read_padded(f, ix->nodes, h.n_nodes) && read_padded(f, ix->seq, h.seq_bytes) && read_padded(f, ix->gbwt, h.gbwt_words)
-                 && read_padded(f, ix->dist, h.n_nodes / 2) && read_padded(f, ix->table, h.table_cells) && read_padded(f, ix->hits, h.n_hits);
+                 && read_padded(f, ix->dist, h.n_nodes / 2) && read_padded(f, ix->table, h.table_cells) && read_padded(f, ix->hits, h.n_hits)
+                 && read_padded(f, ix->slots, h.n_slots) && read_padded(f, ix->site_dist, h.site_dist_len);
     fclose(f);
     if (!ok) { delete ix; return GB_ERR_FORMAT; }
     // offsets must stay inside the arrays (a truncated or foreign file must not make the kernels read out of bounds)
@@ -367,6 +544,11 @@ static int index_load_impl(const char* path, gb_host_index** out) {
         for (uint64_t t = 0; t < n_runs; t++) if ((rec[2 + 2 * n_edges + t] & 1023u) >= n_edges) { delete ix; return GB_ERR_FORMAT; }
     }
     for (const gb_hit& hit : ix->hits) if ((hit.pos >> 10) >= h.n_nodes) { delete ix; return GB_ERR_FORMAT; }
+    // slot tables stay inside site_dist, and a node that claims a place in a site table really has one
+    for (const gb_slot_rec& sr : ix->slots)
+        if (sr.table_off != 0xFFFFFFFFu && (uint64_t)sr.table_off + (uint64_t)sr.n * sr.n > h.site_dist_len) { delete ix; return GB_ERR_FORMAT; }
+    if (h.n_slots) for (const gb_dist_payload& dp : ix->dist)
+        if (dp.allele != 0xFFFF && dp.slot < h.n_slots && ix->slots[dp.slot].table_off != 0xFFFFFFFFu && dp.allele >= ix->slots[dp.slot].n) { delete ix; return GB_ERR_FORMAT; }
     for (const gb_min_cell& c : ix->table)
         if (c.key != GB_NO_KEY && (uint64_t)c.hit_off + c.hit_cnt > h.n_hits) { delete ix; return GB_ERR_FORMAT; }
     *out = ix;

@@ -36,6 +36,30 @@ __device__ __forceinline__ uint32_t rng_next(DevRng& r) {
     return r.state;
 }
 
+// minstd_rand is a pure multiplicative generator, x_n = 48271^n x_0 mod (2^31 - 1): draw n of a batch is one modular power
+// away from the state, so the lanes of a warp can take the next 32 draws at once (tie shuffles) instead of lane 0 walking them.
+__device__ __forceinline__ uint32_t minstd_mulmod(uint32_t a, uint32_t b) {
+    const uint64_t p = (uint64_t)a * b;                                     // < 2^62
+    uint64_t s = (p & 0x7fffffffull) + (p >> 31);                           // < 2^32
+    s = (s & 0x7fffffffull) + (s >> 31);
+    return s >= 2147483647ull ? (uint32_t)(s - 2147483647ull) : (uint32_t)s;
+}
+__device__ __forceinline__ uint32_t minstd_pow(uint32_t e) {               // 48271^e mod (2^31 - 1)
+    uint32_t r = 1, b = 48271u;
+    while (e) { if (e & 1u) r = minstd_mulmod(r, b); b = minstd_mulmod(b, b); e >>= 1; }
+    return r;
+}
+// The n-th next draw (n >= 1) without advancing; rng_skip(r, n) then moves the state past n draws.
+__device__ __forceinline__ uint32_t rng_peek(DevRng r, uint32_t n) {
+    if (!r.inited) { const uint32_t x = r.seed % 2147483647u; r.state = x == 0 ? 1u : x; }
+    return minstd_mulmod(r.state, minstd_pow(n));
+}
+__device__ __forceinline__ void rng_skip(DevRng& r, uint32_t n) {
+    if (n == 0) return;
+    if (!r.inited) { const uint32_t x = r.seed % 2147483647u; r.state = x == 0 ? 1u : x; r.inited = 1; }
+    r.state = minstd_mulmod(r.state, minstd_pow(n));
+}
+
 // One minimizer of the read in SCORE order (MinimizerMapper::Minimizer, minimizer_mapper.hpp:565).
 struct __align__(16) DevMinimizer {
     uint64_t hash;

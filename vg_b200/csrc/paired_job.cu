@@ -109,6 +109,13 @@ int64_t host_oriented_distance(const gb_device* d, uint32_t node_a, uint32_t off
     if (ps.component != pd.component) return UNREACHABLE;
     if ((src >> 1) == (dst >> 1)) return dst_off >= src_off ? dst_off - src_off : UNREACHABLE;
     if (ps.slot < pd.slot) return (src_len - src_off) + ((int64_t)pd.x_in - (int64_t)ps.x_out) + dst_off;
+    if (ps.slot == pd.slot && ps.slot < d->h_slots.size()) {
+        const gb_slot_rec& sr = d->h_slots[ps.slot];
+        if (sr.table_off != 0xFFFFFFFFu && ps.allele < sr.n && pd.allele < sr.n) {
+            const uint16_t t = d->h_site_dist[sr.table_off + (size_t)ps.allele * sr.n + pd.allele];
+            if (t != 0xFFFF) return (src_len - src_off) + (int64_t)t + dst_off;
+        }
+    }
     return UNREACHABLE;
 }
 

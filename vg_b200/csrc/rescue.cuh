@@ -61,8 +61,15 @@ __device__ __forceinline__ bool rescue_in_range(const DevIndex& ix, uint32_t id,
     const uint4 pv = __ldg(reinterpret_cast<const uint4*>(ix.dist) + id);
     if ((ps.w >> 16) != (pv.w >> 16)) return false;
     int64_t d0;
-    if (!(start_node & 1u)) { if (!(ps.z < pv.z)) return false; d0 = to_end + ((int64_t)pv.x - (int64_t)ps.y); }
-    else { if (!(pv.z < ps.z)) return false; d0 = to_end + ((int64_t)ps.x - (int64_t)pv.y); }
+    if (!(start_node & 1u)) {
+        if (ps.z < pv.z) d0 = to_end + ((int64_t)pv.x - (int64_t)ps.y);
+        else if (ps.z == pv.z) { const int64_t t = site_distance(ix, ps, pv); if (t < 0) return false; d0 = to_end + t; }
+        else return false;
+    } else {
+        if (pv.z < ps.z) d0 = to_end + ((int64_t)ps.x - (int64_t)pv.y);
+        else if (ps.z == pv.z) { const int64_t t = site_distance(ix, pv, ps); if (t < 0) return false; d0 = to_end + t; }
+        else return false;
+    }
     const int64_t len = load_node(ix, 2 * id).len;
     return d0 <= max_distance && d0 + len > min_distance;
 }
@@ -70,6 +77,7 @@ __device__ __forceinline__ bool rescue_slot_less(const DevIndex& ix, uint32_t a,
     const uint4 pa = __ldg(reinterpret_cast<const uint4*>(ix.dist) + a), pb = __ldg(reinterpret_cast<const uint4*>(ix.dist) + b);
     if ((pa.w >> 16) != (pb.w >> 16)) return (pa.w >> 16) < (pb.w >> 16);
     if (pa.z != pb.z) return pa.z < pb.z;
+    if ((pa.w & 0xFFFFu) != (pb.w & 0xFFFFu)) return (pa.w & 0xFFFFu) < (pb.w & 0xFFFFu);     // place inside the site = topological
     return a < b;
 }
 

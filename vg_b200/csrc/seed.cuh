@@ -177,7 +177,20 @@ __device__ __forceinline__ bool any_bit_in_range(const uint32_t* words, uint32_t
 }
 
 // unoriented minimum graph distance <= limit between two seeds (see gb_dist_payload)
-__device__ __forceinline__ bool seeds_within(const DevSeed& a, const DevSeed& b, int32_t limit) {
+// Two different nodes of one site: distance through the site's table (either direction), INT_MAX when unreachable.
+// id_off = (node id << 10) | forward offset; c_in = x_in + offset, c_out = x_out - (length - offset).
+__device__ __noinline__ int32_t same_site_distance(const DevIndex& ix, uint32_t ido_a, int32_t c_in_a, int32_t c_out_a, uint32_t ido_b, int32_t c_in_b, int32_t c_out_b) {
+    if (ix.n_slots == 0) return INT_MAX;
+    const uint4 pa = __ldg(reinterpret_cast<const uint4*>(ix.dist) + (ido_a >> 10)), pb = __ldg(reinterpret_cast<const uint4*>(ix.dist) + (ido_b >> 10));
+    int64_t best = -1;
+    int64_t t = site_distance(ix, pa, pb);                       // a -> b: rest of a + table + offset in b
+    if (t >= 0) best = ((int64_t)pa.y - c_out_a) + t + ((int64_t)c_in_b - (int64_t)pb.x);
+    t = site_distance(ix, pb, pa);
+    if (t >= 0) { const int64_t d = ((int64_t)pb.y - c_out_b) + t + ((int64_t)c_in_a - (int64_t)pa.x); if (best < 0 || d < best) best = d; }
+    return best < 0 || best > INT_MAX - 1 ? INT_MAX : (int32_t)best;
+}
+
+__device__ __forceinline__ bool seeds_within(const DevIndex& ix, const DevSeed& a, const DevSeed& b, int32_t limit) {
     const uint32_t ida = a.id_off >> 10, idb = b.id_off >> 10;
     if (ida == idb) {
         const int32_t d = (int32_t)(b.id_off & 1023u) - (int32_t)(a.id_off & 1023u);
@@ -185,7 +198,7 @@ __device__ __forceinline__ bool seeds_within(const DevSeed& a, const DevSeed& b,
     }
     if (a.slot < b.slot) return (b.c_in - a.c_out) <= limit;
     if (b.slot < a.slot) return (a.c_in - b.c_out) <= limit;
-    return false;
+    return same_site_distance(ix, a.id_off, a.c_in, a.c_out, b.id_off, b.c_in, b.c_out) <= limit;
 }
 
 // -----------------------------------------------------------------------------------------
@@ -372,13 +385,21 @@ __device__ __forceinline__ uint32_t seed_phase_a(const DevIndex& ix, const MapPa
                 before += __popc(starts);
             }
             __syncwarp();
-            if (lane == 0) {
-                for (uint32_t i = 1; i < T; i++) {
-                    const uint32_t j = rng_next(rng) % (i + 1);
-                    const uint8_t tb = run_begin[j], tl = run_len[j];
-                    run_begin[j] = run_begin[i]; run_len[j] = run_len[i];
-                    run_begin[i] = tb; run_len[i] = tl;
+            // Knuth shuffle, swap(i, rng() % (i + 1)) for i = 1 .. T-1 (utility.hpp:722-728): the T - 1 draws are taken by the
+            // lanes in parallel (draw i is 48271^i away from the state), only the swaps themselves stay in order
+            {
+                uint8_t* draw_j = tmp_order;                                   // [T] scratch until the runs are laid out below
+                for (uint32_t i = 1 + lane; i < T; i += 32) draw_j[i] = (uint8_t)(rng_peek(rng, i) % (i + 1));
+                __syncwarp();
+                if (lane == 0) {
+                    for (uint32_t i = 1; i < T; i++) {
+                        const uint32_t j = draw_j[i];
+                        const uint8_t tb = run_begin[j], tl = run_len[j];
+                        run_begin[j] = run_begin[i]; run_len[j] = run_len[i];
+                        run_begin[i] = tb; run_len[i] = tl;
+                    }
                 }
+                rng_skip(rng, T - 1);
             }
             __syncwarp();
             uint32_t carry = 0;
@@ -564,7 +585,7 @@ __device__ __forceinline__ uint32_t seed_phase_a(const DevIndex& ix, const MapPa
 }
 
 // Label propagation: every seed's label becomes the smallest label reachable within `limit`.
-__device__ __forceinline__ void propagate_labels(DevSeed* seeds_a, uint32_t na, DevSeed* seeds_b, uint32_t nb, int32_t limit) {
+__device__ __forceinline__ void propagate_labels(const DevIndex& ix, DevSeed* seeds_a, uint32_t na, DevSeed* seeds_b, uint32_t nb, int32_t limit) {
     const int lane = lane_id();
     const uint32_t n = na + nb;
     while (true) {
@@ -576,7 +597,7 @@ __device__ __forceinline__ void propagate_labels(DevSeed* seeds_a, uint32_t na, 
             for (uint32_t j = 0; j < n; j++) {
                 if (j == i) continue;
                 const DevSeed sj = j < na ? seeds_a[j] : seeds_b[j - na];
-                if (sj.label < best && seeds_within(si, sj, limit)) best = sj.label;
+                if (sj.label < best && seeds_within(ix, si, sj, limit)) best = sj.label;
             }
             if (best != si.label) { pi->label = best; changed = true; }
         }
@@ -749,7 +770,7 @@ __device__ __forceinline__ uint32_t cluster_phase_se(const DevIndex& ix, const M
     const DevMinimizer* mins = pools.minimizers + rs.min_off;
     const ClusterScratch cs = carve_cluster_scratch(sm);
     const int32_t limit = (int32_t)max(P.distance_limit, L + 50);      // get_distance_limit, minimizer_mapper.hpp:554
-    propagate_labels(seeds, H, seeds, 0, limit);
+    propagate_labels(ix, seeds, H, seeds, 0, limit);
     const uint32_t Cn = collect_clusters(sm, cs, seeds, H, mins, M, ix.k, L, 0);
     if (Cn == 0xffffffffu) return table_full(sm.Cc, MAX_CLUSTERS);
     rs.n_clusters = Cn;
@@ -839,11 +860,11 @@ __device__ __forceinline__ uint32_t cluster_phase_pe(const DevIndex& ix, const M
 #pragma unroll
         for (uint32_t q = 0; q < 2; q++) { const uint32_t i = lane + 32 * q; has[q] = i < n_all; own[q] = has[q] ? cs.seedbuf[i] : make_uint4(0, 0, 0, 0); }
         // unoriented minimum distance through the payload, as seeds_within; INT_MAX when unreachable
-        auto seed_dist = [](const uint4& a, const uint4& c) -> int32_t {
+        auto seed_dist = [&ix](const uint4& a, const uint4& c) -> int32_t {
             if ((a.x >> 10) == (c.x >> 10)) { const int32_t d = (int32_t)(c.x & 1023u) - (int32_t)(a.x & 1023u); return d >= 0 ? d : -d; }
             if (a.w < c.w) return (int32_t)c.y - (int32_t)a.z;
             if (c.w < a.w) return (int32_t)a.y - (int32_t)c.z;
-            return INT_MAX;
+            return same_site_distance(ix, a.x, (int32_t)a.y, (int32_t)a.z, c.x, (int32_t)c.y, (int32_t)c.z);
         };
         // rows of seeds 0..31: lane i walks all j
         for (uint32_t j = 0; j < n_all; j++) {
@@ -931,7 +952,7 @@ __device__ __forceinline__ uint32_t cluster_phase_pe(const DevIndex& ix, const M
             for (uint32_t i = lane; i < na; i += 32) sa[i].label = i;
             for (uint32_t i = lane; i < nb; i += 32) s1[i].label = na + i;
             __syncwarp();
-            propagate_labels(sa, na, s1, nb, pass == 0 ? fragment_limit : read_limit);
+            propagate_labels(ix, sa, na, s1, nb, pass == 0 ? fragment_limit : read_limit);
             if (pass == 0) {
                 for (uint32_t i = lane; i < H0; i += 32) s0[i].source |= s0[i].label << 8;
                 for (uint32_t i = lane; i < H1; i += 32) s1[i].source |= s1[i].label << 8;

@@ -321,3 +321,59 @@ def truth_seeds(g: SynthGraph, rs: ReadSet, read_offsets=(0, 37, 74, 111), false
             sd.append((2 * nid + int(rng.integers(0, 2)), int(rng.integers(0, L)) - off))
         items.append((i, sd))
     return items
+
+
+def make_nested_graph(n_items=60, n_haps=10, seed=7, max_depth=2, name="nested") -> SynthGraph:
+    """A chain whose sites are everything the flat chain-of-bubbles model could not hold: alleles of several nodes,
+    bubbles nested inside alleles, deletions (empty alleles), sites that touch each other without a backbone node
+    between them.  No payload is passed: the index builder derives chains, sites and site tables from the graph the
+    haplotypes span (gb_index_build with dist = NULL)."""
+    rng = np.random.default_rng(seed)
+    node_seqs = []
+
+    def new_node(lo=1, hi=32):
+        node_seqs.append(bytes(BASES[rng.integers(0, 4, size=int(rng.integers(lo, hi + 1)))]).decode())
+        return len(node_seqs)
+
+    def gen_chain(n, depth, backbone_ends):
+        items = []
+        for i in range(n):
+            r = rng.random()
+            if (backbone_ends and (i == 0 or i == n - 1)) or r < 0.45 or depth == 0 and r < 0.6:
+                items.append(("node", new_node(8, 32)))
+            elif r < 0.65:
+                items.append(("site", [[("node", new_node(1, 1))] for _ in range(int(rng.integers(2, 5)))]))          # SNP
+            elif r < 0.78:
+                items.append(("site", [[("node", new_node(1, 12))], []]))                                               # indel
+            elif r < 0.9 or depth == 0:
+                items.append(("site", [[("node", new_node(1, 32)) for _ in range(int(rng.integers(1, 4)))] for _ in range(int(rng.integers(2, 4)))]))   # multi-node alleles
+            else:
+                items.append(("site", [gen_chain(int(rng.integers(1, 4)), depth - 1, False) for _ in range(int(rng.integers(2, 4)))]))                    # nested
+        return items
+
+    chain = gen_chain(n_items, max_depth, True)
+
+    def walk(items, choose, out):
+        for it in items:
+            if it[0] == "node":
+                out.append(2 * it[1])
+            else:
+                alleles = it[1]
+                walk(alleles[choose(id(it), len(alleles))], choose, out)
+
+    paths = []
+    for h in range(n_haps):
+        memo = {}
+
+        def choose(key, n, h=h, memo=memo):
+            if key not in memo:
+                memo[key] = (h + len(memo)) % n if h < 4 else int(rng.integers(0, n))
+            return memo[key]
+        p = []
+        walk(chain, choose, p)
+        paths.append(p)
+    used = sorted({v >> 1 for p in paths for v in p})
+    remap = {old: new + 1 for new, old in enumerate(used)}           # drop nodes no haplotype visits
+    node_seqs = [node_seqs[o - 1] for o in used]
+    paths = [[2 * remap[v >> 1] for v in p] for p in paths]
+    return SynthGraph(node_seqs, paths, None, slots=None, name=name).finish()
