@@ -20,7 +20,22 @@ struct ExtView {                           // outputs of the extension kernel
     const uint32_t* ext_count; const uint8_t* ext_status;
     const gb_extension* ext; const uint32_t* path_pool; const uint32_t* mism_pool;
     uint32_t max_ext, path_cap, mism_cap;
+    // items redone with large strides (ExtendBig): big_of[item] != 0xffffffff selects the large pools
+    const uint32_t* big_of; const gb_extension* big_ext; const uint32_t* big_path; const uint32_t* big_mism;
+    uint32_t big_max_ext, big_path_cap, big_mism_cap;
 };
+__device__ __forceinline__ const gb_extension* ev_ext(const ExtView& ev, uint32_t item) {
+    const uint32_t s = ev.big_of ? ev.big_of[item] : 0xffffffffu;
+    return s == 0xffffffffu ? ev.ext + (size_t)item * ev.max_ext : ev.big_ext + (size_t)s * ev.big_max_ext;
+}
+__device__ __forceinline__ const uint32_t* ev_path(const ExtView& ev, uint32_t item) {
+    const uint32_t s = ev.big_of ? ev.big_of[item] : 0xffffffffu;
+    return s == 0xffffffffu ? ev.path_pool + (size_t)item * ev.path_cap : ev.big_path + (size_t)s * ev.big_path_cap;
+}
+__device__ __forceinline__ const uint32_t* ev_mism(const ExtView& ev, uint32_t item) {
+    const uint32_t s = ev.big_of ? ev.big_of[item] : 0xffffffffu;
+    return s == 0xffffffffu ? ev.mism_pool + (size_t)item * ev.mism_cap : ev.big_mism + (size_t)s * ev.big_mism_cap;
+}
 
 struct CandBuf {                           // per-warp scratch for candidate alignments
     gb_mapping* maps; uint32_t* edits;     // [MAX_CANDS][map_cap] / [MAX_CANDS][edit_cap]

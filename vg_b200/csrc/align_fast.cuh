@@ -114,7 +114,7 @@ __device__ inline bool fast_pair(const DevIndex& ix, const MapParamsDev& P, cons
         for (uint32_t s = 0; s < S; s++) {
             const uint32_t item = rs.item_off + s;
             if (a.ev.ext_status[item] != GB_ITEM_OK) return false;
-            const gb_extension* ext = a.ev.ext + (size_t)item * a.ev.max_ext;
+            const gb_extension* ext = ev_ext(a.ev, item);
             const uint32_t n_ext = a.ev.ext_count[item];
             // full-length sets carry their own score; anything else needs the sweep estimate (rare)
             if (n_ext > 0 && ext_full(ext[0]) && ext[0].mismatches <= 4) set_score[s] = ext[0].score;
@@ -136,7 +136,7 @@ __device__ inline bool fast_pair(const DevIndex& ix, const MapParamsDev& P, cons
             if (!process) continue;
             unskipped++;
             const uint32_t item = rs.item_off + s;
-            const gb_extension* ext = a.ev.ext + (size_t)item * a.ev.max_ext;
+            const gb_extension* ext = ev_ext(a.ev, item);
             const uint32_t n_ext = a.ev.ext_count[item];
             if (!(n_ext > 0 && ext_full(ext[0]) && ext[0].mismatches <= 4)) return false;     // tail alignment needed
             const DevItem it = a.items[item];
@@ -162,10 +162,10 @@ __device__ inline bool fast_pair(const DevIndex& ix, const MapParamsDev& P, cons
     }
     gb_mapping* out_maps[2] = {a.maps + (size_t)(2 * p) * P.mapping_cap, a.maps + (size_t)(2 * p + 1) * P.mapping_cap};
     uint32_t* out_edits[2] = {a.edits + (size_t)(2 * p) * P.edit_cap, a.edits + (size_t)(2 * p + 1) * P.edit_cap};
-    auto ext_of = [&](const FastCand& c) -> const gb_extension& { return a.ev.ext[(size_t)c.item * a.ev.max_ext + c.ext_j]; };
+    auto ext_of = [&](const FastCand& c) -> const gb_extension& { return ev_ext(a.ev, c.item)[c.ext_j]; };
     auto write_cand = [&](uint32_t r, const FastCand& c) -> bool {
         uint32_t nm = 0, ne = 0;
-        const bool ok = extension_to_output(ix, ext_of(c), a.ev.path_pool + (size_t)c.item * a.ev.path_cap, a.ev.mism_pool + (size_t)c.item * a.ev.mism_cap,
+        const bool ok = extension_to_output(ix, ext_of(c), ev_path(a.ev, c.item), ev_mism(a.ev, c.item),
                                             reads[r], L[r], r == 1, out_maps[r], out_edits[r], P.mapping_cap, P.edit_cap, nm, ne);
         if (!ok) return false;
         out[r].score = c.score; out[r].flags |= nm ? GB_ALN_MAPPED : 0; out[r].n_mappings = (uint16_t)nm; out[r].n_edits = ne;
@@ -186,8 +186,8 @@ __device__ inline bool fast_pair(const DevIndex& ix, const MapParamsDev& P, cons
                     if (cand[c1].frag != f || cand[c1].read != 1) continue;
                     if (n_pairs >= FAST_MAX_PAIRS) return false;
                     uint32_t fn, fo, ln, le, x0, x1, x2, x3;
-                    extension_ends(ix, ext_of(cand[c0]), a.ev.path_pool + (size_t)cand[c0].item * a.ev.path_cap, fn, fo, x0, x1);
-                    extension_ends(ix, ext_of(cand[c1]), a.ev.path_pool + (size_t)cand[c1].item * a.ev.path_cap, x2, x3, ln, le);
+                    extension_ends(ix, ext_of(cand[c0]), ev_path(a.ev, cand[c0].item), fn, fo, x0, x1);
+                    extension_ends(ix, ext_of(cand[c1]), ev_path(a.ev, cand[c1].item), x2, x3, ln, le);
                     const int64_t dist = oriented_distance(ix, fn, fo, ln, le);
                     const double dev = (double)dist - a.frag_mean;
                     const double ll = (-dev * dev / (2.0 * a.frag_sd * a.frag_sd)) / P.log_base;
@@ -283,7 +283,7 @@ __device__ inline bool fast_read(const DevIndex& ix, const MapParamsDev& P, cons
     for (uint32_t s = 0; s < S; s++) {
         const uint32_t item = rs.item_off + s;
         if (a.ev.ext_status[item] != GB_ITEM_OK) return false;
-        const gb_extension* ext = a.ev.ext + (size_t)item * a.ev.max_ext;
+        const gb_extension* ext = ev_ext(a.ev, item);
         const uint32_t n_ext = a.ev.ext_count[item];
         if (n_ext > 0 && ext_full(ext[0]) && ext[0].mismatches <= 4) set_score[s] = ext[0].score;
         else set_score[s] = score_extension_group(ext, n_ext, L, sc.gap_open, sc.gap_extend);
@@ -305,7 +305,7 @@ __device__ inline bool fast_read(const DevIndex& ix, const MapParamsDev& P, cons
         if (set_score[s] < P.extension_set_min_score) continue;                    // :912-916
         unskipped++;
         const uint32_t item = rs.item_off + s;
-        const gb_extension* ext = a.ev.ext + (size_t)item * a.ev.max_ext;
+        const gb_extension* ext = ev_ext(a.ev, item);
         const uint32_t n_ext = a.ev.ext_count[item];
         if (!(n_ext > 0 && ext_full(ext[0]) && ext[0].mismatches <= 4)) return false;     // tail alignment needed
         const DevItem it = a.items[item];
@@ -350,8 +350,8 @@ __device__ inline bool fast_read(const DevIndex& ix, const MapParamsDev& P, cons
     if (win >= 0) {
         const FastCand& c = cand[win];
         uint32_t nm = 0, ne = 0;
-        if (!extension_to_output(ix, a.ev.ext[(size_t)c.item * a.ev.max_ext + c.ext_j], a.ev.path_pool + (size_t)c.item * a.ev.path_cap,
-                                 a.ev.mism_pool + (size_t)c.item * a.ev.mism_cap, read, L, false,
+        if (!extension_to_output(ix, ev_ext(a.ev, c.item)[c.ext_j], ev_path(a.ev, c.item),
+                                 ev_mism(a.ev, c.item), read, L, false,
                                  a.maps + (size_t)r * P.mapping_cap, a.edits + (size_t)r * P.edit_cap, P.mapping_cap, P.edit_cap, nm, ne)) return false;
         out.score = c.score; out.flags = nm ? GB_ALN_MAPPED : 0; out.n_mappings = (uint16_t)nm; out.n_edits = ne;
     }

@@ -286,7 +286,7 @@ __device__ inline uint32_t align_sets(const DevIndex& ix, const MapParamsDev& P,
     for (uint32_t s = 0; s < S; s++) {
         const uint32_t item = rs.item_off + sel[s];
         if (a.ev.ext_status[item] != GB_ITEM_OK) return a.ev.ext_status[item];
-        set_score[s] = score_extension_group(a.ev.ext + (size_t)item * a.ev.max_ext, a.ev.ext_count[item], L, sc.gap_open, sc.gap_extend);
+        set_score[s] = score_extension_group(ev_ext(a.ev, item), a.ev.ext_count[item], L, sc.gap_open, sc.gap_extend);
     }
     for (uint32_t s = 0; s < S; s++) { uint32_t j = s; while (j > 0 && set_score[s] > set_score[set_order[j - 1]]) { set_order[j] = set_order[j - 1]; j--; } set_order[j] = (uint8_t)s; }
     {
@@ -312,10 +312,10 @@ __device__ inline uint32_t align_sets(const DevIndex& ix, const MapParamsDev& P,
         if (!paired && set_score[s] < P.extension_set_min_score) continue;           // single-end only (:912-916)
         unskipped++;
         const uint32_t item = rs.item_off + sel[s];
-        const gb_extension* ext = a.ev.ext + (size_t)item * a.ev.max_ext;
+        const gb_extension* ext = ev_ext(a.ev, item);
         const uint32_t n_ext = a.ev.ext_count[item];
-        const uint32_t* path_pool = a.ev.path_pool + (size_t)item * a.ev.path_cap;
-        const uint32_t* mism_pool = a.ev.mism_pool + (size_t)item * a.ev.mism_cap;
+        const uint32_t* path_pool = ev_path(a.ev, item);
+        const uint32_t* mism_pool = ev_mism(a.ev, item);
         const DevItem it = a.items[item];
 
         int32_t ba_score[50]; uint32_t ba_slot[50]; uint32_t n_ba = 0;

@@ -37,6 +37,11 @@ struct ExtendBatch {
     // device-produced work list (mapping pipeline): when `items` is set, item i is
     // items[i] and the item count is read from *n_items_dev (capped by n_items).
     const DevItem* items; const uint32_t* n_items_dev;
+    // clusters with more seeds than the per-item output strides hold (repeats): the first launch lists them, a second
+    // launch redoes them with large strides; item i of that launch is in_list[i], its outputs live in slot i of the large
+    // pools and big_of[item] = i tells the align stage where (ExtView)
+    uint32_t* retry_list; uint32_t* retry_count; uint32_t retry_cap;
+    const uint32_t* in_list; const uint32_t* in_count; uint32_t* big_of;
 };
 
 __global__ void __launch_bounds__(EXTEND_WARPS * 32, 4)
@@ -49,12 +54,14 @@ extend_kernel(DevIndex ix, ExtendParams p, ExtendBatch b, ExtendWorkspace ws) {
     QEntry* queue = ws.queue + (size_t)gwarp * ws.q_cap;
     ArenaNode* arena = ws.arena + (size_t)gwarp * ws.a_cap;
 
-    const uint32_t n_items = b.items ? min(b.n_items, *b.n_items_dev) : b.n_items;
+    const uint32_t n_items = b.in_list ? min(*b.in_count, b.retry_cap) : (b.items ? min(b.n_items, *b.n_items_dev) : b.n_items);
     while (true) {
         uint32_t item = 0;
         if (lane == 0) item = atomicAdd(b.work_counter, 1u);
         item = __shfl_sync(FULL, item, 0);
         if (item >= n_items) break;
+        const uint32_t out_slot = item;                       // where this item's outputs go
+        if (b.in_list) item = b.in_list[item];
 
         uint32_t r; uint64_t sb; uint32_t n_seeds;
         if (b.items) { const DevItem it = b.items[item]; r = it.read; sb = it.seed_off; n_seeds = it.seed_cnt; }
@@ -74,11 +81,18 @@ extend_kernel(DevIndex ix, ExtendParams p, ExtendBatch b, ExtendWorkspace ws) {
             __syncwarp();
             n = extend_item(ix, p, sread, read_len, b.seeds + sb, n_seeds,
                             queue, ws.q_cap, arena, ws.a_cap,
-                            b.ext + (size_t)item * p.max_ext,
-                            b.path_pool + (size_t)item * p.path_cap,
-                            b.mism_pool + (size_t)item * p.mism_cap, &status);
+                            b.ext + (size_t)out_slot * p.max_ext,
+                            b.path_pool + (size_t)out_slot * p.path_cap,
+                            b.mism_pool + (size_t)out_slot * p.mism_cap, &status);
         }
-        if (lane == 0) { b.ext_count[item] = n; b.status[item] = (uint8_t)status; }
+        if (lane == 0) {
+            if (status == GB_ITEM_OUT_FULL && b.retry_list && read_len <= b.read_cap) {
+                const uint32_t pos = atomicAdd(b.retry_count, 1u);
+                if (pos < b.retry_cap) b.retry_list[pos] = item;
+            }
+            if (b.big_of) b.big_of[item] = out_slot;
+            b.ext_count[item] = n; b.status[item] = (uint8_t)status;
+        }
         __syncwarp();
     }
 }
@@ -239,12 +253,20 @@ int launch_extend_device(gb_device* d, const ExtendParams& p, const uint8_t* rea
                          const uint32_t* item_read, const gb_seed* seeds, const uint64_t* seed_off,
                          const DevItem* items, const uint32_t* n_items_dev, uint32_t n_items_max,
                          uint32_t* ext_count, uint8_t* status, gb_extension* ext, uint32_t* path_pool, uint32_t* mism_pool,
-                         uint32_t max_read_len) {
+                         uint32_t max_read_len, const ExtendBig* big) {
     ExtendBatch b{};
     b.reads = reads; b.read_off = read_off; b.item_read = item_read; b.seeds = seeds; b.seed_off = seed_off;
     b.n_items = n_items_max; b.items = items; b.n_items_dev = n_items_dev;
     b.ext_count = ext_count; b.status = status; b.ext = ext; b.path_pool = path_pool; b.mism_pool = mism_pool;
-    return launch_extend(d, p, b, max_read_len);
+    if (big) { b.retry_list = big->list; b.retry_count = big->count; b.retry_cap = big->cap; }
+    int rc = launch_extend(d, p, b, max_read_len);
+    if (rc || !big) return rc;
+    // second launch: the listed items with the large strides
+    ExtendParams pb = p; pb.max_ext = big->max_ext; pb.path_cap = big->path_cap; pb.mism_cap = big->mism_cap;
+    ExtendBatch b2 = b;
+    b2.retry_list = nullptr; b2.retry_count = nullptr; b2.in_list = big->list; b2.in_count = big->count; b2.retry_cap = big->cap; b2.big_of = big->big_of;
+    b2.ext = big->ext; b2.path_pool = big->path; b2.mism_pool = big->mism;
+    return launch_extend(d, pb, b2, max_read_len);
 }
 
 } // namespace gb

@@ -96,6 +96,7 @@ struct gb_device {
     gb::DevBuf<gb_seed> p_ext_seeds;
     gb::DevBuf<uint32_t> p_cursors, p_ext_count, p_path, p_mism;
     gb::DevBuf<uint8_t> p_ext_status;
+    gb::DevBuf<uint32_t> p_big_list, p_big_of, p_big_path, p_big_mism; gb::DevBuf<gb_extension> p_big_ext;      // ExtendBig
     gb::DevBuf<gb_extension> p_ext;
     gb::DevBuf<uint8_t> ws_tail, ws_cand, w_reads, w_quals, ws_rescue;
     gb::DevBuf<gb::PairState> p_pairs;
@@ -149,7 +150,7 @@ struct gb_device {
         ws_queue.release(); ws_arena.release();
         t_hit.release(); t_plo.release(); t_phred.release(); p_states.release(); p_min.release(); p_seeds.release();
         p_items.release(); p_ext_seeds.release(); p_cursors.release(); p_ext_count.release(); p_path.release(); p_mism.release();
-        p_ext_status.release(); p_ext.release(); ws_tail.release(); ws_cand.release(); ws_rescue.release(); w_reads.release(); w_quals.release(); p_pairs.release(); p_slow.release(); p_rescue.release(); p_retry.release();
+        p_ext_status.release(); p_ext.release(); p_big_list.release(); p_big_of.release(); p_big_path.release(); p_big_mism.release(); p_big_ext.release(); ws_tail.release(); ws_cand.release(); ws_rescue.release(); w_reads.release(); w_quals.release(); p_pairs.release(); p_slow.release(); p_rescue.release(); p_retry.release();
         pad_maps.release(); pad_edits.release(); c_map_off.release(); c_edit_off.release(); c_totals.release(); c_tmp.release();
         io[0].release(); io[1].release(); c_run.release();
         pl_entries.release(); pl_unit_base.release(); pl_unit_count.release(); pl_tile_off.release(); pl_lists.release(); pl_paths.release(); pl_tiles.release(); ws_tile.release(); pl_results.release(); pl_stats.release();

@@ -44,6 +44,14 @@ struct ExtendWorkspace {
     uint32_t q_cap, a_cap;
 };
 
+// large-stride outputs for the few items (clusters of repeats) that overflow the regular per-item strides
+struct ExtendBig {
+    uint32_t* list; uint32_t* count; uint32_t cap;          // items to redo (device list + counter)
+    uint32_t* big_of;                                       // [n_items] slot of an item in the large pools, 0xffffffff: regular
+    gb_extension* ext; uint32_t* path; uint32_t* mism;
+    uint32_t max_ext, path_cap, mism_cap;
+};
+
 struct ExtendParams {
     DevScores sc;
     uint32_t max_mismatches;

@@ -22,7 +22,7 @@ int launch_extend_device(gb_device* d, const ExtendParams& p, const uint8_t* rea
                          const uint32_t* item_read, const gb_seed* seeds, const uint64_t* seed_off,
                          const DevItem* items, const uint32_t* n_items_dev, uint32_t n_items_max,
                          uint32_t* ext_count, uint8_t* status, gb_extension* ext, uint32_t* path_pool, uint32_t* mism_pool,
-                         uint32_t max_read_len);
+                         uint32_t max_read_len, const ExtendBig* big);
 
 constexpr int SEED_WARPS = 16;          // warps per block of the seeding kernels (block-synchronised rounds)
 constexpr int SEED_BLOCKS_PER_SM = 2;
@@ -351,13 +351,22 @@ int map_device(gb_device* d, const gb_map_params* hp, uint32_t n_reads, const ui
     if ((rc = d->p_ext.reserve(item_cap * max_ext))) return rc;
     if ((rc = d->p_path.reserve(item_cap * path_cap))) return rc;
     if ((rc = d->p_mism.reserve(item_cap * mism_cap))) return rc;
+    // clusters whose seeds yield more extensions than those strides hold (repeats: a hundred seeds in one cluster, one
+    // extension per seed before GaplessExtender::extend removes duplicates) are redone with large strides
+    ExtendBig big;
+    big.cap = n_reads / 128 + 256; big.max_ext = 512; big.path_cap = 512 * 24; big.mism_cap = 512 * 4;
+    if ((rc = d->p_big_list.reserve(big.cap)) || (rc = d->p_big_of.reserve(item_cap)) || (rc = d->p_big_ext.reserve((size_t)big.cap * big.max_ext)) ||
+        (rc = d->p_big_path.reserve((size_t)big.cap * big.path_cap)) || (rc = d->p_big_mism.reserve((size_t)big.cap * big.mism_cap))) return rc;
+    GB_CUDA(cudaMemsetAsync(d->p_big_of.ptr, 0xff, sizeof(uint32_t) * item_cap, d->stream));
+    big.list = d->p_big_list.ptr; big.count = cur + 15; big.big_of = d->p_big_of.ptr;
+    big.ext = d->p_big_ext.ptr; big.path = d->p_big_path.ptr; big.mism = d->p_big_mism.ptr;
     {
         ExtendParams ep;
         ep.sc = d->sc; ep.max_mismatches = hp->max_extension_mismatches; ep.overlap_threshold = 0.8; ep.overlap_threshold_unused = 0.f;
         ep.trim = 1; ep.max_ext = max_ext; ep.path_cap = path_cap; ep.mism_cap = mism_cap;
         if ((rc = launch_extend_device(d, ep, d_reads, d_read_off, nullptr, d->p_ext_seeds.ptr, nullptr, d->p_items.ptr, cur + 3,
                                        (uint32_t)item_cap, d->p_ext_count.ptr, d->p_ext_status.ptr, d->p_ext.ptr, d->p_path.ptr,
-                                       d->p_mism.ptr, Lc))) return rc;
+                                       d->p_mism.ptr, Lc, &big))) return rc;
         if ((rc = d->kt_mark("extend_kernel"))) return rc;
     }
     GB_CUDA(cudaEventRecord(d->ev_stage[2], d->stream));
@@ -401,6 +410,8 @@ int map_device(gb_device* d, const gb_map_params* hp, uint32_t n_reads, const ui
         a.items = d->p_items.ptr; a.minimizers = d->p_min.ptr;
         a.ev.ext_count = d->p_ext_count.ptr; a.ev.ext_status = d->p_ext_status.ptr; a.ev.ext = d->p_ext.ptr;
         a.ev.path_pool = d->p_path.ptr; a.ev.mism_pool = d->p_mism.ptr; a.ev.max_ext = max_ext; a.ev.path_cap = path_cap; a.ev.mism_cap = mism_cap;
+        a.ev.big_of = d->p_big_of.ptr; a.ev.big_ext = d->p_big_ext.ptr; a.ev.big_path = d->p_big_path.ptr; a.ev.big_mism = d->p_big_mism.ptr;
+        a.ev.big_max_ext = big.max_ext; a.ev.big_path_cap = big.path_cap; a.ev.big_mism_cap = big.mism_cap;
         a.ws_base = d->ws_tail.ptr; a.ws_stride = ws_stride; a.cand_base = d->ws_cand.ptr; a.cand_stride = cand_stride;
         a.aln = d_aln; a.maps = d_maps; a.edits = d_edits; a.status = d_status; a.tb_cells = tb_cells;
         a.pairs = paired ? d->p_pairs.ptr : nullptr; a.frag_mean = hp->fragment_mean; a.frag_sd = hp->fragment_stdev;

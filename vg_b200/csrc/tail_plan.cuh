@@ -131,7 +131,7 @@ __device__ inline void plan_read(const DevIndex& ix, const MapParamsDev& P, cons
     for (uint32_t s = 0; s < S; s++) {
         const uint32_t item = rs.item_off + s;
         if (a.ev.ext_status[item] != GB_ITEM_OK) return;
-        set_score[s] = score_extension_group(a.ev.ext + (size_t)item * a.ev.max_ext, a.ev.ext_count[item], L, sc.gap_open, sc.gap_extend);
+        set_score[s] = score_extension_group(ev_ext(a.ev, item), a.ev.ext_count[item], L, sc.gap_open, sc.gap_extend);
     }
     for (uint32_t s = 0; s < S; s++) { uint32_t j = s; while (j > 0 && set_score[s] > set_score[set_order[j - 1]]) { set_order[j] = set_order[j - 1]; j--; } set_order[j] = (uint8_t)s; }
     uint32_t ties = 0;
@@ -150,10 +150,10 @@ __device__ inline void plan_read(const DevIndex& ix, const MapParamsDev& P, cons
             unskipped++;
         }
         const uint32_t item = rs.item_off + s;
-        const gb_extension* ext = a.ev.ext + (size_t)item * a.ev.max_ext;
+        const gb_extension* ext = ev_ext(a.ev, item);
         const uint32_t n_ext = a.ev.ext_count[item];
         if (n_ext == 0 || (ext_full(ext[0]) && ext[0].mismatches <= 4)) continue;       // no extensions / direct full-length alignments
-        const uint32_t* path_pool = a.ev.path_pool + (size_t)item * a.ev.path_cap;
+        const uint32_t* path_pool = ev_path(a.ev, item);
         uint32_t min_tails = 1;
         for (uint32_t j = 0; j < n_ext; j++) if (ext_full(ext[j])) min_tails++;
         if (min_tails < 2) min_tails = 2;
