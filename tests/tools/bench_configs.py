@@ -36,7 +36,7 @@ for name, make_graph, kw in [
     want = H.oracle_map(index, rs.reads[:sub], rs.quals[:sub], threads=threads)
     dt = time.time() - t
     bad = H.compare_alignments(got, want, min(sub, 20000))
-    out[name] = {"reads": n, "gpu_kernel_ms": best, "gpu_reads_per_s": n / (best / 1e3), "stage_ms_last_chunk": stages, "kernel_ms": {k: round(v, 3) for k, v in kernels}, "plan": dev.plan_stats(),
+    out[name] = {"reads": n, "gpu_kernel_ms": best, "gpu_reads_per_s": n / (best / 1e3), "stage_ms_last_chunk": stages, "kernel_ms": [(k, round(v, 3)) for k, v in kernels], "plan": dev.plan_stats(),
                  "status_errors": int((got[3] != 0).sum()), "mapped_fraction": float((got[0]["flags"] & 1).mean()),
                  "cpu_reads_per_s": sub / dt, "cpu_threads": threads, "oracle_counters": {k: int(v) for k, v in want[4].items()},
                  "parity_mismatches_of_20000": len(bad)}

@@ -221,6 +221,12 @@ __device__ inline int32_t align_tail(const DevIndex& ix, const MapParamsDev& P, 
     if (tl.pv) {
         const TailPlanEntry* pe = nullptr;
         for (uint32_t x = 0; x < tl.count; x++) if (tl.pv->entries[tl.base + x].key == tl.key) { pe = tl.pv->entries + tl.base + x; break; }
+        // a cancelled tail (the decide pass judged that the reference skips it, :5478-5492) is never asked for; should the
+        // walk here disagree, the tail is simply aligned in place
+        if (pe) for (uint32_t t = 0; t < pe->n_trees; t++) {
+            const uint32_t ti = pe->first_tile + t;
+            if (tl.pv->tile_off[ti] != TILE_REFUSED && tl.pv->results[ti].status == GB_TILE_ST_CANCELLED) { pe = nullptr; break; }
+        }
         if (pe) {
             int32_t best_score = 0;
             if (lane == 0) { pb_add_mapping(res, default_node, default_offset); pb_add_edit(res, edit_word(GB_EDIT_INS, tail_length, 0)); }

@@ -273,7 +273,8 @@ int map_device(gb_device* d, const gb_map_params* hp, uint32_t n_reads, const ui
     if ((rc = d->p_cursors.reserve(48))) return rc;
     GB_CUDA(cudaMemsetAsync(d->p_cursors.ptr, 0, 48 * sizeof(uint32_t), d->stream));
     // 0 seed work, 1 min, 2 seed, 3 item, 4 ext, 5 extend work, 6 align work, 7 slow count, 8-10 seeding retry, 11-12 rescue, 13 pool overflow,
-    // 14 plan work, 16 tiles, 17 tile bytes / 16, 18-23 tile list counts, 25 result path words, 26-31 tile work
+    // 14 plan work, 15 big extension items, 16 tiles, 17 tile bytes / 16, 18-29 tile list counts (2 waves x 6 classes),
+    // 30 result path words, 31 decide work, 32-43 tile work
     uint32_t* cur = d->p_cursors.ptr;
     d->kt_reset();
 
@@ -435,14 +436,14 @@ int map_device(gb_device* d, const gb_map_params* hp, uint32_t n_reads, const ui
             const size_t path_cap = std::min<size_t>(tile_cap * 32, 0xfffffff0u);
             if ((rc = d->pl_entries.reserve((size_t)n_units * PLAN_PER_UNIT)) || (rc = d->pl_unit_base.reserve(n_units)) || (rc = d->pl_unit_count.reserve(n_units)) ||
                 (rc = d->pl_tiles.reserve(unit_cap * 16)) || (rc = d->pl_tile_off.reserve(tile_cap)) || (rc = d->pl_results.reserve(tile_cap)) ||
-                (rc = d->pl_lists.reserve(TILE_CLASSES * tile_cap)) || (rc = d->pl_paths.reserve(path_cap)) || (rc = d->pl_stats.reserve(4))) return rc;
+                (rc = d->pl_lists.reserve(2 * TILE_CLASSES * tile_cap)) || (rc = d->pl_paths.reserve(path_cap)) || (rc = d->pl_stats.reserve(4))) return rc;
             GB_CUDA(cudaMemsetAsync(d->pl_stats.ptr, 0, 4 * sizeof(uint64_t), d->stream));
             PlanPools pp;
             pp.entries = d->pl_entries.ptr; pp.unit_base = d->pl_unit_base.ptr; pp.unit_count = d->pl_unit_count.ptr;
             pp.tiles = d->pl_tiles.ptr; pp.tile_units_cap = (uint32_t)unit_cap; pp.tile_units_cursor = cur + 17;
             pp.tile_off = d->pl_tile_off.ptr; pp.tile_cap = (uint32_t)tile_cap; pp.tile_cursor = cur + 16;
             pp.results = d->pl_results.ptr;
-            for (int c = 0; c < TILE_CLASSES; c++) pp.lists[c] = d->pl_lists.ptr + (size_t)c * tile_cap;
+            for (int c = 0; c < 2 * TILE_CLASSES; c++) pp.lists[c] = d->pl_lists.ptr + (size_t)c * tile_cap;
             pp.list_count = cur + 18; pp.stats = d->pl_stats.ptr;
             MapBatch bpl = b3; bpl.work_counter = cur + 14;
             if (paired) tail_plan_kernel<true><<<grid_plain, ALIGN_WARPS * 32, 0, d->stream>>>(d->ix, P, d->sc, bpl, a, pp);
@@ -450,8 +451,17 @@ int map_device(gb_device* d, const gb_map_params* hp, uint32_t n_reads, const ui
             d->launches++;
             GB_CUDA(cudaGetLastError());
             if ((rc = d->kt_mark("tail_plan_kernel"))) return rc;
-            if ((rc = launch_tile_kernels(d, d->pl_tiles.ptr, d->pl_tile_off.ptr, d->pl_lists.ptr, tile_cap, cur + 18, cur + 26, d->pl_results.ptr,
-                                          d->pl_paths.ptr, (uint32_t)path_cap, cur + 25))) return rc;
+            // wave 0: the tails that are always aligned; the decide pass cancels what the reference would skip; wave 1: the rest
+            if ((rc = launch_tile_kernels(d, d->pl_tiles.ptr, d->pl_tile_off.ptr, d->pl_lists.ptr, tile_cap, cur + 18, cur + 32, d->pl_results.ptr,
+                                          d->pl_paths.ptr, (uint32_t)path_cap, cur + 30))) return rc;
+            MapBatch bdc = b3; bdc.work_counter = cur + 31;
+            if (paired) tail_decide_kernel<true><<<grid_plain, ALIGN_WARPS * 32, 0, d->stream>>>(d->ix, P, d->sc, bdc, a, pp);
+            else tail_decide_kernel<false><<<grid_plain, ALIGN_WARPS * 32, 0, d->stream>>>(d->ix, P, d->sc, bdc, a, pp);
+            d->launches++;
+            GB_CUDA(cudaGetLastError());
+            if ((rc = d->kt_mark("tail_decide_kernel"))) return rc;
+            if ((rc = launch_tile_kernels(d, d->pl_tiles.ptr, d->pl_tile_off.ptr, d->pl_lists.ptr + (size_t)TILE_CLASSES * tile_cap, tile_cap, cur + 18 + TILE_CLASSES,
+                                          cur + 32 + TILE_CLASSES, d->pl_results.ptr, d->pl_paths.ptr, (uint32_t)path_cap, cur + 30))) return rc;
             a.plan.entries = d->pl_entries.ptr; a.plan.unit_base = d->pl_unit_base.ptr; a.plan.unit_count = d->pl_unit_count.ptr;
             a.plan.tile_off = d->pl_tile_off.ptr; a.plan.results = d->pl_results.ptr; a.plan.path_pool = d->pl_paths.ptr;
         }

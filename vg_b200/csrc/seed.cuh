@@ -253,14 +253,6 @@ __device__ __forceinline__ uint32_t seed_phase_a(const DevIndex& ix, const MapPa
         }
     }
     __syncwarp();
-    // top words of the hashes, contiguous: the window scan below compares these and only looks at the full hash on a tie
-    // (they live in m_score | c_score | c_cov, contiguous and not written before the index lookup / the cluster phase; when
-    // that is too small for the read the scan compares full hashes)
-    uint32_t* khi = reinterpret_cast<uint32_t*>(sm.m_score);
-    const bool use_hi = (size_t)8 * sm.Mc + (size_t)32 * sm.Cc >= (size_t)4 * nk;
-    if (use_hi) for (uint32_t s = lane; s < nk; s += 32) khi[s] = (uint32_t)(sm.khash[s] >> 32);
-    __syncwarp();
-
     // ---- window minima -> minimizers in read order ---------------------------------------------
     // (invalid k-mers carry hash ~0, so they never beat a valid one)
     uint32_t M = 0;
@@ -271,17 +263,11 @@ __device__ __forceinline__ uint32_t seed_phase_a(const DevIndex& ix, const MapPa
             bool is_min = false; int32_t lo = 0, hi = -1;
             if (s < nk && (sm.kflag[s] & 1)) {
                 const uint64_t h = sm.khash[s];
-                const uint32_t hh = (uint32_t)(h >> 32);
                 int32_t l = -1000000, r = 1000000;
                 for (int32_t d = 1; d < (int32_t)w; d++) {
                     const int32_t tl = (int32_t)s - d, tr = (int32_t)s + d;
-                    if (use_hi) {
-                        if (l < 0 && tl >= 0) { const uint32_t o = khi[tl]; if (o < hh || (o == hh && sm.khash[tl] < h)) l = tl; }
-                        if (r == 1000000 && tr < (int32_t)nk) { const uint32_t o = khi[tr]; if (o < hh || (o == hh && sm.khash[tr] < h)) r = tr; }
-                    } else {
-                        if (l < 0 && tl >= 0 && sm.khash[tl] < h) l = tl;
-                        if (r == 1000000 && tr < (int32_t)nk && sm.khash[tr] < h) r = tr;
-                    }
+                    if (l < 0 && tl >= 0 && sm.khash[tl] < h) l = tl;
+                    if (r == 1000000 && tr < (int32_t)nk && sm.khash[tr] < h) r = tr;
                 }
                 lo = max(max((int32_t)s - (int32_t)w + 1, l + 1), 0);
                 hi = min(min((int32_t)s, r - (int32_t)w), last_window);

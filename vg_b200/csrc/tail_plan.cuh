@@ -14,13 +14,13 @@ struct PlanPools {
     uint8_t* tiles; uint32_t tile_units_cap; uint32_t* tile_units_cursor;      // 16-byte units
     uint32_t* tile_off; uint32_t tile_cap; uint32_t* tile_cursor;
     TileResult* results;
-    uint32_t* lists[TILE_CLASSES]; uint32_t* list_count;                       // [TILE_CLASSES]
+    uint32_t* lists[2 * TILE_CLASSES]; uint32_t* list_count;                   // [2 waves][TILE_CLASSES]
     uint64_t* stats;                                                           // [4] tails planned, trees, tiles, cells upper bound
 };
 
 // One tail of one extension: forest -> tiles + entry.  Returns false when the tail is left to align_tail.
 __device__ inline bool plan_tail(const DevIndex& ix, const MapParamsDev& P, const DevScores& sc, const TailWs& ws, const gb_extension& e,
-                                 const uint32_t* path_pool, const uint8_t* read, uint32_t L, bool left_tail, uint32_t key,
+                                 const uint32_t* path_pool, const uint8_t* read, uint32_t L, bool left_tail, uint32_t key, uint32_t wave,
                                  const PlanPools& pp, TailPlanEntry* unit_entries, uint32_t& n_entries) {
     const int lane = lane_id();
     if (n_entries >= PLAN_PER_UNIT) return false;
@@ -100,7 +100,7 @@ __device__ inline bool plan_tail(const DevIndex& ix, const MapParamsDev& P, cons
                 pp.tile_off[ti] = unit_at;
                 TileResult pend; pend.score = 0; pend.status = GB_TILE_ST_PENDING; pend.n_maps = pend.n_edits = pend.path_off = 0; pend.cells_lo = pend.cells_hi = pend.pad = 0;
                 pp.results[ti] = pend;
-                const int cls = tile_class(tail_length);
+                const int cls = tile_class(tail_length) + (int)wave * TILE_CLASSES;
                 const uint32_t pos = atomicAdd(&pp.list_count[cls], 1u);
                 if (pos < pp.tile_cap) pp.lists[cls][pos] = ti;
                 atomicAdd((unsigned long long*)&pp.stats[3], (unsigned long long)bases * (tail_length + 1));
@@ -111,7 +111,7 @@ __device__ inline bool plan_tail(const DevIndex& ix, const MapParamsDev& P, cons
         t0 = t1;
     }
     if (lane == 0) {
-        unit_entries[n_entries] = TailPlanEntry{key, first_tile, n_trees, 0u};
+        unit_entries[n_entries] = TailPlanEntry{key, first_tile, n_trees, wave};
         atomicAdd((unsigned long long*)&pp.stats[0], 1ull); atomicAdd((unsigned long long*)&pp.stats[1], (unsigned long long)n_trees);
     }
     n_entries++;
@@ -160,17 +160,26 @@ __device__ inline void plan_read(const DevIndex& ix, const MapParamsDev& P, cons
         uint8_t eo[64]; const uint32_t ne_ = min(n_ext, 64u);
         for (uint32_t j = 0; j < ne_; j++) { uint32_t x = j; while (x > 0 && ext[j].score > ext[eo[x - 1]].score) { eo[x] = eo[x - 1]; x--; } eo[x] = (uint8_t)j; }
         const double ecut = (double)ext[eo[0]].score - (double)P.extension_score_threshold;
+        const int32_t threshold = ext[eo[0]].score - P.extension_score_threshold;
         uint32_t e_unskipped = 0;
+        // The reference skips a partial extension when one has been aligned already, its score is at most `threshold` and its
+        // score estimate cannot beat the running winner (:5478-5492).  The extensions above the threshold (tied at the top, in
+        // whatever order the LazyRNG puts them) and the first partial one are always aligned: wave 0.  The others wait (wave 1)
+        // until tail_decide_kernel has the winner of wave 0 and cancels the ones the reference skips.
+        bool partial_aligned = false;
+        for (uint32_t y = 0; y < ne_ && ext[eo[y]].score > threshold; y++) partial_aligned |= !ext_full(ext[eo[y]]);
         for (uint32_t xi = 0; xi < ne_; xi++) {
             const gb_extension& e = ext[eo[xi]];
             if (P.extension_score_threshold != 0 && (double)e.score <= ecut && e_unskipped >= min_tails) continue;
             e_unskipped++;
             if (ext_full(e)) continue;
+            const bool candidate = !deferred && e.score <= threshold && partial_aligned;
             for (uint32_t side = 0; side < 2; side++) {
                 const bool left_tail = side == 0;
                 if (e.flags & (left_tail ? GB_EXT_LEFT_FULL : GB_EXT_RIGHT_FULL)) continue;
-                plan_tail(ix, P, sc, ws, e, path_pool, read, L, left_tail, tail_key(s, read_num, eo[xi], left_tail), pp, unit_entries, n_entries);
+                plan_tail(ix, P, sc, ws, e, path_pool, read, L, left_tail, tail_key(s, read_num, eo[xi], left_tail), candidate ? 1u : 0u, pp, unit_entries, n_entries);
             }
+            if (e.score <= threshold) partial_aligned = true;
         }
     }
 }
@@ -200,6 +209,125 @@ tail_plan_kernel(DevIndex ix, MapParamsDev P, DevScores sc, MapBatch b, AlignArg
             plan_read(ix, P, sc, rs, a, b.reads + rb, L, ws, PAIRED, r, pp, unit_entries, n_entries);
         }
         if (lane == 0) { pp.unit_base[u] = pos * PLAN_PER_UNIT; pp.unit_count[u] = n_entries; }
+        __syncwarp();
+    }
+}
+
+
+// -----------------------------------------------------------------------------------------------------------------
+// tail_decide_kernel: between the two waves of tiles.  For every set of every slow unit it replays
+// find_optimal_tail_alignments' bookkeeping (:5369-5622) with the wave-0 results: the running winner after the extensions
+// that are always aligned, then the waiting extensions in order — one whose score estimate cannot beat the winner is what
+// the reference skips: its tiles are cancelled.  The first waiting extension that survives stops the replay (its own score
+// would move the winner), so it and everything behind it run in wave 1.
+// -----------------------------------------------------------------------------------------------------------------
+__device__ inline void decide_read(const DevIndex& ix, const MapParamsDev& P, const DevScores& sc, const ReadState& rs, const AlignArgs& a,
+                                   uint32_t L, uint32_t read_num, const TailPlanEntry* entries, uint32_t n_entries, const uint32_t* tile_off, TileResult* results) {
+    if (rs.status != GB_ITEM_OK || rs.pad[0] > 1) return;
+    const uint32_t S = rs.item_cnt;
+    if (S == 0 || S > MAX_SETS) return;
+    auto find_entry = [&](uint32_t key) -> const TailPlanEntry* { for (uint32_t x = 0; x < n_entries; x++) if (entries[x].key == key) return entries + x; return nullptr; };
+    // best score over the trees of a finished tail (deterministic_beats only breaks ties): -1 if the tail is not available
+    auto tail_score = [&](const TailPlanEntry* pe) -> int32_t {
+        int32_t best = 0;
+        for (uint32_t t = 0; t < pe->n_trees; t++) {
+            const uint32_t ti = pe->first_tile + t;
+            if (tile_off[ti] == TILE_REFUSED) continue;
+            if (results[ti].status != GB_TILE_ST_OK) return -1;
+            best = max(best, results[ti].score);
+        }
+        return best;
+    };
+    for (uint32_t s = 0; s < S; s++) {
+        const uint32_t item = rs.item_off + s;
+        if (a.ev.ext_status[item] != GB_ITEM_OK) continue;
+        const gb_extension* ext = ev_ext(a.ev, item);
+        const uint32_t n_ext = a.ev.ext_count[item];
+        if (n_ext == 0 || (ext_full(ext[0]) && ext[0].mismatches <= 4)) continue;
+        bool any_waiting = false;
+        for (uint32_t x = 0; x < n_entries; x++) any_waiting |= entries[x].wave == 1 && (entries[x].key >> 9) == ((read_num << 21) | s);
+        if (!any_waiting) continue;
+        const uint32_t* mism_pool = ev_mism(a.ev, item);
+        uint32_t min_tails = 1;
+        for (uint32_t j = 0; j < n_ext; j++) if (ext_full(ext[j])) min_tails++;
+        if (min_tails < 2) min_tails = 2;
+        Pareto lf[136], rf[136]; uint32_t nl = 0, nr = 0;
+        for (uint32_t j = 0; j < n_ext && nl + 3 < 136; j++) {
+            const gb_extension& e = ext[j];
+            if (ext_full(e)) continue;
+            const int32_t left_penalty = gap_penalty1(e.read_lo, sc);
+            const int32_t mid_penalty = (int32_t)e.mism_len * (sc.match + sc.mismatch);
+            const int32_t right_penalty = gap_penalty1(L - e.read_hi, sc);
+            lf[nl++] = Pareto{e.read_hi, mid_penalty + left_penalty};
+            rf[nr++] = Pareto{L - e.read_lo, mid_penalty + right_penalty};
+            if (e.mism_len > 0) {
+                lf[nl++] = Pareto{mism_pool[e.mism_off], left_penalty};
+                rf[nr++] = Pareto{L - mism_pool[e.mism_off + e.mism_len - 1] - 1, right_penalty};
+            }
+        }
+        lf[nl++] = Pareto{ix.k + ix.w - 2, 0}; rf[nr++] = Pareto{ix.k + ix.w - 2, 0};
+        nl = find_pareto_frontier(lf, nl); nr = find_pareto_frontier(rf, nr);
+        uint8_t eo[64]; const uint32_t ne_ = min(n_ext, 64u);
+        for (uint32_t j = 0; j < ne_; j++) { uint32_t x = j; while (x > 0 && ext[j].score > ext[eo[x - 1]].score) { eo[x] = eo[x - 1]; x--; } eo[x] = (uint8_t)j; }
+        const double ecut = (double)ext[eo[0]].score - (double)P.extension_score_threshold;
+        uint32_t e_unskipped = 0;
+        int32_t winning_score = 0; bool known = true, stop = false;
+        for (uint32_t xi = 0; xi < ne_ && !stop; xi++) {
+            const gb_extension& e = ext[eo[xi]];
+            if (P.extension_score_threshold != 0 && (double)e.score <= ecut && e_unskipped >= min_tails) continue;
+            e_unskipped++;
+            const TailPlanEntry* pl = (e.flags & GB_EXT_LEFT_FULL) ? nullptr : find_entry(tail_key(s, read_num, eo[xi], true));
+            const TailPlanEntry* pr = (e.flags & GB_EXT_RIGHT_FULL) ? nullptr : find_entry(tail_key(s, read_num, eo[xi], false));
+            const bool waiting = (pl && pl->wave == 1) || (pr && pr->wave == 1);
+            if (!waiting) {
+                // always aligned: its total moves the winner (a full-length extension: its own score)
+                int32_t total = e.score;
+                if (!ext_full(e)) {
+                    if ((!(e.flags & GB_EXT_LEFT_FULL) && !pl) || (!(e.flags & GB_EXT_RIGHT_FULL) && !pr)) { known = false; break; }     // aligned in place: winner unknown here
+                    const int32_t ls = pl ? tail_score(pl) : 0, rsx = pr ? tail_score(pr) : 0;
+                    if (ls < 0 || rsx < 0) { known = false; break; }
+                    total += ls + rsx;
+                }
+                winning_score = max(winning_score, total);
+                continue;
+            }
+            if (!known) break;
+            int32_t estimate = (int32_t)L * sc.match + 2 * sc.full_length_bonus - (int32_t)e.mism_len * (sc.match + sc.mismatch);
+            if (!(e.flags & GB_EXT_LEFT_FULL)) estimate -= flank_penalty(e.read_lo, lf, nl, sc);
+            if (!(e.flags & GB_EXT_RIGHT_FULL)) estimate -= flank_penalty(L - e.read_hi, rf, nr, sc);
+            if (estimate <= winning_score) {
+                if (lane_id() == 0) {
+                    for (const TailPlanEntry* pe : {pl, pr}) if (pe) for (uint32_t t = 0; t < pe->n_trees; t++) if (tile_off[pe->first_tile + t] != TILE_REFUSED) results[pe->first_tile + t].status = GB_TILE_ST_CANCELLED;
+                }
+            } else stop = true;           // this one will be aligned and may move the winner: everything behind it runs
+        }
+    }
+}
+
+template <bool PAIRED>
+__global__ void __launch_bounds__(ALIGN_WARPS * 32, 4)
+tail_decide_kernel(DevIndex ix, MapParamsDev P, DevScores sc, MapBatch b, AlignArgs a, PlanPools pp) {
+    const int lane = threadIdx.x & 31;
+    const uint32_t n_units = PAIRED ? b.n_reads / 2 : b.n_reads;
+    while (true) {
+        uint32_t pos = 0, u = 0xffffffffu;
+        if (lane == 0) {
+            pos = atomicAdd(b.work_counter, 1u);
+            if (a.slow_list) u = pos < *a.slow_count ? a.slow_list[pos] : 0xffffffffu; else u = pos;
+        }
+        pos = __shfl_sync(FULL, pos, 0); u = __shfl_sync(FULL, u, 0);
+        if (u >= n_units) break;
+        const TailPlanEntry* entries = pp.entries + (size_t)pos * PLAN_PER_UNIT;
+        const uint32_t n_entries = pp.unit_count[u];
+        bool any = false;
+        for (uint32_t x = 0; x < n_entries; x++) any |= entries[x].wave == 1;
+        if (!any) continue;
+        for (uint32_t r = 0; r < (PAIRED ? 2u : 1u); r++) {
+            const uint32_t ri = PAIRED ? 2 * u + r : u;
+            const ReadState rs = b.states[ri];
+            const uint32_t L = (uint32_t)(b.read_off[ri + 1] - b.read_off[ri]);
+            decide_read(ix, P, sc, rs, a, L, r, entries, n_entries, pp.tile_off, pp.results);
+        }
         __syncwarp();
     }
 }

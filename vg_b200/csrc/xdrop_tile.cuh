@@ -48,6 +48,7 @@ constexpr int TILE_WARPS = 8;
 #define GB_TILE_TREE_SPACE  2u     // stage seam: mappings keep tree indices (no translation)
 #define GB_TILE_ST_OK       0u
 #define GB_TILE_ST_FULL     1u     // a result / traceback capacity was exceeded
+#define GB_TILE_ST_CANCELLED 2u    // second-wave tile whose tail the reference would not align (tail_decide_kernel)
 #define GB_TILE_ST_PENDING  0xffu
 
 struct __align__(16) TileHeader {
@@ -542,6 +543,7 @@ xdrop_tile_kernel(DevScores sc, TileBatch b) {
         const uint8_t* tile = tile_ptr(cur);
         if (cur_staged) { mbar_wait(&bar[which], phase[which]); phase[which] ^= 1u; tile = buf[which]; }
         const uint32_t ti = b.list[cur];
+        if (b.results[ti].status == GB_TILE_ST_CANCELLED) { __syncwarp(); cur = nxt; cur_staged = nxt_staged; which ^= 1; continue; }
         uint32_t nm = 0, ne = 0, mb = 0, eb = 0, st = GB_TILE_ST_OK; uint64_t cells = 0;
         const int32_t score = xdrop_tile_dp<R>(sc, tile, ws, prof, smaps_all, sedits_all, nm, ne, mb, eb, st, cells);
         const gb_mapping* smaps = smaps_all + mb; const uint32_t* sedits = sedits_all + eb;
@@ -612,7 +614,7 @@ xdrop_tile_kernel(DevScores sc, TileBatch b) {
 // sweep, so the plan only ever decides where a DP runs, never what it returns.
 constexpr uint32_t PLAN_PER_UNIT = 32;
 constexpr uint32_t TILE_REFUSED = 0xffffffffu;
-struct TailPlanEntry { uint32_t key, first_tile, n_trees, pad; };
+struct TailPlanEntry { uint32_t key, first_tile, n_trees, wave; };     // wave 1: its tiles wait for tail_decide_kernel
 __device__ __forceinline__ uint32_t tail_key(uint32_t item_local, uint32_t read_num, uint32_t ext, bool left) { return (read_num << 30) | (item_local << 9) | (ext << 1) | (left ? 1u : 0u); }
 struct PlanView {
     const TailPlanEntry* entries;      // [n_units * PLAN_PER_UNIT], unit = position in the slow list
