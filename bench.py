@@ -275,6 +275,41 @@ def algorithmic_bytes_per_read(L, counters, n_reads_sample, mappings_per_read, e
                "P": round(mappings_per_read, 2), "E": round(edits_per_read, 2)}, per_kernel
 
 
+def secondary_workloads(ordinal, n=200_000, check=10_000):
+    """BASELINE.json configs[3], configs[4] and the single-end path on the configs[1] graph, as secondary fields of the bench
+    line (not the metric): kernel-time reads/s of one gb_map_batch call (best of 2), per-kernel times, and a parity count of the
+    first `check` reads against the CPU restatement."""
+    import helpers as H
+    from vg_b200 import capi, synth
+    out = {}
+    threads, _ = usable_cpus()
+    for name, make_graph, kw in [
+        ("configs[3] branchy graph (8 bp nodes, 4-way bubbles), 150 bp SE", lambda: synth.make_branchy_graph(), dict(length=150, sub_rate=0.005, seed=44)),
+        ("configs[4] 250 bp SE, 5 % errors (tail DP)", lambda: synth.make_variant_graph(), dict(length=250, sub_rate=0.03, ins_rate=0.01, del_rate=0.01, seed=55)),
+        ("configs[1] graph, 150 bp SE", lambda: synth.make_variant_graph(), dict(length=150, sub_rate=0.002, seed=23)),
+    ]:
+        g = make_graph(); index = g.build_index()
+        rs = synth.simulate_reads(g, n, **kw)
+        dev = capi.Device(index, ordinal)
+        rbuf, qbuf, read_off = H.pack_reads(rs.reads, rs.quals)
+        best = None
+        for _ in range(2):
+            got = dev.map_arrays(rbuf, qbuf, read_off)
+            best = dev.kernel_ms() if best is None else min(best, dev.kernel_ms())
+        kern = {}
+        for k, v in dev.kernel_times():
+            kern[k] = round(kern.get(k, 0.0) + v, 3)
+        plan = dev.plan_stats()
+        want = H.oracle_map(index, rs.reads[:check], rs.quals[:check], threads=threads)
+        bad = H.compare_alignments(got, want, check)
+        cells = int(want[4]["tail_cells"]) * n // check
+        out[name] = {"reads": n, "reads_per_s": n / (best / 1e3), "kernel_ms": best, "kernel_ms_by_kernel": kern, "status_errors": int((got[3] != 0).sum()),
+                     "parity": {"reads_checked": check, "mismatching_reads": len(bad)},
+                     "tail_dp": {"cells_reference_would_compute": cells, "cells_planned": plan["cells"], "tiles": plan["trees"]}}
+        dev.close(); index.close()
+    return out
+
+
 # ---------------------------------------------------------------------------------------
 def main():
     ap = argparse.ArgumentParser()
@@ -288,6 +323,7 @@ def main():
     ap.add_argument("--scaling", default="weak", choices=["weak", "strong"],
                     help="weak: --reads per GPU (configs[1]); strong: --total-reads split over the GPUs, identical total input for every N (configs[2])")
     ap.add_argument("--total-reads", type=int, default=100_000_000, help="strong scaling: reads of the whole job (BASELINE.json configs[2]: 100M)")
+    ap.add_argument("--no-secondary", action="store_true", help="skip the secondary workloads (configs[3], configs[4], single-end) on rank 0 at N = 1")
     args = ap.parse_args()
 
     rank = int(os.environ.get("RANK", "0"))
@@ -331,7 +367,7 @@ def main():
             "scaling": "weak", "vs_baseline": None, "dtype": "int32", "data": "synthetic",
             "config": {"workload": "configs[1]: 1 Mbp / 1k-variant graph, 150 bp PE reads, fragment N(400,50) forced, 0.2 % substitutions, 0.02 % indels, rescue attempts " + str(args.rescue_attempts),
                        "reads_per_step": used, "note": "CPU restatement of vg giraffe (oracle/, OpenMP over read pairs); vg itself cannot be built in this image"},
-            "cpu_baseline": {"value": value, "unit": "reads/s", "cores": threads, "kind": "port", "sample": f"{used} reads per step, {flags}, {cpu_note}"},
+            "cpu_baseline": {"value": value, "unit": "reads/s", "cores": usable_cpus()[0], "threads": threads, "kind": "port", "sample": f"{used} reads per step, {threads} OpenMP threads, {flags}, {cpu_note}"},
             "e2e": {"value": value, "unit": "reads/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         }
         print(json.dumps(line), flush=True)
@@ -590,6 +626,13 @@ def main():
     except Exception:
         pass
 
+    secondary = None
+    if world == 1 and not args.no_secondary:
+        dev.close()
+        try:
+            secondary = secondary_workloads(local_rank)
+        except Exception as e:                       # never lose the headline line to a secondary workload
+            secondary = {"error": repr(e)}
     line = {
         "metric": "giraffe reads/sec (150 bp PE, synthetic)", "value": value, "unit": "reads/s", "n_gpus": world,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": dev_ms, "higher_is_better": True, "scaling": args.scaling,
@@ -620,8 +663,9 @@ def main():
                      "terms": terms, "reads_per_launch": chunk_reads,
                      "launch_ms": dom_ms, "peak_source": peak_src,
                      "stage_ms_last_chunk": {n: float(x) for n, x in zip(names, last_stage)}},
-        "cpu_baseline": {"value": cpu_rate, "unit": "reads/s", "cores": threads, "kind": "port",
-                         "sample": f"{cpu_sample} reads ({cpu_sample // 2} pairs) of the same batch in {cpu_dt:.1f}s, oracle/ built {flags}, OpenMP over pairs, {cpu_note}"},
+        "cpu_baseline": {"value": cpu_rate, "unit": "reads/s", "cores": usable_cpus()[0], "threads": threads, "kind": "port",
+                         "sample": f"{cpu_sample} reads ({cpu_sample // 2} pairs) of the same batch in {cpu_dt:.1f}s, oracle/ built {flags}, {threads} OpenMP threads over pairs, {cpu_note}"},
+        "secondary": secondary,
     }
     print(json.dumps(line), flush=True)
     if world > 1:
