@@ -326,6 +326,13 @@ def main():
     ap.add_argument("--no-secondary", action="store_true", help="skip the secondary workloads (configs[3], configs[4], single-end) on rank 0 at N = 1")
     args = ap.parse_args()
 
+    # stdout carries exactly one line, the JSON: anything a library prints there (NCCL's version banner) goes to stderr
+    real_stdout = os.dup(1)
+    os.dup2(2, 1)
+
+    def emit_line(obj):
+        os.write(real_stdout, (json.dumps(obj) + "\n").encode())
+
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
@@ -370,7 +377,7 @@ def main():
             "cpu_baseline": {"value": value, "unit": "reads/s", "cores": usable_cpus()[0], "threads": threads, "kind": "port", "sample": f"{used} reads per step, {threads} OpenMP threads, {flags}, {cpu_note}"},
             "e2e": {"value": value, "unit": "reads/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         }
-        print(json.dumps(line), flush=True)
+        emit_line(line)
         return 0
 
     import torch
@@ -667,7 +674,7 @@ def main():
                          "sample": f"{cpu_sample} reads ({cpu_sample // 2} pairs) of the same batch in {cpu_dt:.1f}s, oracle/ built {flags}, {threads} OpenMP threads over pairs, {cpu_note}"},
         "secondary": secondary,
     }
-    print(json.dumps(line), flush=True)
+    emit_line(line)
     if world > 1:
         dist.destroy_process_group()
     return 0

@@ -23,10 +23,14 @@ struct AlignArgs {
     uint32_t* rescue_list; uint32_t* rescue_count;
     // tails whose DPs ran in xdrop_tile_kernel (entries == nullptr: none, every tail is aligned in place)
     PlanView plan;
+    // bytes of shared memory per warp for the five temporary path buffers (0: they live in the HBM candidate workspace).
+    // Paths are assembled by one lane with read-modify-write steps (the edit count of the open mapping): in HBM every step
+    // is an L2 round trip, in shared memory it is a few cycles; the finished path is then copied to its slot by the warp.
+    uint32_t tmp_bytes;
 };
 
 constexpr uint32_t N_SLOTS = 2 * MAX_CANDS + 8 + 32;   // candidate path slots per warp (both mates of a pair, + rescued alignments)
-constexpr uint32_t N_TEMP_SLOTS = 4;              // res_left, res_right, scratch, middle
+constexpr uint32_t N_TEMP_SLOTS = 5;              // res_left, res_right, scratch, middle, assembly
 
 __device__ __forceinline__ double d_add_log(double x, double y) { return x > y ? x + log1p(exp(y - x)) : y + log1p(exp(x - y)); }
 __device__ __forceinline__ double d_subtract_log(double x, double y) { return x + log1p(-exp(y - x)); }
@@ -268,7 +272,7 @@ struct CandList {
 __device__ inline uint32_t align_sets(const DevIndex& ix, const MapParamsDev& P, const DevScores& sc, const ReadState& rs,
                                       const AlignArgs& a, const uint8_t* sread, uint32_t L, const TailWs& ws, DpSmem dps, uint8_t* qbuf,
                                       uint8_t* cand_base, bool* slot_used, DevRng& rng, bool paired, uint32_t read_num,
-                                      CandList& cl, uint32_t* explored, uint32_t unit) {
+                                      CandList& cl, uint32_t* explored, uint32_t unit, uint8_t* stmp) {
     const int lane = lane_id();
     uint32_t status = GB_ITEM_OK;
     uint32_t S = rs.item_cnt;
@@ -298,10 +302,15 @@ __device__ inline uint32_t align_sets(const DevIndex& ix, const MapParamsDev& P,
     const uint32_t min_sets = paired ? 2u : (uint32_t)P.min_extension_sets;
     uint32_t unskipped = 0;
 
-    PathBuf res_left = slot_buf(cand_base, N_SLOTS, map_cap, edit_cap);
-    PathBuf res_right = slot_buf(cand_base, N_SLOTS + 1, map_cap, edit_cap);
-    PathBuf scratch = slot_buf(cand_base, N_SLOTS + 2, map_cap, edit_cap);
-    PathBuf middle = slot_buf(cand_base, N_SLOTS + 3, map_cap, edit_cap);
+    auto tmp_buf = [&](uint32_t k) { return stmp ? slot_buf(stmp, k, map_cap, edit_cap) : slot_buf(cand_base, N_SLOTS + k, map_cap, edit_cap); };
+    PathBuf res_left = tmp_buf(0), res_right = tmp_buf(1), scratch = tmp_buf(2), middle = tmp_buf(3), asmb = tmp_buf(4);
+    // a finished path leaves the assembly buffer for its candidate slot (the whole warp copies)
+    auto store_slot = [&](PathBuf& dst, const PathBuf& src, uint32_t nm, uint32_t ne) {
+        for (uint32_t i = lane; i < nm; i += 32) dst.maps[i] = src.maps[i];
+        for (uint32_t i = lane; i < ne; i += 32) dst.edits[i] = src.edits[i];
+        if (lane == 0) { slot_nm(dst) = nm; slot_ne(dst) = ne; }
+        __syncwarp();
+    };
 
     for (uint32_t oi = 0; oi < S && status == GB_ITEM_OK; oi++) {
         const uint32_t s = set_order[oi];
@@ -324,10 +333,12 @@ __device__ inline uint32_t align_sets(const DevIndex& ix, const MapParamsDev& P,
                 const uint32_t slot = alloc_slot();
                 if (slot == 0xffffffffu) { status = GB_ITEM_OUT_FULL; break; }
                 PathBuf pb = slot_buf(cand_base, slot, map_cap, edit_cap);
-                if (lane == 0) extension_to_path(ix, ext[j], path_pool, mism_pool, sread, pb);
-                const uint32_t nm = __shfl_sync(FULL, pb.n_maps, 0), ne = __shfl_sync(FULL, pb.n_edits, 0);
-                if (__shfl_sync(FULL, (int)pb.overflow, 0) || nm + 1 > map_cap) { status = GB_ITEM_OUT_FULL; break; }
-                if (lane == 0) { slot_nm(pb) = nm; slot_ne(pb) = ne; }
+                pb_reset(asmb);
+                if (lane == 0) extension_to_path(ix, ext[j], path_pool, mism_pool, sread, asmb);
+                __syncwarp();
+                const uint32_t nm = __shfl_sync(FULL, asmb.n_maps, 0), ne = __shfl_sync(FULL, asmb.n_edits, 0);
+                if (__shfl_sync(FULL, (int)asmb.overflow, 0) || nm + 1 > map_cap) { status = GB_ITEM_OUT_FULL; break; }
+                store_slot(pb, asmb, nm, ne);
                 ba_score[n_ba] = ext[j].score; ba_slot[n_ba] = slot; n_ba++;
             }
         } else if (P.do_dp) {
@@ -420,17 +431,18 @@ __device__ inline uint32_t align_sets(const DevIndex& ix, const MapParamsDev& P,
                     dst = alloc_slot();
                     if (dst == 0xffffffffu) { status = GB_ITEM_OUT_FULL; break; }
                     PathBuf pb = slot_buf(cand_base, dst, map_cap, edit_cap);
+                    pb_reset(asmb);
                     if (lane == 0) {
                         pb_reset(middle);
                         extension_to_path(ix, e, path_pool, mism_pool, sread, middle);
-                        add_to_path(pb, res_left.maps, res_left.edits, res_left.n_maps);
-                        add_to_path(pb, middle.maps, middle.edits, middle.n_maps);
-                        add_to_path(pb, res_right.maps, res_right.edits, res_right.n_maps);
-                        if (middle.overflow || pb.n_maps + 1 > map_cap) pb.overflow = true;
-                        slot_nm(pb) = pb.n_maps; slot_ne(pb) = pb.n_edits;
+                        add_to_path(asmb, res_left.maps, res_left.edits, res_left.n_maps);
+                        add_to_path(asmb, middle.maps, middle.edits, middle.n_maps);
+                        add_to_path(asmb, res_right.maps, res_right.edits, res_right.n_maps);
+                        if (middle.overflow || asmb.n_maps + 1 > map_cap) asmb.overflow = true;
                     }
-                    if (__shfl_sync(FULL, (int)pb.overflow, 0)) { status = GB_ITEM_OUT_FULL; break; }
                     __syncwarp();
+                    if (__shfl_sync(FULL, (int)asmb.overflow, 0)) { status = GB_ITEM_OUT_FULL; break; }
+                    store_slot(pb, asmb, __shfl_sync(FULL, asmb.n_maps, 0), __shfl_sync(FULL, asmb.n_edits, 0));
                     if (target == 1) { winning_score = total_score; winning_start = current_start; winning_end = current_end; }
                     else second_score = total_score;
                 }
@@ -686,13 +698,13 @@ __device__ inline uint32_t finalize_pe(const DevIndex& ix, const MapParamsDev& P
 __device__ inline uint32_t align_read(const DevIndex& ix, const MapParamsDev& P, const DevScores& sc, ReadState rs,
                                       const AlignArgs& a, const uint8_t* sread, const uint8_t* qual, uint32_t L, uint32_t read_idx,
                                       const TailWs& ws, DpSmem dps, uint8_t* qbuf, uint8_t* cand_base,
-                                      gb_alignment& out, gb_mapping* out_maps, uint32_t* out_edits) {
+                                      gb_alignment& out, gb_mapping* out_maps, uint32_t* out_edits, uint8_t* stmp) {
     DevRng rng = rs.rng;
     bool slot_used[N_SLOTS];
     for (uint32_t i = 0; i < N_SLOTS; i++) slot_used[i] = false;
     CandList cl; cl.n = 0;
     uint32_t explored[PRESENT_WORDS];
-    uint32_t status = align_sets(ix, P, sc, rs, a, sread, L, ws, dps, qbuf, cand_base, slot_used, rng, false, 0, cl, explored, read_idx);
+    uint32_t status = align_sets(ix, P, sc, rs, a, sread, L, ws, dps, qbuf, cand_base, slot_used, rng, false, 0, cl, explored, read_idx, stmp);
     if (status != GB_ITEM_OK) return status;
     return finalize_se(ix, P, rs, a, cl, explored, rng, sread, qual, L, read_idx, dps, cand_base, out, out_maps, out_edits);
 }

@@ -98,8 +98,9 @@ align_kernel(DevIndex ix, MapParamsDev P, DevScores sc, MapBatch b, AlignArgs a)
     const uint32_t gwarp = blockIdx.x * ALIGN_WARPS + warp;
     const uint32_t W = b.Lc + 1;
     // shared per warp: read, qual, query buffer, 4 DP columns
-    const size_t per_warp = ((size_t)b.Lc * 3 + 15 & ~(size_t)15) + (size_t)W * 4 * 4 + 64;
+    const size_t per_warp = ((size_t)b.Lc * 3 + 15 & ~(size_t)15) + (size_t)W * 4 * 4 + 64 + a.tmp_bytes;
     uint8_t* base = smem + (size_t)warp * per_warp;
+    uint8_t* stmp = a.tmp_bytes ? base + (((size_t)b.Lc * 3 + 15) & ~(size_t)15) + (size_t)W * 4 * 4 + 64 : nullptr;
     uint8_t* sread = base; uint8_t* squal = base + b.Lc; uint8_t* qbuf = base + 2 * (size_t)b.Lc;
     int32_t* cols = reinterpret_cast<int32_t*>(base + (((size_t)b.Lc * 3 + 15) & ~(size_t)15));
     DpSmem dps; dps.Hp = cols; dps.Ep = cols + W; dps.Hc = cols + 2 * W; dps.Ec = cols + 3 * W;
@@ -126,7 +127,7 @@ align_kernel(DevIndex ix, MapParamsDev P, DevScores sc, MapBatch b, AlignArgs a)
         if (status == GB_ITEM_OK) {
             for (uint32_t i = lane; i < L; i += 32) { sread[i] = b.reads[rb + i]; if (b.quals) squal[i] = b.quals[rb + i]; }
             __syncwarp();
-            status = align_read(ix, P, sc, rs, a, sread, b.quals ? squal : nullptr, L, r, ws, dps, qbuf, cand_base, out, out_maps, out_edits);
+            status = align_read(ix, P, sc, rs, a, sread, b.quals ? squal : nullptr, L, r, ws, dps, qbuf, cand_base, out, out_maps, out_edits, stmp);
         }
         out.mapping_off = r * P.mapping_cap; out.edit_off = r * P.edit_cap;
         if (status != GB_ITEM_OK) { out.score = 0; out.flags = 0; out.n_mappings = 0; out.n_edits = 0; out.mapq = 0; }
@@ -374,7 +375,10 @@ int map_device(gb_device* d, const gb_map_params* hp, uint32_t n_reads, const ui
     // ---- K3 ----
     {
         const uint32_t W = Lc + 1;
-        const size_t per_warp = (((size_t)Lc * (paired ? 5 : 3) + 15) & ~(size_t)15) + (size_t)W * 4 * 4 + 64;
+        // the five temporary path buffers of a warp go to shared memory when they fit beside the DP columns
+        const size_t slot_bytes = (size_t)hp->mapping_cap_per_read * sizeof(gb_mapping) + (size_t)hp->edit_cap_per_read * 4;
+        const uint32_t tmp_bytes = N_TEMP_SLOTS * slot_bytes <= 12 * 1024 ? (uint32_t)(N_TEMP_SLOTS * slot_bytes) : 0u;
+        const size_t per_warp = (((size_t)Lc * (paired ? 5 : 3) + 15) & ~(size_t)15) + (size_t)W * 4 * 4 + 64 + tmp_bytes;
         const size_t smem = per_warp * ALIGN_WARPS;
         if (smem > 48 * 1024) {
             GB_CUDA(cudaFuncSetAttribute(align_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -401,7 +405,7 @@ int map_device(gb_device* d, const gb_map_params* hp, uint32_t n_reads, const ui
         if ((rc = d->ws_cand.reserve(cand_stride * n_warps))) return rc;
         AlignArgs a;
         a.plan.entries = nullptr; a.plan.unit_base = nullptr; a.plan.unit_count = nullptr; a.plan.tile_off = nullptr; a.plan.results = nullptr; a.plan.path_pool = nullptr;
-        a.rescue_base = nullptr; a.rescue_stride = 0;
+        a.rescue_base = nullptr; a.rescue_stride = 0; a.tmp_bytes = tmp_bytes;
         if (rescue) {
             a.rescue_stride = (rescue_ws_bytes(Lc) + 255) & ~(size_t)255;
             if ((rc = d->ws_rescue.reserve(a.rescue_stride * (size_t)grid * ALIGN_WARPS))) return rc;

@@ -113,8 +113,9 @@ align_kernel_pe(DevIndex ix, MapParamsDev P, DevScores sc, MapBatch b, AlignArgs
     const uint32_t W = b.Lc + 1;
     // shared per warp: 2 reads, 2 quals, query buffer, 4 DP columns
     const size_t bytes_part = ((size_t)b.Lc * 5 + 15) & ~(size_t)15;
-    const size_t per_warp = bytes_part + (size_t)W * 4 * 4 + 64;
+    const size_t per_warp = bytes_part + (size_t)W * 4 * 4 + 64 + a.tmp_bytes;
     uint8_t* base = smem + (size_t)warp * per_warp;
+    uint8_t* stmp = a.tmp_bytes ? base + bytes_part + (size_t)W * 4 * 4 + 64 : nullptr;
     uint8_t* sread[2] = {base, base + b.Lc};
     uint8_t* squal[2] = {base + 2 * (size_t)b.Lc, base + 3 * (size_t)b.Lc};
     uint8_t* qbuf = base + 4 * (size_t)b.Lc;
@@ -158,7 +159,7 @@ align_kernel_pe(DevIndex ix, MapParamsDev P, DevScores sc, MapBatch b, AlignArgs
             uint32_t explored[2][PRESENT_WORDS];
 #pragma unroll 1
             for (uint32_t r = 0; r < 2 && status == GB_ITEM_OK; r++)          // one copy of align_sets per kernel (instruction cache)
-                status = align_sets(ix, P, sc, rs[r], a, sread[r], L[r], ws, dps, qbuf, cand_base, slot_used, rng, true, r, cl, explored[r], p);
+                status = align_sets(ix, P, sc, rs[r], a, sread[r], L[r], ws, dps, qbuf, cand_base, slot_used, rng, true, r, cl, explored[r], p, stmp);
             if (status == GB_ITEM_OK) {
                 const uint8_t* sr[2] = {sread[0], sread[1]};
                 const uint8_t* sq[2] = {b.quals ? squal[0] : nullptr, b.quals ? squal[1] : nullptr};
