@@ -121,6 +121,16 @@ __device__ inline EdgeFan record_fan(const DevIndex& ix, const gb_node_rec& nr, 
     const uint32_t n_edges = __shfl_sync(FULL, head, 0);
     const uint32_t n_runs = __shfl_sync(FULL, head, 1);
     f.n_edges = n_edges;
+    if (n_edges == 1 && n_runs == 1) {
+        // the usual record away from variant sites: one successor, one run.  Every visit of [lo, hi] takes the edge, so the
+        // extended range is the edge offset plus the visits before lo — no scan over runs, no vote over edges.
+        const uint2 e = __ldg(reinterpret_cast<const uint2*>(rec + 2));
+        const int32_t len = (int32_t)(__ldg(rec + 4) >> 10);
+        const int32_t b = min(max(lo, 0), len);
+        const int32_t o = max(min(len, hi + 1) - max(0, lo), 0);
+        f.to = e.x; f.first = (int32_t)e.y + b; f.cnt = o; f.rev = 0;
+        return f;
+    }
     if (n_edges <= 32) {
         uint32_t my_to = 0, my_off = 0;
         if (lane < n_edges) {
