@@ -1,0 +1,20 @@
+#!/bin/bash
+# Round-2 measurement pass on one B200 (run under gpurun from the repo root):
+#   gpurun --timeout 2400 -- 'bash scripts/measure_r02.sh'
+# Everything lands in gpurun_out/; scripts/profile_summary.py turns the ncu outputs into profiles/*.{json,md} afterwards.
+set -u
+O=gpurun_out
+mkdir -p $O
+python -m pytest tests -m gpu -q > $O/r02_gputest.log 2>&1; echo "gpu tests rc=$?"; tail -2 $O/r02_gputest.log
+python bench.py > $O/r02_bench_head.json 2> $O/r02_bench_head.err; echo "bench rc=$?"
+K='seed_kernel|extend_kernel|align_|tail_plan|tail_decide|xdrop_tile|prep_pairs|compact_gather|rebase_offsets|advance_run|DeviceScan'
+ncu --metrics gpu__time_duration.sum --clock-control none -k regex:"$K" -c 800 --csv --log-file $O/r02_launches.csv \
+    python bench.py --steps 1 --warmup 1 --cpu-seconds 1 --no-secondary > $O/r02_bench_under_ncu.log 2>&1; echo "launch list rc=$?"
+ncu --set full --clock-control none --import-source on -k regex:"seed_kernel_pe|extend_kernel|align_fast|align_kernel|tail_plan|tail_decide|xdrop_tile" -s 26 -c 30 \
+    -o $O/r02_full_pe python scripts/profile_pe.py 1000000 2 > $O/r02_full_pe.log 2>&1; echo "full pe rc=$?"
+ncu --set full --clock-control none --import-source on -k regex:"xdrop_tile|tail_plan|tail_decide|^align_kernel" -s 14 -c 16 \
+    -o $O/r02_full_cfg5 python tests/tools/run_config.py config5 100000 > $O/r02_full_cfg5.log 2>&1; echo "full cfg5 rc=$?"
+timeout 1200 compute-sanitizer --tool memcheck --error-exitcode 1 --print-limit 20 python -m pytest tests/test_map_paired_parity.py tests/test_xdrop_golden.py tests/test_distance_model.py tests/test_vcf_graphs.py -m gpu -q \
+    > $O/r02_sanitizer_memcheck.log 2>&1; echo "memcheck rc=$?"; tail -3 $O/r02_sanitizer_memcheck.log
+timeout 900 compute-sanitizer --tool racecheck --error-exitcode 1 --print-limit 20 python -m pytest tests/test_map_paired_parity.py tests/test_xdrop_golden.py -m gpu -q -k "rescue or vectors or repeats" \
+    > $O/r02_sanitizer_racecheck.log 2>&1; echo "racecheck rc=$?"; tail -3 $O/r02_sanitizer_racecheck.log
