@@ -10,7 +10,7 @@ from pathlib import Path
 
 ROOT = Path(__file__).resolve().parents[1]
 tag, launches = sys.argv[1], sys.argv[2]
-rep = next((a for a in sys.argv[3:] if a.endswith(".ncu-rep")), None)
+rep = next((a for a in sys.argv[3:] if a.endswith(".ncu-rep") or a.endswith("_raw.csv")), None)      # a report, or its `--page raw --csv` export
 reads = int(sys.argv[sys.argv.index("--reads") + 1]) if "--reads" in sys.argv else None
 commit = sys.argv[sys.argv.index("--commit") + 1] if "--commit" in sys.argv else subprocess.run(["git", "rev-parse", "--short", "HEAD"], capture_output=True, text=True, cwd=ROOT).stdout.strip()
 
@@ -53,7 +53,7 @@ KEYS = {"gpu__time_duration.sum": "duration_ms", "launch__grid_size": "grid", "l
         "smsp__average_warps_issue_stalled_barrier_per_issue_active.ratio": "stall_barrier"}
 UNIT = {"Gbyte": 1e9, "Mbyte": 1e6, "Kbyte": 1e3, "byte": 1.0}
 if rep:
-    out = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+    out = open(rep, errors="replace").read() if rep.endswith(".csv") else subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
     rr = list(csv.reader(io.StringIO(out)))
     h, units = rr[0], rr[1]
     for r in rr[2:]:

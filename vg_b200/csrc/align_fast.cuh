@@ -361,7 +361,11 @@ __device__ inline bool fast_read(const DevIndex& ix, const MapParamsDev& P, cons
 
 struct FastArgs { uint32_t* slow_list; uint32_t* slow_count; };
 
-__global__ void __launch_bounds__(128)
+// MINB != 0 caps the registers for that many resident blocks per SM: the kernel waits on scattered record loads, more warps
+// in flight hide more of them (measured per 1 M reads: uncapped 48 registers 6.15 ms, 12 blocks 5.16 ms, 16 blocks 5.34 ms).
+// GIRAFFE_B200_FAST_MINB = 0 | 12 | 16 picks the instantiation; 12 is the default
+template <int MINB>
+__global__ void __launch_bounds__(128, MINB ? MINB : 1)
 align_fast_kernel_pe(DevIndex ix, MapParamsDev P, DevScores sc, MapBatch b, AlignArgs a, FastArgs fa) {
     const uint32_t n_pairs = b.n_reads / 2;
     for (uint32_t p = blockIdx.x * blockDim.x + threadIdx.x; p < n_pairs; p += gridDim.x * blockDim.x) {

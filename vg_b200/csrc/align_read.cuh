@@ -138,6 +138,7 @@ __device__ inline double faster_cap_warp(const MapParamsDev& P, const DevMinimiz
     if (qual == nullptr) return INFINITY;
     const int lane = lane_id();
     uint32_t n = 0;
+    __syncwarp();                                  // mp / c reuse the DP columns: every lane is done with them
     if (lane == 0) {
         for (uint32_t i = 0; i < M; i++) if (explored_mask[i >> 5] & (1u << (i & 31))) {
             const DevMinimizer dm = mins[i];
@@ -153,10 +154,11 @@ __device__ inline double faster_cap_warp(const MapParamsDev& P, const DevMinimiz
             mp[j] = wd; n++;
         }
     }
+    __syncwarp();                                  // lane 0's sorted words are visible to the warp
     n = __shfl_sync(FULL, n, 0);
     for (uint32_t i = lane; i <= n; i += 32) c[i] = i == 0 ? 0.0 : -INFINITY;
     __syncwarp();
-    if (n == 0) return -c[n] * 10;
+    if (n == 0) { const double r0 = -c[n] * 10; __syncwarp(); return r0; }
     auto column_prob = [&](uint32_t begin, uint32_t end, uint32_t index) {
         double p = P.phred_prob[qual[index]];
         for (uint32_t it = begin; it != end; ++it) {
@@ -213,7 +215,9 @@ __device__ inline double faster_cap_warp(const MapParamsDev& P, const DevMinimiz
         }
     }
     __syncwarp();
-    return -c[n] * 10;
+    const double result = -c[n] * 10;
+    __syncwarp();                                  // the next call (the mate) rewrites mp / c
+    return result;
 }
 
 // MappingQualityCalculator::compute_max_mapping_quality (exact, no multiplicities),

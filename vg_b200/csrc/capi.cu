@@ -44,7 +44,10 @@ struct ExtendBatch {
     const uint32_t* in_list; const uint32_t* in_count; uint32_t* big_of;
 };
 
-__global__ void __launch_bounds__(EXTEND_WARPS * 32, 4)
+// MINB: resident blocks per SM the register budget is cut for (4: 64 registers, 3: 80, 2: 128); GIRAFFE_B200_EXTEND_MINB picks
+// the instantiation at run time (tuning knob; default 4)
+template <int MINB>
+__global__ void __launch_bounds__(EXTEND_WARPS * 32, MINB)
 extend_kernel(DevIndex ix, ExtendParams p, ExtendBatch b, ExtendWorkspace ws) {
     extern __shared__ __align__(16) uint8_t smem[];
     const int warp_in_block = threadIdx.x >> 5;
@@ -124,6 +127,8 @@ extern "C" int gb_device_create(const gb_flat_index* ix, int device_ordinal, gb_
         if (v >= 2 && v <= (1ul << 24)) d->map_chunk = (uint32_t)(v & ~1ul);
     }
     if (const char* env = std::getenv("GIRAFFE_B200_TILES")) d->use_tiles = std::atoi(env) != 0;
+    if (const char* env = std::getenv("GIRAFFE_B200_EXTEND_MINB")) { const int v = std::atoi(env); if (v >= 2 && v <= 4) d->extend_minb = v; }
+    if (const char* env = std::getenv("GIRAFFE_B200_FAST_MINB")) { const int v = std::atoi(env); if (v == 0 || v == 12 || v == 16) d->fast_minb = v; }
     if (const char* env = std::getenv("GIRAFFE_B200_POOL_SCALE")) {
         const double v = std::strtod(env, nullptr);
         if (v > 0.0 && v <= 1024.0) d->pool_scale = v;
@@ -229,9 +234,11 @@ int launch_extend(gb_device* d, const ExtendParams& p, const ExtendBatch& b_in, 
     if (b.read_cap == 0) b.read_cap = 16;
     const size_t smem = (size_t)EXTEND_WARPS * b.read_cap;
     if (smem > 200 * 1024) { g_last_error = "read too long for the extension kernel"; return GB_ERR_ARG; }
-    if (smem > 48 * 1024) GB_CUDA(cudaFuncSetAttribute(extend_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    const int minb = d->extend_minb;
+    auto kern = minb == 2 ? extend_kernel<2> : (minb == 3 ? extend_kernel<3> : extend_kernel<4>);
+    if (smem > 48 * 1024) GB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     int blocks_per_sm = 0;
-    GB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocks_per_sm, extend_kernel, EXTEND_WARPS * 32, smem));
+    GB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocks_per_sm, kern, EXTEND_WARPS * 32, smem));
     if (blocks_per_sm < 1) blocks_per_sm = 1;
     uint32_t grid = (uint32_t)(d->n_sms * blocks_per_sm);
     const uint32_t needed = (b.n_items + EXTEND_WARPS - 1) / EXTEND_WARPS;
@@ -243,7 +250,7 @@ int launch_extend(gb_device* d, const ExtendParams& p, const ExtendBatch& b_in, 
     ExtendWorkspace ws{d->ws_queue.ptr, d->ws_arena.ptr, EXTEND_Q_CAP, EXTEND_A_CAP};
     b.work_counter = d->work_counter;
     GB_CUDA(cudaMemsetAsync(d->work_counter, 0, sizeof(uint32_t), d->stream));
-    extend_kernel<<<grid, EXTEND_WARPS * 32, smem, d->stream>>>(d->ix, p, b, ws);
+    kern<<<grid, EXTEND_WARPS * 32, smem, d->stream>>>(d->ix, p, b, ws);
     d->launches++;
     GB_CUDA(cudaGetLastError());
     return GB_OK;

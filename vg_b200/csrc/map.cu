@@ -427,7 +427,11 @@ int map_device(gb_device* d, const gb_map_params* hp, uint32_t n_reads, const ui
         FastArgs fa; fa.slow_list = d->p_slow.ptr; fa.slow_count = cur + 7;
         const uint32_t fgrid = std::max<uint32_t>(1u, std::min<uint32_t>((n_units + 127) / 128, (uint32_t)d->n_sms * 16));
         a.slow_list = nullptr; a.slow_count = nullptr;
-        if (paired) align_fast_kernel_pe<<<fgrid, 128, 0, d->stream>>>(d->ix, P, d->sc, b3, a, fa);
+        if (paired) {
+            if (d->fast_minb == 12) align_fast_kernel_pe<12><<<fgrid, 128, 0, d->stream>>>(d->ix, P, d->sc, b3, a, fa);
+            else if (d->fast_minb == 16) align_fast_kernel_pe<16><<<fgrid, 128, 0, d->stream>>>(d->ix, P, d->sc, b3, a, fa);
+            else align_fast_kernel_pe<0><<<fgrid, 128, 0, d->stream>>>(d->ix, P, d->sc, b3, a, fa);
+        }
         else align_fast_kernel<<<fgrid, 128, 0, d->stream>>>(d->ix, P, d->sc, b3, a, fa);
         d->launches++;
         GB_CUDA(cudaGetLastError());
