@@ -123,3 +123,36 @@ def test_map_parity_tail_alignment_with_non_acgt_bases():
     for i in rng.integers(0, rs.n, size=600):
         rs.reads[i, rng.integers(0, rs.length, size=3)] = ord("N")
     _run(g, rs)
+
+
+def _run_scored(g, rs, scores):
+    index = g.build_index()
+    dev = capi.Device(index, scores=scores)
+    got = H.gpu_map(dev, rs.reads, rs.quals)
+    plan = dev.plan_stats()
+    want = H.oracle_map(index, rs.reads, rs.quals, scores=scores, threads=8)
+    bad = H.compare_alignments(got, want, rs.n)
+    dev.close()
+    assert not bad, f"{len(bad)} of {rs.n} reads differ; first: read {bad[0][0]}\n got={bad[0][1]}\nwant={bad[0][2]}"
+    return plan, want
+
+
+@pytest.mark.gpu
+def test_map_parity_with_the_tile_kernels_switched_off(monkeypatch):
+    """GIRAFFE_B200_TILES=0: every tail DP runs the int32 column sweep inside the align kernels (the path a tile the
+    int16 kernel cannot take falls back to); same records as with the tiles."""
+    monkeypatch.setenv("GIRAFFE_B200_TILES", "0")
+    g = synth.make_variant_graph(length=200000, n_snp=320, n_ins=40, n_del=40, n_haps=8, seed=2)
+    rs = synth.simulate_reads(g, 2000, length=250, sub_rate=0.03, ins_rate=0.01, del_rate=0.01, seed=58)
+    plan, want = _run_scored(g, rs, None)
+    assert want[4]["tail_dps"] > 1000 and plan["cells"] == 0 and plan["tails"] == 0
+
+
+@pytest.mark.gpu
+def test_map_parity_when_the_scores_do_not_fit_int16_tiles():
+    """Scoring parameters x20: tile_scores_fit_int16 rejects 250 bp tails, so the plan holds no tiles and the tails are
+    aligned by the int32 sweep; the records still equal the oracle's under the same scores."""
+    g = synth.make_variant_graph(length=200000, n_snp=320, n_ins=40, n_del=40, n_haps=8, seed=2)
+    rs = synth.simulate_reads(g, 2000, length=250, sub_rate=0.03, ins_rate=0.01, del_rate=0.01, seed=59)
+    plan, want = _run_scored(g, rs, capi.Scores(20, 80, 120, 20, 100))
+    assert want[4]["tail_dps"] > 1000 and plan["cells"] == 0 and plan["tails"] == 0
