@@ -305,7 +305,7 @@ def secondary_workloads(ordinal, n=200_000, check=10_000):
         cells = int(want[4]["tail_cells"]) * n // check
         out[name] = {"reads": n, "reads_per_s": n / (best / 1e3), "kernel_ms": best, "kernel_ms_by_kernel": kern, "status_errors": int((got[3] != 0).sum()),
                      "parity": {"reads_checked": check, "mismatching_reads": len(bad)},
-                     "tail_dp": {"cells_reference_would_compute": cells, "cells_planned": plan["cells"], "tiles": plan["trees"]}}
+                     "tail_dp": {"cells_reference_would_compute": cells, "cells_planned": plan["cells"], "tiles": plan["trees"], "tails_aligned_in_place": plan["in_place"]}}
         dev.close(); index.close()
     return out
 

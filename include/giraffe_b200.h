@@ -470,8 +470,9 @@ int gb_stage_times(gb_device* dev, float* ms4);
 /* Device time of every kernel of the last mapping call (its last chunk), in launch order: names[i * 48 ..] (NUL
  * terminated) and ms[i]; at most cap entries, *n receives the count.  CUDA events recorded between the launches. */
 int gb_kernel_times(gb_device* dev, uint32_t cap, char* names, float* ms, uint32_t* n);
-/* Counters of the tail plan of the last mapping call (its last chunk): out4 = tails planned, haplotype trees, 0, DP cells
- * (columns x rows) handed to xdrop_tile_kernel. */
+/* Counters of the tail plan of the last mapping call (its last chunk): out4 = tails planned, haplotype trees, tails the
+ * align kernels aligned in place (int32 sweep) although their read had a plan, DP cells (columns x rows) handed to
+ * xdrop_tile_kernel. */
 int gb_plan_stats(gb_device* dev, uint64_t* out4);
 
 /* ------------------------------------------------------------------------------------

@@ -7,16 +7,16 @@ O=gpurun_out
 mkdir -p $O
 python -m pytest tests -m gpu -q > $O/r02_gputest.log 2>&1; echo "gpu tests rc=$?"; tail -2 $O/r02_gputest.log
 python bench.py > $O/r02_bench_head.json 2> $O/r02_bench_head.err; echo "bench rc=$?"
-K='seed_kernel|extend_kernel|align_|tail_plan|tail_decide|xdrop_tile|prep_pairs|compact_gather|rebase_offsets|advance_run|DeviceScan'
+K='seed_kernel|extend_|align_|tail_plan|tail_decide|xdrop_tile|prep_pairs|compact_gather|rebase_offsets|advance_run|DeviceScan'
 ncu --metrics gpu__time_duration.sum --clock-control none -k regex:"$K" -c 800 --csv --log-file $O/r02_launches.csv \
     python bench.py --steps 1 --warmup 1 --cpu-seconds 1 --no-secondary > $O/r02_bench_under_ncu.log 2>&1; echo "launch list rc=$?"
-ncu --set full --clock-control none --import-source on -k regex:"seed_kernel_pe|extend_kernel|align_fast|align_kernel|tail_plan|tail_decide|xdrop_tile" -s 26 -c 30 \
+ncu --set full --clock-control none --import-source on --profile-from-start off -k regex:"seed_kernel_pe|extend_|align_fast|align_kernel|tail_plan|tail_decide|xdrop_tile" -c 40 \
     -o $O/r02_full_pe python scripts/profile_pe.py 1000000 2 > $O/r02_full_pe.log 2>&1; echo "full pe rc=$?"
 # gpurun brings back at most 64 MiB: keep the raw metric page (and the hottest source lines), not the report
 ncu -i $O/r02_full_pe.ncu-rep --page raw --csv > $O/r02_full_pe_raw.csv 2>/dev/null
-for k in seed_kernel_pe extend_kernel align_fast_kernel_pe; do python scripts/ncu_lines.py $O/r02_full_pe.ncu-rep "$k" 25 > $O/r02_lines_$k.txt 2>&1; done
+for k in seed_kernel_pe extend_kernel extend_finish_kernel align_fast_kernel_pe; do python scripts/ncu_lines.py $O/r02_full_pe.ncu-rep "$k" 25 > $O/r02_lines_$k.txt 2>&1; done
 rm -f $O/r02_full_pe.ncu-rep
-ncu --set full --clock-control none --import-source on -k regex:"xdrop_tile|tail_plan|tail_decide|^align_kernel" -s 14 -c 16 \
+ncu --set full --clock-control none --import-source on --profile-from-start off -k regex:"xdrop_tile|tail_plan|tail_decide|^align_kernel" -c 40 \
     -o $O/r02_full_cfg5 python tests/tools/run_config.py config5 100000 > $O/r02_full_cfg5.log 2>&1; echo "full cfg5 rc=$?"
 ncu -i $O/r02_full_cfg5.ncu-rep --page raw --csv > $O/r02_full_cfg5_raw.csv 2>/dev/null
 python scripts/ncu_lines.py $O/r02_full_cfg5.ncu-rep "xdrop_tile_kernel" 25 > $O/r02_lines_xdrop_tile_kernel.txt 2>&1

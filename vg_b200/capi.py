@@ -7,6 +7,7 @@ There is no Python or CPU implementation of any hot-path stage in this package.
 from __future__ import annotations
 
 import ctypes as C
+import os
 from pathlib import Path
 
 import numpy as np
@@ -112,9 +113,10 @@ def load_library() -> C.CDLL:
     global _lib
     if _lib is not None:
         return _lib
-    if not LIB_PATH.exists():
-        raise RuntimeError(f"{LIB_PATH} is missing: run `python -m vg_b200.build` (there is no fallback path)")
-    lib = C.CDLL(str(LIB_PATH))
+    path = Path(os.environ.get("GIRAFFE_B200_LIB", LIB_PATH))      # another build of the same library (kernel A/B runs)
+    if not path.exists():
+        raise RuntimeError(f"{path} is missing: run `python -m vg_b200.build` (there is no fallback path)")
+    lib = C.CDLL(str(path))
     vp, u32, u64 = C.c_void_p, C.c_uint32, C.c_uint64
     lib.gb_index_build.argtypes = [u32, vp, vp, u32, vp, vp, vp, u32, u32, C.POINTER(vp)]
     lib.gb_index_build.restype = C.c_int
@@ -678,7 +680,7 @@ class Device:
 
     def kernel_times(self):
         """Per-kernel device time of the last mapping call's last chunk: list of (kernel name, ms)."""
-        cap = 32
+        cap = 48
         names = C.create_string_buffer(cap * 48); ms = (C.c_float * cap)(); n = C.c_uint32()
         rc = load_library().gb_kernel_times(self._h, cap, names, ms, C.byref(n))
         if rc != GB_OK:
@@ -690,7 +692,7 @@ class Device:
         rc = load_library().gb_plan_stats(self._h, out)
         if rc != GB_OK:
             raise GbError(rc, "gb_plan_stats")
-        return {"tails": int(out[0]), "trees": int(out[1]), "cells": int(out[3])}
+        return {"tails": int(out[0]), "trees": int(out[1]), "in_place": int(out[2]), "cells": int(out[3])}
 
     def stage_times(self):
         ms = (C.c_float * 4)()

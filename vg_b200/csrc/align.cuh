@@ -54,19 +54,24 @@ __device__ inline int score_extension_group(const gb_extension* ext, uint32_t n,
     int best_chain[64];
     bool active[64];
     const uint32_t nn = min(n, 64u);
+#pragma unroll 1
     for (uint32_t i = 0; i < nn; i++) { best_chain[i] = 0; active[i] = false; }
     int overlap_enc[64]; bool overlap_live[64];
+#pragma unroll 1
     for (uint32_t i = 0; i < nn; i++) overlap_live[i] = false;
     int64_t sweep_line = 0, last_sweep_line = 0;
     uint32_t unentered = 0;
     int best_gap_score = 0, best_past_ending_score_ever = 0, overlap_score_offset = 0;
+#pragma unroll 1
     while (last_sweep_line <= (int64_t)seq_len) {
         int64_t next_seed_start = INT64_MAX, next_seed_end = INT64_MAX;
         if (unentered < nn) next_seed_start = ext[unentered].read_lo;
+#pragma unroll 1
         for (uint32_t i = 0; i < nn; i++) if (active[i]) next_seed_end = min(next_seed_end, (int64_t)ext[i].read_hi);
         sweep_line = min(min(next_seed_end, next_seed_start), (int64_t)seq_len);
         const int sweep_distance = (int)(sweep_line - last_sweep_line + 1);
         int best_past_ending_score_here = 0;
+#pragma unroll 1
         for (uint32_t i = 0; i < nn; i++) if (active[i] && (int64_t)ext[i].read_hi == sweep_line) {
             best_past_ending_score_here = max(best_past_ending_score_here, best_chain[i]);
             active[i] = false;
@@ -78,6 +83,7 @@ __device__ inline int score_extension_group(const gb_extension* ext, uint32_t n,
         {
             // top of the max-heap over (encoded score, past-end) among entries not yet passed
             bool any = false; int best_enc = 0; uint32_t best_end = 0;
+#pragma unroll 1
             for (uint32_t i = 0; i < nn; i++) {
                 if (!overlap_live[i]) continue;
                 if ((int64_t)ext[i].read_hi <= sweep_line) continue;
@@ -87,6 +93,7 @@ __device__ inline int score_extension_group(const gb_extension* ext, uint32_t n,
         }
         if (best_gap_score != 0) best_gap_score -= sweep_distance * ge;
         best_gap_score = max(0, max(best_gap_score, best_past_ending_score_here - (go - ge)));
+#pragma unroll 1
         while (unentered < nn && (int64_t)ext[unentered].read_lo == sweep_line) {
             best_chain[unentered] = max(best_overlap_score, max(best_gap_score, best_past_ending_score_here)) + ext[unentered].score;
             const int extension_length = (int)(ext[unentered].read_hi - ext[unentered].read_lo);
@@ -105,11 +112,13 @@ __device__ inline void extension_to_path(const DevIndex& ix, const gb_extension&
                                          const uint8_t* read, PathBuf& pb) {
     uint32_t mi = 0;
     uint32_t read_offset = e.read_lo, node_offset = e.offset;
+#pragma unroll 1
     for (uint32_t i = 0; i < e.path_len; i++) {
         const uint32_t h = path_pool[e.path_off + i];
         const uint32_t nlen = load_node(ix, h).len;
         const uint32_t limit = min(read_offset + nlen - node_offset, e.read_hi);
         pb_add_mapping(pb, h, node_offset);
+#pragma unroll 1
         while (mi < e.mism_len && mism_pool[e.mism_off + mi] < limit) {
             const uint32_t mp = mism_pool[e.mism_off + mi];
             if (read_offset < mp) pb_add_edit(pb, edit_word(GB_EDIT_MATCH, mp - read_offset, 0));
@@ -128,6 +137,7 @@ __device__ __forceinline__ bool mapping_is_total_insertion(const PathBuf& p, uin
 // add_to_path (minimizer_mapper.cpp:5318-5367): append `src` mappings to `dst` (lane 0 only).
 __device__ inline void add_to_path(PathBuf& dst, const gb_mapping* src_maps, const uint32_t* src_edits, uint32_t n_maps) {
     uint32_t se = 0;
+#pragma unroll 1
     for (uint32_t i = 0; i < n_maps; i++) {
         const gb_mapping m = src_maps[i];
         bool combined = false;
@@ -146,6 +156,7 @@ __device__ inline void add_to_path(PathBuf& dst, const gb_mapping* src_maps, con
                     }
                 }
                 if (can_combine) {
+#pragma unroll 1
                     for (uint32_t x = 0; x < m.n_edits; x++) pb_add_edit(dst, src_edits[se + x]);
                     combined = true;
                 }
@@ -153,6 +164,7 @@ __device__ inline void add_to_path(PathBuf& dst, const gb_mapping* src_maps, con
         }
         if (!combined) {
             pb_add_mapping(dst, m.node, m.offset);
+#pragma unroll 1
             for (uint32_t x = 0; x < m.n_edits; x++) pb_add_edit(dst, src_edits[se + x]);
         }
         se += m.n_edits;
@@ -164,13 +176,18 @@ struct Pareto { uint32_t first; int32_t second; };
 __device__ inline uint32_t find_pareto_frontier(Pareto* v, uint32_t n) {
     if (n == 0) return 0;
     // sort by (second asc, first desc)
+#pragma unroll 1
     for (uint32_t i = 1; i < n; i++) { Pareto key = v[i]; uint32_t j = i;
+#pragma unroll 1
         while (j > 0 && (key.second < v[j - 1].second || (key.second == v[j - 1].second && key.first > v[j - 1].first))) { v[j] = v[j - 1]; j--; }
         v[j] = key; }
     uint32_t tail = 1;
+#pragma unroll 1
     for (uint32_t i = 1; i < n; i++) { if (v[i].first <= v[tail - 1].first) continue; v[tail] = v[i]; tail++; }
     n = tail;
+#pragma unroll 1
     for (uint32_t i = 1; i < n; i++) { Pareto key = v[i]; uint32_t j = i;
+#pragma unroll 1
         while (j > 0 && (key.first < v[j - 1].first || (key.first == v[j - 1].first && key.second < v[j - 1].second))) { v[j] = v[j - 1]; j--; }
         v[j] = key; }
     return n;
@@ -181,6 +198,7 @@ __device__ __forceinline__ int32_t gap_penalty2(uint32_t start, uint32_t limit, 
 }
 __device__ inline int32_t flank_penalty(uint32_t length, const Pareto* f, uint32_t n, const DevScores& s) {
     int32_t result = gap_penalty1(length, s);
+#pragma unroll 1
     for (uint32_t i = 0; i < n; i++) {
         result = min(result, f[i].second + gap_penalty2(f[i].first, length, s));
         if (f[i].first >= length) break;
@@ -208,6 +226,7 @@ __device__ inline int32_t align_tail(const DevIndex& ix, const MapParamsDev& P, 
     } else {
         from_node = last;
         uint32_t tail_off = e.offset + (e.read_hi - e.read_lo);
+#pragma unroll 1
         for (uint32_t i = 0; i + 1 < e.path_len; i++) tail_off -= load_node(ix, path_pool[e.path_off + i]).len;
         from_offset = tail_off;
         lo = (int32_t)e.fwd_lo; hi = (int32_t)e.fwd_hi;
@@ -220,6 +239,7 @@ __device__ inline int32_t align_tail(const DevIndex& ix, const MapParamsDev& P, 
     // the same LazyRNG draws on ties, as the in-place loop below (get_best_alignment_against_any_tree, :5626-5743)
     if (tl.pv) {
         const TailPlanEntry* pe = nullptr;
+#pragma unroll 1
         for (uint32_t x = 0; x < tl.count; x++) if (tl.pv->entries[tl.base + x].key == tl.key) { pe = tl.pv->entries + tl.base + x; break; }
         // a cancelled tail (the decide pass judged that the reference skips it, :5478-5492) is never asked for; should the
         // walk here disagree, the tail is simply aligned in place
@@ -232,6 +252,7 @@ __device__ inline int32_t align_tail(const DevIndex& ix, const MapParamsDev& P, 
             if (lane == 0) { pb_add_mapping(res, default_node, default_offset); pb_add_edit(res, edit_word(GB_EDIT_INS, tail_length, 0)); }
             __syncwarp();
             res.n_maps = 1; res.n_edits = 1;
+#pragma unroll 1
             for (uint32_t t = 0; t < pe->n_trees; t++) {
                 const uint32_t ti = pe->first_tile + t;
                 if (tl.pv->tile_off[ti] == TILE_REFUSED) continue;            // subgraph too large for max_dozeu_cells (:5694-5701)
@@ -245,7 +266,9 @@ __device__ inline int32_t align_tail(const DevIndex& ix, const MapParamsDev& P, 
                     if (tr.n_maps > res.map_cap || tr.n_edits > res.edit_cap) { status = GB_ITEM_OUT_FULL; return 0; }
                     const gb_mapping* gm = reinterpret_cast<const gb_mapping*>(tl.pv->path_pool + tr.path_off);
                     const uint32_t* gedits = tl.pv->path_pool + tr.path_off + 2 * tr.n_maps;
+#pragma unroll 1
                     for (uint32_t i = lane; i < tr.n_maps; i += 32) res.maps[i] = gm[i];
+#pragma unroll 1
                     for (uint32_t i = lane; i < tr.n_edits; i += 32) res.edits[i] = gedits[i];
                     __syncwarp();
                     res.n_maps = tr.n_maps; res.n_edits = tr.n_edits; res.overflow = false;
@@ -253,9 +276,11 @@ __device__ inline int32_t align_tail(const DevIndex& ix, const MapParamsDev& P, 
             }
             return best_score;
         }
+        if (lane == 0 && tl.pv->stats) atomicAdd((unsigned long long*)&tl.pv->stats[2], 1ull);
     }
     const uint32_t gap = longest_detectable_gap(sc, L, tail_length);
     // query: the tail itself (right tail) or its reverse complement (left tail)
+#pragma unroll 1
     for (uint32_t i = lane; i < tail_length; i += 32)
         qbuf[i] = dp_query_base(left_tail ? comp_base(read[tail_length - 1 - i]) : read[e.read_hi + i]);
     __syncwarp();
@@ -270,11 +295,14 @@ __device__ inline int32_t align_tail(const DevIndex& ix, const MapParamsDev& P, 
     const uint32_t n_forest = build_tail_forest(ix, ws, from_node, lo, hi, from_offset, gap + tail_length, root_trim);
     if (n_forest == 0xffffffffu) { status = GB_ITEM_OUT_FULL; return 0; }
     uint32_t t0 = 0;
+#pragma unroll 1
     while (t0 < n_forest) {
         uint32_t t1 = t0 + 1;
+#pragma unroll 1
         while (t1 < n_forest && ws.tree[t1].parent >= 0) t1++;
         // subgraph size check (:5694-5701)
         uint32_t bases = 0;
+#pragma unroll 1
         for (uint32_t i = t0 + lane; i < t1; i += 32) bases += ws.tree[i].len;
         bases = (uint32_t)warp_sum((int)bases);
         if ((uint64_t)bases * tail_length <= P.max_dozeu_cells) {
@@ -295,12 +323,14 @@ __device__ inline int32_t align_tail(const DevIndex& ix, const MapParamsDev& P, 
                     if (!left_tail) {
                         // translate_down (tree_subgraph.cpp:172-195)
                         uint32_t se = 0;
+#pragma unroll 1
                         for (uint32_t i = 0; i < scratch.n_maps; i++) {
                             const gb_mapping m = scratch.maps[i];
                             const TreeNode tn = ws.tree[m.node];
                             uint32_t off = m.offset;
                             if (m.node == t0 && root_trim != 0) off += root_trim;    // trimmed root, forward strand
                             pb_add_mapping(res, tn.node, off);
+#pragma unroll 1
                             for (uint32_t x = 0; x < m.n_edits; x++) pb_add_edit(res, scratch.edits[se + x]);
                             se += m.n_edits;
                         }
@@ -310,14 +340,17 @@ __device__ inline int32_t align_tail(const DevIndex& ix, const MapParamsDev& P, 
                         (void)ends;
                         // edit start offsets per mapping
                         uint32_t se_end = scratch.n_edits;
+#pragma unroll 1
                         for (int64_t i = (int64_t)scratch.n_maps - 1; i >= 0; i--) {
                             const gb_mapping m = scratch.maps[i];
                             const uint32_t se_begin = se_end - m.n_edits;
                             const TreeNode tn = ws.tree[m.node];
                             uint32_t used = 0;
+#pragma unroll 1
                             for (uint32_t x = se_begin; x < se_end; x++) { const uint32_t wd = scratch.edits[x]; const uint32_t op = wd & 3u; if (op != GB_EDIT_INS) used += (op == GB_EDIT_SUB) ? 1u : (wd >> 4); }
                             const uint32_t new_off = tn.len - used - m.offset;
                             pb_add_mapping(res, tn.node ^ 1u, new_off);
+#pragma unroll 1
                             for (int64_t x = (int64_t)se_end - 1; x >= (int64_t)se_begin; x--) {
                                 uint32_t wd = scratch.edits[x];
                                 if ((wd & 3u) == GB_EDIT_SUB) wd = (wd & ~0xCu) | ((3u - ((wd >> 2) & 3u)) << 2);   // complement the base

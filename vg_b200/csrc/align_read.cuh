@@ -32,8 +32,9 @@ struct AlignArgs {
 constexpr uint32_t N_SLOTS = 2 * MAX_CANDS + 8 + 32;   // candidate path slots per warp (both mates of a pair, + rescued alignments)
 constexpr uint32_t N_TEMP_SLOTS = 5;              // res_left, res_right, scratch, middle, assembly
 
-__device__ __forceinline__ double d_add_log(double x, double y) { return x > y ? x + log1p(exp(y - x)) : y + log1p(exp(x - y)); }
-__device__ __forceinline__ double d_subtract_log(double x, double y) { return x + log1p(-exp(y - x)); }
+// (real calls: the FP64 log1p / exp bodies are several hundred instructions and the align kernels are instruction-fetch bound)
+static __device__ __noinline__ double d_add_log(double x, double y) { return x > y ? x + log1p(exp(y - x)) : y + log1p(exp(x - y)); }
+static __device__ __noinline__ double d_subtract_log(double x, double y) { return x + log1p(-exp(y - x)); }
 
 __device__ inline PathBuf slot_buf(uint8_t* cand_base, uint32_t slot, uint32_t map_cap, uint32_t edit_cap) {
     PathBuf p;
@@ -140,12 +141,14 @@ __device__ inline double faster_cap_warp(const MapParamsDev& P, const DevMinimiz
     uint32_t n = 0;
     __syncwarp();                                  // mp / c reuse the DP columns: every lane is done with them
     if (lane == 0) {
+#pragma unroll 1
         for (uint32_t i = 0; i < M; i++) if (explored_mask[i >> 5] & (1u << (i & 31))) {
             const DevMinimizer dm = mins[i];
             const uint32_t as = dm.agg_start, ae = (uint32_t)dm.agg_start + dm.agg_len;
             const uint64_t wd = (uint64_t)as | ((uint64_t)ae << 16) | ((uint64_t)dm.fwd_offset << 32) | ((dm.hash >> 56) << 48);
             const uint32_t key = (ae << 16) | as;
             uint32_t j = n;
+#pragma unroll 1
             while (j > 0) {
                 const uint64_t o = mp[j - 1];
                 const uint32_t okey = ((uint32_t)(o >> 16) << 16) | (uint32_t)(o & 0xffffu);
@@ -156,11 +159,13 @@ __device__ inline double faster_cap_warp(const MapParamsDev& P, const DevMinimiz
     }
     __syncwarp();                                  // lane 0's sorted words are visible to the warp
     n = __shfl_sync(FULL, n, 0);
+#pragma unroll 1
     for (uint32_t i = lane; i <= n; i += 32) c[i] = i == 0 ? 0.0 : -INFINITY;
     __syncwarp();
     if (n == 0) { const double r0 = -c[n] * 10; __syncwarp(); return r0; }
     auto column_prob = [&](uint32_t begin, uint32_t end, uint32_t index) {
         double p = P.phred_prob[qual[index]];
+#pragma unroll 1
         for (uint32_t it = begin; it != end; ++it) {
             const uint64_t wd = mp[it];
             const uint32_t as = (uint32_t)wd & 0xffffu, ae = (uint32_t)(wd >> 16) & 0xffffu, fwd = (uint32_t)(wd >> 32) & 0xffffu;
@@ -181,10 +186,12 @@ __device__ inline double faster_cap_warp(const MapParamsDev& P, const DevMinimiz
         __syncwarp();
         if (lane == 0) {
             const double pv = c[ib] + p_here;
+#pragma unroll 1
             for (uint32_t i = ib + 1; i < itop + 1; i++) if (c[i] < pv) c[i] = pv;
         }
         __syncwarp();
     };
+#pragma unroll 1
     while (true) {
         if (left < pending_right) {
             const uint32_t stack_size = back - front, stack_top_end = agg_end_of(front);
@@ -197,10 +204,12 @@ __device__ inline double faster_cap_warp(const MapParamsDev& P, const DevMinimiz
             } else { right = pending_right; left = pending_right; }
             if (col0 == right) { close_interval(ib, itop, 0.0); continue; }
             double p = 0.0; bool first = true;
+#pragma unroll 1
             for (uint32_t base = col0; base < right; base += 32) {
                 const uint32_t idx = base + lane;
                 const double cp = idx < right ? column_prob(ib, itop, idx) : 0.0;
                 const uint32_t cnt = min(32u, right - base);
+#pragma unroll 1
                 for (uint32_t x = 0; x < cnt; x++) {
                     const double col_p = __shfl_sync(FULL, cp, x);
                     p = first ? col_p : (p + col_p - (p * col_p));
@@ -225,6 +234,7 @@ __device__ inline double faster_cap_warp(const MapParamsDev& P, const DevMinimiz
 __device__ inline double max_mapping_quality(const double* scores, uint32_t n, double log_base) {
     const double quality_scale_factor = 10.0 / log(10.0);
     double log_sum_exp = -DBL_MAX, to_score = -DBL_MAX;
+#pragma unroll 1
     for (int64_t i = (int64_t)n - 1; i >= 0; --i) {
         const double score = log_base * scores[i];
         if (score >= to_score) to_score = score;
@@ -247,9 +257,12 @@ __device__ inline bool deferred_cluster_selection(const MapParamsDev& P, const R
     if (ties <= 1) return false;
     const uint32_t Cr = rs.item_cnt;
     uint8_t order[MAX_SETS];
+#pragma unroll 1
     for (uint32_t i = 0; i < Cr; i++) order[i] = (uint8_t)i;
+#pragma unroll 1
     for (uint32_t i = 1; i < ties && i < Cr; i++) { const uint32_t j = rng_next(rng) % (i + 1); const uint8_t t = order[j]; order[j] = order[i]; order[i] = t; }
     uint32_t unskipped = 0, kept_cluster_count = 0, nk = 0;
+#pragma unroll 1
     for (uint32_t i = 0; i < Cr; i++) {
         if (unskipped >= P.max_extensions) continue;
         const uint32_t fl = items[rs.item_off + order[i]].fragment >> 8;
@@ -286,20 +299,28 @@ __device__ inline uint32_t align_sets(const DevIndex& ix, const MapParamsDev& P,
     uint8_t sel[MAX_SETS];                        // work items of this read in processing order (indices into its item list)
     if (!deferred_cluster_selection(P, rs, a.items, rng, sel, S)) for (uint32_t s = 0; s < S; s++) sel[s] = (uint8_t)s;
     const uint32_t map_cap = P.mapping_cap, edit_cap = P.edit_cap;
-    auto alloc_slot = [&]() -> uint32_t { for (uint32_t i = 0; i < N_SLOTS; i++) if (!slot_used[i]) { slot_used[i] = true; return i; } return 0xffffffffu; };
+    auto alloc_slot = [&]() -> uint32_t {
+#pragma unroll 1
+        for (uint32_t i = 0; i < N_SLOTS; i++) if (!slot_used[i]) { slot_used[i] = true; return i; }
+        return 0xffffffffu;
+    };
 #pragma unroll
     for (uint32_t x = 0; x < PRESENT_WORDS; x++) explored[x] = 0;
 
     int set_score[MAX_SETS]; uint8_t set_order[MAX_SETS];
+#pragma unroll 1
     for (uint32_t s = 0; s < S; s++) {
         const uint32_t item = rs.item_off + sel[s];
         if (a.ev.ext_status[item] != GB_ITEM_OK) return a.ev.ext_status[item];
         set_score[s] = score_extension_group(ev_ext(a.ev, item), a.ev.ext_count[item], L, sc.gap_open, sc.gap_extend);
     }
+#pragma unroll 1
     for (uint32_t s = 0; s < S; s++) { uint32_t j = s; while (j > 0 && set_score[s] > set_score[set_order[j - 1]]) { set_order[j] = set_order[j - 1]; j--; } set_order[j] = (uint8_t)s; }
     {
         uint32_t ties = 0;
+#pragma unroll 1
         while (ties < S && !(set_score[set_order[0]] > set_score[set_order[ties]])) ties++;
+#pragma unroll 1
         for (uint32_t i = 1; i < ties; i++) { const uint32_t j = rng_next(rng) % (i + 1); const uint8_t t = set_order[j]; set_order[j] = set_order[i]; set_order[i] = t; }
     }
     const double set_cutoff = S == 0 ? 0.0 : (double)set_score[set_order[0]] - P.extension_set_score_threshold;
@@ -310,12 +331,15 @@ __device__ inline uint32_t align_sets(const DevIndex& ix, const MapParamsDev& P,
     PathBuf res_left = tmp_buf(0), res_right = tmp_buf(1), scratch = tmp_buf(2), middle = tmp_buf(3), asmb = tmp_buf(4);
     // a finished path leaves the assembly buffer for its candidate slot (the whole warp copies)
     auto store_slot = [&](PathBuf& dst, const PathBuf& src, uint32_t nm, uint32_t ne) {
+#pragma unroll 1
         for (uint32_t i = lane; i < nm; i += 32) dst.maps[i] = src.maps[i];
+#pragma unroll 1
         for (uint32_t i = lane; i < ne; i += 32) dst.edits[i] = src.edits[i];
         if (lane == 0) { slot_nm(dst) = nm; slot_ne(dst) = ne; }
         __syncwarp();
     };
 
+#pragma unroll 1
     for (uint32_t oi = 0; oi < S && status == GB_ITEM_OK; oi++) {
         const uint32_t s = set_order[oi];
         bool process;
@@ -333,6 +357,7 @@ __device__ inline uint32_t align_sets(const DevIndex& ix, const MapParamsDev& P,
 
         int32_t ba_score[50]; uint32_t ba_slot[50]; uint32_t n_ba = 0;
         if (n_ext > 0 && ext_full(ext[0]) && ext[0].mismatches <= 4) {
+#pragma unroll 1
             for (uint32_t j = 0; j < n_ext && (j == 0 || ext_full(ext[j])) && n_ba < 49; j++) {
                 const uint32_t slot = alloc_slot();
                 if (slot == 0xffffffffu) { status = GB_ITEM_OUT_FULL; break; }
@@ -348,9 +373,11 @@ __device__ inline uint32_t align_sets(const DevIndex& ix, const MapParamsDev& P,
         } else if (P.do_dp) {
             // ---- find_optimal_tail_alignments (:5369-5622) -----------------------------------------
             uint32_t min_tails = 1;
+#pragma unroll 1
             for (uint32_t j = 0; j < n_ext; j++) if (ext_full(ext[j])) min_tails++;
             if (min_tails < 2) min_tails = 2;
             Pareto lf[136], rf[136]; uint32_t nl = 0, nr = 0;
+#pragma unroll 1
             for (uint32_t j = 0; j < n_ext && nl + 3 < 136; j++) {
                 const gb_extension& e = ext[j];
                 if (ext_full(e)) continue;
@@ -368,10 +395,13 @@ __device__ inline uint32_t align_sets(const DevIndex& ix, const MapParamsDev& P,
             nl = find_pareto_frontier(lf, nl); nr = find_pareto_frontier(rf, nr);
 
             uint8_t eo[64]; const uint32_t ne_ = min(n_ext, 64u);
+#pragma unroll 1
             for (uint32_t j = 0; j < ne_; j++) { uint32_t x = j; while (x > 0 && ext[j].score > ext[eo[x - 1]].score) { eo[x] = eo[x - 1]; x--; } eo[x] = (uint8_t)j; }
             {
                 uint32_t ties = 0;
+#pragma unroll 1
                 while (ties < ne_ && !(ext[eo[0]].score > ext[eo[ties]].score)) ties++;
+#pragma unroll 1
                 for (uint32_t i = 1; i < ties; i++) { const uint32_t j = rng_next(rng) % (i + 1); const uint8_t t = eo[j]; eo[j] = eo[i]; eo[i] = t; }
             }
             const double ecut = ne_ == 0 ? 0.0 : (double)ext[eo[0]].score - (double)P.extension_score_threshold;
@@ -380,6 +410,7 @@ __device__ inline uint32_t align_sets(const DevIndex& ix, const MapParamsDev& P,
             int32_t winning_score = 0, second_score = 0;
             int64_t winning_start = 0, winning_end = 0;
             bool partial_extension_aligned = false; int32_t threshold = -1;
+#pragma unroll 1
             for (uint32_t xi = 0; xi < ne_ && status == GB_ITEM_OK; xi++) {
                 const gb_extension& e = ext[eo[xi]];
                 bool eproc;
@@ -457,6 +488,7 @@ __device__ inline uint32_t align_sets(const DevIndex& ix, const MapParamsDev& P,
         if (status != GB_ITEM_OK) break;
         // keep alignments with score != 0 and >= 0.8 * best (:1025-1028, :2008-2011)
         bool keep = true;
+#pragma unroll 1
         for (uint32_t j = 0; j < n_ba; j++) {
             if (keep && ba_score[j] != 0 && (double)ba_score[j] >= (double)ba_score[0] * 0.8) {
                 if (cl.n >= 2 * MAX_CANDS || (cl.n >= MAX_CANDS && !paired)) { status = GB_ITEM_OUT_FULL; break; }
@@ -481,8 +513,10 @@ __device__ inline void write_alignment(const DevIndex& ix, const PathBuf& pb, ui
                                        gb_mapping* out_maps, uint32_t* out_edits) {
     if (!rc) {
         uint32_t qoff = 0, e = 0;
+#pragma unroll 1
         for (uint32_t i = 0; i < nm; i++) {
             out_maps[i] = pb.maps[i];
+#pragma unroll 1
             for (uint32_t x = 0; x < pb.maps[i].n_edits; x++, e++) {
                 uint32_t wd = pb.edits[e]; const uint32_t op = wd & 3u, len = wd >> 4;
                 if (op == GB_EDIT_SUB) { wd = (1u << 4) | (base2(sread[qoff]) << 2) | GB_EDIT_SUB; qoff += 1; }
@@ -494,13 +528,16 @@ __device__ inline void write_alignment(const DevIndex& ix, const PathBuf& pb, ui
         // walk mappings backwards; query offsets count from the end of the rightward read
         uint32_t e_end = ne, qend = L, w = 0;
         // total query length consumed equals L (softclips included)
+#pragma unroll 1
         for (int64_t i = (int64_t)nm - 1; i >= 0; i--) {
             const gb_mapping m = pb.maps[i];
             const uint32_t e_begin = e_end - m.n_edits;
             uint32_t used = 0;
+#pragma unroll 1
             for (uint32_t x = e_begin; x < e_end; x++) { const uint32_t wd = pb.edits[x]; const uint32_t op = wd & 3u; if (op != GB_EDIT_INS) used += (op == GB_EDIT_SUB) ? 1u : (wd >> 4); }
             gb_mapping o; o.node = m.node ^ 1u; o.offset = (uint16_t)(load_node(ix, m.node).len - used - m.offset); o.n_edits = m.n_edits;
             out_maps[nm - 1 - (uint32_t)i] = o;
+#pragma unroll 1
             for (int64_t x = (int64_t)e_end - 1; x >= (int64_t)e_begin; x--) {
                 uint32_t wd = pb.edits[x]; const uint32_t op = wd & 3u, len = wd >> 4;
                 if (op == GB_EDIT_SUB) {
@@ -528,10 +565,14 @@ __device__ inline uint32_t finalize_se(const DevIndex& ix, const MapParamsDev& P
     if (cl.n == 0) { scores_sorted[0] = 0.0; n_scores = 1; }
     else {
         uint8_t co[MAX_CANDS];
+#pragma unroll 1
         for (uint32_t c = 0; c < cl.n; c++) { uint32_t j = c; while (j > 0 && cl.score[c] > cl.score[co[j - 1]]) { co[j] = co[j - 1]; j--; } co[j] = (uint8_t)c; }
         uint32_t ties = 0;
+#pragma unroll 1
         while (ties < cl.n && !(cl.score[co[0]] > cl.score[co[ties]])) ties++;
+#pragma unroll 1
         for (uint32_t i = 1; i < ties; i++) { const uint32_t j = rng_next(rng) % (i + 1); const uint8_t t = co[j]; co[j] = co[i]; co[i] = t; }
+#pragma unroll 1
         for (uint32_t c = 0; c < cl.n; c++) scores_sorted[c] = (double)cl.score[co[c]];
         n_scores = cl.n; win = co[0];
     }
@@ -587,6 +628,7 @@ __device__ inline uint32_t finalize_pe(const DevIndex& ix, const MapParamsDev& P
                                        DpSmem dps, uint8_t* cand_base, gb_alignment* out /*[2]*/, gb_mapping* const* out_maps, uint32_t* const* out_edits) {
     const int lane = lane_id();
     const uint32_t map_cap = P.mapping_cap, edit_cap = P.edit_cap;
+#pragma unroll 1
     for (uint32_t r = 0; r < 2; r++) {
         out[r].read_id = read_idx0 + r; out[r].score = 0; out[r].mapq = 0; out[r].flags = GB_ALN_PAIRED; out[r].n_mappings = 0; out[r].n_edits = 0;
         out[r].mapq_uncapped = 0.f; out[r].mapq_explored_cap = 0.f;
@@ -598,13 +640,17 @@ __device__ inline uint32_t finalize_pe(const DevIndex& ix, const MapParamsDev& P
     uint32_t n_pairs = 0; bool found_pair = false;
     uint8_t unpaired[2 * MAX_CANDS]; uint32_t n_unpaired = 0;
     uint32_t status = GB_ITEM_OK;
+#pragma unroll 1
     for (uint32_t f = 0; f < n_frag_slots && status == GB_ITEM_OK; f++) {
         bool has0 = false, has1 = false;
+#pragma unroll 1
         for (uint32_t c = 0; c < cl.n; c++) if (cl.frag[c] == f) { if (cl.read[c] == 0) has0 = true; else has1 = true; }
         if (has0 && has1) {
             found_pair = true;
+#pragma unroll 1
             for (uint32_t c0 = 0; c0 < cl.n && status == GB_ITEM_OK; c0++) {
                 if (cl.frag[c0] != f || cl.read[c0] != 0) continue;
+#pragma unroll 1
                 for (uint32_t c1 = 0; c1 < cl.n; c1++) {
                     if (cl.frag[c1] != f || cl.read[c1] != 1) continue;
                     if (n_pairs >= MAX_PAIRS) { status = GB_ITEM_OUT_FULL; break; }
@@ -617,6 +663,7 @@ __device__ inline uint32_t finalize_pe(const DevIndex& ix, const MapParamsDev& P
                         const uint32_t nm1 = slot_nm(p1), ne1 = slot_ne(p1);
                         const gb_mapping last = p1.maps[nm1 - 1];
                         uint32_t used = 0;
+#pragma unroll 1
                         for (uint32_t x = ne1 - last.n_edits; x < ne1; x++) { const uint32_t wd = p1.edits[x]; const uint32_t op = wd & 3u; if (op != GB_EDIT_INS) used += (op == GB_EDIT_SUB) ? 1u : (wd >> 4); }
                         dist = oriented_distance(ix, first.node, first.offset, last.node, (uint32_t)last.offset + used);
                     }
@@ -631,6 +678,7 @@ __device__ inline uint32_t finalize_pe(const DevIndex& ix, const MapParamsDev& P
                 }
             }
         } else {
+#pragma unroll 1
             for (uint32_t r = 0; r < 2; r++) for (uint32_t c = 0; c < cl.n; c++) if (cl.frag[c] == f && cl.read[c] == r) unpaired[n_unpaired++] = (uint8_t)c;
         }
     }
@@ -640,12 +688,14 @@ __device__ inline uint32_t finalize_pe(const DevIndex& ix, const MapParamsDev& P
     if (n_unpaired > 0 && !found_pair) {
         // max_rescue_attempts == 0 (:2227-2287): best alignment of each end, MAPQ 1
         int best_c[2] = {-1, -1}; int32_t best_score[2] = {0, 0};
+#pragma unroll 1
         for (uint32_t u = 0; u < n_unpaired; u++) {
             const uint32_t c = unpaired[u]; const uint32_t r = cl.read[c];
             bool beats = cl.score[c] > best_score[r];
             if (!beats && cl.score[c] == best_score[r]) beats = (rng_next(rng) % 2) != 0;
             if (beats) { best_c[r] = (int)c; best_score[r] = cl.score[c]; }
         }
+#pragma unroll 1
         for (uint32_t r = 0; r < 2; r++) {
             out[r].mapq = 1;
             if (best_c[r] >= 0) {
@@ -662,13 +712,17 @@ __device__ inline uint32_t finalize_pe(const DevIndex& ix, const MapParamsDev& P
 
     // winner (:2505-2598)
     uint8_t po[MAX_PAIRS];
+#pragma unroll 1
     for (uint32_t p = 0; p < n_pairs; p++) { uint32_t j = p; while (j > 0 && pair_score[p] > pair_score[po[j - 1]]) { po[j] = po[j - 1]; j--; } po[j] = (uint8_t)p; }
     {
         uint32_t ties = 0;
+#pragma unroll 1
         while (ties < n_pairs && !(pair_score[po[0]] > pair_score[po[ties]])) ties++;
+#pragma unroll 1
         for (uint32_t i = 1; i < ties; i++) { const uint32_t j = rng_next(rng) % (i + 1); const uint8_t t = po[j]; po[j] = po[i]; po[i] = t; }
     }
     double scores_sorted[MAX_PAIRS];
+#pragma unroll 1
     for (uint32_t p = 0; p < n_pairs; p++) scores_sorted[p] = pair_score[po[p]];
     const uint32_t wp = po[0];
     const double uncapped_mapq = scores_sorted[0] == 0 ? 0.0 : max_mapping_quality(scores_sorted, n_pairs, P.log_base);
@@ -680,6 +734,7 @@ __device__ inline uint32_t finalize_pe(const DevIndex& ix, const MapParamsDev& P
 #pragma unroll 1
     for (uint32_t r = 0; r < 2; r++) caps[r] = faster_cap_warp(P, a.minimizers + rs[r].min_off, ix.k, explored[r], rs[r].min_cnt, qual[r], L[r], ordbuf, cbuf);
     const uint32_t cwin[2] = {pair_c0[wp], pair_c1[wp]};
+#pragma unroll 1
     for (uint32_t r = 0; r < 2; r++) {
         const double escape_bonus = uncapped_mapq < 2147483647.0 ? 1.0 : 2.0;
         const double mapq_cap = fmin(fragment_cluster_cap, (caps[0] + caps[1]) * escape_bonus);
@@ -705,6 +760,7 @@ __device__ inline uint32_t align_read(const DevIndex& ix, const MapParamsDev& P,
                                       gb_alignment& out, gb_mapping* out_maps, uint32_t* out_edits, uint8_t* stmp) {
     DevRng rng = rs.rng;
     bool slot_used[N_SLOTS];
+#pragma unroll 1
     for (uint32_t i = 0; i < N_SLOTS; i++) slot_used[i] = false;
     CandList cl; cl.n = 0;
     uint32_t explored[PRESENT_WORDS];

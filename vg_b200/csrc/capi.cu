@@ -42,9 +42,11 @@ struct ExtendBatch {
     // pools and big_of[item] = i tells the align stage where (ExtView)
     uint32_t* retry_list; uint32_t* retry_count; uint32_t retry_cap;
     const uint32_t* in_list; const uint32_t* in_count; uint32_t* big_of;
+    // items extend_kernel leaves for extend_finish_kernel (anything but one exact full-length extension)
+    uint32_t* post_list; uint32_t* post_count; uint32_t* post_work;
 };
 
-// MINB: resident blocks per SM the register budget is cut for (4: 64 registers, 3: 80, 2: 128); GIRAFFE_B200_EXTEND_MINB picks
+// MINB: resident blocks per SM the register budget is cut for (6: 40 registers, 5: 48, 4: 64, 3: 80, 2: 128); GIRAFFE_B200_EXTEND_MINB picks
 // the instantiation at run time (tuning knob; default 4)
 template <int MINB>
 __global__ void __launch_bounds__(EXTEND_WARPS * 32, MINB)
@@ -82,18 +84,58 @@ extend_kernel(DevIndex ix, ExtendParams p, ExtendBatch b, ExtendWorkspace ws) {
                 sread[i] = c;
             }
             __syncwarp();
-            n = extend_item(ix, p, sread, read_len, b.seeds + sb, n_seeds,
-                            queue, ws.q_cap, arena, ws.a_cap,
-                            b.ext + (size_t)out_slot * p.max_ext,
-                            b.path_pool + (size_t)out_slot * p.path_cap,
-                            b.mism_pool + (size_t)out_slot * p.mism_cap, &status);
+            n = extend_search(ix, p, sread, read_len, b.seeds + sb, n_seeds,
+                              queue, ws.q_cap, arena, ws.a_cap,
+                              b.ext + (size_t)out_slot * p.max_ext,
+                              b.path_pool + (size_t)out_slot * p.path_cap, &status);
         }
+        // everything but a single exact full-length extension goes on to extend_finish_kernel
+        const bool unfinished = status == GB_ITEM_OK && !extend_result_is_final(b.ext + (size_t)out_slot * p.max_ext, n);
         if (lane == 0) {
             if (status == GB_ITEM_OUT_FULL && b.retry_list && read_len <= b.read_cap) {
                 const uint32_t pos = atomicAdd(b.retry_count, 1u);
                 if (pos < b.retry_cap) b.retry_list[pos] = item;
             }
             if (b.big_of) b.big_of[item] = out_slot;
+            b.ext_count[item] = n; b.status[item] = (uint8_t)status;
+            if (unfinished) b.post_list[atomicAdd(b.post_count, 1u)] = item;
+        }
+        __syncwarp();
+    }
+}
+
+// Second half of GaplessExtender::extend (extend.cuh: extend_finish) for the items extend_kernel listed.
+__global__ void __launch_bounds__(EXTEND_WARPS * 32)
+extend_finish_kernel(DevIndex ix, ExtendParams p, ExtendBatch b) {
+    extern __shared__ __align__(16) uint8_t smem[];
+    const int warp_in_block = threadIdx.x >> 5;
+    const int lane = threadIdx.x & 31;
+    uint8_t* sread = smem + (size_t)warp_in_block * b.read_cap;
+    const uint32_t n_listed = *b.post_count;
+    while (true) {
+        uint32_t i = 0;
+        if (lane == 0) i = atomicAdd(b.post_work, 1u);
+        i = __shfl_sync(FULL, i, 0);
+        if (i >= n_listed) break;
+        const uint32_t item = b.post_list[i];
+        const uint32_t out_slot = b.in_list ? b.big_of[item] : item;
+        const uint32_t r = b.items ? b.items[item].read : b.item_read[item];
+        const uint64_t rb = b.read_off[r];
+        const uint32_t read_len = (uint32_t)(b.read_off[r + 1] - rb);
+        for (uint32_t k = lane; k < read_len; k += 32) {
+            uint8_t c = b.reads[rb + k];
+            if (c != 'A' && c != 'C' && c != 'G' && c != 'T') c = 'X';
+            sread[k] = c;
+        }
+        __syncwarp();
+        uint32_t status = GB_ITEM_OK;
+        const uint32_t n = extend_finish(ix, p, sread, b.ext + (size_t)out_slot * p.max_ext, b.ext_count[item],
+                                         b.path_pool + (size_t)out_slot * p.path_cap, b.mism_pool + (size_t)out_slot * p.mism_cap, &status);
+        if (lane == 0) {
+            if (status == GB_ITEM_OUT_FULL && b.retry_list) {
+                const uint32_t pos = atomicAdd(b.retry_count, 1u);
+                if (pos < b.retry_cap) b.retry_list[pos] = item;
+            }
             b.ext_count[item] = n; b.status[item] = (uint8_t)status;
         }
         __syncwarp();
@@ -127,7 +169,7 @@ extern "C" int gb_device_create(const gb_flat_index* ix, int device_ordinal, gb_
         if (v >= 2 && v <= (1ul << 24)) d->map_chunk = (uint32_t)(v & ~1ul);
     }
     if (const char* env = std::getenv("GIRAFFE_B200_TILES")) d->use_tiles = std::atoi(env) != 0;
-    if (const char* env = std::getenv("GIRAFFE_B200_EXTEND_MINB")) { const int v = std::atoi(env); if (v >= 2 && v <= 4) d->extend_minb = v; }
+    if (const char* env = std::getenv("GIRAFFE_B200_EXTEND_MINB")) { const int v = std::atoi(env); if (v >= 2 && v <= 6) d->extend_minb = v; }
     if (const char* env = std::getenv("GIRAFFE_B200_FAST_MINB")) { const int v = std::atoi(env); if (v == 0 || v == 12 || v == 16) d->fast_minb = v; }
     if (const char* env = std::getenv("GIRAFFE_B200_POOL_SCALE")) {
         const double v = std::strtod(env, nullptr);
@@ -228,15 +270,18 @@ extern "C" uint64_t gb_launch_count(const gb_device* d) { return d ? d->launches
 namespace gb {
 
 // Device-resident launch used by both the host-buffer entry point and the mapping pipeline.
-int launch_extend(gb_device* d, const ExtendParams& p, const ExtendBatch& b_in, uint32_t max_read_len) {
+int launch_extend(gb_device* d, const ExtendParams& p, const ExtendBatch& b_in, uint32_t max_read_len, bool mark = false) {
     ExtendBatch b = b_in;
     b.read_cap = (max_read_len + 15u) & ~15u;
     if (b.read_cap == 0) b.read_cap = 16;
     const size_t smem = (size_t)EXTEND_WARPS * b.read_cap;
     if (smem > 200 * 1024) { g_last_error = "read too long for the extension kernel"; return GB_ERR_ARG; }
     const int minb = d->extend_minb;
-    auto kern = minb == 2 ? extend_kernel<2> : (minb == 3 ? extend_kernel<3> : extend_kernel<4>);
-    if (smem > 48 * 1024) GB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    auto kern = minb == 2 ? extend_kernel<2> : (minb == 3 ? extend_kernel<3> : (minb == 5 ? extend_kernel<5> : (minb == 6 ? extend_kernel<6> : extend_kernel<4>)));
+    if (smem > 48 * 1024) {
+        GB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        GB_CUDA(cudaFuncSetAttribute(extend_finish_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    }
     int blocks_per_sm = 0;
     GB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocks_per_sm, kern, EXTEND_WARPS * 32, smem));
     if (blocks_per_sm < 1) blocks_per_sm = 1;
@@ -247,12 +292,24 @@ int launch_extend(gb_device* d, const ExtendParams& p, const ExtendBatch& b_in, 
     int rc;
     if ((rc = d->ws_queue.reserve(n_warps * EXTEND_Q_CAP))) return rc;
     if ((rc = d->ws_arena.reserve(n_warps * EXTEND_A_CAP))) return rc;
+    if ((rc = d->p_post.reserve(b.n_items ? b.n_items : 1))) return rc;
     ExtendWorkspace ws{d->ws_queue.ptr, d->ws_arena.ptr, EXTEND_Q_CAP, EXTEND_A_CAP};
-    b.work_counter = d->work_counter;
-    GB_CUDA(cudaMemsetAsync(d->work_counter, 0, sizeof(uint32_t), d->stream));
+    b.work_counter = d->work_counter; b.post_list = d->p_post.ptr; b.post_count = d->work_counter + 1; b.post_work = d->work_counter + 2;
+    GB_CUDA(cudaMemsetAsync(d->work_counter, 0, 4 * sizeof(uint32_t), d->stream));
     kern<<<grid, EXTEND_WARPS * 32, smem, d->stream>>>(d->ix, p, b, ws);
     d->launches++;
     GB_CUDA(cudaGetLastError());
+    if (mark && (rc = d->kt_mark(b.in_list ? "extend_kernel(large strides)" : "extend_kernel"))) return rc;
+    // post-processing of the items the search left unfinished (its own kernel: the search loop stays instruction-cache resident)
+    int fin_blocks = 0;
+    GB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&fin_blocks, extend_finish_kernel, EXTEND_WARPS * 32, smem));
+    if (fin_blocks < 1) fin_blocks = 1;
+    uint32_t fgrid = (uint32_t)(d->n_sms * fin_blocks);
+    if (fgrid > needed) fgrid = needed ? needed : 1;
+    extend_finish_kernel<<<fgrid, EXTEND_WARPS * 32, smem, d->stream>>>(d->ix, p, b);
+    d->launches++;
+    GB_CUDA(cudaGetLastError());
+    if (mark && (rc = d->kt_mark(b.in_list ? "extend_finish_kernel(large strides)" : "extend_finish_kernel"))) return rc;
     return GB_OK;
 }
 
@@ -261,19 +318,20 @@ int launch_extend_device(gb_device* d, const ExtendParams& p, const uint8_t* rea
                          const DevItem* items, const uint32_t* n_items_dev, uint32_t n_items_max,
                          uint32_t* ext_count, uint8_t* status, gb_extension* ext, uint32_t* path_pool, uint32_t* mism_pool,
                          uint32_t max_read_len, const ExtendBig* big) {
+    const bool mark = big != nullptr;          // the mapping pipeline times its kernels
     ExtendBatch b{};
     b.reads = reads; b.read_off = read_off; b.item_read = item_read; b.seeds = seeds; b.seed_off = seed_off;
     b.n_items = n_items_max; b.items = items; b.n_items_dev = n_items_dev;
     b.ext_count = ext_count; b.status = status; b.ext = ext; b.path_pool = path_pool; b.mism_pool = mism_pool;
     if (big) { b.retry_list = big->list; b.retry_count = big->count; b.retry_cap = big->cap; }
-    int rc = launch_extend(d, p, b, max_read_len);
+    int rc = launch_extend(d, p, b, max_read_len, mark);
     if (rc || !big) return rc;
     // second launch: the listed items with the large strides
     ExtendParams pb = p; pb.max_ext = big->max_ext; pb.path_cap = big->path_cap; pb.mism_cap = big->mism_cap;
     ExtendBatch b2 = b;
     b2.retry_list = nullptr; b2.retry_count = nullptr; b2.in_list = big->list; b2.in_count = big->count; b2.retry_cap = big->cap; b2.big_of = big->big_of;
     b2.ext = big->ext; b2.path_pool = big->path; b2.mism_pool = big->mism;
-    return launch_extend(d, pb, b2, max_read_len);
+    return launch_extend(d, pb, b2, max_read_len, mark);
 }
 
 } // namespace gb

@@ -83,6 +83,7 @@ struct gb_device {
     std::vector<gb_slot_rec> h_slots; std::vector<uint16_t> h_site_dist;      // host copies (fragment-length training)
     gb::DevBuf<gb::QEntry> ws_queue;
     gb::DevBuf<gb::ArenaNode> ws_arena;
+    gb::DevBuf<uint32_t> p_post;                     // items extend_kernel hands to extend_finish_kernel
     uint32_t* work_counter = nullptr;
     float last_kernel_ms = 0.f;
     uint64_t launches = 0;
@@ -133,7 +134,7 @@ struct gb_device {
     gb::DevBuf<gb::TileResult> pl_results;
     gb::DevBuf<uint64_t> pl_stats;
     // per-kernel device times of the last map_device call (events between the launches)
-    static constexpr int KT_MAX = 32;
+    static constexpr int KT_MAX = 48;
     cudaEvent_t kt_ev[KT_MAX] = {}; const char* kt_name[KT_MAX] = {}; int kt_n = 0;
     void kt_reset() { kt_n = 0; }
     int kt_mark(const char* name) {
@@ -148,7 +149,7 @@ struct gb_device {
     uint32_t map_chunk = 1u << 20;         // reads per chunk; GIRAFFE_B200_MAP_CHUNK overrides
     void release_all() {
         nodes.release(); seq.release(); gbwt.release(); dist.release(); table.release(); hits.release(); slot_order.release(); slots.release(); site_dist.release();
-        ws_queue.release(); ws_arena.release();
+        ws_queue.release(); ws_arena.release(); p_post.release();
         t_hit.release(); t_plo.release(); t_phred.release(); p_states.release(); p_min.release(); p_seeds.release();
         p_items.release(); p_ext_seeds.release(); p_cursors.release(); p_ext_count.release(); p_path.release(); p_mism.release();
         p_ext_status.release(); p_ext.release(); p_big_list.release(); p_big_of.release(); p_big_path.release(); p_big_mism.release(); p_big_ext.release(); ws_tail.release(); ws_cand.release(); ws_rescue.release(); w_reads.release(); w_quals.release(); p_pairs.release(); p_slow.release(); p_rescue.release(); p_retry.release();

@@ -374,16 +374,22 @@ __device__ inline bool trim_mismatches(const DevIndex& ix, gb_extension& e, cons
 }
 
 // --------------------------------------------------------------------------------------
-// extend_item: the whole of GaplessExtender::extend for one work item, executed by one warp.
+// GaplessExtender::extend for one work item, executed by one warp, in two parts so that the kernels of the mapping
+// pipeline keep the search loop and the post-processing in separate (instruction-cache sized) kernels:
+//   extend_search  gbwt_extender.cpp:540-700  best-first search per seed; writes one raw record per seed that produced
+//                  an extension (path in path_pool, `mismatches` = mismatch count of the search, no mismatch list yet)
+//   extend_finish  gbwt_extender.cpp:702-736  full-length selection with the overlap filter, or duplicate removal +
+//                  mismatch lists + trimming, on those records
+// extend_item runs both (rescue, which extends inside the align kernel).
 // `ext`, `path_pool`, `mism_pool` point at this item's output regions (capacities in p).
 // Returns the number of extensions; *status receives a GB_ITEM_* code.
 // --------------------------------------------------------------------------------------
-__device__ inline uint32_t extend_item(const DevIndex& ix, const ExtendParams& p,
-                                       const uint8_t* sread, uint32_t read_len,
-                                       const gb_seed* seeds, uint32_t n_seeds,
-                                       QEntry* queue, uint32_t q_cap, ArenaNode* arena, uint32_t a_cap,
-                                       gb_extension* ext, uint32_t* path_pool, uint32_t* mism_pool,
-                                       uint32_t* status_out) {
+__device__ inline uint32_t extend_search(const DevIndex& ix, const ExtendParams& p,
+                                         const uint8_t* sread, uint32_t read_len,
+                                         const gb_seed* seeds, uint32_t n_seeds,
+                                         QEntry* queue, uint32_t q_cap, ArenaNode* arena, uint32_t a_cap,
+                                         gb_extension* ext, uint32_t* path_pool,
+                                         uint32_t* status_out) {
     const int lane = lane_id();
     uint32_t status = GB_ITEM_OK;
     uint32_t n_res = 0, path_used = 0;
@@ -583,7 +589,29 @@ __device__ inline uint32_t extend_item(const DevIndex& ix, const ExtendParams& p
         }
     }
 
-    if (status != GB_ITEM_OK) { *status_out = status; return 0; }
+    __syncwarp();
+    *status_out = status;
+    return status == GB_ITEM_OK ? n_res : 0;
+}
+
+// A raw record set that extend_finish would leave unchanged: one exact full-length extension.
+__device__ __forceinline__ bool extend_result_is_final(const gb_extension* ext, uint32_t n_res) {
+    if (n_res == 0) return true;
+    if (n_res != 1) return false;
+    return (ext[0].flags & 3u) == 3u && ext[0].mismatches == 0;
+}
+
+__device__ inline uint32_t extend_finish(const DevIndex& ix, const ExtendParams& p, const uint8_t* sread,
+                                         gb_extension* ext, uint32_t n_res, uint32_t* path_pool, uint32_t* mism_pool,
+                                         uint32_t* status_out) {
+    const int lane = lane_id();
+    uint32_t status = GB_ITEM_OK;
+    // the best full-length alignment of the search (gbwt_extender.cpp:696-699): fewest mismatches among the full-length records
+    uint32_t best_alignment = NONE, best_alignment_mm = 0;
+    for (uint32_t i = 0; i < n_res; i++) {
+        const uint32_t fl = ext[i].flags, mmc = ext[i].mismatches;
+        if ((fl & 3u) == 3u && (best_alignment == NONE || mmc < best_alignment_mm)) { best_alignment = i; best_alignment_mm = mmc; }
+    }
     __syncwarp();
 
     uint32_t mism_used = 0;
@@ -651,6 +679,18 @@ __device__ inline uint32_t extend_item(const DevIndex& ix, const ExtendParams& p
     __syncwarp();
     *status_out = status;
     return status == GB_ITEM_OK ? n_res : 0;
+}
+
+__device__ inline uint32_t extend_item(const DevIndex& ix, const ExtendParams& p,
+                                       const uint8_t* sread, uint32_t read_len,
+                                       const gb_seed* seeds, uint32_t n_seeds,
+                                       QEntry* queue, uint32_t q_cap, ArenaNode* arena, uint32_t a_cap,
+                                       gb_extension* ext, uint32_t* path_pool, uint32_t* mism_pool,
+                                       uint32_t* status_out) {
+    const uint32_t n = extend_search(ix, p, sread, read_len, seeds, n_seeds, queue, q_cap, arena, a_cap, ext, path_pool, status_out);
+    if (*status_out != GB_ITEM_OK || extend_result_is_final(ext, n)) return n;
+    __syncwarp();
+    return extend_finish(ix, p, sread, ext, n, path_pool, mism_pool, status_out);
 }
 
 } // namespace gb

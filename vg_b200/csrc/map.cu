@@ -369,7 +369,6 @@ int map_device(gb_device* d, const gb_map_params* hp, uint32_t n_reads, const ui
         if ((rc = launch_extend_device(d, ep, d_reads, d_read_off, nullptr, d->p_ext_seeds.ptr, nullptr, d->p_items.ptr, cur + 3,
                                        (uint32_t)item_cap, d->p_ext_count.ptr, d->p_ext_status.ptr, d->p_ext.ptr, d->p_path.ptr,
                                        d->p_mism.ptr, Lc, &big))) return rc;
-        if ((rc = d->kt_mark("extend_kernel"))) return rc;
     }
     GB_CUDA(cudaEventRecord(d->ev_stage[2], d->stream));
     // ---- K3 ----
@@ -404,7 +403,7 @@ int map_device(gb_device* d, const gb_map_params* hp, uint32_t n_reads, const ui
         if ((rc = d->ws_tail.reserve(ws_stride * n_warps))) return rc;
         if ((rc = d->ws_cand.reserve(cand_stride * n_warps))) return rc;
         AlignArgs a;
-        a.plan.entries = nullptr; a.plan.unit_base = nullptr; a.plan.unit_count = nullptr; a.plan.tile_off = nullptr; a.plan.results = nullptr; a.plan.path_pool = nullptr;
+        a.plan.entries = nullptr; a.plan.unit_base = nullptr; a.plan.unit_count = nullptr; a.plan.tile_off = nullptr; a.plan.results = nullptr; a.plan.path_pool = nullptr; a.plan.stats = nullptr;
         a.rescue_base = nullptr; a.rescue_stride = 0; a.tmp_bytes = tmp_bytes;
         if (rescue) {
             a.rescue_stride = (rescue_ws_bytes(Lc) + 255) & ~(size_t)255;
@@ -471,7 +470,7 @@ int map_device(gb_device* d, const gb_map_params* hp, uint32_t n_reads, const ui
             if ((rc = launch_tile_kernels(d, d->pl_tiles.ptr, d->pl_tile_off.ptr, d->pl_lists.ptr + (size_t)TILE_CLASSES * tile_cap, tile_cap, cur + 18 + TILE_CLASSES,
                                           cur + 32 + TILE_CLASSES, d->pl_results.ptr, d->pl_paths.ptr, (uint32_t)path_cap, cur + 30))) return rc;
             a.plan.entries = d->pl_entries.ptr; a.plan.unit_base = d->pl_unit_base.ptr; a.plan.unit_count = d->pl_unit_count.ptr;
-            a.plan.tile_off = d->pl_tile_off.ptr; a.plan.results = d->pl_results.ptr; a.plan.path_pool = d->pl_paths.ptr;
+            a.plan.tile_off = d->pl_tile_off.ptr; a.plan.results = d->pl_results.ptr; a.plan.path_pool = d->pl_paths.ptr; a.plan.stats = d->pl_stats.ptr;
         }
         if (paired) {
             // the plain kernel takes every listed pair; with rescue enabled it defers the pairs that turn out to have
@@ -797,7 +796,8 @@ extern "C" int gb_stage_times(gb_device* d, float* ms4) {
     return GB_OK;
 }
 
-// Counters of the tail plan of the last mapping call (its last chunk): tails planned, trees, (unused), DP cells of the tiles.
+// Counters of the tail plan of the last mapping call (its last chunk): tails planned, trees, tails aligned in place by the
+// align kernels although the unit had a plan (not planned, cancelled, or not tileable), DP cells of the tiles.
 extern "C" int gb_plan_stats(gb_device* d, uint64_t* out4) {
     if (!d || !out4) return GB_ERR_ARG;
     for (int i = 0; i < 4; i++) out4[i] = 0;

@@ -8,11 +8,14 @@ __global__ void prep_pairs_kernel(const uint8_t* reads, const uint8_t* quals, co
                                   uint8_t* w_reads, uint8_t* w_quals) {
     const uint32_t warps_per_block = blockDim.x >> 5;
     const uint32_t lane = threadIdx.x & 31;
+#pragma unroll 1
     for (uint32_t r = blockIdx.x * warps_per_block + (threadIdx.x >> 5); r < n_reads; r += gridDim.x * warps_per_block) {
         const uint64_t b = read_off[r]; const uint32_t L = (uint32_t)(read_off[r + 1] - b);
         if ((r & 1u) == 0) {
+#pragma unroll 1
             for (uint32_t i = lane; i < L; i += 32) { w_reads[b + i] = reads[b + i]; if (quals) w_quals[b + i] = quals[b + i]; }
         } else {
+#pragma unroll 1
             for (uint32_t i = lane; i < L; i += 32) {
                 w_reads[b + i] = comp_base(reads[b + L - 1 - i]);
                 if (quals) w_quals[b + i] = quals[b + L - 1 - i];
@@ -42,6 +45,7 @@ seed_kernel_pe(DevIndex ix, MapParamsDev P, MapBatch b, SeedPools pools, PairBat
     const SeedSmem sm = carve_seed_smem(smem + (size_t)warp * seed_smem_bytes(lay_L, lay_M, lay_C), lay_L, lay_M, lay_C, b.Ns);
     const uint32_t n_pairs = b.n_reads / 2;
     const uint32_t limit = b.in_list ? min(*b.in_count, n_pairs) : n_pairs;
+#pragma unroll 1
     while (true) {
         __syncthreads();
         if (threadIdx.x == 0) s_base = atomicAdd(b.work_counter, blockDim.x >> 5);
@@ -56,6 +60,7 @@ seed_kernel_pe(DevIndex ix, MapParamsDev P, MapBatch b, SeedPools pools, PairBat
         uint32_t status = GB_ITEM_OK;
         uint32_t L[2] = {0, 0};
         if (active) {
+#pragma unroll 1
             for (uint32_t r = 0; r < 2; r++) L[r] = (uint32_t)(b.read_off[2 * p + r + 1] - b.read_off[2 * p + r]);
             if (L[0] > b.Lc || L[1] > b.Lc) status = GB_ITEM_OUT_FULL;
         }
@@ -63,8 +68,10 @@ seed_kernel_pe(DevIndex ix, MapParamsDev P, MapBatch b, SeedPools pools, PairBat
         // LazyRNG seed: aln1.sequence() + aln2.sequence() with mate 2 already rightward (:1529-1531)
         DevRng rng; rng.inited = 0; rng.state = 0; rng.seed = 0;
         if (work) {
+#pragma unroll 1
             for (uint32_t r = 0; r < 2; r++) {
                 const uint64_t rb = b.read_off[2 * p + r];
+#pragma unroll 1
                 for (uint32_t i = lane; i < L[r]; i += 32) sm.read[i] = b.reads[rb + i];
                 __syncwarp();
                 rng.seed = fold_seed(rng.seed, sm.read, L[r]);
@@ -76,6 +83,7 @@ seed_kernel_pe(DevIndex ix, MapParamsDev P, MapBatch b, SeedPools pools, PairBat
             __syncthreads();
             if (work && status == GB_ITEM_OK) {
                 const uint64_t rb = b.read_off[2 * p + r];
+#pragma unroll 1
                 for (uint32_t i = lane; i < L[r]; i += 32) sm.read[i] = b.reads[rb + i];
                 __syncwarp();
                 ReadState cur;
@@ -125,6 +133,7 @@ align_kernel_pe(DevIndex ix, MapParamsDev P, DevScores sc, MapBatch b, AlignArgs
     uint8_t* cand_base = a.cand_base + (size_t)gwarp * a.cand_stride;
     const uint32_t n_pairs = b.n_reads / 2;
 
+#pragma unroll 1
     while (true) {
         uint32_t p = 0;
         if (lane == 0) {
@@ -140,6 +149,7 @@ align_kernel_pe(DevIndex ix, MapParamsDev P, DevScores sc, MapBatch b, AlignArgs
         memset(&out[0], 0, sizeof(gb_alignment)); memset(&out[1], 0, sizeof(gb_alignment));
         uint32_t L[2];
         gb_mapping* out_maps[2]; uint32_t* out_edits[2];
+#pragma unroll 1
         for (uint32_t r = 0; r < 2; r++) {
             const uint32_t ri = 2 * p + r;
             L[r] = (uint32_t)(b.read_off[ri + 1] - b.read_off[ri]);
@@ -147,13 +157,16 @@ align_kernel_pe(DevIndex ix, MapParamsDev P, DevScores sc, MapBatch b, AlignArgs
             out[r].read_id = ri; out[r].flags = GB_ALN_PAIRED;
         }
         if (status == GB_ITEM_OK) {
+#pragma unroll 1
             for (uint32_t r = 0; r < 2; r++) {
                 const uint64_t rb = b.read_off[2 * p + r];
+#pragma unroll 1
                 for (uint32_t i = lane; i < L[r]; i += 32) { sread[r][i] = b.reads[rb + i]; if (b.quals) squal[r][i] = b.quals[rb + i]; }
             }
             __syncwarp();
             DevRng rng = rs[0].rng;
             bool slot_used[N_SLOTS];
+#pragma unroll 1
             for (uint32_t i = 0; i < N_SLOTS; i++) slot_used[i] = false;
             CandList cl; cl.n = 0;
             uint32_t explored[2][PRESENT_WORDS];
@@ -176,6 +189,7 @@ align_kernel_pe(DevIndex ix, MapParamsDev P, DevScores sc, MapBatch b, AlignArgs
             __syncwarp();
             continue;
         }
+#pragma unroll 1
         for (uint32_t r = 0; r < 2; r++) {
             const uint32_t ri = 2 * p + r;
             out[r].mapping_off = ri * P.mapping_cap; out[r].edit_off = ri * P.edit_cap;

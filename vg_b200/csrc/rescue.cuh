@@ -85,7 +85,9 @@ __device__ __forceinline__ bool rescue_slot_less(const DevIndex& ix, uint32_t a,
 __device__ inline int32_t rescue_rescore(const DevScores& sc, const PathBuf& pb) {
     int32_t score = 0; bool last_was_deletion = false;
     uint32_t e = 0;
+#pragma unroll 1
     for (uint32_t i = 0; i < pb.n_maps; i++) {
+#pragma unroll 1
         for (uint32_t j = 0; j < pb.maps[i].n_edits; j++, e++) {
             const uint32_t wd = pb.edits[e], op = wd & 3u, len = wd >> 4;
             if (op == GB_EDIT_MATCH) { score += sc.match * (int32_t)len; last_was_deletion = false; }
@@ -111,7 +113,9 @@ __device__ inline int32_t rescue_rescore(const DevScores& sc, const PathBuf& pb)
 __device__ inline void rescue_fix_end_deletions(PathBuf& pb) {
     // leading mappings / edits that consume no read
     uint32_t i = 0, j = 0, e = 0;
+#pragma unroll 1
     for (; i < pb.n_maps; i++) {
+#pragma unroll 1
         for (j = 0; j < pb.maps[i].n_edits; j++) { const uint32_t wd = pb.edits[e + j]; if ((wd & 3u) != GB_EDIT_DEL && (wd >> 4) != 0) break; }
         if (j != pb.maps[i].n_edits) break;
         e += pb.maps[i].n_edits;
@@ -119,17 +123,22 @@ __device__ inline void rescue_fix_end_deletions(PathBuf& pb) {
     if (i == pb.n_maps) { pb.n_maps = 0; pb.n_edits = 0; return; }
     if (i != 0 || j != 0) {
         uint32_t removed = 0;
+#pragma unroll 1
         for (uint32_t k = 0; k < j; k++) removed += pb.edits[e + k] >> 4;          // deletions: from_length
         const uint32_t drop_edits = e + j;
+#pragma unroll 1
         for (uint32_t x = drop_edits; x < pb.n_edits; x++) pb.edits[x - drop_edits] = pb.edits[x];
         pb.n_edits -= drop_edits;
         gb_mapping first = pb.maps[i]; first.n_edits = (uint16_t)(first.n_edits - j); first.offset = (uint16_t)(first.offset + removed);
+#pragma unroll 1
         for (uint32_t x = i; x < pb.n_maps; x++) pb.maps[x - i] = pb.maps[x];
         pb.n_maps -= i; pb.maps[0] = first;
     }
     // trailing deletions
+#pragma unroll 1
     while (pb.n_maps > 0) {
         gb_mapping& m = pb.maps[pb.n_maps - 1];
+#pragma unroll 1
         while (m.n_edits > 0 && (pb.edits[pb.n_edits - 1] & 3u) == GB_EDIT_DEL) { m.n_edits--; pb.n_edits--; }
         if (m.n_edits == 0) pb.n_maps--; else break;
     }
@@ -138,6 +147,7 @@ __device__ inline void rescue_fix_end_deletions(PathBuf& pb) {
 // position of oriented node v in the rescue DAG (forward half in chain order, mirrored half after it)
 __device__ inline uint32_t rescue_index_of(const RescueWs& rw, uint32_t n_ids, uint32_t v) {
     const uint32_t id = v >> 1;
+#pragma unroll 1
     for (uint32_t x = 0; x < n_ids; x++) if (rw.ids[x] == id) return (v & 1u) ? 2 * n_ids - 1 - x : x;
     return 0xffffffffu;
 }
@@ -159,11 +169,13 @@ __device__ inline int32_t attempt_rescue(const DevIndex& ix, const MapParamsDev&
     else {
         const gb_mapping last = anchor.maps[anchor_nm - 1];
         uint32_t used = 0;
+#pragma unroll 1
         for (uint32_t x = anchor_ne - last.n_edits; x < anchor_ne; x++) { const uint32_t wd = anchor.edits[x]; const uint32_t op = wd & 3u; if (op != GB_EDIT_INS) used += (op == GB_EDIT_SUB) ? 1u : (wd >> 4); }
         start_node = last.node ^ 1u; to_end = (int64_t)(last.offset + used) + 1;
     }
     // ---- subgraph ids in chain order ---------------------------------------------------------------------
     uint32_t n_ids = 0;
+#pragma unroll 1
     for (uint32_t base = 0; base < ix.n_ids; base += 32) {
         const uint32_t x = base + lane;
         uint32_t id = 0; bool in = false;
@@ -177,10 +189,12 @@ __device__ inline int32_t attempt_rescue(const DevIndex& ix, const MapParamsDev&
     if (n_ids == 0) return 0;
     // ---- seeds_in_subgraph: distinct (handle, read offset - node offset) of the hits on subgraph nodes -------
     uint32_t n_raw = 0; bool raw_full = false;
+#pragma unroll 1
     for (uint32_t mi = 0; mi < M && !raw_full; mi++) {
         const DevMinimizer dm = mins[mi];
         const uint32_t hoff = dm.pad[0], hits = dm.pad[1];
         const int32_t pin = (int32_t)dm.fwd_offset + (dm.is_reverse ? (int32_t)ix.k - 1 : 0);
+#pragma unroll 1
         for (uint32_t hb = 0; hb < hits; hb += 32) {
             const uint32_t j = hb + lane;
             bool in = false; unsigned long long key = 0;
@@ -205,16 +219,19 @@ __device__ inline int32_t attempt_rescue(const DevIndex& ix, const MapParamsDev&
     if (lane == 0) {
         // sorted distinct keys (ascending node, diagonal)
         unsigned long long* keys = rw.raw;       // in-place insertion: distinct prefix grows from the front
+#pragma unroll 1
         for (uint32_t x = 0; x < n_raw; x++) {
             const unsigned long long key = keys[x];
             uint32_t lo = 0; while (lo < n_seeds && keys[lo] < key) lo++;
             if (lo < n_seeds && keys[lo] == key) continue;
             if (n_seeds > P.rescue_seed_limit) { n_seeds = P.rescue_seed_limit + 1; break; }
+#pragma unroll 1
             for (uint32_t y = n_seeds; y > lo; y--) keys[y] = keys[y - 1];
             keys[lo] = key; n_seeds++;
             if (n_seeds > P.rescue_seed_limit) break;
         }
         if (n_seeds <= P.rescue_seed_limit && n_seeds <= RESCUE_SEEDS)
+#pragma unroll 1
             for (uint32_t x = 0; x < n_seeds; x++) { gb_seed g; g.node = (uint32_t)(keys[x] >> 32); g.diag = (int32_t)((uint32_t)keys[x] ^ 0x80000000u); rw.seeds[x] = g; }
     }
     n_seeds = __shfl_sync(FULL, n_seeds, 0);
@@ -222,6 +239,7 @@ __device__ inline int32_t attempt_rescue(const DevIndex& ix, const MapParamsDev&
     if (n_seeds > P.rescue_seed_limit) return 0;
     if (n_seeds > RESCUE_SEEDS) { status = GB_ITEM_OUT_FULL; return 0; }
     // ---- gapless extension of the seeds (masked read in the query buffer) -------------------------------------
+#pragma unroll 1
     for (uint32_t i = lane; i < L; i += 32) { const uint8_t c = sread[i]; qbuf[i] = is_acgt(c) ? c : (uint8_t)'X'; }
     __syncwarp();
     ExtendParams ep; ep.sc = sc; ep.max_mismatches = 4; ep.overlap_threshold = 0.8; ep.overlap_threshold_unused = 0.f; ep.trim = 1;
@@ -239,16 +257,19 @@ __device__ inline int32_t attempt_rescue(const DevIndex& ix, const MapParamsDev&
         return rw.ext[0].score;
     }
     uint32_t best = n_ext;
+#pragma unroll 1
     for (uint32_t i = 0; i < n_ext; i++) if (best >= n_ext || rw.ext[i].score > rw.ext[best].score) best = i;
     // the best extension's nodes join the subgraph (:3347-3349)
     if (best < n_ext) {
         if (lane == 0) {
             const gb_extension e = rw.ext[best];
+#pragma unroll 1
             for (uint32_t x = 0; x < e.path_len; x++) {
                 const uint32_t id = rw.path_pool[e.path_off + x] >> 1;
                 uint32_t lo = 0; while (lo < n_ids && rescue_slot_less(ix, rw.ids[lo], id)) lo++;
                 if (lo < n_ids && rw.ids[lo] == id) continue;
                 if (n_ids >= RESCUE_IDS) { n_ids = RESCUE_IDS + 1; break; }
+#pragma unroll 1
                 for (uint32_t y = n_ids; y > lo; y--) rw.ids[y] = rw.ids[y - 1];
                 rw.ids[lo] = id; n_ids++;
             }
@@ -260,15 +281,18 @@ __device__ inline int32_t attempt_rescue(const DevIndex& ix, const MapParamsDev&
     // ---- the DAG: both orientations in chain order, edges among them ---------------------------------------------
     const uint32_t N = 2 * n_ids;
     uint32_t bases = 0;
+#pragma unroll 1
     for (uint32_t x = lane; x < n_ids; x += 32) { const uint32_t id = rw.ids[x]; rw.nodes[x] = 2 * id; rw.nodes[N - 1 - x] = 2 * id + 1; bases += 2 * load_node(ix, 2 * id).len; }
     bases = (uint32_t)warp_sum((int)bases);
     __syncwarp();
     if ((uint64_t)bases * L > P.max_dozeu_cells) return 0;                     // :3371-3381
     if (bases > RESCUE_BASES || L > Lc) { status = GB_ITEM_OUT_FULL; return 0; }
     // edges i -> j (j > i), collected per source, then CSR by target and by source (lists ascending, distinct)
+#pragma unroll 1
     for (uint32_t x = lane; x <= N; x += 32) rw.cnt[x] = 0;
     __syncwarp();
     uint32_t n_edges = 0; bool deg_full = false;
+#pragma unroll 1
     for (uint32_t ib = 0; ib < N; ib += 32) {
         const uint32_t i = ib + lane;
         uint32_t tgt[RESCUE_DEG]; uint32_t nt = 0;
@@ -277,12 +301,14 @@ __device__ inline int32_t attempt_rescue(const DevIndex& ix, const MapParamsDev&
             if (nr.size != 0) {
                 const uint32_t* rec = ix.gbwt + nr.rec_off;
                 const uint32_t ne = __ldg(rec);
+#pragma unroll 1
                 for (uint32_t e = 0; e < ne; e++) {
                     const uint32_t to = __ldg(rec + 2 + 2 * e);
                     if (to == 0) continue;
                     const uint32_t j = rescue_index_of(rw, n_ids, to);
                     if (j == 0xffffffffu || j <= i) continue;
                     bool dup = false;
+#pragma unroll 1
                     for (uint32_t y = 0; y < nt; y++) dup |= tgt[y] == j;
                     if (dup) continue;
                     if (nt >= RESCUE_DEG) { deg_full = true; break; }
@@ -293,6 +319,7 @@ __device__ inline int32_t attempt_rescue(const DevIndex& ix, const MapParamsDev&
         // this chunk's edges, in source order
         const uint32_t incl = (uint32_t)warp_incl_scan((int)nt);
         const uint32_t basee = n_edges + incl - nt;
+#pragma unroll 1
         for (uint32_t y = 0; y < nt; y++) { rw.esrc[basee + y] = i; rw.edst[basee + y] = tgt[y]; }
         n_edges += __shfl_sync(FULL, incl, 31);
     }
@@ -300,18 +327,27 @@ __device__ inline int32_t attempt_rescue(const DevIndex& ix, const MapParamsDev&
     if (__any_sync(FULL, deg_full)) { status = GB_ITEM_OUT_FULL; return 0; }
     if (lane == 0) {
         // CSR by target (sources ascending because edges are in source order), then by source (targets sorted)
+#pragma unroll 1
         for (uint32_t x = 0; x <= N; x++) rw.cnt[x] = 0;
+#pragma unroll 1
         for (uint32_t x = 0; x < n_edges; x++) rw.cnt[rw.edst[x] + 1]++;
         rw.pred_off[0] = 0; for (uint32_t x = 0; x < N; x++) rw.pred_off[x + 1] = rw.pred_off[x] + rw.cnt[x + 1];
+#pragma unroll 1
         for (uint32_t x = 0; x <= N; x++) rw.cnt[x] = 0;
+#pragma unroll 1
         for (uint32_t x = 0; x < n_edges; x++) { const uint32_t d = rw.edst[x]; rw.pred[rw.pred_off[d] + rw.cnt[d]++] = rw.esrc[x]; }
+#pragma unroll 1
         for (uint32_t x = 0; x <= N; x++) rw.cnt[x] = 0;
+#pragma unroll 1
         for (uint32_t x = 0; x < n_edges; x++) rw.cnt[rw.esrc[x] + 1]++;
         rw.succ_off[0] = 0; for (uint32_t x = 0; x < N; x++) rw.succ_off[x + 1] = rw.succ_off[x] + rw.cnt[x + 1];
+#pragma unroll 1
         for (uint32_t x = 0; x <= N; x++) rw.cnt[x] = 0;
+#pragma unroll 1
         for (uint32_t x = 0; x < n_edges; x++) {
             const uint32_t s = rw.esrc[x], d = rw.edst[x];
             uint32_t pos = rw.cnt[s]++; const uint64_t b0 = rw.succ_off[s];
+#pragma unroll 1
             while (pos > 0 && rw.succ[b0 + pos - 1] > d) { rw.succ[b0 + pos] = rw.succ[b0 + pos - 1]; pos--; }
             rw.succ[b0 + pos] = d;
         }
@@ -360,6 +396,7 @@ __device__ inline int32_t attempt_rescue(const DevIndex& ix, const MapParamsDev&
 __device__ inline double max_mapping_quality_mult(const double* scores, uint32_t n, double log_base, const double* mult) {
     const double quality_scale_factor = 10.0 / log(10.0);
     double log_sum_exp = -DBL_MAX, to_score = -DBL_MAX;
+#pragma unroll 1
     for (int64_t i = (int64_t)n - 1; i >= 0; --i) {
         double score = log_base * scores[i];
         if (score >= to_score) to_score = score;
@@ -387,6 +424,7 @@ __device__ inline uint32_t finalize_pe_rescue(const DevIndex& ix, const MapParam
                                               gb_alignment* out /*[2]*/, gb_mapping* const* out_maps, uint32_t* const* out_edits) {
     const int lane = lane_id();
     const uint32_t map_cap = P.mapping_cap, edit_cap = P.edit_cap;
+#pragma unroll 1
     for (uint32_t r = 0; r < 2; r++) {
         out[r].read_id = read_idx0 + r; out[r].score = 0; out[r].mapq = 0; out[r].flags = GB_ALN_PAIRED; out[r].n_mappings = 0; out[r].n_edits = 0;
         out[r].mapq_uncapped = 0.f; out[r].mapq_explored_cap = 0.f;
@@ -400,6 +438,7 @@ __device__ inline uint32_t finalize_pe_rescue(const DevIndex& ix, const MapParam
     uint32_t unpaired_count[2] = {0, 0}, rescued_count[2] = {0, 0};
     uint32_t status = GB_ITEM_OK;
     int32_t best_alignment_scores[2] = {0, 0};
+#pragma unroll 1
     for (uint32_t c = 0; c < cl.n; c++) best_alignment_scores[cl.read[c]] = max(best_alignment_scores[cl.read[c]], cl.score[c]);
     // distance_between(first mate's alignment c0, second mate's alignment c1) (:3895-3903)
     auto distance_between = [&](uint32_t c0, uint32_t c1) -> int64_t {
@@ -409,6 +448,7 @@ __device__ inline uint32_t finalize_pe_rescue(const DevIndex& ix, const MapParam
         const uint32_t nm1 = slot_nm(p1), ne1 = slot_ne(p1);
         const gb_mapping last = p1.maps[nm1 - 1];
         uint32_t used = 0;
+#pragma unroll 1
         for (uint32_t x = ne1 - last.n_edits; x < ne1; x++) { const uint32_t wd = p1.edits[x]; const uint32_t op = wd & 3u; if (op != GB_EDIT_INS) used += (op == GB_EDIT_SUB) ? 1u : (wd >> 4); }
         return oriented_distance(ix, first.node, first.offset, last.node, (uint32_t)last.offset + used);
     };
@@ -417,13 +457,17 @@ __device__ inline uint32_t finalize_pe_rescue(const DevIndex& ix, const MapParam
         const double ll = (-dev * dev / (2.0 * a.frag_sd * a.frag_sd)) / P.log_base;
         return fmax((double)s0 + (double)s1 + ll, fmin((double)s0, (double)s1));
     };
+#pragma unroll 1
     for (uint32_t f = 0; f + 1 < n_frag_slots && status == GB_ITEM_OK; f++) {
         bool has0 = false, has1 = false;
+#pragma unroll 1
         for (uint32_t c = 0; c < cl.n; c++) if (cl.frag[c] == f) { if (cl.read[c] == 0) has0 = true; else has1 = true; }
         if (has0 && has1) {
             found_pair = true;
+#pragma unroll 1
             for (uint32_t c0 = 0; c0 < cl.n && status == GB_ITEM_OK; c0++) {
                 if (cl.frag[c0] != f || cl.read[c0] != 0) continue;
+#pragma unroll 1
                 for (uint32_t c1 = 0; c1 < cl.n; c1++) {
                     if (cl.frag[c1] != f || cl.read[c1] != 1) continue;
                     if (n_pairs >= RESCUE_MAX_PAIRS) { status = GB_ITEM_OUT_FULL; break; }
@@ -434,6 +478,7 @@ __device__ inline uint32_t finalize_pe_rescue(const DevIndex& ix, const MapParam
                 }
             }
         } else {
+#pragma unroll 1
             for (uint32_t r = 0; r < 2; r++) for (uint32_t c = 0; c < cl.n; c++) if (cl.frag[c] == f && cl.read[c] == r) { unpaired[n_unpaired++] = (uint8_t)c; unpaired_count[r]++; }
         }
     }
@@ -443,6 +488,7 @@ __device__ inline uint32_t finalize_pe_rescue(const DevIndex& ix, const MapParam
     if (n_unpaired > 0) {
         if (!found_pair) {
             int best_c[2] = {-1, -1}; int32_t best_score[2] = {0, 0};
+#pragma unroll 1
             for (uint32_t u = 0; u < n_unpaired; u++) {
                 const uint32_t c = unpaired[u]; const uint32_t r = cl.read[c];
                 unpaired_scores[r][n_unpaired_scores[r]++] = (double)cl.score[c];
@@ -459,13 +505,17 @@ __device__ inline uint32_t finalize_pe_rescue(const DevIndex& ix, const MapParam
         }
         // rescue from the unpaired alignments, best first (:2338-2457)
         uint8_t uo[2 * MAX_CANDS];
+#pragma unroll 1
         for (uint32_t u = 0; u < n_unpaired; u++) { uint32_t j = u; while (j > 0 && cl.score[unpaired[u]] > cl.score[unpaired[uo[j - 1]]]) { uo[j] = uo[j - 1]; j--; } uo[j] = (uint8_t)u; }
         {
             uint32_t ties = 0;
+#pragma unroll 1
             while (ties < n_unpaired && !(cl.score[unpaired[uo[0]]] > cl.score[unpaired[uo[ties]]])) ties++;
+#pragma unroll 1
             for (uint32_t i = 1; i < ties; i++) { const uint32_t j = rng_next(rng) % (i + 1); const uint8_t t = uo[j]; uo[j] = uo[i]; uo[i] = t; }
         }
         uint32_t unskipped = 0;
+#pragma unroll 1
         for (uint32_t oi = 0; oi < n_unpaired && status == GB_ITEM_OK; oi++) {
             if (unskipped >= P.max_rescue_attempts) continue;
             unskipped++;
@@ -473,6 +523,7 @@ __device__ inline uint32_t finalize_pe_rescue(const DevIndex& ix, const MapParam
             if (found_pair && (double)cl.score[c] < (double)best_alignment_scores[r] * P.paired_rescue_score_limit) continue;
             if (cl.n >= 2 * MAX_CANDS + 32 || n_pairs >= RESCUE_MAX_PAIRS) { status = GB_ITEM_OUT_FULL; break; }
             uint32_t slot = 0xffffffffu;
+#pragma unroll 1
             for (uint32_t i = 0; i < N_SLOTS; i++) if (!slot_used[i]) { slot_used[i] = true; slot = i; break; }
             if (slot == 0xffffffffu) { status = GB_ITEM_OUT_FULL; break; }
             const PathBuf anchor = slot_buf(cand_base, cl.slot[c], map_cap, edit_cap);
@@ -499,16 +550,21 @@ __device__ inline uint32_t finalize_pe_rescue(const DevIndex& ix, const MapParam
 
     // winner (:2505-2598)
     uint8_t po[RESCUE_MAX_PAIRS];
+#pragma unroll 1
     for (uint32_t p = 0; p < n_pairs; p++) { uint32_t j = p; while (j > 0 && pair_score[p] > pair_score[po[j - 1]]) { po[j] = po[j - 1]; j--; } po[j] = (uint8_t)p; }
     {
         uint32_t ties = 0;
+#pragma unroll 1
         while (ties < n_pairs && !(pair_score[po[0]] > pair_score[po[ties]])) ties++;
+#pragma unroll 1
         for (uint32_t i = 1; i < ties; i++) { const uint32_t j = rng_next(rng) % (i + 1); const uint8_t t = po[j]; po[j] = po[i]; po[i] = t; }
     }
     double scores_sorted[RESCUE_MAX_PAIRS], mult[RESCUE_MAX_PAIRS];
     double est_mult[2];
+#pragma unroll 1
     for (uint32_t r = 0; r < 2; r++) est_mult[r] = unpaired_count[r] > 0 ? (double)unpaired_count[r] / (double)min(rescued_count[r], P.max_rescue_attempts) : 1.0;
     bool all_rescued = true;
+#pragma unroll 1
     for (uint32_t p = 0; p < n_pairs; p++) {
         scores_sorted[p] = pair_score[po[p]];
         const uint8_t t = pair_type[po[p]];
@@ -526,6 +582,7 @@ __device__ inline uint32_t finalize_pe_rescue(const DevIndex& ix, const MapParam
 #pragma unroll 1
     for (uint32_t r = 0; r < 2; r++) caps[r] = faster_cap_warp(P, a.minimizers + rs[r].min_off, ix.k, explored[r], rs[r].min_cnt, qual[r], L[r], ordbuf, cbuf);
     const uint32_t cwin[2] = {pair_c0[wp], pair_c1[wp]};
+#pragma unroll 1
     for (uint32_t r = 0; r < 2; r++) {
         const double escape_bonus = uncapped_mapq < 2147483647.0 ? 1.0 : 2.0;
         double mapq_cap = fmin(fragment_cluster_cap, (caps[0] + caps[1]) * escape_bonus);

@@ -129,9 +129,11 @@ __device__ __forceinline__ bool pool_claim(uint32_t* cursor, uint32_t n, uint32_
 __device__ __forceinline__ void dbg_dump_clusters(const SeedPools& pools, const SeedSmem& sm, uint32_t read_idx, uint32_t cbase, uint32_t Cn,
                                                   const uint8_t* kept, uint32_t n_kept, bool deferred = false) {
     if (!pools.dbg_clusters) return;
+#pragma unroll 1
     for (uint32_t c = lane_id(); c < Cn; c += 32) {
         DbgCluster dc; dc.score = sm.c_score[cbase + c]; dc.coverage = sm.c_cov[cbase + c]; dc.first_seed = sm.c_label[cbase + c];
         dc.fragment = sm.c_frag[cbase + c]; dc.kept_rank = 0xffffffffu; dc.valid = deferred ? 2u : 1u;
+#pragma unroll 1
         for (uint32_t t = 0; t < n_kept; t++) if (kept[t] == c) dc.kept_rank = t;
         pools.dbg_clusters[(size_t)read_idx * MAX_CLUSTERS + c] = dc;
     }
@@ -163,6 +165,7 @@ __device__ __forceinline__ void set_bit_range(uint32_t* words, uint32_t lo, uint
     const uint32_t m0 = 0xffffffffu << (lo & 31), m1 = 0xffffffffu >> (31 - ((hi - 1) & 31));
     if (w0 == w1) { words[w0] |= (m0 & m1); return; }
     words[w0] |= m0;
+#pragma unroll 1
     for (uint32_t w = w0 + 1; w < w1; w++) words[w] = 0xffffffffu;
     words[w1] |= m1;
 }
@@ -172,6 +175,7 @@ __device__ __forceinline__ bool any_bit_in_range(const uint32_t* words, uint32_t
     const uint32_t m0 = 0xffffffffu << (lo & 31), m1 = 0xffffffffu >> (31 - ((hi - 1) & 31));
     if (w0 == w1) return (words[w0] & m0 & m1) != 0;
     if (words[w0] & m0) return true;
+#pragma unroll 1
     for (uint32_t w = w0 + 1; w < w1; w++) if (words[w]) return true;
     return (words[w1] & m1) != 0;
 }
@@ -223,6 +227,7 @@ __device__ __forceinline__ uint32_t seed_phase_a(const DevIndex& ix, const MapPa
         uint64_t* packed = sm.m_key;                                    // [n_blocks + 1]; m_key is filled later
         uint32_t* invalid = reinterpret_cast<uint32_t*>(sm.m_key + 17);  // [n_blocks]  (Mc >= 16: 24 * Mc bytes follow m_key)
         const uint32_t n_blocks = (L + 31) >> 5;
+#pragma unroll 1
         for (uint32_t t = 0; t < n_blocks; t++) {
             const uint32_t pos = t * 32 + lane;
             const uint32_t ch = pos < L ? sm.read[pos] : 0u;
@@ -237,6 +242,7 @@ __device__ __forceinline__ uint32_t seed_phase_a(const DevIndex& ix, const MapPa
         }
         if (lane == 0) packed[n_blocks] = 0;
         __syncwarp();
+#pragma unroll 1
         for (uint32_t s = lane; s < nk; s += 32) {
             const uint32_t wd = s >> 5, sh = 2 * (s & 31);
             const uint64_t x = sh ? (packed[wd] << sh) | (packed[wd + 1] >> (64 - sh)) : packed[wd];
@@ -258,6 +264,7 @@ __device__ __forceinline__ uint32_t seed_phase_a(const DevIndex& ix, const MapPa
     uint32_t M = 0;
     {
         const int32_t last_window = (int32_t)(L - window_bp);
+#pragma unroll 1
         for (uint32_t base = 0; base < nk; base += 32) {
             const uint32_t s = base + lane;
             bool is_min = false; int32_t lo = 0, hi = -1;
@@ -289,10 +296,12 @@ __device__ __forceinline__ uint32_t seed_phase_a(const DevIndex& ix, const MapPa
     if (M == 0) return GB_ITEM_OK;
 
     // ---- index lookup + score ----------------------------------------------------------------------
+#pragma unroll 1
     for (uint32_t a = lane; a < M; a += 32) {
         const uint64_t key = sm.m_key[a];
         uint64_t h = gbmin::hash64(key) & ix.table_mask;
         uint32_t off = 0, cnt = 0;
+#pragma unroll 1
         while (true) {
             const uint4 cell = __ldg(reinterpret_cast<const uint4*>(ix.table) + h);
             const uint64_t ckey = ((uint64_t)cell.y << 32) | cell.x;
@@ -306,6 +315,7 @@ __device__ __forceinline__ uint32_t seed_phase_a(const DevIndex& ix, const MapPa
     __syncwarp();
 
     // ---- score order (stable rank sort on (score desc, key asc)) -----------------------------------
+#pragma unroll 1
     for (uint32_t a = lane; a < M; a += 32) {
         const double sa = sm.m_score[a]; const uint64_t ka = sm.m_key[a];
         uint32_t rank = 0;
@@ -375,9 +385,11 @@ __device__ __forceinline__ uint32_t seed_phase_a(const DevIndex& ix, const MapPa
             // lanes in parallel (draw i is 48271^i away from the state), only the swaps themselves stay in order
             {
                 uint8_t* draw_j = tmp_order;                                   // [T] scratch until the runs are laid out below
+#pragma unroll 1
                 for (uint32_t i = 1 + lane; i < T; i += 32) draw_j[i] = (uint8_t)(rng_peek(rng, i) % (i + 1));
                 __syncwarp();
                 if (lane == 0) {
+#pragma unroll 1
                     for (uint32_t i = 1; i < T; i++) {
                         const uint32_t j = draw_j[i];
                         const uint8_t tb = run_begin[j], tl = run_len[j];
@@ -389,6 +401,7 @@ __device__ __forceinline__ uint32_t seed_phase_a(const DevIndex& ix, const MapPa
             }
             __syncwarp();
             uint32_t carry = 0;
+#pragma unroll 1
             for (uint32_t qb = 0; qb < T; qb += 32) {
                 const uint32_t q = qb + lane;
                 const uint32_t len = q < T ? run_len[q] : 0u;
@@ -398,6 +411,7 @@ __device__ __forceinline__ uint32_t seed_phase_a(const DevIndex& ix, const MapPa
                 carry += __shfl_sync(FULL, incl, 31);
             }
             __syncwarp();
+#pragma unroll 1
             for (uint32_t x = lane; x < tied_end; x += 32) sm.m_order[x] = tmp_order[x];
             __syncwarp();
             run_start_words(rsw);                      // runs moved as blocks: new start positions
@@ -417,6 +431,7 @@ __device__ __forceinline__ uint32_t seed_phase_a(const DevIndex& ix, const MapPa
         uint32_t* s_hits = reinterpret_cast<uint32_t*>(sm.khash);           // [M]
         uint32_t* s_runhits = s_hits + M;                                    // [M]  bit 31 = run start
         double* s_score = reinterpret_cast<double*>(sm.kkey);                // [M]
+#pragma unroll 1
         for (uint32_t i = lane; i < M; i += 32) { const uint32_t a = sm.m_order[i]; s_hits[i] = sm.m_hit_cnt[a]; s_score[i] = sm.m_score[a]; }
         __syncwarp();
 #pragma unroll
@@ -459,6 +474,7 @@ __device__ __forceinline__ uint32_t seed_phase_a(const DevIndex& ix, const MapPa
         double base_target_score = 0.0, target_score = 0.0, selected_score = 0.0;
         const bool use_fraction = (P.hit_cap != 0 || P.minimizer_score_fraction != 1.0);
         if (use_fraction) {
+#pragma unroll 1
             for (uint32_t i = 0; i < M; i++) base_target_score += sm.m_score[sm.m_order[i]];
             target_score = (base_target_score * P.minimizer_score_fraction) + 0.000001;
         }
@@ -472,10 +488,12 @@ __device__ __forceinline__ uint32_t seed_phase_a(const DevIndex& ix, const MapPa
         const uint32_t unique_cap = max(P.max_unique_min, num_min_by_read_len);
         const bool track_cov = M > unique_cap;
         if (track_cov) for (uint32_t x = 0; x < cov_words; x++) cov[x] = 0;
+#pragma unroll 1
         for (uint32_t i = 0; i < M; i++) {
             const uint32_t a = sm.m_order[i];
             if (i >= limit) {
                 limit = i + 1; run_hits = sm.m_hit_cnt[a];
+#pragma unroll 1
                 for (uint32_t j = i + 1; j < M && sm.m_key[sm.m_order[j]] == sm.m_key[a]; j++) { limit++; run_hits += sm.m_hit_cnt[sm.m_order[j]]; }
                 taking_run = false;
             }
@@ -513,6 +531,7 @@ __device__ __forceinline__ uint32_t seed_phase_a(const DevIndex& ix, const MapPa
     // ---- minimizer records (score order) -------------------------------------------------------------------
     uint32_t min_off = 0;
     if (!pool_claim(pools.min_cursor, M, pools.min_cap, pools.overflow, min_off)) return GB_ITEM_OUT_FULL;
+#pragma unroll 1
     for (uint32_t i = lane; i < M; i += 32) {
         const uint32_t a = sm.m_order[i];
         DevMinimizer dm; dm.hash = sm.m_hash[a]; dm.score = sm.m_score[a]; dm.fwd_offset = sm.m_fwd[a];
@@ -531,6 +550,7 @@ __device__ __forceinline__ uint32_t seed_phase_a(const DevIndex& ix, const MapPa
         // each seed index finds its minimizer by binary search (seed order = score order, hit order)
         uint32_t* pre = reinterpret_cast<uint32_t*>(sm.khash);             // [M + 1]
         uint32_t carry = 0;
+#pragma unroll 1
         for (uint32_t base = 0; base < M; base += 32) {
             const uint32_t i = base + lane;
             const uint32_t h = (i < M && sm.m_pass[i]) ? sm.m_hit_cnt[sm.m_order[i]] : 0u;
@@ -540,8 +560,10 @@ __device__ __forceinline__ uint32_t seed_phase_a(const DevIndex& ix, const MapPa
         }
         if (lane == 0) pre[M] = carry;
         __syncwarp();
+#pragma unroll 1
         for (uint32_t idx = lane; idx < total_hits; idx += 32) {
             uint32_t lo = 0, hi = M;                                         // last i with pre[i] <= idx
+#pragma unroll 1
             while (hi - lo > 1) { const uint32_t mid = (lo + hi) >> 1; if (pre[mid] <= idx) lo = mid; else hi = mid; }
             const uint32_t i = lo, j = idx - pre[lo];
             const uint32_t a = sm.m_order[i];
@@ -574,8 +596,10 @@ __device__ __forceinline__ uint32_t seed_phase_a(const DevIndex& ix, const MapPa
 __device__ __forceinline__ void propagate_labels(const DevIndex& ix, DevSeed* seeds_a, uint32_t na, DevSeed* seeds_b, uint32_t nb, int32_t limit) {
     const int lane = lane_id();
     const uint32_t n = na + nb;
+#pragma unroll 1
     while (true) {
         bool changed = false;
+#pragma unroll 1
         for (uint32_t i = lane; i < n; i += 32) {
             DevSeed* pi = i < na ? seeds_a + i : seeds_b + (i - na);
             const DevSeed si = *pi;
@@ -636,6 +660,7 @@ __device__ __forceinline__ uint32_t collect_clusters(const SeedSmem& sm, const C
                                                      const DevMinimizer* mins, uint32_t M, uint32_t k, uint32_t L, uint32_t cbase) {
     const int lane = lane_id();
     uint32_t Cn = 0;
+#pragma unroll 1
     for (uint32_t base = 0; base < H; base += 32) {
         const uint32_t i = base + lane;
         const bool root = i < H && seeds[i].label == i;
@@ -660,6 +685,7 @@ __device__ __forceinline__ uint32_t collect_clusters(const SeedSmem& sm, const C
         uint32_t present[PRESENT_WORDS];
 #pragma unroll
         for (uint32_t x = 0; x < PRESENT_WORDS; x++) present[x] = 0;
+#pragma unroll 1
         for (uint32_t i = lane; i < H; i += 32) {
             const DevSeed sd = seeds[i];
             if (sd.label == label) {
@@ -675,6 +701,7 @@ __device__ __forceinline__ uint32_t collect_clusters(const SeedSmem& sm, const C
 #pragma unroll
         for (uint32_t x = 0; x < PRESENT_WORDS; x++) {
             uint32_t bits = present[x];
+#pragma unroll 1
             while (bits) { const int bpos = __ffs(bits) - 1; bits &= bits - 1; score += __shfl_sync(FULL, mscore[x], bpos); }
         }
         // coverage: a base is covered when a present minimizer's k-mer starts in (pos - k, pos]
@@ -685,6 +712,7 @@ __device__ __forceinline__ uint32_t collect_clusters(const SeedSmem& sm, const C
             if ((present[x] >> lane) & 1u) atomicOr(&cs.startbits[mfwd[x] >> 5], 1u << (mfwd[x] & 31));
         __syncwarp();
         uint32_t cnt = 0;
+#pragma unroll 1
         for (uint32_t wd = 0; wd < n_words; wd++) {
             const uint32_t pos = wd * 32 + lane;
             const bool covered = pos < L && any_bit_in_range(cs.startbits, pos + 1 > k ? pos + 1 - k : 0u, pos + 1);
@@ -710,15 +738,18 @@ __device__ __forceinline__ uint32_t emit_items(const DevIndex& ix, const SeedSme
     if (n_kept == 0) return GB_ITEM_OK;
     uint32_t item_off = 0;
     if (!pool_claim(pools.item_cursor, n_kept, pools.item_cap, pools.overflow, item_off)) return GB_ITEM_OUT_FULL;
+#pragma unroll 1
     for (uint32_t t = 0; t < n_kept; t++) {
         const uint32_t c = kept[t];
         const uint32_t label = sm.c_label[cbase + c];
         uint32_t cnt = 0;
+#pragma unroll 1
         for (uint32_t i = lane; i < H; i += 32) cnt += seeds[i].label == label ? 1u : 0u;
         cnt = (uint32_t)warp_sum((int)cnt);
         uint32_t eoff = 0;
         if (!pool_claim(pools.ext_cursor, cnt, pools.ext_cap, pools.overflow, eoff)) return GB_ITEM_OUT_FULL;
         uint32_t wpos = 0;
+#pragma unroll 1
         for (uint32_t base = 0; base < H; base += 32) {
             const uint32_t i = base + lane;
             const bool mine = i < H && seeds[i].label == label;
@@ -760,12 +791,14 @@ __device__ __forceinline__ uint32_t cluster_phase_se(const DevIndex& ix, const M
     const uint32_t Cn = collect_clusters(sm, cs, seeds, H, mins, M, ix.k, L, 0);
     if (Cn == 0xffffffffu) return table_full(sm.Cc, MAX_CLUSTERS);
     rs.n_clusters = Cn;
+#pragma unroll 1
     for (uint32_t c = lane; c < Cn; c += 32) sm.c_frag[c] = 0;
 
     uint32_t n_kept = 0;
     uint8_t* kept = sm.scratch;
     if (lane == 0) {
         double best_cluster_score = 0.0, second_best_cluster_score = 0.0;
+#pragma unroll 1
         for (uint32_t c = 0; c < Cn; c++) {
             const double sc = sm.c_score[c];
             if (sc > best_cluster_score) { second_best_cluster_score = best_cluster_score; best_cluster_score = sc; }
@@ -777,19 +810,24 @@ __device__ __forceinline__ uint32_t cluster_phase_se(const DevIndex& ix, const M
         auto comes_before = [&](uint32_t a, uint32_t b) {
             return (sm.c_cov[a] > sm.c_cov[b]) || (sm.c_cov[a] == sm.c_cov[b] && sm.c_score[a] > sm.c_score[b]);
         };
+#pragma unroll 1
         for (uint32_t c = 0; c < Cn; c++) {
             uint32_t j = c;
+#pragma unroll 1
             while (j > 0 && comes_before(c, sm.c_order[j - 1])) { sm.c_order[j] = sm.c_order[j - 1]; j--; }
             sm.c_order[j] = (uint8_t)c;
         }
         uint32_t ties = 0;
+#pragma unroll 1
         while (ties < Cn && !comes_before(sm.c_order[0], sm.c_order[ties])) ties++;
+#pragma unroll 1
         for (uint32_t i = 1; i < ties; i++) {
             const uint32_t j = rng_next(rng) % (i + 1);
             const uint8_t t = sm.c_order[j]; sm.c_order[j] = sm.c_order[i]; sm.c_order[i] = t;
         }
         const double cutoff = Cn == 0 ? 0.0 : sm.c_cov[sm.c_order[0]] - P.cluster_coverage_threshold;
         uint32_t unskipped = 0, kept_cluster_count = 0;
+#pragma unroll 1
         for (uint32_t i = 0; i < Cn; i++) {
             const uint32_t c = sm.c_order[i];
             bool process;
@@ -837,6 +875,7 @@ __device__ __forceinline__ uint32_t cluster_phase_pe(const DevIndex& ix, const M
         // ---- small seed sets (the usual case): one pass builds both adjacency relations as 64-bit
         // masks in registers (lane owns seeds lane and lane + 32), components by min-label sweeps
         // over the masks; labels live in shared memory.
+#pragma unroll 1
         for (uint32_t i = lane; i < n_all; i += 32) {
             const DevSeed sd = i < H0 ? s0[i] : s1[i - H0];
             cs.seedbuf[i] = make_uint4(sd.id_off, (uint32_t)sd.c_in, (uint32_t)sd.c_out, sd.slot);
@@ -862,6 +901,7 @@ __device__ __forceinline__ uint32_t cluster_phase_pe(const DevIndex& ix, const M
             if (d <= read_limit && ((uint32_t)lane < H0) == (j < H0)) adj_r[0] |= 1ull << j;
         }
         // rows of the few seeds beyond 32: the warp evaluates one row at a time, lane = column, rows by vote
+#pragma unroll 1
         for (uint32_t i = 32; i < n_all; i++) {
             const uint4 si = cs.seedbuf[i];
             bool f_lo = false, r_lo = false, f_hi = false, r_hi = false;
@@ -886,12 +926,14 @@ __device__ __forceinline__ uint32_t cluster_phase_pe(const DevIndex& ix, const M
                 const uint32_t i = lane + 32 * q;
                 mine[q] = row ? min(i, (uint32_t)(__ffsll((long long)row) - 1)) : i;
             }
+#pragma unroll 1
             while (true) {
                 const uint32_t p_lo = __reduce_or_sync(FULL, (has[0] && mine[0] < 32 ? 1u << mine[0] : 0u) | (has[1] && mine[1] < 32 ? 1u << mine[1] : 0u));
                 const uint32_t p_hi = __reduce_or_sync(FULL, (has[0] && mine[0] >= 32 ? 1u << (mine[0] - 32) : 0u) | (has[1] && mine[1] >= 32 ? 1u << (mine[1] - 32) : 0u));
                 uint64_t present = ((uint64_t)p_hi << 32) | p_lo;
                 uint32_t next[2] = {mine[0], mine[1]};
                 bool changed = false;
+#pragma unroll 1
                 while (present) {
                     const uint32_t L = (uint32_t)(__ffsll((long long)present) - 1); present &= present - 1;
                     const uint64_t carriers = (uint64_t)__ballot_sync(FULL, has[0] && mine[0] == L) | ((uint64_t)__ballot_sync(FULL, has[1] && mine[1] == L) << 32);
@@ -909,6 +951,7 @@ __device__ __forceinline__ uint32_t cluster_phase_pe(const DevIndex& ix, const M
             __syncwarp();
         }
         // read-cluster labels back to the records (local index space of each read)
+#pragma unroll 1
         for (uint32_t i = lane; i < n_all; i += 32) {
             if (i < H0) s0[i].label = cs.lab_read[i]; else s1[i - H0].label = (uint32_t)cs.lab_read[i] - H0;
         }
@@ -917,6 +960,7 @@ __device__ __forceinline__ uint32_t cluster_phase_pe(const DevIndex& ix, const M
         for (uint32_t r = 0; r < 2; r++) {
             const uint32_t Hr = r ? H1 : H0, g0 = r ? H0 : 0u;
             uint32_t n_roots = 0;
+#pragma unroll 1
             for (uint32_t base = 0; base < Hr && !overflow; base += 32) {
                 const uint32_t i = base + lane;
                 const bool root = i < Hr && cs.lab_read[g0 + i] == g0 + i;
@@ -935,12 +979,16 @@ __device__ __forceinline__ uint32_t cluster_phase_pe(const DevIndex& ix, const M
         for (uint32_t pass = 0; pass < 3; pass++) {
             DevSeed* sa = pass == 2 ? s1 : s0; const uint32_t na = pass == 2 ? H1 : H0;
             const uint32_t nb = pass == 0 ? H1 : 0u;
+#pragma unroll 1
             for (uint32_t i = lane; i < na; i += 32) sa[i].label = i;
+#pragma unroll 1
             for (uint32_t i = lane; i < nb; i += 32) s1[i].label = na + i;
             __syncwarp();
             propagate_labels(ix, sa, na, s1, nb, pass == 0 ? fragment_limit : read_limit);
             if (pass == 0) {
+#pragma unroll 1
                 for (uint32_t i = lane; i < H0; i += 32) s0[i].source |= s0[i].label << 8;
+#pragma unroll 1
                 for (uint32_t i = lane; i < H1; i += 32) s1[i].source |= s1[i].label << 8;
             }
             __syncwarp();
@@ -950,6 +998,7 @@ __device__ __forceinline__ uint32_t cluster_phase_pe(const DevIndex& ix, const M
         for (uint32_t r = 0; r < 2; r++) {
             DevSeed* sr = r ? s1 : s0; const uint32_t Hr = r ? H1 : H0;
             uint32_t n_roots = 0;
+#pragma unroll 1
             for (uint32_t base = 0; base < Hr && !overflow; base += 32) {
                 const uint32_t i = base + lane;
                 const bool root = i < Hr && sr[i].label == i;
@@ -959,6 +1008,7 @@ __device__ __forceinline__ uint32_t cluster_phase_pe(const DevIndex& ix, const M
                 n_roots += __popc(bal);
             }
             __syncwarp();
+#pragma unroll 1
             for (uint32_t i = lane; i < Hr; i += 32) sr[i].source &= 0xffu;
             __syncwarp();
         }
@@ -980,6 +1030,7 @@ __device__ __forceinline__ uint32_t cluster_phase_pe(const DevIndex& ix, const M
     uint32_t n_frag = 0;
     if (lane == 0) {
         // fragment renumbering (:129-141 of the clusterer wrapper)
+#pragma unroll 1
         for (uint32_t r = 0; r < 2; r++) for (uint32_t c = 0; c < (r ? Cn[1] : Cn[0]); c++) {
             const uint32_t head = cs.side[r * sm.Cc + c];
             uint32_t f = 0; while (f < n_frag && cs.heads[f] != head) f++;
@@ -990,24 +1041,32 @@ __device__ __forceinline__ uint32_t cluster_phase_pe(const DevIndex& ix, const M
         else {
             double* const fs[2] = {cs.fs0, cs.fs1}; double* const fc[2] = {cs.fc0, cs.fc1};
             uint8_t* has_first = cs.has_first; uint8_t* has_pair = cs.has_pair; uint8_t* fo = cs.fo;
+#pragma unroll 1
             for (uint32_t f = 0; f < n_frag; f++) { has_first[f] = has_pair[f] = 0; fs[0][f] = fs[1][f] = fc[0][f] = fc[1][f] = 0.0; }
             bool found_paired_cluster = false;
+#pragma unroll 1
             for (uint32_t c = 0; c < Cn[0]; c++) has_first[sm.c_frag[c]] = 1;
+#pragma unroll 1
             for (uint32_t c = 0; c < Cn[1]; c++) { const uint32_t f = sm.c_frag[sm.Cc + c]; has_pair[f] = has_first[f]; if (has_first[f]) found_paired_cluster = true; }
+#pragma unroll 1
             for (uint32_t r = 0; r < 2; r++) for (uint32_t c = 0; c < (r ? Cn[1] : Cn[0]); c++) {
                 const uint32_t t = r * sm.Cc + c, f = sm.c_frag[t];
                 fs[r][f] = max(fs[r][f], sm.c_score[t]); fc[r][f] = max(fc[r][f], sm.c_cov[t]);
             }
             // better_cluster_count (:1657-1690)
             auto total = [&](uint32_t f) { return (fc[0][f] + fc[1][f]) + (fs[0][f] + fs[1][f]); };
+#pragma unroll 1
             for (uint32_t f = 0; f < n_frag; f++) { uint32_t j = f; while (j > 0 && total(f) > total(fo[j - 1])) { fo[j] = fo[j - 1]; j--; } fo[j] = (uint8_t)f; }
             {
                 uint32_t ties = 0;
+#pragma unroll 1
                 while (ties < n_frag && !(total(fo[0]) > total(fo[ties]))) ties++;
+#pragma unroll 1
                 for (uint32_t i = 1; i < ties; i++) { const uint32_t j = rng_next(rng) % (i + 1); const uint8_t t = fo[j]; fo[j] = fo[i]; fo[i] = t; }
             }
             double prev_score_sum = 0.0;
             uint8_t* better = gps->better_cluster_count;
+#pragma unroll 1
             for (int rank = (int)n_frag - 1; rank >= 0; rank--) {
                 const uint32_t f = fo[rank];
                 if (rank == (int)n_frag - 1) better[f] = (uint8_t)(rank + 1);
@@ -1025,6 +1084,7 @@ __device__ __forceinline__ uint32_t cluster_phase_pe(const DevIndex& ix, const M
                 const uint32_t cb = r * sm.Cc, Cr = r ? Cn[1] : Cn[0];
                 double cluster_score_cutoff = 0.0, cluster_coverage_cutoff = 0.0, second_best = 0.0;
                 double best_cov = 0.0, best_cov_score = 0.0;
+#pragma unroll 1
                 for (uint32_t c = 0; c < Cr; c++) {
                     const double cov = sm.c_cov[cb + c], sc = sm.c_score[cb + c];
                     if (cov > best_cov) { best_cov = cov; best_cov_score = sc; }
@@ -1047,8 +1107,10 @@ __device__ __forceinline__ uint32_t cluster_phase_pe(const DevIndex& ix, const M
                     else return sm.c_score[cb + a] > sm.c_score[cb + b];
                 };
                 uint8_t* order = sm.c_order + cb;
+#pragma unroll 1
                 for (uint32_t c = 0; c < Cr; c++) { uint32_t j = c; while (j > 0 && comes_before(c, order[j - 1])) { order[j] = order[j - 1]; j--; } order[j] = (uint8_t)c; }
                 uint32_t ties = 0;
+#pragma unroll 1
                 while (ties < Cr && !comes_before(order[0], order[ties])) ties++;
                 uint8_t* kept = r == 0 ? kept0 : kept1;
                 if (r == 1 && ties > 1) {
@@ -1057,6 +1119,7 @@ __device__ __forceinline__ uint32_t cluster_phase_pe(const DevIndex& ix, const M
                     // are not known here, so the shuffle and the order-dependent keep loop move to the align stage: every
                     // cluster becomes a work item, in comparator order, carrying the order-independent inputs of the keep
                     // decision as flags (bit 0 eligible, bit 1 below the coverage cutoff, bit 2 below the score cutoff).
+#pragma unroll 1
                     for (uint32_t i = 0; i < Cr; i++) {
                         const uint32_t c = order[i];
                         const uint32_t f = sm.c_frag[cb + c];
@@ -1070,9 +1133,11 @@ __device__ __forceinline__ uint32_t cluster_phase_pe(const DevIndex& ix, const M
                     n_kept1 = Cr; defer_ties = ties;
                     continue;
                 }
+#pragma unroll 1
                 for (uint32_t i = 1; i < ties; i++) { const uint32_t j = rng_next(rng) % (i + 1); const uint8_t t = order[j]; order[j] = order[i]; order[i] = t; }
                 // process_until_threshold_c with threshold 0: everything is "good enough", max_extensions caps
                 uint32_t unskipped = 0, kept_cluster_count = 0, nk = 0;
+#pragma unroll 1
                 for (uint32_t i = 0; i < Cr; i++) {
                     const uint32_t c = order[i];
                     if (unskipped >= P.max_extensions) continue;

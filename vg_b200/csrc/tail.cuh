@@ -123,6 +123,7 @@ __device__ inline uint32_t build_tail_forest(const DevIndex& ix, const TailWs& w
     if (lane == 0) ws.stack[0] = DfsFrame{start_node, lo, hi, 0u, 0u};
     sp = 1;
     __syncwarp();
+#pragma unroll 1
     while (sp > 0) {
         const DfsFrame f = ws.stack[sp - 1];
         const bool is_root = (sp == 1);
@@ -151,6 +152,7 @@ __device__ inline uint32_t build_tail_forest(const DevIndex& ix, const TailWs& w
             if (used < walk_distance) {
                 const EdgeFan fan = record_fan(ix, nr, f.lo, f.hi);
                 bool pushed_any = false;
+#pragma unroll 1
                 for (uint32_t e = 0; e < fan.n_edges; e++) {
                     uint32_t to; int32_t first, cnt, rev;
                     if (fan.n_edges <= 32) {
@@ -195,6 +197,7 @@ __device__ inline int32_t xdrop_tree(const DevIndex& ix, const DevScores& sc, co
     int32_t best = 0; uint32_t best_node = 0, best_col = 0, best_j = 0; bool have_best = false;
     uint32_t tb_cols = 0;
     const uint32_t n_chunks = (W + 31) >> 5;
+#pragma unroll 1
     for (uint32_t i = t0; i < t1; i++) {
         TreeNode tn = ws.tree[i];
         int32_t run_max;
@@ -202,6 +205,7 @@ __device__ inline int32_t xdrop_tree(const DevIndex& ix, const DevScores& sc, co
         // and are never read; the X-drop keeps that range a narrow band around the best diagonal.
         uint32_t plo, phi;
         if (tn.parent < 0) {
+#pragma unroll 1
             for (uint32_t j = lane; j < W; j += 32) {
                 int32_t h = DP_NEG;
                 if (j == 0) h = 0; else if (j <= max_gap) h = -(go + (int32_t)(j - 1) * ge);
@@ -215,6 +219,7 @@ __device__ inline int32_t xdrop_tree(const DevIndex& ix, const DevScores& sc, co
             plo = par.band_lo; phi = par.band_hi;
             const int32_t* cH = ws.colH + (size_t)par.depth * (ws.Lc + 1);
             const int32_t* cE = ws.colE + (size_t)par.depth * (ws.Lc + 1);
+#pragma unroll 1
             for (uint32_t j = plo * 32 + lane; j < min(W, phi * 32); j += 32) { dps.Hp[j] = cH[j]; dps.Ep[j] = cE[j]; }
             run_max = par.lineage_max;
         }
@@ -223,6 +228,7 @@ __device__ inline int32_t xdrop_tree(const DevIndex& ix, const DevScores& sc, co
         tn.tb_col = tb_cols; tn.computed = 1;
         // this lane's best cell of the node: first column, then smallest j, on ties (strict > below)
         int32_t lane_best = DP_NEG; uint32_t lane_col = 0, lane_j = 0;
+#pragma unroll 1
         for (uint32_t c = 0; c < tn.len && plo < phi; c++) {
             const uint8_t r = __ldg(ix.seq + tn.seq_off + c);
             uint8_t* tbcol = ws.tb + (size_t)(tb_cols + c) * W;
@@ -231,6 +237,7 @@ __device__ inline int32_t xdrop_tree(const DevIndex& ix, const DevScores& sc, co
             int32_t prev_ph_last = DP_NEG;    // previous column's H of the last cell of the previous chunk (diagonal)
             int32_t col_max = DP_NEG;
             uint32_t clo = n_chunks, chi = 0;
+#pragma unroll 1
             for (uint32_t ch = plo; ch < n_chunks; ch++) {
                 const uint32_t j = ch * 32 + lane;
                 const bool in = j < W;
@@ -304,6 +311,7 @@ __device__ inline int32_t xdrop_tree(const DevIndex& ix, const DevScores& sc, co
         if (plo < phi) {
             int32_t* cH = ws.colH + (size_t)tn.depth * (ws.Lc + 1);
             int32_t* cE = ws.colE + (size_t)tn.depth * (ws.Lc + 1);
+#pragma unroll 1
             for (uint32_t j = plo * 32 + lane; j < min(W, phi * 32); j += 32) { cH[j] = dps.Hp[j]; cE[j] = dps.Ep[j]; }
         }
         tn.band_lo = (uint8_t)min(plo, 255u); tn.band_hi = (uint8_t)(plo < phi ? phi : min(plo, 255u));
@@ -330,8 +338,10 @@ __device__ inline int32_t xdrop_tree(const DevIndex& ix, const DevScores& sc, co
         uint32_t node = best_node, col = best_col, j = best_j;
         int state = 0;   // 0 H, 1 E, 2 F
         bool at_virtual = false;
+#pragma unroll 1
         while (true) {
             if (at_virtual) {
+#pragma unroll 1
                 for (; j > 0; j--) { if (n_steps >= TAIL_STEP_CAP) { overflow = true; return 0; } if (lane == 0) ws.steps[n_steps] = (t0 << 8) | 2u; n_steps++; }
                 break;
             }
@@ -380,6 +390,7 @@ __device__ inline int32_t xdrop_tree(const DevIndex& ix, const DevScores& sc, co
     if (lane == 0) {
         uint32_t query_offset = 0;
         int64_t si = (int64_t)n_steps - 1;
+#pragma unroll 1
         while (si >= 0) {
             const uint32_t nd = ws.steps[si] >> 8;
             pb_add_mapping(out, nd, 0);
@@ -392,6 +403,7 @@ __device__ inline int32_t xdrop_tree(const DevIndex& ix, const DevScores& sc, co
                     else if (cur == 3) { pb_add_edit(out, edit_word(GB_EDIT_DEL, run, 0)); }
                 }
             };
+#pragma unroll 1
             while (si >= 0 && (ws.steps[si] >> 8) == nd) {
                 const uint32_t op = ws.steps[si] & 0xffu;
                 if (op == cur) run++; else { if (cur != 0xff) flush(); cur = op; run = 1; }

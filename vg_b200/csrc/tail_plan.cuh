@@ -32,6 +32,7 @@ __device__ inline bool plan_tail(const DevIndex& ix, const MapParamsDev& P, cons
     } else {
         from_node = last;
         uint32_t tail_off = e.offset + (e.read_hi - e.read_lo);
+#pragma unroll 1
         for (uint32_t i = 0; i + 1 < e.path_len; i++) tail_off -= load_node(ix, path_pool[e.path_off + i]).len;
         from_offset = tail_off; lo = (int32_t)e.fwd_lo; hi = (int32_t)e.fwd_hi; tail_length = L - e.read_hi;
     }
@@ -46,10 +47,13 @@ __device__ inline bool plan_tail(const DevIndex& ix, const MapParamsDev& P, cons
     uint32_t n_trees = 0, units = 0;
     {
         uint32_t t0 = 0;
+#pragma unroll 1
         while (t0 < n_forest) {
             uint32_t t1 = t0 + 1;
+#pragma unroll 1
             while (t1 < n_forest && ws.tree[t1].parent >= 0) t1++;
             uint32_t bases = 0, depth = 0;
+#pragma unroll 1
             for (uint32_t i = t0 + lane; i < t1; i += 32) { bases += ws.tree[i].len; depth = max(depth, ws.tree[i].depth); }
             bases = (uint32_t)warp_sum((int)bases); depth = __reduce_max_sync(FULL, depth);
             if ((uint64_t)bases * tail_length <= P.max_dozeu_cells) {
@@ -69,10 +73,13 @@ __device__ inline bool plan_tail(const DevIndex& ix, const MapParamsDev& P, cons
     first_tile = __shfl_sync(FULL, first_tile, 0); first_unit = __shfl_sync(FULL, first_unit, 0);
     if (first_tile == 0xffffffffu) return false;
     uint32_t t0 = 0, ti = first_tile, unit_at = first_unit;
+#pragma unroll 1
     while (t0 < n_forest) {
         uint32_t t1 = t0 + 1;
+#pragma unroll 1
         while (t1 < n_forest && ws.tree[t1].parent >= 0) t1++;
         uint32_t bases = 0;
+#pragma unroll 1
         for (uint32_t i = t0 + lane; i < t1; i += 32) bases += ws.tree[i].len;
         bases = (uint32_t)warp_sum((int)bases);
         if ((uint64_t)bases * tail_length > P.max_dozeu_cells) {
@@ -85,12 +92,15 @@ __device__ inline bool plan_tail(const DevIndex& ix, const MapParamsDev& P, cons
             uint8_t* tq = tb + ((bases + 15u) & ~15u);
             // node table + bases: lane-parallel over nodes for the table, node by node for the bases (nodes are <= 32 bp on these graphs)
             uint32_t at = 0;
+#pragma unroll 1
             for (uint32_t i = t0; i < t1; i++) {
                 const TreeNode t = ws.tree[i];
                 if (lane == 0) { TileNode o; o.parent = t.parent < 0 ? 0xffffu : (uint16_t)((uint32_t)t.parent - t0); o.len = (uint16_t)t.len; o.node = t.node; tn[i - t0] = o; }
+#pragma unroll 1
                 for (uint32_t x = lane; x < t.len; x += 32) tb[at + x] = __ldg(ix.seq + t.seq_off + x);
                 at += t.len;
             }
+#pragma unroll 1
             for (uint32_t x = lane; x < tail_length; x += 32)
                 tq[x] = dp_query_base(left_tail ? comp_base(read[tail_length - 1 - x]) : read[e.read_hi + x]);
             if (lane == 0) {
@@ -128,17 +138,21 @@ __device__ inline void plan_read(const DevIndex& ix, const MapParamsDev& P, cons
     if (S == 0 || S > MAX_SETS) return;
     const bool deferred = rs.pad[0] > 1;                 // read 2 with tied clusters: align_sets picks a subset of the items later
     int set_score[MAX_SETS]; uint8_t set_order[MAX_SETS];
+#pragma unroll 1
     for (uint32_t s = 0; s < S; s++) {
         const uint32_t item = rs.item_off + s;
         if (a.ev.ext_status[item] != GB_ITEM_OK) return;
         set_score[s] = score_extension_group(ev_ext(a.ev, item), a.ev.ext_count[item], L, sc.gap_open, sc.gap_extend);
     }
+#pragma unroll 1
     for (uint32_t s = 0; s < S; s++) { uint32_t j = s; while (j > 0 && set_score[s] > set_score[set_order[j - 1]]) { set_order[j] = set_order[j - 1]; j--; } set_order[j] = (uint8_t)s; }
     uint32_t ties = 0;
+#pragma unroll 1
     while (ties < S && !(set_score[set_order[0]] > set_score[set_order[ties]])) ties++;
     const double set_cutoff = (double)set_score[set_order[0]] - P.extension_set_score_threshold;
     const uint32_t min_sets = paired ? 2u : (uint32_t)P.min_extension_sets;
     uint32_t unskipped = 0;
+#pragma unroll 1
     for (uint32_t oi = 0; oi < S; oi++) {
         const uint32_t s = set_order[oi];
         if (!deferred) {
@@ -155,9 +169,11 @@ __device__ inline void plan_read(const DevIndex& ix, const MapParamsDev& P, cons
         if (n_ext == 0 || (ext_full(ext[0]) && ext[0].mismatches <= 4)) continue;       // no extensions / direct full-length alignments
         const uint32_t* path_pool = ev_path(a.ev, item);
         uint32_t min_tails = 1;
+#pragma unroll 1
         for (uint32_t j = 0; j < n_ext; j++) if (ext_full(ext[j])) min_tails++;
         if (min_tails < 2) min_tails = 2;
         uint8_t eo[64]; const uint32_t ne_ = min(n_ext, 64u);
+#pragma unroll 1
         for (uint32_t j = 0; j < ne_; j++) { uint32_t x = j; while (x > 0 && ext[j].score > ext[eo[x - 1]].score) { eo[x] = eo[x - 1]; x--; } eo[x] = (uint8_t)j; }
         const double ecut = (double)ext[eo[0]].score - (double)P.extension_score_threshold;
         const int32_t threshold = ext[eo[0]].score - P.extension_score_threshold;
@@ -167,13 +183,16 @@ __device__ inline void plan_read(const DevIndex& ix, const MapParamsDev& P, cons
         // whatever order the LazyRNG puts them) and the first partial one are always aligned: wave 0.  The others wait (wave 1)
         // until tail_decide_kernel has the winner of wave 0 and cancels the ones the reference skips.
         bool partial_aligned = false;
+#pragma unroll 1
         for (uint32_t y = 0; y < ne_ && ext[eo[y]].score > threshold; y++) partial_aligned |= !ext_full(ext[eo[y]]);
+#pragma unroll 1
         for (uint32_t xi = 0; xi < ne_; xi++) {
             const gb_extension& e = ext[eo[xi]];
             if (P.extension_score_threshold != 0 && (double)e.score <= ecut && e_unskipped >= min_tails) continue;
             e_unskipped++;
             if (ext_full(e)) continue;
             const bool candidate = !deferred && e.score <= threshold && partial_aligned;
+#pragma unroll 1
             for (uint32_t side = 0; side < 2; side++) {
                 const bool left_tail = side == 0;
                 if (e.flags & (left_tail ? GB_EXT_LEFT_FULL : GB_EXT_RIGHT_FULL)) continue;
@@ -191,6 +210,7 @@ tail_plan_kernel(DevIndex ix, MapParamsDev P, DevScores sc, MapBatch b, AlignArg
     const uint32_t gwarp = blockIdx.x * ALIGN_WARPS + warp;
     const TailWs ws = carve_tail_ws(a.ws_base + (size_t)gwarp * a.ws_stride, b.Lc, a.tb_cells);
     const uint32_t n_units = PAIRED ? b.n_reads / 2 : b.n_reads;
+#pragma unroll 1
     while (true) {
         uint32_t pos = 0, u = 0xffffffffu;
         if (lane == 0) {
@@ -201,6 +221,7 @@ tail_plan_kernel(DevIndex ix, MapParamsDev P, DevScores sc, MapBatch b, AlignArg
         if (u >= n_units) break;
         TailPlanEntry* unit_entries = pp.entries + (size_t)pos * PLAN_PER_UNIT;
         uint32_t n_entries = 0;
+#pragma unroll 1
         for (uint32_t r = 0; r < (PAIRED ? 2u : 1u); r++) {
             const uint32_t ri = PAIRED ? 2 * u + r : u;
             const ReadState rs = b.states[ri];
@@ -230,6 +251,7 @@ __device__ inline void decide_read(const DevIndex& ix, const MapParamsDev& P, co
     // best score over the trees of a finished tail (deterministic_beats only breaks ties): -1 if the tail is not available
     auto tail_score = [&](const TailPlanEntry* pe) -> int32_t {
         int32_t best = 0;
+#pragma unroll 1
         for (uint32_t t = 0; t < pe->n_trees; t++) {
             const uint32_t ti = pe->first_tile + t;
             if (tile_off[ti] == TILE_REFUSED) continue;
@@ -238,6 +260,7 @@ __device__ inline void decide_read(const DevIndex& ix, const MapParamsDev& P, co
         }
         return best;
     };
+#pragma unroll 1
     for (uint32_t s = 0; s < S; s++) {
         const uint32_t item = rs.item_off + s;
         if (a.ev.ext_status[item] != GB_ITEM_OK) continue;
@@ -245,13 +268,16 @@ __device__ inline void decide_read(const DevIndex& ix, const MapParamsDev& P, co
         const uint32_t n_ext = a.ev.ext_count[item];
         if (n_ext == 0 || (ext_full(ext[0]) && ext[0].mismatches <= 4)) continue;
         bool any_waiting = false;
+#pragma unroll 1
         for (uint32_t x = 0; x < n_entries; x++) any_waiting |= entries[x].wave == 1 && (entries[x].key >> 9) == ((read_num << 21) | s);
         if (!any_waiting) continue;
         const uint32_t* mism_pool = ev_mism(a.ev, item);
         uint32_t min_tails = 1;
+#pragma unroll 1
         for (uint32_t j = 0; j < n_ext; j++) if (ext_full(ext[j])) min_tails++;
         if (min_tails < 2) min_tails = 2;
         Pareto lf[136], rf[136]; uint32_t nl = 0, nr = 0;
+#pragma unroll 1
         for (uint32_t j = 0; j < n_ext && nl + 3 < 136; j++) {
             const gb_extension& e = ext[j];
             if (ext_full(e)) continue;
@@ -268,10 +294,12 @@ __device__ inline void decide_read(const DevIndex& ix, const MapParamsDev& P, co
         lf[nl++] = Pareto{ix.k + ix.w - 2, 0}; rf[nr++] = Pareto{ix.k + ix.w - 2, 0};
         nl = find_pareto_frontier(lf, nl); nr = find_pareto_frontier(rf, nr);
         uint8_t eo[64]; const uint32_t ne_ = min(n_ext, 64u);
+#pragma unroll 1
         for (uint32_t j = 0; j < ne_; j++) { uint32_t x = j; while (x > 0 && ext[j].score > ext[eo[x - 1]].score) { eo[x] = eo[x - 1]; x--; } eo[x] = (uint8_t)j; }
         const double ecut = (double)ext[eo[0]].score - (double)P.extension_score_threshold;
         uint32_t e_unskipped = 0;
         int32_t winning_score = 0; bool known = true, stop = false;
+#pragma unroll 1
         for (uint32_t xi = 0; xi < ne_ && !stop; xi++) {
             const gb_extension& e = ext[eo[xi]];
             if (P.extension_score_threshold != 0 && (double)e.score <= ecut && e_unskipped >= min_tails) continue;
@@ -297,6 +325,7 @@ __device__ inline void decide_read(const DevIndex& ix, const MapParamsDev& P, co
             if (!(e.flags & GB_EXT_RIGHT_FULL)) estimate -= flank_penalty(L - e.read_hi, rf, nr, sc);
             if (estimate <= winning_score) {
                 if (lane_id() == 0) {
+#pragma unroll 1
                     for (const TailPlanEntry* pe : {pl, pr}) if (pe) for (uint32_t t = 0; t < pe->n_trees; t++) if (tile_off[pe->first_tile + t] != TILE_REFUSED) results[pe->first_tile + t].status = GB_TILE_ST_CANCELLED;
                 }
             } else stop = true;           // this one will be aligned and may move the winner: everything behind it runs
@@ -309,6 +338,7 @@ __global__ void __launch_bounds__(ALIGN_WARPS * 32, 4)
 tail_decide_kernel(DevIndex ix, MapParamsDev P, DevScores sc, MapBatch b, AlignArgs a, PlanPools pp) {
     const int lane = threadIdx.x & 31;
     const uint32_t n_units = PAIRED ? b.n_reads / 2 : b.n_reads;
+#pragma unroll 1
     while (true) {
         uint32_t pos = 0, u = 0xffffffffu;
         if (lane == 0) {
@@ -320,8 +350,10 @@ tail_decide_kernel(DevIndex ix, MapParamsDev P, DevScores sc, MapBatch b, AlignA
         const TailPlanEntry* entries = pp.entries + (size_t)pos * PLAN_PER_UNIT;
         const uint32_t n_entries = pp.unit_count[u];
         bool any = false;
+#pragma unroll 1
         for (uint32_t x = 0; x < n_entries; x++) any |= entries[x].wave == 1;
         if (!any) continue;
+#pragma unroll 1
         for (uint32_t r = 0; r < (PAIRED ? 2u : 1u); r++) {
             const uint32_t ri = PAIRED ? 2 * u + r : u;
             const ReadState rs = b.states[ri];

@@ -623,6 +623,7 @@ struct PlanView {
     const uint32_t* tile_off;
     const TileResult* results;
     const uint32_t* path_pool;
+    uint64_t* stats;                   // plan counters (gb_plan_stats); [2] counts tails of planned units that were aligned in place
 };
 struct TailLookup { const PlanView* pv; uint32_t base, count, key; };     // pv == nullptr: no plan (always in place)
 
