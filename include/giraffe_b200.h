@@ -157,6 +157,24 @@ int gb_index_view(const gb_host_index* ix, gb_flat_index* out);
  * GBWT version 5 / GBWTGraph version 3 in simple-sds serialization.  GB_ERR_FORMAT for anything else, and for graphs
  * outside the index model (haplotypes that step onto a reverse strand, cycles, a site of more than 4096 nodes). */
 int gb_index_from_gbz(const char* path, uint32_t k, uint32_t w, gb_host_index** out);
+/* The same with the minimizer table READ from the gbwtgraph .min file giraffe loads beside the GBZ (`-m`,
+ * giraffe_main.cpp:1825-1881) instead of re-derived by scanning every haplotype: k, w, keys and positions come from the
+ * file (minimizer index version 10, 16-byte payloads), every position is checked against the graph (node, offset, the
+ * bases of the k-mer on that node), and zipcodes_path (may be NULL; `-z`, zip_code.cpp:2111-2170) must hold every
+ * oversized zipcode the table points at.  The distance payload is still the library's own chain model derived from the
+ * graph (vg's zipcodes are a different encoding of the same coordinates: tests/test_gbz.py pins the prefix sums); `.dist`
+ * is not needed.  Limit, stated rather than guessed: a .min whose keys have several occurrences stores them after the table
+ * in a layout the reference's only .min fixture (test/primers/y.min) does not show — such a file is GB_ERR_FORMAT and the
+ * caller uses gb_index_from_gbz. */
+int gb_index_from_gbz_min(const char* gbz_path, const char* min_path, const char* zipcodes_path, gb_host_index** out);
+/* gb_index_build with the minimizer hits given by the caller: hit i = (keys[i], positions[i]), position =
+ * id << 11 | is_reverse << 10 | offset of the first base of the canonical k-mer on that oriented node (gbwtgraph's
+ * Position encoding).  Hits that do not lie on the graph or do not spell their key are GB_ERR_FORMAT. */
+int gb_index_build_with_hits(uint32_t n_node_ids, const uint8_t* node_seq, const uint64_t* node_off,
+                             uint32_t n_paths, const uint32_t* path_nodes, const uint64_t* path_off,
+                             const gb_dist_payload* dist, uint32_t k, uint32_t w,
+                             uint64_t n_hits, const uint64_t* keys, const uint64_t* positions,
+                             gb_host_index** out);
 int gb_index_save(const gb_flat_index* ix, const char* path);
 int gb_index_load(const char* path, gb_host_index** out);
 

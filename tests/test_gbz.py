@@ -394,3 +394,86 @@ def test_cuda_path_equals_oracle_on_the_reference_gbz_graph():
     p = H.paired_params(); p.max_rescue_attempts = 15
     assert not H.compare_alignments(H.gpu_map(dev, pairs, pq, p, paired=True), H.oracle_map_paired(index, pairs, pq, p, threads=8), len(pairs))
     dev.close(); index.close()
+
+
+# ---- the .min / .zipcodes files giraffe loads beside the GBZ (giraffe_main.cpp:1825-1881) -----------------------------------
+
+def _table_as_dict(index):
+    table, hits = index.array("table"), index.array("hits")
+    return {int(c["key"]): sorted((int(hits[int(c["hit_off"]) + i]["pos"]), bytes(hits[int(c["hit_off"]) + i]["payload"].tobytes()))
+                                  for i in range(int(c["hit_cnt"])))
+            for c in table if int(c["key"]) != 0xFFFFFFFFFFFFFFFF}
+
+
+def test_index_from_the_reference_min_file_equals_the_rederived_one():
+    """gb_index_from_gbz_min takes k, w, keys and positions from the reference's y.min (and checks y.zipcodes holds the
+    oversized codes it points at); the result must be the index gb_index_from_gbz derives by scanning the haplotypes:
+    same table, same hits, same distance payload, and the oracle maps reads identically on both."""
+    d = GBZ.parent
+    a = capi.HostIndex.from_gbz_min(GBZ, d / "y.min", d / "y.zipcodes")
+    b = capi.HostIndex.from_gbz(GBZ, k=31, w=50)
+    assert (a.k, a.w) == (31, 50)
+    assert _table_as_dict(a) == _table_as_dict(b) and len(_table_as_dict(a)) == 62
+    for name in ("nodes", "gbwt", "dist", "slots", "site_dist"):
+        assert a.array(name).tobytes() == b.array(name).tobytes(), name
+    seqs, paths, _ = read_gbz(GBZ)
+    hap = "".join(seqs[(v >> 1) - 1] for v in paths[0])
+    reads = np.stack([np.frombuffer(hap[s:s + 150].encode(), dtype=np.uint8) for s in range(0, len(hap) - 150, 37)])
+    quals = np.full(reads.shape, 30, dtype=np.uint8)
+    ra, rb = H.oracle_map(a, reads, quals, threads=2), H.oracle_map(b, reads, quals, threads=2)
+    assert ra[0].tobytes() == rb[0].tobytes() and (ra[0]["flags"] & 1).all()
+    a.close(); b.close()
+
+
+def test_min_files_that_do_not_fit_are_refused(tmp_path):
+    d = GBZ.parent
+    raw = bytearray((d / "y.min").read_bytes())
+    W = lambda i: struct.unpack_from("<Q", raw, 8 * i)[0]
+
+    def variant(name, edit):
+        b = bytearray(raw); edit(b); p = tmp_path / name; p.write_bytes(bytes(b)); return p
+
+    first = next(c for c in range(1024) if W(10 + 4 * c) != 0x7FFFFFFFFFFFFFFF)
+    cases = {
+        "tag.min": lambda b: struct.pack_into("<I", b, 0, 0x12345678),
+        "version.min": lambda b: struct.pack_into("<I", b, 4, 9),
+        "syncmers.min": lambda b: struct.pack_into("<Q", b, 64, W(8) | 1),
+        "multi.min": lambda b: struct.pack_into("<Q", b, 48, W(6) + 1),                       # values != keys: a key with two occurrences
+        "pointer.min": lambda b: struct.pack_into("<Q", b, 8 * (10 + 4 * first), W(10 + 4 * first) | (1 << 63)),
+        "otherkmer.min": lambda b: struct.pack_into("<Q", b, 8 * (10 + 4 * first), W(10 + 4 * first) ^ (3 << 60)),   # first base of the key changed
+        "offgraph.min": lambda b: struct.pack_into("<Q", b, 8 * (11 + 4 * first), (5000 << 11)),
+        "pastnode.min": lambda b: struct.pack_into("<Q", b, 8 * (11 + 4 * first), (W(11 + 4 * first) & ~1023) | 900),
+        "short.min": lambda b: b.__delitem__(slice(len(b) - 16, len(b))),
+    }
+    for name, edit in cases.items():
+        with pytest.raises(capi.GbError):
+            capi.HostIndex.from_gbz_min(GBZ, variant(name, edit), d / "y.zipcodes")
+    # a .zipcodes file that lacks the oversized codes the table points at, or is not one
+    z = (d / "y.zipcodes").read_bytes()
+    (tmp_path / "empty.zipcodes").write_bytes(z[:8])
+    (tmp_path / "foreign.zipcodes").write_bytes(b"NOPE" + z[4:])
+    for name in ("empty.zipcodes", "foreign.zipcodes", "missing.zipcodes"):
+        with pytest.raises(capi.GbError):
+            capi.HostIndex.from_gbz_min(GBZ, d / "y.min", tmp_path / name)
+    capi.HostIndex.from_gbz_min(GBZ, d / "y.min").close()                                     # the zipcode file is optional
+
+
+def test_build_with_hits_equals_the_haplotype_scan():
+    """gb_index_build_with_hits on a graph with repeated k-mers: handing the builder the (key, position) pairs it would
+    find itself (several occurrences per key here, unlike y.min) gives the identical index."""
+    g = synth.make_variant_graph(length=6000, n_snp=20, n_ins=3, n_del=3, n_haps=4, seed=9)
+    ref = g.build_index()
+    table, hits = ref.array("table"), ref.array("hits")
+    keys, pos = [], []
+    for c in table:
+        if int(c["key"]) == 0xFFFFFFFFFFFFFFFF:
+            continue
+        for i in range(int(c["hit_cnt"])):
+            keys.append(int(c["key"])); pos.append(int(hits[int(c["hit_off"]) + i]["pos"]))
+    order = np.random.default_rng(3).permutation(len(keys))
+    got = capi.HostIndex(g.node_seqs, g.paths, g.dist, k=ref.k, w=ref.w,
+                         hits=(np.asarray(keys, dtype=np.uint64)[order], np.asarray(pos, dtype=np.uint64)[order]))
+    assert _table_as_dict(got) == _table_as_dict(ref)
+    for name in ("nodes", "gbwt", "dist", "table", "hits"):
+        assert got.array(name).tobytes() == ref.array(name).tobytes(), name
+    got.close(); ref.close()

@@ -132,6 +132,10 @@ def load_library() -> C.CDLL:
     lib.gb_last_error.restype = C.c_char_p
     lib.gb_index_from_gbz.argtypes = [C.c_char_p, u32, u32, vp]
     lib.gb_index_from_gbz.restype = C.c_int
+    lib.gb_index_from_gbz_min.argtypes = [C.c_char_p, C.c_char_p, C.c_char_p, vp]
+    lib.gb_index_from_gbz_min.restype = C.c_int
+    lib.gb_index_build_with_hits.argtypes = [u32, vp, vp, u32, vp, vp, vp, u32, u32, u64, vp, vp, vp]
+    lib.gb_index_build_with_hits.restype = C.c_int
     lib.gb_index_save.argtypes = [C.POINTER(FlatIndex), C.c_char_p]
     lib.gb_index_save.restype = C.c_int
     lib.gb_index_load.argtypes = [C.c_char_p, vp]
@@ -219,7 +223,8 @@ class GbError(RuntimeError):
 class HostIndex:
     """Owns a gb_host_index built by the library from node sequences and haplotype paths."""
 
-    def __init__(self, node_seqs, paths, dist=None, k=29, w=11):
+    def __init__(self, node_seqs, paths, dist=None, k=29, w=11, hits=None):
+        """hits = (keys, positions): the minimizer table is taken from the caller (gb_index_build_with_hits)."""
         lib = load_library()
         n = len(node_seqs)
         node_off = np.zeros(n + 1, dtype=np.uint64)
@@ -235,7 +240,13 @@ class HostIndex:
             assert len(dist) == n + 1, "dist payload is indexed by node id (entry 0 unused)"
             dptr = ptr(dist)
         h = C.c_void_p()
-        rc = lib.gb_index_build(n, ptr(seq), ptr(node_off), len(paths), ptr(flat), ptr(path_off), dptr, k, w, C.byref(h))
+        if hits is None:
+            rc = lib.gb_index_build(n, ptr(seq), ptr(node_off), len(paths), ptr(flat), ptr(path_off), dptr, k, w, C.byref(h))
+        else:
+            hk, hp = (np.ascontiguousarray(a, dtype=np.uint64) for a in hits)
+            assert len(hk) == len(hp)
+            rc = lib.gb_index_build_with_hits(n, ptr(seq), ptr(node_off), len(paths), ptr(flat), ptr(path_off), dptr, k, w,
+                                              len(hk), ptr(hk), ptr(hp), C.byref(h))
         if rc != GB_OK:
             raise GbError(rc, "gb_index_build")
         self._h = h
@@ -269,6 +280,24 @@ class HostIndex:
             raise GbError(rc, "gb_index_view")
         self.node_seqs, self.paths = None, None
         self.k, self.w = k, w
+        return self
+
+    @classmethod
+    def from_gbz_min(cls, gbz, min_path, zipcodes=None):
+        """gb_index_from_gbz_min: GBZ + the .min (and .zipcodes) files giraffe loads beside it; k and w come from the .min."""
+        lib = load_library()
+        h = C.c_void_p()
+        rc = lib.gb_index_from_gbz_min(str(gbz).encode(), str(min_path).encode(), str(zipcodes).encode() if zipcodes else None, C.byref(h))
+        if rc != GB_OK:
+            raise GbError(rc, "gb_index_from_gbz_min")
+        self = cls.__new__(cls)
+        self._h = h
+        self.view = FlatIndex()
+        rc = lib.gb_index_view(h, C.byref(self.view))
+        if rc != GB_OK:
+            raise GbError(rc, "gb_index_view")
+        self.node_seqs, self.paths = None, None
+        self.k, self.w = int(self.view.k), int(self.view.w)
         return self
 
     @classmethod

@@ -115,7 +115,66 @@ int fail(const char* why) { if (getenv("GB_GBZ_DEBUG")) fprintf(stderr, "gbz rea
 
 } // namespace
 
-static int index_from_gbz_impl(const char* path, uint32_t k, uint32_t w, gb_host_index** out) {
+// The minimizer table of a gbwtgraph .min file (what `vg giraffe -m` loads, giraffe_main.cpp:1825-1881; written by
+// gbwtgraph::DefaultMinimizerIndex::serialize, gbwtgraph @ e27bc43 — absent from the reference tree).  Layout as found in
+// the file the reference ships for its test GBZ (test/primers/y.min, kept as tests/golden/gbz/y.min) and checked there
+// cell by cell against this library's own minimizer scan (tests/test_gbz.py):
+//   9-word header  tag 0x31513151 | version 10 << 32, k, w, keys, (unused), max_keys, values, unique, flags
+//                  (flags bit 0 = syncmers, refused; bits 5.. = payload words, 2: vg's 16-byte zipcode payload)
+//   word 9         capacity, then capacity 32-byte cells: key, position, payload[2]; the empty key is 2^63 - 1
+//   after the table one 64-bit count of multi-occurrence values: 0 in that file.
+// Keys with SEVERAL occurrences (key bit 63 set; values == unique is false) are laid out after the table in a way that
+// file cannot show, so such a file is refused (GB_ERR_FORMAT) rather than guessed at: the caller then falls back to
+// gb_index_from_gbz, which finds the same minimizers by scanning the haplotypes.
+struct MinFile { uint32_t k = 0, w = 0; std::vector<uint64_t> keys, pos, payload0, payload1; };
+static int read_min_file(const char* path, MinFile& m) {
+    FILE* f = fopen(path, "rb");
+    if (!f) return fail("open .min");
+    std::vector<uint8_t> bytes;
+    { uint8_t buf[65536]; size_t n; while ((n = fread(buf, 1, sizeof buf, f)) > 0) bytes.insert(bytes.end(), buf, buf + n); }
+    fclose(f);
+    if (bytes.size() < 88 || bytes.size() % 8 != 0) return fail(".min size");
+    std::vector<uint64_t> W(bytes.size() / 8);
+    memcpy(W.data(), bytes.data(), bytes.size());
+    if ((uint32_t)W[0] != 0x31513151u || (W[0] >> 32) != 10) return fail("not a minimizer index version 10");
+    const uint64_t k = W[1], w = W[2], keys = W[3], values = W[6], unique = W[7], flags = W[8], capacity = W[9];
+    if (k == 0 || k > 31 || w == 0 || w > 4096) return fail(".min k / w");
+    if ((flags & 1u) != 0) return fail(".min holds syncmers, not minimizers");
+    if ((flags >> 5) != 2) return fail(".min payload is not 16 bytes");
+    if (capacity == 0 || (capacity & (capacity - 1)) != 0 || capacity > (W.size() - 10) / 4) return fail(".min capacity");
+    if (keys > capacity || values != keys || unique != keys) return fail(".min has keys with several occurrences (layout not covered)");
+    if (W.size() != 10 + 4 * capacity + 1 || W.back() != 0) return fail(".min tail");
+    m.k = (uint32_t)k; m.w = (uint32_t)w;
+    for (uint64_t c = 0; c < capacity; c++) {
+        const uint64_t* cell = &W[10 + 4 * c];
+        if (cell[0] == 0x7FFFFFFFFFFFFFFFull) continue;
+        if (cell[0] >> 63) return fail(".min pointer cell");
+        m.keys.push_back(cell[0]); m.pos.push_back(cell[1]); m.payload0.push_back(cell[2]); m.payload1.push_back(cell[3]);
+    }
+    if (m.keys.size() != keys) return fail(".min key count");
+    return GB_OK;
+}
+// The oversized zipcodes of a .zipcodes file ("SPIZ", zip_code.cpp:2111-2170): only counted here — a cell whose payload is
+// (0, i) points at zipcode i of this file, and the three files must agree on that (zip_code.cpp:2018-2058).
+static int count_zipcodes(const char* path, uint64_t& count) {
+    FILE* f = fopen(path, "rb");
+    if (!f) return fail("open .zipcodes");
+    std::vector<uint8_t> z;
+    { uint8_t buf[65536]; size_t n; while ((n = fread(buf, 1, sizeof buf, f)) > 0) z.insert(z.end(), buf, buf + n); }
+    fclose(f);
+    if (z.size() < 8 || memcmp(z.data(), "SPIZ", 4) != 0) return fail("not a zipcode file");
+    size_t i = 8; count = 0;
+    auto varint = [&](uint64_t& v) { v = 0; for (unsigned sh = 0; sh < 64; sh += 7) { if (i >= z.size()) return false; const uint8_t c = z[i++]; v |= (uint64_t)(c & 0x7F) << sh; if (!(c & 0x80)) return true; } return false; };
+    while (i < z.size()) {
+        uint64_t n;
+        if (!varint(n) || n > z.size() - i) return fail("zipcode length"); i += n;        // the zipcode's varints
+        if (!varint(n) || n > z.size() - i) return fail("decoder length"); i += n;        // its decoder
+        count++;
+    }
+    return GB_OK;
+}
+
+static int index_from_gbz_impl(const char* path, uint32_t k, uint32_t w, gb_host_index** out, const MinFile* min = nullptr) {
     if (!path || !out) return GB_ERR_ARG;
     *out = nullptr;
     FILE* f = fopen(path, "rb");
@@ -215,7 +274,9 @@ static int index_from_gbz_impl(const char* path, uint32_t k, uint32_t w, gb_host
     std::vector<uint32_t> flat; std::vector<uint64_t> path_off{0};
     for (const auto& p : paths) { flat.insert(flat.end(), p.begin(), p.end()); path_off.push_back(flat.size()); }
     if (node_seq.empty()) node_seq.push_back(0);
-    const int rc = gb_index_build((uint32_t)n_ids, node_seq.data(), node_off.data(), (uint32_t)paths.size(), flat.data(), path_off.data(), nullptr, k, w, out);
+    const int rc = min ? gb_index_build_with_hits((uint32_t)n_ids, node_seq.data(), node_off.data(), (uint32_t)paths.size(), flat.data(), path_off.data(), nullptr, k, w,
+                                                  min->keys.size(), min->keys.data(), min->pos.data(), out)
+                       : gb_index_build((uint32_t)n_ids, node_seq.data(), node_off.data(), (uint32_t)paths.size(), flat.data(), path_off.data(), nullptr, k, w, out);
     if (rc == GB_OK && !gb_index_has_distance_model(*out)) { gb_index_free(*out); *out = nullptr; return fail("graph outside the chain model (cycle, reversing haplotype or oversized site)"); }
     return rc;
 }
@@ -223,4 +284,23 @@ static int index_from_gbz_impl(const char* path, uint32_t k, uint32_t w, gb_host
 extern "C" int gb_index_from_gbz(const char* path, uint32_t k, uint32_t w, gb_host_index** out) {
     try { return index_from_gbz_impl(path, k, w, out); }          // no exception crosses the ABI
     catch (...) { if (out) *out = nullptr; return GB_ERR_FORMAT; }
+}
+
+extern "C" int gb_index_from_gbz_min(const char* gbz_path, const char* min_path, const char* zipcodes_path, gb_host_index** out) {
+    try {
+        if (!gbz_path || !min_path || !out) return GB_ERR_ARG;
+        *out = nullptr;
+        MinFile m;
+        int rc = read_min_file(min_path, m);
+        if (rc != GB_OK) return rc;
+        uint64_t oversized = 0;
+        for (size_t i = 0; i < m.keys.size(); i++) if ((m.payload0[i] & 0xFF) == 0) oversized = std::max<uint64_t>(oversized, m.payload1[i] + 1);
+        if (zipcodes_path) {
+            uint64_t n = 0;
+            rc = count_zipcodes(zipcodes_path, n);
+            if (rc != GB_OK) return rc;
+            if (oversized > n) return fail(".min points past the end of .zipcodes");
+        }
+        return index_from_gbz_impl(gbz_path, m.k, m.w, out, &m);
+    } catch (...) { if (out) *out = nullptr; return GB_ERR_FORMAT; }
 }

@@ -257,8 +257,11 @@ bool derive_distance_payload(uint32_t n_node_ids, const std::vector<uint32_t>& l
 static int index_build_impl(uint32_t n_node_ids, const uint8_t* node_seq, const uint64_t* node_off,
                             uint32_t n_paths, const uint32_t* path_nodes, const uint64_t* path_off,
                             const gb_dist_payload* dist, uint32_t k, uint32_t w,
-                            gb_host_index** out) {
+                            gb_host_index** out,
+                            uint64_t n_ext_hits = 0, const uint64_t* ext_keys = nullptr, const uint64_t* ext_pos = nullptr) {
     if (!node_seq || !node_off || !out || (n_paths && (!path_nodes || !path_off))) return GB_ERR_ARG;
+    const bool external = ext_keys != nullptr || ext_pos != nullptr;
+    if (external && (!ext_keys || !ext_pos)) return GB_ERR_ARG;
     if (k == 0 || k > 31 || w == 0) return GB_ERR_ARG;
     // offsets into seq / gbwt / hits are 32-bit (gb_node_rec, gb_min_cell): both orientations at 1 B/base bound the
     // graph at 2 Gbp; larger inputs are refused instead of wrapping
@@ -382,7 +385,27 @@ static int index_build_impl(uint32_t n_node_ids, const uint8_t* node_seq, const 
     std::vector<KP> kps;
     std::string hap; std::vector<uint32_t> base_node; std::vector<uint32_t> base_off;
     std::vector<gbmin::Minimizer> mins;
-    for (uint32_t p = 0; p < n_paths; p++) {
+    if (external) {
+        // the minimizer table comes from the caller (what a gbwtgraph .min file holds, giraffe_main.cpp:1825-1881):
+        // (key, position) pairs, position = id << 11 | is_reverse << 10 | offset, the first base of the canonical k-mer
+        // on that oriented node.  Each is checked against the graph: the node exists, the offset lies inside it, and the
+        // bases of the k-mer that fall on this node spell the leading bases of the key — a table that belongs to
+        // another graph is GB_ERR_FORMAT, not a silent source of wrong seeds.
+        kps.reserve(n_ext_hits);
+        for (uint64_t i = 0; i < n_ext_hits; i++) {
+            const uint64_t pos = ext_pos[i], v = pos >> 10; const uint32_t o = (uint32_t)(pos & 1023u);
+            if (v < 2 || v >= ix->n_nodes || (k < 32 && (ext_keys[i] >> (2 * k)) != 0)) { delete ix; return GB_ERR_FORMAT; }
+            const gb_node_rec& nr = ix->nodes[v];
+            if (nr.len == 0 || o >= nr.len) { delete ix; return GB_ERR_FORMAT; }
+            const uint32_t on_node = std::min<uint32_t>(k, nr.len - o);
+            for (uint32_t j = 0; j < on_node; j++) {
+                const uint32_t c = gbmin::base_code(ix->seq[nr.seq_off + o + j]);
+                if (c != ((ext_keys[i] >> (2 * (k - 1 - j))) & 3u)) { delete ix; return GB_ERR_FORMAT; }
+            }
+            kps.push_back(KP{ext_keys[i], pos});
+        }
+    }
+    for (uint32_t p = 0; p < n_paths && !external; p++) {
         hap.clear(); base_node.clear(); base_off.clear();
         for (uint32_t v : seqs[2 * p]) {
             const gb_node_rec& nr = ix->nodes[v];
@@ -429,6 +452,18 @@ extern "C" int gb_index_build(uint32_t n_node_ids, const uint8_t* node_seq, cons
                               const gb_dist_payload* dist, uint32_t k, uint32_t w,
                               gb_host_index** out) {
     try { return index_build_impl(n_node_ids, node_seq, node_off, n_paths, path_nodes, path_off, dist, k, w, out); }
+    catch (const std::bad_alloc&) { return GB_ERR_CAPACITY; }
+    catch (...) { return GB_ERR_ARG; }
+}
+
+extern "C" int gb_index_build_with_hits(uint32_t n_node_ids, const uint8_t* node_seq, const uint64_t* node_off,
+                                        uint32_t n_paths, const uint32_t* path_nodes, const uint64_t* path_off,
+                                        const gb_dist_payload* dist, uint32_t k, uint32_t w,
+                                        uint64_t n_hits, const uint64_t* keys, const uint64_t* positions,
+                                        gb_host_index** out) {
+    static const uint64_t none = 0;
+    if (n_hits == 0) { keys = keys ? keys : &none; positions = positions ? positions : &none; }
+    try { return index_build_impl(n_node_ids, node_seq, node_off, n_paths, path_nodes, path_off, dist, k, w, out, n_hits, keys, positions); }
     catch (const std::bad_alloc&) { return GB_ERR_CAPACITY; }
     catch (...) { return GB_ERR_ARG; }
 }
