@@ -570,6 +570,51 @@ int gb_wfa_batch(gb_device* dev, uint32_t n, const uint8_t* seq, const uint64_t*
                  int32_t* ok, int32_t* score, uint32_t* node_offset, uint32_t* seq_offset, uint32_t* length,
                  uint32_t* path, uint32_t* n_path, uint32_t* edits, uint32_t* n_edits);
 
+/* ------------------------------------------------------------------------------------
+ * Chaining route, stage seam: algorithms::find_best_chains  (algorithms/chain_items.hpp:576, chain_items.cpp:733-900)
+ * = add_transition_if_legal (:262-355) + chain_items_dp (:395-640) + chain_items_traceback (:642-735), the anchor
+ * chaining DP of minimizer_mapper_from_chains.cpp:1201 (fragments) and :1933 (chains).  The zip-code tree that
+ * enumerates candidate (source, destination, graph distance) triples (zip_code_tree.cpp; generate_zip_tree_transitions
+ * chain_items.cpp:157-260) stays on the caller's side: it is the iterator argument of the reference function.
+ *
+ * Problem p: anchors[anchor_off[p] .. anchor_off[p+1]) sorted by read_start (ties: longer first, sort_anchor_indexes :102),
+ * candidates[cand_off[p] .. cand_off[p+1]) in any order; from / to are anchor indices inside the problem and
+ * graph_distance is what the zip-code tree measured between the two hint positions.  A candidate becomes a transition
+ * when the read distance exists and is <= max_read_lookback_bases, the exclusion zones do not overlap, the hint offsets
+ * fit into graph_distance and the indel |read - graph| is <= max_indel_bases.
+ * Outputs: dp_score / dp_source per anchor (the TracedScore table; source 0xffffffff = nowhere), dp_paths / dp_rec per
+ * anchor (supported haplotype flags, recombinations so far); per problem up to max_chains chains in the reference's
+ * order (penalty ascending): chain_score[p * max_chains + c], chain_begin / chain_count into chain_items (anchor
+ * indices left to right; chain_items is laid out like anchors: a problem's chains share its anchor range).
+ * n_chains[p] = chains written (0 for a problem without anchors: the reference returns one empty chain of score 0).
+ * Where the reference leaves the order open (std::sort of equal keys in the traceback starts and in the final
+ * penalty sort) the lower anchor index / the earlier traceback comes first.
+ * ---------------------------------------------------------------------------------- */
+typedef struct {
+    uint32_t read_start, length;               /* Anchor::read_start(), length()                                        */
+    uint32_t margin_before, margin_after;      /* read_exclusion_start = read_start - margin_before, ..._end = read_end + margin_after */
+    int32_t  score;                            /* Anchor::score()                                                       */
+    uint32_t start_hint_offset, end_hint_offset;
+    uint32_t base_seed_length;
+    uint64_t start_paths, end_paths;           /* anchor_start_paths(), anchor_end_paths() (path_flags_t)               */
+} gb_chain_anchor;                             /* 48 bytes */
+typedef struct { uint32_t from, to; uint64_t graph_distance; } gb_chain_candidate;     /* 16 bytes */
+typedef struct {
+    int32_t  item_bonus;                       /* ChainScoringScheme, chain_items.hpp:407-418 */
+    int32_t  recombination_penalty, consistency_bonus;
+    uint32_t max_chains;                       /* >= 1 */
+    double   gap_scale;
+    uint64_t max_indel_bases;                  /* <= 65535 */
+    uint64_t max_read_lookback_bases;
+} gb_chain_params;
+void gb_chain_params_default(gb_chain_params* p);      /* 0, 0, 0, 1 chain, 1.0, 100, unlimited */
+int gb_chain_batch(gb_device* dev, const gb_chain_params* params, uint32_t n_problems,
+                   const gb_chain_anchor* anchors, const uint64_t* anchor_off,
+                   const gb_chain_candidate* candidates, const uint64_t* cand_off,
+                   int32_t* dp_score, uint32_t* dp_source, uint64_t* dp_paths, uint32_t* dp_rec,
+                   uint32_t* n_chains, int32_t* chain_score, uint32_t* chain_begin, uint32_t* chain_count,
+                   uint32_t* chain_items);
+
 /* Kernel-only timing of the last gb_*_batch call on this handle, milliseconds
  * (CUDA events on the handle's stream around the kernels, copies excluded). */
 float gb_last_kernel_ms(const gb_device* dev);

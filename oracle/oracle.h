@@ -57,6 +57,15 @@ int oracle_map_paired_batch(const gb_flat_index* ix, const gb_scores* scores, co
                             gb_alignment* aln, gb_mapping* mappings, uint32_t* edits, uint8_t* status,
                             int n_threads, uint64_t* counters_out);
 
+/* algorithms::find_best_chains for one problem (chain_items.cpp:733-800) with the candidate list standing in for the
+ * zip-code-tree iterator; outputs as gb_chain_batch (chain_begin relative to chain_items).  -1: a candidate names an
+ * anchor that does not exist. */
+int oracle_chain(const gb_chain_params* P, uint32_t n_anchors, const gb_chain_anchor* anchors,
+                 uint64_t n_candidates, const gb_chain_candidate* candidates,
+                 int32_t* dp_score, uint32_t* dp_source, uint64_t* dp_paths, uint32_t* dp_rec,
+                 uint32_t* n_chains, int32_t* chain_score, uint32_t* chain_begin, uint32_t* chain_count,
+                 uint32_t* chain_items);
+
 #ifdef __cplusplus
 }
 #endif

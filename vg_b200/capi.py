@@ -57,6 +57,18 @@ class Scores(C.Structure):
                 ("gap_extend", C.c_int8), ("full_length_bonus", C.c_int8)]
 
 
+class ChainParams(C.Structure):
+    _fields_ = [("item_bonus", C.c_int32), ("recombination_penalty", C.c_int32), ("consistency_bonus", C.c_int32),
+                ("max_chains", C.c_uint32), ("gap_scale", C.c_double), ("max_indel_bases", C.c_uint64),
+                ("max_read_lookback_bases", C.c_uint64)]
+
+
+chain_anchor_dt = np.dtype([("read_start", "<u4"), ("length", "<u4"), ("margin_before", "<u4"), ("margin_after", "<u4"),
+                            ("score", "<i4"), ("start_hint_offset", "<u4"), ("end_hint_offset", "<u4"), ("base_seed_length", "<u4"),
+                            ("start_paths", "<u8"), ("end_paths", "<u8")])
+chain_candidate_dt = np.dtype([("from", "<u4"), ("to", "<u4"), ("graph_distance", "<u8")])
+
+
 class ExtendParams(C.Structure):
     _fields_ = [("max_mismatches", C.c_uint32), ("overlap_threshold", C.c_double), ("trim", C.c_uint32),
                 ("max_ext_per_item", C.c_uint32), ("path_cap_per_item", C.c_uint32),
@@ -166,6 +178,10 @@ def load_library() -> C.CDLL:
     lib.gb_xdrop_dag_batch.restype = C.c_int
     lib.gb_wfa_batch.argtypes = [vp, u32, vp, vp, vp, vp, vp, u32, u32, vp, vp, vp, vp, vp, vp, vp, vp, vp]
     lib.gb_wfa_batch.restype = C.c_int
+    lib.gb_chain_params_default.argtypes = [C.POINTER(ChainParams)]
+    lib.gb_chain_params_default.restype = None
+    lib.gb_chain_batch.argtypes = [vp, C.POINTER(ChainParams), u32, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp]
+    lib.gb_chain_batch.restype = C.c_int
     lib.gb_fragment_create.argtypes = [u64, u64, C.c_double]
     lib.gb_fragment_create.restype = vp
     lib.gb_fragment_destroy.argtypes = [vp]
@@ -611,6 +627,33 @@ class Device:
                     ed.append(["MSID"[w & 3], w >> 4, "ACGT"[(w >> 2) & 3] if (w & 3) == 1 else ""])
                 path.append([int(m["node"]), int(m["offset"]), ed])
             out.append((int(score[i]), path))
+        return out
+
+    def chain_batch(self, problems, params=None):
+        """gb_chain_batch.  problems: list of (anchors, candidates) structured arrays (chain_anchor_dt sorted by read_start,
+        chain_candidate_dt).  Returns per problem {"dp": [(score, source, paths, rec)], "chains": [(score, [anchor indices])]}."""
+        lib = load_library()
+        if params is None:
+            params = ChainParams(); lib.gb_chain_params_default(C.byref(params))
+        n = len(problems)
+        aoff = np.zeros(n + 1, dtype=np.uint64); coff = np.zeros(n + 1, dtype=np.uint64)
+        aoff[1:] = np.cumsum([len(a) for a, _ in problems]); coff[1:] = np.cumsum([len(c) for _, c in problems])
+        anchors = np.ascontiguousarray(np.concatenate([np.asarray(a, dtype=chain_anchor_dt) for a, _ in problems] + [np.zeros(1, chain_anchor_dt)]))
+        cands = np.ascontiguousarray(np.concatenate([np.asarray(c, dtype=chain_candidate_dt) for _, c in problems] + [np.zeros(1, chain_candidate_dt)]))
+        ta = int(aoff[-1]); k = int(params.max_chains)
+        dps = np.zeros(ta + 1, np.int32); dpsrc = np.zeros(ta + 1, np.uint32); dpp = np.zeros(ta + 1, np.uint64); dpr = np.zeros(ta + 1, np.uint32)
+        nch = np.zeros(n, np.uint32); cs = np.zeros(n * k, np.int32); cb = np.zeros(n * k, np.uint32); cc = np.zeros(n * k, np.uint32)
+        items = np.zeros(ta + 1, np.uint32)
+        rc = lib.gb_chain_batch(self._h, C.byref(params), n, ptr(anchors), ptr(aoff), ptr(cands), ptr(coff),
+                                ptr(dps), ptr(dpsrc), ptr(dpp), ptr(dpr), ptr(nch), ptr(cs), ptr(cb), ptr(cc), ptr(items))
+        if rc != GB_OK:
+            raise GbError(rc, "gb_chain_batch")
+        out = []
+        for p in range(n):
+            a0, a1 = int(aoff[p]), int(aoff[p + 1])
+            out.append({"dp": [(int(dps[i]), int(dpsrc[i]), int(dpp[i]), int(dpr[i])) for i in range(a0, a1)],
+                        "chains": [(int(cs[p * k + c]), [int(x) for x in items[int(cb[p * k + c]): int(cb[p * k + c]) + int(cc[p * k + c])]])
+                                   for c in range(int(nch[p]))]})
         return out
 
     def wfa_batch(self, problems, error_model=None, path_cap=512, edit_cap=512):
