@@ -277,6 +277,8 @@ typedef struct gb_mapping {       /* one Mapping: position + run of edits (8 B) 
 #define GB_ALN_SECONDARY  2u
 #define GB_ALN_PAIRED     4u      /* produced by map_paired                                  */
 #define GB_ALN_RESCUED    8u
+#define GB_ALN_ABSENT     16u     /* max_multimaps > 1: this rank of this read has no mapping (skip the record)   */
+#define GB_MAX_MULTIMAPS  8u
 
 typedef struct gb_alignment {     /* 32 B header per output alignment                        */
     uint32_t read_id;             /* index of the read in the batch                          */
@@ -311,7 +313,7 @@ typedef struct gb_map_params {
     int32_t  extension_set_min_score;    /* 20   */
     uint32_t max_alignments;             /* 8    */
     uint32_t max_extension_mismatches;   /* 4    */
-    uint32_t max_multimaps;              /* 1 (only 1 is supported)                          */
+    uint32_t max_multimaps;              /* 1 .. GB_MAX_MULTIMAPS: mappings reported per read (or pairs per pair)   */
     uint32_t max_dozeu_cells;            /* 1.5 * 1024 * 1024                                */
     uint32_t do_dp;                      /* 1    */
     /* paired-end (map_paired, minimizer_mapper.cpp:1462) */
@@ -333,8 +335,11 @@ void gb_map_params_default(gb_map_params* p);
 
 /* Single-end batch.  reads/quals are concatenated bytes addressed by read_off[n_reads+1]
  * (quals = raw Phred bytes, may be NULL: then the explored-minimizer cap is +inf as in
- * minimizer_mapper.cpp:2950).  One primary alignment per read (max_multimaps = 1):
- * aln[n_reads] and status[n_reads]; mappings / edits are DENSE pools of the given capacities
+ * minimizer_mapper.cpp:2950).  aln[n_reads * max_multimaps] and status[n_reads]: record j * n_reads + r is
+ * mapping j of read r in output order (minimizer_mapper.cpp:1087-1206; map_paired: pair j of the pair, :2505-2598) —
+ * j = 0 the primary, which alone carries the MAPQ; j >= 1 secondaries (GB_ALN_SECONDARY), or GB_ALN_ABSENT when the
+ * read has fewer mappings.  With max_multimaps = 1 (the default) that is one record per read.
+ * mappings / edits are DENSE pools of the given capacities
  * (gb_alignment.mapping_off / edit_off index into them); the elements used are returned
  * through n_mappings_used / n_edits_used (may be NULL).  GB_ERR_CAPACITY if a pool is too
  * small.  Internally the batch is processed in chunks of 2^20 reads. */

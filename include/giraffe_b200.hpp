@@ -29,6 +29,7 @@ struct Alignment {
     std::string sequence, quality, name;          // quality: raw phred bytes, as vg keeps them
     Path path;
     int32_t score = 0, mapping_quality = 0;
+    bool is_secondary = false;                    // mappings 1 .. max_multimaps - 1 (minimizer_mapper.cpp:1205, :2555)
     double identity = 0.0;
     std::map<std::string, double> annotation;     // mapq_uncapped, mapq_explored_cap (minimizer_mapper.cpp:1173-1174), rescued
     std::string fragment_prev, fragment_next;     // mate names, set by map_paired (pair_all, minimizer_mapper.cpp:1280-1300)
@@ -82,22 +83,33 @@ public:
     double get_fragment_length_stdev() const { return fragment_length_distr.std_dev(); }
     size_t get_fragment_length_sample_size() const { return fragment_length_distr.curr_sample_size(); }
 
-    // vector<Alignment> map(Alignment& aln), minimizer_mapper.hpp:55: the winner first (max_multimaps = 1: only the winner)
+    uint32_t& max_multimaps = params.max_multimaps;
+
+    // vector<Alignment> map(Alignment& aln), minimizer_mapper.hpp:55: the winner first, then up to max_multimaps - 1 secondaries
     std::vector<Alignment> map(Alignment& aln) {
-        std::vector<Alignment> batch{aln};
-        map_batch(batch);
-        return batch;
+        Packed in; in.add(aln);
+        Outputs out(1, params);
+        uint64_t nm = 0, ne = 0;
+        check(gb_map_batch(dev, &params, 1, in.reads.data(), in.quality_or_null(), in.off.data(), out.aln.data(), out.maps.data(), out.maps.size(),
+                           out.edits.data(), out.edits.size(), out.status.data(), &nm, &ne));
+        return ranks_of(aln, 0, 1, out);
     }
     // pair<vector<Alignment>, vector<Alignment>> map_paired(Alignment& aln1, Alignment& aln2), minimizer_mapper.hpp:100;
     // needs a finalized distribution, like the reference's overload without the ambiguous-pair buffer
     std::pair<std::vector<Alignment>, std::vector<Alignment>> map_paired(Alignment& aln1, Alignment& aln2) {
         if (!fragment_distr_is_finalized()) throw std::runtime_error("map_paired: the fragment length distribution is not finalized");
-        std::vector<std::pair<Alignment, Alignment>> batch{{aln1, aln2}};
-        map_paired_batch(batch);
-        return {{batch[0].first}, {batch[0].second}};
+        Packed in; in.add(aln1); in.add(aln2);
+        Outputs out(2, params);
+        gb_map_params p = params; p.fragment_mean = get_fragment_length_mean(); p.fragment_stdev = get_fragment_length_stdev();
+        uint64_t nm = 0, ne = 0;
+        check(gb_map_paired_batch(dev, &p, 2, in.reads.data(), in.quality_or_null(), in.off.data(), out.aln.data(), out.maps.data(), out.maps.size(),
+                                  out.edits.data(), out.edits.size(), out.status.data(), &nm, &ne));
+        std::pair<std::vector<Alignment>, std::vector<Alignment>> res{ranks_of(aln1, 0, 2, out), ranks_of(aln2, 1, 2, out)};
+        for (size_t j = 0; j < res.first.size() && j < res.second.size(); j++) { res.first[j].fragment_next = aln2.name; res.second[j].fragment_prev = aln1.name; }
+        return res;
     }
 
-    // batch forms: the alignments are filled in place (path, score, mapping_quality, identity, annotations)
+    // batch forms: the alignments are filled in place with the PRIMARY mapping (path, score, mapping_quality, identity, annotations)
     void map_batch(std::vector<Alignment>& batch) {
         Packed in; for (Alignment& a : batch) in.add(a);
         Outputs out(in.n(), params);
@@ -142,14 +154,28 @@ private:
     };
     struct Outputs {
         std::vector<gb_alignment> aln; std::vector<gb_mapping> maps; std::vector<uint32_t> edits; std::vector<uint8_t> status;
-        Outputs(uint32_t n, const gb_map_params& p) : aln(n), maps((size_t)n * p.mapping_cap_per_read + 1), edits((size_t)n * p.edit_cap_per_read + 1), status(n) {}
+        // n * max_multimaps records, rank-major: record j * n + read (gb_map_batch)
+        Outputs(uint32_t n, const gb_map_params& p) : aln((size_t)n * p.max_multimaps), maps((size_t)n * p.max_multimaps * p.mapping_cap_per_read + 1),
+                                                      edits((size_t)n * p.max_multimaps * p.edit_cap_per_read + 1), status(n) {}
     };
+    // the mappings of read i (of n) that exist, primary first
+    std::vector<Alignment> ranks_of(const Alignment& in, uint32_t i, uint32_t n, const Outputs& out) const {
+        std::vector<Alignment> res;
+        for (uint32_t j = 0; j < params.max_multimaps; j++) {
+            const gb_alignment& r = out.aln[(size_t)j * n + i];
+            if (r.flags & GB_ALN_ABSENT) break;
+            res.push_back(in);
+            fill(res.back(), i, out, (size_t)j * n + i);
+        }
+        return res;
+    }
     // one record -> vg's Alignment fields (the inverse of what map_from_extensions sets, minimizer_mapper.cpp:1146-1216)
-    static void fill(Alignment& a, uint32_t i, const Outputs& out) {
+    static void fill(Alignment& a, uint32_t i, const Outputs& out, size_t record = (size_t)-1) {
+        if (record == (size_t)-1) record = i;
         if (out.status[i] != GB_ITEM_OK) throw std::runtime_error("read " + (a.name.empty() ? std::to_string(i) : a.name) + ": per-read capacity exceeded (status " + std::to_string(out.status[i]) + ")");
-        const gb_alignment& r = out.aln[i];
+        const gb_alignment& r = out.aln[record];
         a.path.mapping.clear();
-        a.score = r.score; a.mapping_quality = r.mapq;
+        a.score = r.score; a.mapping_quality = r.mapq; a.is_secondary = (r.flags & GB_ALN_SECONDARY) != 0;
         a.annotation["mapq_uncapped"] = r.mapq_uncapped; a.annotation["mapq_explored_cap"] = r.mapq_explored_cap;
         if (r.flags & GB_ALN_RESCUED) a.annotation["rescued"] = 1.0;
         uint64_t q = 0, matches = 0; uint32_t e = r.edit_off;

@@ -661,7 +661,10 @@ Alignment map_from_extensions(const gb_flat_index* ix, const gb_scores& scores, 
     out.mapq_explored_cap = mapq_explored_cap;
     mapq = std::round(std::min(mapq_explored_cap, std::min(mapq, 60.0)));
     out.mapq = std::max(std::min(mapq, 60.0), 0.0);
-    return std::move(out);
+    // mappings 1 .. max_multimaps - 1 are the secondaries, in score order (:1199-1206); only the primary carries a MAPQ
+    Alignment result = std::move(out);
+    for (size_t i = 1; i < mappings.size(); i++) { mappings[i].secondary = true; result.secondaries.push_back(std::move(mappings[i])); }
+    return result;
 }
 
 // ---------------------------------------------------------------------------------------
@@ -673,7 +676,7 @@ int pack_alignment(const Alignment& a, uint32_t read_id, gb_alignment* rec, gb_m
                    uint32_t* edits, uint32_t edit_cap, uint32_t mapping_base, uint32_t edit_base) {
     rec->read_id = read_id; rec->score = a.score;
     rec->mapq = (uint8_t)a.mapq;
-    rec->flags = (a.path.empty() ? 0 : GB_ALN_MAPPED) | (a.rescued ? GB_ALN_RESCUED : 0);
+    rec->flags = (a.path.empty() ? 0 : GB_ALN_MAPPED) | (a.rescued ? GB_ALN_RESCUED : 0) | (a.secondary ? GB_ALN_SECONDARY : 0);
     rec->mapping_off = mapping_base; rec->edit_off = edit_base;
     rec->mapq_uncapped = (float)a.mapq_uncapped; rec->mapq_explored_cap = (float)a.mapq_explored_cap;
     if (a.path.size() > mapping_cap) return -1;
@@ -693,6 +696,25 @@ int pack_alignment(const Alignment& a, uint32_t read_id, gb_alignment* rec, gb_m
     }
     rec->n_mappings = (uint16_t)a.path.size(); rec->n_edits = ne;
     return 0;
+}
+
+// Records of ranks 1 .. max_multimaps - 1 of read r (rank-major layout of gb_map_batch: record j * n_reads + r).
+int pack_secondaries(const Alignment& primary, const gb_map_params& P, uint32_t n_reads, uint32_t r, uint32_t extra_flags,
+                     gb_alignment* aln, gb_mapping* mappings, uint32_t* edits) {
+    int rc = 0;
+    for (uint32_t j = 1; j < P.max_multimaps; j++) {
+        const size_t R = (size_t)j * n_reads + r;
+        if (j - 1 < primary.secondaries.size()) {
+            rc |= pack_alignment(primary.secondaries[j - 1], r, aln + R, mappings + R * P.mapping_cap_per_read, P.mapping_cap_per_read,
+                                 edits + R * P.edit_cap_per_read, P.edit_cap_per_read, (uint32_t)(R * P.mapping_cap_per_read), (uint32_t)(R * P.edit_cap_per_read));
+            aln[R].flags |= extra_flags;
+        } else {
+            memset(aln + R, 0, sizeof(gb_alignment));
+            aln[R].read_id = r; aln[R].flags = GB_ALN_ABSENT;
+            aln[R].mapping_off = (uint32_t)(R * P.mapping_cap_per_read); aln[R].edit_off = (uint32_t)(R * P.edit_cap_per_read);
+        }
+    }
+    return rc;
 }
 
 } // namespace oracle
@@ -730,6 +752,7 @@ extern "C" int oracle_map_batch(const gb_flat_index* ix, const gb_scores* scores
                                             p->mapping_cap_per_read, edits + (size_t)r * p->edit_cap_per_read,
                                             p->edit_cap_per_read, (uint32_t)(r * p->mapping_cap_per_read),
                                             (uint32_t)(r * p->edit_cap_per_read));
+            rc |= oracle::pack_secondaries(a, *p, n_reads, (uint32_t)r, 0, aln, mappings, edits);
             status[r] = rc == 0 ? GB_ITEM_OK : GB_ITEM_OUT_FULL;
             if (rc) {
 #pragma omp atomic

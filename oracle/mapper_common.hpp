@@ -107,6 +107,8 @@ struct Alignment {
     double mapq = 0;
     double mapq_uncapped = 0, mapq_explored_cap = 0;
     bool rescued = false;
+    bool secondary = false;                    // set_is_secondary (:1205, :2555)
+    std::vector<Alignment> secondaries;        // on a primary: mappings 1 .. max_multimaps - 1 in output order
 };
 
 // MinimizerMapper::Minimizer, minimizer_mapper.hpp:565-621

@@ -33,6 +33,8 @@ int score_extension_group(size_t seq_len, const std::vector<GaplessExtension>& e
 double faster_cap(const std::vector<Minimizer>& minimizers, std::vector<size_t>& explored, const std::string& sequence, const std::string& quality);
 Alignment map_from_extensions(const gb_flat_index* ix, const gb_scores& scores, const gb_map_params& P,
                               const std::string& sequence, const std::string& quality, MapCounters* counters);
+int pack_secondaries(const Alignment& primary, const gb_map_params& P, uint32_t n_reads, uint32_t r, uint32_t extra_flags,
+                     gb_alignment* aln, gb_mapping* mappings, uint32_t* edits);
 int pack_alignment(const Alignment& a, uint32_t read_id, gb_alignment* rec, gb_mapping* mappings, uint32_t mapping_cap,
                    uint32_t* edits, uint32_t edit_cap, uint32_t mapping_base, uint32_t edit_base);
 
@@ -465,6 +467,8 @@ PairResult map_paired(const gb_flat_index* ix, const gb_scores& scores, const gb
         out.mapq = (double)(int32_t)read_mapq;          // Alignment.mapping_quality is int32
         out.mapq_uncapped = uncapped_mapq; out.mapq_explored_cap = mapq_cap;
         result.aln[r] = out;
+        // pairs 1 .. max_multimaps - 1 are secondary for both reads (:2552-2557)
+        for (size_t i = 1; i < mappings[r].size(); i++) { mappings[r][i].secondary = true; result.aln[r].secondaries.push_back(mappings[r][i]); }
     }
     return result;
 }
@@ -497,6 +501,7 @@ extern "C" int oracle_map_paired_batch(const gb_flat_index* ix, const gb_scores*
                                                 p->mapping_cap_per_read, edits + (size_t)ri * p->edit_cap_per_read, p->edit_cap_per_read,
                                                 (uint32_t)(ri * p->mapping_cap_per_read), (uint32_t)(ri * p->edit_cap_per_read));
                 aln[ri].flags |= GB_ALN_PAIRED;
+                rc |= oracle::pack_secondaries(res.aln[r], *p, n_reads, (uint32_t)ri, GB_ALN_PAIRED, aln, mappings, edits);
                 status[ri] = rc == 0 ? GB_ITEM_OK : GB_ITEM_OUT_FULL;
                 if (rc) {
 #pragma omp atomic
@@ -524,7 +529,7 @@ extern "C" int oracle_map_paired_job(const gb_flat_index* ix, const gb_scores* s
                                      uint32_t n_reads, const uint8_t* reads, const uint8_t* quals, const uint64_t* read_off,
                                      gb_alignment* aln, gb_mapping* mappings, uint32_t* edits, uint8_t* status, uint8_t* route,
                                      int n_threads, double* frag_out) {
-    if (n_reads % 2 != 0) return -2;
+    if (n_reads % 2 != 0 || p_in->max_multimaps != 1) return -2;
     using namespace oracle;
     gb_map_params P = *p_in;
     FragmentLengthDistribution distr(maximum_sample_size, reestimation_frequency, robust_estimation_fraction);

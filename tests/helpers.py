@@ -192,9 +192,10 @@ def oracle_map(index, reads, quals=None, params=None, scores=None, threads=1):
     scores = scores or capi.DEFAULT_SCORES
     rbuf, qbuf, read_off = pack_reads(reads, quals)
     n = len(read_off) - 1
-    aln = np.zeros(n, dtype=alignment_dt)
-    maps = np.zeros(n * p.mapping_cap_per_read, dtype=mapping_dt)
-    edits = np.zeros(n * p.edit_cap_per_read, dtype=np.uint32)
+    k = max(1, int(p.max_multimaps))
+    aln = np.zeros(n * k, dtype=alignment_dt)
+    maps = np.zeros(n * k * p.mapping_cap_per_read, dtype=mapping_dt)
+    edits = np.zeros(n * k * p.edit_cap_per_read, dtype=np.uint32)
     status = np.zeros(n, dtype=np.uint8)
     counters = np.zeros(len(COUNTER_NAMES), dtype=np.uint64)
     rc = lib.oracle_map_batch(C.byref(index.view), C.byref(scores), C.byref(p), n, capi.ptr(rbuf),
@@ -223,18 +224,21 @@ def gpu_map(dev, reads, quals=None, params=None, paired=False):
     return dev.map_arrays(rbuf, qbuf, read_off, params, paired=paired)
 
 
-def compare_alignments(got, want, n, mapq_tol=1, indices=None):
+def compare_alignments(got, want, n, mapq_tol=1, indices=None, k=1):
     """got / want = (aln, maps, edits, status[, counters]).  Scores, paths and edits must be
-    identical; MAPQ within +-mapq_tol (FP64 libm differences, BASELINE.json north_star)."""
+    identical; MAPQ within +-mapq_tol (FP64 libm differences, BASELINE.json north_star).
+    k = max_multimaps: the n * k rank-major records are all compared, and so are their mapped / secondary / absent flags."""
     ga, gm, ge, gs = got[:4]
     wa, wm, we, ws = want[:4]
     bad = []
-    for i in (range(n) if indices is None else indices):
-        assert gs[i] == 0, f"read {i}: GPU status {gs[i]}"
-        assert ws[i] == 0
+    which = 1 if k == 1 else (1 | 2 | 16)
+    for i in (range(n * k) if indices is None else indices):
+        assert gs[i % n] == 0, f"read {i % n}: GPU status {gs[i % n]}"
+        assert ws[i % n] == 0
         gd = decode_alignment(ga[i], gm, ge)
         wd = decode_alignment(wa[i], wm, we)
-        if gd[0] != wd[0] or gd[2] != wd[2] or abs(gd[1] - wd[1]) > mapq_tol or (ga[i]["flags"] & 1) != (wa[i]["flags"] & 1):
+        if gd[0] != wd[0] or gd[2] != wd[2] or abs(gd[1] - wd[1]) > mapq_tol or (ga[i]["flags"] & which) != (wa[i]["flags"] & which) or \
+                (k > 1 and int(ga[i]["read_id"]) != int(wa[i]["read_id"])):
             bad.append((i, gd, wd))
     return bad
 
@@ -242,9 +246,10 @@ def compare_alignments(got, want, n, mapq_tol=1, indices=None):
 def oracle_out_buffers(n, p):
     """Pre-touched output buffers for oracle_map*/oracle_map_paired (reusable across calls so a timed
     CPU run does not pay first-touch page faults)."""
-    aln = np.zeros(n, dtype=alignment_dt)
-    maps = np.zeros(n * p.mapping_cap_per_read, dtype=mapping_dt)
-    edits = np.zeros(n * p.edit_cap_per_read, dtype=np.uint32)
+    k = max(1, int(p.max_multimaps))
+    aln = np.zeros(n * k, dtype=alignment_dt)
+    maps = np.zeros(n * k * p.mapping_cap_per_read, dtype=mapping_dt)
+    edits = np.zeros(n * k * p.edit_cap_per_read, dtype=np.uint32)
     status = np.zeros(n, dtype=np.uint8)
     for a in (aln, maps, edits, status):
         a.view(np.uint8).reshape(-1)[::4096] = 0
@@ -268,7 +273,7 @@ def oracle_map_paired(index, reads, quals=None, params=None, scores=None, thread
                                      capi.ptr(qbuf) if qbuf is not None else None, capi.ptr(read_off), capi.ptr(aln),
                                      capi.ptr(maps), capi.ptr(edits), capi.ptr(status), threads, capi.ptr(counters))
     assert rc == 0, f"oracle_map_paired_batch rc {rc}"
-    return aln[:n], maps, edits, status[:n], dict(zip(COUNTER_NAMES, (int(c) for c in counters)))
+    return aln[:n * max(1, int(p.max_multimaps))], maps, edits, status[:n], dict(zip(COUNTER_NAMES, (int(c) for c in counters)))
 
 
 def paired_params(mean=400.0, stdev=50.0):

@@ -19,7 +19,8 @@ GB_OK = 0
 GB_ERR_ARG, GB_ERR_CUDA, GB_ERR_NO_DEVICE, GB_ERR_CAPACITY, GB_ERR_FORMAT = -1, -2, -3, -4, -5
 GB_ITEM_OK, GB_ITEM_QUEUE_FULL, GB_ITEM_OUT_FULL, GB_ITEM_DP_REFUSED = 0, 1, 2, 3
 GB_EXT_LEFT_FULL, GB_EXT_RIGHT_FULL = 1, 2
-GB_ALN_MAPPED, GB_ALN_SECONDARY, GB_ALN_PAIRED, GB_ALN_RESCUED = 1, 2, 4, 8
+GB_ALN_MAPPED, GB_ALN_SECONDARY, GB_ALN_PAIRED, GB_ALN_RESCUED, GB_ALN_ABSENT = 1, 2, 4, 8, 16
+GB_MAX_MULTIMAPS = 8
 
 # numpy mirrors of the ABI structs
 node_rec_dt = np.dtype([("seq_off", "<u4"), ("rec_off", "<u4"), ("len", "<u4"), ("size", "<u4")])
@@ -689,10 +690,11 @@ class Device:
         lib = load_library()
         p = params or default_map_params()
         n = len(read_off) - 1
+        k = max(1, int(p.max_multimaps))              # aln holds n * max_multimaps records, rank-major (record j * n + read)
         if out is None:
-            aln = np.zeros(n, dtype=alignment_dt)
-            maps = np.zeros(n * 24 + 1024, dtype=mapping_dt)
-            edits = np.zeros(n * 32 + 1024, dtype=np.uint32)
+            aln = np.zeros(n * k, dtype=alignment_dt)
+            maps = np.zeros(n * k * 24 + 1024, dtype=mapping_dt)
+            edits = np.zeros(n * k * 32 + 1024, dtype=np.uint32)
             status = np.zeros(n, dtype=np.uint8)
         else:
             aln, maps, edits, status = out
@@ -701,8 +703,8 @@ class Device:
         rc = fn(self._h, C.byref(p), n, ptr(rbuf), ptr(qbuf) if qbuf is not None else None, ptr(read_off), ptr(aln),
                 ptr(maps), len(maps), ptr(edits), len(edits), ptr(status), C.byref(used[0]), C.byref(used[1]))
         if rc == GB_ERR_CAPACITY and out is None:
-            maps = np.zeros(n * p.mapping_cap_per_read, dtype=mapping_dt)
-            edits = np.zeros(n * p.edit_cap_per_read, dtype=np.uint32)
+            maps = np.zeros(n * k * p.mapping_cap_per_read, dtype=mapping_dt)
+            edits = np.zeros(n * k * p.edit_cap_per_read, dtype=np.uint32)
             rc = fn(self._h, C.byref(p), n, ptr(rbuf), ptr(qbuf) if qbuf is not None else None, ptr(read_off), ptr(aln),
                     ptr(maps), len(maps), ptr(edits), len(edits), ptr(status), C.byref(used[0]), C.byref(used[1]))
         if rc != GB_OK:

@@ -91,6 +91,7 @@ __device__ inline bool fast_pair(const DevIndex& ix, const MapParamsDev& P, cons
     const ReadState rs0 = b.states[2 * p], rs1 = b.states[2 * p + 1];
     const ReadState* rsp[2] = {&rs0, &rs1};
     if (rs0.status != GB_ITEM_OK) return false;                 // let the slow kernel report it
+    if (P.max_multimaps > 1) return false;                      // secondaries are written by the warp kernels only
     if (rs1.pad[0] > 1) return false;                           // deferred cluster selection of read 2 (rare: tied clusters): warp kernel
     const PairState ps = a.pairs[p];
     if (ps.n_fragments + 1 > MAX_FRAGMENTS) return false;
@@ -269,6 +270,7 @@ __device__ inline bool fast_pair(const DevIndex& ix, const MapParamsDev& P, cons
 __device__ inline bool fast_read(const DevIndex& ix, const MapParamsDev& P, const DevScores& sc, const MapBatch& b, const AlignArgs& a, uint32_t r) {
     const ReadState rs = b.states[r];
     if (rs.status != GB_ITEM_OK) return false;
+    if (P.max_multimaps > 1) return false;                      // secondaries are written by the warp kernels only
     DevRng rng = rs.rng;
     const uint64_t rb = b.read_off[r];
     const uint32_t L = (uint32_t)(b.read_off[r + 1] - rb);

@@ -562,9 +562,9 @@ __device__ inline uint32_t finalize_se(const DevIndex& ix, const MapParamsDev& P
     const uint32_t map_cap = P.mapping_cap, edit_cap = P.edit_cap;
     double scores_sorted[MAX_CANDS + 1];
     uint32_t n_scores = 0; uint32_t win = 0xffffffffu;
+    uint8_t co[MAX_CANDS];
     if (cl.n == 0) { scores_sorted[0] = 0.0; n_scores = 1; }
     else {
-        uint8_t co[MAX_CANDS];
 #pragma unroll 1
         for (uint32_t c = 0; c < cl.n; c++) { uint32_t j = c; while (j > 0 && cl.score[c] > cl.score[co[j - 1]]) { co[j] = co[j - 1]; j--; } co[j] = (uint8_t)c; }
         uint32_t ties = 0;
@@ -596,6 +596,23 @@ __device__ inline uint32_t finalize_se(const DevIndex& ix, const MapParamsDev& P
         out.score = cl.score[win]; out.flags = nm ? GB_ALN_MAPPED : 0; out.n_mappings = (uint16_t)nm; out.n_edits = ne;
         if (lane == 0) write_alignment(ix, pb, nm, ne, sread, L, false, out_maps, out_edits);
     }
+    // mappings 1 .. max_multimaps - 1 in the same order (:1095-1130, :1199-1206): secondaries, no MAPQ of their own
+#pragma unroll 1
+    for (uint32_t j = 1; j < P.max_multimaps && j < cl.n; j++) {
+        const uint32_t c = co[j];
+        PathBuf pb = slot_buf(cand_base, cl.slot[c], map_cap, edit_cap);
+        const uint32_t nm = slot_nm(pb), ne = slot_ne(pb);
+        if (nm + 1 > map_cap || ne > edit_cap) return GB_ITEM_OUT_FULL;
+        const size_t R = (size_t)j * P.out_stride + read_idx;
+        if (lane == 0) {
+            gb_alignment sec;
+            sec.read_id = read_idx; sec.score = cl.score[c]; sec.mapq = 0; sec.flags = (nm ? GB_ALN_MAPPED : 0) | GB_ALN_SECONDARY;
+            sec.n_mappings = (uint16_t)nm; sec.n_edits = ne; sec.mapping_off = (uint32_t)(R * map_cap); sec.edit_off = (uint32_t)(R * edit_cap);
+            sec.mapq_uncapped = 0.f; sec.mapq_explored_cap = 0.f;
+            write_alignment(ix, pb, nm, ne, sread, L, false, a.maps + R * map_cap, a.edits + R * edit_cap);
+            a.aln[R] = sec;
+        }
+    }
     __syncwarp();
     return GB_ITEM_OK;
 }
@@ -619,6 +636,42 @@ __device__ inline int64_t oriented_distance(const DevIndex& ix, uint32_t node_a,
     if (ps.z < pd.z) return (src_len - src_off) + ((int64_t)pd.x - (int64_t)ps.y) + dst_off;
     if (ps.z == pd.z) { const int64_t t = site_distance(ix, ps, pd); if (t >= 0) return (src_len - src_off) + t + dst_off; }
     return UNREACHABLE;
+}
+
+// Pairs 1 .. max_multimaps - 1 of a pair in output order (:2505-2598): both reads of such a pair are secondary
+// (:2552-2557) and carry no MAPQ.  Records of rank j live at j * P.out_stride + read.  rescue_frag = the fragment slot of
+// rescued alignments (0xffffffff: none).  Capacities are checked before anything is written.
+__device__ inline uint32_t write_secondary_pairs(const DevIndex& ix, const MapParamsDev& P, const AlignArgs& a, const CandList& cl,
+                                                 const uint8_t* po, uint32_t n_pairs, const uint8_t* pair_c0, const uint8_t* pair_c1, uint32_t rescue_frag,
+                                                 const uint8_t* const* sread, const uint32_t* L, uint32_t read_idx0, uint8_t* cand_base) {
+    const int lane = lane_id();
+    const uint32_t map_cap = P.mapping_cap, edit_cap = P.edit_cap;
+    const uint32_t n_out = min(P.max_multimaps, n_pairs);
+#pragma unroll 1
+    for (uint32_t pass = 0; pass < 2; pass++) {
+#pragma unroll 1
+        for (uint32_t j = 1; j < n_out; j++) {
+#pragma unroll 1
+            for (uint32_t r = 0; r < 2; r++) {
+                const uint32_t c = r == 0 ? pair_c0[po[j]] : pair_c1[po[j]];
+                PathBuf pb = slot_buf(cand_base, cl.slot[c], map_cap, edit_cap);
+                const uint32_t nm = slot_nm(pb), ne = slot_ne(pb);
+                if (pass == 0) { if (nm + 1 > map_cap || ne > edit_cap) return GB_ITEM_OUT_FULL; continue; }
+                const size_t R = (size_t)j * P.out_stride + read_idx0 + r;
+                if (lane == 0) {
+                    gb_alignment sec;
+                    sec.read_id = read_idx0 + r; sec.score = cl.score[c]; sec.mapq = 0;
+                    sec.flags = GB_ALN_PAIRED | GB_ALN_SECONDARY | (nm ? GB_ALN_MAPPED : 0) | (cl.frag[c] == rescue_frag ? GB_ALN_RESCUED : 0);
+                    sec.n_mappings = (uint16_t)nm; sec.n_edits = ne; sec.mapping_off = (uint32_t)(R * map_cap); sec.edit_off = (uint32_t)(R * edit_cap);
+                    sec.mapq_uncapped = 0.f; sec.mapq_explored_cap = 0.f;
+                    if (nm) write_alignment(ix, pb, nm, ne, sread[r], L[r], r == 1, a.maps + R * map_cap, a.edits + R * edit_cap);
+                    a.aln[R] = sec;
+                }
+            }
+        }
+    }
+    __syncwarp();
+    return GB_ITEM_OK;
 }
 
 // ---- paired-end: pairing, winner, MAPQ, two records (max_rescue_attempts = 0) ------------------------------------
@@ -750,6 +803,7 @@ __device__ inline uint32_t finalize_pe(const DevIndex& ix, const MapParamsDev& P
         if (lane == 0) write_alignment(ix, pb, nm, ne, sread[r], L[r], r == 1, out_maps[r], out_edits[r]);
     }
     __syncwarp();
+    if (P.max_multimaps > 1) return write_secondary_pairs(ix, P, a, cl, po, n_pairs, pair_c0, pair_c1, 0xffffffffu, sread, L, read_idx0, cand_base);
     return GB_ITEM_OK;
 }
 

@@ -8,7 +8,8 @@ struct CountMappings { const gb_alignment* a; __host__ __device__ uint64_t opera
 struct CountEdits { const gb_alignment* a; __host__ __device__ uint64_t operator()(uint32_t i) const { return a[i].n_edits; } };
 
 // One warp per read: copy its mappings / edits to their scanned offsets and patch the header.
-__global__ void compact_gather_kernel(uint32_t n_reads, gb_alignment* aln, const gb_mapping* maps, const uint32_t* edits,
+// n_reads = records (reads x max_multimaps, rank-major: record j * per_rank + read), per_rank = reads of the chunk.
+__global__ void compact_gather_kernel(uint32_t n_reads, uint32_t per_rank, gb_alignment* aln, const gb_mapping* maps, const uint32_t* edits,
                                       uint32_t map_cap, uint32_t edit_cap, const uint64_t* map_off, const uint64_t* edit_off,
                                       gb_mapping* out_maps, uint64_t out_map_cap, uint32_t* out_edits, uint64_t out_edit_cap,
                                       const uint64_t* run_base, uint32_t read_base, uint64_t* totals, uint8_t* status) {
@@ -26,11 +27,21 @@ __global__ void compact_gather_kernel(uint32_t n_reads, gb_alignment* aln, const
             for (uint32_t i = lane; i < a.n_edits; i += 32) out_edits[eo + i] = se[i];
         }
         if (lane == 0) {
-            a.mapping_off = (uint32_t)(map_base + mo); a.edit_off = (uint32_t)(edit_base + eo); a.read_id = read_base + r;
-            if (!fits) { a.n_mappings = 0; a.n_edits = 0; a.flags &= ~GB_ALN_MAPPED; a.score = 0; a.mapq = 0; status[r] = GB_ITEM_OUT_FULL; }
+            a.mapping_off = (uint32_t)(map_base + mo); a.edit_off = (uint32_t)(edit_base + eo); a.read_id = read_base + r % per_rank;
+            if (!fits) { a.n_mappings = 0; a.n_edits = 0; a.flags &= ~GB_ALN_MAPPED; a.score = 0; a.mapq = 0; status[r % per_rank] = GB_ITEM_OUT_FULL; }
             aln[r] = a;
             if (r == n_reads - 1) { totals[0] = mo + a.n_mappings; totals[1] = eo + a.n_edits; }
         }
+    }
+}
+
+// max_multimaps > 1: every record of rank >= 1 starts out absent; the align kernels overwrite the ones that exist.
+__global__ void init_absent_kernel(gb_alignment* aln, uint32_t per_rank, uint32_t n_records, uint32_t map_cap, uint32_t edit_cap) {
+    for (uint32_t R = per_rank + blockIdx.x * blockDim.x + threadIdx.x; R < n_records; R += gridDim.x * blockDim.x) {
+        gb_alignment a;
+        a.read_id = R % per_rank; a.score = 0; a.mapq = 0; a.flags = GB_ALN_ABSENT; a.n_mappings = 0; a.mapping_off = R * map_cap; a.edit_off = R * edit_cap;
+        a.n_edits = 0; a.mapq_uncapped = 0.f; a.mapq_explored_cap = 0.f;
+        aln[R] = a;
     }
 }
 
@@ -43,7 +54,7 @@ __global__ void rebase_offsets_kernel(uint64_t* off, uint32_t n, uint64_t b0) {
 
 // Scans + gather on the handle's stream.  d_totals[0..1] receive the mappings / edits used by
 // this chunk.  Temporary storage comes from the handle.
-inline int compact_outputs(gb_device* d, uint32_t n_reads, gb_alignment* d_aln, const gb_mapping* d_maps, const uint32_t* d_edits,
+inline int compact_outputs(gb_device* d, uint32_t n_reads, uint32_t per_rank, gb_alignment* d_aln, const gb_mapping* d_maps, const uint32_t* d_edits,
                            uint32_t map_cap, uint32_t edit_cap, gb_mapping* out_maps, uint64_t out_map_cap, uint32_t* out_edits,
                            uint64_t out_edit_cap, const uint64_t* d_run_base, uint32_t read_base, uint64_t* d_totals, uint8_t* d_status) {
     int rc;
@@ -61,7 +72,7 @@ inline int compact_outputs(gb_device* d, uint32_t n_reads, gb_alignment* d_aln, 
     GB_CUDA(cub::DeviceScan::ExclusiveSum(d->c_tmp.ptr, tb, it_e, d->c_edit_off.ptr, (int)n_reads, d->stream));
     d->launches += 2;
     const uint32_t grid = std::min<uint32_t>((uint32_t)d->n_sms * 8, (n_reads + 7) / 8);
-    compact_gather_kernel<<<grid ? grid : 1, 256, 0, d->stream>>>(n_reads, d_aln, d_maps, d_edits, map_cap, edit_cap, d->c_map_off.ptr,
+    compact_gather_kernel<<<grid ? grid : 1, 256, 0, d->stream>>>(n_reads, per_rank, d_aln, d_maps, d_edits, map_cap, edit_cap, d->c_map_off.ptr,
                                                                d->c_edit_off.ptr, out_maps, out_map_cap, out_edits, out_edit_cap,
                                                                d_run_base, read_base, d_totals, d_status);
     d->launches++;

@@ -15,6 +15,7 @@
 #include <cstdio>
 #include <cstring>
 #include <string>
+#include <vector>
 
 namespace {
 
@@ -101,6 +102,7 @@ static int gb_emit_gaf_impl(const gb_flat_index* ix, uint32_t n, const gb_alignm
     Out o{out, out_cap, 0, false};
     for (uint32_t x = 0; x < n; x++) {
         const gb_alignment& a = aln[x];
+        if (a.flags & GB_ALN_ABSENT) continue;                   // max_multimaps > 1: this read has fewer mappings than ranks
         const uint32_t r = a.read_id;
         const uint8_t* seq = reads + read_off[r];
         const uint32_t L = (uint32_t)(read_off[r + 1] - read_off[r]);
@@ -166,6 +168,7 @@ static int gb_emit_json_impl(const gb_flat_index* ix, uint32_t n, const gb_align
     Out o{out, out_cap, 0, false};
     for (uint32_t x = 0; x < n; x++) {
         const gb_alignment& a = aln[x];
+        if (a.flags & GB_ALN_ABSENT) continue;
         const uint32_t r = a.read_id;
         const uint8_t* seq = reads + read_off[r];
         const uint32_t L = (uint32_t)(read_off[r + 1] - read_off[r]);
@@ -198,6 +201,7 @@ static int gb_emit_json_impl(const gb_flat_index* ix, uint32_t n, const gb_align
         if (quals) { o.str(", \"quality\": \""); base64(o, quals + read_off[r], L); o.ch('"'); }
         if (a.mapq) { o.str(", \"mapping_quality\": "); o.num(a.mapq); }
         if (a.score) { o.str(", \"score\": "); o.num(a.score); }
+        if (a.flags & GB_ALN_SECONDARY) o.str(", \"is_secondary\": true");        // set_is_secondary, minimizer_mapper.cpp:1205, :2555
         if ((a.flags & GB_ALN_MAPPED) && L) { o.str(", \"identity\": "); o.real((double)matches / (double)L); }      // identity(path), alignment.cpp
         if (a.flags & GB_ALN_PAIRED) {
             if ((r & 1u) == 0) { o.str(", \"fragment_next\": {\"name\": "); json_string(o, read_name(names, name_off, r + 1)); o.ch('}'); }
@@ -245,12 +249,16 @@ static int gb_emit_gam_impl(const gb_flat_index* ix, uint32_t n, const gb_alignm
     if (!records_valid(ix, n, aln, mappings, mapping_pool_len, edits, edit_pool_len, n_reads, read_off, names, name_off)) return GB_ERR_ARG;
     Out o{out, out_cap, 0, false};
     const uint32_t GROUP = 1000;                 // messages per group
-    for (uint32_t g0 = 0; g0 < n; g0 += GROUP) {
-        const uint32_t gn = std::min(GROUP, n - g0);
+    std::vector<uint32_t> present;               // max_multimaps > 1: ranks a read does not have are skipped
+    present.reserve(n);
+    for (uint32_t x = 0; x < n; x++) if (!(aln[x].flags & GB_ALN_ABSENT)) present.push_back(x);
+    const uint32_t np = (uint32_t)present.size();
+    for (uint32_t g0 = 0; g0 < np; g0 += GROUP) {
+        const uint32_t gn = std::min(GROUP, np - g0);
         std::string group;
         pb_varint(group, (uint64_t)gn + 1); pb_varint(group, 3); group += "GAM";
-        for (uint32_t x = g0; x < g0 + gn; x++) {
-            const gb_alignment& a = aln[x];
+        for (uint32_t y = g0; y < g0 + gn; y++) {
+            const gb_alignment& a = aln[present[y]];
             const uint32_t r = a.read_id;
             const char* seq = (const char*)reads + read_off[r];
             const uint32_t L = (uint32_t)(read_off[r + 1] - read_off[r]);
@@ -290,6 +298,7 @@ static int gb_emit_gam_impl(const gb_flat_index* ix, uint32_t n, const gb_alignm
                 std::string frag; pb_bytes(frag, 3, mate.data(), mate.size());
                 pb_msg(msg, (r & 1u) ? 11 : 12, frag);
             }
+            if (a.flags & GB_ALN_SECONDARY) pb_uint(msg, 15, 1);           // vg.proto Alignment.is_secondary = 15
             if ((a.flags & GB_ALN_MAPPED) && L) pb_double(msg, 16, (double)matches / (double)L);
             std::string st, v;
             v.clear(); pb_double(v, 2, (double)a.mapq_uncapped); pb_annotation(st, "mapq_uncapped", v);

@@ -215,15 +215,17 @@ int map_device(gb_device* d, const gb_map_params* hp, uint32_t n_reads, const ui
                gb_mapping* out_maps, uint64_t out_map_cap, uint32_t* out_edits, uint64_t out_edit_cap,
                const uint64_t* d_run_base, uint32_t read_base, uint64_t* d_totals, uint32_t* d_overflow) {
     int rc0;
-    if ((rc0 = d->pad_maps.reserve((size_t)n_reads * hp->mapping_cap_per_read))) return rc0;
-    if ((rc0 = d->pad_edits.reserve((size_t)n_reads * hp->edit_cap_per_read))) return rc0;
+    if (hp->max_multimaps == 0 || hp->max_multimaps > GB_MAX_MULTIMAPS) { g_last_error = "max_multimaps must be 1 .. GB_MAX_MULTIMAPS"; return GB_ERR_ARG; }
+    const uint32_t K = hp->max_multimaps;            // records per read, rank-major: record j * n_reads + read
+    if ((uint64_t)n_reads * K * std::max(hp->mapping_cap_per_read, hp->edit_cap_per_read) > 0xffffffffull) { g_last_error = "chunk too large for 32-bit record offsets (reads x max_multimaps x cap)"; return GB_ERR_ARG; }
+    if ((rc0 = d->pad_maps.reserve((size_t)n_reads * K * hp->mapping_cap_per_read))) return rc0;
+    if ((rc0 = d->pad_edits.reserve((size_t)n_reads * K * hp->edit_cap_per_read))) return rc0;
     gb_mapping* d_maps = d->pad_maps.ptr; uint32_t* d_edits = d->pad_edits.ptr;
     if (paired) {
         if (n_reads % 2 != 0) { g_last_error = "paired mapping needs an even number of reads"; return GB_ERR_ARG; }
         if (hp->max_rescue_attempts != 0 && hp->rescue_seed_limit >= RESCUE_SEEDS) { g_last_error = "rescue_seed_limit must be below 128"; return GB_ERR_ARG; }
         if (!(hp->fragment_stdev > 0)) { g_last_error = "paired mapping needs a forced fragment length distribution"; return GB_ERR_ARG; }
     }
-    if (hp->max_multimaps != 1) { g_last_error = "only max_multimaps = 1 is supported"; return GB_ERR_ARG; }
     const uint32_t Lc = std::max<uint32_t>(32u, (max_len + 15u) & ~15u);
     if (Lc > 512) { g_last_error = "reads longer than 512 bp are not supported by the short-read path"; return GB_ERR_ARG; }
     int rc;
@@ -252,6 +254,7 @@ int map_device(gb_device* d, const gb_map_params* hp, uint32_t n_reads, const ui
     P.extension_set_min_score = hp->extension_set_min_score; P.max_alignments = hp->max_alignments;
     P.max_extension_mismatches = hp->max_extension_mismatches; P.max_dozeu_cells = hp->max_dozeu_cells; P.do_dp = hp->do_dp;
     P.mapping_cap = hp->mapping_cap_per_read; P.edit_cap = hp->edit_cap_per_read;
+    P.max_multimaps = K; P.out_stride = n_reads;
     P.log_base = recover_log_base(d->sc);
     P.max_rescue_attempts = paired ? hp->max_rescue_attempts : 0; P.rescue_seed_limit = hp->rescue_seed_limit;
     P.paired_rescue_score_limit = hp->paired_rescue_score_limit; P.rescue_subgraph_stdevs = hp->rescue_subgraph_stdevs;
@@ -278,6 +281,11 @@ int map_device(gb_device* d, const gb_map_params* hp, uint32_t n_reads, const ui
     // 30 result path words, 31 decide work, 32-43 tile work
     uint32_t* cur = d->p_cursors.ptr;
     d->kt_reset();
+    if (K > 1) {
+        init_absent_kernel<<<d->n_sms * 4, 256, 0, d->stream>>>(d_aln, n_reads, n_reads * K, hp->mapping_cap_per_read, hp->edit_cap_per_read);
+        d->launches++;
+        GB_CUDA(cudaGetLastError());
+    }
 
     int32_t fragment_limit = 0;
     if (paired) {
@@ -492,7 +500,7 @@ int map_device(gb_device* d, const gb_map_params* hp, uint32_t n_reads, const ui
         if ((rc = d->kt_mark(!paired ? "align_kernel" : (rescue ? "align_kernel_pe<rescue>" : "align_kernel_pe")))) return rc;
     }
     GB_CUDA(cudaEventRecord(d->ev_stage[3], d->stream));
-    if ((rc = compact_outputs(d, n_reads, d_aln, d_maps, d_edits, hp->mapping_cap_per_read, hp->edit_cap_per_read,
+    if ((rc = compact_outputs(d, n_reads * K, n_reads, d_aln, d_maps, d_edits, hp->mapping_cap_per_read, hp->edit_cap_per_read,
                               out_maps, out_map_cap, out_edits, out_edit_cap, d_run_base, read_base, d_totals, d_status))) return rc;
     if ((rc = d->kt_mark("compact (2 scans + gather)"))) return rc;
     if (d_overflow) GB_CUDA(cudaMemcpyAsync(d_overflow, cur + 13, sizeof(uint32_t), cudaMemcpyDeviceToDevice, d->stream));
@@ -513,6 +521,8 @@ static int map_batch_host(gb_device* d, const gb_map_params* hp, bool paired,
     if (n_mappings_used) *n_mappings_used = 0;
     if (n_edits_used) *n_edits_used = 0;
     if (n_reads == 0) return GB_OK;
+    if (hp->max_multimaps == 0 || hp->max_multimaps > GB_MAX_MULTIMAPS) { g_last_error = "max_multimaps must be 1 .. GB_MAX_MULTIMAPS"; return GB_ERR_ARG; }
+    const uint32_t K = hp->max_multimaps;
     if (paired && n_reads % 2 == 0) {
         // A distribution the clusterer cannot use (fragment limit below the read limit): the reference maps both
         // ends single-ended and emits them as a pair (minimizer_mapper.cpp:1469-1496).  The test is per pair
@@ -526,7 +536,7 @@ static int map_batch_host(gb_device* d, const gb_map_params* hp, bool paired,
         if (fallback == n_reads / 2) {
             const int rcs = map_batch_host(d, hp, false, n_reads, reads, quals, read_off, aln, mappings, mapping_pool_cap, edits, edit_pool_cap,
                                            status, n_mappings_used, n_edits_used);
-            if (rcs == GB_OK) for (uint32_t r = 0; r < n_reads; r++) aln[r].flags |= GB_ALN_PAIRED;
+            if (rcs == GB_OK) for (size_t r = 0; r < (size_t)n_reads * K; r++) if (!(aln[r].flags & GB_ALN_ABSENT)) aln[r].flags |= GB_ALN_PAIRED;
             return rcs;
         }
         if (fallback != 0) { g_last_error = "fragment distance limit below the read distance limit for some pairs only (mixed single-end fallback, minimizer_mapper.cpp:1471, is not supported in one batch)"; return GB_ERR_ARG; }
@@ -576,14 +586,14 @@ static int map_batch_host(gb_device* d, const gb_map_params* hp, bool paired,
         const uint64_t b0 = read_off[c0], b1 = read_off[c0 + cn], total = b1 - b0;
         uint32_t max_len = 0;
         for (uint32_t r = 0; r < cn; r++) max_len = std::max<uint32_t>(max_len, (uint32_t)(read_off[c0 + r + 1] - read_off[c0 + r]));
-        const uint64_t chunk_map_cap = (uint64_t)cn * hp->mapping_cap_per_read, chunk_edit_cap = (uint64_t)cn * hp->edit_cap_per_read;
+        const uint64_t chunk_map_cap = (uint64_t)cn * K * hp->mapping_cap_per_read, chunk_edit_cap = (uint64_t)cn * K * hp->edit_cap_per_read;
         if (used[ci & 1]) {
             // this set's inputs were read by chunk ci-2's kernels; its outputs must have left the device
             GB_CUDA(cudaStreamWaitEvent(d->s_in, io.ev_done, 0));
             GB_CUDA(cudaStreamWaitEvent(d->stream, io.ev_out, 0));
         }
         if ((rc = io.reads.reserve(total ? total : 1)) || (quals && (rc = io.quals.reserve(total ? total : 1))) || (rc = io.read_off.reserve(cn + 1)) ||
-            (rc = io.aln.reserve(cn)) || (rc = io.status.reserve(cn)) || (rc = io.totals.reserve(3)) ||
+            (rc = io.aln.reserve((size_t)cn * K)) || (rc = io.status.reserve(cn)) || (rc = io.totals.reserve(3)) ||
             (rc = io.maps.reserve(chunk_map_cap)) || (rc = io.edits.reserve(chunk_edit_cap))) return rc;
         if (total) GB_CUDA(cudaMemcpyAsync(io.reads.ptr, reads + b0, total, cudaMemcpyHostToDevice, d->s_in));
         if (quals && total) GB_CUDA(cudaMemcpyAsync(io.quals.ptr, quals + b0, total, cudaMemcpyHostToDevice, d->s_in));
@@ -603,9 +613,12 @@ static int map_batch_host(gb_device* d, const gb_map_params* hp, bool paired,
         // headers + totals of this chunk leave as soon as it is done
         GB_CUDA(cudaStreamWaitEvent(d->s_out, io.ev_done, 0));
         GB_CUDA(cudaMemcpyAsync(d->h_totals + 3 * (ci & 1), io.totals.ptr, 3 * sizeof(uint64_t), cudaMemcpyDeviceToHost, d->s_out));
-        GB_CUDA(cudaMemcpyAsync(aln + c0, io.aln.ptr, sizeof(gb_alignment) * cn, cudaMemcpyDeviceToHost, d->s_out));
+        // rank j of the chunk's reads goes to rank j of the batch (record j * n_reads + read)
+        for (uint32_t j = 0; j < K; j++) {
+            GB_CUDA(cudaMemcpyAsync(aln + (size_t)j * n_reads + c0, io.aln.ptr + (size_t)j * cn, sizeof(gb_alignment) * cn, cudaMemcpyDeviceToHost, d->s_out));
+            if (d->mirror_aln) GB_CUDA(cudaMemcpyAsync(d->mirror_aln + (size_t)j * n_reads + c0, io.aln.ptr + (size_t)j * cn, sizeof(gb_alignment) * cn, cudaMemcpyDeviceToDevice, d->s_out));
+        }
         GB_CUDA(cudaMemcpyAsync(status + c0, io.status.ptr, cn, cudaMemcpyDeviceToHost, d->s_out));
-        if (d->mirror_aln) GB_CUDA(cudaMemcpyAsync(d->mirror_aln + c0, io.aln.ptr, sizeof(gb_alignment) * cn, cudaMemcpyDeviceToDevice, d->s_out));
         GB_CUDA(cudaEventRecord(io.ev_hdr, d->s_out));
         return GB_OK;
     };
@@ -697,7 +710,7 @@ extern "C" int gb_debug_seed_stage(gb_device* d, const gb_map_params* hp, int pa
         int rc;
         if ((rc = d_reads.upload(reads, total + 16, d->stream, total)) || (quals && (rc = d_quals.upload(quals, total + 16, d->stream, total))) ||
             (rc = d_off.upload(read_off, n_reads + 1, d->stream)) || (rc = d_status.reserve(n_reads)) || (rc = d_totals.reserve(2)) ||
-            (rc = d_aln.reserve(n_reads)) || (rc = d_dbg.reserve((size_t)n_reads * MAX_CLUSTERS))) return rc;
+            (rc = d_aln.reserve((size_t)n_reads * std::max<uint32_t>(hp->max_multimaps, 1u))) || (rc = d_dbg.reserve((size_t)n_reads * MAX_CLUSTERS))) return rc;
         GB_CUDA(cudaMemsetAsync(d_dbg.ptr, 0, sizeof(DbgCluster) * (size_t)n_reads * MAX_CLUSTERS, d->stream));
         std::vector<ReadState> st(n_reads);
         uint32_t cursors[16];

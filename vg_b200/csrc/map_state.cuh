@@ -122,6 +122,7 @@ struct MapParamsDev {
     int32_t  extension_score_threshold, min_extension_sets, extension_set_min_score;
     uint32_t max_alignments, max_extension_mismatches, max_dozeu_cells, do_dp;
     uint32_t mapping_cap, edit_cap;
+    uint32_t max_multimaps, out_stride;   // mappings reported per read; records of rank j live at j * out_stride + read (out_stride = reads of the chunk)
     uint32_t max_rescue_attempts, rescue_seed_limit;
     double   paired_rescue_score_limit, rescue_subgraph_stdevs, rescue_likelihood_limit;
     double   log_base;

@@ -143,6 +143,7 @@ extern "C" int gb_map_paired_job(gb_device* d, const gb_map_params* hp, gb_fragm
                                  uint8_t* status, uint8_t* pair_route, uint64_t* n_mappings_used, uint64_t* n_edits_used) {
     if (!d || !hp || !f) { g_last_error = "gb_map_paired_job: null argument"; return GB_ERR_ARG; }
     if (n_reads % 2 != 0) { g_last_error = "paired mapping needs an even number of reads"; return GB_ERR_ARG; }
+    if (hp->max_multimaps != 1) { g_last_error = "gb_map_paired_job reports one mapping per read (max_multimaps = 1); use gb_map_paired_batch with a forced distribution for multi-mapping"; return GB_ERR_ARG; }
     if (training_window == 0) training_window = 2048;
     const uint32_t n_pairs = n_reads / 2;
     if (n_pairs == 0) { if (n_mappings_used) *n_mappings_used = 0; if (n_edits_used) *n_edits_used = 0; return GB_OK; }     // nothing to map: the distribution stays as it is

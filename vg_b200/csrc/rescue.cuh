@@ -600,5 +600,6 @@ __device__ inline uint32_t finalize_pe_rescue(const DevIndex& ix, const MapParam
         if (lane == 0 && nm) write_alignment(ix, pb, nm, ne, sread[r], L[r], r == 1, out_maps[r], out_edits[r]);
     }
     __syncwarp();
+    if (P.max_multimaps > 1) return write_secondary_pairs(ix, P, a, cl, po, n_pairs, pair_c0, pair_c1, rescue_frag, sread, L, read_idx0, cand_base);
     return GB_ITEM_OK;
 }
