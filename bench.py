@@ -32,6 +32,8 @@ sys.path.insert(0, str(ROOT))
 sys.path.insert(0, str(ROOT / "tests"))
 
 READ_LEN = 150
+WORKLOAD = ("configs[1]: 1 Mbp random graph, 1k SNP+indel variants, 8 haplotypes, nodes <= 32 bp, k=29 w=11; "
+            "150 bp paired-end reads, fragment N(400,50) forced, 0.2 % substitutions, 0.02 % indels (SURVEY §8(d) config 2)")
 FRAG_MEAN, FRAG_SD = 400.0, 50.0
 SUB_RATE = 0.002
 INDEL_RATE = 0.0002        # per base; at most one 1-bp insertion or deletion per read, half each
@@ -372,8 +374,10 @@ def main():
             "impl": "reference", "metric": "giraffe reads/sec (150 bp PE, synthetic)", "value": value, "unit": "reads/s",
             "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "int32", "data": "synthetic",
-            "config": {"workload": "configs[1]: 1 Mbp / 1k-variant graph, 150 bp PE reads, fragment N(400,50) forced, 0.2 % substitutions, 0.02 % indels, rescue attempts " + str(args.rescue_attempts),
-                       "reads_per_step": used, "note": "CPU restatement of vg giraffe (oracle/, OpenMP over read pairs); vg itself cannot be built in this image"},
+            "config": {"workload": WORKLOAD,
+                       "mapper": f"map_paired, vg giraffe defaults (--rescue-attempts {args.rescue_attempts}), forced fragment distribution",
+                       "reads_per_step": used, "sample": f"{used} reads of the same generator (error model, graph and seed family) per step: a bounded sample of the GPU arm's {n_reads}-read step",
+                       "note": "CPU restatement of vg giraffe (oracle/, OpenMP over read pairs); vg itself cannot be built in this image"},
             "cpu_baseline": {"value": value, "unit": "reads/s", "cores": usable_cpus()[0], "threads": threads, "kind": "port", "sample": f"{used} reads per step, {threads} OpenMP threads, {flags}, {cpu_note}"},
             "e2e": {"value": value, "unit": "reads/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         }
@@ -645,8 +649,7 @@ def main():
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": dev_ms, "higher_is_better": True, "scaling": args.scaling,
         "vs_baseline": None, "dtype": "int32", "data": "synthetic",
         "config": {
-            "workload": "configs[1]: 1 Mbp random graph, 1k SNP+indel variants, 8 haplotypes, nodes <= 32 bp, k=29 w=11; "
-                        "150 bp paired-end reads, fragment N(400,50) forced, 0.2 % substitutions, 0.02 % indels (SURVEY §8(d) config 2)",
+            "workload": WORKLOAD,
             "reads_per_gpu_per_step": n_reads, "pairs_per_gpu_per_step": n_reads // 2,
             "total_reads_per_step": job_reads,
             "emission": (None if world == 1 else {"what": "whole records (32 B header + mappings + edits) of every rank gathered on rank 0 over NCCL, exact sizes, side stream overlapped with the next step, then to pinned host memory",
