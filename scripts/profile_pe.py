@@ -29,4 +29,5 @@ for it in range(iters):
     assert rc == 0
     torch.cuda.synchronize()
     print("stage ms", dev.stage_times(), flush=True)
+    print("kernel ms", {k: round(v, 3) for k, v in dev.kernel_times() if v >= 0.05}, flush=True)
 torch.cuda.profiler.stop()
