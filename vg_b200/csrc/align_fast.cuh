@@ -85,34 +85,13 @@ __device__ inline void extension_ends(const DevIndex& ix, const gb_extension& e,
     last_node = path_pool[e.path_off + e.path_len - 1]; last_end = tail;
 }
 
-// The thread-per-pair kernel is latency-bound (profiles/ncu_summary_r02: long-scoreboard stall 14.9 per issue): a thread
-// walks ReadState -> items / extensions -> ... -> minimizer records and qualities (faster_cap, last), one dependent
-// DRAM round trip after the other.  With FastArgs.prefetch the lines the LAST phases need are requested into L2 as soon
-// as the ReadStates are known, so those round trips overlap the set scoring and the pairing.
-__device__ __forceinline__ void prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];" :: "l"(p)); }
-__device__ __forceinline__ void fast_prefetch_read(const MapBatch& b, const AlignArgs& a, const ReadState& rs, uint32_t r) {
-    const char* m = reinterpret_cast<const char*>(a.minimizers + rs.min_off);
-    const uint32_t mbytes = min(rs.min_cnt, 32u) * (uint32_t)sizeof(DevMinimizer);
-    for (uint32_t o = 0; o < mbytes; o += 128) prefetch_l2(m + o);
-    if (b.quals) {
-        const uint64_t rb = b.read_off[r];
-        const uint32_t L = (uint32_t)(b.read_off[r + 1] - rb);
-        const char* q = reinterpret_cast<const char*>(b.quals + rb);
-        for (uint32_t o = 0; o < L; o += 128) prefetch_l2(q + o);
-    }
-    const char* it = reinterpret_cast<const char*>(a.items + rs.item_off);
-    const uint32_t ibytes = min(rs.item_cnt, 8u) * (uint32_t)sizeof(DevItem);
-    for (uint32_t o = 0; o < ibytes; o += 128) prefetch_l2(it + o);
-}
-
 // Returns true when the pair was fully handled (outputs written), false when it must go to the
 // warp-per-pair kernel.
-__device__ inline bool fast_pair(const DevIndex& ix, const MapParamsDev& P, const DevScores& sc, const MapBatch& b, const AlignArgs& a, uint32_t p, bool prefetch) {
+__device__ inline bool fast_pair(const DevIndex& ix, const MapParamsDev& P, const DevScores& sc, const MapBatch& b, const AlignArgs& a, uint32_t p) {
     const ReadState rs0 = b.states[2 * p], rs1 = b.states[2 * p + 1];
     const ReadState* rsp[2] = {&rs0, &rs1};
     if (rs0.status != GB_ITEM_OK) return false;                 // let the slow kernel report it
     if (P.max_multimaps > 1) return false;                      // secondaries are written by the warp kernels only
-    if (prefetch) { fast_prefetch_read(b, a, rs0, 2 * p); fast_prefetch_read(b, a, rs1, 2 * p + 1); }
     if (rs1.pad[0] > 1) return false;                           // deferred cluster selection of read 2 (rare: tied clusters): warp kernel
     const PairState ps = a.pairs[p];
     if (ps.n_fragments + 1 > MAX_FRAGMENTS) return false;
@@ -382,8 +361,7 @@ __device__ inline bool fast_read(const DevIndex& ix, const MapParamsDev& P, cons
     return true;
 }
 
-struct FastArgs { uint32_t* slow_list; uint32_t* slow_count; uint32_t prefetch; };
-
+struct FastArgs { uint32_t* slow_list; uint32_t* slow_count; };
 
 // MINB != 0 caps the registers for that many resident blocks per SM: the kernel waits on scattered record loads, more warps
 // in flight hide more of them (measured per 1 M reads: uncapped 48 registers 6.15 ms, 12 blocks 5.16 ms, 16 blocks 5.34 ms).
@@ -393,7 +371,7 @@ __global__ void __launch_bounds__(128, MINB ? MINB : 1)
 align_fast_kernel_pe(DevIndex ix, MapParamsDev P, DevScores sc, MapBatch b, AlignArgs a, FastArgs fa) {
     const uint32_t n_pairs = b.n_reads / 2;
     for (uint32_t p = blockIdx.x * blockDim.x + threadIdx.x; p < n_pairs; p += gridDim.x * blockDim.x) {
-        if (!fast_pair(ix, P, sc, b, a, p, fa.prefetch != 0)) {
+        if (!fast_pair(ix, P, sc, b, a, p)) {
             const uint32_t slot = atomicAdd(fa.slow_count, 1u);
             fa.slow_list[slot] = p;
         }

@@ -170,7 +170,6 @@ extern "C" int gb_device_create(const gb_flat_index* ix, int device_ordinal, gb_
     }
     if (const char* env = std::getenv("GIRAFFE_B200_TILES")) d->use_tiles = std::atoi(env) != 0;
     if (const char* env = std::getenv("GIRAFFE_B200_EXTEND_MINB")) { const int v = std::atoi(env); if (v >= 2 && v <= 6) d->extend_minb = v; }
-    if (const char* env = std::getenv("GIRAFFE_B200_FAST_PREFETCH")) d->fast_prefetch = std::atoi(env) != 0;
     if (const char* env = std::getenv("GIRAFFE_B200_FAST_MINB")) { const int v = std::atoi(env); if (v == 0 || v == 12 || v == 16) d->fast_minb = v; }
     if (const char* env = std::getenv("GIRAFFE_B200_POOL_SCALE")) {
         const double v = std::strtod(env, nullptr);

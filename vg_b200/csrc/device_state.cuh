@@ -127,7 +127,6 @@ struct gb_device {
     // tail plan + DP tiles (xdrop_tile.cuh); GIRAFFE_B200_TILES=0 keeps every tail DP in the align kernels (int32 sweep)
     bool use_tiles = true; uint32_t last_tile_problems = 0;
     int extend_minb = 4, fast_minb = 12;          // launch-bounds instantiations (GIRAFFE_B200_EXTEND_MINB / _FAST_MINB)
-    bool fast_prefetch = false;                   // align_fast_kernel_pe: L2 prefetch of the late-phase records (GIRAFFE_B200_FAST_PREFETCH)
     gb_alignment* mirror_aln = nullptr; gb_mapping* mirror_maps = nullptr; uint32_t* mirror_edits = nullptr; uint64_t mirror_map_cap = 0, mirror_edit_cap = 0;
     gb::DevBuf<gb::TailPlanEntry> pl_entries;
     gb::DevBuf<uint32_t> pl_unit_base, pl_unit_count, pl_tile_off, pl_lists, pl_paths;

@@ -431,7 +431,7 @@ int map_device(gb_device* d, const gb_map_params* hp, uint32_t n_reads, const ui
         // thread-per-unit fast path first; whatever it cannot finish goes to the warp-per-unit kernel
         const uint32_t n_units = paired ? n_reads / 2 : n_reads;
         if ((rc = d->p_slow.reserve(n_units + 1))) return rc;
-        FastArgs fa; fa.slow_list = d->p_slow.ptr; fa.slow_count = cur + 7; fa.prefetch = d->fast_prefetch ? 1u : 0u;
+        FastArgs fa; fa.slow_list = d->p_slow.ptr; fa.slow_count = cur + 7;
         const uint32_t fgrid = std::max<uint32_t>(1u, std::min<uint32_t>((n_units + 127) / 128, (uint32_t)d->n_sms * 16));
         a.slow_list = nullptr; a.slow_count = nullptr;
         if (paired) {
