@@ -70,7 +70,8 @@ typedef struct gb_node_rec {
  * consecutive cut nodes — any DAG: nested bubbles, alleles of several nodes, adjacent or overlapping variants.
  *   x_in  = minimum distance from the chain start to the first base of the node
  *   x_out = x_in of the cut node behind the node's slot - minimum distance from the node's end to that cut node
- *           (a cut node: x_in + its length)
+ *           (a cut node: x_in + its length).  SIGNED, two's complement in the 32-bit field: a route that bypasses the
+ *           site (a deletion spanning it) makes the cut node's coordinate smaller than the way out of the site
  *   slot  = index of the slot along the chain;  allele = index of the node inside its site in topological order
  *           (0xFFFF: cut node);  component = the chain
  * For u before v in different slots:  d(end of u -> start of v) = x_in[v] - x_out[u]  (every walk crosses the cut nodes
@@ -619,6 +620,25 @@ int gb_chain_batch(gb_device* dev, const gb_chain_params* params, uint32_t n_pro
                    int32_t* dp_score, uint32_t* dp_source, uint64_t* dp_paths, uint32_t* dp_rec,
                    uint32_t* n_chains, int32_t* chain_score, uint32_t* chain_begin, uint32_t* chain_count,
                    uint32_t* chain_items);
+
+/* The candidate side of the same seam: what zip_tree_transition_iterator enumerates for find_best_chains
+ * (chain_items.cpp:116-260 over ZipCodeTree::find_distances, zip_code_tree.cpp): for every destination seed the seeds it
+ * can be reached FROM within max_graph_lookback_bases, with the minimum graph distance between the two positions (the
+ * number of bases walked from the source position to the destination position; positions on different strands, on
+ * parallel alleles or in different components do not see each other).  The reference reads those distances off its
+ * zip-code tree; this library has no snarl tree, the distances come from its own distance model (gb_dist_payload: chains
+ * of cut nodes and sites with all-pairs tables), which answers the same minimum-distance query — pinned by the
+ * "Check iterator" expectations of the reference's zip-code-tree tests on DAGs (unittest/zip_code_tree.cpp).  The
+ * iteration ORDER of the tree is not reproduced: the chaining DP does not depend on it (gb_chain_batch).
+ * Problem p: seeds seed_pos[2 * i], seed_pos[2 * i + 1] = oriented node, offset for i in seed_off[p] .. seed_off[p+1].
+ * Output: candidates of problem p at cand_off[p] .. cand_off[p+1], sorted by (destination, source), from / to = seed
+ * indices inside the problem; two seeds at the same position see each other in both directions at distance 0 (the tree
+ * offers one of the two; the read-order test of add_transition_if_legal keeps at most one).  cand_off is always filled;
+ * GB_ERR_CAPACITY when cand_off[n_problems] > candidate_cap (nothing is written then).  Needs an index with a distance
+ * model. */
+int gb_chain_candidates_batch(gb_device* dev, uint32_t n_problems, const uint32_t* seed_pos, const uint64_t* seed_off,
+                              uint64_t max_graph_lookback_bases, gb_chain_candidate* candidates, uint64_t candidate_cap,
+                              uint64_t* cand_off);
 
 /* Kernel-only timing of the last gb_*_batch call on this handle, milliseconds
  * (CUDA events on the handle's stream around the kernels, copies excluded). */

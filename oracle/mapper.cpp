@@ -313,7 +313,7 @@ static int64_t directed_distance(const gb_flat_index* ix, uint32_t id_a, uint32_
     if (id_a == id_b) return off_b >= off_a ? (int64_t)off_b - off_a : INF_DIST;
     if (pa.slot < pb.slot) {
         int64_t len_a = ix->nodes[2 * id_a].len;
-        return (len_a - (int64_t)off_a) + ((int64_t)pb.x_in - (int64_t)pa.x_out) + (int64_t)off_b;
+        return (len_a - (int64_t)off_a) + ((int64_t)(int32_t)pb.x_in - (int64_t)(int32_t)pa.x_out) + (int64_t)off_b;
     }
     if (pa.slot == pb.slot) {
         const int64_t t = site_distance(ix, pa, pb);           // inside one site: its all-pairs table

@@ -82,7 +82,7 @@ int64_t oriented_distance(const gb_flat_index* ix, uint32_t node_a, uint32_t off
     const gb_dist_payload& ps = ix->dist[src_id]; const gb_dist_payload& pd = ix->dist[dst_id];
     if (ps.component != pd.component) return UNREACHABLE;
     if (src_id == dst_id) return dst_off >= src_off ? dst_off - src_off : UNREACHABLE;
-    if (ps.slot < pd.slot) return (src_len - src_off) + ((int64_t)pd.x_in - (int64_t)ps.x_out) + dst_off;
+    if (ps.slot < pd.slot) return (src_len - src_off) + ((int64_t)(int32_t)pd.x_in - (int64_t)(int32_t)ps.x_out) + dst_off;
     if (ps.slot == pd.slot) { const int64_t t = site_distance(ix, ps, pd); if (t >= 0) return (src_len - src_off) + t + dst_off; }
     return UNREACHABLE;
 }
@@ -649,4 +649,23 @@ extern "C" int oracle_seed_stage(const gb_flat_index* ix, const gb_scores* score
         }
     }
     return 0;
+}
+
+// The candidate side of find_best_chains (test entry for gb_chain_candidates_batch): every ordered pair of seeds (from, to)
+// whose minimum graph distance from -> to exists and is <= limit, sorted by (to, from) — what zip_tree_transition_iterator
+// offers (chain_items.cpp:116-260), with the distances taken from the distance payload instead of the zip-code tree.
+// Returns the number of candidates (written up to cap).
+extern "C" uint64_t oracle_chain_candidates(const gb_flat_index* ix, uint32_t n_seeds, const uint32_t* seed_pos, uint64_t limit,
+                                            gb_chain_candidate* out, uint64_t cap) {
+    const int64_t UNREACHABLE = (int64_t)std::numeric_limits<size_t>::max();
+    uint64_t n = 0;
+    for (uint32_t j = 0; j < n_seeds; j++)
+        for (uint32_t i = 0; i < n_seeds; i++) {
+            if (i == j) continue;
+            const int64_t d = oracle::oriented_distance(ix, seed_pos[2 * i], seed_pos[2 * i + 1], seed_pos[2 * j], seed_pos[2 * j + 1]);
+            if (d == UNREACHABLE || d < 0 || (uint64_t)d > limit) continue;
+            if (n < cap) { out[n].from = i; out[n].to = j; out[n].graph_distance = (uint64_t)d; }
+            n++;
+        }
+    return n;
 }

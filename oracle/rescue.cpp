@@ -41,11 +41,11 @@ std::vector<uint32_t> subgraph_in_distance_range(const gb_flat_index* ix, uint32
         if (pv.component != ps.component) continue;
         int64_t d0;     // distance from the origin to the first base of the node in walk direction
         if (!rev) {
-            if (ps.slot < pv.slot) d0 = to_end + ((int64_t)pv.x_in - (int64_t)ps.x_out);
+            if (ps.slot < pv.slot) d0 = to_end + ((int64_t)(int32_t)pv.x_in - (int64_t)(int32_t)ps.x_out);
             else if (ps.slot == pv.slot) { const int64_t t = site_distance(ix, ps, pv); if (t < 0) continue; d0 = to_end + t; }
             else continue;
         } else {
-            if (pv.slot < ps.slot) d0 = to_end + ((int64_t)ps.x_in - (int64_t)pv.x_out);
+            if (pv.slot < ps.slot) d0 = to_end + ((int64_t)(int32_t)ps.x_in - (int64_t)(int32_t)pv.x_out);
             else if (ps.slot == pv.slot) { const int64_t t = site_distance(ix, pv, ps); if (t < 0) continue; d0 = to_end + t; }
             else continue;
         }

@@ -24,7 +24,7 @@ GB_MAX_MULTIMAPS = 8
 
 # numpy mirrors of the ABI structs
 node_rec_dt = np.dtype([("seq_off", "<u4"), ("rec_off", "<u4"), ("len", "<u4"), ("size", "<u4")])
-dist_dt = np.dtype([("x_in", "<u4"), ("x_out", "<u4"), ("slot", "<u4"), ("allele", "<u2"), ("component", "<u2")])
+dist_dt = np.dtype([("x_in", "<i4"), ("x_out", "<i4"), ("slot", "<u4"), ("allele", "<u2"), ("component", "<u2")])
 min_cell_dt = np.dtype([("key", "<u8"), ("hit_off", "<u4"), ("hit_cnt", "<u4")])
 hit_dt = np.dtype([("pos", "<u8"), ("payload", dist_dt)])
 slot_dt = np.dtype([("table_off", "<u4"), ("n", "<u4")])
@@ -183,6 +183,8 @@ def load_library() -> C.CDLL:
     lib.gb_chain_params_default.restype = None
     lib.gb_chain_batch.argtypes = [vp, C.POINTER(ChainParams), u32, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp]
     lib.gb_chain_batch.restype = C.c_int
+    lib.gb_chain_candidates_batch.argtypes = [vp, u32, vp, vp, u64, vp, u64, vp]
+    lib.gb_chain_candidates_batch.restype = C.c_int
     lib.gb_fragment_create.argtypes = [u64, u64, C.c_double]
     lib.gb_fragment_create.restype = vp
     lib.gb_fragment_destroy.argtypes = [vp]
@@ -629,6 +631,25 @@ class Device:
                 path.append([int(m["node"]), int(m["offset"]), ed])
             out.append((int(score[i]), path))
         return out
+
+    def chain_candidates_batch(self, problems, limit=2 ** 64 - 1, cap=None):
+        """gb_chain_candidates_batch.  problems: list of seed lists [(oriented node, offset), ...].
+        Returns per problem a chain_candidate_dt array sorted by (to, from)."""
+        lib = load_library()
+        n = len(problems)
+        off = np.zeros(n + 1, dtype=np.uint64); off[1:] = np.cumsum([len(p) for p in problems])
+        pos = np.ascontiguousarray(np.array([x for p in problems for x in p] + [(0, 0)], dtype=np.uint32).reshape(-1))
+        coff = np.zeros(n + 1, dtype=np.uint64)
+        if cap is None:
+            rc = lib.gb_chain_candidates_batch(self._h, n, ptr(pos), ptr(off), limit, None, 0, ptr(coff))      # sizes first
+            if rc not in (GB_OK, GB_ERR_CAPACITY):
+                raise GbError(rc, "gb_chain_candidates_batch")
+            cap = int(coff[n])
+        out = np.zeros(cap + 1, dtype=chain_candidate_dt)
+        rc = lib.gb_chain_candidates_batch(self._h, n, ptr(pos), ptr(off), limit, ptr(out), cap, ptr(coff))
+        if rc != GB_OK:
+            raise GbError(rc, "gb_chain_candidates_batch")
+        return [out[int(coff[p]): int(coff[p + 1])].copy() for p in range(n)]
 
     def chain_batch(self, problems, params=None):
         """gb_chain_batch.  problems: list of (anchors, candidates) structured arrays (chain_anchor_dt sorted by read_start,

@@ -16,6 +16,7 @@
 //      dependent loads over every anchor exactly once), then max_chains selections of the smallest penalty.
 // The minimap2-style gap cost (:364-372) is evaluated in FP64 exactly as the host does: 0.5 * log2(d) comes from a
 // table built with the host libm, the product and the sum are separate IEEE operations (no FMA contraction).
+#include <cub/cub.cuh>
 #include "giraffe_b200.h"
 #include "device_state.cuh"
 
@@ -251,6 +252,38 @@ __global__ void __launch_bounds__(CHAIN_WARPS * 32) chain_kernel(ChainBatch b) {
     }
 }
 
+// ---- candidates: every (source, destination) pair of seeds within the lookback, with its minimum graph distance -------------
+// One warp per DESTINATION seed; the lanes take the sources of the same problem 32 at a time.  Two passes: count, then (after
+// an exclusive scan over all seeds) fill — so the output is dense and sorted by (destination, source) without atomics.
+struct CandBatch {
+    uint32_t n_seeds; const uint32_t* pos; const uint32_t* prob_begin; const uint32_t* prob_end;    // per seed: its problem's seed range
+    uint64_t limit; uint64_t* count; const uint64_t* offset; gb_chain_candidate* out;
+};
+template <bool FILL>
+__global__ void __launch_bounds__(128) chain_candidates_kernel(DevIndex ix, CandBatch b) {
+    const int lane = threadIdx.x & 31;
+    const uint32_t warps = (gridDim.x * blockDim.x) >> 5;
+    for (uint32_t j = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; j < b.n_seeds; j += warps) {
+        const uint32_t a0 = b.prob_begin[j], a1 = b.prob_end[j];
+        const uint32_t nj = b.pos[2 * j], oj = b.pos[2 * j + 1];
+        uint64_t n = 0;
+        const uint64_t base = FILL ? b.offset[j] : 0;
+        for (uint32_t i0 = a0; i0 < a1; i0 += 32) {
+            const uint32_t i = i0 + lane;
+            int64_t d = -1;
+            if (i < a1 && i != j) d = oriented_distance(ix, b.pos[2 * i], b.pos[2 * i + 1], nj, oj);
+            const bool hit = d >= 0 && (uint64_t)d <= b.limit;
+            const unsigned m = __ballot_sync(0xffffffffu, hit);
+            if (FILL && hit) {
+                gb_chain_candidate c; c.from = i - a0; c.to = j - a0; c.graph_distance = (uint64_t)d;
+                b.out[base + n + __popc(m & ((1u << lane) - 1u))] = c;
+            }
+            n += __popc(m);
+        }
+        if (!FILL && lane == 0) b.count[j] = n;
+    }
+}
+
 } // namespace gb
 
 using namespace gb;
@@ -347,5 +380,68 @@ extern "C" int gb_chain_batch(gb_device* d, const gb_chain_params* P, uint32_t n
         return chain_batch_impl(d, P, n_problems, anchors, anchor_off, cands, cand_off, dp_score, dp_source, dp_paths, dp_rec,
                                 n_chains, chain_score, chain_begin, chain_count, chain_items);
     } catch (const std::bad_alloc&) { return GB_ERR_CAPACITY; }
+    catch (...) { return GB_ERR_ARG; }
+}
+
+static int chain_candidates_impl(gb_device* d, uint32_t n_problems, const uint32_t* seed_pos, const uint64_t* seed_off,
+                                 uint64_t limit, gb_chain_candidate* candidates, uint64_t candidate_cap, uint64_t* cand_off) {
+    if (!d || !seed_off || !cand_off || (candidate_cap && !candidates)) return GB_ERR_ARG;
+    for (uint32_t p = 0; p <= n_problems; p++) cand_off[p] = 0;
+    if (n_problems == 0) return GB_OK;
+    const uint64_t total = seed_off[n_problems];
+    if (total >= 0x7ffffff0ull || (total && !seed_pos)) return GB_ERR_ARG;
+    if (total == 0) return GB_OK;
+    std::vector<uint32_t> pb(total), pe(total);
+    for (uint32_t p = 0; p < n_problems; p++) {
+        if (seed_off[p + 1] < seed_off[p]) return GB_ERR_ARG;
+        for (uint64_t i = seed_off[p]; i < seed_off[p + 1]; i++) {
+            const uint32_t v = seed_pos[2 * i], o = seed_pos[2 * i + 1];
+            if (v < 2 || v >= d->h_node_len.size() || d->h_node_len[v] == 0 || o >= d->h_node_len[v]) { g_last_error = "gb_chain_candidates_batch: seed position outside the graph"; return GB_ERR_ARG; }
+            pb[i] = (uint32_t)seed_off[p]; pe[i] = (uint32_t)seed_off[p + 1];
+        }
+    }
+    GB_CUDA(cudaSetDevice(d->device));
+    DevBuf<uint32_t> d_pos, d_pb, d_pe; DevBuf<uint64_t> d_count, d_offset; DevBuf<uint8_t> d_tmp; DevBuf<gb_chain_candidate> d_out;
+    int rc;
+    if ((rc = d_pos.upload(seed_pos, 2 * total, d->stream)) || (rc = d_pb.upload(pb.data(), total, d->stream)) || (rc = d_pe.upload(pe.data(), total, d->stream)) ||
+        (rc = d_count.reserve(total + 1)) || (rc = d_offset.reserve(total + 1))) return rc;
+    GB_CUDA(cudaMemsetAsync(d_count.ptr + total, 0, sizeof(uint64_t), d->stream));
+    CandBatch b; b.n_seeds = (uint32_t)total; b.pos = d_pos.ptr; b.prob_begin = d_pb.ptr; b.prob_end = d_pe.ptr; b.limit = limit;
+    b.count = d_count.ptr; b.offset = d_offset.ptr; b.out = nullptr;
+    const uint32_t grid = std::max<uint32_t>(1u, std::min<uint32_t>((uint32_t)d->n_sms * 16, (uint32_t)((total + 3) / 4)));
+    GB_CUDA(cudaEventRecord(d->ev0, d->stream));
+    chain_candidates_kernel<false><<<grid, 128, 0, d->stream>>>(d->ix, b);
+    d->launches++;
+    GB_CUDA(cudaGetLastError());
+    size_t tmp_bytes = 0;
+    GB_CUDA(cub::DeviceScan::ExclusiveSum(nullptr, tmp_bytes, d_count.ptr, d_offset.ptr, (int)(total + 1), d->stream));
+    if ((rc = d_tmp.reserve(tmp_bytes + 256))) return rc;
+    size_t tb = d_tmp.cap;
+    GB_CUDA(cub::DeviceScan::ExclusiveSum(d_tmp.ptr, tb, d_count.ptr, d_offset.ptr, (int)(total + 1), d->stream));
+    d->launches++;
+    std::vector<uint64_t> h_off(total + 1);
+    GB_CUDA(cudaMemcpyAsync(h_off.data(), d_offset.ptr, sizeof(uint64_t) * (total + 1), cudaMemcpyDeviceToHost, d->stream));
+    GB_CUDA(cudaStreamSynchronize(d->stream));
+    for (uint32_t p = 0; p <= n_problems; p++) cand_off[p] = h_off[seed_off[p]];
+    const uint64_t n_out = h_off[total];
+    if (n_out > candidate_cap) { g_last_error = "gb_chain_candidates_batch: candidate capacity too small (cand_off holds the sizes needed)"; return GB_ERR_CAPACITY; }
+    if (n_out) {
+        if ((rc = d_out.reserve(n_out))) return rc;
+        b.out = d_out.ptr;
+        chain_candidates_kernel<true><<<grid, 128, 0, d->stream>>>(d->ix, b);
+        d->launches++;
+        GB_CUDA(cudaGetLastError());
+        GB_CUDA(cudaEventRecord(d->ev1, d->stream));
+        GB_CUDA(cudaMemcpyAsync(candidates, d_out.ptr, sizeof(gb_chain_candidate) * n_out, cudaMemcpyDeviceToHost, d->stream));
+    } else GB_CUDA(cudaEventRecord(d->ev1, d->stream));
+    GB_CUDA(cudaStreamSynchronize(d->stream));
+    GB_CUDA(cudaEventElapsedTime(&d->last_kernel_ms, d->ev0, d->ev1));
+    return GB_OK;
+}
+
+extern "C" int gb_chain_candidates_batch(gb_device* d, uint32_t n_problems, const uint32_t* seed_pos, const uint64_t* seed_off,
+                                         uint64_t max_graph_lookback_bases, gb_chain_candidate* candidates, uint64_t candidate_cap, uint64_t* cand_off) {
+    try { return chain_candidates_impl(d, n_problems, seed_pos, seed_off, max_graph_lookback_bases, candidates, candidate_cap, cand_off); }
+    catch (const std::bad_alloc&) { return GB_ERR_CAPACITY; }
     catch (...) { return GB_ERR_ARG; }
 }

@@ -62,6 +62,28 @@ __device__ __forceinline__ gb_node_rec load_node(const DevIndex& ix, uint32_t v)
     return n;
 }
 
+// minimum_distance(pos1, pos2) on cut-style positions through the distance payload; unreachable
+// is size_t max stored into int64_t (= -1), as in distance_between (:3879-3884).
+__device__ inline int64_t oriented_distance(const DevIndex& ix, uint32_t node_a, uint32_t off_a, uint32_t node_b, uint32_t off_b) {
+    const int64_t UNREACHABLE = -1;
+    if ((node_a & 1u) != (node_b & 1u)) return UNREACHABLE;
+    uint32_t src = node_a, dst = node_b; int64_t src_off = off_a, dst_off = off_b;
+    if (node_a & 1u) {
+        src = node_b; dst = node_a;
+        src_off = (int64_t)load_node(ix, node_b).len - (int64_t)off_b;
+        dst_off = (int64_t)load_node(ix, node_a).len - (int64_t)off_a;
+    }
+    const int64_t src_len = load_node(ix, src).len;
+    const uint4 ps = __ldg(reinterpret_cast<const uint4*>(ix.dist) + (src >> 1));
+    const uint4 pd = __ldg(reinterpret_cast<const uint4*>(ix.dist) + (dst >> 1));
+    if ((ps.w >> 16) != (pd.w >> 16)) return UNREACHABLE;               // component
+    if ((src >> 1) == (dst >> 1)) return dst_off >= src_off ? dst_off - src_off : UNREACHABLE;
+    if (ps.z < pd.z) return (src_len - src_off) + ((int64_t)(int32_t)pd.x - (int64_t)(int32_t)ps.y) + dst_off;
+    if (ps.z == pd.z) { const int64_t t = site_distance(ix, ps, pd); if (t >= 0) return (src_len - src_off) + t + dst_off; }
+    return UNREACHABLE;
+}
+
+
 __device__ __forceinline__ int warp_sum(int v) {
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(FULL, v, o);

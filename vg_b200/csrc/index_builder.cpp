@@ -174,7 +174,7 @@ bool derive_distance_payload(uint32_t n_node_ids, const std::vector<uint32_t>& l
         for (uint32_t v : ord) {
             if (pred[v].empty()) dS[v] = 0;
             for (uint32_t p : pred[v]) dS[v] = std::min(dS[v], dS[p] + len[p]);
-            if (dS[v] > 0xFFFFFFF0ull) return false;
+            if (dS[v] > 0x7FFFFFF0ull) return false;               // coordinates are read as int32
         }
         // cut nodes: every walk from a source to a sink passes them.  Sweep the order counting open edges (tail placed, head
         // not), with one virtual edge into every source and one out of every sink: v is a cut node exactly when all open
@@ -242,8 +242,11 @@ bool derive_distance_payload(uint32_t n_node_ids, const std::vector<uint32_t>& l
             }
             for (uint32_t x = 0; x < n; x++) {
                 const uint32_t v = local[x];
-                const uint64_t xo = to_exit[x] == INF ? dS[v] + len[v] : exit_coord - std::min(exit_coord, to_exit[x]);
-                dist[v] = gb_dist_payload{(uint32_t)dS[v], (uint32_t)xo, slot, (uint16_t)x, (uint16_t)c};
+                // x_out is SIGNED (two's complement in the 32-bit field): when a shorter route bypasses the site (a deletion
+                // spanning it), the way from this node to the exit is longer than the exit's own chain coordinate
+                const int64_t xo = to_exit[x] == INF ? (int64_t)(dS[v] + len[v]) : (int64_t)exit_coord - (int64_t)to_exit[x];
+                if (xo < -(int64_t)0x7ffffff0 || xo > (int64_t)0x7ffffff0) return false;
+                dist[v] = gb_dist_payload{(uint32_t)dS[v], (uint32_t)(int32_t)xo, slot, (uint16_t)x, (uint16_t)c};
             }
             slots.push_back(gb_slot_rec{table_off, n});
             i = j;

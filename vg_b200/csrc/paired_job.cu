@@ -108,7 +108,7 @@ int64_t host_oriented_distance(const gb_device* d, uint32_t node_a, uint32_t off
     const gb_dist_payload& ps = d->h_dist[src >> 1]; const gb_dist_payload& pd = d->h_dist[dst >> 1];
     if (ps.component != pd.component) return UNREACHABLE;
     if ((src >> 1) == (dst >> 1)) return dst_off >= src_off ? dst_off - src_off : UNREACHABLE;
-    if (ps.slot < pd.slot) return (src_len - src_off) + ((int64_t)pd.x_in - (int64_t)ps.x_out) + dst_off;
+    if (ps.slot < pd.slot) return (src_len - src_off) + ((int64_t)(int32_t)pd.x_in - (int64_t)(int32_t)ps.x_out) + dst_off;
     if (ps.slot == pd.slot && ps.slot < d->h_slots.size()) {
         const gb_slot_rec& sr = d->h_slots[ps.slot];
         if (sr.table_off != 0xFFFFFFFFu && ps.allele < sr.n && pd.allele < sr.n) {

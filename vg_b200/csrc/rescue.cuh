@@ -62,11 +62,11 @@ __device__ __forceinline__ bool rescue_in_range(const DevIndex& ix, uint32_t id,
     if ((ps.w >> 16) != (pv.w >> 16)) return false;
     int64_t d0;
     if (!(start_node & 1u)) {
-        if (ps.z < pv.z) d0 = to_end + ((int64_t)pv.x - (int64_t)ps.y);
+        if (ps.z < pv.z) d0 = to_end + ((int64_t)(int32_t)pv.x - (int64_t)(int32_t)ps.y);
         else if (ps.z == pv.z) { const int64_t t = site_distance(ix, ps, pv); if (t < 0) return false; d0 = to_end + t; }
         else return false;
     } else {
-        if (pv.z < ps.z) d0 = to_end + ((int64_t)ps.x - (int64_t)pv.y);
+        if (pv.z < ps.z) d0 = to_end + ((int64_t)(int32_t)ps.x - (int64_t)(int32_t)pv.y);
         else if (ps.z == pv.z) { const int64_t t = site_distance(ix, pv, ps); if (t < 0) return false; d0 = to_end + t; }
         else return false;
     }

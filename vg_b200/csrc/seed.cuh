@@ -188,9 +188,9 @@ __device__ __noinline__ int32_t same_site_distance(const DevIndex& ix, uint32_t 
     const uint4 pa = __ldg(reinterpret_cast<const uint4*>(ix.dist) + (ido_a >> 10)), pb = __ldg(reinterpret_cast<const uint4*>(ix.dist) + (ido_b >> 10));
     int64_t best = -1;
     int64_t t = site_distance(ix, pa, pb);                       // a -> b: rest of a + table + offset in b
-    if (t >= 0) best = ((int64_t)pa.y - c_out_a) + t + ((int64_t)c_in_b - (int64_t)pb.x);
+    if (t >= 0) best = ((int64_t)(int32_t)pa.y - c_out_a) + t + ((int64_t)c_in_b - (int64_t)(int32_t)pb.x);
     t = site_distance(ix, pb, pa);
-    if (t >= 0) { const int64_t d = ((int64_t)pb.y - c_out_b) + t + ((int64_t)c_in_a - (int64_t)pa.x); if (best < 0 || d < best) best = d; }
+    if (t >= 0) { const int64_t d = ((int64_t)(int32_t)pb.y - c_out_b) + t + ((int64_t)c_in_a - (int64_t)(int32_t)pa.x); if (best < 0 || d < best) best = d; }
     return best < 0 || best > INT_MAX - 1 ? INT_MAX : (int32_t)best;
 }
 
