@@ -15,6 +15,7 @@
 #include "align.cuh"
 
 #include <algorithm>
+#include <cstdlib>
 #include <vector>
 
 namespace gb {
@@ -23,6 +24,7 @@ constexpr uint32_t WFA_NODES = 64;          // trie nodes per problem
 constexpr uint32_t WFA_SEQ_POOL = 24576;    // bytes of concatenated node sequence per problem
 constexpr uint32_t WFA_PATH_POOL = 2048;    // graph nodes over all trie nodes
 constexpr uint32_t WFA_HASH = 4096;         // wavefront points (power of two)
+constexpr uint32_t WFA_HASH_SMALL = 256;    // first attempt
 constexpr uint32_t WFA_SCORES = 512;        // distinct possible scores
 constexpr uint32_t WFA_STACK = 64;          // MatchPos path depth / traversal stack
 constexpr uint32_t WFA_TARGET_LENGTH = 1024;
@@ -45,7 +47,9 @@ struct WfaScore { int32_t score, min_diagonal, max_diagonal; uint32_t reachable_
 struct WfaWs {
     WfaNode* nodes; uint8_t* seq; uint32_t* path; uint64_t* hash; WfaScore* scores;
     uint32_t n_nodes, seq_used, path_used, n_scores;
-    bool overflow;
+    uint32_t hash_mask;         // table size in use - 1: problems start with WFA_HASH_SMALL cells (clearing the table is most of a
+                                // small problem's memory traffic) and are redone with all WFA_HASH cells when that fills up
+    bool overflow, hash_full;
 };
 
 struct WfaPos {            // MatchPos: offsets + the trie path from a leaf (bottom) to the node (top)
@@ -74,27 +78,27 @@ __device__ __forceinline__ uint32_t wfa_key(uint32_t type, uint32_t node, int32_
 }
 __device__ inline bool wfa_find(const WfaWs& ws, uint32_t type, uint32_t node, int32_t score, int32_t diagonal, uint32_t& seq_offset, uint32_t& node_offset) {
     const uint32_t key = wfa_key(type, node, score, diagonal);
-    uint32_t h = (key * 2654435761u) & (WFA_HASH - 1);
+    uint32_t h = (key * 2654435761u) & ws.hash_mask;
     while (true) {
         const uint64_t e = ws.hash[h];
         if (e == ~0ull) return false;
         if ((uint32_t)(e >> 32) == key) { seq_offset = (uint32_t)e >> 16; node_offset = (uint32_t)e & 0xffffu; return true; }
-        h = (h + 1) & (WFA_HASH - 1);
+        h = (h + 1) & ws.hash_mask;
     }
 }
 __device__ inline void wfa_update(WfaWs& ws, uint32_t type, uint32_t node, int32_t score, int32_t diagonal, uint32_t seq_offset, uint32_t node_offset, uint32_t& n_points) {
     if (score < 0 || score >= 8192 || diagonal < -1024 || diagonal >= 1024 || seq_offset > 0xffffu || node_offset > 0xffffu) { ws.overflow = true; return; }
     const uint32_t key = wfa_key(type, node, score, diagonal);
-    uint32_t h = (key * 2654435761u) & (WFA_HASH - 1);
+    uint32_t h = (key * 2654435761u) & ws.hash_mask;
     while (true) {
         const uint64_t e = ws.hash[h];
         if (e == ~0ull) {
-            if (n_points + 1 >= WFA_HASH * 3 / 4) { ws.overflow = true; return; }
+            if (n_points + 1 >= (ws.hash_mask + 1) * 3 / 4) { ws.overflow = true; ws.hash_full = true; return; }
             n_points++;
             break;
         }
         if ((uint32_t)(e >> 32) == key) break;
-        h = (h + 1) & (WFA_HASH - 1);
+        h = (h + 1) & ws.hash_mask;
     }
     ws.hash[h] = ((uint64_t)key << 32) | (seq_offset << 16) | node_offset;
 }
@@ -296,8 +300,8 @@ __device__ inline void wfa_connect(const DevIndex& ix, const DevScores& sc, cons
     auto evaluate = [&](int e) { return min((int32_t)em[3 * e + 2], (int32_t)(em[3 * e] * (double)seq_len) + (int32_t)em[3 * e + 1]); };
     P.score_bound = evaluate(0) * P.mismatch + evaluate(1) * P.gap_open + evaluate(2) * P.gap_extend;
     const int32_t distance_band = evaluate(3);
-    ws.n_nodes = 0; ws.seq_used = 0; ws.path_used = 0; ws.n_scores = 0; ws.overflow = false;
-    for (uint32_t i = 0; i < WFA_HASH; i++) ws.hash[i] = ~0ull;
+    ws.n_nodes = 0; ws.seq_used = 0; ws.path_used = 0; ws.n_scores = 0; ws.overflow = false; ws.hash_full = false;
+    for (uint32_t i = 0; i <= ws.hash_mask; i++) ws.hash[i] = ~0ull;
     uint32_t n_points = 0;
     wfa_make_node(ix, ws, P, from_node, 0, (int32_t)load_node(ix, from_node).size - 1, 0);
     wfa_update(ws, WF_MATCHES, 0, 0, 0, 0, from_offset + 1, n_points);
@@ -384,7 +388,7 @@ __device__ inline void wfa_connect(const DevIndex& ix, const DevScores& sc, cons
         // trim: best partial alignment; ties to the smallest (trie node, score, diagonal) as in the oracle
         P.cand_score = 0; P.cand_diagonal = 0; P.cand_seq_offset = 0; P.cand_node_offset = 0; P.cand_node = 0;
         int32_t best_score = 0; uint64_t best_key = ~0ull;
-        for (uint32_t h = 0; h < WFA_HASH; h++) {
+        for (uint32_t h = 0; h <= ws.hash_mask; h++) {
             const uint64_t e = ws.hash[h];
             if (e == ~0ull) continue;
             const uint32_t key = (uint32_t)(e >> 32);
@@ -486,6 +490,7 @@ struct WfaBatch {
     uint8_t* work_seq;                          // masked (and for prefix: reverse-complemented) copies
     WfaNode* nodes; uint8_t* seq_pool; uint32_t* path_pool; uint64_t* hash; WfaScore* scores;
     uint32_t* work_counter;
+    uint32_t first_hash_mask;                   // WFA_HASH_SMALL - 1, or WFA_HASH - 1 with GIRAFFE_B200_WFA_SMALL_TABLE=0
 };
 
 __global__ void __launch_bounds__(WFA_THREADS)
@@ -515,7 +520,14 @@ wfa_kernel(DevIndex ix, DevScores sc, WfaBatch b) {
             for (uint32_t i = 0; i < L; i++) { const uint8_t c = b.seq[s0 + i]; wseq[i] = (c == 'A' || c == 'C' || c == 'G' || c == 'T') ? c : (uint8_t)'X'; }
             if (mode == 1) { to_node = 0; to_offset = 0; }
         }
-        if (run) wfa_connect(ix, sc, b.error_model, ws, wseq, L, from_node, from_offset, to_node, to_offset, opath, b.path_cap, oedits, b.edit_cap, out);
+        if (run) {
+            ws.hash_mask = b.first_hash_mask;
+            wfa_connect(ix, sc, b.error_model, ws, wseq, L, from_node, from_offset, to_node, to_offset, opath, b.path_cap, oedits, b.edit_cap, out);
+            if (out.ok == -1 && ws.hash_full && ws.hash_mask != WFA_HASH - 1) {          // the small table filled up: the same problem with the whole table
+                ws.hash_mask = WFA_HASH - 1;
+                wfa_connect(ix, sc, b.error_model, ws, wseq, L, from_node, from_offset, to_node, to_offset, opath, b.path_cap, oedits, b.edit_cap, out);
+            }
+        }
         if (run && out.ok == 1 && mode == 1) {
             if (out.n_edits > 0 && out.length == L && ((oedits[out.n_edits - 1] & 3u) == W_MATCH || (oedits[out.n_edits - 1] & 3u) == W_MISMATCH)) out.score += sc.full_length_bonus;
         }
@@ -576,6 +588,7 @@ extern "C" int gb_wfa_batch(gb_device* d, uint32_t n, const uint8_t* seq, const 
     b.ok = d_ok.ptr; b.score = d_score.ptr; b.node_offset = d_noff.ptr; b.seq_offset = d_sqoff.ptr; b.length = d_len.ptr; b.n_path = d_np.ptr; b.n_edits = d_ne.ptr;
     b.path = d_path.ptr; b.edits = d_edits.ptr; b.path_cap = path_cap; b.edit_cap = edit_cap; b.work_seq = d_work.ptr;
     b.nodes = d_nodes.ptr; b.seq_pool = d_pool.ptr; b.path_pool = d_ppool.ptr; b.hash = d_hash.ptr; b.scores = d_scores.ptr; b.work_counter = d_counter.ptr;
+    { const char* env = std::getenv("GIRAFFE_B200_WFA_SMALL_TABLE"); b.first_hash_mask = (env && std::atoi(env) == 0) ? WFA_HASH - 1 : WFA_HASH_SMALL - 1; }
     GB_CUDA(cudaEventRecord(d->ev0, d->stream));
     wfa_kernel<<<grid, WFA_THREADS, 0, d->stream>>>(d->ix, d->sc, b);
     d->launches++;
