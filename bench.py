@@ -312,6 +312,71 @@ def secondary_workloads(ordinal, n=200_000, check=10_000):
     return out
 
 
+def secondary_seams(ordinal, n_problems=4000, check=40):
+    """Secondary fields for the entry points outside the headline path: the chaining seams (seeds -> candidate transitions ->
+    find_best_chains) and multi-mapping (max_multimaps = 3 on a repeat graph).  Kernel time only, with a parity count against
+    the CPU restatement on a sample."""
+    import helpers as H
+    import test_chain_golden as TC
+    import test_chain_candidates as TK
+    from vg_b200 import capi, synth
+    out = {}
+    threads, _ = usable_cpus()
+    g = synth.make_variant_graph()
+    index = g.build_index()
+    dev = capi.Device(index, ordinal)
+    rng = np.random.default_rng(77)
+    problems, anchors = [], []
+    for _ in range(n_problems):
+        h = int(rng.integers(0, len(g.hap_node)))
+        base = int(rng.integers(0, len(g.hap_node[h]) - 1600))
+        starts = sorted(set(int(x) for x in rng.integers(0, 1500, size=int(rng.integers(8, 64)))))
+        jitter = rng.integers(-3, 4, size=len(starts))
+        seeds = [(2 * int(g.hap_node[h][base + s]), int(g.hap_off[h][base + s])) for s in starts]
+        A = np.zeros(len(starts), capi.chain_anchor_dt)
+        A["read_start"] = np.maximum(0, np.asarray(starts) + jitter); A["length"] = 12; A["score"] = rng.integers(5, 13, size=len(starts))
+        A["end_hint_offset"] = 12; A["base_seed_length"] = 12
+        order = np.argsort(A["read_start"], kind="stable")
+        problems.append([seeds[i] for i in order]); anchors.append(A[order])
+    best_c = best_d = None
+    for _ in range(2):
+        cands = dev.chain_candidates_batch(problems, 300)
+        best_c = dev.kernel_ms() if best_c is None else min(best_c, dev.kernel_ms())
+        p = TC.params(max_chains=2)
+        got = dev.chain_batch(list(zip(anchors, cands)), p)
+        best_d = dev.kernel_ms() if best_d is None else min(best_d, dev.kernel_ms())
+    bad = 0
+    for i in range(check):
+        want_c = TK.oracle_candidates(index, problems[i], 300)
+        bad += int(cands[i].tobytes() != want_c.tobytes() or got[i] != TC.oracle_chain(anchors[i], want_c, p))
+    out["chaining seams (gb_chain_candidates_batch + gb_chain_batch), config-2 graph"] = {
+        "problems": n_problems, "seeds": int(sum(len(x) for x in problems)), "candidates": int(sum(len(c) for c in cands)),
+        "candidates_kernel_ms": best_c, "chain_kernel_ms": best_d, "problems_per_s": n_problems / ((best_c + best_d) / 1e3),
+        "parity": {"problems_checked": check, "mismatching_problems": bad}}
+    dev.close(); index.close()
+
+    g = synth.make_variant_graph(length=60000, n_snp=100, n_ins=10, n_del=10, n_haps=4, seed=23, repeat_unit=600, repeat_copies=6)
+    index = g.build_index()
+    dev = capi.Device(index, ordinal)
+    n, k, chk = 100_000, 3, 5000
+    rs = synth.simulate_reads(g, n, length=150, sub_rate=0.01, seed=36)
+    p = H.default_map_params(); p.max_multimaps = k
+    rbuf, qbuf, read_off = H.pack_reads(rs.reads, rs.quals)
+    best = None
+    for _ in range(2):
+        got = dev.map_arrays(rbuf, qbuf, read_off, p)
+        best = dev.kernel_ms() if best is None else min(best, dev.kernel_ms())
+    want = H.oracle_map(index, rs.reads[:chk], rs.quals[:chk], p, threads=threads)
+    sub = tuple(np.concatenate([got[0][j * n: j * n + chk] for j in range(k)]) if i == 0 else (got[i][:chk] if i == 3 else got[i]) for i in range(4))
+    bad = H.compare_alignments(sub, want, chk, k=k)
+    out["max_multimaps = 3, repeat graph (6 copies of a 600 bp unit), 150 bp SE"] = {
+        "reads": n, "reads_per_s": n / (best / 1e3), "kernel_ms": best,
+        "secondary_records": int(((got[0]["flags"] & capi.GB_ALN_SECONDARY) != 0).sum()),
+        "parity": {"reads_checked": chk, "records_checked": chk * k, "mismatching_records": len(bad)}}
+    dev.close(); index.close()
+    return out
+
+
 # ---------------------------------------------------------------------------------------
 def main():
     ap = argparse.ArgumentParser()
@@ -644,6 +709,10 @@ def main():
             secondary = secondary_workloads(local_rank)
         except Exception as e:                       # never lose the headline line to a secondary workload
             secondary = {"error": repr(e)}
+        try:
+            secondary.update(secondary_seams(local_rank))
+        except Exception as e:
+            secondary["seams_error"] = repr(e)
     line = {
         "metric": "giraffe reads/sec (150 bp PE, synthetic)", "value": value, "unit": "reads/s", "n_gpus": world,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": dev_ms, "higher_is_better": True, "scaling": args.scaling,
