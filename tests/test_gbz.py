@@ -437,7 +437,9 @@ def test_min_files_that_do_not_fit_are_refused(tmp_path):
     cases = {
         "tag.min": lambda b: struct.pack_into("<I", b, 0, 0x12345678),
         "version.min": lambda b: struct.pack_into("<I", b, 4, 9),
-        "syncmers.min": lambda b: struct.pack_into("<Q", b, 64, W(8) | 1),
+        "syncmers.min": lambda b: struct.pack_into("<Q", b, 64, W(8) | 0x100),
+        "key128.min": lambda b: struct.pack_into("<Q", b, 64, 128),
+        "otherflag.min": lambda b: struct.pack_into("<Q", b, 64, W(8) | 0x400),
         "multi.min": lambda b: struct.pack_into("<Q", b, 48, W(6) + 1),                       # values != keys: a key with two occurrences
         "pointer.min": lambda b: struct.pack_into("<Q", b, 8 * (10 + 4 * first), W(10 + 4 * first) | (1 << 63)),
         "otherkmer.min": lambda b: struct.pack_into("<Q", b, 8 * (10 + 4 * first), W(10 + 4 * first) ^ (3 << 60)),   # first base of the key changed

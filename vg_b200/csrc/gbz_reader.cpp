@@ -120,7 +120,7 @@ int fail(const char* why) { if (getenv("GB_GBZ_DEBUG")) fprintf(stderr, "gbz rea
 // the file the reference ships for its test GBZ (test/primers/y.min, kept as tests/golden/gbz/y.min) and checked there
 // cell by cell against this library's own minimizer scan (tests/test_gbz.py):
 //   9-word header  tag 0x31513151 | version 10 << 32, k, w, keys, (unused), max_keys, values, unique, flags
-//                  (flags bit 0 = syncmers, refused; bits 5.. = payload words, 2: vg's 16-byte zipcode payload)
+//                  (flags 0x40 in that file: bits 0-7 the key size in bits, 64; bit 8 = syncmers, refused)
 //   word 9         capacity, then capacity 32-byte cells: key, position, payload[2]; the empty key is 2^63 - 1
 //   after the table one 64-bit count of multi-occurrence values: 0 in that file.
 // Keys with SEVERAL occurrences (key bit 63 set; values == unique is false) are laid out after the table in a way that
@@ -139,8 +139,11 @@ static int read_min_file(const char* path, MinFile& m) {
     if ((uint32_t)W[0] != 0x31513151u || (W[0] >> 32) != 10) return fail("not a minimizer index version 10");
     const uint64_t k = W[1], w = W[2], keys = W[3], values = W[6], unique = W[7], flags = W[8], capacity = W[9];
     if (k == 0 || k > 31 || w == 0 || w > 4096) return fail(".min k / w");
-    if ((flags & 1u) != 0) return fail(".min holds syncmers, not minimizers");
-    if ((flags >> 5) != 2) return fail(".min payload is not 16 bytes");
+    // flags: bits 0-7 = key size in bits (64: Key64, the only key type giraffe uses), bit 8 = syncmers; anything else
+    // (weighted minimizers, further bits) is refused.  The 16-byte payload shows in the 32-byte cells below.
+    if ((flags & 0xFFu) != 64) return fail(".min keys are not 64-bit");
+    if ((flags & 0x100u) != 0) return fail(".min holds syncmers, not minimizers");
+    if ((flags & ~0x1FFull) != 0) return fail(".min carries flags this reader does not know");
     if (capacity == 0 || (capacity & (capacity - 1)) != 0 || capacity > (W.size() - 10) / 4) return fail(".min capacity");
     if (keys > capacity || values != keys || unique != keys) return fail(".min has keys with several occurrences (layout not covered)");
     if (W.size() != 10 + 4 * capacity + 1 || W.back() != 0) return fail(".min tail");
