@@ -605,6 +605,7 @@ typedef struct {
     uint64_t start_paths, end_paths;           /* anchor_start_paths(), anchor_end_paths() (path_flags_t)               */
 } gb_chain_anchor;                             /* 48 bytes */
 typedef struct { uint32_t from, to; uint64_t graph_distance; } gb_chain_candidate;     /* 16 bytes */
+#define GB_CHAIN_MAX_ANCHORS 65535u            /* anchors (seeds) per problem: both kernels do all-pairs work inside a problem */
 typedef struct {
     int32_t  item_bonus;                       /* ChainScoringScheme, chain_items.hpp:407-418 */
     int32_t  recombination_penalty, consistency_bonus;

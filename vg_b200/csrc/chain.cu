@@ -309,6 +309,8 @@ static int chain_batch_impl(gb_device* d, const gb_chain_params* P, uint32_t n_p
     for (uint32_t p = 0; p < n_problems; p++) {
         if (anchor_off[p + 1] < anchor_off[p] || cand_off[p + 1] < cand_off[p]) return GB_ERR_ARG;
         const uint64_t a0 = anchor_off[p], n = anchor_off[p + 1] - a0;
+        // the traceback starts are ordered by a rank sort (n^2 / 32 steps per warp): bound the problem so one call cannot run for minutes
+        if (n > GB_CHAIN_MAX_ANCHORS) { g_last_error = "gb_chain_batch: more than GB_CHAIN_MAX_ANCHORS anchors in one problem"; return GB_ERR_ARG; }
         for (uint64_t i = 0; i < n; i++) {
             const gb_chain_anchor& a = anchors[a0 + i];
             // the DP visits destinations in index order: anchors must come sorted by read start, and an anchor covers >= 1 base
@@ -394,6 +396,7 @@ static int chain_candidates_impl(gb_device* d, uint32_t n_problems, const uint32
     std::vector<uint32_t> pb(total), pe(total);
     for (uint32_t p = 0; p < n_problems; p++) {
         if (seed_off[p + 1] < seed_off[p]) return GB_ERR_ARG;
+        if (seed_off[p + 1] - seed_off[p] > GB_CHAIN_MAX_ANCHORS) { g_last_error = "gb_chain_candidates_batch: more than GB_CHAIN_MAX_ANCHORS seeds in one problem"; return GB_ERR_ARG; }
         for (uint64_t i = seed_off[p]; i < seed_off[p + 1]; i++) {
             const uint32_t v = seed_pos[2 * i], o = seed_pos[2 * i + 1];
             if (v < 2 || v >= d->h_node_len.size() || d->h_node_len[v] == 0 || o >= d->h_node_len[v]) { g_last_error = "gb_chain_candidates_batch: seed position outside the graph"; return GB_ERR_ARG; }
