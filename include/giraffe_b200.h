@@ -621,6 +621,23 @@ int gb_chain_batch(gb_device* dev, const gb_chain_params* params, uint32_t n_pro
                    int32_t* dp_score, uint32_t* dp_source, uint64_t* dp_paths, uint32_t* dp_rec,
                    uint32_t* n_chains, int32_t* chain_score, uint32_t* chain_begin, uint32_t* chain_count,
                    uint32_t* chain_items);
+/* The same, also returning what add_transition_if_legal made of every candidate: candidate_indel[c] = the indel size of the
+ * transition, 0xffffffff for a candidate that is not one (candidate_indel may be NULL). */
+int gb_chain_batch_transitions(gb_device* dev, const gb_chain_params* params, uint32_t n_problems,
+                               const gb_chain_anchor* anchors, const uint64_t* anchor_off,
+                               const gb_chain_candidate* candidates, const uint64_t* cand_off,
+                               int32_t* dp_score, uint32_t* dp_source, uint64_t* dp_paths, uint32_t* dp_rec,
+                               uint32_t* n_chains, int32_t* chain_score, uint32_t* chain_begin, uint32_t* chain_count,
+                               uint32_t* chain_items, uint32_t* candidate_indel);
+/* MinimizerMapper::to_anchor (minimizer_mapper_from_chains.cpp:3978-4038), host side: seed i = position seed_pos[2i],
+ * seed_pos[2i + 1] (oriented node, offset: the FIRST graph base of a forward-read-strand minimizer's match, the LAST base of a
+ * reverse-read-strand one, as the seeds of find_seeds carry them) of a minimizer with pin offset min_offset[i]
+ * (Minimizer::value.offset), strand min_is_reverse[i] and length min_length[i].  The anchor is the part of the match on the
+ * seed's node (margins record what was cut off, the hint offsets where the seed position lies inside the anchor), scored as an
+ * exact match of the whole minimizer.  paths (may be NULL) = Seed::paths.  Pinned by unittest/minimizer_mapper.cpp:882-1048. */
+int gb_chain_anchors(const gb_flat_index* ix, const gb_scores* scores, uint32_t n, const uint32_t* seed_pos,
+                     const uint32_t* min_offset, const uint8_t* min_is_reverse, const uint32_t* min_length,
+                     const uint64_t* paths, gb_chain_anchor* out);
 
 /* The candidate side of the same seam: what zip_tree_transition_iterator enumerates for find_best_chains
  * (chain_items.cpp:116-260 over ZipCodeTree::find_distances, zip_code_tree.cpp): for every destination seed the seeds it

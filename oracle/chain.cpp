@@ -94,7 +94,7 @@ extern "C" int oracle_chain(const gb_chain_params* P, uint32_t n_anchors, const 
                             uint64_t n_candidates, const gb_chain_candidate* candidates,
                             int32_t* dp_score, uint32_t* dp_source, uint64_t* dp_paths, uint32_t* dp_rec,
                             uint32_t* n_chains, int32_t* chain_score, uint32_t* chain_begin, uint32_t* chain_count,
-                            uint32_t* chain_items) {
+                            uint32_t* chain_items, uint32_t* candidate_indel) {
     *n_chains = 0;
     if (n_anchors == 0) return 0;                          // find_best_chains :748-755: one empty chain of score 0
     std::vector<Anchor> to_chain(n_anchors);
@@ -104,8 +104,10 @@ extern "C" int oracle_chain(const gb_chain_params* P, uint32_t n_anchors, const 
     std::vector<Transition> all_transitions;
     for (uint64_t c = 0; c < n_candidates; c++) {
         if (candidates[c].from >= n_anchors || candidates[c].to >= n_anchors) return -1;
+        const size_t before = all_transitions.size();
         add_transition_if_legal(all_transitions, to_chain, P->max_read_lookback_bases, P->max_indel_bases,
                                 candidates[c].from, candidates[c].to, candidates[c].graph_distance);
+        if (candidate_indel) candidate_indel[c] = all_transitions.size() > before ? (uint32_t)all_transitions.back().indel_size : 0xffffffffu;
     }
     std::stable_sort(all_transitions.begin(), all_transitions.end(), [&](const Transition& a, const Transition& b) {
         return to_chain[a.to_anchor].read_start() < to_chain[b.to_anchor].read_start();
@@ -202,4 +204,29 @@ extern "C" int oracle_chain(const gb_chain_params* P, uint32_t n_anchors, const 
     }
     *n_chains = (uint32_t)tracebacks.size();
     return 0;
+}
+
+// MinimizerMapper::to_anchor, minimizer_mapper_from_chains.cpp:3978-4038 (test entry; node_len = length of the seed's node)
+extern "C" void oracle_to_anchor(const gb_scores* scores, uint32_t node_len, uint32_t seed_offset, uint32_t min_offset, int min_is_reverse,
+                                 uint32_t min_length, uint64_t paths, gb_chain_anchor* out) {
+    size_t length, read_start, hint_start, margin_left, margin_right;
+    if (min_is_reverse) {
+        size_t graph_end_offset = (size_t)seed_offset + 1;
+        length = std::min((size_t)min_length, graph_end_offset);
+        margin_left = (size_t)min_length - length;
+        margin_right = 0;
+        read_start = (size_t)min_offset + 1 - length;
+        hint_start = length - 1;
+    } else {
+        length = std::min((size_t)min_length, (size_t)node_len - seed_offset);
+        margin_left = 0;
+        margin_right = (size_t)min_length - length;
+        read_start = min_offset;
+        hint_start = 0;
+    }
+    int score = scores->match * (int)(margin_left + length + margin_right);         // score_exact_match(aln, read_start - margin_left, ...)
+    // Anchor::Anchor(read_start, graph_start, length, margin_before, margin_after, score, seed, hint, hint_start, skippable, paths), chain_items.hpp:231-244
+    out->read_start = (uint32_t)read_start; out->length = (uint32_t)length; out->margin_before = (uint32_t)margin_left; out->margin_after = (uint32_t)margin_right;
+    out->score = score; out->start_hint_offset = (uint32_t)hint_start; out->end_hint_offset = (uint32_t)(length - hint_start);
+    out->base_seed_length = (uint32_t)(margin_left + length + margin_right); out->start_paths = out->end_paths = paths;
 }

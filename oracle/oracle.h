@@ -64,7 +64,9 @@ int oracle_chain(const gb_chain_params* P, uint32_t n_anchors, const gb_chain_an
                  uint64_t n_candidates, const gb_chain_candidate* candidates,
                  int32_t* dp_score, uint32_t* dp_source, uint64_t* dp_paths, uint32_t* dp_rec,
                  uint32_t* n_chains, int32_t* chain_score, uint32_t* chain_begin, uint32_t* chain_count,
-                 uint32_t* chain_items);
+                 uint32_t* chain_items, uint32_t* candidate_indel /* may be NULL */);
+void oracle_to_anchor(const gb_scores* scores, uint32_t node_len, uint32_t seed_offset, uint32_t min_offset, int min_is_reverse,
+                      uint32_t min_length, uint64_t paths, gb_chain_anchor* out);
 
 #ifdef __cplusplus
 }

@@ -227,3 +227,79 @@ def test_every_position_pair_of_the_reference_graphs_equals_exhaustive_shortest_
     got_rev = as_set(oracle_candidates(index, rev, INF))
     assert got_rev == {(j, i, d) for i, j, d in got}
     index.close()
+
+
+# ---- unittest/minimizer_mapper.cpp:882-1048: "can make correct anchors from minimizers and their zip codes" --------------------------
+# A 10 bp read along a 10 bp node, four minimizer hits: 3 bp at the read start (anchored at its first or, as a reverse-strand
+# minimizer, its last base), 3 bp at the read end (likewise), a 3 bp one overlapping the first, a 2 bp one abutting the first.
+# Expected: read_start == forward_offset, length == minimizer length, and exactly the transitions (0,1) (2,1) (3,1) (0,3), all
+# with indel 0 — for both graph strands and all four strand combinations of the outer minimizers.
+
+def anchor_case(graph_reverse_strand, a_rev, b_rev):
+    hits = [((2 if a_rev else 0), a_rev, 3), ((9 if b_rev else 7), b_rev, 3), (1, False, 3), (3, False, 2)]      # (offset = pin, is_reverse, length)
+    seeds = [(2 * 1 + int(graph_reverse_strand), off) for off, _, _ in hits]          # the graph position equals the read position: same strand walk
+    forward_offset = [off - (ln - 1) if rev else off for off, rev, ln in hits]        # Minimizer::forward_offset, minimizer_mapper.hpp:583-592
+    return hits, seeds, forward_offset
+
+
+def oracle_to_anchor(node_len, seed_offset, min_offset, rev, length):
+    lib = H.oracle_lib()
+    lib.oracle_to_anchor.restype = None
+    lib.oracle_to_anchor.argtypes = [C.POINTER(capi.Scores), C.c_uint32, C.c_uint32, C.c_uint32, C.c_int, C.c_uint32, C.c_uint64, C.c_void_p]
+    out = np.zeros(1, capi.chain_anchor_dt)
+    lib.oracle_to_anchor(C.byref(capi.DEFAULT_SCORES), node_len, seed_offset, min_offset, int(rev), length, 0, capi.ptr(out))
+    return out[0]
+
+
+EXPECTED_TRANSITIONS = {(0, 1): 0, (2, 1): 0, (3, 1): 0, (0, 3): 0}
+
+
+@pytest.mark.parametrize("graph_reverse_strand", [False, True])
+@pytest.mark.parametrize("a_rev", [False, True])
+@pytest.mark.parametrize("b_rev", [False, True])
+def test_anchors_and_transitions_match_the_reference_minimizer_mapper_test(graph_reverse_strand, a_rev, b_rev):
+    import test_chain_golden as T
+    index = capi.HostIndex(["AAAAAAAAAA"], [[2]], k=5, w=3)
+    hits, seeds, fwd = anchor_case(graph_reverse_strand, a_rev, b_rev)
+    anchors = capi.chain_anchors(index, seeds, [h[0] for h in hits], [h[1] for h in hits], [h[2] for h in hits])
+    for i, (off, rev, ln) in enumerate(hits):
+        assert int(anchors[i]["read_start"]) == fwd[i] and int(anchors[i]["length"]) == ln          # :1003-1006
+        assert anchors[i].tobytes() == oracle_to_anchor(10, seeds[i][1], off, rev, ln).tobytes()
+        assert int(anchors[i]["score"]) == ln and int(anchors[i]["start_hint_offset"]) == (ln - 1 if rev else 0)
+    cands = oracle_candidates(index, seeds, INF)
+    got = T.oracle_chain(anchors, cands, T.params(max_indel_bases=65535), transitions=True)
+    assert got == EXPECTED_TRANSITIONS                                                               # :1024-1045
+    index.close()
+
+
+def test_anchors_are_cut_at_node_ends():
+    """to_anchor keeps the part of the match on the seed's node (:3997, :4015); the margins record the rest."""
+    index = capi.HostIndex(["ACGTACGT", "TTGCA"], [[2, 4]], k=5, w=3)
+    a = capi.chain_anchors(index, [(2, 6), (4, 1)], [20, 40], [0, 1], [5, 5])
+    assert (int(a[0]["length"]), int(a[0]["margin_before"]), int(a[0]["margin_after"]), int(a[0]["read_start"])) == (2, 0, 3, 20)
+    assert (int(a[1]["length"]), int(a[1]["margin_before"]), int(a[1]["margin_after"]), int(a[1]["read_start"])) == (2, 3, 0, 39)
+    assert int(a[0]["score"]) == 5 and int(a[1]["end_hint_offset"]) == 1 and int(a[1]["base_seed_length"]) == 5
+    with pytest.raises(capi.GbError):
+        capi.chain_anchors(index, [(2, 8)], [0], [0], [5])
+    index.close()
+
+
+@pytest.mark.gpu
+def test_cuda_anchors_candidates_and_transitions_match_the_reference_minimizer_mapper_test():
+    import test_chain_golden as T
+    index = capi.HostIndex(["AAAAAAAAAA"], [[2]], k=5, w=3)
+    dev = capi.Device(index, 0)
+    for graph_reverse_strand in (False, True):
+        for a_rev in (False, True):
+            for b_rev in (False, True):
+                hits, seeds, fwd = anchor_case(graph_reverse_strand, a_rev, b_rev)
+                anchors = capi.chain_anchors(index, seeds, [h[0] for h in hits], [h[1] for h in hits], [h[2] for h in hits])
+                cands = dev.chain_candidates_batch([seeds])[0]
+                order = np.argsort(anchors["read_start"], kind="stable")                 # gb_chain_batch takes anchors in read order
+                rank = np.empty(len(order), np.uint32); rank[order] = np.arange(len(order))
+                c = cands.copy(); c["from"] = rank[cands["from"]]; c["to"] = rank[cands["to"]]
+                res = dev.chain_batch([(anchors[order], c)], T.params(max_indel_bases=65535), transitions=True)[0]
+                back = {(int(order[f]), int(order[t])): i for (f, t), i in res["transitions"].items()}
+                assert back == EXPECTED_TRANSITIONS
+                assert res["dp"] == T.oracle_chain(anchors[order], c, T.params(max_indel_bases=65535))["dp"]
+    dev.close(); index.close()

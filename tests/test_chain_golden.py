@@ -27,19 +27,22 @@ def params(**kw):
     return p
 
 
-def oracle_chain(anchors, cands, p):
+def oracle_chain(anchors, cands, p, transitions=False):
     lib = H.oracle_lib()
     lib.oracle_chain.restype = C.c_int
-    lib.oracle_chain.argtypes = [C.POINTER(capi.ChainParams), C.c_uint32, C.c_void_p, C.c_uint64] + [C.c_void_p] * 10
+    lib.oracle_chain.argtypes = [C.POINTER(capi.ChainParams), C.c_uint32, C.c_void_p, C.c_uint64] + [C.c_void_p] * 11
     anchors = np.ascontiguousarray(anchors, dtype=A); cands = np.ascontiguousarray(cands, dtype=CD)
     n = len(anchors); k = int(p.max_chains)
     dps = np.zeros(n + 1, np.int32); src = np.zeros(n + 1, np.uint32); pth = np.zeros(n + 1, np.uint64); rec = np.zeros(n + 1, np.uint32)
     nch = np.zeros(1, np.uint32); cs = np.zeros(k + n + 1, np.int32); cb = np.zeros(k + n + 1, np.uint32); cc = np.zeros(k + n + 1, np.uint32)
     items = np.zeros(n + 1, np.uint32)
     a = np.concatenate([anchors, np.zeros(1, A)]); c = np.concatenate([cands, np.zeros(1, CD)])
+    indel = np.zeros(len(cands) + 1, np.uint32)
     rc = lib.oracle_chain(C.byref(p), n, capi.ptr(a), len(cands), capi.ptr(c), capi.ptr(dps), capi.ptr(src), capi.ptr(pth), capi.ptr(rec),
-                          capi.ptr(nch), capi.ptr(cs), capi.ptr(cb), capi.ptr(cc), capi.ptr(items))
+                          capi.ptr(nch), capi.ptr(cs), capi.ptr(cb), capi.ptr(cc), capi.ptr(items), capi.ptr(indel))
     assert rc == 0
+    if transitions:
+        return {(int(x["from"]), int(x["to"])): int(i) for x, i in zip(cands, indel[:len(cands)]) if i != 0xffffffff}
     return {"dp": [(int(dps[i]), int(src[i]), int(pth[i]), int(rec[i])) for i in range(n)],
             "chains": [(int(cs[c]), [int(x) for x in items[int(cb[c]): int(cb[c]) + int(cc[c])]]) for c in range(int(nch[0]))]}
 

@@ -183,6 +183,10 @@ def load_library() -> C.CDLL:
     lib.gb_chain_params_default.restype = None
     lib.gb_chain_batch.argtypes = [vp, C.POINTER(ChainParams), u32, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp]
     lib.gb_chain_batch.restype = C.c_int
+    lib.gb_chain_batch_transitions.argtypes = [vp, C.POINTER(ChainParams), u32, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp]
+    lib.gb_chain_batch_transitions.restype = C.c_int
+    lib.gb_chain_anchors.argtypes = [C.POINTER(FlatIndex), C.POINTER(Scores), u32, vp, vp, vp, vp, vp, vp]
+    lib.gb_chain_anchors.restype = C.c_int
     lib.gb_chain_candidates_batch.argtypes = [vp, u32, vp, vp, u64, vp, u64, vp]
     lib.gb_chain_candidates_batch.restype = C.c_int
     lib.gb_fragment_create.argtypes = [u64, u64, C.c_double]
@@ -365,6 +369,22 @@ class HostIndex:
 
 
 GB_PAIR_PAIRED, GB_PAIR_TRAINING, GB_PAIR_BUFFERED = 0, 1, 2
+
+
+def chain_anchors(index, seeds, min_offset, min_is_reverse, min_length, paths=None, scores=None):
+    """gb_chain_anchors (MinimizerMapper::to_anchor): seeds = [(oriented node, offset)], per-seed minimizer pin offset, strand, length."""
+    lib = load_library()
+    n = len(seeds)
+    pos = np.ascontiguousarray(np.array(list(seeds) + [(0, 0)], dtype=np.uint32).reshape(-1))
+    mo = np.ascontiguousarray(list(min_offset) + [0], dtype=np.uint32); mr = np.ascontiguousarray(list(min_is_reverse) + [0], dtype=np.uint8)
+    ml = np.ascontiguousarray(list(min_length) + [0], dtype=np.uint32)
+    pa = None if paths is None else np.ascontiguousarray(list(paths) + [0], dtype=np.uint64)
+    out = np.zeros(n + 1, dtype=chain_anchor_dt)
+    sc = scores or DEFAULT_SCORES
+    rc = lib.gb_chain_anchors(C.byref(index.view), C.byref(sc), n, ptr(pos), ptr(mo), ptr(mr), ptr(ml), None if pa is None else ptr(pa), ptr(out))
+    if rc != GB_OK:
+        raise GbError(rc, "gb_chain_anchors")
+    return out[:n]
 
 
 def emit_text(kind, flat_index, aln, maps, edits, rbuf, qbuf, read_off, names=None):
@@ -651,9 +671,10 @@ class Device:
             raise GbError(rc, "gb_chain_candidates_batch")
         return [out[int(coff[p]): int(coff[p + 1])].copy() for p in range(n)]
 
-    def chain_batch(self, problems, params=None):
+    def chain_batch(self, problems, params=None, transitions=False):
         """gb_chain_batch.  problems: list of (anchors, candidates) structured arrays (chain_anchor_dt sorted by read_start,
-        chain_candidate_dt).  Returns per problem {"dp": [(score, source, paths, rec)], "chains": [(score, [anchor indices])]}."""
+        chain_candidate_dt).  Returns per problem {"dp": [(score, source, paths, rec)], "chains": [(score, [anchor indices])]};
+        transitions=True (gb_chain_batch_transitions) adds "transitions": {(from, to): indel} of the legal candidates."""
         lib = load_library()
         if params is None:
             params = ChainParams(); lib.gb_chain_params_default(C.byref(params))
@@ -666,14 +687,22 @@ class Device:
         dps = np.zeros(ta + 1, np.int32); dpsrc = np.zeros(ta + 1, np.uint32); dpp = np.zeros(ta + 1, np.uint64); dpr = np.zeros(ta + 1, np.uint32)
         nch = np.zeros(n, np.uint32); cs = np.zeros(n * k, np.int32); cb = np.zeros(n * k, np.uint32); cc = np.zeros(n * k, np.uint32)
         items = np.zeros(ta + 1, np.uint32)
-        rc = lib.gb_chain_batch(self._h, C.byref(params), n, ptr(anchors), ptr(aoff), ptr(cands), ptr(coff),
-                                ptr(dps), ptr(dpsrc), ptr(dpp), ptr(dpr), ptr(nch), ptr(cs), ptr(cb), ptr(cc), ptr(items))
+        indel = np.zeros(int(coff[-1]) + 1, np.uint32)
+        if transitions:
+            rc = lib.gb_chain_batch_transitions(self._h, C.byref(params), n, ptr(anchors), ptr(aoff), ptr(cands), ptr(coff),
+                                                ptr(dps), ptr(dpsrc), ptr(dpp), ptr(dpr), ptr(nch), ptr(cs), ptr(cb), ptr(cc), ptr(items), ptr(indel))
+        else:
+            rc = lib.gb_chain_batch(self._h, C.byref(params), n, ptr(anchors), ptr(aoff), ptr(cands), ptr(coff),
+                                    ptr(dps), ptr(dpsrc), ptr(dpp), ptr(dpr), ptr(nch), ptr(cs), ptr(cb), ptr(cc), ptr(items))
         if rc != GB_OK:
             raise GbError(rc, "gb_chain_batch")
         out = []
         for p in range(n):
             a0, a1 = int(aoff[p]), int(aoff[p + 1])
-            out.append({"dp": [(int(dps[i]), int(dpsrc[i]), int(dpp[i]), int(dpr[i])) for i in range(a0, a1)],
+            if transitions:
+                c0, c1 = int(coff[p]), int(coff[p + 1])
+                tr = {(int(x["from"]), int(x["to"])): int(i) for x, i in zip(cands[c0:c1], indel[c0:c1]) if i != 0xffffffff}
+            out.append({**({"transitions": tr} if transitions else {}),"dp": [(int(dps[i]), int(dpsrc[i]), int(dpp[i]), int(dpr[i])) for i in range(a0, a1)],
                         "chains": [(int(cs[p * k + c]), [int(x) for x in items[int(cb[p * k + c]): int(cb[p * k + c]) + int(cc[p * k + c])]])
                                    for c in range(int(nch[p]))]})
         return out

@@ -298,7 +298,8 @@ static int chain_batch_impl(gb_device* d, const gb_chain_params* P, uint32_t n_p
                             const gb_chain_anchor* anchors, const uint64_t* anchor_off,
                             const gb_chain_candidate* cands, const uint64_t* cand_off,
                             int32_t* dp_score, uint32_t* dp_source, uint64_t* dp_paths, uint32_t* dp_rec,
-                            uint32_t* n_chains, int32_t* chain_score, uint32_t* chain_begin, uint32_t* chain_count, uint32_t* chain_items) {
+                            uint32_t* n_chains, int32_t* chain_score, uint32_t* chain_begin, uint32_t* chain_count, uint32_t* chain_items,
+                            uint32_t* candidate_indel) {
     if (!d || !P || !anchor_off || !cand_off || !n_chains || !chain_score || !chain_begin || !chain_count) return GB_ERR_ARG;
     if (P->max_chains == 0 || P->max_indel_bases > 65535 || P->recombination_penalty < 0 || P->consistency_bonus < 0) { g_last_error = "gb_chain_batch: parameters out of range"; return GB_ERR_ARG; }
     if (n_problems == 0) return GB_OK;
@@ -364,6 +365,7 @@ static int chain_batch_impl(gb_device* d, const gb_chain_params* P, uint32_t n_p
         GB_CUDA(cudaMemcpyAsync(dp_rec, d_rec.ptr, 4 * total_a, cudaMemcpyDeviceToHost, d->stream));
         GB_CUDA(cudaMemcpyAsync(chain_items, d_citems.ptr, 4 * total_a, cudaMemcpyDeviceToHost, d->stream));
     }
+    if (candidate_indel && total_c) GB_CUDA(cudaMemcpyAsync(candidate_indel, d_legal.ptr, 4 * total_c, cudaMemcpyDeviceToHost, d->stream));
     GB_CUDA(cudaMemcpyAsync(n_chains, d_nch.ptr, 4 * (size_t)n_problems, cudaMemcpyDeviceToHost, d->stream));
     GB_CUDA(cudaMemcpyAsync(chain_score, d_cscore.ptr, 4 * nk, cudaMemcpyDeviceToHost, d->stream));
     GB_CUDA(cudaMemcpyAsync(chain_begin, d_cbegin.ptr, 4 * nk, cudaMemcpyDeviceToHost, d->stream));
@@ -380,9 +382,54 @@ extern "C" int gb_chain_batch(gb_device* d, const gb_chain_params* P, uint32_t n
                               uint32_t* n_chains, int32_t* chain_score, uint32_t* chain_begin, uint32_t* chain_count, uint32_t* chain_items) {
     try {
         return chain_batch_impl(d, P, n_problems, anchors, anchor_off, cands, cand_off, dp_score, dp_source, dp_paths, dp_rec,
-                                n_chains, chain_score, chain_begin, chain_count, chain_items);
+                                n_chains, chain_score, chain_begin, chain_count, chain_items, nullptr);
     } catch (const std::bad_alloc&) { return GB_ERR_CAPACITY; }
     catch (...) { return GB_ERR_ARG; }
+}
+
+extern "C" int gb_chain_batch_transitions(gb_device* d, const gb_chain_params* P, uint32_t n_problems,
+                                          const gb_chain_anchor* anchors, const uint64_t* anchor_off,
+                                          const gb_chain_candidate* cands, const uint64_t* cand_off,
+                                          int32_t* dp_score, uint32_t* dp_source, uint64_t* dp_paths, uint32_t* dp_rec,
+                                          uint32_t* n_chains, int32_t* chain_score, uint32_t* chain_begin, uint32_t* chain_count, uint32_t* chain_items,
+                                          uint32_t* candidate_indel) {
+    try {
+        return chain_batch_impl(d, P, n_problems, anchors, anchor_off, cands, cand_off, dp_score, dp_source, dp_paths, dp_rec,
+                                n_chains, chain_score, chain_begin, chain_count, chain_items, candidate_indel);
+    } catch (const std::bad_alloc&) { return GB_ERR_CAPACITY; }
+    catch (...) { return GB_ERR_ARG; }
+}
+
+// MinimizerMapper::to_anchor, minimizer_mapper_from_chains.cpp:3978-4038 (host side: a few integer operations per seed)
+extern "C" int gb_chain_anchors(const gb_flat_index* ix, const gb_scores* scores, uint32_t n, const uint32_t* seed_pos,
+                                const uint32_t* min_offset, const uint8_t* min_is_reverse, const uint32_t* min_length,
+                                const uint64_t* paths, gb_chain_anchor* out) {
+    if (!ix || !scores || (n && (!seed_pos || !min_offset || !min_is_reverse || !min_length || !out))) return GB_ERR_ARG;
+    for (uint32_t i = 0; i < n; i++) {
+        const uint32_t v = seed_pos[2 * i], off = seed_pos[2 * i + 1], mlen = min_length[i];
+        if (v < 2 || v >= ix->n_nodes || ix->nodes[v].len == 0 || off >= ix->nodes[v].len || mlen == 0) { g_last_error = "gb_chain_anchors: seed outside the graph or empty minimizer"; return GB_ERR_ARG; }
+        uint32_t length, margin_left, margin_right, read_start, hint_start;
+        if (min_is_reverse[i]) {
+            const uint32_t end = off + 1;                              // the seed is the final base of the match: past-end position
+            length = std::min(mlen, end);                              // how much of the node lies before it
+            margin_left = mlen - length; margin_right = 0;
+            if (min_offset[i] + 1 < length) { g_last_error = "gb_chain_anchors: reverse minimizer runs off the read start"; return GB_ERR_ARG; }
+            read_start = min_offset[i] + 1 - length;
+            hint_start = length - 1;                                   // the seed is the last 1 bp interval
+        } else {
+            length = std::min(mlen, ix->nodes[v].len - off);           // how much of the node lies behind the seed
+            margin_left = 0; margin_right = mlen - length;
+            read_start = min_offset[i];
+            hint_start = 0;
+        }
+        gb_chain_anchor a;
+        a.read_start = read_start; a.length = length; a.margin_before = margin_left; a.margin_after = margin_right;
+        a.score = (int32_t)scores->match * (int32_t)(margin_left + length + margin_right);        // score_exact_match over the whole minimizer
+        a.start_hint_offset = hint_start; a.end_hint_offset = length - hint_start; a.base_seed_length = margin_left + length + margin_right;
+        a.start_paths = a.end_paths = paths ? paths[i] : 0;
+        out[i] = a;
+    }
+    return GB_OK;
 }
 
 static int chain_candidates_impl(gb_device* d, uint32_t n_problems, const uint32_t* seed_pos, const uint64_t* seed_off,
