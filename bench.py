@@ -701,6 +701,21 @@ def main():
         traffic_commit = prof.get("commit")
     except Exception:
         pass
+    # The path is issue-bound, not HBM-bound: the second view of the same kernel is instruction issue — warp
+    # instructions of one launch (from the same ncu capture) over the LIVE launch time, against SMs x 4 schedulers x the SM clock
+    # sampled during the timed region.
+    issue = None
+    try:
+        winst = float(prof["kernels"][dom_name]["ncu_full"]["warp_instructions"]) * chunk_reads / float(prof["reads_per_launch"])
+        sms = torch.cuda.get_device_properties(device).multi_processor_count
+        clock_hz = float(clocks["sm_mhz"]) * 1e6
+        peak_i = sms * 4 * clock_hz
+        issue = {"kernel": dom_name, "warp_instructions_per_launch": winst, "warp_instructions_per_read": winst / chunk_reads,
+                 "achieved_warp_inst_per_s": winst / (dom_ms / 1e3), "peak_warp_inst_per_s": peak_i,
+                 "frac": (winst / (dom_ms / 1e3)) / peak_i, "profile_commit": traffic_commit,
+                 "note": "instruction counts from profiles/ncu_summary_r02.json, time and clock measured in this run"}
+    except Exception:
+        pass
 
     secondary = None
     if world == 1 and not args.no_secondary:
@@ -735,6 +750,7 @@ def main():
                 "ms_per_step": e2e_ms},
         "roofline": {"bound": "hbm", "kernel": dom_name, "achieved": achieved, "peak": peak, "unit": "GB/s",
                      "frac": (achieved / peak) if achieved else None, "traffic": traffic, "traffic_profile_commit": traffic_commit,
+                     "issue": issue,
                      "kernel_ms_last_chunk": {k: round(v, 4) for k, v in kdict.items()},
                      "tail_plan": plan_stats, "pool_overflow": pool_overflow,
                      "algorithmic_bytes_per_read": B, "algorithmic_bytes_per_read_this_kernel": B_dom,
