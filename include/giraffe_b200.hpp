@@ -198,4 +198,68 @@ private:
     }
 };
 
+// ---- chaining route seams (algorithms/chain_items.hpp): anchors, the transition candidates, find_best_chains ------------------------
+namespace algorithms {
+
+struct ChainScoringScheme { int item_bonus = 0; double gap_scale = 1.0; int recombination_penalty = 0; int consistency_bonus = 0; };   // chain_items.hpp:407-418
+using Anchor = gb_chain_anchor;                 // the fields chaining reads of algorithms::Anchor (chain_items.hpp:48-276)
+using transition_candidate = gb_chain_candidate;
+
+// MinimizerMapper::to_anchor for a whole seed list (minimizer_mapper_from_chains.cpp:3969-4038): seed i = (oriented node, offset) of
+// the minimizer (pin offset, is_reverse, length) at the same index
+inline std::vector<Anchor> to_anchors(const gb_flat_index& index, const gb_scores& scores, const std::vector<std::pair<uint32_t, uint32_t>>& seeds,
+                                      const std::vector<uint32_t>& pin_offset, const std::vector<uint8_t>& is_reverse, const std::vector<uint32_t>& length) {
+    if (pin_offset.size() != seeds.size() || is_reverse.size() != seeds.size() || length.size() != seeds.size()) throw std::runtime_error("to_anchors: one minimizer per seed");
+    std::vector<uint32_t> pos; pos.reserve(2 * seeds.size() + 2);
+    for (const auto& s : seeds) { pos.push_back(s.first); pos.push_back(s.second); }
+    pos.push_back(0); pos.push_back(0);
+    std::vector<Anchor> out(seeds.size() + 1);
+    if (gb_chain_anchors(&index, &scores, (uint32_t)seeds.size(), pos.data(), pin_offset.data(), is_reverse.data(), length.data(), nullptr, out.data()) != GB_OK)
+        throw std::runtime_error(gb_last_error());
+    out.resize(seeds.size());
+    return out;
+}
+
+// what zip_tree_transition_iterator enumerates for one read (chain_items.cpp:116-260), from the library's distance model
+inline std::vector<transition_candidate> transition_candidates(gb_device* dev, const std::vector<std::pair<uint32_t, uint32_t>>& seeds, uint64_t max_graph_lookback_bases) {
+    std::vector<uint32_t> pos; pos.reserve(2 * seeds.size() + 2);
+    for (const auto& s : seeds) { pos.push_back(s.first); pos.push_back(s.second); }
+    pos.push_back(0); pos.push_back(0);
+    const uint64_t seed_off[2] = {0, seeds.size()};
+    uint64_t cand_off[2] = {0, 0};
+    int rc = gb_chain_candidates_batch(dev, 1, pos.data(), seed_off, max_graph_lookback_bases, nullptr, 0, cand_off);      // sizes first
+    if (rc != GB_OK && rc != GB_ERR_CAPACITY) throw std::runtime_error(gb_last_error());
+    std::vector<transition_candidate> out(cand_off[1] + 1);
+    if (gb_chain_candidates_batch(dev, 1, pos.data(), seed_off, max_graph_lookback_bases, out.data(), cand_off[1], cand_off) != GB_OK) throw std::runtime_error(gb_last_error());
+    out.resize(cand_off[1]);
+    return out;
+}
+
+// find_best_chains(to_chain, ..., for_each_transition, scheme, max_chains, max_indel_bases), chain_items.hpp:576: (score, anchor
+// indices left to right) per chain, best first.  to_chain in read order (the reference's VectorView), candidates over its indices.
+inline std::vector<std::pair<int, std::vector<size_t>>> find_best_chains(gb_device* dev, const std::vector<Anchor>& to_chain,
+                                                                         const std::vector<transition_candidate>& candidates,
+                                                                         const ChainScoringScheme& scheme = ChainScoringScheme(), size_t max_chains = 1,
+                                                                         size_t max_indel_bases = 100, size_t max_read_lookback_bases = ~(size_t)0) {
+    std::vector<std::pair<int, std::vector<size_t>>> result;
+    if (to_chain.empty()) { result.push_back({0, {}}); return result; }                     // :748-755
+    gb_chain_params P; gb_chain_params_default(&P);
+    P.item_bonus = scheme.item_bonus; P.gap_scale = scheme.gap_scale; P.recombination_penalty = scheme.recombination_penalty;
+    P.consistency_bonus = scheme.consistency_bonus; P.max_chains = (uint32_t)max_chains; P.max_indel_bases = max_indel_bases;
+    P.max_read_lookback_bases = max_read_lookback_bases;
+    const uint64_t aoff[2] = {0, to_chain.size()}, coff[2] = {0, candidates.size()};
+    const size_t n = to_chain.size();
+    std::vector<int32_t> dp_score(n), chain_score(max_chains); std::vector<uint32_t> dp_source(n), dp_rec(n), chain_begin(max_chains), chain_count(max_chains), items(n);
+    std::vector<uint64_t> dp_paths(n); uint32_t n_chains = 0;
+    static const transition_candidate none{0, 0, 0};
+    if (gb_chain_batch(dev, &P, 1, to_chain.data(), aoff, candidates.empty() ? &none : candidates.data(), coff, dp_score.data(), dp_source.data(), dp_paths.data(),
+                       dp_rec.data(), &n_chains, chain_score.data(), chain_begin.data(), chain_count.data(), items.data()) != GB_OK)
+        throw std::runtime_error(gb_last_error());
+    for (uint32_t c = 0; c < n_chains; c++)
+        result.push_back({chain_score[c], std::vector<size_t>(items.begin() + chain_begin[c], items.begin() + chain_begin[c] + chain_count[c])});
+    return result;
+}
+
+} // namespace algorithms
+
 } // namespace giraffe_b200
