@@ -87,6 +87,78 @@ with tempfile.TemporaryDirectory() as tmp:
             built += 1; lib.gb_index_free(hg)
     print("damaged GBZ files: refused", 400 - built, "built", built)
 
+# the .min / .zipcodes readers beside it: intact, truncated, random bytes overwritten (must refuse or build, never fault)
+lib.gb_index_from_gbz_min.argtypes = [C.c_char_p, C.c_char_p, C.c_char_p, C.POINTER(vp)]
+gdir = ROOT / "tests" / "golden" / "gbz"
+minraw, zipraw = (gdir / "y.min").read_bytes(), (gdir / "y.zipcodes").read_bytes()
+with tempfile.TemporaryDirectory() as tmp:
+    qg = os.path.join(tmp, "y.gbz"); open(qg, "wb").write(gbz)
+    qm = os.path.join(tmp, "y.min"); qz = os.path.join(tmp, "y.zipcodes")
+    open(qm, "wb").write(minraw); open(qz, "wb").write(zipraw)
+    hm = vp(); assert lib.gb_index_from_gbz_min(qg.encode(), qm.encode(), qz.encode(), C.byref(hm)) == 0; lib.gb_index_free(hm)
+    rng = np.random.default_rng(7); built = 0
+    for t in range(600):
+        bm, bz = bytearray(minraw), bytearray(zipraw)
+        which = t % 3
+        target = bm if which < 2 else bz
+        if t % 5 == 0:
+            del target[int(rng.integers(0, len(target))):]
+        else:
+            for _ in range(int(rng.integers(1, 4))):
+                hot = 96 if (which == 0) else len(target)                     # every third file: damage the header words
+                target[int(rng.integers(0, hot))] = int(rng.integers(0, 256))
+        open(qm, "wb").write(bytes(bm)); open(qz, "wb").write(bytes(bz))
+        hm = vp()
+        if lib.gb_index_from_gbz_min(qg.encode(), qm.encode(), qz.encode(), C.byref(hm)) == 0:
+            built += 1; lib.gb_index_free(hm)
+    print("damaged .min / .zipcodes files: refused", 600 - built, "built", built)
+
+# gb_index_build_with_hits: hits that lie off the graph, past a node, on the wrong k-mer (must refuse, never fault)
+lib.gb_index_build_with_hits.argtypes = [u32, vp, vp, u32, vp, vp, vp, u32, u32, u64, vp, vp, C.POINTER(vp)]
+ref_index = g.build_index()
+tb, hits = ref_index.array("table"), ref_index.array("hits")
+keys, poss = [], []
+for c in tb:
+    if int(c["key"]) != 0xFFFFFFFFFFFFFFFF:
+        for i in range(int(c["hit_cnt"])):
+            keys.append(int(c["key"])); poss.append(int(hits[int(c["hit_off"]) + i]["pos"]))
+keys = np.asarray(keys, dtype=np.uint64); poss = np.asarray(poss, dtype=np.uint64)
+hh = vp(); assert lib.gb_index_build_with_hits(len(g.node_seqs), capi.ptr(seq), capi.ptr(node_off), len(g.paths), capi.ptr(flat), capi.ptr(path_off), capi.ptr(dist), 29, 11,
+                                               len(keys), capi.ptr(keys), capi.ptr(poss), C.byref(hh)) == 0
+lib.gb_index_free(hh)
+rng = np.random.default_rng(8); refused = 0
+for t in range(200):
+    k2, p2 = keys.copy(), poss.copy()
+    i = int(rng.integers(0, len(k2)))
+    if t % 2 == 0:
+        p2[i] = np.uint64(int(rng.integers(0, 1 << 40)))
+    else:
+        k2[i] = np.uint64(int(k2[i]) ^ (1 << int(rng.integers(0, 58))))
+    hh = vp()
+    rc = lib.gb_index_build_with_hits(len(g.node_seqs), capi.ptr(seq), capi.ptr(node_off), len(g.paths), capi.ptr(flat), capi.ptr(path_off), capi.ptr(dist), 29, 11,
+                                      len(k2), capi.ptr(k2), capi.ptr(p2), C.byref(hh))
+    if rc == 0:
+        lib.gb_index_free(hh)
+    else:
+        refused += 1
+print("damaged hit lists refused:", refused, "of 200")
+ref_index.close()
+
+# multi-mapping records (secondaries, absent ranks) through the emitters
+index_r = synth.make_variant_graph(length=24000, n_snp=40, n_ins=4, n_del=4, n_haps=4, seed=23, repeat_unit=600, repeat_copies=6)
+ix_r = index_r.build_index()
+rs_r = synth.simulate_reads(index_r, 90, length=150, sub_rate=0.01, seed=36)
+pm = H.default_map_params(); pm.max_multimaps = 3
+res_r = H.oracle_map(ix_r, rs_r.reads, rs_r.quals, pm, threads=2)
+rb_r, qb_r, ro_r = H.pack_reads(rs_r.reads, rs_r.quals)
+aln_r = np.ascontiguousarray(res_r[0]); out_r = np.zeros(1 << 22, dtype=np.uint8)
+for fn in (lib.gb_emit_gaf, lib.gb_emit_json, lib.gb_emit_gam):
+    used = u64()
+    assert fn(C.byref(ix_r.view), len(aln_r), capi.ptr(aln_r), capi.ptr(res_r[1]), len(res_r[1]), capi.ptr(res_r[2]), len(res_r[2]), rs_r.n, capi.ptr(rb_r), capi.ptr(qb_r),
+              capi.ptr(ro_r), None, None, capi.ptr(out_r), len(out_r), C.byref(used)) == 0
+print("multi-mapping records emitted:", int(((aln_r["flags"] & 16) == 0).sum()), "of", len(aln_r), "ranks present")
+ix_r.close()
+
 # records from the oracle (tail alignments, soft clips, unmapped reads, pairs), through all three emitters
 index = g.build_index()
 rs = synth.simulate_pairs(g, 120, sub_rate=0.02, seed=5, indel_rate=0.002)
