@@ -439,7 +439,8 @@ int gb_bgzf_compress(const void* in, uint64_t in_bytes, int level, void* out, ui
 
 /* Device-pointer variant of both (paired != 0 selects map_paired): every pointer is a DEVICE
  * address (inputs already resident in HBM, outputs stay in HBM); all reads are at most
- * max_read_len long; d_totals[2] (device) receives {mappings used, edits used}.  The call only
+ * max_read_len long; d_aln holds n_reads * p->max_multimaps records (rank-major, as gb_map_batch);
+ * d_totals[2] (device) receives {mappings used, edits used}.  The call only
  * enqueues work on the handle's stream (gb_device_set_stream) and returns; use
  * gb_device_synchronize or stream ordering before reading the outputs. */
 int gb_map_batch_device(gb_device* dev, const gb_map_params* p, int paired, uint32_t n_reads,
