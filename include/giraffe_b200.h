@@ -139,7 +139,10 @@ typedef struct gb_host_index gb_host_index;
  * (chains of cut nodes and sites, see gb_dist_payload) — any graph whose haplotypes walk forward through a DAG;
  * a cycle, a reversing step or a site of more than 4096 nodes leaves the index WITHOUT a distance model
  * (gb_index_has_distance_model() == 0: extension / DP / WFA seams work on it, mapping needs the model).
- * dist != NULL: a hand-made payload indexed by node id (slots without tables). */
+ * dist != NULL: a hand-made payload indexed by node id (slots without tables).
+ * The minimizer table is found either by scanning every haplotype end to end or — with more than 32 haplotypes, or
+ * GIRAFFE_B200_WINDOW_BUILDER=1 — by visiting every haplotype-consistent window of k + w - 1 bases once through GBWT
+ * search states (gbwtgraph's index_haplotypes); both give the same table. */
 int gb_index_build(uint32_t n_node_ids, const uint8_t* node_seq, const uint64_t* node_off,
                    uint32_t n_paths, const uint32_t* path_nodes, const uint64_t* path_off,
                    const gb_dist_payload* dist, uint32_t k, uint32_t w,

@@ -479,3 +479,24 @@ def test_build_with_hits_equals_the_haplotype_scan():
     for name in ("nodes", "gbwt", "dist", "table", "hits"):
         assert got.array(name).tobytes() == ref.array(name).tobytes(), name
     got.close(); ref.close()
+
+
+@pytest.mark.parametrize("which", ["variants", "repeats", "nested", "branchy", "reference gbz"])
+def test_window_enumeration_builds_the_same_index_as_the_haplotype_scan(which, monkeypatch):
+    """The builder's two routes to the minimizer table — every haplotype end to end, or every haplotype-consistent
+    (k + w - 1)-window once by following GBWT search states (what gbwtgraph's index_haplotypes does; chosen when there are
+    more than 32 haplotypes) — must give byte-identical indexes."""
+    def build():
+        if which == "reference gbz":
+            return capi.HostIndex.from_gbz(GBZ, k=31, w=50)
+        g = {"variants": lambda: synth.make_variant_graph(length=40000, n_snp=120, n_ins=15, n_del=15, n_haps=8, seed=4),
+             "repeats": lambda: synth.make_variant_graph(length=24000, n_snp=40, n_ins=4, n_del=4, n_haps=4, seed=23, repeat_unit=600, repeat_copies=6),
+             "nested": lambda: synth.make_nested_graph(n_items=120, n_haps=10, seed=5),
+             "branchy": lambda: synth.make_branchy_graph(n_layers=600, n_haps=16, seed=4)}[which]()
+        return g.build_index() if which != "nested" else g.build_index(k=11, w=5)
+    monkeypatch.setenv("GIRAFFE_B200_WINDOW_BUILDER", "0"); a = build()
+    monkeypatch.setenv("GIRAFFE_B200_WINDOW_BUILDER", "1"); b = build()
+    assert int(a.view.n_hits) == int(b.view.n_hits) and int(a.view.n_hits) > 50
+    for name in ("nodes", "gbwt", "dist", "table", "hits"):
+        assert a.array(name).tobytes() == b.array(name).tobytes(), name
+    a.close(); b.close()

@@ -14,6 +14,8 @@
 #include "minimizer_common.h"
 
 #include <algorithm>
+#include <cstdlib>
+#include <array>
 #include <cstdio>
 #include <cstring>
 #include <functional>
@@ -408,7 +410,79 @@ static int index_build_impl(uint32_t n_node_ids, const uint8_t* node_seq, const 
             kps.push_back(KP{ext_keys[i], pos});
         }
     }
-    for (uint32_t p = 0; p < n_paths && !external; p++) {
+    // Two ways to the same set of (key, position) pairs.  The scan below walks every haplotype from end to end: work ~ haplotypes x
+    // genome.  The window enumeration is what gbwtgraph's index construction does (index_haplotypes over for_each_haplotype_window,
+    // gbwtgraph @ e27bc43, absent): every haplotype-consistent window of k + w - 1 bases is visited ONCE, however many haplotypes
+    // share it, by following GBWT search states from every start position — work ~ graph x local diversity.  The minimizers of a
+    // sequence are the union of the minimizers of its windows, so both give the same table (tests/test_gbz.py builds both).
+    // Chosen by the haplotype count (more than 32: windows); GIRAFFE_B200_WINDOW_BUILDER=0|1 forces one.
+    bool use_windows = n_paths > 32;
+    if (const char* env = std::getenv("GIRAFFE_B200_WINDOW_BUILDER")) use_windows = std::atoi(env) != 0;
+    if (use_windows && !external) {
+        const uint32_t W = k + w - 1;
+        bool forward_only = true;                      // every haplotype stays on forward strands: forward starts cover every window
+        for (uint32_t p = 0; p < n_paths && forward_only; p++) for (uint32_t v : seqs[2 * p]) if (v & 1u) { forward_only = false; break; }
+        // successors of a GBWT search state (node, [lo, hi]) in record order
+        auto follow = [&](uint32_t v, int64_t lo, int64_t hi, std::vector<std::array<int64_t, 3>>& out) {
+            out.clear();
+            const gb_node_rec& nr = ix->nodes[v];
+            if (nr.size == 0) return;
+            const uint32_t* rec = ix->gbwt.data() + nr.rec_off;
+            const uint32_t n_edges = rec[0], n_runs = rec[1];
+            const uint32_t* runs = rec + 2 + 2 * n_edges;
+            std::vector<int64_t> below(n_edges, 0), cnt(n_edges, 0);
+            int64_t pos = 0;
+            for (uint32_t r = 0; r < n_runs && pos <= hi; r++) {
+                const int64_t len = runs[r] >> 10; const uint32_t e = runs[r] & 1023u;
+                const int64_t b = pos, en = pos + len;
+                below[e] += std::min<int64_t>(std::max<int64_t>(lo - b, 0), len);
+                cnt[e] += std::max<int64_t>(std::min<int64_t>(en, hi + 1) - std::max<int64_t>(b, lo), 0);
+                pos = en;
+            }
+            for (uint32_t e = 0; e < n_edges; e++) {
+                const uint32_t to = rec[2 + 2 * e];
+                if (to == 0 || cnt[e] <= 0) continue;
+                const int64_t first = (int64_t)rec[3 + 2 * e] + below[e];
+                out.push_back({(int64_t)to, first, first + cnt[e] - 1});
+            }
+        };
+        std::string win; std::vector<uint32_t> wnode, woff;
+        struct Frame { uint32_t node; int64_t lo, hi; size_t restore; };
+        std::vector<Frame> stack; std::vector<std::array<int64_t, 3>> next;
+        for (uint32_t v0 = 2; v0 < ix->n_nodes; v0++) {
+            if (ix->nodes[v0].size == 0 || (forward_only && (v0 & 1u))) continue;
+            for (uint32_t s0 = 0; s0 < ix->nodes[v0].len; s0++) {
+                stack.clear();
+                stack.push_back(Frame{v0, 0, (int64_t)ix->nodes[v0].size - 1, 0});
+                win.clear(); wnode.clear(); woff.clear();
+                bool first = true;
+                while (!stack.empty()) {
+                    const Frame f = stack.back(); stack.pop_back();
+                    win.resize(f.restore); wnode.resize(f.restore); woff.resize(f.restore);
+                    const gb_node_rec& nr = ix->nodes[f.node];
+                    for (uint32_t o = first ? s0 : 0; o < nr.len && win.size() < W; o++) { win.push_back((char)ix->seq[nr.seq_off + o]); wnode.push_back(f.node); woff.push_back(o); }
+                    first = false;
+                    if (win.size() == W) {
+                        mins.clear();
+                        gbmin::minimizers((const uint8_t*)win.data(), W, k, w, mins, nullptr);
+                        for (const auto& m : mins) {
+                            uint32_t v = wnode[m.offset], o = woff[m.offset];
+                            if (m.is_reverse) { o = ix->nodes[v].len - 1 - o; v ^= 1u; }
+                            kps.push_back(KP{m.key, ((uint64_t)v << 10) | o});
+                        }
+                        continue;
+                    }
+                    follow(f.node, f.lo, f.hi, next);
+                    for (size_t x = next.size(); x-- > 0;) stack.push_back(Frame{(uint32_t)next[x][0], next[x][1], next[x][2], win.size()});
+                }
+                if (kps.size() > (1ull << 26)) {      // keep the pair list bounded while it is full of duplicates
+                    std::sort(kps.begin(), kps.end(), [](const KP& a, const KP& b) { return a.key != b.key ? a.key < b.key : a.pos < b.pos; });
+                    kps.erase(std::unique(kps.begin(), kps.end(), [](const KP& a, const KP& b) { return a.key == b.key && a.pos == b.pos; }), kps.end());
+                }
+            }
+        }
+    }
+    for (uint32_t p = 0; p < n_paths && !external && !use_windows; p++) {
         hap.clear(); base_node.clear(); base_off.clear();
         for (uint32_t v : seqs[2 * p]) {
             const gb_node_rec& nr = ix->nodes[v];
