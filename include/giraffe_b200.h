@@ -156,8 +156,9 @@ int gb_index_view(const gb_host_index* ix, gb_flat_index* out);
  * back to back, each padded to 16 bytes, little endian.  gb_index_load checks sizes and offsets and returns
  * GB_ERR_FORMAT for anything that is not such a file; the result is freed with gb_index_free. */
 /* Build the flat index from a GBZ file (gbwtgraph::GBZ, what `vg giraffe -Z` loads, giraffe_main.cpp:1825-1881): node
- * sequences from the GBWTGraph, haplotype paths by walking the bidirectional GBWT, the distance payload from the
- * chain-of-bubbles decomposition of those paths, minimizers (k, w) by the library's own builder.  GBZ version 1 /
+ * sequences from the GBWTGraph, the GBWT records re-laid as they are (no haplotype is walked: gb_index_build_from_gbwt), the
+ * distance payload from the chain decomposition of the graph the forward records span, minimizers (k, w) by window
+ * enumeration over GBWT search states.  GBZ version 1 /
  * GBWT version 5 / GBWTGraph version 3 in simple-sds serialization.  GB_ERR_FORMAT for anything else, and for graphs
  * outside the index model (haplotypes that step onto a reverse strand, cycles, a site of more than 4096 nodes). */
 int gb_index_from_gbz(const char* path, uint32_t k, uint32_t w, gb_host_index** out);
@@ -174,6 +175,16 @@ int gb_index_from_gbz_min(const char* gbz_path, const char* min_path, const char
 /* gb_index_build with the minimizer hits given by the caller: hit i = (keys[i], positions[i]), position =
  * id << 11 | is_reverse << 10 | offset of the first base of the canonical k-mer on that oriented node (gbwtgraph's
  * Position encoding).  Hits that do not lie on the graph or do not spell their key are GB_ERR_FORMAT. */
+/* The same from a GBWT instead of haplotype paths: gbwt_words / rec_off in the blob layout of gb_flat_index (record of oriented
+ * node v at gbwt_words[rec_off[v]], rec_off[v] == 0: no record; rec_off has 2 * (n_node_ids + 1) entries).  This is what a
+ * caller holding vg's gbwt::GBWT hands over after flattening its records, and what gb_index_from_gbz does with the GBZ's own
+ * records: no haplotype is walked, the distance model comes from the edges of the forward records, the minimizers from the
+ * window enumeration (or from keys / positions when given, as gb_index_build_with_hits).  Records are validated (edges
+ * ascending, ranks inside the edge list, offsets inside the successor's record): GB_ERR_FORMAT otherwise. */
+int gb_index_build_from_gbwt(uint32_t n_node_ids, const uint8_t* node_seq, const uint64_t* node_off, uint32_t n_paths,
+                             const uint32_t* gbwt_words, uint64_t n_words, const uint32_t* rec_off,
+                             const gb_dist_payload* dist, uint32_t k, uint32_t w,
+                             uint64_t n_hits, const uint64_t* keys, const uint64_t* positions, gb_host_index** out);
 int gb_index_build_with_hits(uint32_t n_node_ids, const uint8_t* node_seq, const uint64_t* node_off,
                              uint32_t n_paths, const uint32_t* path_nodes, const uint64_t* path_off,
                              const gb_dist_payload* dist, uint32_t k, uint32_t w,

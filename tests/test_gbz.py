@@ -500,3 +500,45 @@ def test_window_enumeration_builds_the_same_index_as_the_haplotype_scan(which, m
     for name in ("nodes", "gbwt", "dist", "table", "hits"):
         assert a.array(name).tobytes() == b.array(name).tobytes(), name
     a.close(); b.close()
+
+
+@pytest.mark.parametrize("which", ["variants", "repeats", "nested", "branchy", "reference gbz"])
+def test_index_from_the_flat_gbwt_equals_the_index_from_the_paths(which):
+    """gb_index_build_from_gbwt: node sequences + GBWT records, no haplotype paths — distance model from the edges of the
+    forward records, minimizers by window enumeration, record blobs copied after validation.  Feeding it the flat GBWT of a
+    path-built index must give that index back byte for byte (hand-made payloads are passed through, derived ones re-derived)."""
+    if which == "reference gbz":
+        seqs, paths, _ = read_gbz(GBZ)
+        ref = capi.HostIndex(seqs, paths, k=31, w=50); dist = None; k, w = 31, 50
+    else:
+        g = {"variants": lambda: synth.make_variant_graph(length=40000, n_snp=120, n_ins=15, n_del=15, n_haps=8, seed=4),
+             "repeats": lambda: synth.make_variant_graph(length=24000, n_snp=40, n_ins=4, n_del=4, n_haps=4, seed=23, repeat_unit=600, repeat_copies=6),
+             "nested": lambda: synth.make_nested_graph(n_items=120, n_haps=10, seed=5),
+             "branchy": lambda: synth.make_branchy_graph(n_layers=600, n_haps=16, seed=4)}[which]()
+        k, w = (11, 5) if which == "nested" else (29, 11)
+        ref = g.build_index(k=k, w=w); seqs, paths, dist = g.node_seqs, g.paths, g.dist
+    nodes = ref.array("nodes")
+    got = capi.HostIndex.from_gbwt(seqs, len(paths), ref.array("gbwt"), nodes["rec_off"], dist, k=k, w=w)
+    assert int(got.view.n_paths) == len(paths)
+    for name in ("nodes", "seq", "gbwt", "dist", "slots", "site_dist", "table", "hits"):
+        assert got.array(name).tobytes() == ref.array(name).tobytes(), name
+    got.close(); ref.close()
+
+
+def test_damaged_gbwt_records_are_refused():
+    g = synth.make_variant_graph(length=6000, n_snp=20, n_ins=3, n_del=3, n_haps=4, seed=9)
+    ref = g.build_index()
+    words, rec_off = ref.array("gbwt").copy(), ref.array("nodes")["rec_off"].copy()
+    v = int(np.flatnonzero(rec_off)[5]); off = int(rec_off[v])
+    n_edges = int(words[off])
+
+    def attempt(mut):
+        w2, r2 = words.copy(), rec_off.copy(); mut(w2, r2)
+        with pytest.raises(capi.GbError):
+            capi.HostIndex.from_gbwt(g.node_seqs, len(g.paths), w2, r2, g.dist)
+    attempt(lambda w2, r2: r2.__setitem__(v, len(w2) + 5))                                        # record outside the blob
+    attempt(lambda w2, r2: w2.__setitem__(off, 5000))                                             # absurd edge count
+    attempt(lambda w2, r2: w2.__setitem__(off + 2, 2 * (len(g.node_seqs) + 9)))                   # successor outside the graph
+    attempt(lambda w2, r2: w2.__setitem__(off + 3, 1 << 30))                                      # offset outside the successor's record
+    attempt(lambda w2, r2: w2.__setitem__(off + 2 + 2 * n_edges, (1 << 10) | 900))                # run rank outside the edge list
+    ref.close()

@@ -149,6 +149,8 @@ def load_library() -> C.CDLL:
     lib.gb_index_from_gbz_min.restype = C.c_int
     lib.gb_index_build_with_hits.argtypes = [u32, vp, vp, u32, vp, vp, vp, u32, u32, u64, vp, vp, vp]
     lib.gb_index_build_with_hits.restype = C.c_int
+    lib.gb_index_build_from_gbwt.argtypes = [u32, vp, vp, u32, vp, u64, vp, vp, u32, u32, u64, vp, vp, vp]
+    lib.gb_index_build_from_gbwt.restype = C.c_int
     lib.gb_index_save.argtypes = [C.POINTER(FlatIndex), C.c_char_p]
     lib.gb_index_save.restype = C.c_int
     lib.gb_index_load.argtypes = [C.c_char_p, vp]
@@ -302,6 +304,36 @@ class HostIndex:
         if rc != GB_OK:
             raise GbError(rc, "gb_index_view")
         self.node_seqs, self.paths = None, None
+        self.k, self.w = k, w
+        return self
+
+    @classmethod
+    def from_gbwt(cls, node_seqs, n_paths, gbwt_words, rec_off, dist=None, k=29, w=11, hits=None):
+        """gb_index_build_from_gbwt: node sequences + a flat GBWT (gb_flat_index blob layout) instead of haplotype paths."""
+        lib = load_library()
+        n = len(node_seqs)
+        node_off = np.zeros(n + 1, dtype=np.uint64)
+        node_off[1:] = np.cumsum([len(s) for s in node_seqs])
+        seq = np.frombuffer("".join(node_seqs).encode(), dtype=np.uint8).copy() if n else np.zeros(1, np.uint8)
+        words = np.ascontiguousarray(gbwt_words, dtype=np.uint32); ro = np.ascontiguousarray(rec_off, dtype=np.uint32)
+        dptr = None
+        if dist is not None:
+            dist = np.ascontiguousarray(dist, dtype=dist_dt); dptr = ptr(dist)
+        hk = hp = None
+        if hits is not None:
+            hk, hp = (np.ascontiguousarray(a, dtype=np.uint64) for a in hits)
+        h = C.c_void_p()
+        rc = lib.gb_index_build_from_gbwt(n, ptr(seq), ptr(node_off), n_paths, ptr(words), len(words), ptr(ro), dptr, k, w,
+                                          0 if hk is None else len(hk), None if hk is None else ptr(hk), None if hp is None else ptr(hp), C.byref(h))
+        if rc != GB_OK:
+            raise GbError(rc, "gb_index_build_from_gbwt")
+        self = cls.__new__(cls)
+        self._h = h
+        self.view = FlatIndex()
+        rc = lib.gb_index_view(h, C.byref(self.view))
+        if rc != GB_OK:
+            raise GbError(rc, "gb_index_view")
+        self.node_seqs, self.paths = list(node_seqs), None
         self.k, self.w = k, w
         return self
 

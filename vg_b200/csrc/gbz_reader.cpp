@@ -1,6 +1,7 @@
 // gbz_reader.cpp — read a GBZ file (what `vg giraffe -Z` loads, giraffe_main.cpp:1825-1881) and build the flat index
-// from it: node sequences from the GBWTGraph, haplotype paths by walking the GBWT; the distance payload (chains of cut
-// nodes and sites) and the minimizers come from the library's own index builder.
+// from it: node sequences from the GBWTGraph, the GBWT records decoded and handed to the builder in its blob layout
+// (gb_index_build_from_gbwt: no haplotype is walked, so the work follows the graph, not haplotypes x genome); the distance
+// payload (chains of cut nodes and sites) and the minimizers come from the library's own index builder.
 //
 // gbwt (jltsiren/gbwt @ c2e0199), gbwtgraph (@ e27bc43) and simple-sds are ABSENT from the reference tree; the layout
 // below is their published serialization format, checked against the GBZ the reference ships as test data
@@ -200,7 +201,7 @@ static int index_from_gbz_impl(const char* path, uint32_t k, uint32_t w, gb_host
     if ((uint32_t)g0 != 0x6B376B37u || (g0 >> 32) != 5) return fail("gbwt header");
     const uint64_t sequences = r.u(), size = r.u(), offset = r.u(), alphabet_size = r.u(), gflags = r.u();
     if (!r.ok || !(gflags & 1) || !(gflags & 4) || alphabet_size <= offset + 1 || sequences % 2 != 0) return fail("gbwt must be bidirectional simple-sds");
-    if (size > (1ull << 31) || sequences > size) return fail("gbwt too large for this reader");
+    if (sequences > size) return fail("gbwt sizes");
     if (!string_array(r, tags)) return fail("gbwt tags");
     std::vector<uint64_t> rec_start; uint64_t universe; std::vector<uint8_t> data;
     if (!sparse_values(r, rec_start, universe) || !vector_u8(r, data) || universe != data.size() || rec_start.size() != alphabet_size - offset) return fail("bwt");
@@ -231,37 +232,34 @@ static int index_from_gbz_impl(const char* path, uint32_t k, uint32_t w, gb_host
             records[c].runs.push_back({(uint32_t)rank, len});
         }
     }
-    // LF(record, position) -> (successor node, position in its record)
-    auto lf = [&](uint64_t comp, uint64_t pos, uint64_t& node, uint64_t& next) -> bool {
-        if (comp >= records.size()) return false;
-        const Record& rc = records[comp];
-        std::vector<uint64_t> seen(rc.edges.size(), 0);
-        uint64_t p = 0;
-        for (const auto& run : rc.runs) {
-            if (pos < p + run.second) { node = rc.edges[run.first].first; next = rc.edges[run.first].second + seen[run.first] + (pos - p); return true; }
-            seen[run.first] += run.second; p += run.second;
-        }
-        return false;
-    };
-    // ---- haplotype paths: the forward orientation of each bidirectional sequence pair ----
-    // GBWT node = 2 * id + orientation; graph sequence s belongs to id first_id + s
+    // ---- the records in the library's blob layout: nothing below walks a haplotype (work ~ graph, not haplotypes x genome) ----
+    // GBWT node = 2 * id + orientation; record c belongs to node c + offset; graph sequence s belongs to id first_id + s
     const uint64_t first_id = (offset + 1) / 2;
     const uint64_t n_ids = first_id + n_graph_nodes - 1;               // ids 1 .. n_ids are addressable; those below first_id stay empty
     if (n_ids == 0 || n_ids > (1u << 26)) return fail("node ids");
-    std::vector<std::vector<uint32_t>> paths;
-    uint64_t walked = 0;
-    for (uint64_t s = 0; s < sequences; s += 2) {
-        uint64_t node, pos;
-        if (!lf(0, s, node, pos)) return fail("endmarker");
-        std::vector<uint32_t> p;
-        while (node != 0) {
-            if (node <= offset || node >= alphabet_size || (node >> 1) > n_ids || walked++ > size) return fail("walk");
-            p.push_back((uint32_t)node);
-            uint64_t nn, np;
-            if (!lf(node - offset, pos, nn, np)) return fail("lf");
-            node = nn; pos = np;
+    std::vector<uint32_t> blob{0, 0}, rec_off(2 * (n_ids + 1), 0);
+    for (size_t c = 1; c < records.size(); c++) {
+        const Record& rc = records[c];
+        if (rc.runs.empty()) continue;
+        const uint64_t v = c + offset;
+        if (v < 2 || (v >> 1) > n_ids || rc.edges.empty() || rc.edges.size() >= 1024) return fail("record node");
+        if (blob.size() & 1) blob.push_back(0);
+        if (blob.size() > 0xfffffff0ull) return fail("gbwt too large for 32-bit record offsets");
+        rec_off[v] = (uint32_t)blob.size();
+        blob.push_back((uint32_t)rc.edges.size());
+        const size_t n_runs_at = blob.size(); blob.push_back(0);
+        for (const auto& e : rc.edges) {
+            if (e.first >= alphabet_size || (e.first != 0 && e.first <= offset) || e.second > 0xfffffff0ull) return fail("record edge");
+            blob.push_back((uint32_t)e.first); blob.push_back((uint32_t)e.second);
         }
-        paths.push_back(p);                     // identical haplotypes stay: GBWT record sizes count visits
+        uint32_t n_runs = 0;
+        for (const auto& run : rc.runs) {
+            for (uint64_t left = run.second; left > 0;) {                 // a run word holds up to 2^22 - 1 visits
+                const uint64_t piece = std::min<uint64_t>(left, (1u << 22) - 1);
+                blob.push_back(((uint32_t)piece << 10) | run.first); n_runs++; left -= piece;
+            }
+        }
+        blob[n_runs_at] = n_runs;
     }
     // ---- node sequences ----
     std::vector<uint8_t> node_seq; std::vector<uint64_t> node_off(n_ids + 1, 0);
@@ -270,16 +268,12 @@ static int index_from_gbz_impl(const char* path, uint32_t k, uint32_t w, gb_host
         if (id >= first_id) { const std::string& s = seqs[id - first_id]; node_seq.insert(node_seq.end(), s.begin(), s.end()); len[id] = (uint32_t)s.size(); }
         node_off[id] = node_seq.size();
     }
-    // ---- distance payload: derived by the builder from the graph these paths span (chains of cut nodes and sites with
-    // all-pairs tables, see gb_dist_payload): nested bubbles, multi-node alleles and adjacent variants are all fine ----
-    for (const auto& p : paths) if (p.empty()) return fail("empty haplotype");
-    // ---- build ----
-    std::vector<uint32_t> flat; std::vector<uint64_t> path_off{0};
-    for (const auto& p : paths) { flat.insert(flat.end(), p.begin(), p.end()); path_off.push_back(flat.size()); }
+    // ---- build: distance payload derived from the edges of the forward records (chains of cut nodes and sites with all-pairs
+    // tables, see gb_dist_payload: nested bubbles, multi-node alleles and adjacent variants are all fine), minimizers by window
+    // enumeration over GBWT search states, or taken from the .min file ----
     if (node_seq.empty()) node_seq.push_back(0);
-    const int rc = min ? gb_index_build_with_hits((uint32_t)n_ids, node_seq.data(), node_off.data(), (uint32_t)paths.size(), flat.data(), path_off.data(), nullptr, k, w,
-                                                  min->keys.size(), min->keys.data(), min->pos.data(), out)
-                       : gb_index_build((uint32_t)n_ids, node_seq.data(), node_off.data(), (uint32_t)paths.size(), flat.data(), path_off.data(), nullptr, k, w, out);
+    const int rc = gb_index_build_from_gbwt((uint32_t)n_ids, node_seq.data(), node_off.data(), (uint32_t)(sequences / 2), blob.data(), blob.size(), rec_off.data(),
+                                            nullptr, k, w, min ? min->keys.size() : 0, min ? min->keys.data() : nullptr, min ? min->pos.data() : nullptr, out);
     if (rc == GB_OK && !gb_index_has_distance_model(*out)) { gb_index_free(*out); *out = nullptr; return fail("graph outside the chain model (cycle, reversing haplotype or oversized site)"); }
     return rc;
 }

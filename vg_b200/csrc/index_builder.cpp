@@ -115,20 +115,28 @@ void gbwt_visit_order(const std::vector<std::vector<uint32_t>>& seqs,
 // Returns false for anything outside that model (a reverse step, a cycle, an oversized site).
 constexpr uint32_t MAX_SITE_NODES = 4096;
 
-bool derive_distance_payload(uint32_t n_node_ids, const std::vector<uint32_t>& len /* by id */, const std::vector<std::vector<uint32_t>>& fwd_paths,
+// The forward-strand graph of a set of haplotype paths: node ids in use and (id, id) edges; false when a haplotype steps onto a
+// reverse strand.
+bool forward_graph_of_paths(uint32_t n_node_ids, const std::vector<std::vector<uint32_t>>& fwd_paths, std::vector<bool>& used,
+                            std::vector<std::pair<uint32_t, uint32_t>>& edges) {
+    used.assign(n_node_ids + 1, false); edges.clear();
+    for (const auto& p : fwd_paths) {
+        for (size_t i = 0; i < p.size(); i++) {
+            if (p[i] & 1u) return false;
+            used[p[i] >> 1] = true;
+            if (i) edges.emplace_back(p[i - 1] >> 1, p[i] >> 1);
+        }
+    }
+    return true;
+}
+
+bool derive_distance_payload(uint32_t n_node_ids, const std::vector<uint32_t>& len /* by id */, const std::vector<bool>& used_in,
+                             std::vector<std::pair<uint32_t, uint32_t>> edges,
                              std::vector<gb_dist_payload>& dist, std::vector<gb_slot_rec>& slots, std::vector<uint16_t>& site_dist) {
     const uint32_t N = n_node_ids + 1;
     std::vector<std::vector<uint32_t>> succ(N), pred(N);
-    std::vector<bool> used(N, false);
+    std::vector<bool> used = used_in;
     {
-        std::vector<std::pair<uint32_t, uint32_t>> edges;
-        for (const auto& p : fwd_paths) {
-            for (size_t i = 0; i < p.size(); i++) {
-                if (p[i] & 1u) return false;                      // a haplotype steps onto a reverse strand
-                used[p[i] >> 1] = true;
-                if (i) edges.emplace_back(p[i - 1] >> 1, p[i] >> 1);
-            }
-        }
         std::sort(edges.begin(), edges.end());
         edges.erase(std::unique(edges.begin(), edges.end()), edges.end());
         for (const auto& e : edges) { succ[e.first].push_back(e.second); pred[e.second].push_back(e.first); }
@@ -259,12 +267,18 @@ bool derive_distance_payload(uint32_t n_node_ids, const std::vector<uint32_t>& l
 
 } // namespace
 
+// A GBWT node record handed to the builder instead of haplotype paths (GBZ files, gb_index_build_from_gbwt): edges sorted by
+// successor (oriented node, 0 = endmarker) with the offset of this node's visits in the successor's record, and the body as runs.
+struct GbwtRecordIn { std::vector<std::pair<uint32_t, uint32_t>> edges; std::vector<std::pair<uint32_t, uint64_t>> runs; };
+
 static int index_build_impl(uint32_t n_node_ids, const uint8_t* node_seq, const uint64_t* node_off,
                             uint32_t n_paths, const uint32_t* path_nodes, const uint64_t* path_off,
                             const gb_dist_payload* dist, uint32_t k, uint32_t w,
                             gb_host_index** out,
-                            uint64_t n_ext_hits = 0, const uint64_t* ext_keys = nullptr, const uint64_t* ext_pos = nullptr) {
-    if (!node_seq || !node_off || !out || (n_paths && (!path_nodes || !path_off))) return GB_ERR_ARG;
+                            uint64_t n_ext_hits = 0, const uint64_t* ext_keys = nullptr, const uint64_t* ext_pos = nullptr,
+                            const std::vector<GbwtRecordIn>* records = nullptr) {
+    if (!node_seq || !node_off || !out || (!records && n_paths && (!path_nodes || !path_off))) return GB_ERR_ARG;
+    if (records && records->size() != 2 * ((size_t)n_node_ids + 1)) return GB_ERR_ARG;
     const bool external = ext_keys != nullptr || ext_pos != nullptr;
     if (external && (!ext_keys || !ext_pos)) return GB_ERR_ARG;
     if (k == 0 || k > 31 || w == 0) return GB_ERR_ARG;
@@ -296,10 +310,28 @@ static int index_build_impl(uint32_t n_node_ids, const uint8_t* node_seq, const 
     else {
         std::vector<uint32_t> len_by_id(n_node_ids + 1, 0);
         for (uint32_t id = 1; id <= n_node_ids; id++) len_by_id[id] = (uint32_t)(node_off[id] - node_off[id - 1]);
-        std::vector<std::vector<uint32_t>> fwd(n_paths);
-        for (uint32_t p = 0; p < n_paths; p++) fwd[p].assign(path_nodes + path_off[p], path_nodes + path_off[p + 1]);
-        for (const auto& f : fwd) for (uint32_t v : f) if (v < 2 || v >= ix->n_nodes) { delete ix; return GB_ERR_FORMAT; }
-        if (!derive_distance_payload(n_node_ids, len_by_id, fwd, ix->dist, ix->slots, ix->site_dist)) {
+        std::vector<bool> used; std::vector<std::pair<uint32_t, uint32_t>> edges; bool forward = true;
+        if (records) {
+            // the forward-strand graph straight from the records of the forward nodes
+            used.assign(n_node_ids + 1, false);
+            for (uint32_t v = 2; v < ix->n_nodes && forward; v += 2) {
+                const GbwtRecordIn& rc = (*records)[v];
+                if (rc.runs.empty()) continue;
+                used[v >> 1] = true;
+                for (const auto& e : rc.edges) {
+                    if (e.first == 0) continue;
+                    if (e.first >= ix->n_nodes) { delete ix; return GB_ERR_FORMAT; }
+                    if (e.first & 1u) { forward = false; break; }
+                    edges.emplace_back(v >> 1, e.first >> 1);
+                }
+            }
+        } else {
+            std::vector<std::vector<uint32_t>> fwd(n_paths);
+            for (uint32_t p = 0; p < n_paths; p++) fwd[p].assign(path_nodes + path_off[p], path_nodes + path_off[p + 1]);
+            for (const auto& f : fwd) for (uint32_t v : f) if (v < 2 || v >= ix->n_nodes) { delete ix; return GB_ERR_FORMAT; }
+            forward = forward_graph_of_paths(n_node_ids, fwd, used, edges);
+        }
+        if (!forward || !derive_distance_payload(n_node_ids, len_by_id, used, std::move(edges), ix->dist, ix->slots, ix->site_dist)) {
             // outside the chain model (a cycle, a reversing haplotype, an oversized site): the graph, GBWT and minimizers are
             // still built, so the stage seams work on it (the reference's cyclic WFA test graphs), but there is no
             // distance payload: gb_index_has_distance_model() says so and gb_index_from_gbz refuses such a file
@@ -309,79 +341,122 @@ static int index_build_impl(uint32_t n_node_ids, const uint8_t* node_seq, const 
     }
 
     // --- bidirectional GBWT ---
-    std::vector<std::vector<uint32_t>> seqs(2 * (size_t)n_paths);
-    for (uint32_t p = 0; p < n_paths; p++) {
-        uint64_t b = path_off[p], e = path_off[p + 1];
-        auto& f = seqs[2 * p]; auto& r = seqs[2 * p + 1];
-        f.assign(path_nodes + b, path_nodes + e);
-        r.resize(e - b);
-        for (uint64_t i = 0; i < e - b; i++) r[i] = path_nodes[e - 1 - i] ^ 1u;
-        for (uint32_t v : f) if (v < 2 || v >= ix->n_nodes) { delete ix; return GB_ERR_FORMAT; }
-    }
-    std::vector<uint32_t> vrank; std::vector<uint64_t> seq_start;
-    gbwt_visit_order(seqs, vrank, seq_start);
-    size_t nvis = vrank.size();
-    // group visits per node in record order
-    struct Visit { uint32_t node, rank, pred, succ; };
-    std::vector<Visit> visits(nvis);
-    for (size_t s = 0; s < seqs.size(); s++) {
-        for (size_t i = 0; i < seqs[s].size(); i++) {
-            size_t p = seq_start[s] + i;
-            visits[p] = Visit{seqs[s][i], vrank[p], i ? seqs[s][i - 1] : 0u,
-                              i + 1 < seqs[s].size() ? seqs[s][i + 1] : 0u};
+    std::vector<std::vector<uint32_t>> seqs(records ? 0 : 2 * (size_t)n_paths);
+    if (!records) {
+        for (uint32_t p = 0; p < n_paths; p++) {
+            uint64_t b = path_off[p], e = path_off[p + 1];
+            auto& f = seqs[2 * p]; auto& r = seqs[2 * p + 1];
+            f.assign(path_nodes + b, path_nodes + e);
+            r.resize(e - b);
+            for (uint64_t i = 0; i < e - b; i++) r[i] = path_nodes[e - 1 - i] ^ 1u;
+            for (uint32_t v : f) if (v < 2 || v >= ix->n_nodes) { delete ix; return GB_ERR_FORMAT; }
         }
-    }
-    std::sort(visits.begin(), visits.end(), [](const Visit& a, const Visit& b) {
-        if (a.node != b.node) return a.node < b.node;
-        return a.rank < b.rank;
-    });
-    // record start per node
-    std::vector<size_t> rec_begin(ix->n_nodes + 1, 0);
-    for (auto& vis : visits) rec_begin[vis.node + 1]++;
-    for (uint32_t v = 0; v < ix->n_nodes; v++) rec_begin[v + 1] += rec_begin[v];
-
-    ix->gbwt.clear();
-    ix->gbwt.push_back(0); ix->gbwt.push_back(0);   // offset 0 = "no record" sentinel (0 edges, 0 runs)
-    for (uint32_t v = 2; v < ix->n_nodes; v++) {
-        size_t b = rec_begin[v], e = rec_begin[v + 1];
-        ix->nodes[v].size = (uint32_t)(e - b);
-        if (e == b) { ix->nodes[v].rec_off = 0; continue; }
-        // distinct successors, ascending
-        std::vector<uint32_t> succ;
-        for (size_t i = b; i < e; i++) succ.push_back(visits[i].succ);
-        std::sort(succ.begin(), succ.end());
-        succ.erase(std::unique(succ.begin(), succ.end()), succ.end());
-        if (succ.size() >= 1024) { delete ix; return GB_ERR_FORMAT; }
-        if (ix->gbwt.size() & 1) ix->gbwt.push_back(0);   // 8-byte align the edge pairs
-        if (ix->gbwt.size() > 0xfffffff0ull) { delete ix; return GB_ERR_FORMAT; }
-        ix->nodes[v].rec_off = (uint32_t)ix->gbwt.size();
-        ix->gbwt.push_back((uint32_t)succ.size());
-        size_t nruns_at = ix->gbwt.size();
-        ix->gbwt.push_back(0);
-        for (uint32_t wnode : succ) {
-            uint32_t off = 0;
-            if (wnode != 0) {
-                // number of visits in record(w) whose predecessor is smaller than v
-                size_t wb = rec_begin[wnode], we = rec_begin[wnode + 1];
-                // visits in a record are sorted by predecessor first
-                size_t lo = wb, hi = we;
-                while (lo < hi) { size_t mid = (lo + hi) / 2; if (visits[mid].pred < v) lo = mid + 1; else hi = mid; }
-                off = (uint32_t)(lo - wb);
+        std::vector<uint32_t> vrank; std::vector<uint64_t> seq_start;
+        gbwt_visit_order(seqs, vrank, seq_start);
+        size_t nvis = vrank.size();
+        // group visits per node in record order
+        struct Visit { uint32_t node, rank, pred, succ; };
+        std::vector<Visit> visits(nvis);
+        for (size_t s = 0; s < seqs.size(); s++) {
+            for (size_t i = 0; i < seqs[s].size(); i++) {
+                size_t p = seq_start[s] + i;
+                visits[p] = Visit{seqs[s][i], vrank[p], i ? seqs[s][i - 1] : 0u,
+                                  i + 1 < seqs[s].size() ? seqs[s][i + 1] : 0u};
             }
-            ix->gbwt.push_back(wnode);
-            ix->gbwt.push_back(off);
         }
-        uint32_t nruns = 0;
-        size_t i = b;
-        while (i < e) {
-            size_t j = i;
-            while (j < e && visits[j].succ == visits[i].succ && (j - i) < ((1u << 22) - 1)) j++;
-            uint32_t outrank = (uint32_t)(std::lower_bound(succ.begin(), succ.end(), visits[i].succ) - succ.begin());
-            ix->gbwt.push_back(((uint32_t)(j - i) << 10) | outrank);
-            nruns++;
-            i = j;
+        std::sort(visits.begin(), visits.end(), [](const Visit& a, const Visit& b) {
+            if (a.node != b.node) return a.node < b.node;
+            return a.rank < b.rank;
+        });
+        // record start per node
+        std::vector<size_t> rec_begin(ix->n_nodes + 1, 0);
+        for (auto& vis : visits) rec_begin[vis.node + 1]++;
+        for (uint32_t v = 0; v < ix->n_nodes; v++) rec_begin[v + 1] += rec_begin[v];
+
+        ix->gbwt.clear();
+        ix->gbwt.push_back(0); ix->gbwt.push_back(0);   // offset 0 = "no record" sentinel (0 edges, 0 runs)
+        for (uint32_t v = 2; v < ix->n_nodes; v++) {
+            size_t b = rec_begin[v], e = rec_begin[v + 1];
+            ix->nodes[v].size = (uint32_t)(e - b);
+            if (e == b) { ix->nodes[v].rec_off = 0; continue; }
+            // distinct successors, ascending
+            std::vector<uint32_t> succ;
+            for (size_t i = b; i < e; i++) succ.push_back(visits[i].succ);
+            std::sort(succ.begin(), succ.end());
+            succ.erase(std::unique(succ.begin(), succ.end()), succ.end());
+            if (succ.size() >= 1024) { delete ix; return GB_ERR_FORMAT; }
+            if (ix->gbwt.size() & 1) ix->gbwt.push_back(0);   // 8-byte align the edge pairs
+            if (ix->gbwt.size() > 0xfffffff0ull) { delete ix; return GB_ERR_FORMAT; }
+            ix->nodes[v].rec_off = (uint32_t)ix->gbwt.size();
+            ix->gbwt.push_back((uint32_t)succ.size());
+            size_t nruns_at = ix->gbwt.size();
+            ix->gbwt.push_back(0);
+            for (uint32_t wnode : succ) {
+                uint32_t off = 0;
+                if (wnode != 0) {
+                    // number of visits in record(w) whose predecessor is smaller than v
+                    size_t wb = rec_begin[wnode], we = rec_begin[wnode + 1];
+                    // visits in a record are sorted by predecessor first
+                    size_t lo = wb, hi = we;
+                    while (lo < hi) { size_t mid = (lo + hi) / 2; if (visits[mid].pred < v) lo = mid + 1; else hi = mid; }
+                    off = (uint32_t)(lo - wb);
+                }
+                ix->gbwt.push_back(wnode);
+                ix->gbwt.push_back(off);
+            }
+            uint32_t nruns = 0;
+            size_t i = b;
+            while (i < e) {
+                size_t j = i;
+                while (j < e && visits[j].succ == visits[i].succ && (j - i) < ((1u << 22) - 1)) j++;
+                uint32_t outrank = (uint32_t)(std::lower_bound(succ.begin(), succ.end(), visits[i].succ) - succ.begin());
+                ix->gbwt.push_back(((uint32_t)(j - i) << 10) | outrank);
+                nruns++;
+                i = j;
+            }
+            ix->gbwt[nruns_at] = nruns;
         }
-        ix->gbwt[nruns_at] = nruns;
+    } else {
+        // the records as given: same blob layout, same normalisation as above (edges ascending by successor, the endmarker edge with
+        // offset 0, maximal runs cut at 2^22 - 1), so an index built from the records of a GBWT equals the one built from its paths
+        ix->gbwt.clear();
+        ix->gbwt.push_back(0); ix->gbwt.push_back(0);
+        std::vector<uint64_t> rec_size(ix->n_nodes, 0);
+        for (uint32_t v = 2; v < ix->n_nodes; v++) for (const auto& r : (*records)[v].runs) rec_size[v] += r.second;
+        for (uint32_t v = 2; v < ix->n_nodes; v++) {
+            const GbwtRecordIn& rc = (*records)[v];
+            if (rec_size[v] == 0) { ix->nodes[v].rec_off = 0; ix->nodes[v].size = 0; continue; }
+            if (rec_size[v] > 0xfffffff0ull || rc.edges.empty() || rc.edges.size() >= 1024) { delete ix; return GB_ERR_FORMAT; }
+            ix->nodes[v].size = (uint32_t)rec_size[v];
+            // every visit leaves through an edge; the offsets must lie inside the successor's record
+            std::vector<uint64_t> through(rc.edges.size(), 0);
+            for (const auto& r : rc.runs) { if (r.first >= rc.edges.size() || r.second == 0) { delete ix; return GB_ERR_FORMAT; } through[r.first] += r.second; }
+            for (size_t e = 0; e < rc.edges.size(); e++) {
+                const uint32_t to = rc.edges[e].first;
+                if (e && to <= rc.edges[e - 1].first) { delete ix; return GB_ERR_FORMAT; }
+                if (to == 0) continue;
+                if (to < 2 || to >= ix->n_nodes || (uint64_t)rc.edges[e].second + through[e] > rec_size[to]) { delete ix; return GB_ERR_FORMAT; }
+            }
+            if (ix->gbwt.size() & 1) ix->gbwt.push_back(0);
+            if (ix->gbwt.size() > 0xfffffff0ull) { delete ix; return GB_ERR_FORMAT; }
+            ix->nodes[v].rec_off = (uint32_t)ix->gbwt.size();
+            ix->gbwt.push_back((uint32_t)rc.edges.size());
+            const size_t nruns_at = ix->gbwt.size();
+            ix->gbwt.push_back(0);
+            for (const auto& e : rc.edges) { ix->gbwt.push_back(e.first); ix->gbwt.push_back(e.first == 0 ? 0u : e.second); }
+            uint32_t nruns = 0;
+            for (size_t i = 0; i < rc.runs.size();) {
+                uint64_t len = 0; size_t j = i;
+                while (j < rc.runs.size() && rc.runs[j].first == rc.runs[i].first) { len += rc.runs[j].second; j++; }
+                while (len > 0) {
+                    const uint64_t piece = std::min<uint64_t>(len, (1u << 22) - 1);
+                    ix->gbwt.push_back(((uint32_t)piece << 10) | rc.runs[i].first);
+                    nruns++; len -= piece;
+                }
+                i = j;
+            }
+            ix->gbwt[nruns_at] = nruns;
+        }
     }
     ix->gbwt.resize(ix->gbwt.size() + 64, 0);
 
@@ -418,10 +493,12 @@ static int index_build_impl(uint32_t n_node_ids, const uint8_t* node_seq, const 
     // Chosen by the haplotype count (more than 32: windows); GIRAFFE_B200_WINDOW_BUILDER=0|1 forces one.
     bool use_windows = n_paths > 32;
     if (const char* env = std::getenv("GIRAFFE_B200_WINDOW_BUILDER")) use_windows = std::atoi(env) != 0;
+    if (records) use_windows = true;                   // there are no paths to scan
     if (use_windows && !external) {
         const uint32_t W = k + w - 1;
         bool forward_only = true;                      // every haplotype stays on forward strands: forward starts cover every window
-        for (uint32_t p = 0; p < n_paths && forward_only; p++) for (uint32_t v : seqs[2 * p]) if (v & 1u) { forward_only = false; break; }
+        if (records) { for (uint32_t v = 2; v < ix->n_nodes && forward_only; v += 2) for (const auto& e : (*records)[v].edges) if (e.first & 1u) { forward_only = false; break; } }
+        else for (uint32_t p = 0; p < n_paths && forward_only; p++) for (uint32_t v : seqs[2 * p]) if (v & 1u) { forward_only = false; break; }
         // successors of a GBWT search state (node, [lo, hi]) in record order
         auto follow = [&](uint32_t v, int64_t lo, int64_t hi, std::vector<std::array<int64_t, 3>>& out) {
             out.clear();
@@ -541,6 +618,35 @@ extern "C" int gb_index_build_with_hits(uint32_t n_node_ids, const uint8_t* node
     static const uint64_t none = 0;
     if (n_hits == 0) { keys = keys ? keys : &none; positions = positions ? positions : &none; }
     try { return index_build_impl(n_node_ids, node_seq, node_off, n_paths, path_nodes, path_off, dist, k, w, out, n_hits, keys, positions); }
+    catch (const std::bad_alloc&) { return GB_ERR_CAPACITY; }
+    catch (...) { return GB_ERR_ARG; }
+}
+
+// The index from node sequences and a flat GBWT (the blob layout of gb_flat_index.gbwt) instead of haplotype paths: nothing here
+// walks a haplotype, so the work follows the size of the graph, not haplotypes x genome.
+extern "C" int gb_index_build_from_gbwt(uint32_t n_node_ids, const uint8_t* node_seq, const uint64_t* node_off, uint32_t n_paths,
+                                        const uint32_t* gbwt_words, uint64_t n_words, const uint32_t* rec_off,
+                                        const gb_dist_payload* dist, uint32_t k, uint32_t w,
+                                        uint64_t n_hits, const uint64_t* keys, const uint64_t* positions, gb_host_index** out) {
+    try {
+        if (!gbwt_words || !rec_off || !out || n_node_ids >= 0x7ffffff0u) return GB_ERR_ARG;
+        const size_t n_nodes = 2 * ((size_t)n_node_ids + 1);
+        std::vector<GbwtRecordIn> records(n_nodes);
+        for (size_t v = 2; v < n_nodes; v++) {
+            const uint64_t off = rec_off[v];
+            if (off == 0) continue;
+            if (off + 2 > n_words) return GB_ERR_FORMAT;
+            const uint64_t n_edges = gbwt_words[off], n_runs = gbwt_words[off + 1];
+            if (n_edges >= 1024 || off + 2 + 2 * n_edges + n_runs > n_words) return GB_ERR_FORMAT;
+            GbwtRecordIn& rc = records[v];
+            for (uint64_t e = 0; e < n_edges; e++) rc.edges.push_back({gbwt_words[off + 2 + 2 * e], gbwt_words[off + 3 + 2 * e]});
+            for (uint64_t r = 0; r < n_runs; r++) { const uint32_t wd = gbwt_words[off + 2 + 2 * n_edges + r]; rc.runs.push_back({wd & 1023u, (uint64_t)(wd >> 10)}); }
+        }
+        static const uint64_t none = 0;
+        const bool ext = keys || positions;
+        if (ext && n_hits == 0) { keys = keys ? keys : &none; positions = positions ? positions : &none; }
+        return index_build_impl(n_node_ids, node_seq, node_off, n_paths, nullptr, nullptr, dist, k, w, out, n_hits, keys, positions, &records);
+    }
     catch (const std::bad_alloc&) { return GB_ERR_CAPACITY; }
     catch (...) { return GB_ERR_ARG; }
 }
