@@ -354,6 +354,8 @@ void gb_map_params_default(gb_map_params* p);
  * mapping j of read r in output order (minimizer_mapper.cpp:1087-1206; map_paired: pair j of the pair, :2505-2598) —
  * j = 0 the primary, which alone carries the MAPQ; j >= 1 secondaries (GB_ALN_SECONDARY), or GB_ALN_ABSENT when the
  * read has fewer mappings.  With max_multimaps = 1 (the default) that is one record per read.
+ * Limits of the mapping entry points: reads up to 512 bp; node ids below 2^22 (the seeding kernels pack id and offset into
+ * 32 bits; GB_ERR_CAPACITY for a larger index — the stage seams gb_extend_batch etc. are not affected).
  * mappings / edits are DENSE pools of the given capacities
  * (gb_alignment.mapping_off / edit_off index into them); the elements used are returned
  * through n_mappings_used / n_edits_used (may be NULL).  GB_ERR_CAPACITY if a pool is too
