@@ -2,8 +2,10 @@
 
 Giraffe reads are independent once the fragment-length distribution is fixed
 (giraffe_main.cpp:2416-2459), so rank r maps pairs [lo, hi) of the batch with its own replica of
-the index; the only exchange is the gather of the fixed-width 32-byte alignment headers on rank 0
-for emission."""
+the index; the only exchange is the gather of every rank's whole records (headers, mappings, edits:
+gather_records) on rank 0 for emission, plus two doubles when the distribution is
+learned (share_fragment_distribution).  With max_multimaps > 1 the header array simply holds
+n * max_multimaps records per rank (absent ranks included; the emitters skip them)."""
 from __future__ import annotations
 
 
@@ -16,7 +18,8 @@ def shard_pairs(n_pairs: int, rank: int, world: int):
 
 
 def gather_headers(headers, rank: int, world: int, dst: int = 0):
-    """Gather per-rank [n_i, 32] uint8 header tensors on `dst`, padded to the largest shard.
+    """Headers only (round 1's gather, kept for callers that need just scores / MAPQs; gather_records moves whole records):
+    gather per-rank [n_i, 32] uint8 header tensors on `dst`, padded to the largest shard.
     Returns the list of per-rank tensors (trimmed) on dst, None elsewhere."""
     import torch
     import torch.distributed as dist
