@@ -133,7 +133,8 @@ typedef struct gb_flat_index {
  * ---------------------------------------------------------------------------------- */
 typedef struct gb_host_index gb_host_index;
 
-/* node i (1-based id) has forward sequence node_seq[node_off[i-1] .. node_off[i]).
+/* node i (1-based id) has forward sequence node_seq[node_off[i-1] .. node_off[i]); an EMPTY sequence marks an id the graph
+ * does not use (ids need not start at 1: outputs always carry the caller's ids) — no path or record may name it.
  * path p is path_nodes[path_off[p] .. path_off[p+1]) in GBWT node encoding.
  * dist == NULL: the builder derives the distance payload and the site tables itself from the graph the paths span
  * (chains of cut nodes and sites, see gb_dist_payload) — any graph whose haplotypes walk forward through a DAG;

@@ -542,3 +542,37 @@ def test_damaged_gbwt_records_are_refused():
     attempt(lambda w2, r2: w2.__setitem__(off + 3, 1 << 30))                                      # offset outside the successor's record
     attempt(lambda w2, r2: w2.__setitem__(off + 2 + 2 * n_edges, (1 << 10) | 900))                # run rank outside the edge list
     ref.close()
+
+
+def test_unused_low_node_ids_are_allowed():
+    """A graph whose node ids do not start at 1 (a GBWT with an alphabet offset: ids below the first stay unused): the same
+    graph with every id shifted by 100 builds (from paths and from its flat GBWT), keeps the original ids in its outputs, and
+    the oracle maps reads to the shifted nodes exactly as to the unshifted ones; a path or record naming an unused id is refused."""
+    shift = 100
+    g = synth.make_variant_graph(length=20000, n_snp=40, n_ins=5, n_del=5, n_haps=4, seed=12)
+    ref = g.build_index()
+    seqs = [""] * shift + list(g.node_seqs)
+    paths = [[v + 2 * shift for v in p] for p in g.paths]
+    dist = np.zeros(len(seqs) + 1, dtype=capi.dist_dt); dist["allele"] = 0xFFFF
+    dist[shift + 1:] = np.asarray(g.dist)[1:]
+    shifted = capi.HostIndex(seqs, paths, dist)
+    assert int(shifted.view.n_nodes) == int(ref.view.n_nodes) + 2 * shift
+    assert (shifted.array("nodes")["len"][: 2 * shift + 2] == 0).all()
+    assert shifted.array("nodes")["len"][2 * shift + 2:].tobytes() == ref.array("nodes")["len"][2:].tobytes()
+    again = capi.HostIndex.from_gbwt(seqs, len(paths), shifted.array("gbwt"), shifted.array("nodes")["rec_off"], dist)
+    for name in ("nodes", "seq", "gbwt", "table", "hits"):
+        assert again.array(name).tobytes() == shifted.array(name).tobytes(), name
+    rs = synth.simulate_reads(g, 300, length=150, sub_rate=0.01, seed=4)
+    a = H.oracle_map(ref, rs.reads, rs.quals, threads=4)
+    b = H.oracle_map(shifted, rs.reads, rs.quals, threads=4)
+    assert a[0]["score"].tobytes() == b[0]["score"].tobytes() and a[0]["mapq"].tobytes() == b[0]["mapq"].tobytes()
+    for i in range(rs.n):
+        pa, pb = H.decode_alignment(a[0][i], a[1], a[2])[2], H.decode_alignment(b[0][i], b[1], b[2])[2]
+        assert [(n + 2 * shift, o, e) for n, o, e in pa] == pb
+    with pytest.raises(capi.GbError):
+        capi.HostIndex(seqs, [[2 * 5] + paths[0]], dist)                                     # a path through an unused id
+    bad_off = shifted.array("nodes")["rec_off"].copy(); bad_off[2 * 7] = bad_off[2 * shift + 2]
+    with pytest.raises(capi.GbError):
+        capi.HostIndex.from_gbwt(seqs, len(paths), shifted.array("gbwt"), bad_off, dist)      # a record on an unused id
+    for x in (ref, shifted, again):
+        x.close()

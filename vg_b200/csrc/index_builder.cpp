@@ -296,7 +296,8 @@ static int index_build_impl(uint32_t n_node_ids, const uint8_t* node_seq, const 
     for (uint32_t id = 1; id <= n_node_ids; id++) {
         uint64_t b = node_off[id - 1], e = node_off[id];
         uint32_t len = (uint32_t)(e - b);
-        if (len == 0 || len > 1024) { delete ix; return GB_ERR_FORMAT; }
+        if (len > 1024) { delete ix; return GB_ERR_FORMAT; }
+        if (len == 0) continue;                       // an id the graph does not use (a GBZ whose ids do not start at 1): no sequence, and no path or record may name it
         uint32_t vf = 2 * id, vr = 2 * id + 1;
         ix->nodes[vf].seq_off = (uint32_t)ix->seq.size(); ix->nodes[vf].len = len;
         for (uint64_t i = b; i < e; i++) ix->seq.push_back(node_seq[i]);
@@ -328,7 +329,7 @@ static int index_build_impl(uint32_t n_node_ids, const uint8_t* node_seq, const 
         } else {
             std::vector<std::vector<uint32_t>> fwd(n_paths);
             for (uint32_t p = 0; p < n_paths; p++) fwd[p].assign(path_nodes + path_off[p], path_nodes + path_off[p + 1]);
-            for (const auto& f : fwd) for (uint32_t v : f) if (v < 2 || v >= ix->n_nodes) { delete ix; return GB_ERR_FORMAT; }
+            for (const auto& f : fwd) for (uint32_t v : f) if (v < 2 || v >= ix->n_nodes || ix->nodes[v].len == 0) { delete ix; return GB_ERR_FORMAT; }
             forward = forward_graph_of_paths(n_node_ids, fwd, used, edges);
         }
         if (!forward || !derive_distance_payload(n_node_ids, len_by_id, used, std::move(edges), ix->dist, ix->slots, ix->site_dist)) {
@@ -349,7 +350,7 @@ static int index_build_impl(uint32_t n_node_ids, const uint8_t* node_seq, const 
             f.assign(path_nodes + b, path_nodes + e);
             r.resize(e - b);
             for (uint64_t i = 0; i < e - b; i++) r[i] = path_nodes[e - 1 - i] ^ 1u;
-            for (uint32_t v : f) if (v < 2 || v >= ix->n_nodes) { delete ix; return GB_ERR_FORMAT; }
+            for (uint32_t v : f) if (v < 2 || v >= ix->n_nodes || ix->nodes[v].len == 0) { delete ix; return GB_ERR_FORMAT; }
         }
         std::vector<uint32_t> vrank; std::vector<uint64_t> seq_start;
         gbwt_visit_order(seqs, vrank, seq_start);
@@ -426,7 +427,7 @@ static int index_build_impl(uint32_t n_node_ids, const uint8_t* node_seq, const 
         for (uint32_t v = 2; v < ix->n_nodes; v++) {
             const GbwtRecordIn& rc = (*records)[v];
             if (rec_size[v] == 0) { ix->nodes[v].rec_off = 0; ix->nodes[v].size = 0; continue; }
-            if (rec_size[v] > 0xfffffff0ull || rc.edges.empty() || rc.edges.size() >= 1024) { delete ix; return GB_ERR_FORMAT; }
+            if (rec_size[v] > 0xfffffff0ull || rc.edges.empty() || rc.edges.size() >= 1024 || ix->nodes[v].len == 0) { delete ix; return GB_ERR_FORMAT; }
             ix->nodes[v].size = (uint32_t)rec_size[v];
             // every visit leaves through an edge; the offsets must lie inside the successor's record
             std::vector<uint64_t> through(rc.edges.size(), 0);
