@@ -170,8 +170,8 @@ int gb_index_from_gbz(const char* path, uint32_t k, uint32_t w, gb_host_index** 
  * oversized zipcode the table points at.  The distance payload is still the library's own chain model derived from the
  * graph (vg's zipcodes are a different encoding of the same coordinates: tests/test_gbz.py pins the prefix sums); `.dist`
  * is not needed.  Limit, stated rather than guessed: a .min whose keys have several occurrences stores them after the table
- * in a layout the reference's only .min fixture (test/primers/y.min) does not show — such a file is GB_ERR_FORMAT and the
- * caller uses gb_index_from_gbz. */
+ * in a layout the reference's only .min fixture (test/primers/y.min) does not show — from such a file only k and w are
+ * taken, and the minimizers are found on the graph by window enumeration (the same set: that is what a .min holds). */
 int gb_index_from_gbz_min(const char* gbz_path, const char* min_path, const char* zipcodes_path, gb_host_index** out);
 /* gb_index_build with the minimizer hits given by the caller: hit i = (keys[i], positions[i]), position =
  * id << 11 | is_reverse << 10 | offset of the first base of the canonical k-mer on that oriented node (gbwtgraph's

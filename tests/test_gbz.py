@@ -440,7 +440,6 @@ def test_min_files_that_do_not_fit_are_refused(tmp_path):
         "syncmers.min": lambda b: struct.pack_into("<Q", b, 64, W(8) | 0x100),
         "key128.min": lambda b: struct.pack_into("<Q", b, 64, 128),
         "otherflag.min": lambda b: struct.pack_into("<Q", b, 64, W(8) | 0x400),
-        "multi.min": lambda b: struct.pack_into("<Q", b, 48, W(6) + 1),                       # values != keys: a key with two occurrences
         "pointer.min": lambda b: struct.pack_into("<Q", b, 8 * (10 + 4 * first), W(10 + 4 * first) | (1 << 63)),
         "otherkmer.min": lambda b: struct.pack_into("<Q", b, 8 * (10 + 4 * first), W(10 + 4 * first) ^ (3 << 60)),   # first base of the key changed
         "offgraph.min": lambda b: struct.pack_into("<Q", b, 8 * (11 + 4 * first), (5000 << 11)),
@@ -458,6 +457,13 @@ def test_min_files_that_do_not_fit_are_refused(tmp_path):
         with pytest.raises(capi.GbError):
             capi.HostIndex.from_gbz_min(GBZ, d / "y.min", tmp_path / name)
     capi.HostIndex.from_gbz_min(GBZ, d / "y.min").close()                                     # the zipcode file is optional
+    # a .min that says it holds keys with several occurrences: its table is not read, k and w are, the minimizers are re-derived
+    multi = variant("multi.min", lambda b: struct.pack_into("<Q", b, 48, W(6) + 1))
+    a = capi.HostIndex.from_gbz_min(GBZ, multi, d / "y.zipcodes"); b = capi.HostIndex.from_gbz(GBZ, k=31, w=50)
+    assert (a.k, a.w) == (31, 50)
+    for name in ("nodes", "gbwt", "dist", "table", "hits"):
+        assert a.array(name).tobytes() == b.array(name).tobytes(), name
+    a.close(); b.close()
 
 
 def test_build_with_hits_equals_the_haplotype_scan():

@@ -125,9 +125,9 @@ int fail(const char* why) { if (getenv("GB_GBZ_DEBUG")) fprintf(stderr, "gbz rea
 //   word 9         capacity, then capacity 32-byte cells: key, position, payload[2]; the empty key is 2^63 - 1
 //   after the table one 64-bit count of multi-occurrence values: 0 in that file.
 // Keys with SEVERAL occurrences (key bit 63 set; values == unique is false) are laid out after the table in a way that
-// file cannot show, so such a file is refused (GB_ERR_FORMAT) rather than guessed at: the caller then falls back to
-// gb_index_from_gbz, which finds the same minimizers by scanning the haplotypes.
-struct MinFile { uint32_t k = 0, w = 0; std::vector<uint64_t> keys, pos, payload0, payload1; };
+// file cannot show, so the table of such a file is not read rather than guessed at: k and w are taken from its header and
+// the minimizers are found on the graph by window enumeration — the same set, since a .min is exactly that.
+struct MinFile { uint32_t k = 0, w = 0; bool multi = false; std::vector<uint64_t> keys, pos, payload0, payload1; };
 static int read_min_file(const char* path, MinFile& m) {
     FILE* f = fopen(path, "rb");
     if (!f) return fail("open .min");
@@ -146,7 +146,9 @@ static int read_min_file(const char* path, MinFile& m) {
     if ((flags & 0x100u) != 0) return fail(".min holds syncmers, not minimizers");
     if ((flags & ~0x1FFull) != 0) return fail(".min carries flags this reader does not know");
     if (capacity == 0 || (capacity & (capacity - 1)) != 0 || capacity > (W.size() - 10) / 4) return fail(".min capacity");
-    if (keys > capacity || values != keys || unique != keys) return fail(".min has keys with several occurrences (layout not covered)");
+    m.k = (uint32_t)k; m.w = (uint32_t)w;
+    if (keys > capacity) return fail(".min key count");
+    if (values != keys || unique != keys) { m.multi = true; return GB_OK; }      // several occurrences per key: only k and w are taken from this file
     if (W.size() != 10 + 4 * capacity + 1 || W.back() != 0) return fail(".min tail");
     m.k = (uint32_t)k; m.w = (uint32_t)w;
     for (uint64_t c = 0; c < capacity; c++) {
@@ -290,6 +292,13 @@ extern "C" int gb_index_from_gbz_min(const char* gbz_path, const char* min_path,
         MinFile m;
         int rc = read_min_file(min_path, m);
         if (rc != GB_OK) return rc;
+        if (m.multi) {
+            // keys with several occurrences: their layout after the table is not known to this reader (see above), so the
+            // table is not read — k and w come from the file, the minimizers are found on the graph (the same set: a .min IS
+            // the minimizers of the haplotypes), the zipcode file is still checked for being one
+            if (zipcodes_path) { uint64_t n = 0; rc = count_zipcodes(zipcodes_path, n); if (rc != GB_OK) return rc; }
+            return index_from_gbz_impl(gbz_path, m.k, m.w, out, nullptr);
+        }
         uint64_t oversized = 0;
         for (size_t i = 0; i < m.keys.size(); i++) if ((m.payload0[i] & 0xFF) == 0) oversized = std::max<uint64_t>(oversized, m.payload1[i] + 1);
         if (zipcodes_path) {
