@@ -527,36 +527,35 @@ static int index_build_impl(uint32_t n_node_ids, const uint8_t* node_seq, const 
         std::string win; std::vector<uint32_t> wnode, woff;
         struct Frame { uint32_t node; int64_t lo, hi; size_t restore; };
         std::vector<Frame> stack; std::vector<std::array<int64_t, 3>> next;
+        // Per start node: every haplotype-consistent continuation of W - 1 bases behind it.  The string node + continuation holds
+        // exactly the windows that start on the node along that walk; its minimizers are computed once with the rolling hash.
+        auto process = [&](size_t len) {
+            mins.clear();
+            gbmin::minimizers((const uint8_t*)win.data(), len, k, w, mins, nullptr);
+            for (const auto& m : mins) {
+                uint32_t v = wnode[m.offset], o = woff[m.offset];
+                if (m.is_reverse) { o = ix->nodes[v].len - 1 - o; v ^= 1u; }
+                kps.push_back(KP{m.key, ((uint64_t)v << 10) | o});
+            }
+        };
         for (uint32_t v0 = 2; v0 < ix->n_nodes; v0++) {
             if (ix->nodes[v0].size == 0 || (forward_only && (v0 & 1u))) continue;
-            for (uint32_t s0 = 0; s0 < ix->nodes[v0].len; s0++) {
-                stack.clear();
-                stack.push_back(Frame{v0, 0, (int64_t)ix->nodes[v0].size - 1, 0});
-                win.clear(); wnode.clear(); woff.clear();
-                bool first = true;
-                while (!stack.empty()) {
-                    const Frame f = stack.back(); stack.pop_back();
-                    win.resize(f.restore); wnode.resize(f.restore); woff.resize(f.restore);
-                    const gb_node_rec& nr = ix->nodes[f.node];
-                    for (uint32_t o = first ? s0 : 0; o < nr.len && win.size() < W; o++) { win.push_back((char)ix->seq[nr.seq_off + o]); wnode.push_back(f.node); woff.push_back(o); }
-                    first = false;
-                    if (win.size() == W) {
-                        mins.clear();
-                        gbmin::minimizers((const uint8_t*)win.data(), W, k, w, mins, nullptr);
-                        for (const auto& m : mins) {
-                            uint32_t v = wnode[m.offset], o = woff[m.offset];
-                            if (m.is_reverse) { o = ix->nodes[v].len - 1 - o; v ^= 1u; }
-                            kps.push_back(KP{m.key, ((uint64_t)v << 10) | o});
-                        }
-                        continue;
-                    }
-                    follow(f.node, f.lo, f.hi, next);
-                    for (size_t x = next.size(); x-- > 0;) stack.push_back(Frame{(uint32_t)next[x][0], next[x][1], next[x][2], win.size()});
-                }
-                if (kps.size() > (1ull << 26)) {      // keep the pair list bounded while it is full of duplicates
-                    std::sort(kps.begin(), kps.end(), [](const KP& a, const KP& b) { return a.key != b.key ? a.key < b.key : a.pos < b.pos; });
-                    kps.erase(std::unique(kps.begin(), kps.end(), [](const KP& a, const KP& b) { return a.key == b.key && a.pos == b.pos; }), kps.end());
-                }
+            const size_t need = (size_t)ix->nodes[v0].len + W - 1;
+            stack.clear();
+            stack.push_back(Frame{v0, 0, (int64_t)ix->nodes[v0].size - 1, 0});
+            while (!stack.empty()) {
+                const Frame f = stack.back(); stack.pop_back();
+                win.resize(f.restore); wnode.resize(f.restore); woff.resize(f.restore);
+                const gb_node_rec& nr = ix->nodes[f.node];
+                for (uint32_t o = 0; o < nr.len && win.size() < need; o++) { win.push_back((char)ix->seq[nr.seq_off + o]); wnode.push_back(f.node); woff.push_back(o); }
+                if (win.size() == need) { process(need); continue; }
+                follow(f.node, f.lo, f.hi, next);
+                if (next.empty()) { if (win.size() >= W) process(win.size()); continue; }          // the haplotypes end here
+                for (size_t x = next.size(); x-- > 0;) stack.push_back(Frame{(uint32_t)next[x][0], next[x][1], next[x][2], win.size()});
+            }
+            if (kps.size() > (1ull << 26)) {      // keep the pair list bounded while it is full of duplicates
+                std::sort(kps.begin(), kps.end(), [](const KP& a, const KP& b) { return a.key != b.key ? a.key < b.key : a.pos < b.pos; });
+                kps.erase(std::unique(kps.begin(), kps.end(), [](const KP& a, const KP& b) { return a.key == b.key && a.pos == b.pos; }), kps.end());
             }
         }
     }
